@@ -1,0 +1,153 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+The reference is imported as-is (oracle/ref_import.py); Exp(1) draws are injected through a
+patched Tensor.exponential_, so the recorded outputs are what the reference's own code
+computes on inputs we can replay through the CUDA path and the numpy oracle.
+
+Fixtures (all fp32 CPU; sizes kept small so the files stay a few hundred KB):
+  sampler_<indicator>.npz   Poisson(log_rate, temp, indicator, n_exp).rsample() and its autograd
+                            gradient for three temperatures            (base/distributions.py:55-81)
+  hard_counts.npz           (cumsum(Exponential(rate).rsample((n,)), 0) <= 1).sum(0)
+                                                                       (base/distributions.py:60-63)
+  vae_step_<tag>.npz        PoissonVAE lin|lin forward, loss, backward, one Adamax step
+                            (main/vae.py:384-450, main/train_vae.py:346-362, base/adamax.py:34-100)
+  scalars.npz               compute_n_exp / update_n table, softclamps, indicator grids, schedules
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from oracle import pvae_oracle as po
+from oracle import ref_import
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _draws(seed, offset, shape, n_exp):
+    idx = np.arange(int(np.prod(shape)), dtype=np.uint32).reshape(shape)
+    u = po.draw_uniforms(seed, offset, idx, n_exp)
+    return u, po.exponential_from_uniform(u)
+
+
+def gen_sampler(ref):
+    rng = np.random.default_rng(20241)
+    B, K, n_exp = 4, 48, 32
+    for kind in po.INDICATORS:
+        rec = {}
+        log_rate = np.minimum(rng.normal(-1.0, 2.0, size=(B, K)), 5.0).astype(np.float32)
+        w = rng.normal(size=(B, K)).astype(np.float32)
+        seed, offset = 1234 + len(kind), 7
+        u, e = _draws(seed, offset, (B, K), n_exp)
+        rec.update(log_rate=log_rate, w=w, u=u, e=e, seed=seed, offset=offset, n_exp=n_exp)
+        for temp in (1.0, 0.3, 0.05):
+            lr = torch.tensor(log_rate, requires_grad=True)
+            with ref_import.inject_exponentials([e]):
+                dist = ref.dist.Poisson(log_rate=lr, temp=temp, indicator_approx=kind, n_exp=n_exp)
+                z = dist.rsample()
+            (g,) = torch.autograd.grad((z * torch.tensor(w)).sum(), lr)
+            tag = f"t{temp:g}"
+            rec[f"z_{tag}"] = z.detach().numpy()
+            rec[f"g_{tag}"] = g.numpy()
+            rec["rate"] = dist.rate.detach().numpy()
+        np.savez_compressed(os.path.join(OUT, f"sampler_{kind}.npz"), **rec)
+
+
+def gen_hard(ref):
+    rng = np.random.default_rng(77)
+    B, K, n_exp = 8, 64, 48
+    log_rate = np.minimum(rng.normal(0.0, 2.0, size=(B, K)), 5.0).astype(np.float32)
+    u, e = _draws(99, 3, (B, K), n_exp)
+    with ref_import.inject_exponentials([e]):
+        dist = ref.dist.Poisson(log_rate=torch.tensor(log_rate), temp=1.0, n_exp=n_exp)
+        x = dist._exp.rsample((dist.n_exp,))  # step (1)
+        times = torch.cumsum(x, dim=0)  # step (2)
+    counts = (times <= 1).sum(0).float().numpy()
+    np.savez_compressed(os.path.join(OUT, "hard_counts.npz"), log_rate=log_rate, u=u, e=e, seed=99, offset=3,
+                        n_exp=n_exp, rate=dist.rate.numpy(), counts=counts, times=times.numpy())
+
+
+def gen_vae(ref):
+    cases = [
+        dict(tag="k64_t1_b1", K=64, B=16, n_exp=20, temp=1.0, beta=1.0, exc_only=False, seed=3),
+        dict(tag="k128_t01_b25", K=128, B=12, n_exp=24, temp=0.1, beta=2.5, exc_only=False, seed=4),
+        dict(tag="k64_exc", K=64, B=8, n_exp=16, temp=0.5, beta=1.0, exc_only=True, seed=5),
+    ]
+    for c in cases:
+        cfg_vae, cfg_tr = ref.cfg.default_configs("vH16", "poisson", "lin|lin")
+        cfg_vae.update(n_latents=c["K"], exc_only=c["exc_only"], seed=c["seed"])
+        cfg = ref.cfg.ConfigPoisVAE(save=False, **cfg_vae)
+        model = ref.vae.PoissonVAE(cfg)
+        model.n_exp.fill_(c["n_exp"])
+        model.update_t(c["temp"])
+        # make rates non-trivial: shift the prior up so several arrivals land in [0, 1]
+        with torch.no_grad():
+            model.log_rate.add_(4.0)
+        rng = np.random.default_rng(1000 + c["seed"])  # data seed != cfg.seed
+        x = rng.standard_normal((c["B"], 1, 16, 16)).astype(np.float32)
+        x = (x - x.mean((1, 2, 3), keepdims=True)) / x.std((1, 2, 3), keepdims=True)
+        u, e = _draws(2024, 11, (c["B"], c["K"]), c["n_exp"])
+        p0 = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
+        optim = ref.adamax.Adamax(model.parameters(), lr=cfg_tr["lr"])
+        optim.zero_grad(set_to_none=True)
+        xt = torch.tensor(x)
+        with ref_import.inject_exponentials([e]):
+            dist, log_dr, z, y = model(xt)  # main/vae.py:384-391
+        recon = model.loss_recon(y, xt)  # main/vae.py:68-72
+        kl = model.loss_kl(log_dr)  # main/vae.py:446-450
+        loss = torch.mean(recon + c["beta"] * torch.sum(kl, dim=1))  # main/train_vae.py:347-351
+        loss.backward()
+        grads = {n: p.grad.detach().clone().numpy() for n, p in model.named_parameters()}
+        optim.step()
+        p1 = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
+        rec = dict(x=x, u=u, e=e, seed=2024, offset=11, n_exp=c["n_exp"], temp=c["temp"], beta=c["beta"],
+                   exc_only=int(c["exc_only"]), lr=cfg_tr["lr"],
+                   log_dr=log_dr.detach().numpy(), rate=dist.rate.detach().numpy(), z=z.detach().numpy(),
+                   y=y.detach().numpy(), recon=recon.detach().numpy(), kl=kl.detach().numpy(),
+                   loss=loss.detach().numpy())
+        for k, v in p0.items():
+            rec["p0_" + k] = v
+        for k, v in p1.items():
+            rec["p1_" + k] = v
+        for k, v in grads.items():
+            rec["g_" + k] = v
+        np.savez_compressed(os.path.join(OUT, f"vae_step_{c['tag']}.npz"), **rec)
+
+
+def gen_scalars(ref):
+    rec = {}
+    rates = np.array([0.05, 0.1, 0.43, 1, 5, 20, 50, 100, 148.4, 200], dtype=np.float64)
+    rec["n_exp_rates"] = rates
+    rec["n_exp_p1e-5"] = np.array([ref.dist.compute_n_exp(float(r), 1e-5) for r in rates])
+    rec["n_exp_p1e-3"] = np.array([ref.dist.compute_n_exp(float(r), 1e-3) for r in rates])
+    x = torch.linspace(-40, 40, 801)
+    rec["clamp_x"] = x.numpy()
+    rec["softclamp_upper_10"] = ref.dist.softclamp_upper(x, 10.0).numpy()
+    rec["softclamp_upper_5"] = ref.dist.softclamp_upper(x, 5.0).numpy()
+    rec["softclamp_10_0"] = ref.dist.softclamp(x, 10.0, 0).numpy()
+    l = torch.linspace(-3, 3, 601)
+    rec["ind_l"] = l.numpy()
+    for kind, fn in ref.dist._INDICATOR_FNS.items():
+        rec[f"ind_{kind}"] = fn(l).numpy()
+    rec["temp_lin_1000"] = ref.utils.temp_anneal_linear(1000, 1.0, 0.05, 0.5)
+    rec["beta_lin_1000"] = ref.utils.beta_anneal_linear(1000, 2.5, 0.5, 0.0, 1e-4)
+    np.savez_compressed(os.path.join(OUT, "scalars.npz"), **rec)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)
+    ref = ref_import.load()
+    gen_scalars(ref)
+    gen_sampler(ref)
+    gen_hard(ref)
+    gen_vae(ref)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
