@@ -1,0 +1,112 @@
+/* pvae_b200.h - C ABI of the B200-native P-VAE training hot path.
+ *
+ * The reference (hadivafaii/PoissonVAE) is pure Python/PyTorch and has no FFI; the surface this
+ * library replaces is a set of Python methods.  Each entry point below names the reference code it
+ * replaces (file:line relative to the reference checkout).  INTEGRATION.md shows the ctypes binding
+ * a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer (fp32 unless stated) owned by the caller; the library never
+ *    allocates or frees caller-visible memory and never synchronises the device;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it (graph-capturable);
+ *  - matrices are row-major and contiguous: (B, K) means element (b, k) at [b * K + k];
+ *  - return value: 0 on success, a negative PVAE_ERR_* otherwise; pvae_last_error() returns a
+ *    thread-local message for the last failure.
+ *
+ * RNG contract (tests/test_sampler_gpu.py pins it against oracle/pvae_oracle.py)
+ *  Philox4x32-10, key = (lo32(seed) ^ 0x50564145, hi32(seed)),
+ *  counter = (latent_quad, event, lo32(off), hi32(off)) where off = offset + (*offset_dev if given),
+ *  latent_quad = ((row_offset + b) * K + k) >> 2 and word ((row_offset + b) * K + k) & 3 of the
+ *  block is the draw for event `event` of latent (b, k):  u = ((word >> 9) + 0.5) * 2^-23,
+ *  e = -logf(u).  The stream depends on the GLOBAL sample index only, so 1/2/4/8-GPU runs that
+ *  shard the batch draw identical numbers.  Callers advance `offset` by 1 per sampling call.
+ */
+#ifndef PVAE_B200_H_
+#define PVAE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVAE_OK 0
+#define PVAE_ERR_INVALID (-1)     /* bad argument (shape, null pointer, unknown indicator, temp < 0) */
+#define PVAE_ERR_UNSUPPORTED (-2) /* valid request this build does not cover */
+#define PVAE_ERR_CUDA (-3)        /* a CUDA call failed; see pvae_last_error() */
+
+/* base/distributions.py:294-300 */
+#define PVAE_IND_SIGMOID 0
+#define PVAE_IND_COSINE 1
+#define PVAE_IND_LINEAR 2
+#define PVAE_IND_CUBIC 3
+#define PVAE_IND_QUINTIC 4
+
+/* exit_logit values.  The chain of a latent stops once every later term is below the threshold:
+ * PVAE_EXIT_LOSSLESS stops only where the reference's fp32 term is exactly 0 (sigmoid: logit <
+ * -88.73, finite-support indicators: logit <= -1), PVAE_EXIT_NEVER runs all n_exp events. */
+#define PVAE_EXIT_LOSSLESS 0.0f
+#define PVAE_EXIT_NEVER (-1.0f)
+
+int pvae_version(void);
+const char* pvae_last_error(void);
+
+/* Rows of the (P, K) partial-sum workspaces the backward entry points need for batch size B. */
+int64_t pvae_num_partials(int64_t B);
+
+/* ---- fused encoder-output -> relaxed spike counts (+ KL) ------------------------------------
+ * Replaces, for one batch: PoissonVAE.infer main/vae.py:393-415 (softclamp_upper x2 or softclamp,
+ * base/distributions.py:233-242), Poisson.__init__ rate = exp(.)+eps base/distributions.py:24-25,
+ * Poisson.rsample base/distributions.py:55-81 and PoissonVAE.loss_kl main/vae.py:446-450.
+ *   h (B,K) = fc_enc(x) WITHOUT bias; b_enc (K) optional bias; log_r (K) prior log-rates.
+ *   z (B,K) out.  Optional outputs (NULL to skip): log_dr (B,K), rate (B,K), kl (B,K),
+ *   kl_rowsum (B) = kl.sum(1), rate_max (1 float, must be pre-set by the caller, updated with max).
+ *   temp > 0: relaxed counts with `indicator`; temp == 0: hard counts #{t_n <= 1} (the reference
+ *   draws torch.poisson there, base/distributions.py:56-57,83-85 - same law, different stream). */
+int pvae_sampler_fwd(const float* h, const float* log_r, const float* b_enc, float* z, float* log_dr,
+                     float* rate, float* kl, float* kl_rowsum, float* rate_max, int64_t B, int64_t K,
+                     int64_t row_offset, int n_exp, float temp, int indicator, int exc_only,
+                     float exit_logit, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                     void* stream);
+
+/* ---- backward of the above, recomputing the chain from the Philox counters ------------------
+ * Replaces autograd through base/distributions.py:55-81 and main/vae.py:393-415,446-450
+ * (closed form: SURVEY.md section 8 row a13).  Must be called with the same h/log_r/b_enc,
+ * shape, n_exp, temp, indicator, exc_only, exit_logit, seed and offset as the forward.
+ *   g_z (B,K) upstream gradient wrt z; g_log_dr (B,K) optional upstream gradient wrt the returned
+ *   log_dr; kl_scale = beta / B_global fuses the gradient of beta * mean_b(sum_k kl) (0 to skip).
+ *   g_h (B,K) out; g_log_r (K) and g_b_enc (K, optional) out - overwritten, or added to if
+ *   accumulate != 0; partial_ws: workspace of 2 * pvae_num_partials(B) * K floats. */
+int pvae_sampler_bwd(const float* h, const float* log_r, const float* b_enc, const float* g_z,
+                     const float* g_log_dr, float kl_scale, float* g_h, float* g_log_r, float* g_b_enc,
+                     float* partial_ws, int accumulate, int64_t B, int64_t K, int64_t row_offset,
+                     int n_exp, float temp, int indicator, int exc_only, float exit_logit,
+                     uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream);
+
+/* ---- bare Poisson(log_rate).rsample() / hard counts -----------------------------------------
+ * Replaces Poisson.__init__ + rsample base/distributions.py:6-30,55-81 for a caller-supplied
+ * log_rate of n_rows x K (PoissonVAE.sample main/vae.py:431-444 and standalone use).
+ * clamp < 0 means "no clamp" (reference clamp=None), otherwise softclamp_upper(log_rate, clamp). */
+int pvae_rsample_fwd(const float* log_rate, float* z, float* rate, int64_t B, int64_t K, int64_t row_offset,
+                     int n_exp, float temp, int indicator, float clamp, float exit_logit, uint64_t seed,
+                     uint64_t offset, const uint64_t* offset_dev, void* stream);
+int pvae_rsample_bwd(const float* log_rate, const float* g_z, float* g_log_rate, int64_t B, int64_t K,
+                     int64_t row_offset, int n_exp, float temp, int indicator, float clamp, float exit_logit,
+                     uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream);
+
+/* ---- PoissonVAE.loss_kl main/vae.py:446-450 as a standalone elementwise op -------------------
+ * kl (B,K) = exp(log_r) * (1 + exp(log_dr) * (log_dr - 1)); backward gives g_log_dr (B,K) and
+ * g_log_r (K) from g_kl (B,K). */
+int pvae_kl_fwd(const float* log_dr, const float* log_r, float* kl, int64_t B, int64_t K, void* stream);
+int pvae_kl_bwd(const float* log_dr, const float* log_r, const float* g_kl, float* g_log_dr, float* g_log_r,
+                float* partial_ws, int accumulate, int64_t B, int64_t K, void* stream);
+
+/* ---- parity harness only: dump the uniforms / exponentials the kernels consume ---------------
+ * U, E: (n_exp, B, K).  Either may be NULL. */
+int pvae_debug_draws(float* U, float* E, int64_t B, int64_t K, int64_t row_offset, int n_exp, uint64_t seed,
+                     uint64_t offset, const uint64_t* offset_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVAE_B200_H_ */

@@ -40,7 +40,7 @@ def gen_sampler(ref):
         rec = {}
         log_rate = np.minimum(rng.normal(-1.0, 2.0, size=(B, K)), 5.0).astype(np.float32)
         w = rng.normal(size=(B, K)).astype(np.float32)
-        seed, offset = 1234 + len(kind), 7
+        seed, offset = 1234 + len(kind), 8
         u, e = _draws(seed, offset, (B, K), n_exp)
         rec.update(log_rate=log_rate, w=w, u=u, e=e, seed=seed, offset=offset, n_exp=n_exp)
         for temp in (1.0, 0.3, 0.05):
@@ -60,13 +60,13 @@ def gen_hard(ref):
     rng = np.random.default_rng(77)
     B, K, n_exp = 8, 64, 48
     log_rate = np.minimum(rng.normal(0.0, 2.0, size=(B, K)), 5.0).astype(np.float32)
-    u, e = _draws(99, 3, (B, K), n_exp)
+    u, e = _draws(99, 4, (B, K), n_exp)
     with ref_import.inject_exponentials([e]):
         dist = ref.dist.Poisson(log_rate=torch.tensor(log_rate), temp=1.0, n_exp=n_exp)
         x = dist._exp.rsample((dist.n_exp,))  # step (1)
         times = torch.cumsum(x, dim=0)  # step (2)
     counts = (times <= 1).sum(0).float().numpy()
-    np.savez_compressed(os.path.join(OUT, "hard_counts.npz"), log_rate=log_rate, u=u, e=e, seed=99, offset=3,
+    np.savez_compressed(os.path.join(OUT, "hard_counts.npz"), log_rate=log_rate, u=u, e=e, seed=99, offset=4,
                         n_exp=n_exp, rate=dist.rate.numpy(), counts=counts, times=times.numpy())
 
 
@@ -83,13 +83,14 @@ def gen_vae(ref):
         model = ref.vae.PoissonVAE(cfg)
         model.n_exp.fill_(c["n_exp"])
         model.update_t(c["temp"])
-        # make rates non-trivial: shift the prior up so several arrivals land in [0, 1]
-        with torch.no_grad():
-            model.log_rate.add_(4.0)
         rng = np.random.default_rng(1000 + c["seed"])  # data seed != cfg.seed
         x = rng.standard_normal((c["B"], 1, 16, 16)).astype(np.float32)
         x = (x - x.mean((1, 2, 3), keepdims=True)) / x.std((1, 2, 3), keepdims=True)
-        u, e = _draws(2024, 11, (c["B"], c["K"]), c["n_exp"])
+        u, e = _draws(2024, 12, (c["B"], c["K"]), c["n_exp"])
+        p_init = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
+        # make rates non-trivial: shift the prior up so several arrivals land in [0, 1]
+        with torch.no_grad():
+            model.log_rate.add_(4.0)
         p0 = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
         optim = ref.adamax.Adamax(model.parameters(), lr=cfg_tr["lr"])
         optim.zero_grad(set_to_none=True)
@@ -103,11 +104,14 @@ def gen_vae(ref):
         grads = {n: p.grad.detach().clone().numpy() for n, p in model.named_parameters()}
         optim.step()
         p1 = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
-        rec = dict(x=x, u=u, e=e, seed=2024, offset=11, n_exp=c["n_exp"], temp=c["temp"], beta=c["beta"],
+        rec = dict(x=x, u=u, e=e, seed=2024, offset=12, n_exp=c["n_exp"], temp=c["temp"], beta=c["beta"],
                    exc_only=int(c["exc_only"]), lr=cfg_tr["lr"],
                    log_dr=log_dr.detach().numpy(), rate=dist.rate.detach().numpy(), z=z.detach().numpy(),
                    y=y.detach().numpy(), recon=recon.detach().numpy(), kl=kl.detach().numpy(),
                    loss=loss.detach().numpy())
+        rec["cfg_seed"] = c["seed"]
+        for k, v in p_init.items():
+            rec["init_" + k] = v
         for k, v in p0.items():
             rec["p0_" + k] = v
         for k, v in p1.items():

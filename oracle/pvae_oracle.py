@@ -32,8 +32,8 @@ INDICATORS = ("sigmoid", "cosine", "linear", "cubic", "quintic")  # base/distrib
 # ----------------------------------------------------------------------------
 # Philox4x32-10 (Salmon et al., SC'11; Random123 v1.14 philox.h).  The CUDA
 # kernels key it as  key = (seed_lo ^ DOMAIN, seed_hi),
-# ctr = (latent_index, event_quad, offset_lo, offset_hi); word j of block q is
-# event 4q+j of that latent.  See include/pvae_b200.h "RNG contract".
+# ctr = (latent_index >> 2, event, offset_lo, offset_hi); word latent_index & 3 of
+# the block is that latent's draw for that event.  See include/pvae_b200.h "RNG contract".
 # ----------------------------------------------------------------------------
 PHILOX_M0 = np.uint64(0xD2511F53)
 PHILOX_M1 = np.uint64(0xCD9E8D57)
@@ -65,18 +65,18 @@ def uniform_from_bits(bits: np.ndarray) -> np.ndarray:
 
 
 def draw_uniforms(seed: int, offset: int, latent_index: np.ndarray, n_exp: int) -> np.ndarray:
-    """The (n_exp, *latent_index.shape) uniforms the kernels consume."""
-    idx = np.asarray(latent_index, dtype=np.uint32)
-    nq = (n_exp + 3) // 4
-    ctr = np.zeros((nq,) + idx.shape + (4,), dtype=np.uint32)
-    ctr[..., 0] = idx[None]
-    ctr[..., 1] = np.arange(nq, dtype=np.uint32).reshape((nq,) + (1,) * idx.ndim)
+    """The (n_exp, *latent_index.shape) uniforms the kernels consume (include/pvae_b200.h "RNG
+    contract"): block (latent_index >> 2, event) word latent_index & 3."""
+    idx = np.asarray(latent_index, dtype=np.uint64)
+    ctr = np.zeros((n_exp,) + idx.shape + (4,), dtype=np.uint32)
+    ctr[..., 0] = (idx >> np.uint64(2)).astype(np.uint32)[None]
+    ctr[..., 1] = np.arange(n_exp, dtype=np.uint32).reshape((n_exp,) + (1,) * idx.ndim)
     ctr[..., 2] = np.uint32(offset & 0xFFFFFFFF)
     ctr[..., 3] = np.uint32((offset >> 32) & 0xFFFFFFFF)
     key = ((seed & 0xFFFFFFFF) ^ PVAE_KEY_DOMAIN, (seed >> 32) & 0xFFFFFFFF)
-    bits = philox4x32_10(ctr, key)  # (nq, ..., 4)
-    bits = np.moveaxis(bits, -1, 1).reshape((nq * 4,) + idx.shape)
-    return uniform_from_bits(bits[:n_exp])
+    bits = philox4x32_10(ctr, key)  # (n_exp, ..., 4)
+    word = np.broadcast_to((idx & np.uint64(3)).astype(np.int64)[None, ..., None], bits.shape[:-1] + (1,))
+    return uniform_from_bits(np.take_along_axis(bits, word, axis=-1)[..., 0])
 
 
 def exponential_from_uniform(u: np.ndarray) -> np.ndarray:

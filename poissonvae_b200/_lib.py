@@ -1,0 +1,79 @@
+"""ctypes binding of the C-ABI in include/pvae_b200.h (libpvae_b200.so, built in-tree by nvcc).
+
+There is no CPU fallback: if the shared library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libpvae_b200.so")
+SOURCES = ["capi.cu", "sampler.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+_lib = None
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into libpvae_b200.so (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    deps.append(os.path.join(os.path.dirname(_HERE), "include", "pvae_b200.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs + ["-lcuda"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_f, _i, _i64, _u64, _p = C.c_float, C.c_int, C.c_int64, C.c_uint64, C.c_void_p
+
+_SIGNATURES = {
+    "pvae_version": (C.c_int, []),
+    "pvae_last_error": (C.c_char_p, []),
+    "pvae_num_partials": (_i64, [_i64]),
+    "pvae_sampler_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _f, _i, _i, _f, _u64, _u64, _p, _p]),
+    "pvae_sampler_bwd": (_i, [_p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _i, _i64, _i64, _i64, _i, _f, _i, _i, _f, _u64, _u64, _p, _p]),
+    "pvae_rsample_fwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i, _f, _i, _f, _f, _u64, _u64, _p, _p]),
+    "pvae_rsample_bwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i, _f, _i, _f, _f, _u64, _u64, _p, _p]),
+    "pvae_kl_fwd": (_i, [_p, _p, _p, _i64, _i64, _p]),
+    "pvae_kl_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _i64, _p]),
+    "pvae_debug_draws": (_i, [_p, _p, _i64, _i64, _i64, _i, _u64, _u64, _p, _p]),
+}
+
+EXPORTS = tuple(_SIGNATURES)
+
+
+def load():
+    """Load libpvae_b200.so; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(poissonvae_b200 has no CPU or PyTorch fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().pvae_last_error().decode()
+        if rc == -1:
+            raise ValueError(msg or what)
+        if rc == -2:
+            raise NotImplementedError(msg or what)
+        raise RuntimeError(msg or what)

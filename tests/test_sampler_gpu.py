@@ -1,0 +1,289 @@
+"""GPU parity of the sampler / KL kernels (through the C-ABI) against the numpy oracle, the golden
+fixtures made by the unmodified reference, and torch's own CUDA ops fed the same uniforms."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pvae_oracle as po
+from tests.helpers import assert_rel
+
+pytestmark = pytest.mark.gpu
+
+IND = {"sigmoid": 0, "cosine": 1, "linear": 2, "cubic": 3, "quintic": 4}
+LOSSLESS, NEVER = 0.0, -1.0
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from poissonvae_b200 import _lib
+    return _lib.load()
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def P(t):
+    return None if t is None else t.data_ptr()
+
+
+def draws(lib, B, K, n_exp, seed, offset, row_offset=0):
+    U = torch.empty(n_exp, B, K, device="cuda")
+    E = torch.empty(n_exp, B, K, device="cuda")
+    assert lib.pvae_debug_draws(P(U), P(E), B, K, row_offset, n_exp, seed, offset, None, stream()) == 0
+    return U, E
+
+
+def rsample(lib, log_rate, n_exp, temp, kind, seed, offset, clamp=-1.0, exit_logit=LOSSLESS, row_offset=0,
+            want_rate=False):
+    B, K = log_rate.shape
+    z = torch.empty_like(log_rate)
+    rate = torch.empty_like(log_rate) if want_rate else None
+    rc = lib.pvae_rsample_fwd(P(log_rate), P(z), P(rate), B, K, row_offset, n_exp, temp, IND[kind], clamp, exit_logit,
+                              seed, offset, None, stream())
+    assert rc == 0, lib.pvae_last_error()
+    return (z, rate) if want_rate else z
+
+
+def rsample_bwd(lib, log_rate, g_z, n_exp, temp, kind, seed, offset, clamp=-1.0, exit_logit=LOSSLESS):
+    B, K = log_rate.shape
+    g = torch.empty_like(log_rate)
+    rc = lib.pvae_rsample_bwd(P(log_rate), P(g_z), P(g), B, K, 0, n_exp, temp, IND[kind], clamp, exit_logit, seed,
+                              offset, None, stream())
+    assert rc == 0, lib.pvae_last_error()
+    return g
+
+
+# ---------------------------------------------------------------------------------------------
+def test_draws_match_oracle_philox(lib):
+    B, K, n_exp, seed, offset, row_offset = 5, 36, 9, 0x1234567890ABCDEF, (7 << 32) + 12, 3
+    U, E = draws(lib, B, K, n_exp, seed, offset, row_offset)
+    idx = (np.arange(B * K, dtype=np.uint64) + row_offset * K).reshape(B, K)
+    u_ref = po.draw_uniforms(seed, offset, idx, n_exp)
+    assert np.array_equal(U.cpu().numpy(), u_ref)  # bit-exact
+    # e = -logf(u): bit-exact against torch's CUDA log (same libdevice logf), <= 2 ulp against numpy
+    assert torch.equal(E, -torch.log(U))
+    e_np = po.exponential_from_uniform(u_ref)
+    assert np.max(np.abs(E.cpu().numpy() - e_np) / np.maximum(e_np, 1e-30)) < 3e-7
+
+
+def test_offset_dev_is_added(lib):
+    B, K, n_exp = 2, 8, 3
+    U0, _ = draws(lib, B, K, n_exp, 5, 40)
+    off = torch.tensor([28], dtype=torch.int64, device="cuda")
+    U1 = torch.empty_like(U0)
+    assert lib.pvae_debug_draws(P(U1), None, B, K, 0, n_exp, 5, 12, P(off), stream()) == 0
+    assert torch.equal(U0, U1)
+
+
+@pytest.mark.parametrize("exit_logit", [LOSSLESS, NEVER])
+def test_hard_counts_bit_exact(lib, golden_dir, exit_logit):
+    g = np.load(os.path.join(golden_dir, "hard_counts.npz"))
+    log_rate = dev(g["log_rate"])
+    B, K = log_rate.shape
+    n_exp, seed, offset = int(g["n_exp"]), int(g["seed"]), int(g["offset"])
+    counts, rate = rsample(lib, log_rate, n_exp, 0.0, "sigmoid", seed, offset, exit_logit=exit_logit, want_rate=True)
+    U, E = draws(lib, B, K, n_exp, seed, offset)
+    assert np.array_equal(U.cpu().numpy(), g["u"])
+    # (a) the numpy oracle on the kernel's own exponentials and rates: bit-exact
+    want = po.hard_count(E.cpu().numpy(), rate.cpu().numpy())
+    assert np.array_equal(counts.cpu().numpy(), want)
+    # (b) the reference's own torch ops on the GPU, fed the same uniforms: bit-exact
+    rate_t = torch.exp(log_rate) + torch.finfo(torch.float32).eps  # base/distributions.py:24-25
+    times = torch.cumsum(-torch.log(U) / rate_t, dim=0)  # :60-63
+    assert torch.equal(counts, (times <= 1).sum(0).float())
+    assert torch.equal(rate, rate_t)
+    # (c) the fixture the unmodified reference produced on CPU (double running sum there): the counts
+    # may differ only where an arrival lands within an ulp of t = 1
+    diff = counts.cpu().numpy() != g["counts"]
+    assert diff.mean() < 0.01
+
+
+@pytest.mark.parametrize("kind", list(IND))
+def test_relaxed_matches_reference_fixture(lib, golden_dir, kind):
+    g = np.load(os.path.join(golden_dir, f"sampler_{kind}.npz"))
+    log_rate = dev(g["log_rate"])
+    n_exp, seed, offset = int(g["n_exp"]), int(g["seed"]), int(g["offset"])
+    w = dev(g["w"])
+    for temp in (1.0, 0.3, 0.05):
+        z_never = rsample(lib, log_rate, n_exp, temp, kind, seed, offset, exit_logit=NEVER)
+        z = rsample(lib, log_rate, n_exp, temp, kind, seed, offset, exit_logit=LOSSLESS)
+        assert torch.equal(z, z_never), "the lossless early exit must not change a single bit"
+        assert_rel(z.cpu().numpy(), g[f"z_t{temp:g}"], what=f"z {kind} {temp}")
+        gr = rsample_bwd(lib, log_rate, w, n_exp, temp, kind, seed, offset, exit_logit=LOSSLESS)
+        gr_never = rsample_bwd(lib, log_rate, w, n_exp, temp, kind, seed, offset, exit_logit=NEVER)
+        assert torch.equal(gr, gr_never)
+        assert_rel(gr.cpu().numpy(), g[f"g_t{temp:g}"], what=f"grad {kind} {temp}")
+
+
+@pytest.mark.parametrize("kind", list(IND))
+@pytest.mark.parametrize("temp", [1.0, 0.1])
+def test_relaxed_matches_oracle_random(lib, kind, temp):
+    rng = np.random.default_rng(7)
+    B, K, n_exp, seed, offset = 33, 256, 40, 42, 16
+    log_rate = dev(np.minimum(rng.normal(-1.5, 2.0, size=(B, K)), 5.0).astype(np.float32))
+    z, rate = rsample(lib, log_rate, n_exp, temp, kind, seed, offset, want_rate=True)
+    _, E = draws(lib, B, K, n_exp, seed, offset)
+    e, r = E.cpu().numpy(), rate.cpu().numpy()
+    assert_rel(r, po.rate_from_log_rate(log_rate.cpu().numpy()), rtol=5e-7, what="rate")
+    assert_rel(z.cpu().numpy(), po.rsample(e, r, temp, kind), what="z")
+    gz = dev(rng.normal(size=(B, K)).astype(np.float32))
+    g = rsample_bwd(lib, log_rate, gz, n_exp, temp, kind, seed, offset)
+    want = po.rsample_grad_log_rate(e.astype(np.float64), r.astype(np.float64), temp, kind) * gz.cpu().numpy()
+    assert_rel(g.cpu().numpy(), want, what="g_log_rate")
+
+
+def test_clamp_and_positive_exit(lib):
+    rng = np.random.default_rng(8)
+    B, K, n_exp, seed, offset = 16, 128, 64, 1, 4
+    log_rate = dev(rng.normal(2.0, 3.0, size=(B, K)).astype(np.float32))
+    z, rate = rsample(lib, log_rate, n_exp, 0.5, "sigmoid", seed, offset, clamp=4.0, want_rate=True)
+    lam = po.softclamp_upper(log_rate.cpu().numpy(), 4.0)
+    assert_rel(rate.cpu().numpy(), po.rate_from_log_rate(lam), rtol=2e-6, what="clamped rate")
+    # an epsilon-bounded exit (c = 30) stays within the fp32 tolerance of the full chain
+    z30 = rsample(lib, log_rate, n_exp, 0.5, "sigmoid", seed, offset, clamp=4.0, exit_logit=30.0)
+    assert_rel(z30.cpu().numpy(), z.cpu().numpy(), what="exit 30")
+
+
+def fused_fwd(lib, h, log_r, b_enc, n_exp, temp, kind, exc_only, seed, offset, exit_logit=LOSSLESS, row_offset=0):
+    B, K = h.shape
+    out = {k: torch.empty_like(h) for k in ("z", "log_dr", "rate", "kl")}
+    out["kl_rowsum"] = torch.empty(B, device="cuda")
+    out["rate_max"] = torch.zeros(1, device="cuda")
+    rc = lib.pvae_sampler_fwd(P(h), P(log_r), P(b_enc), P(out["z"]), P(out["log_dr"]), P(out["rate"]), P(out["kl"]),
+                              P(out["kl_rowsum"]), P(out["rate_max"]), B, K, row_offset, n_exp, temp, IND[kind],
+                              int(exc_only), exit_logit, seed, offset, None, stream())
+    assert rc == 0, lib.pvae_last_error()
+    return out
+
+
+@pytest.mark.parametrize("exc_only", [False, True])
+@pytest.mark.parametrize("with_bias", [False, True])
+@pytest.mark.parametrize("K", [64, 512, 1024, 520])
+def test_fused_fwd_bwd_matches_oracle(lib, exc_only, with_bias, K):
+    rng = np.random.default_rng(K + exc_only)
+    B, n_exp, temp, beta, seed, offset = 37, 30, 0.4, 2.5, 77, 8
+    h = dev(rng.normal(0.0, 3.0, size=(B, K)).astype(np.float32))
+    h[0, :8] = torch.tensor([-40.0, -25.0, -15.0, 9.0, 15.0, 31.0, 40.0, 0.0])  # both softplus branches
+    log_r = dev(rng.uniform(-6, 2, size=K).astype(np.float32))
+    b_enc = dev(rng.normal(size=K).astype(np.float32)) if with_bias else None
+    out = fused_fwd(lib, h, log_r, b_enc, n_exp, temp, "sigmoid", exc_only, seed, offset)
+    hb = h.cpu().numpy() + (b_enc.cpu().numpy()[None] if with_bias else 0)
+    log_dr, u, lam, rate = po.infer(hb.astype(np.float32), log_r.cpu().numpy(), exc_only)
+    assert_rel(out["log_dr"].cpu().numpy(), log_dr, rtol=2e-6, what="log_dr")
+    assert_rel(out["rate"].cpu().numpy(), rate, what="rate")
+    kl = po.loss_kl(log_r.cpu().numpy(), log_dr)
+    assert_rel(out["kl"].cpu().numpy(), kl, what="kl")
+    assert_rel(out["kl_rowsum"].cpu().numpy(), kl.sum(1), what="kl_rowsum")
+    assert out["rate_max"].item() == out["rate"].max().item()
+    _, E = draws(lib, B, K, n_exp, seed, offset)
+    e, r = E.cpu().numpy(), out["rate"].cpu().numpy()
+    assert_rel(out["z"].cpu().numpy(), po.rsample(e, r, temp, "sigmoid"), what="z")
+
+    # backward, KL gradient fused (kl_scale = beta / B)
+    g_z = dev(rng.normal(size=(B, K)).astype(np.float32))
+    g_h, g_lr = torch.empty_like(h), torch.empty(K, device="cuda")
+    g_b = torch.empty(K, device="cuda") if with_bias else None
+    ws = torch.empty(2 * lib.pvae_num_partials(B) * K, device="cuda")
+    scale = beta / B
+    rc = lib.pvae_sampler_bwd(P(h), P(log_r), P(b_enc), P(g_z), None, scale, P(g_h), P(g_lr), P(g_b), P(ws), 0, B, K, 0,
+                              n_exp, temp, 0, int(exc_only), LOSSLESS, seed, offset, None, stream())
+    assert rc == 0, lib.pvae_last_error()
+    f8 = np.float64
+    dz = po.rsample_grad_log_rate(e.astype(f8), r.astype(f8), temp, "sigmoid")
+    hb8, lr8 = hb.astype(f8), log_r.cpu().numpy().astype(f8)
+    ld8, u8, _, _ = po.infer(hb8, lr8, exc_only)
+    g_u = g_z.cpu().numpy().astype(f8) * dz * po.softclamp_upper_grad(u8, 5.0)
+    g_ld = g_u + scale * np.exp(lr8)[None] * ld8 * np.exp(ld8)
+    dcl = po.softclamp_grad(hb8, 10.0, 0.0) if exc_only else po.softclamp_upper_grad(hb8, 10.0)
+    assert_rel(g_h.cpu().numpy(), g_ld * dcl, what="g_h")
+    assert_rel(g_lr.cpu().numpy(), (g_u + scale * po.loss_kl(lr8, ld8)).sum(0), what="g_log_r")
+    if with_bias:
+        assert_rel(g_b.cpu().numpy(), (g_ld * dcl).sum(0), what="g_b_enc")
+
+
+def test_standalone_kl(lib):
+    rng = np.random.default_rng(3)
+    B, K = 50, 256
+    log_dr = dev(rng.normal(0, 2, size=(B, K)).astype(np.float32))
+    log_r = dev(rng.uniform(-6, -2, size=K).astype(np.float32))
+    kl = torch.empty_like(log_dr)
+    assert lib.pvae_kl_fwd(P(log_dr), P(log_r), P(kl), B, K, stream()) == 0
+    assert_rel(kl.cpu().numpy(), po.loss_kl(log_r.cpu().numpy(), log_dr.cpu().numpy()), what="kl")
+    g_kl = dev(rng.normal(size=(B, K)).astype(np.float32))
+    g_ld, g_lr = torch.empty_like(log_dr), torch.empty(K, device="cuda")
+    ws = torch.empty(lib.pvae_num_partials(B) * K, device="cuda")
+    assert lib.pvae_kl_bwd(P(log_dr), P(log_r), P(g_kl), P(g_ld), P(g_lr), P(ws), 0, B, K, stream()) == 0
+    d, l, g = (t.cpu().numpy().astype(np.float64) for t in (log_dr, log_r, g_kl))
+    assert_rel(g_ld.cpu().numpy(), g * np.exp(l)[None] * d * np.exp(d), what="g_log_dr")
+    assert_rel(g_lr.cpu().numpy(), (g * po.loss_kl(l, d)).sum(0), what="g_log_r")
+
+
+def test_batch_sharding_draws_identical_counts(lib):
+    """Data-parallel invariance: a shard launched with row_offset reproduces the rows of the full batch."""
+    rng = np.random.default_rng(11)
+    B, K, n_exp = 64, 512, 50
+    h = dev(rng.normal(0, 1.5, size=(B, K)).astype(np.float32))
+    log_r = dev(rng.uniform(-6, 0, size=K).astype(np.float32))
+    full = fused_fwd(lib, h, log_r, None, n_exp, 0.3, "sigmoid", False, 9, 20)["z"]
+    for lo, hi in ((0, 16), (16, 40), (40, 64)):
+        part = fused_fwd(lib, h[lo:hi].contiguous(), log_r, None, n_exp, 0.3, "sigmoid", False, 9, 20, row_offset=lo)["z"]
+        assert torch.equal(part, full[lo:hi])
+
+
+def test_full_size_properties(lib):
+    """BASELINE config 2 shape (B=4096, K=512, n_exp=263) with a trained-like rate distribution:
+    size-independent checks."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, K, n_exp = 4096, 512, 263
+    log_rate = torch.clamp(torch.randn(B, K, device="cuda", generator=g) * 2 - 3, max=5.0)
+    z = rsample(lib, log_rate, n_exp, 0.05, "sigmoid", 2024, 4, exit_logit=LOSSLESS)
+    z_never = rsample(lib, log_rate, n_exp, 0.05, "sigmoid", 2024, 4, exit_logit=NEVER)
+    assert torch.equal(z, z_never)
+    assert torch.isfinite(z).all() and (z >= 0).all() and (z <= n_exp).all()
+    # relaxed counts at low temperature track the hard counts of the same chain
+    hard = rsample(lib, log_rate, n_exp, 0.0, "sigmoid", 2024, 4)
+    assert (z - hard).abs().mean().item() < 0.05
+    assert torch.equal(hard, hard.round())
+    # Poisson law: E[count] = rate (well below the n_exp truncation), Var = rate
+    rate = torch.exp(log_rate)
+    sel = rate < 50
+    assert abs((hard[sel].sum() / rate[sel].sum()).item() - 1) < 5e-3
+    lo = (rate > 0.9) & (rate < 1.1)
+    assert abs(hard[lo].var().item() / rate[lo].mean().item() - 1) < 0.05
+
+
+def test_hard_count_law_against_torch_poisson(lib):
+    """temp == 0: same distribution as the reference's torch.poisson branch (base/distributions.py:83-85)."""
+    B, K, n_exp = 2048, 512, po.compute_n_exp(8.0)
+    for lam in (0.05, 0.7, 3.0, 8.0):
+        log_rate = torch.full((B, K), float(np.log(lam)), device="cuda")
+        c = rsample(lib, log_rate, n_exp, 0.0, "sigmoid", 31337, 8).cpu().numpy().ravel()
+        ref = torch.poisson(torch.full((B, K), lam, device="cuda")).cpu().numpy().ravel()
+        kmax = int(max(c.max(), ref.max())) + 1
+        pc = np.bincount(c.astype(int), minlength=kmax) / c.size
+        pr = np.bincount(ref.astype(int), minlength=kmax) / ref.size
+        from scipy import stats
+        pmf = stats.poisson(lam).pmf(np.arange(kmax))
+        assert np.abs(pc - pmf).max() < 3e-3 and np.abs(pr - pmf).max() < 3e-3, lam
+
+
+def test_error_paths(lib):
+    t = torch.zeros(4, 8, device="cuda")
+    assert lib.pvae_rsample_fwd(P(t), P(t), None, 4, 8, 0, 4, -0.5, 0, -1.0, 0.0, 1, 0, None, stream()) == -1
+    assert b"non-neg" in lib.pvae_last_error()
+    assert lib.pvae_rsample_fwd(P(t), P(t), None, 4, 8, 0, 4, 1.0, 9, -1.0, 0.0, 1, 0, None, stream()) == -1
+    assert lib.pvae_rsample_fwd(P(t), P(t), None, 4, 6, 0, 4, 1.0, 0, -1.0, 0.0, 1, 0, None, stream()) == -2
+    assert lib.pvae_rsample_fwd(None, P(t), None, 4, 8, 0, 4, 1.0, 0, -1.0, 0.0, 1, 0, None, stream()) == -1
+    assert lib.pvae_rsample_fwd(P(t), P(t), None, 0, 8, 0, 4, 1.0, 0, -1.0, 0.0, 1, 0, None, stream()) == 0  # empty batch
+    assert lib.pvae_rsample_bwd(P(t), P(t), P(t), 4, 8, 0, 4, 0.0, 0, -1.0, 0.0, 1, 0, None, stream()) == -1
+    # n_exp = 0: no events, zero counts
+    z = torch.ones(4, 8, device="cuda")
+    assert lib.pvae_rsample_fwd(P(t), P(z), None, 4, 8, 0, 0, 1.0, 0, -1.0, 0.0, 1, 0, None, stream()) == 0
+    assert z.abs().sum().item() == 0
