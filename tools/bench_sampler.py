@@ -1,0 +1,78 @@
+"""Micro-benchmark of the sampler kernels (CUDA events, L2 flushed between launches)."""
+import argparse
+import json
+import sys
+import os
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from poissonvae_b200 import _lib  # noqa: E402
+
+
+def P(t):
+    return None if t is None else t.data_ptr()
+
+
+def time_it(fn, iters=20, warmup=3, flush=None):
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=4096)
+    ap.add_argument("--K", type=int, default=512)
+    ap.add_argument("--n_exp", type=int, default=263)
+    ap.add_argument("--iters", type=int, default=10)
+    args = ap.parse_args()
+    lib = _lib.load()
+    B, K, n_exp = args.B, args.K, args.n_exp
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator("cuda").manual_seed(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    dists = {
+        "random_init": (torch.randn(B, K, device="cuda", generator=g) * 0.82,
+                        torch.rand(K, device="cuda", generator=g) * 2 - 6),
+        "trained_like": (torch.randn(B, K, device="cuda", generator=g) * 2.0,
+                         torch.full((K,), -3.0, device="cuda")),
+    }
+    z = torch.empty(B, K, device="cuda")
+    gz = torch.randn(B, K, device="cuda", generator=g)
+    gh = torch.empty(B, K, device="cuda")
+    glr = torch.empty(K, device="cuda")
+    ws = torch.empty(2 * lib.pvae_num_partials(B) * K, device="cuda")
+    klrow = torch.empty(B, device="cuda")
+    for name, (h, log_r) in dists.items():
+        for temp in (1.0, 0.05):
+            for exit_name, ex in (("lossless", 0.0), ("c30", 30.0), ("never", -1.0)):
+                def fwd():
+                    rc = lib.pvae_sampler_fwd(P(h), P(log_r), None, P(z), None, None, None, P(klrow), None, B, K, 0, n_exp,
+                                              temp, 0, 0, ex, 1, 4, None, s)
+                    assert rc == 0
+
+                def bwd():
+                    rc = lib.pvae_sampler_bwd(P(h), P(log_r), None, P(gz), None, 1.0 / B, P(gh), P(glr), None, P(ws), 0, B, K,
+                                              0, n_exp, temp, 0, 0, ex, 1, 4, None, s)
+                    assert rc == 0
+                it = args.iters if ex >= 0 else 3
+                tf, tb = time_it(fwd, it, 2, flush), time_it(bwd, it, 2, flush)
+                print(json.dumps(dict(dist=name, temp=temp, exit=exit_name, fwd_us=round(tf, 1), bwd_us=round(tb, 1),
+                                      fwd_gbs=round(B * K * 8 / tf / 1e3, 1), bwd_gbs=round(B * K * 12 / tb / 1e3, 1),
+                                      mean_z=round(z.mean().item(), 4))), flush=True)
+
+
+if __name__ == "__main__":
+    main()
