@@ -101,6 +101,26 @@ int pvae_kl_fwd(const float* log_dr, const float* log_r, float* kl, int64_t B, i
 int pvae_kl_bwd(const float* log_dr, const float* log_r, const float* g_kl, float* g_log_dr, float* g_log_r,
                 float* partial_ws, int accumulate, int64_t B, int64_t K, void* stream);
 
+/* ---- training-step pieces around the sampler and the GEMMs -----------------------------------
+ * pvae_recon_residual: BaseVAE.loss_recon main/vae.py:68-72 and its gradient in one pass:
+ *   recon (B) = sum_d (y - x)^2,  g_y (B,D) = g_scale * (y - x)  (g_scale = 2 / B_global is
+ *   d mean_b(recon) / d y).  g_y or recon may be NULL.  D must be a multiple of 4.
+ * pvae_loss_assemble: main/train_vae.py:347-351: out3[0] = sum_b(recon + beta * kl_rowsum) / B_global,
+ *   out3[1] = sum recon / B_global, out3[2] = sum kl_rowsum / B_global (shards: sum over ranks).
+ * pvae_grad_norm: nn.utils.clip_grad_norm_ main/train_vae.py:365-377 without the host sync:
+ *   out2[0] = ||g||_2, out2[1] = min(1, max_norm / (||g|| + 1e-6)) (1 if max_norm <= 0);
+ *   ws: pvae_grad_norm_ws_floats() floats.
+ * pvae_adamax_step: base/adamax.py:34-100 on a flat buffer of n parameters; `step` >= 1 is the
+ *   1-based update count (bias correction 1 - beta1^step); clip_coef = out2 of pvae_grad_norm or NULL. */
+int pvae_recon_residual(const float* y, const float* x, float* g_y, float* recon, int64_t B, int64_t D, float g_scale,
+                        void* stream);
+int pvae_loss_assemble(const float* recon, const float* kl_rowsum, float* out3, int64_t B, float beta, int64_t B_global,
+                       void* stream);
+int64_t pvae_grad_norm_ws_floats(void);
+int pvae_grad_norm(const float* g, int64_t n, float max_norm, float* ws, float* out2, void* stream);
+int pvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, float lr, int step, float beta1,
+                     float beta2, float eps, float weight_decay, const float* clip_coef, void* stream);
+
 /* ---- parity harness only: dump the uniforms / exponentials the kernels consume ---------------
  * U, E: (n_exp, B, K).  Either may be NULL. */
 int pvae_debug_draws(float* U, float* E, int64_t B, int64_t K, int64_t row_offset, int n_exp, uint64_t seed,

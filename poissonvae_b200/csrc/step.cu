@@ -1,0 +1,144 @@
+// Small fused kernels of the training step around the sampler and the GEMMs (sm_100a):
+// reconstruction residual + per-sample squared error, loss assembly, gradient norm / clip
+// coefficient and the Adamax update over the flat parameter buffer.
+//
+// Reference semantics: main/vae.py:68-72 (loss_recon), main/train_vae.py:346-377 (loss assembly,
+// clip_grad_norm_), base/adamax.py:34-100 (Adamax "fast").
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pvae_b200.h"
+#include "pvae_device.cuh"
+#include "pvae_host.h"
+
+namespace pvae {
+
+// ---- residual: g_y = (2 / B_global) * (y - x), recon[b] = sum_d (y - x)^2 -----------------------
+// One warp per sample; D is a multiple of 4.
+__global__ void __launch_bounds__(256) recon_kernel(const float* __restrict__ y, const float* __restrict__ x,
+                                                    float* __restrict__ g_y, float* __restrict__ recon, long long B,
+                                                    long long D, float g_scale) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long b = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
+    float acc = 0.f;
+    for (long long d = 4 * lane; d < D; d += 128) {
+      const float4 yv = ldg4(y + b * D + d), xv = ldg4(x + b * D + d);
+      const float4 r = make_float4(yv.x - xv.x, yv.y - xv.y, yv.z - xv.z, yv.w - xv.w);
+      acc += (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
+      if (g_y != nullptr) stg4(g_y + b * D + d, make_float4(g_scale * r.x, g_scale * r.y, g_scale * r.z, g_scale * r.w));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0 && recon != nullptr) recon[b] = acc;
+  }
+}
+
+// ---- loss assembly: out[0] = sum_b(recon + beta * kl_row) / B_global, out[1] = sum recon / Bg,
+// out[2] = sum kl_row / Bg.  Single block, fixed order (deterministic).
+__global__ void __launch_bounds__(1024) loss_kernel(const float* __restrict__ recon, const float* __restrict__ kl_row,
+                                                    float* __restrict__ out, long long B, float beta, float inv_bg) {
+  __shared__ float s_r[32], s_k[32];
+  float r = 0.f, k = 0.f;
+  for (long long b = threadIdx.x; b < B; b += 1024) {
+    r += recon[b];
+    k += kl_row[b];
+  }
+  r = warp_sum(r), k = warp_sum(k);
+  if ((threadIdx.x & 31) == 0) s_r[threadIdx.x >> 5] = r, s_k[threadIdx.x >> 5] = k;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    r = warp_sum(s_r[threadIdx.x]), k = warp_sum(s_k[threadIdx.x]);
+    if (threadIdx.x == 0) {
+      out[0] = (r + beta * k) * inv_bg;
+      out[1] = r * inv_bg;
+      out[2] = k * inv_bg;
+    }
+  }
+}
+
+// ---- gradient L2 norm over the flat buffer, two fixed-order stages -----------------------------
+constexpr int kNormBlocks = 148;
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ part) {
+  __shared__ float s[8];
+  float a = 0.f;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) a = fmaf(g[i], g[i], a);
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s[w];
+    part[blockIdx.x] = t;
+  }
+}
+// out[0] = ||g||, out[1] = clip coefficient min(1, max_norm / (||g|| + 1e-6)) (torch clip_grad_norm_)
+__global__ void norm_finalize_kernel(const float* __restrict__ part, int nparts, float max_norm, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < nparts; ++i) t += part[i];
+    const float nrm = sqrtf(t);
+    out[0] = nrm;
+    out[1] = max_norm > 0.f ? fminf(1.f, max_norm / (nrm + 1e-6f)) : 1.f;
+  }
+}
+
+// ---- Adamax (base/adamax.py:79-88): m = b1 m + (1-b1) g; u = max(b2 u, |g| + eps); p -= clr m / u
+__global__ void __launch_bounds__(256) adamax_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                     float* __restrict__ u, long long n, float clr, float beta1, float beta2,
+                                                     float eps, float weight_decay, const float* __restrict__ clip_coef) {
+  const float cc = clip_coef != nullptr ? clip_coef[1] : 1.f;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
+    float gi = g[i] * cc;
+    const float pi = p[i];
+    if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
+    const float mi = m[i] * beta1 + (1.f - beta1) * gi;
+    const float ui = fmaxf(u[i] * beta2, fabsf(gi) + eps);
+    m[i] = mi;
+    u[i] = ui;
+    p[i] = pi - clr * (mi / ui);
+  }
+}
+
+}  // namespace pvae
+
+using namespace pvae;
+
+extern "C" int pvae_recon_residual(const float* y, const float* x, float* g_y, float* recon, int64_t B, int64_t D,
+                                   float g_scale, void* stream) {
+  if (B < 0 || D <= 0 || D % 4 != 0) return fail(PVAE_ERR_INVALID, "pvae_recon_residual: bad shape B=%lld D=%lld", (long long)B, (long long)D);
+  if (B == 0) return PVAE_OK;
+  if (!y || !x) return fail(PVAE_ERR_INVALID, "pvae_recon_residual: null y/x");
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((B + 7) / 8, 148ll * 8));
+  recon_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, x, g_y, recon, B, D, g_scale);
+  return cuda_ok("pvae_recon_residual", cudaGetLastError());
+}
+
+extern "C" int pvae_loss_assemble(const float* recon, const float* kl_rowsum, float* out3, int64_t B, float beta,
+                                  int64_t B_global, void* stream) {
+  if (B <= 0 || B_global <= 0 || !recon || !kl_rowsum || !out3) return fail(PVAE_ERR_INVALID, "pvae_loss_assemble: bad argument");
+  loss_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(recon, kl_rowsum, out3, B, beta, 1.f / static_cast<float>(B_global));
+  return cuda_ok("pvae_loss_assemble", cudaGetLastError());
+}
+
+extern "C" int64_t pvae_grad_norm_ws_floats(void) { return kNormBlocks; }
+
+extern "C" int pvae_grad_norm(const float* g, int64_t n, float max_norm, float* ws, float* out2, void* stream) {
+  if (n <= 0 || !g || !ws || !out2) return fail(PVAE_ERR_INVALID, "pvae_grad_norm: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  sumsq_partial_kernel<<<kNormBlocks, 256, 0, s>>>(g, n, ws);
+  norm_finalize_kernel<<<1, 32, 0, s>>>(ws, kNormBlocks, max_norm, out2);
+  return cuda_ok("pvae_grad_norm", cudaGetLastError());
+}
+
+extern "C" int pvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, float lr, int step,
+                                float beta1, float beta2, float eps, float weight_decay, const float* clip_coef,
+                                void* stream) {
+  if (n <= 0 || !p || !g || !exp_avg || !exp_inf || step < 1) return fail(PVAE_ERR_INVALID, "pvae_adamax_step: bad argument");
+  const double bias_correction = 1.0 - pow(static_cast<double>(beta1), step);  // base/adamax.py:75-76
+  const float clr = static_cast<float>(static_cast<double>(lr) / bias_correction);
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((n + 255) / 256, 148ll * 8));
+  adamax_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, exp_avg, exp_inf, n, clr, beta1, beta2, eps,
+                                                                      weight_decay, clip_coef);
+  return cuda_ok("pvae_adamax_step", cudaGetLastError());
+}

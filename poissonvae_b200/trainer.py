@@ -1,0 +1,219 @@
+"""Host-side mirror of the reference training step (main/train_vae.py:317-459 `TrainerVAE.iteration`,
+schedules main/train_vae.py:17-74, optimiser base/adamax.py, lr schedule base/train_base.py:258-307)
+for the poisson lin|lin model, driving the sm_100a kernels through include/pvae_b200.h.
+
+One step = forward + loss + backward + optimiser update on a device-resident batch; the gradient
+is the closed form of SURVEY.md section 8 row a13 evaluated by the kernels (no autograd graph).
+Data parallel: every rank runs the same step on its contiguous slice of the global batch, the flat
+gradient buffer is summed with one NCCL all-reduce, and the Philox stream is keyed by the global
+sample index, so the result does not depend on the number of GPUs.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .distributions import INDICATOR_CODES, _ptr, _stream
+from .linear import gemm_nn, gemm_nt, gemm_tn
+from .rng import next_philox
+from .vae import PoissonVAE
+
+
+def temp_anneal_linear(n_iters, t0=1.0, t1=0.1, portion=0.7):
+    """base/utils_model.py:6-14."""
+    temps = np.ones(n_iters) * t1
+    i = int(np.ceil(portion * n_iters))
+    temps[:i] = np.linspace(t0, t1, i)
+    return temps
+
+
+def temp_anneal_exp(n_iters, t0=1.0, t1=0.1, portion=0.7):
+    """base/utils_model.py:17-34 with rate='infer'."""
+    n = min(int(np.ceil(n_iters * portion)), n_iters)
+    rate = -(n / (n - 1)) * np.log(t1 / 100)
+    temps = np.ones(n_iters) * t1
+    i = np.arange(n)
+    temps[:n] = t1 + (t0 - t1) * np.exp(-rate * i / n)
+    return temps
+
+
+def beta_anneal_linear(n_iters, beta=1.0, anneal_portion=0.3, constant_portion=0.0, min_beta=1e-4):
+    """base/utils_model.py:57-68."""
+    betas = np.ones(n_iters) * beta
+    a = int(np.ceil(constant_portion * n_iters))
+    b = int(np.ceil((constant_portion + anneal_portion) * n_iters))
+    betas[:a] = min_beta
+    betas[a:b] = np.linspace(min_beta, beta, b - a)
+    return betas
+
+
+class ConfigTrainVAE:
+    """The fields of the reference ConfigTrainVAE / BaseConfigTrain the step reads
+    (main/config_vae.py:267-330, base/config_base.py:66-110)."""
+
+    def __init__(self, method='mc', kl_beta=1.0, kl_beta_min=1e-4, kl_anneal_cycles=0, kl_anneal_portion=0.5,
+                 kl_const_portion=1e-2, temp_anneal_portion=0.5, temp_anneal_type='lin', temp_start=1.0,
+                 temp_stop=0.05, lr=0.002, epochs=1200, batch_size=200, warmup_portion=0.01,
+                 optimizer='adamax_fast', scheduler_type='cosine', grad_clip=500, betas=(0.9, 0.999), eps=1e-8,
+                 weight_decay=0.0, eta_min=1e-5, **unused):
+        if method != 'mc':
+            raise NotImplementedError("method='exact' is a 'next' row (SURVEY.md 8f)")
+        if kl_anneal_cycles != 0:
+            raise NotImplementedError("cyclic beta annealing")
+        if optimizer not in ('adamax_fast', 'adamax'):
+            raise NotImplementedError(optimizer)
+        if scheduler_type not in ('cosine', None):
+            raise NotImplementedError(scheduler_type)
+        assert temp_anneal_type in ('lin', 'exp')
+        self.__dict__.update({k: v for k, v in locals().items() if k not in ('self', 'unused')})
+
+
+class TrainerVAE:
+    def __init__(self, model: PoissonVAE, cfg: ConfigTrainVAE, n_batches_per_epoch: int = 1,
+                 process_group=None):
+        self.model, self.cfg = model, cfg
+        self.device = model.log_rate.device
+        if self.device.type != 'cuda':
+            raise RuntimeError("TrainerVAE needs the model on a CUDA device (no CPU path)")
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        self.n_iters = cfg.epochs * n_batches_per_epoch
+        self.betas = beta_anneal_linear(self.n_iters, cfg.kl_beta, cfg.kl_anneal_portion, cfg.kl_const_portion,
+                                        cfg.kl_beta_min)  # main/train_vae.py:27-34
+        if cfg.temp_anneal_portion > 0.0:  # main/train_vae.py:59-74
+            fn = temp_anneal_linear if cfg.temp_anneal_type == 'lin' else temp_anneal_exp
+            self.temperatures = fn(self.n_iters, cfg.temp_start, cfg.temp_stop, cfg.temp_anneal_portion)
+        else:
+            self.temperatures = np.ones(self.n_iters) * cfg.temp_stop
+        self._flatten_parameters()
+        self.opt_step = 0
+        self.stats = {}
+        self._bufs = {}
+        self.lib = _lib.load()
+        self.r_max = torch.zeros(max(n_batches_per_epoch, 1), device=self.device)  # rate.max() of each step of the epoch
+
+    # -- one flat fp32 buffer for parameters, gradients and Adamax state ------------------------
+    def _flatten_parameters(self):
+        m = self.model
+        names = ['log_rate', 'fc_enc.weight', 'fc_dec.weight']
+        if m.fc_enc.bias is not None:
+            names.append('fc_enc.bias')
+        if m.fc_dec.bias is not None:
+            raise NotImplementedError("decoder bias")
+        params = dict(m.named_parameters())
+        n = sum(params[k].numel() for k in names)
+        self.flat_p = torch.empty(n, device=self.device, dtype=torch.float32)
+        self.flat_g = torch.zeros_like(self.flat_p)
+        self.exp_avg = torch.zeros_like(self.flat_p)
+        self.exp_inf = torch.zeros_like(self.flat_p)
+        self.views, self.gviews, o = {}, {}, 0
+        for k in names:
+            p = params[k]
+            self.flat_p[o:o + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[o:o + p.numel()].view_as(p)
+            self.views[k] = p.data
+            self.gviews[k] = self.flat_g[o:o + p.numel()].view_as(p)
+            o += p.numel()
+
+    def _buffers(self, B):
+        if B not in self._bufs:
+            K, D = self.model.cfg.n_latents, self.model.cfg.input_sz ** 2
+            f = lambda *s: torch.empty(*s, device=self.device, dtype=torch.float32)
+            self._bufs[B] = dict(h=f(B, K), z=f(B, K), y=f(B, D), g_y=f(B, D), g_z=f(B, K), g_h=f(B, K),
+                                 recon=f(B), klrow=f(B), loss=f(3),
+                                 ws=f(2 * self.lib.pvae_num_partials(B) * K),
+                                 nws=f(self.lib.pvae_grad_norm_ws_floats()), norm=f(2))
+        return self._bufs[B]
+
+    # -- schedules, main/train_vae.py:326-345, 391-400 -------------------------------------------
+    def lr_at(self, gstep: int) -> float:
+        cfg = self.cfg
+        progress = gstep / self.n_iters
+        if progress < cfg.warmup_portion:
+            return cfg.lr * progress / cfg.warmup_portion
+        if cfg.scheduler_type is None:
+            return cfg.lr
+        warm = math.ceil(cfg.warmup_portion * self.n_iters)  # first gstep with progress >= warmup_portion
+        t_max = self.n_iters - self.n_iters * cfg.warmup_portion  # base/train_base.py:286-287
+        s = gstep - warm  # scheduler steps taken before this iteration
+        return cfg.eta_min + (cfg.lr - cfg.eta_min) * (1 + math.cos(math.pi * s / t_max)) / 2
+
+    # -- the step ------------------------------------------------------------------------------------
+    def train_step(self, x: torch.Tensor, gstep: int = 0, philox=None):
+        """x: (B_local, 1, H, W) or (B_local, D) device tensor (this rank's slice of the global batch).
+        Returns the device tensor [loss, mse, kl] (global-batch means; no host sync)."""
+        cfg, m, lib = self.cfg, self.model, self.lib
+        x2 = x.reshape(x.shape[0], -1)
+        B, D = x2.shape
+        K = m.cfg.n_latents
+        Bg = B * self.world
+        row_offset = self.rank * B
+        temp = float(self.temperatures[min(gstep, self.n_iters - 1)])
+        beta = float(self.betas[min(gstep, self.n_iters - 1)])
+        lr = self.lr_at(gstep)
+        m.update_t(temp)
+        n_exp = m._n_exp_host
+        ind = INDICATOR_CODES[m.cfg.indicator_approx]
+        seed, offset = next_philox(self.device) if philox is None else philox
+        b = self._buffers(B)
+        s = _stream()
+        w_enc, w_dec, log_r = self.views['fc_enc.weight'], self.views['fc_dec.weight'], self.views['log_rate']
+        b_enc = self.views.get('fc_enc.bias')
+        chk = _lib.check
+        # forward: encoder GEMM -> fused sampler (+KL row sums, r_max) -> decoder GEMM -> residual
+        gemm_nt(x2, w_enc, out=b['h'])
+        chk(lib.pvae_sampler_fwd(_ptr(b['h']), _ptr(log_r), _ptr(b_enc), _ptr(b['z']), None, None, None,
+                                 _ptr(b['klrow']), self.r_max.data_ptr() + 4 * (gstep % self.r_max.numel()), B, K, row_offset, n_exp, temp, ind,
+                                 int(m.cfg.exc_only), m.exit_logit, seed, offset, None, s))
+        gemm_nt(b['z'], w_dec, out=b['y'])
+        chk(lib.pvae_recon_residual(_ptr(b['y']), _ptr(x2), _ptr(b['g_y']), _ptr(b['recon']), B, D, 2.0 / Bg, s))
+        chk(lib.pvae_loss_assemble(_ptr(b['recon']), _ptr(b['klrow']), _ptr(b['loss']), B, beta, Bg, s))
+        # backward (closed form)
+        gemm_tn(b['g_y'], b['z'], out=self.gviews['fc_dec.weight'])  # g_W_dec = g_y^T z
+        gemm_nn(b['g_y'], w_dec, out=b['g_z'])  # g_z = g_y W_dec
+        chk(lib.pvae_sampler_bwd(_ptr(b['h']), _ptr(log_r), _ptr(b_enc), _ptr(b['g_z']), None, beta / Bg,
+                                 _ptr(b['g_h']), _ptr(self.gviews['log_rate']),
+                                 None if b_enc is None else _ptr(self.gviews['fc_enc.bias']), _ptr(b['ws']), 0, B, K,
+                                 row_offset, n_exp, temp, ind, int(m.cfg.exc_only), m.exit_logit, seed, offset,
+                                 None, s))
+        gemm_tn(b['g_h'], x2, out=self.gviews['fc_enc.weight'])  # g_W_enc = g_h^T x
+        if self.world > 1:
+            dist.all_reduce(self.flat_g, group=self.pg)  # gradients already carry 1 / B_global
+            dist.all_reduce(b['loss'], group=self.pg)
+        # clip (main/train_vae.py:365-377) + Adamax (base/adamax.py)
+        clip = None
+        if cfg.grad_clip is not None:
+            warming = gstep / self.n_iters < cfg.warmup_portion
+            chk(lib.pvae_grad_norm(_ptr(self.flat_g), self.flat_g.numel(), cfg.grad_clip * (3 if warming else 1),
+                                   _ptr(b['nws']), _ptr(b['norm']), s))
+            clip = b['norm']
+        self.opt_step += 1
+        chk(lib.pvae_adamax_step(_ptr(self.flat_p), _ptr(self.flat_g), _ptr(self.exp_avg), _ptr(self.exp_inf),
+                                 self.flat_p.numel(), lr, self.opt_step, cfg.betas[0], cfg.betas[1], cfg.eps,
+                                 cfg.weight_decay, _ptr(clip), s))
+        return b['loss']
+
+    def iteration(self, data: torch.Tensor, epoch: int = 0):
+        """One epoch over a device-resident dataset (N, 1, H, W), like main/train_vae.py:317-459 with a
+        batched index-select instead of the DataLoader; returns the epoch's mean nelbo (one host sync)."""
+        B = self.cfg.batch_size
+        n_batches = data.shape[0] // B  # drop_last
+        perm = torch.randperm(data.shape[0], device=data.device)
+        self.r_max.zero_()
+        total = torch.zeros(3, device=self.device)
+        for i in range(n_batches):
+            x = data[perm[i * B:(i + 1) * B]]
+            total += self.train_step(x, epoch * n_batches + i)
+        nelbo_mse_kl = (total / max(n_batches, 1)).tolist()
+        # end-of-epoch n_exp update from the mean of the per-step rate.max(), main/train_vae.py:388,456-457
+        if self.world > 1:
+            dist.all_reduce(self.r_max, op=dist.ReduceOp.MAX, group=self.pg)
+        r_max = self.r_max[:n_batches].mean().item() if n_batches <= self.r_max.numel() else self.r_max.mean().item()
+        if r_max > 0:
+            self.model.update_n(r_max)
+        return nelbo_mse_kl[1] + nelbo_mse_kl[2]

@@ -1,0 +1,92 @@
+"""GPU: the explicit training step (kernels + closed-form backward + Adamax) against the fixtures the
+unmodified reference produced with autograd and its own Adamax (oracle/make_golden.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pvae_oracle as po
+from tests.helpers import assert_rel
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "vae_step_*.npz")))
+
+
+def make_trainer(g, **over):
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
+    K = g["p0_log_rate"].shape[1]
+    model = PoissonVAE(ConfigPoisVAE(n_latents=K, prior_clamp=-4, exc_only=bool(g["exc_only"]), seed=int(g["cfg_seed"])))
+    model.load_state_dict({k: torch.tensor(g["p0_" + k]) for k in model.state_dict()})
+    model = model.cuda()
+    model.n_exp.fill_(int(g["n_exp"]))
+    model._n_exp_host = int(g["n_exp"])
+    kw = dict(lr=float(g["lr"]), epochs=1, batch_size=g["x"].shape[0], warmup_portion=0.0, scheduler_type=None,
+              grad_clip=None, kl_beta=float(g["beta"]), kl_anneal_portion=0.0, kl_const_portion=0.0,
+              temp_anneal_portion=0.0, temp_stop=float(g["temp"]))
+    kw.update(over)
+    return TrainerVAE(model, ConfigTrainVAE(**kw))
+
+
+@pytest.mark.parametrize("path", GOLDEN)
+def test_train_step_matches_reference(path):
+    g = np.load(path)
+    tr = make_trainer(g)
+    x = torch.tensor(g["x"], device="cuda")
+    loss = tr.train_step(x, 0, philox=(int(g["seed"]), int(g["offset"])))
+    torch.cuda.synchronize()
+    assert_rel(loss[0].item(), float(g["loss"]), rtol=2e-5, what="loss")
+    assert_rel(loss[1].item(), float(g["recon"].mean()), rtol=2e-5, what="mse")
+    assert_rel(loss[2].item(), float(g["kl"].sum(1).mean()), rtol=2e-5, what="kl")
+    for name in ("log_rate", "fc_enc.weight", "fc_dec.weight"):
+        assert_rel(tr.gviews[name].cpu().numpy(), g["g_" + name], rtol=2e-5, what="grad " + name)
+        assert_rel(tr.views[name].cpu().numpy(), g["p1_" + name], rtol=1e-6, what="adamax " + name)
+    # the module's parameters are views of the flat buffer: state_dict sees the update
+    sd = tr.model.state_dict()
+    assert torch.equal(sd["fc_dec.weight"], tr.views["fc_dec.weight"])
+
+
+def test_grad_clip_and_second_step_follow_the_oracle():
+    g = np.load(GOLDEN[0])
+    tr = make_trainer(g, grad_clip=0.05)  # far below the actual norm: the clip must engage
+    x = torch.tensor(g["x"], device="cuda")
+    ph = (int(g["seed"]), int(g["offset"]))
+    flat_p0 = tr.flat_p.clone()
+    tr.train_step(x, 0, philox=ph)
+    grads = tr.flat_g.cpu().numpy().astype(np.float64)
+    norm = float(np.sqrt((grads ** 2).sum()))
+    b = tr._buffers(x.shape[0])
+    assert_rel(b["norm"][0].item(), norm, rtol=1e-5, what="norm")
+    coef = min(1.0, 0.05 / (norm + 1e-6))
+    assert_rel(b["norm"][1].item(), coef, rtol=1e-5, what="clip coefficient")
+    p1, m1, u1 = po.adamax_step(flat_p0.cpu().numpy(), (grads * coef).astype(np.float32), np.zeros_like(grads, np.float32),
+                                np.zeros_like(grads, np.float32), 1, float(g["lr"]))
+    assert_rel(tr.flat_p.cpu().numpy(), p1, rtol=1e-6, what="params after step 1")
+    # a second step continues the Adamax state (step = 2)
+    tr.train_step(x, 0, philox=ph)
+    g2 = tr.flat_g.cpu().numpy().astype(np.float64)
+    c2 = min(1.0, 0.05 / (float(np.sqrt((g2 ** 2).sum())) + 1e-6))
+    p2, _, _ = po.adamax_step(p1, (g2 * c2).astype(np.float32), m1, u1, 2, float(g["lr"]))
+    assert_rel(tr.flat_p.cpu().numpy(), p2, rtol=1e-6, what="params after step 2")
+
+
+def test_schedules_and_epoch_loop():
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
+    model = PoissonVAE(ConfigPoisVAE(n_latents=64, prior_clamp=-4, seed=0)).cuda()
+    cfg = ConfigTrainVAE(lr=0.005, epochs=10, batch_size=50, grad_clip=None, kl_const_portion=0.0)
+    tr = TrainerVAE(model, cfg, n_batches_per_epoch=4)
+    assert tr.n_iters == 40
+    assert np.array_equal(tr.temperatures, po.temp_anneal_linear(40, 1.0, 0.05, 0.5))
+    assert np.array_equal(tr.betas, po.beta_anneal_linear(40, 1.0, 0.5, 0.0, 1e-4))
+    assert tr.lr_at(0) == 0.0 and tr.lr_at(39) < tr.lr_at(1)
+    data = torch.randn(200, 1, 16, 16, device="cuda")
+    before = model.fc_dec.weight.detach().clone()
+    n0 = int(model.n_exp)
+    nelbo = [tr.iteration(data, epoch) for epoch in range(3)]
+    assert all(np.isfinite(nelbo)) and nelbo[-1] < nelbo[0]
+    assert not torch.equal(before, model.fc_dec.weight)
+    assert int(model.n_exp) < n0  # update_n from the epoch's mean rate.max(), main/train_vae.py:456-457
