@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""Benchmark of the P-VAE training hot path (BASELINE.json metric: training samples/s, poisson
+lin|lin K=512, batch 4096 per GPU, n_exp=263, fp32; synthetic whitened 16x16 patches, random-init
+weights).  Prints ONE JSON line.
+
+  python bench.py [--gpus N --steps K --warmup W]          our arm (torchrun for N > 1)
+  python bench.py --impl reference [...]                   the reference's step on the host cores
+                                                           (oracle/ref_port.py, pinned bit-for-bit to
+                                                           the unmodified reference), bounded sample
+
+A step = forward + loss + backward + Adamax update of one batch.  `value` is timed with inputs
+resident in HBM; `e2e` feeds every batch from pinned host memory through the public
+TrainerVAE.train_step_host call and reads the loss back every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "training samples/sec (P-VAE lin|lin K=512)"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
+    ap.add_argument("--latents", type=int, default=512)
+    ap.add_argument("--n_exp", type=int, default=263, help="fresh-model value, main/vae.py:382")
+    ap.add_argument("--temp", type=float, default=1.0)
+    ap.add_argument("--beta", type=float, default=1.0)
+    ap.add_argument("--exit", default="lossless", choices=["lossless", "never"])
+    ap.add_argument("--cpu_rows", type=int, default=256, help="rows of the batch the CPU baseline steps on")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    return {"workload": f"poisson lin|lin K={args.latents} beta={args.beta:g} batch {args.batch}/GPU n_exp={args.n_exp} "
+                        f"temp={args.temp:g} fp32, fwd+loss+bwd+Adamax, exit={args.exit}",
+            "batch_per_gpu": args.batch, "n_latents": args.latents, "n_exp": args.n_exp, "temp": args.temp,
+            "input": "16x16 z-scored N(0,1) patches, seed 1234; weights N(0,0.05^2), log_rate U(-6,-4), cfg.seed 0"}
+
+
+def synthetic_patches(n, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 256, generator=g)
+    return (x - x.mean(1, keepdim=True)) / x.std(1, keepdim=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_steps(args, steps, warmup):
+    """The reference's step (torch CPU port) on `cpu_rows` rows of the workload; returns samples/s."""
+    import torch
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = ref_port.make_params(K=args.latents, D=256, seed=0)
+    optim = ref_port.Adamax(params, lr=0.005)
+    x = synthetic_patches(args.cpu_rows, 1234).view(-1, 1, 16, 16)
+    for _ in range(warmup):
+        ref_port.train_step(params, optim, x, args.n_exp, args.temp, args.beta)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref_port.train_step(params, optim, x, args.n_exp, args.temp, args.beta)
+    dt = time.perf_counter() - t0
+    return args.cpu_rows * steps / dt, cores, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 8))  # each step is a bounded sample; keep the arm within minutes
+    warmup = max(1, min(args.warmup, 2))
+    v, cores, sps = cpu_reference_steps(args, steps, warmup)
+    sample = f"{args.cpu_rows} of {args.batch} rows per step, {steps} steps after {warmup} warm-up, torch CPU {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": round(sps * 1e3, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(args),
+            "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        rows = [r.split(",") for r in self.f.read().strip().splitlines() if r.count(",") >= 7]
+        self.f.close()
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = sorted(float(r[1]) for r in rows)
+        out["sm_mhz"] = sm[len(sm) // 2]
+        out["sm_max_mhz"] = float(rows[0][2])
+        out["power_w_max"] = max(float(r[3]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out["reasons"] = [n for i, n in enumerate(names) if any("Active" == r[4 + i].strip() for r in rows)]
+        out["samples"] = len(rows)
+        return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from poissonvae_b200 import _lib
+    from poissonvae_b200.distributions import EXIT_LOSSLESS, EXIT_NEVER
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path for the product arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.load()  # fails loudly if the CUDA extension has not been built
+    dev = torch.device("cuda", local)
+    B, K, K_steps, W = args.batch, args.latents, args.steps, args.warmup
+
+    model = PoissonVAE(ConfigPoisVAE(n_latents=K, prior_clamp=-4, seed=0),
+                       exit_logit=EXIT_LOSSLESS if args.exit == "lossless" else EXIT_NEVER).to(dev)
+    model.n_exp.fill_(args.n_exp)
+    model._n_exp_host = args.n_exp
+    cfg = ConfigTrainVAE(lr=0.005, epochs=1_000_000, batch_size=B, warmup_portion=0.0, grad_clip=None,
+                         kl_beta=args.beta, kl_anneal_portion=0.0, kl_const_portion=0.0, temp_anneal_portion=0.0,
+                         temp_stop=args.temp)
+    tr = TrainerVAE(model, cfg)
+
+    # inputs: 64 distinct batches (268 MB at B=4096 > 126 MB L2) so that no step finds its input in L2
+    NB = 64
+    host = synthetic_patches(NB * B, 1234 + rank).view(NB, B, 256).pin_memory()
+    data = host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    for i in range(W):
+        tr.train_step(data[i % NB], i)
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    tr.kernel_events = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K_steps):
+        tr.train_step(data[(W + i) % NB], W + i)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    ktimes = tr.kernel_times_us()
+    tr.kernel_events = None
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+
+    # ---- end to end: pinned host batches in, loss out, every step --------------------------------
+    loss_host = torch.empty(2, 3).pin_memory()
+    for i in range(W):
+        tr.train_step_host(host[i % NB], i, host[(i + 1) % NB])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K_steps):
+        j = W + i
+        out = tr.train_step_host(host[j % NB], j, host[(j + 1) % NB])
+        loss_host[i % 2].copy_(out, non_blocking=True)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    clk = clocks.stop() if clocks is not None else None
+    final_loss = loss_host[(K_steps - 1) % 2][0].item()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    dom = max(("sampler_fwd", "sampler_bwd"), key=lambda k: ktimes.get(k, 0.0))
+    bytes_per_latent = {"sampler_fwd": 8, "sampler_bwd": 12}[dom]
+    achieved = B * K * bytes_per_latent / (ktimes[dom] * 1e-6) / 1e9
+    value = world * B * K_steps / (ms_total * 1e-3)
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": W,
+        "ms_per_step": round(ms_total / K_steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": dict(workload(args), l2="inputs rotate over 64 distinct batches (268 MB > 126 MB L2)",
+                       parallelism=f"dp{world}", final_loss=round(final_loss, 4)),
+        "clocks": clk,
+        "e2e": {"value": round(world * B * K_steps / e2e_s.item(), 1), "unit": UNIT,
+                "h2d_bytes_per_step": B * 256 * 4, "d2h_bytes_per_step": 12},
+        "gpu_launches": K_steps * tr.launches_per_step(),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": B * K * bytes_per_latent,
+                     "kernel_us": {k: round(v, 2) for k, v in ktimes.items()}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        steps_cpu = 3
+        v, cores, _ = cpu_reference_steps(args, steps_cpu, 1)
+        line["cpu_baseline"] = {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_rows} of {B} rows per step, {steps_cpu} steps after 1 warm-up, "
+                                          f"torch CPU port of the reference step (oracle/ref_port.py)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

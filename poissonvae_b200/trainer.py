@@ -96,6 +96,8 @@ class TrainerVAE:
         self._bufs = {}
         self.lib = _lib.load()
         self.r_max = torch.zeros(max(n_batches_per_epoch, 1), device=self.device)  # rate.max() of each step of the epoch
+        self.kernel_events = None  # set to {} to record CUDA events around the named launches (bench.py)
+        self._copy_stream = None
 
     # -- one flat fp32 buffer for parameters, gradients and Adamax state ------------------------
     def _flatten_parameters(self):
@@ -143,6 +145,65 @@ class TrainerVAE:
         s = gstep - warm  # scheduler steps taken before this iteration
         return cfg.eta_min + (cfg.lr - cfg.eta_min) * (1 + math.cos(math.pi * s / t_max)) / 2
 
+    def _timed(self, name, fn, *args):
+        """Launch `fn(*args)`; when kernel_events is a dict, bracket it with CUDA events on the launch stream."""
+        if self.kernel_events is None:
+            return fn(*args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn(*args)
+        e1.record()
+        self.kernel_events.setdefault(name, []).append((e0, e1))
+        return out
+
+    def launches_per_step(self) -> int:
+        """Kernels of libpvae_b200.so launched by one train_step (the five GEMMs are counted apart)."""
+        n = 6  # sampler fwd, residual, loss, sampler bwd, column-sum finalize, Adamax
+        if self.model.fc_enc.bias is not None:
+            n += 1  # second column-sum finalize (bias gradient)
+        if self.cfg.grad_clip is not None:
+            n += 2  # sum of squares partials + finalize
+        return n
+
+    def kernel_times_us(self):
+        """Mean duration per launch of the launches recorded in kernel_events (call after a synchronize)."""
+        return {k: 1e3 * sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in (self.kernel_events or {}).items()}
+
+    # -- host-fed step: the public entry point for batches that live in (pinned) host memory ----------
+    def train_step_host(self, x_host: torch.Tensor, gstep: int = 0, x_next_host: torch.Tensor = None):
+        """One step on a pinned host batch: the host->device copy of the NEXT batch is issued on a
+        side stream before this step's kernels so that it overlaps them (double-buffered staging).
+        Returns the device tensor [loss, mse, kl]; the caller reads it back (`.to('cpu')`)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage = [None, None]
+            self._stage_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_src = [None, None]
+            self._cur = 0
+        cur = self._cur
+        main = torch.cuda.current_stream()
+        if self._stage_src[cur] is not x_host:  # not prefetched: copy now
+            self._upload(cur, x_host, main)
+        if x_next_host is not None:
+            self._upload(1 - cur, x_next_host, main)
+        main.wait_event(self._stage_ev[cur])
+        out = self.train_step(self._stage[cur], gstep)
+        self._stage_free[cur].record(main)
+        self._stage_src[cur] = None
+        self._cur = 1 - cur
+        return out
+
+    def _upload(self, slot, x_host, main):
+        if self._stage[slot] is None or self._stage[slot].shape != x_host.shape:
+            self._stage[slot] = torch.empty(x_host.shape, device=self.device, dtype=torch.float32)
+        cs = self._copy_stream
+        cs.wait_event(self._stage_free[slot])  # the step that last read this slot has finished
+        with torch.cuda.stream(cs):
+            self._stage[slot].copy_(x_host, non_blocking=True)
+            self._stage_ev[slot].record(cs)
+        self._stage_src[slot] = x_host
+
     # -- the step ------------------------------------------------------------------------------------
     def train_step(self, x: torch.Tensor, gstep: int = 0, philox=None):
         """x: (B_local, 1, H, W) or (B_local, D) device tensor (this rank's slice of the global batch).
@@ -167,20 +228,20 @@ class TrainerVAE:
         chk = _lib.check
         # forward: encoder GEMM -> fused sampler (+KL row sums, r_max) -> decoder GEMM -> residual
         gemm_nt(x2, w_enc, out=b['h'])
-        chk(lib.pvae_sampler_fwd(_ptr(b['h']), _ptr(log_r), _ptr(b_enc), _ptr(b['z']), None, None, None,
+        self._timed('sampler_fwd', lambda: chk(lib.pvae_sampler_fwd(_ptr(b['h']), _ptr(log_r), _ptr(b_enc), _ptr(b['z']), None, None, None,
                                  _ptr(b['klrow']), self.r_max.data_ptr() + 4 * (gstep % self.r_max.numel()), B, K, row_offset, n_exp, temp, ind,
-                                 int(m.cfg.exc_only), m.exit_logit, seed, offset, None, s))
+                                 int(m.cfg.exc_only), m.exit_logit, seed, offset, None, s)))
         gemm_nt(b['z'], w_dec, out=b['y'])
         chk(lib.pvae_recon_residual(_ptr(b['y']), _ptr(x2), _ptr(b['g_y']), _ptr(b['recon']), B, D, 2.0 / Bg, s))
         chk(lib.pvae_loss_assemble(_ptr(b['recon']), _ptr(b['klrow']), _ptr(b['loss']), B, beta, Bg, s))
         # backward (closed form)
         gemm_tn(b['g_y'], b['z'], out=self.gviews['fc_dec.weight'])  # g_W_dec = g_y^T z
         gemm_nn(b['g_y'], w_dec, out=b['g_z'])  # g_z = g_y W_dec
-        chk(lib.pvae_sampler_bwd(_ptr(b['h']), _ptr(log_r), _ptr(b_enc), _ptr(b['g_z']), None, beta / Bg,
+        self._timed('sampler_bwd', lambda: chk(lib.pvae_sampler_bwd(_ptr(b['h']), _ptr(log_r), _ptr(b_enc), _ptr(b['g_z']), None, beta / Bg,
                                  _ptr(b['g_h']), _ptr(self.gviews['log_rate']),
                                  None if b_enc is None else _ptr(self.gviews['fc_enc.bias']), _ptr(b['ws']), 0, B, K,
                                  row_offset, n_exp, temp, ind, int(m.cfg.exc_only), m.exit_logit, seed, offset,
-                                 None, s))
+                                 None, s)))
         gemm_tn(b['g_h'], x2, out=self.gviews['fc_enc.weight'])  # g_W_enc = g_h^T x
         if self.world > 1:
             dist.all_reduce(self.flat_g, group=self.pg)  # gradients already carry 1 / B_global
