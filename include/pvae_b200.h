@@ -121,8 +121,16 @@ int pvae_grad_norm(const float* g, int64_t n, float max_norm, float* ws, float* 
 int pvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, float lr, int step, float beta1,
                      float beta2, float eps, float weight_decay, const float* clip_coef, void* stream);
 
+/* Tuning knob (process-wide): number of events each quad of latents walks thread-per-quad before a
+ * still-unfinished chain is handed to a whole warp (32 events per step).  Default 8.  Results do
+ * not depend on the launch geometry, but the float summation order of a chain depends on this value. */
+int pvae_set_phase_a_events(int n);
+
 /* ---- parity harness only: dump the uniforms / exponentials the kernels consume ---------------
- * U, E: (n_exp, B, K).  Either may be NULL. */
+ * U, E: (n_exp, B, K).  Either may be NULL.
+ * pvae_debug_log_check adds to *mismatches_dev the number of the 2^23 possible uniforms for which the
+ * kernels' -log(u) differs by a bit from libdevice's -logf(u) (expected 0). */
+int pvae_debug_log_check(uint64_t* mismatches_dev, void* stream);
 int pvae_debug_draws(float* U, float* E, int64_t B, int64_t K, int64_t row_offset, int n_exp, uint64_t seed,
                      uint64_t offset, const uint64_t* offset_dev, void* stream);
 

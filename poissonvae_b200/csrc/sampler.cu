@@ -1,11 +1,19 @@
 // Fused Poisson reparameterised sampler + KL kernels for sm_100a.
 //
-// One thread owns a quad of four consecutive latents of one sample (128-bit loads of the encoder
-// output, 128-bit stores of the counts) and walks their arrival chains in lock step: one
-// Philox4x32-10 block per event feeds the four chains, the running arrival times stay in
-// registers and the (n_exp, B, K) tensors of the reference never exist.  A block owns a tile of
-// rows and all columns of those rows, so per-sample KL sums and per-latent (batch) gradient sums
-// are produced without atomics, in a fixed order.
+// Work decomposition.  A block owns a tile of rows (samples) and all K latents of those rows.
+//   Phase A  one thread per quad of four consecutive latents (128-bit loads of the encoder output,
+//            128-bit stores of the counts): softclamps, rate and KL in registers, then the four
+//            arrival chains in lock step - one Philox4x32-10 block per event feeds the four chains.
+//            A chain leaves as soon as every later term is exactly zero (lossless early exit).
+//            Quads still alive after `phase_a` events are parked in shared memory.
+//   Phase B  each warp takes parked quads one at a time and walks the rest of the chain 32 events
+//            per step: lane i draws event n0+i, the arrival times come from a warp prefix sum
+//            (shfl.up), so one long chain costs n/32 steps instead of stalling 31 idle lanes.
+// The (n_exp, B, K) tensors of the reference never exist; per-sample KL sums and per-latent
+// (batch) gradient sums are produced without atomics, in a fixed order.
+//
+// Hard counts (temp == 0) run Phase A only: the running sum is then the same sequential fp32 sum
+// as torch's CUDA cumsum, which makes the hard counts bit-exact.
 //
 // Reference semantics: base/distributions.py:5-92 (Poisson), main/vae.py:393-415 (infer),
 // main/vae.py:446-450 (loss_kl); closed-form backward SURVEY.md section 8 row a13.
@@ -19,20 +27,21 @@
 
 namespace pvae {
 
-constexpr int kThreads = 128;          // threads per block
+constexpr int kThreads = 128;               // threads per block
+constexpr int kWarps = kThreads / 32;
 constexpr int kColsPerPass = 4 * kThreads;  // latents of one row a block covers per pass
-constexpr int kMaxRowsPerBlock = 8;
+constexpr int kMaxRows = 4;                 // rows per block tile
+constexpr int kSlots = kMaxRows * kThreads; // parked-quad table: one slot per (row, thread)
+constexpr int kSlotWords = 12;              // rate[4], t[4], acc[4]
 
 enum Mode : int { kFwdSoft = 0, kFwdHard = 1, kBwd = 2 };
 
 struct SamplerParams {
-  // inputs
-  const float* h;      // (B,K) encoder output, or log_rate in RAW mode
-  const float* log_r;  // (K)
-  const float* b_enc;  // (K) or null
-  const float* g_z;    // (B,K) bwd
+  const float* h;         // (B,K) encoder output, or log_rate in RAW mode
+  const float* log_r;     // (K)
+  const float* b_enc;     // (K) or null
+  const float* g_z;       // (B,K) bwd
   const float* g_log_dr;  // (B,K) bwd, optional
-  // outputs
   float* z;
   float* log_dr;
   float* rate;
@@ -45,8 +54,11 @@ struct SamplerParams {
   long long B, K, row_offset;
   int rows_per_block;
   int n_exp;
-  float temp, inv_temp, exit_logit;  // exit_logit < 0: never leave early
-  float clamp_dr, clamp_rate;        // RAW: clamp_rate < 0 means no clamp
+  int phase_a;        // events walked thread-per-quad before a quad is parked for phase B
+  float inv_temp;     // 1 / temp
+  float sig_a;        // log2(e) / temp: sigmoid((1 - t) / temp) = 1 / (1 + 2^(sig_a * (t - 1)))
+  float t_exit;       // leave a chain once every arrival time exceeds this (+inf: never)
+  float clamp_dr, clamp_rate;  // RAW: clamp_rate < 0 means no clamp
   float kl_scale;
   int exc_only;
   uint64_t offset;
@@ -54,82 +66,141 @@ struct SamplerParams {
   PhiloxKey ks;
 };
 
-struct Quad {
-  float v[4];
-};
-
-// ---- the arrival chain of four latents ---------------------------------------------------------
-// Returns, per latent, acc_f = sum_n f(logit_n) (relaxed count) or the hard count, and if GRAD
-// acc_g = sum_n f'(logit_n) * t_n.
-template <int MODE, int IND>
-__device__ __forceinline__ void run_chain(const SamplerParams& p, uint32_t quad, uint32_t off_lo, uint32_t off_hi,
-                                          const float (&rate)[4], float (&acc_f)[4], float (&acc_g)[4]) {
-  float t[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) acc_f[j] = acc_g[j] = 0.f;
-  const float inv_temp = p.inv_temp;
-  const float exit_logit = p.exit_logit;
-  const bool may_exit = exit_logit >= 0.f;
-  for (int n = 0; n < p.n_exp; ++n) {
-    const uint4 r = philox4x32_10(quad, static_cast<uint32_t>(n), off_lo, off_hi, p.ks);
-    const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
-    float lmax = -3.0e38f, tmin = 3.0e38f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float e = exponential_from_bits(bits[j]);
-      t[j] = __fadd_rn(t[j], __fdiv_rn(e, rate[j]));
-      if (MODE == kFwdHard) {
-        acc_f[j] += (t[j] <= 1.f) ? 1.f : 0.f;
-        tmin = fminf(tmin, t[j]);
-      } else {
-        const float l = (1.f - t[j]) * inv_temp;
-        float f, df;
-        indicator_eval<IND, MODE == kBwd>(l, f, df);
-        if (MODE == kBwd) acc_g[j] = fmaf(df, t[j], acc_g[j]);
-        else acc_f[j] += f;
-        lmax = fmaxf(lmax, l);
-      }
-    }
-    if (MODE == kFwdHard) {
-      if (may_exit && tmin > 1.f) break;
-    } else {
-      if (may_exit && lmax < -exit_logit) break;
-    }
+// ---- one soft-threshold term -------------------------------------------------------------------
+template <int IND, bool GRAD>
+__device__ __forceinline__ void soft_term(const SamplerParams& p, float t, float& f, float& df) {
+  if (IND == kSigmoid) {
+    const float w = ex2_approx(fmaf(t, p.sig_a, -p.sig_a));  // exp(-(1 - t) / temp)
+    f = rcp_approx(1.f + w);
+    if (GRAD) df = fmaf(-f, f, f);
+  } else {
+    indicator_eval<IND, GRAD>(fmaf(-t, p.inv_temp, p.inv_temp), f, df);
   }
 }
 
-// ---- prologue: encoder output -> log_dr, u, log-rate, rate -------------------------------------
+// x = e / rate.  Soft path: Markstein's correction on a correctly rounded reciprocal (equals div.rn
+// except in pathological cases, 3 FMA-pipe ops).  Hard path: IEEE division, bit-exact by definition.
+template <bool EXACT>
+__device__ __forceinline__ float div_by_rate(float e, float rate, float inv_rate) {
+  if (EXACT) return __fdiv_rn(e, rate);
+  const float q = e * inv_rate;
+  return fmaf(fmaf(-q, rate, e), inv_rate, q);
+}
+
+// ---- phase A: four chains in lock step, events [0, n_end) ---------------------------------------
+// acc: sum_n f(logit_n) (fwd), hard count (hard) or sum_n f'(logit_n) * t_n (bwd).
+// Returns true when the chains are complete (exit reached or all n_exp events walked).
+template <int MODE, int IND>
+__device__ __forceinline__ bool phase_a(const SamplerParams& p, uint32_t quad, uint32_t off_lo, uint32_t off_hi,
+                                        const float (&rate)[4], const float (&inv_rate)[4], float (&t)[4],
+                                        float (&acc)[4], int n_end) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) t[j] = acc[j] = 0.f;
+  const float t_exit = p.t_exit;
+  for (int n = 0; n < n_end; ++n) {
+    const uint4 r = philox4x32_10(quad, static_cast<uint32_t>(n), off_lo, off_hi, p.ks);
+    const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float e = exponential_from_bits(bits[j]);
+      t[j] = __fadd_rn(t[j], div_by_rate<MODE == kFwdHard>(e, rate[j], inv_rate[j]));
+      if (MODE == kFwdHard) {
+        acc[j] += (t[j] <= 1.f) ? 1.f : 0.f;
+      } else {
+        float f, df;
+        soft_term<IND, MODE == kBwd>(p, t[j], f, df);
+        acc[j] = MODE == kBwd ? fmaf(df, t[j], acc[j]) : acc[j] + f;
+      }
+    }
+    if (fminf(fminf(t[0], t[1]), fminf(t[2], t[3])) > t_exit) return true;
+  }
+  return n_end >= p.n_exp;
+}
+
+// ---- phase B: one warp finishes one parked quad, 32 events per step ----------------------------
+template <int MODE, int IND>
+__device__ __forceinline__ void phase_b(const SamplerParams& p, uint32_t quad, uint32_t off_lo, uint32_t off_hi,
+                                        const float (&rate)[4], float (&t0)[4], float (&acc)[4], int lane) {
+  float inv_rate[4], part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) inv_rate[j] = __frcp_rn(rate[j]);
+  for (int n0 = p.phase_a; n0 < p.n_exp; n0 += 32) {
+    const int n = n0 + lane;
+    const bool valid = n < p.n_exp;
+    const uint4 r = philox4x32_10(quad, static_cast<uint32_t>(n), off_lo, off_hi, p.ks);
+    const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x = valid ? div_by_rate<false>(exponential_from_bits(bits[j]), rate[j], inv_rate[j]) : 0.f;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {  // inclusive prefix sum over the lanes
+        const float y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      const float t = t0[j] + x;
+      float f, df;
+      soft_term<IND, MODE == kBwd>(p, t, f, df);
+      const float term = MODE == kBwd ? df * t : f;
+      part[j] += valid ? term : 0.f;
+      t0[j] = __shfl_sync(0xffffffffu, t, 31);
+    }
+    if (fminf(fminf(t0[0], t0[1]), fminf(t0[2], t0[3])) > p.t_exit) break;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] += warp_sum(part[j]);
+}
+
+// ---- prologue: encoder output -> log_dr, u, rate (and the clamp derivatives for the backward) ---
 struct Latent {
-  float hb;      // h + bias
   float log_dr;  // delta
-  float u;       // log_r + delta
   float explam;  // exp(lambda)
   float rate;    // exp(lambda) + eps
+  float d_rate;  // d lambda / d u            (softclamp_upper'(u, 5))
+  float d_dr;    // d delta / d (h + bias)    (softclamp'(h, 10) / softclamp_upper'(h, 10))
 };
 
-template <bool RAW>
+template <bool RAW, bool GRAD>
 __device__ __forceinline__ Latent prologue(const SamplerParams& p, float hv, float lr, float bias) {
   Latent q;
+  float lam;
   if (RAW) {
-    q.hb = hv;
     q.log_dr = 0.f;
-    q.u = hv;
-    const float lam = p.clamp_rate >= 0.f ? softclamp_upper(hv, p.clamp_rate) : hv;
-    q.explam = expf(lam);
+    q.d_dr = 1.f;
+    if (p.clamp_rate >= 0.f) {
+      const Softplus s = softplus20_fast<GRAD>(p.clamp_rate - hv);
+      lam = p.clamp_rate - s.value;
+      q.d_rate = s.grad;
+    } else {
+      lam = hv;
+      q.d_rate = 1.f;
+    }
   } else {
-    q.hb = hv + bias;
-    q.log_dr = p.exc_only ? softclamp_band(q.hb, p.clamp_dr, 0.f) : softclamp_upper(q.hb, p.clamp_dr);
-    q.u = lr + q.log_dr;
-    q.explam = expf(softclamp_upper(q.u, p.clamp_rate));
+    const float hb = hv + bias;
+    if (p.exc_only) {  // softclamp(h, 10, 0) = softplus(h) - softplus(h - 10), base/distributions.py:233-234
+      const Softplus a = softplus20_fast<GRAD>(hb), b = softplus20_fast<GRAD>(hb - p.clamp_dr);
+      q.log_dr = a.value - b.value;
+      q.d_dr = a.grad - b.grad;
+    } else {  // softclamp_upper(h, 10) = 10 - softplus(10 - h), base/distributions.py:241-242
+      const Softplus a = softplus20_fast<GRAD>(p.clamp_dr - hb);
+      q.log_dr = p.clamp_dr - a.value;
+      q.d_dr = a.grad;
+    }
+    const Softplus c = softplus20_fast<GRAD>(p.clamp_rate - (lr + q.log_dr));  // main/vae.py:409
+    lam = p.clamp_rate - c.value;
+    q.d_rate = c.grad;
   }
-  q.rate = q.explam + kF32Eps;
+  q.explam = expf(lam);
+  q.rate = q.explam + kF32Eps;  // base/distributions.py:24-25
   return q;
 }
 
 template <int MODE, int IND, bool RAW>
 __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p) {
-  __shared__ float s_rowsum[kMaxRowsPerBlock][kThreads / 32];
-  __shared__ float s_max[kThreads / 32];
+  __shared__ float s_tab[kSlotWords][kSlots];  // parked quads, one word-plane per field
+  __shared__ unsigned short s_list[kSlots];
+  __shared__ int s_count;
+  __shared__ float s_rowsum[kMaxRows][kWarps];
+  __shared__ float s_max[kWarps];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -138,18 +209,18 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
   uint64_t off = p.offset;
   if (p.offset_dev != nullptr) off += *p.offset_dev;
   const uint32_t off_lo = static_cast<uint32_t>(off), off_hi = static_cast<uint32_t>(off >> 32);
+  const int n_a = min(p.phase_a, p.n_exp);
 
   float rmax = 0.f;
   const bool want_rowsum = MODE != kBwd && !RAW && p.kl_rowsum != nullptr;
-  if (want_rowsum) {
-    if (tid < kMaxRowsPerBlock * (kThreads / 32)) (&s_rowsum[0][0])[tid] = 0.f;
-    __syncthreads();
-  }
+  if (tid < kMaxRows * kWarps) (&s_rowsum[0][0])[tid] = 0.f;
 
-  // every thread runs every pass so that the warp-level reductions below see full warps
+  // every thread runs every pass so that the block-level steps below see whole warps
   for (long long k0 = 0; k0 < p.K; k0 += kColsPerPass) {
     const long long k = k0 + 4 * tid;
     const bool act = k < p.K;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
     float lr[4] = {0.f, 0.f, 0.f, 0.f}, bias[4] = {0.f, 0.f, 0.f, 0.f}, elr[4] = {0.f, 0.f, 0.f, 0.f};
     if (!RAW && act) {
       const float4 v = ldg4(p.log_r + k);
@@ -162,85 +233,139 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
       for (int j = 0; j < 4; ++j) elr[j] = expf(lr[j]);
     }
     float col_lr[4] = {0.f, 0.f, 0.f, 0.f}, col_b[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned parked = 0;  // bit r: this thread's quad of row r waits for phase B
 
+    // backward epilogue of one quad: gradients from acc = sum_n f'(l_n) t_n
+    auto bwd_finish = [&](long long base, const Latent (&q)[4], const float (&acc)[4]) {
+      const float4 gz4 = ldg4(p.g_z + base);
+      const float gz[4] = {gz4.x, gz4.y, gz4.z, gz4.w};
+      float gld[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!RAW && p.g_log_dr != nullptr) {
+        const float4 g = ldg4(p.g_log_dr + base);
+        gld[0] = g.x, gld[1] = g.y, gld[2] = g.z, gld[3] = g.w;
+      }
+      float gh[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // d z / d lambda = (sum_n f'(l_n) t_n) / temp * exp(lambda) / rate; then the clamp chain
+        const float g_u = gz[j] * (acc[j] * p.inv_temp * (q[j].explam / q[j].rate)) * q[j].d_rate;
+        if (RAW) {
+          gh[j] = g_u;
+        } else {
+          const float d = q[j].log_dr, ed = expf(d);
+          gh[j] = (g_u + p.kl_scale * elr[j] * d * ed + gld[j]) * q[j].d_dr;
+          col_lr[j] += g_u + p.kl_scale * (elr[j] * (1.f + ed * (d - 1.f)));
+          col_b[j] += gh[j];
+        }
+      }
+      stg4(p.g_h + base, make_float4(gh[0], gh[1], gh[2], gh[3]));
+    };
+
+    // ---------------- phase A ----------------
 #pragma unroll 1
     for (int r = 0; r < nrows; ++r) {
       float klsum = 0.f;
       if (act) {
-      const long long row = row0 + r;
-      const long long base = row * p.K + k;
-      const float4 hv4 = ldg4(p.h + base);
-      const float hv[4] = {hv4.x, hv4.y, hv4.z, hv4.w};
-      Latent q[4];
-      float rate[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        q[j] = prologue<RAW>(p, hv[j], lr[j], bias[j]);
-        rate[j] = q[j].rate;
-      }
-      const uint32_t quad = static_cast<uint32_t>(((p.row_offset + row) * p.K + k) >> 2);
-      float acc_f[4], acc_g[4];
-      run_chain<MODE, IND>(p, quad, off_lo, off_hi, rate, acc_f, acc_g);
-
-      if (MODE != kBwd) {
-        stg4(p.z + base, make_float4(acc_f[0], acc_f[1], acc_f[2], acc_f[3]));
-        if (p.rate != nullptr) stg4(p.rate + base, make_float4(rate[0], rate[1], rate[2], rate[3]));
-        if (p.rate_max != nullptr) rmax = fmaxf(fmaxf(fmaxf(rate[0], rate[1]), fmaxf(rate[2], rate[3])), rmax);
-        if (!RAW) {
-          if (p.log_dr != nullptr)
-            stg4(p.log_dr + base, make_float4(q[0].log_dr, q[1].log_dr, q[2].log_dr, q[3].log_dr));
-          if (p.kl != nullptr || p.kl_rowsum != nullptr) {
-            float klv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float d = q[j].log_dr;
-              klv[j] = elr[j] * (1.f + expf(d) * (d - 1.f));  // main/vae.py:448-449
-            }
-            if (p.kl != nullptr) stg4(p.kl + base, make_float4(klv[0], klv[1], klv[2], klv[3]));
-            klsum = (klv[0] + klv[1]) + (klv[2] + klv[3]);
-          }
-        }
-      } else {
-        const float4 gz4 = ldg4(p.g_z + base);
-        const float gz[4] = {gz4.x, gz4.y, gz4.z, gz4.w};
-        float gld[4] = {0.f, 0.f, 0.f, 0.f};
-        if (!RAW && p.g_log_dr != nullptr) {
-          const float4 g = ldg4(p.g_log_dr + base);
-          gld[0] = g.x, gld[1] = g.y, gld[2] = g.z, gld[3] = g.w;
-        }
-        float gh[4];
+        const long long row = row0 + r;
+        const long long base = row * p.K + k;
+        const float4 hv4 = ldg4(p.h + base);
+        const float hv[4] = {hv4.x, hv4.y, hv4.z, hv4.w};
+        Latent q[4];
+        float rate[4], inv_rate[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          // d z / d lambda = (sum_n f'(l_n) t_n) / temp * exp(lambda) / rate
-          const float dz = acc_g[j] * p.inv_temp * (q[j].explam / q[j].rate);
-          if (RAW) {
-            gh[j] = gz[j] * dz * (p.clamp_rate >= 0.f ? softclamp_upper_grad(q[j].u, p.clamp_rate) : 1.f);
-          } else {
-            const float d = q[j].log_dr;
-            const float g_u = gz[j] * dz * softclamp_upper_grad(q[j].u, p.clamp_rate);
-            const float ed = expf(d);
-            const float g_d = g_u + p.kl_scale * elr[j] * d * ed + gld[j];
-            const float dcl = p.exc_only ? softclamp_band_grad(q[j].hb, p.clamp_dr, 0.f)
-                                         : softclamp_upper_grad(q[j].hb, p.clamp_dr);
-            gh[j] = g_d * dcl;
-            col_lr[j] += g_u + p.kl_scale * (elr[j] * (1.f + ed * (d - 1.f)));
-            col_b[j] += gh[j];
+          q[j] = prologue<RAW, MODE == kBwd>(p, hv[j], lr[j], bias[j]);
+          rate[j] = q[j].rate;
+          inv_rate[j] = __frcp_rn(rate[j]);
+        }
+        if (MODE != kBwd) {  // outputs that do not depend on the chain
+          if (p.rate != nullptr) stg4(p.rate + base, make_float4(rate[0], rate[1], rate[2], rate[3]));
+          if (p.rate_max != nullptr) rmax = fmaxf(fmaxf(fmaxf(rate[0], rate[1]), fmaxf(rate[2], rate[3])), rmax);
+          if (!RAW) {
+            if (p.log_dr != nullptr)
+              stg4(p.log_dr + base, make_float4(q[0].log_dr, q[1].log_dr, q[2].log_dr, q[3].log_dr));
+            if (p.kl != nullptr || p.kl_rowsum != nullptr) {
+              float klv[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float d = q[j].log_dr;
+                klv[j] = elr[j] * (1.f + expf(d) * (d - 1.f));  // main/vae.py:448-449
+              }
+              if (p.kl != nullptr) stg4(p.kl + base, make_float4(klv[0], klv[1], klv[2], klv[3]));
+              klsum = (klv[0] + klv[1]) + (klv[2] + klv[3]);
+            }
           }
         }
-        stg4(p.g_h + base, make_float4(gh[0], gh[1], gh[2], gh[3]));
+        const uint32_t quad = static_cast<uint32_t>(((p.row_offset + row) * p.K + k) >> 2);
+        float t[4], acc[4];
+        const bool done = phase_a<MODE, IND>(p, quad, off_lo, off_hi, rate, inv_rate, t, acc, n_a);
+        if (done) {
+          if (MODE != kBwd) stg4(p.z + base, make_float4(acc[0], acc[1], acc[2], acc[3]));
+          else bwd_finish(base, q, acc);
+        } else {
+          const int slot = r * kThreads + tid;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            s_tab[j][slot] = rate[j];
+            s_tab[4 + j][slot] = t[j];
+            s_tab[8 + j][slot] = acc[j];
+          }
+          s_list[atomicAdd(&s_count, 1)] = static_cast<unsigned short>(slot);
+          parked |= 1u << r;
+        }
       }
-      }  // act
       if (want_rowsum) {
         __syncwarp();
         const float s = warp_sum(klsum);
         if (lane == 0) s_rowsum[r][warp] += s;
       }
     }
-    if (MODE == kBwd && !RAW && act) {
-      const long long pbase = static_cast<long long>(blockIdx.x) * p.K + k;
-      stg4(p.part_log_r + pbase, make_float4(col_lr[0], col_lr[1], col_lr[2], col_lr[3]));
-      if (p.part_b != nullptr) stg4(p.part_b + pbase, make_float4(col_b[0], col_b[1], col_b[2], col_b[3]));
+    __syncthreads();
+
+    // ---------------- phase B ----------------
+    const int n_parked = s_count;
+    if (MODE != kFwdHard) {
+      for (int i = warp; i < n_parked; i += kWarps) {
+        const int slot = s_list[i];
+        const int r = slot / kThreads, owner = slot % kThreads;
+        float rate[4], t0[4], acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rate[j] = s_tab[j][slot], t0[j] = s_tab[4 + j][slot], acc[j] = s_tab[8 + j][slot];
+        const long long base = (row0 + r) * p.K + k0 + 4 * owner;
+        const uint32_t quad = static_cast<uint32_t>(((p.row_offset + row0 + r) * p.K + k0 + 4 * owner) >> 2);
+        phase_b<MODE, IND>(p, quad, off_lo, off_hi, rate, t0, acc, lane);
+        if (MODE == kBwd) {
+          if (lane < 4) s_tab[8 + lane][slot] = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+        } else if (lane == 0) {
+          stg4(p.z + base, make_float4(acc[0], acc[1], acc[2], acc[3]));
+        }
+      }
     }
+    if (MODE == kBwd) {
+      __syncthreads();
+      // the owner finishes its parked quads (prologue recomputed: cheap next to a parked chain)
+      for (int r = 0; r < nrows; ++r) {
+        if (!((parked >> r) & 1u)) continue;
+        const long long base = (row0 + r) * p.K + k;
+        const float4 hv4 = ldg4(p.h + base);
+        const float hv[4] = {hv4.x, hv4.y, hv4.z, hv4.w};
+        Latent q[4];
+        float acc[4];
+        const int slot = r * kThreads + tid;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          q[j] = prologue<RAW, true>(p, hv[j], lr[j], bias[j]);
+          acc[j] = s_tab[8 + j][slot];
+        }
+        bwd_finish(base, q, acc);
+      }
+      if (!RAW && act) {
+        const long long pbase = static_cast<long long>(blockIdx.x) * p.K + k;
+        stg4(p.part_log_r + pbase, make_float4(col_lr[0], col_lr[1], col_lr[2], col_lr[3]));
+        if (p.part_b != nullptr) stg4(p.part_b + pbase, make_float4(col_b[0], col_b[1], col_b[2], col_b[3]));
+      }
+    }
+    __syncthreads();  // the table is reused by the next pass
   }
 
   if (MODE != kBwd) {
@@ -249,7 +374,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
       if (tid < nrows) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) s += s_rowsum[tid][w];
+        for (int w = 0; w < kWarps; ++w) s += s_rowsum[tid][w];
         p.kl_rowsum[row0 + tid] = s;
       }
     }
@@ -260,7 +385,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
       if (tid == 0) {
         float mm = s_max[0];
 #pragma unroll
-        for (int w = 1; w < kThreads / 32; ++w) mm = fmaxf(mm, s_max[w]);
+        for (int w = 1; w < kWarps; ++w) mm = fmaxf(mm, s_max[w]);
         atomicMax(reinterpret_cast<int*>(p.rate_max), __float_as_int(mm));  // rates are > 0
       }
     }
@@ -329,7 +454,7 @@ __global__ void __launch_bounds__(kThreads) kl_bwd_kernel(const float* __restric
   }
 }
 
-// ---- parity harness: dump the draws -------------------------------------------------------------
+// ---- parity harness: dump the draws; count mismatches of neg_log_unit against -logf --------------
 __global__ void debug_draws_kernel(float* U, float* E, long long B, long long K, long long row_offset, int n_exp,
                                    uint64_t offset, const uint64_t* offset_dev, const PhiloxKey ks) {
   uint64_t off = offset;
@@ -348,13 +473,22 @@ __global__ void debug_draws_kernel(float* U, float* E, long long B, long long K,
   }
 }
 
+__global__ void debug_log_check_kernel(unsigned long long* mismatches) {
+  unsigned long long bad = 0;
+  for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < (1u << 23); m += gridDim.x * blockDim.x) {
+    const float u = uniform_from_bits(m << 9);
+    if (__float_as_int(neg_log_unit(u)) != __float_as_int(-logf(u))) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
 // ---- host-side launch --------------------------------------------------------------------------
 static int rows_per_block_for(long long B) {
-  // enough blocks for several waves over 148 SMs, at most kMaxRowsPerBlock rows per block
-  const long long target_blocks = 148ll * 12;
+  // enough blocks for several waves over 148 SMs, at most kMaxRows rows per block
+  const long long target_blocks = 148ll * 8;
   long long r = B / target_blocks;
   if (r < 1) r = 1;
-  if (r > kMaxRowsPerBlock) r = kMaxRowsPerBlock;
+  if (r > kMaxRows) r = kMaxRows;
   return static_cast<int>(r);
 }
 
@@ -371,11 +505,29 @@ static cudaError_t launch_ind(const SamplerParams& p, int indicator, dim3 grid, 
   return cudaGetLastError();
 }
 
-static float resolve_exit(float exit_logit, int indicator, bool hard) {
-  if (exit_logit < 0.f) return -1.f;                       // never
-  if (hard) return 0.f;                                    // value unused, >= 0 enables the exit
-  if (exit_logit == 0.f) return indicator == kSigmoid ? 88.73f : 1.0f;  // lossless
-  return exit_logit;
+static int g_phase_a_events = 8;
+
+// Chain-control fields: temperature constants, early-exit threshold and the phase split.
+static void set_chain(SamplerParams& p, int n_exp, float temp, int indicator, float exit_logit) {
+  const bool hard = temp == 0.f;
+  p.n_exp = n_exp;
+  p.inv_temp = hard ? 0.f : 1.f / temp;
+  p.sig_a = hard ? 0.f : 1.4426950408889634f / temp;
+  const int split = g_phase_a_events < n_exp ? g_phase_a_events : n_exp;
+  if (hard) {  // sequential fp32 running sum (bit-exact against torch's CUDA cumsum)
+    p.t_exit = exit_logit < 0.f ? __builtin_inff() : 1.f;  // every later arrival is > 1 as well
+    p.phase_a = n_exp;
+  } else if (exit_logit < 0.f) {  // never: walk all n_exp events (same phase split, hence same bits)
+    p.t_exit = __builtin_inff();
+    p.phase_a = split;
+  } else {
+    // lossless: the reference's fp32 term is exactly 0 below this logit (sigmoid: exp(-l) overflows for
+    // l < -88.7228; finite-support indicators vanish for l <= -1); a hair of slack keeps the test
+    // t > t_exit on the safe side of the rounding of 1 + c * temp.
+    const float c = exit_logit == 0.f ? (indicator == kSigmoid ? 88.73f : 1.0f) : exit_logit;
+    p.t_exit = (1.f + c * temp) * (1.f + 4e-7f);
+    p.phase_a = split;
+  }
 }
 
 static int check_common(const char* fn, long long B, long long K, long long row_offset, int n_exp, float temp,
@@ -405,6 +557,12 @@ extern "C" int64_t pvae_num_partials(int64_t B) {
   return (B + r - 1) / r;
 }
 
+extern "C" int pvae_set_phase_a_events(int n) {
+  if (n < 1) return fail(PVAE_ERR_INVALID, "pvae_set_phase_a_events: n=%d must be >= 1", n);
+  g_phase_a_events = n;
+  return PVAE_OK;
+}
+
 extern "C" int pvae_sampler_fwd(const float* h, const float* log_r, const float* b_enc, float* z, float* log_dr,
                                 float* rate, float* kl, float* kl_rowsum, float* rate_max, int64_t B, int64_t K,
                                 int64_t row_offset, int n_exp, float temp, int indicator, int exc_only,
@@ -417,8 +575,7 @@ extern "C" int pvae_sampler_fwd(const float* h, const float* log_r, const float*
   p.h = h, p.log_r = log_r, p.b_enc = b_enc, p.z = z, p.log_dr = log_dr, p.rate = rate, p.kl = kl;
   p.kl_rowsum = kl_rowsum, p.rate_max = rate_max;
   p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = rows_per_block_for(B);
-  p.n_exp = n_exp, p.temp = temp, p.inv_temp = temp > 0.f ? 1.f / temp : 0.f;
-  p.exit_logit = resolve_exit(exit_logit, indicator, temp == 0.f);
+  set_chain(p, n_exp, temp, indicator, exit_logit);
   p.clamp_dr = 10.f, p.clamp_rate = 5.f, p.exc_only = exc_only;  // main/vae.py:403-409
   p.offset = offset, p.offset_dev = offset_dev;
   philox_key_schedule(seed, p.ks);
@@ -445,8 +602,7 @@ extern "C" int pvae_sampler_bwd(const float* h, const float* log_r, const float*
   const long long P = (B + p.rows_per_block - 1) / p.rows_per_block;
   p.part_log_r = partial_ws;
   p.part_b = g_b_enc ? partial_ws + P * K : nullptr;
-  p.n_exp = n_exp, p.temp = temp, p.inv_temp = 1.f / temp;
-  p.exit_logit = resolve_exit(exit_logit, indicator, false);
+  set_chain(p, n_exp, temp, indicator, exit_logit);
   p.clamp_dr = 10.f, p.clamp_rate = 5.f, p.exc_only = exc_only, p.kl_scale = kl_scale;
   p.offset = offset, p.offset_dev = offset_dev;
   philox_key_schedule(seed, p.ks);
@@ -467,8 +623,7 @@ extern "C" int pvae_rsample_fwd(const float* log_rate, float* z, float* rate, in
   SamplerParams p{};
   p.h = log_rate, p.z = z, p.rate = rate;
   p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = rows_per_block_for(B);
-  p.n_exp = n_exp, p.temp = temp, p.inv_temp = temp > 0.f ? 1.f / temp : 0.f;
-  p.exit_logit = resolve_exit(exit_logit, indicator, temp == 0.f);
+  set_chain(p, n_exp, temp, indicator, exit_logit);
   p.clamp_rate = clamp;
   p.offset = offset, p.offset_dev = offset_dev;
   philox_key_schedule(seed, p.ks);
@@ -489,8 +644,7 @@ extern "C" int pvae_rsample_bwd(const float* log_rate, const float* g_z, float* 
   SamplerParams p{};
   p.h = log_rate, p.g_z = g_z, p.g_h = g_log_rate;
   p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = rows_per_block_for(B);
-  p.n_exp = n_exp, p.temp = temp, p.inv_temp = 1.f / temp;
-  p.exit_logit = resolve_exit(exit_logit, indicator, false);
+  set_chain(p, n_exp, temp, indicator, exit_logit);
   p.clamp_rate = clamp;
   p.offset = offset, p.offset_dev = offset_dev;
   philox_key_schedule(seed, p.ks);
@@ -531,4 +685,10 @@ extern "C" int pvae_debug_draws(float* U, float* E, int64_t B, int64_t K, int64_
   const unsigned grid = static_cast<unsigned>(std::min<long long>((total + 255) / 256, 148ll * 32));
   debug_draws_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(U, E, B, K, row_offset, n_exp, offset, offset_dev, ks);
   return cuda_ok("pvae_debug_draws", cudaGetLastError());
+}
+
+extern "C" int pvae_debug_log_check(uint64_t* mismatches_dev, void* stream) {
+  if (!mismatches_dev) return fail(PVAE_ERR_INVALID, "pvae_debug_log_check: null pointer");
+  debug_log_check_kernel<<<148 * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long*>(mismatches_dev));
+  return cuda_ok("pvae_debug_log_check", cudaGetLastError());
 }

@@ -73,6 +73,39 @@ def test_draws_match_oracle_philox(lib):
     assert np.max(np.abs(E.cpu().numpy() - e_np) / np.maximum(e_np, 1e-30)) < 3e-7
 
 
+def test_fast_log_is_bit_identical_to_logf(lib):
+    """All 2^23 uniforms the generator can produce: the kernels' -log(u) equals libdevice's -logf(u)."""
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    assert lib.pvae_debug_log_check(P(bad), stream()) == 0
+    assert bad.item() == 0
+
+
+def test_phase_split_only_changes_summation_order(lib):
+    """Thread-per-quad (phase A) and warp-per-quad (phase B) walk the same chain: any split agrees with
+    the sequential oracle within the fp32 tolerance, and the sharded/unsharded launches stay bit-identical."""
+    rng = np.random.default_rng(21)
+    B, K, n_exp, seed, offset = 24, 256, 100, 3, 8
+    log_rate = dev(np.minimum(rng.normal(0.0, 2.5, size=(B, K)), 5.0).astype(np.float32))
+    _, E = draws(lib, B, K, n_exp, seed, offset)
+    gz = dev(rng.normal(size=(B, K)).astype(np.float32))
+    try:
+        for split in (1, 3, 8, 33, 1000):
+            assert lib.pvae_set_phase_a_events(split) == 0
+            for temp in (1.0, 0.05):
+                z, rate = rsample(lib, log_rate, n_exp, temp, "sigmoid", seed, offset, want_rate=True)
+                e, r = E.cpu().numpy(), rate.cpu().numpy()
+                assert_rel(z.cpu().numpy(), po.rsample(e, r, temp, "sigmoid"), what=f"z split={split}")
+                assert torch.equal(z, rsample(lib, log_rate, n_exp, temp, "sigmoid", seed, offset, exit_logit=NEVER))
+                g = rsample_bwd(lib, log_rate, gz, n_exp, temp, "sigmoid", seed, offset)
+                want = po.rsample_grad_log_rate(e.astype(np.float64), r.astype(np.float64), temp, "sigmoid")
+                assert_rel(g.cpu().numpy(), want * gz.cpu().numpy(), what=f"grad split={split}")
+                half = rsample(lib, log_rate[8:].contiguous(), n_exp, temp, "sigmoid", seed, offset, row_offset=8)
+                assert torch.equal(half, z[8:])
+        assert lib.pvae_set_phase_a_events(0) == -1
+    finally:
+        lib.pvae_set_phase_a_events(8)
+
+
 def test_offset_dev_is_added(lib):
     B, K, n_exp = 2, 8, 3
     U0, _ = draws(lib, B, K, n_exp, 5, 40)
