@@ -101,6 +101,21 @@ int pvae_kl_fwd(const float* log_dr, const float* log_r, float* kl, int64_t B, i
 int pvae_kl_bwd(const float* log_dr, const float* log_r, const float* g_kl, float* g_log_dr, float* g_log_r,
                 float* partial_ws, int accumulate, int64_t B, int64_t K, void* stream);
 
+/* ---- dense contractions on the tensor cores -------------------------------------------------
+ * C (M,N) = A' * B'^T with A' (M,Kd), B' (N,Kd); fp32 in HBM, TF32 tcgen05.mma, fp32 accumulation in TMEM.
+ * a_kmajor != 0: A is stored (M,Kd) row-major; a_kmajor == 0: A is stored (Kd,M) row-major (same for B/N),
+ * so no transposed copy is ever made.  Replaces F.linear in Linear.forward base/common.py:409-414 as used by
+ * fc_enc (main/vae.py:51) and fc_dec (main/vae.py:59-60), and the dgrad / wgrad GEMMs autograd derives:
+ *   forward  y = x W^T      : A = x (kmajor), B = W (kmajor)
+ *   dgrad    g_x = g_y W    : A = g_y (kmajor), B = W (Kd = out features, stored (Kd,N) -> b_kmajor = 0)
+ *   wgrad    g_W = g_y^T x  : A = g_y (stored (Kd = batch, M) -> a_kmajor = 0), B = x (b_kmajor = 0)
+ * M, N, Kd must be multiples of 4 and pointers 16-byte aligned.  splits > 1 cuts Kd into that many
+ * ranges (one CTA each) whose partial tiles are summed in a fixed order; splitk_ws then needs
+ * pvae_gemm_ws_floats(M, N, splits) floats. */
+int64_t pvae_gemm_ws_floats(int64_t M, int64_t N, int splits);
+int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t Kd, int a_kmajor, int b_kmajor,
+                   int splits, float* splitk_ws, void* stream);
+
 /* ---- training-step pieces around the sampler and the GEMMs -----------------------------------
  * pvae_recon_residual: BaseVAE.loss_recon main/vae.py:68-72 and its gradient in one pass:
  *   recon (B) = sum_d (y - x)^2,  g_y (B,D) = g_scale * (y - x)  (g_scale = 2 / B_global is

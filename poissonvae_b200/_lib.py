@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpvae_b200.so")
-SOURCES = ["capi.cu", "sampler.cu", "step.cu"]
+SOURCES = ["capi.cu", "sampler.cu", "step.cu", "gemm_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -26,7 +26,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs + ["-lcuda"]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
@@ -47,6 +47,8 @@ _SIGNATURES = {
     "pvae_rsample_bwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i, _f, _i, _f, _f, _u64, _u64, _p, _p]),
     "pvae_kl_fwd": (_i, [_p, _p, _p, _i64, _i64, _p]),
     "pvae_kl_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _i64, _p]),
+    "pvae_gemm_ws_floats": (_i64, [_i64, _i64, _i]),
+    "pvae_gemm_tf32": (_i, [_p, _p, _p, _i64, _i64, _i64, _i, _i, _i, _p, _p]),
     "pvae_recon_residual": (_i, [_p, _p, _p, _p, _i64, _i64, _f, _p]),
     "pvae_loss_assemble": (_i, [_p, _p, _p, _i64, _f, _i64, _p]),
     "pvae_grad_norm_ws_floats": (_i64, []),

@@ -1,0 +1,356 @@
+// Dense contractions of the lin|lin P-VAE on the 5th-generation tensor cores (sm_100a):
+//   C (M,N) = op(A) * op(B)^T-like products, fp32 in HBM, TF32 tcgen05.mma, fp32 accumulators in TMEM.
+//
+// One 128 x BN output tile per CTA (optionally one K-split of it), warp-specialised:
+//   warp 0      TMA producer     cp.async.bulk.tensor (128B swizzle) into a 4-stage smem ring
+//   warp 1      MMA issuer       one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) and
+//                                commits to the ring's "empty" barriers / the accumulator-full barrier
+//   warps 2-5   epilogue         tcgen05.ld of the accumulator (32 lanes x 32 columns per instruction),
+//                                128-byte row segments stored straight to global memory
+// Both operand majors are supported without any transposed copy in HBM: a K-major operand is a
+// (rows, Kd) row-major matrix loaded as one {32 x 128} box per stage; an MN-major operand is a (Kd, rows)
+// row-major matrix loaded as BN/32 (or 4) {32 x 32} boxes whose 1024-byte swizzle atoms are walked along
+// K by the UMMA descriptor.  That covers forward (x W^T), dgrad (g W) and wgrad (g^T x) of a linear layer.
+//
+// Replaces: F.linear in Linear.forward base/common.py:409-414 (fc_enc main/vae.py:51, fc_dec :59-60)
+// and the three GEMMs autograd derives from each of them.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "../../include/pvae_b200.h"
+#include "pvae_host.h"
+
+namespace pvae {
+
+constexpr int kBM = 128;       // output rows per CTA  (= UMMA M, one TMEM lane per row)
+constexpr int kBK = 32;        // K elements per stage (32 fp32 = one 128-byte swizzle row)
+constexpr int kStages = 4;
+constexpr int kGemmThreads = 192;
+constexpr int kUmmaK = 8;      // K per tcgen05.mma for 32-bit operands
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor (tcgen05): start address, leading / stride byte offsets (16-byte units),
+// descriptor version 1, 128-byte swizzle.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // version
+  d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor: D fp32, A/B tf32, majors, N >> 3, M >> 4.
+__host__ __device__ inline uint32_t make_idesc(int m, int n, bool a_mn_major, bool b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;   // c_format = F32
+  d |= 2u << 7;   // a_format = TF32
+  d |= 2u << 10;  // b_format = TF32
+  d |= (a_mn_major ? 1u : 0u) << 15;
+  d |= (b_mn_major ? 1u : 0u) << 16;
+  d |= static_cast<uint32_t>(n >> 3) << 17;
+  d |= static_cast<uint32_t>(m >> 4) << 24;
+  return d;
+}
+
+struct GemmParams {
+  float* C;              // (M,N) row-major, or the split-K workspace (splits, M, N)
+  int M, N, Kd;
+  int k_per_split;       // multiple of kBK
+  int a_kmajor, b_kmajor;
+  long long split_stride;  // M * N when splits > 1
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+  constexpr uint32_t kABytes = kBM * kBK * 4;  // 16 KB
+  constexpr uint32_t kBBytes = BN * kBK * 4;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* accum_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+  const int k_begin = blockIdx.z * p.k_per_split;
+  const int k_end = min(p.Kd, k_begin + p.k_per_split);
+  const int num_kb = (k_end - k_begin + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: BN fp32 accumulator columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t round = kb / kStages;
+        mbar_wait(&empty_bar[s], (round & 1) ^ 1);
+        uint8_t* sa = smem + s * kStageBytes;
+        uint8_t* sb = sa + kABytes;
+        mbar_expect_tx(&full_bar[s], kStageBytes);
+        const int k0 = k_begin + kb * kBK;
+        if (p.a_kmajor) {
+          tma_load_2d(&tma_a, &full_bar[s], sa, k0, m0);  // box {32 k, 128 rows}
+        } else {
+#pragma unroll
+          for (int i = 0; i < kBM / 32; ++i) tma_load_2d(&tma_a, &full_bar[s], sa + i * 4096, m0 + 32 * i, k0);  // {32 m, 32 k}
+        }
+        if (p.b_kmajor) {
+          tma_load_2d(&tma_b, &full_bar[s], sb, k0, n0);  // box {32 k, BN rows}
+        } else {
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i) tma_load_2d(&tma_b, &full_bar[s], sb + i * 4096, n0 + 32 * i, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kBM, BN, !p.a_kmajor, !p.b_kmajor);
+      // K-major: 8-row groups 1024 B apart, K advances 32 B inside the swizzle row.
+      // MN-major: 32-wide slabs 4096 B apart (LBO), 8-deep K atoms 1024 B apart (SBO), K advances by one atom.
+      const uint32_t a_lbo = p.a_kmajor ? 16 : 4096, b_lbo = p.b_kmajor ? 16 : 4096;
+      const uint32_t a_step = p.a_kmajor ? kUmmaK * 4 : 1024, b_step = p.b_kmajor ? kUmmaK * 4 : 1024;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t round = kb / kStages;
+        mbar_wait(&full_bar[s], round & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem + s * kStageBytes), sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          const uint64_t da = make_smem_desc(sa + k * a_step, a_lbo, 1024);
+          const uint64_t db = make_smem_desc(sb + k * b_step, b_lbo, 1024);
+          umma_tf32(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(accum_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    mbar_wait(accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quarter = warp & 3;  // a warp may only read TMEM lanes [32 * (warp % 4), +32)
+    const int m = m0 + quarter * 32 + lane;
+    float* crow = p.C + static_cast<long long>(blockIdx.z) * p.split_stride + static_cast<long long>(m) * p.N;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (m < p.M) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + c0 + j;
+          if (n < p.N)  // N is a multiple of 4
+            *reinterpret_cast<float4*>(crow + n) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+  }
+}
+
+// fixed-order sum of the split-K partials
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, long long n4,
+                                                            int splits) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += gridDim.x * 256ll) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(ws) + i);
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ws) + s * n4 + i);
+      a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+    }
+    reinterpret_cast<float4*>(C)[i] = a;
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &st) == cudaSuccess &&
+        st == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// 2-D fp32 row-major (rows, cols) tensor, box {box_cols (inner), box_rows}, 128-byte swizzle, OOB = 0.
+static int make_map(CUtensorMap* out, const float* base, long long rows, long long cols, int box_cols, int box_rows) {
+  typedef std::tuple<const void*, long long, long long, int, int> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  const Key key(base, rows, cols, box_cols, box_rows);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return PVAE_OK;
+  }
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(PVAE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 4};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return fail(PVAE_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(rc));
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *out;
+  return PVAE_OK;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int splits, cudaStream_t s) {
+  constexpr int smem = kStages * (kBM * kBK * 4 + BN * kBK * 4) + 1024 + 128;
+  static bool configured = false;
+  if (!configured) {
+    if (int rc = cuda_ok("cudaFuncSetAttribute", cudaFuncSetAttribute(gemm_tf32_kernel<BN>,
+                                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem)))
+      return rc;
+    configured = true;
+  }
+  dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, splits);
+  gemm_tf32_kernel<BN><<<grid, kGemmThreads, smem, s>>>(ma, mb, p);
+  return cuda_ok("gemm_tf32_kernel", cudaGetLastError());
+}
+
+}  // namespace pvae
+
+using namespace pvae;
+
+extern "C" int64_t pvae_gemm_ws_floats(int64_t M, int64_t N, int splits) { return splits > 1 ? splits * M * N : 0; }
+
+extern "C" int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t Kd, int a_kmajor,
+                              int b_kmajor, int splits, float* splitk_ws, void* stream) {
+  if (M <= 0 || N <= 0 || Kd <= 0) return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)Kd);
+  if (M % 4 || N % 4 || Kd % 4)
+    return fail(PVAE_ERR_UNSUPPORTED, "pvae_gemm_tf32: M=%lld N=%lld K=%lld must be multiples of 4 (16-byte TMA strides)",
+                (long long)M, (long long)N, (long long)Kd);
+  if (!A || !B || !C) return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: null pointer");
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15)
+    return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: pointers must be 16-byte aligned");
+  if (splits < 1) splits = 1;
+  const long long kblocks = (Kd + kBK - 1) / kBK;
+  if (splits > kblocks) splits = static_cast<int>(kblocks);
+  if (splits > 1 && !splitk_ws) return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: split-K needs a workspace");
+  {  // every split must own at least one K block
+    const long long per = (kblocks + splits - 1) / splits;
+    splits = static_cast<int>((kblocks + per - 1) / per);
+  }
+  // 128-wide tiles unless that leaves most of the 148 SMs without a CTA
+  const int BN = (N <= 64 || ((N + 127) / 128) * ((M + kBM - 1) / kBM) * splits < 96) ? 64 : 128;
+  CUtensorMap ma, mb;
+  // K-major operand: (rows, Kd) row-major, box {32 k, rows_per_tile}; MN-major: (Kd, rows) row-major, box {32 rows, 32 k}
+  if (int rc = a_kmajor ? make_map(&ma, A, M, Kd, kBK, kBM) : make_map(&ma, A, Kd, M, 32, kBK)) return rc;
+  if (int rc = b_kmajor ? make_map(&mb, B, N, Kd, kBK, BN) : make_map(&mb, B, Kd, N, 32, kBK)) return rc;
+  GemmParams p;
+  p.C = splits > 1 ? splitk_ws : C;
+  p.M = static_cast<int>(M), p.N = static_cast<int>(N), p.Kd = static_cast<int>(Kd);
+  p.k_per_split = static_cast<int>(((kblocks + splits - 1) / splits) * kBK);
+  p.a_kmajor = a_kmajor, p.b_kmajor = b_kmajor;
+  p.split_stride = splits > 1 ? M * N : 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = BN == 64 ? launch_gemm<64>(ma, mb, p, splits, s) : launch_gemm<128>(ma, mb, p, splits, s)) return rc;
+  if (splits > 1) {
+    const long long n4 = M * N / 4;
+    const unsigned grid = static_cast<unsigned>(std::min<long long>((n4 + 255) / 256, 148ll * 8));
+    splitk_reduce_kernel<<<grid, 256, 0, s>>>(splitk_ws, C, n4, splits);
+    return cuda_ok("splitk_reduce_kernel", cudaGetLastError());
+  }
+  return PVAE_OK;
+}

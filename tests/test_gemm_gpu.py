@@ -1,0 +1,83 @@
+"""GPU: the tcgen05 / TMEM / TMA GEMM (pvae_gemm_tf32) for every operand-major combination the
+lin|lin P-VAE needs (forward, dgrad, wgrad), ragged sizes and split-K."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from poissonvae_b200 import _lib
+    return _lib.load()
+
+
+def run(lib, A, B, M, N, Kd, a_k, b_k, splits=1):
+    C = torch.full((M, N), float("nan"), device="cuda")
+    ws = torch.empty(max(1, lib.pvae_gemm_ws_floats(M, N, splits)), device="cuda")
+    rc = lib.pvae_gemm_tf32(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, Kd, a_k, b_k, splits, ws.data_ptr(),
+                            torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.pvae_last_error()
+    torch.cuda.synchronize()
+    return C
+
+
+def operands(M, N, Kd, a_k, b_k, gen, integers):
+    if integers:
+        A2 = torch.randint(-4, 5, (M, Kd), device="cuda", generator=gen).float()
+        B2 = torch.randint(-4, 5, (N, Kd), device="cuda", generator=gen).float()
+    else:
+        A2 = torch.randn(M, Kd, device="cuda", generator=gen)
+        B2 = torch.randn(N, Kd, device="cuda", generator=gen)
+    A = A2 if a_k else A2.t().contiguous()  # stored (Kd, M) when MN-major
+    B = B2 if b_k else B2.t().contiguous()
+    return A2, B2, A, B
+
+
+SHAPES = [(128, 128, 32), (128, 64, 64), (4096, 512, 256), (4096, 256, 512), (12, 64, 256), (520, 136, 100),
+          (256, 512, 1024), (8, 128, 4)]
+
+
+@pytest.mark.parametrize("majors", [(1, 1), (1, 0), (0, 0), (0, 1)])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_exact_on_tf32_representable_inputs(lib, majors, shape):
+    """Small integers are exact in TF32 and the sums stay below 2^24: any layout / descriptor mistake shows."""
+    M, N, Kd = shape
+    gen = torch.Generator("cuda").manual_seed(M + N + Kd)
+    A2, B2, A, B = operands(M, N, Kd, *majors, gen, integers=True)
+    C = run(lib, A, B, M, N, Kd, *majors)
+    assert torch.equal(C, (A2.double() @ B2.double().t()).float())
+
+
+@pytest.mark.parametrize("majors", [(1, 1), (1, 0), (0, 0)])
+def test_tf32_error_bound(lib, majors):
+    M, N, Kd = 1024, 512, 256
+    gen = torch.Generator("cuda").manual_seed(5)
+    A2, B2, A, B = operands(M, N, Kd, *majors, gen, integers=False)
+    C = run(lib, A, B, M, N, Kd, *majors)
+    ref = A2.double() @ B2.double().t()
+    bound = 2.0 ** -10 * (A2.abs().double() @ B2.abs().double().t())  # operands truncated to 10 mantissa bits
+    assert ((C.double() - ref).abs() <= bound).all()
+    rel = ((C.double() - ref).norm() / ref.norm()).item()
+    assert rel < 1e-3, rel
+
+
+@pytest.mark.parametrize("splits", [2, 16, 64])
+def test_split_k_wgrad_shape(lib, splits):
+    """wgrad: g_W (256, 512) = g_y^T z over a batch of 4096, both operands stored batch-major (MN-major)."""
+    M, N, Kd = 256, 512, 4096
+    gen = torch.Generator("cuda").manual_seed(splits)
+    A2, B2, A, B = operands(M, N, Kd, 0, 0, gen, integers=True)
+    C = run(lib, A, B, M, N, Kd, 0, 0, splits)
+    assert torch.equal(C, (A2.double() @ B2.double().t()).float())
+    C1 = run(lib, A, B, M, N, Kd, 0, 0, splits)
+    assert torch.equal(C, C1)  # fixed-order reduction: deterministic
+
+
+def test_argument_checks(lib):
+    t = torch.zeros(64, 64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    assert lib.pvae_gemm_tf32(t.data_ptr(), t.data_ptr(), t.data_ptr(), 64, 64, 6, 1, 1, 1, None, s) == -2
+    assert lib.pvae_gemm_tf32(None, t.data_ptr(), t.data_ptr(), 64, 64, 64, 1, 1, 1, None, s) == -1
+    assert lib.pvae_gemm_tf32(t.data_ptr(), t.data_ptr(), t.data_ptr(), 64, 64, 64, 1, 1, 4, None, s) == -1  # no workspace
