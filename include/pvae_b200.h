@@ -103,6 +103,9 @@ int pvae_kl_bwd(const float* log_dr, const float* log_r, const float* g_kl, floa
 
 /* ---- dense contractions on the tensor cores -------------------------------------------------
  * C (M,N) = A' * B'^T with A' (M,Kd), B' (N,Kd); fp32 in HBM, TF32 tcgen05.mma, fp32 accumulation in TMEM.
+ * precise != 0 ("3xTF32"): every operand is split in shared memory into its TF32-representable part and the
+ * exact remainder and hi*hi + lo*hi + hi*lo is accumulated - products good to ~2^-22, i.e. fp32-grade;
+ * precise == 0: single pass, operands cut to 10 mantissa bits (relative error up to 2^-10 per product).
  * a_kmajor != 0: A is stored (M,Kd) row-major; a_kmajor == 0: A is stored (Kd,M) row-major (same for B/N),
  * so no transposed copy is ever made.  Replaces F.linear in Linear.forward base/common.py:409-414 as used by
  * fc_enc (main/vae.py:51) and fc_dec (main/vae.py:59-60), and the dgrad / wgrad GEMMs autograd derives:
@@ -114,7 +117,7 @@ int pvae_kl_bwd(const float* log_dr, const float* log_r, const float* g_kl, floa
  * pvae_gemm_ws_floats(M, N, splits) floats. */
 int64_t pvae_gemm_ws_floats(int64_t M, int64_t N, int splits);
 int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t Kd, int a_kmajor, int b_kmajor,
-                   int splits, float* splitk_ws, void* stream);
+                   int precise, int splits, float* splitk_ws, void* stream);
 
 /* ---- training-step pieces around the sampler and the GEMMs -----------------------------------
  * pvae_recon_residual: BaseVAE.loss_recon main/vae.py:68-72 and its gradient in one pass:

@@ -48,7 +48,7 @@ _SIGNATURES = {
     "pvae_kl_fwd": (_i, [_p, _p, _p, _i64, _i64, _p]),
     "pvae_kl_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _i64, _p]),
     "pvae_gemm_ws_floats": (_i64, [_i64, _i64, _i]),
-    "pvae_gemm_tf32": (_i, [_p, _p, _p, _i64, _i64, _i64, _i, _i, _i, _p, _p]),
+    "pvae_gemm_tf32": (_i, [_p, _p, _p, _i64, _i64, _i64, _i, _i, _i, _i, _p, _p]),
     "pvae_recon_residual": (_i, [_p, _p, _p, _p, _i64, _i64, _f, _p]),
     "pvae_loss_assemble": (_i, [_p, _p, _p, _i64, _f, _i64, _p]),
     "pvae_grad_norm_ws_floats": (_i64, []),

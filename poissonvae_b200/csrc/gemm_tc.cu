@@ -7,6 +7,10 @@
 //                                commits to the ring's "empty" barriers / the accumulator-full barrier
 //   warps 2-5   epilogue         tcgen05.ld of the accumulator (32 lanes x 32 columns per instruction),
 //                                128-byte row segments stored straight to global memory
+// Precision.  kind::tf32 reads 10 mantissa bits of each operand.  In the default "3xTF32" mode the four
+// epilogue warps first split every landed stage in place into hi = the TF32-representable part and
+// lo = x - hi (exact), and the issuer accumulates hi*hi + lo*hi + hi*lo: the dropped lo*lo term and the
+// rounding of lo are ~2^-22 relative, i.e. fp32-grade products with fp32 accumulation in TMEM.
 // Both operand majors are supported without any transposed copy in HBM: a K-major operand is a
 // (rows, Kd) row-major matrix loaded as one {32 x 128} box per stage; an MN-major operand is a (Kd, rows)
 // row-major matrix loaded as BN/32 (or 4) {32 x 32} boxes whose 1024-byte swizzle atoms are walked along
@@ -29,7 +33,6 @@ namespace pvae {
 
 constexpr int kBM = 128;       // output rows per CTA  (= UMMA M, one TMEM lane per row)
 constexpr int kBK = 32;        // K elements per stage (32 fp32 = one 128-byte swizzle row)
-constexpr int kStages = 4;
 constexpr int kGemmThreads = 192;
 constexpr int kUmmaK = 8;      // K per tcgen05.mma for 32-bit operands
 
@@ -76,14 +79,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 }
 
 // Shared-memory matrix descriptor (tcgen05): start address, leading / stride byte offsets (16-byte units),
-// descriptor version 1, 128-byte swizzle.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// descriptor version 1, swizzle mode (2 = SWIZZLE_128B with 16-byte atoms, 1 = SWIZZLE_128B with 32-byte
+// atoms - the only layout the hardware accepts for MN-major 32-bit operands).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;  // version
-  d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
+  d |= static_cast<uint64_t>(layout) << 61;
   return d;
 }
 
@@ -108,17 +112,28 @@ struct GemmParams {
   long long split_stride;  // M * N when splits > 1
 };
 
-template <int BN>
+template <int BN, bool SPLIT>
+struct GemmCfg {
+  static constexpr uint32_t kABytes = kBM * kBK * 4;  // 16 KB
+  static constexpr uint32_t kBBytes = BN * kBK * 4;
+  static constexpr uint32_t kTileBytes = kABytes + kBBytes;             // what TMA writes per stage
+  static constexpr uint32_t kStageBytes = SPLIT ? 2 * kTileBytes : kTileBytes;  // + the lo planes
+  static constexpr int kStages = SPLIT ? (BN == 128 ? 3 : 4) : 4;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
-  constexpr uint32_t kABytes = kBM * kBK * 4;  // 16 KB
-  constexpr uint32_t kBBytes = BN * kBK * 4;
-  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  using Cfg = GemmCfg<BN, SPLIT>;
+  constexpr uint32_t kABytes = Cfg::kABytes, kTileBytes = Cfg::kTileBytes, kStageBytes = Cfg::kStageBytes;
+  constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* accum_bar = empty_bar + kStages;
+  uint64_t* conv_bar = empty_bar + kStages;
+  uint64_t* accum_bar = conv_bar + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -133,6 +148,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&conv_bar[s], kGemmThreads - 64);
     }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -155,7 +171,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         mbar_wait(&empty_bar[s], (round & 1) ^ 1);
         uint8_t* sa = smem + s * kStageBytes;
         uint8_t* sb = sa + kABytes;
-        mbar_expect_tx(&full_bar[s], kStageBytes);
+        mbar_expect_tx(&full_bar[s], kTileBytes);
         const int k0 = k_begin + kb * kBK;
         if (p.a_kmajor) {
           tma_load_2d(&tma_a, &full_bar[s], sa, k0, m0);  // box {32 k, 128 rows}
@@ -175,27 +191,60 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(kBM, BN, !p.a_kmajor, !p.b_kmajor);
-      // K-major: 8-row groups 1024 B apart, K advances 32 B inside the swizzle row.
-      // MN-major: 32-wide slabs 4096 B apart (LBO), 8-deep K atoms 1024 B apart (SBO), K advances by one atom.
+      // K-major (SWIZZLE_128B): 8-row groups 1024 B apart (SBO), K advances 32 B inside the swizzle row.
+      // MN-major (SWIZZLE_128B, 32-byte atoms): 32-wide slabs 4096 B apart (LBO), 4-deep K groups 512 B
+      // apart (SBO), one MMA (K = 8) spans two of them, K advances 1024 B.
       const uint32_t a_lbo = p.a_kmajor ? 16 : 4096, b_lbo = p.b_kmajor ? 16 : 4096;
+      const uint32_t a_sbo = p.a_kmajor ? 1024 : 512, b_sbo = p.b_kmajor ? 1024 : 512;
+      const uint32_t a_lay = p.a_kmajor ? 2 : 1, b_lay = p.b_kmajor ? 2 : 1;
       const uint32_t a_step = p.a_kmajor ? kUmmaK * 4 : 1024, b_step = p.b_kmajor ? kUmmaK * 4 : 1024;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t round = kb / kStages;
-        mbar_wait(&full_bar[s], round & 1);
+        mbar_wait(SPLIT ? &conv_bar[s] : &full_bar[s], round & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_u32(smem + s * kStageBytes), sb = sa + kABytes;
 #pragma unroll
         for (int k = 0; k < kBK / kUmmaK; ++k) {
-          const uint64_t da = make_smem_desc(sa + k * a_step, a_lbo, 1024);
-          const uint64_t db = make_smem_desc(sb + k * b_step, b_lbo, 1024);
+          const uint64_t da = make_smem_desc(sa + k * a_step, a_lbo, a_sbo, a_lay);
+          const uint64_t db = make_smem_desc(sb + k * b_step, b_lbo, b_sbo, b_lay);
           umma_tf32(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          if (SPLIT) {  // + lo(A) hi(B) + hi(A) lo(B); the lo planes sit kTileBytes above the hi planes
+            const uint64_t dal = make_smem_desc(sa + kTileBytes + k * a_step, a_lbo, a_sbo, a_lay);
+            const uint64_t dbl = make_smem_desc(sb + kTileBytes + k * b_step, b_lbo, b_sbo, b_lay);
+            umma_tf32(tmem_base, dal, db, idesc, 1u);
+            umma_tf32(tmem_base, da, dbl, idesc, 1u);
+          }
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
       }
       umma_commit(accum_bar);  // accumulator complete
     }
   } else {
+    if (SPLIT) {
+      // ===== operand splitter: hi = TF32-representable part (in place), lo = x - hi (second plane) =====
+      const int ct = threadIdx.x - 64;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(&full_bar[s], (kb / kStages) & 1);
+        uint4* tile = reinterpret_cast<uint4*>(smem + s * kStageBytes);
+        uint4* tile_lo = reinterpret_cast<uint4*>(smem + s * kStageBytes + kTileBytes);
+#pragma unroll 4
+        for (int i = ct; i < static_cast<int>(kTileBytes / 16); i += kGemmThreads - 64) {
+          const uint4 v = tile[i];
+          uint4 hi, lo;
+          hi.x = v.x & 0xFFFFE000u, hi.y = v.y & 0xFFFFE000u, hi.z = v.z & 0xFFFFE000u, hi.w = v.w & 0xFFFFE000u;
+          lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(hi.x));
+          lo.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(hi.y));
+          lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(hi.z));
+          lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(hi.w));
+          tile[i] = hi;
+          tile_lo[i] = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core reads
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv_bar[s])) : "memory");
+      }
+    }
     // ===== epilogue: TMEM -> registers -> global =====
     mbar_wait(accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -267,8 +316,11 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// 2-D fp32 row-major (rows, cols) tensor, box {box_cols (inner), box_rows}, 128-byte swizzle, OOB = 0.
-static int make_map(CUtensorMap* out, const float* base, long long rows, long long cols, int box_cols, int box_rows) {
+// 2-D fp32 row-major (rows, cols) tensor, box {box_cols (inner), box_rows}, 128-byte swizzle with 16-byte
+// atoms (K-major operands) or 32-byte atoms (MN-major operands), OOB = 0.
+static int make_map(CUtensorMap* out, const float* base, long long rows, long long cols, int box_cols, int box_rows,
+                    bool atom32 = false) {
+  if (atom32) box_rows = -box_rows;  // distinct cache key
   typedef std::tuple<const void*, long long, long long, int, int> Key;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
@@ -283,10 +335,11 @@ static int make_map(CUtensorMap* out, const float* base, long long rows, long lo
   if (!fn) return fail(PVAE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 4};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(atom32 ? -box_rows : box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) return fail(PVAE_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(rc));
   if (cache.size() > 4096) cache.clear();
@@ -294,18 +347,18 @@ static int make_map(CUtensorMap* out, const float* base, long long rows, long lo
   return PVAE_OK;
 }
 
-template <int BN>
+template <int BN, bool SPLIT>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int splits, cudaStream_t s) {
-  constexpr int smem = kStages * (kBM * kBK * 4 + BN * kBK * 4) + 1024 + 128;
+  constexpr int smem = GemmCfg<BN, SPLIT>::kSmem;
   static bool configured = false;
   if (!configured) {
-    if (int rc = cuda_ok("cudaFuncSetAttribute", cudaFuncSetAttribute(gemm_tf32_kernel<BN>,
+    if (int rc = cuda_ok("cudaFuncSetAttribute", cudaFuncSetAttribute(gemm_tf32_kernel<BN, SPLIT>,
                                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem)))
       return rc;
     configured = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, splits);
-  gemm_tf32_kernel<BN><<<grid, kGemmThreads, smem, s>>>(ma, mb, p);
+  gemm_tf32_kernel<BN, SPLIT><<<grid, kGemmThreads, smem, s>>>(ma, mb, p);
   return cuda_ok("gemm_tf32_kernel", cudaGetLastError());
 }
 
@@ -316,7 +369,7 @@ using namespace pvae;
 extern "C" int64_t pvae_gemm_ws_floats(int64_t M, int64_t N, int splits) { return splits > 1 ? splits * M * N : 0; }
 
 extern "C" int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t Kd, int a_kmajor,
-                              int b_kmajor, int splits, float* splitk_ws, void* stream) {
+                              int b_kmajor, int precise, int splits, float* splitk_ws, void* stream) {
   if (M <= 0 || N <= 0 || Kd <= 0) return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)Kd);
   if (M % 4 || N % 4 || Kd % 4)
     return fail(PVAE_ERR_UNSUPPORTED, "pvae_gemm_tf32: M=%lld N=%lld K=%lld must be multiples of 4 (16-byte TMA strides)",
@@ -336,8 +389,8 @@ extern "C" int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t 
   const int BN = (N <= 64 || ((N + 127) / 128) * ((M + kBM - 1) / kBM) * splits < 96) ? 64 : 128;
   CUtensorMap ma, mb;
   // K-major operand: (rows, Kd) row-major, box {32 k, rows_per_tile}; MN-major: (Kd, rows) row-major, box {32 rows, 32 k}
-  if (int rc = a_kmajor ? make_map(&ma, A, M, Kd, kBK, kBM) : make_map(&ma, A, Kd, M, 32, kBK)) return rc;
-  if (int rc = b_kmajor ? make_map(&mb, B, N, Kd, kBK, BN) : make_map(&mb, B, Kd, N, 32, kBK)) return rc;
+  if (int rc = a_kmajor ? make_map(&ma, A, M, Kd, kBK, kBM) : make_map(&ma, A, Kd, M, 32, kBK, true)) return rc;
+  if (int rc = b_kmajor ? make_map(&mb, B, N, Kd, kBK, BN) : make_map(&mb, B, Kd, N, 32, kBK, true)) return rc;
   GemmParams p;
   p.C = splits > 1 ? splitk_ws : C;
   p.M = static_cast<int>(M), p.N = static_cast<int>(N), p.Kd = static_cast<int>(Kd);
@@ -345,7 +398,10 @@ extern "C" int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t 
   p.a_kmajor = a_kmajor, p.b_kmajor = b_kmajor;
   p.split_stride = splits > 1 ? M * N : 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (int rc = BN == 64 ? launch_gemm<64>(ma, mb, p, splits, s) : launch_gemm<128>(ma, mb, p, splits, s)) return rc;
+  int rc;
+  if (precise) rc = BN == 64 ? launch_gemm<64, true>(ma, mb, p, splits, s) : launch_gemm<128, true>(ma, mb, p, splits, s);
+  else rc = BN == 64 ? launch_gemm<64, false>(ma, mb, p, splits, s) : launch_gemm<128, false>(ma, mb, p, splits, s);
+  if (rc) return rc;
   if (splits > 1) {
     const long long n4 = M * N / 4;
     const unsigned grid = static_cast<unsigned>(std::min<long long>((n4 + 255) / 256, 148ll * 8));

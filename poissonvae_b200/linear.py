@@ -1,27 +1,86 @@
 """Dense contractions of the lin|lin P-VAE (fc_enc main/vae.py:51, fc_dec main/vae.py:59-60 via
-base/common.py:409-414) and of their backward (dgrad / wgrad)."""
+base/common.py:409-414) and of their backward (dgrad / wgrad), on the tcgen05 / TMEM / TMA GEMM
+(csrc/gemm_tc.cu, pvae_gemm_tf32 in include/pvae_b200.h).  fp32 tensors in HBM, no transposed copies."""
 from __future__ import annotations
 
 import torch
-from torch.nn import functional as F
 
-# TODO(round 1): route these through the tcgen05 GEMM in csrc/gemm_tc.cu
+from . import _lib
+
+# 3xTF32 operand splitting (fp32-grade products).  False = single-pass TF32 (10-bit operands).
+PRECISE = True
+
+_ws_cache = {}
+
+
+def _splits_for(m: int, n: int, kd: int) -> int:
+    """Split the reduction when the output has too few 128x128 tiles to occupy the 148 SMs (wgrad)."""
+    tiles = ((m + 127) // 128) * ((n + 127) // 128)
+    if tiles >= 64 or kd < 512:
+        return 1
+    return max(1, min(128 // tiles, kd // 256))
+
+
+def _gemm(a, b, out, m, n, kd, a_kmajor, b_kmajor):
+    for t, name in ((a, "a"), (b, "b"), (out, "out")):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError(f"gemm operand {name} must be a contiguous CUDA float32 tensor (no CPU path)")
+    lib = _lib.load()
+    splits = _splits_for(m, n, kd)
+    ws = None
+    if splits > 1:
+        key = (a.device, m, n, splits)
+        ws = _ws_cache.get(key)
+        if ws is None:
+            ws = _ws_cache[key] = torch.empty(lib.pvae_gemm_ws_floats(m, n, splits), device=a.device, dtype=torch.float32)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.pvae_gemm_tf32(a.data_ptr(), b.data_ptr(), out.data_ptr(), m, n, kd, a_kmajor, b_kmajor,
+                                      int(PRECISE), splits, None if ws is None else ws.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """out (M,N) = a (M,K) @ b (N,K)^T  - linear forward"""
+    m, kd = a.shape
+    n = b.shape[0]
+    out = torch.empty(m, n, device=a.device, dtype=torch.float32) if out is None else out
+    return _gemm(a, b, out, m, n, kd, 1, 1)
+
+
+def gemm_nn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """out (M,N) = a (M,K) @ b (K,N)  - dgrad"""
+    m, kd = a.shape
+    n = b.shape[1]
+    out = torch.empty(m, n, device=a.device, dtype=torch.float32) if out is None else out
+    return _gemm(a, b, out, m, n, kd, 1, 0)
+
+
+def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """out (M,N) = a (K,M)^T @ b (K,N)  - wgrad"""
+    kd, m = a.shape
+    n = b.shape[1]
+    out = torch.empty(m, n, device=a.device, dtype=torch.float32) if out is None else out
+    return _gemm(a, b, out, m, n, kd, 0, 0)
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight):
+        x = x.contiguous()
+        ctx.save_for_backward(x, weight)
+        return gemm_nt(x, weight.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        gx = gemm_nn(g, weight.contiguous()) if ctx.needs_input_grad[0] else None
+        gw = gemm_tn(g, x) if ctx.needs_input_grad[1] else None
+        return gx, gw
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
-    return F.linear(x, weight, bias)
-
-
-def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-    """out (M,N) = a (M,K) @ b (N,K)^T"""
-    return torch.matmul(a, b.t(), out=out)
-
-
-def gemm_nn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-    """out (M,N) = a (M,K) @ b (K,N)"""
-    return torch.matmul(a, b, out=out)
-
-
-def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-    """out (M,N) = a (K,M)^T @ b (K,N)"""
-    return torch.matmul(a.t(), b, out=out)
+    """F.linear for 2-D inputs (base/common.py:409-414)."""
+    y = _LinearFn.apply(x, weight)
+    return y if bias is None else y + bias

@@ -13,10 +13,10 @@ def lib():
     return _lib.load()
 
 
-def run(lib, A, B, M, N, Kd, a_k, b_k, splits=1):
+def run(lib, A, B, M, N, Kd, a_k, b_k, splits=1, precise=0):
     C = torch.full((M, N), float("nan"), device="cuda")
     ws = torch.empty(max(1, lib.pvae_gemm_ws_floats(M, N, splits)), device="cuda")
-    rc = lib.pvae_gemm_tf32(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, Kd, a_k, b_k, splits, ws.data_ptr(),
+    rc = lib.pvae_gemm_tf32(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, Kd, a_k, b_k, precise, splits, ws.data_ptr(),
                             torch.cuda.current_stream().cuda_stream)
     assert rc == 0, lib.pvae_last_error()
     torch.cuda.synchronize()
@@ -46,8 +46,25 @@ def test_exact_on_tf32_representable_inputs(lib, majors, shape):
     M, N, Kd = shape
     gen = torch.Generator("cuda").manual_seed(M + N + Kd)
     A2, B2, A, B = operands(M, N, Kd, *majors, gen, integers=True)
-    C = run(lib, A, B, M, N, Kd, *majors)
-    assert torch.equal(C, (A2.double() @ B2.double().t()).float())
+    for precise in (0, 1):
+        C = run(lib, A, B, M, N, Kd, *majors, precise=precise)
+        assert torch.equal(C, (A2.double() @ B2.double().t()).float()), precise
+
+
+@pytest.mark.parametrize("majors", [(1, 1), (1, 0), (0, 0), (0, 1)])
+@pytest.mark.parametrize("shape", [(1024, 512, 256), (256, 512, 4096), (200, 264, 520)])
+def test_3xtf32_is_fp32_grade(lib, majors, shape):
+    """Operand splitting (hi*hi + lo*hi + hi*lo): error at the level of an fp32 GEMM, ~1000x below single-pass TF32."""
+    M, N, Kd = shape
+    gen = torch.Generator("cuda").manual_seed(17)
+    A2, B2, A, B = operands(M, N, Kd, *majors, gen, integers=False)
+    C = run(lib, A, B, M, N, Kd, *majors, precise=1, splits=4 if Kd >= 4096 else 1)
+    ref = A2.double() @ B2.double().t()
+    bound = 3 * 2.0 ** -22 * (A2.abs().double() @ B2.abs().double().t())
+    assert ((C.double() - ref).abs() <= bound).all()
+    rel = ((C.double() - ref).norm() / ref.norm()).item()
+    fp32 = (((A2 @ B2.t()).double() - ref).norm() / ref.norm()).item()
+    assert rel < 1e-6 and rel < 4 * max(fp32, 1e-7), (rel, fp32)
 
 
 @pytest.mark.parametrize("majors", [(1, 1), (1, 0), (0, 0)])
@@ -78,6 +95,6 @@ def test_split_k_wgrad_shape(lib, splits):
 def test_argument_checks(lib):
     t = torch.zeros(64, 64, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
-    assert lib.pvae_gemm_tf32(t.data_ptr(), t.data_ptr(), t.data_ptr(), 64, 64, 6, 1, 1, 1, None, s) == -2
-    assert lib.pvae_gemm_tf32(None, t.data_ptr(), t.data_ptr(), 64, 64, 64, 1, 1, 1, None, s) == -1
-    assert lib.pvae_gemm_tf32(t.data_ptr(), t.data_ptr(), t.data_ptr(), 64, 64, 64, 1, 1, 4, None, s) == -1  # no workspace
+    assert lib.pvae_gemm_tf32(t.data_ptr(), t.data_ptr(), t.data_ptr(), 64, 64, 6, 1, 1, 1, 1, None, s) == -2
+    assert lib.pvae_gemm_tf32(None, t.data_ptr(), t.data_ptr(), 64, 64, 64, 1, 1, 1, 1, None, s) == -1
+    assert lib.pvae_gemm_tf32(t.data_ptr(), t.data_ptr(), t.data_ptr(), 64, 64, 64, 1, 1, 1, 2, None, s) == -1  # no workspace
