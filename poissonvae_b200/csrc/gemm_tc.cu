@@ -153,8 +153,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: BN fp32 accumulator columns x 128 lanes
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN));
+  // TMEM: BN fp32 accumulator columns x 128 lanes; 3xTF32 keeps the hi*hi sum and the (2^-10 smaller)
+  // cross terms in separate accumulators so that the tensor core's truncating fp32 adds act on each alone
+  constexpr uint32_t kTmemCols = SPLIT ? 2 * BN : BN;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -212,8 +215,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (SPLIT) {  // + lo(A) hi(B) + hi(A) lo(B); the lo planes sit kTileBytes above the hi planes
             const uint64_t dal = make_smem_desc(sa + kTileBytes + k * a_step, a_lbo, a_sbo, a_lay);
             const uint64_t dbl = make_smem_desc(sb + kTileBytes + k * b_step, b_lbo, b_sbo, b_lay);
-            umma_tf32(tmem_base, dal, db, idesc, 1u);
-            umma_tf32(tmem_base, da, dbl, idesc, 1u);
+            umma_tf32(tmem_base + BN, dal, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(tmem_base + BN, da, dbl, idesc, 1u);
           }
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
@@ -264,7 +267,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
             "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
           : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (SPLIT) {  // + the cross-term accumulator
+        uint32_t w[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+              "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]),
+              "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]),
+              "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+            : "r"(taddr + BN));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+      } else {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      }
       if (m < p.M) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -281,7 +300,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
   }
 }
 

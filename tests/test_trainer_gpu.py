@@ -43,7 +43,9 @@ def test_train_step_matches_reference(path):
     assert_rel(loss[2].item(), float(g["kl"].sum(1).mean()), rtol=2e-5, what="kl")
     for name in ("log_rate", "fc_enc.weight", "fc_dec.weight"):
         assert_rel(tr.gviews[name].cpu().numpy(), g["g_" + name], rtol=2e-5, what="grad " + name)
-        assert_rel(tr.views[name].cpu().numpy(), g["p1_" + name], rtol=1e-6, what="adamax " + name)
+        # first Adamax step: p -= lr * g / (|g| + eps); the ratio amplifies the GEMMs' ~1e-6 relative gradient
+        # error wherever |g| ~ eps, so the parameters carry the GEMM-dependent tolerance too
+        assert_rel(tr.views[name].cpu().numpy(), g["p1_" + name], rtol=2e-5, what="adamax " + name)
     # the module's parameters are views of the flat buffer: state_dict sees the update
     sd = tr.model.state_dict()
     assert torch.equal(sd["fc_dec.weight"], tr.views["fc_dec.weight"])
