@@ -139,6 +139,22 @@ int pvae_grad_norm(const float* g, int64_t n, float max_norm, float* ws, float* 
 int pvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, float lr, int step, float beta1,
                      float beta2, float eps, float weight_decay, const float* clip_coef, void* stream);
 
+/* ---- one call per training step of the lin|lin model ------------------------------------------
+ * Replaces the forward + loss + backward part of TrainerVAE.iteration main/train_vae.py:342-362 (model forward
+ * main/vae.py:384-391, losses :68-72 / :446-450, loss assembly main/train_vae.py:347-351, autograd backward) for
+ * this rank's B samples of a global batch of B_global (row_offset = global index of the first local sample).
+ *   x (B,D) input patches; params / grads: flat [log_r (K) | W_enc (K,D) | W_dec (D,K) | b_enc (K) if has_bias];
+ *   grads is overwritten with d loss / d params where loss = mean over the GLOBAL batch (sum the buffers of all
+ *   ranks to get the global gradient); loss3 = this rank's share of [loss, mse, kl] (sum over ranks);
+ *   ws: pvae_lin_step_ws_floats(B, K, D) floats of scratch; rate_max: optional running max of the rates;
+ *   precise: GEMM mode (see pvae_gemm_tf32); events: NULL or 4 cudaEvent_t recorded before/after the sampler
+ *   forward (0,1) and before/after the sampler backward (2,3) - used by bench.py for the roofline timing. */
+int64_t pvae_lin_step_ws_floats(int64_t B, int64_t K, int64_t D);
+int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, float* ws, float* loss3, float* rate_max,
+                          int64_t B, int64_t B_global, int64_t row_offset, int64_t K, int64_t D, int has_bias, int n_exp,
+                          float temp, float beta, int indicator, int exc_only, float exit_logit, int precise,
+                          uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* const* events, void* stream);
+
 /* Tuning knob (process-wide): number of events each quad of latents walks thread-per-quad before a
  * still-unfinished chain is handed to a whole warp (32 events per step).  Default 8.  Results do
  * not depend on the launch geometry, but the float summation order of a chain depends on this value. */

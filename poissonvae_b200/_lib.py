@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpvae_b200.so")
-SOURCES = ["capi.cu", "sampler.cu", "step.cu", "gemm_tc.cu"]
+SOURCES = ["capi.cu", "sampler.cu", "step.cu", "gemm_tc.cu", "lin_step.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -54,6 +54,9 @@ _SIGNATURES = {
     "pvae_grad_norm_ws_floats": (_i64, []),
     "pvae_grad_norm": (_i, [_p, _i64, _f, _p, _p, _p]),
     "pvae_adamax_step": (_i, [_p, _p, _p, _p, _i64, _f, _i, _f, _f, _f, _f, _p, _p]),
+    "pvae_lin_step_ws_floats": (_i64, [_i64, _i64, _i64]),
+    "pvae_lin_step_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i,
+                                   _u64, _u64, _p, _p, _p]),
     "pvae_set_phase_a_events": (_i, [_i]),
     "pvae_debug_log_check": (_i, [_p, _p]),
     "pvae_debug_draws": (_i, [_p, _p, _i64, _i64, _i64, _i, _u64, _u64, _p, _p]),

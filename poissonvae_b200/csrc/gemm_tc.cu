@@ -304,13 +304,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   }
 }
 
-// fixed-order sum of the split-K partials
+// fixed-order sum of the split-K partials (loads of eight splits in flight per thread)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, long long n4,
                                                             int splits) {
+  const float4* w = reinterpret_cast<const float4*>(ws);
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += gridDim.x * 256ll) {
-    float4 a = __ldg(reinterpret_cast<const float4*>(ws) + i);
-    for (int s = 1; s < splits; ++s) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(ws) + s * n4 + i);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+    for (; s + 8 <= splits; s += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(w + (s + u) * n4 + i);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a.x += v[u].x, a.y += v[u].y, a.z += v[u].z, a.w += v[u].w;
+    }
+    for (; s < splits; ++s) {
+      const float4 b = __ldg(w + s * n4 + i);
       a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
     }
     reinterpret_cast<float4*>(C)[i] = a;
@@ -423,7 +432,7 @@ extern "C" int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t 
   if (rc) return rc;
   if (splits > 1) {
     const long long n4 = M * N / 4;
-    const unsigned grid = static_cast<unsigned>(std::min<long long>((n4 + 255) / 256, 148ll * 8));
+    const unsigned grid = static_cast<unsigned>(std::min<long long>((n4 + 255) / 256, 148ll * 16));
     splitk_reduce_kernel<<<grid, 256, 0, s>>>(splitk_ws, C, n4, splits);
     return cuda_ok("splitk_reduce_kernel", cudaGetLastError());
   }

@@ -1,0 +1,102 @@
+// One C call per training step of the lin|lin P-VAE: enqueues, back to back on one stream, every kernel of
+// forward + loss + backward (closed form) for this rank's slice of the batch.
+//
+//   h   = x W_enc^T                                   tcgen05 GEMM            main/vae.py:44-51
+//   z   = rsample(softclamps(h, log_r)), kl row sums  fused sampler           main/vae.py:393-415, base/distributions.py:55-81
+//   y   = z W_dec^T                                   tcgen05 GEMM            main/vae.py:59-60
+//   g_y = 2 (y - x) / B_global, recon                 residual kernel         main/vae.py:68-72
+//   loss = sum_b(recon + beta kl) / B_global          loss kernel             main/train_vae.py:347-351
+//   g_W_dec = g_y^T z (split-K), g_z = g_y W_dec      tcgen05 GEMMs
+//   g_h, g_log_r (+ g_b_enc)                          sampler backward, chain recomputed from the Philox counters
+//   g_W_enc = g_h^T x (split-K)                       tcgen05 GEMM
+// The caller then all-reduces the flat gradient buffer (data parallel) and calls pvae_grad_norm /
+// pvae_adamax_step.  Parameter and gradient buffers are flat: [log_r (K) | W_enc (K,D) | W_dec (D,K) | b_enc (K)].
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pvae_b200.h"
+#include "pvae_host.h"
+
+namespace {
+
+struct Ws {
+  float *h, *z, *y, *g_y, *g_z, *g_h, *recon, *klrow, *partials, *splitk;
+  int64_t total;
+};
+
+int wgrad_splits(int64_t m, int64_t n, int64_t kd) {
+  const int64_t tiles = ((m + 127) / 128) * ((n + 127) / 128);
+  if (tiles >= 64 || kd < 512) return 1;
+  int64_t s = 128 / tiles;
+  if (s > kd / 256) s = kd / 256;
+  return static_cast<int>(s < 1 ? 1 : s);
+}
+
+Ws carve(float* base, int64_t B, int64_t K, int64_t D) {
+  Ws w;
+  int64_t o = 0;
+  auto take = [&](int64_t n) {
+    float* p = base ? base + o : nullptr;
+    o += (n + 3) & ~int64_t(3);  // keep every buffer 16-byte aligned
+    return p;
+  };
+  w.h = take(B * K), w.z = take(B * K), w.y = take(B * D), w.g_y = take(B * D), w.g_z = take(B * K), w.g_h = take(B * K);
+  w.recon = take(B), w.klrow = take(B);
+  w.partials = take(2 * pvae_num_partials(B) * K);
+  const int64_t s1 = pvae_gemm_ws_floats(D, K, wgrad_splits(D, K, B)), s2 = pvae_gemm_ws_floats(K, D, wgrad_splits(K, D, B));
+  w.splitk = take(s1 > s2 ? s1 : s2);
+  w.total = o;
+  return w;
+}
+
+}  // namespace
+
+extern "C" int64_t pvae_lin_step_ws_floats(int64_t B, int64_t K, int64_t D) {
+  if (B <= 0 || K <= 0 || D <= 0) return 0;
+  return carve(nullptr, B, K, D).total;
+}
+
+extern "C" int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, float* ws, float* loss3,
+                                     float* rate_max, int64_t B, int64_t B_global, int64_t row_offset, int64_t K, int64_t D,
+                                     int has_bias, int n_exp, float temp, float beta, int indicator, int exc_only,
+                                     float exit_logit, int precise, uint64_t seed, uint64_t offset,
+                                     const uint64_t* offset_dev, void* const* events, void* stream) {
+  using pvae::fail;
+  if (B <= 0 || B_global < B || K <= 0 || D <= 0) return fail(PVAE_ERR_INVALID, "pvae_lin_step_fwd_bwd: bad shape");
+  if (B % 4 || K % 4 || D % 4)
+    return fail(PVAE_ERR_UNSUPPORTED, "pvae_lin_step_fwd_bwd: B=%lld K=%lld D=%lld must be multiples of 4", (long long)B,
+                (long long)K, (long long)D);
+  if (!x || !params || !grads || !ws || !loss3) return fail(PVAE_ERR_INVALID, "pvae_lin_step_fwd_bwd: null pointer");
+  if (!(temp > 0.f)) return fail(PVAE_ERR_INVALID, "pvae_lin_step_fwd_bwd: training needs temp > 0, got %g", temp);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const Ws w = carve(ws, B, K, D);
+  const float *log_r = params, *w_enc = params + K, *w_dec = w_enc + K * D;
+  const float* b_enc = has_bias ? w_dec + D * K : nullptr;
+  float *g_log_r = grads, *g_w_enc = grads + K, *g_w_dec = g_w_enc + K * D;
+  float* g_b_enc = has_bias ? g_w_dec + D * K : nullptr;
+  auto mark = [&](int i) {
+    if (events && events[i]) cudaEventRecord(static_cast<cudaEvent_t>(events[i]), s);
+  };
+  int rc;
+  // ---- forward
+  if ((rc = pvae_gemm_tf32(x, w_enc, w.h, B, K, D, 1, 1, precise, 1, nullptr, s))) return rc;
+  mark(0);
+  if ((rc = pvae_sampler_fwd(w.h, log_r, b_enc, w.z, nullptr, nullptr, nullptr, w.klrow, rate_max, B, K, row_offset, n_exp,
+                             temp, indicator, exc_only, exit_logit, seed, offset, offset_dev, s)))
+    return rc;
+  mark(1);
+  if ((rc = pvae_gemm_tf32(w.z, w_dec, w.y, B, D, K, 1, 1, precise, 1, nullptr, s))) return rc;
+  if ((rc = pvae_recon_residual(w.y, x, w.g_y, w.recon, B, D, 2.0f / static_cast<float>(B_global), s))) return rc;
+  if ((rc = pvae_loss_assemble(w.recon, w.klrow, loss3, B, beta, B_global, s))) return rc;
+  // ---- backward
+  if ((rc = pvae_gemm_tf32(w.g_y, w.z, g_w_dec, D, K, B, 0, 0, precise, wgrad_splits(D, K, B), w.splitk, s))) return rc;
+  if ((rc = pvae_gemm_tf32(w.g_y, w_dec, w.g_z, B, K, D, 1, 0, precise, 1, nullptr, s))) return rc;
+  mark(2);
+  if ((rc = pvae_sampler_bwd(w.h, log_r, b_enc, w.g_z, nullptr, beta / static_cast<float>(B_global), w.g_h, g_log_r, g_b_enc,
+                             w.partials, 0, B, K, row_offset, n_exp, temp, indicator, exc_only, exit_logit, seed, offset,
+                             offset_dev, s)))
+    return rc;
+  mark(3);
+  if ((rc = pvae_gemm_tf32(w.g_h, x, g_w_enc, K, D, B, 0, 0, precise, wgrad_splits(K, D, B), w.splitk, s))) return rc;
+  return PVAE_OK;
+}

@@ -393,16 +393,26 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
 }
 
 // ---- fixed-order column reduction of the (P,K) partials ----------------------------------------
-constexpr int kRedX = 32, kRedY = 8;
+// One block per 32 columns; 32 row-lanes each keep four independent running sums (rows ty + 32 * (4i + u)),
+// then a fixed-order combine through shared memory.  Deterministic for a given P.
+constexpr int kRedX = 32, kRedY = 32;
 __global__ void __launch_bounds__(kRedX* kRedY) colsum_finalize_kernel(const float* __restrict__ part, float* __restrict__ out,
                                                                       long long P, long long K, int accumulate) {
   __shared__ float s[kRedY][kRedX + 1];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const long long k = static_cast<long long>(blockIdx.x) * kRedX + tx;
-  float a = 0.f;
-  if (k < K)
-    for (long long r = ty; r < P; r += kRedY) a += part[r * K + k];
-  s[ty][tx] = a;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (k < K) {
+    long long r = ty;
+    for (; r + 3 * kRedY < P; r += 4 * kRedY) {
+      a0 += __ldg(part + r * K + k);
+      a1 += __ldg(part + (r + kRedY) * K + k);
+      a2 += __ldg(part + (r + 2 * kRedY) * K + k);
+      a3 += __ldg(part + (r + 3 * kRedY) * K + k);
+    }
+    for (; r < P; r += kRedY) a0 += __ldg(part + r * K + k);
+  }
+  s[ty][tx] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (ty == 0 && k < K) {
     float v = s[0][tx];

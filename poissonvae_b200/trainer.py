@@ -10,6 +10,7 @@ sample index, so the result does not depend on the number of GPUs.
 """
 from __future__ import annotations
 
+import ctypes
 import math
 
 import numpy as np
@@ -18,7 +19,7 @@ import torch.distributed as dist
 
 from . import _lib
 from .distributions import INDICATOR_CODES, _ptr, _stream
-from .linear import gemm_nn, gemm_nt, gemm_tn
+from . import linear as linear_mod
 from .rng import next_philox
 from .vae import PoissonVAE
 
@@ -126,9 +127,7 @@ class TrainerVAE:
         if B not in self._bufs:
             K, D = self.model.cfg.n_latents, self.model.cfg.input_sz ** 2
             f = lambda *s: torch.empty(*s, device=self.device, dtype=torch.float32)
-            self._bufs[B] = dict(h=f(B, K), z=f(B, K), y=f(B, D), g_y=f(B, D), g_z=f(B, K), g_h=f(B, K),
-                                 recon=f(B), klrow=f(B), loss=f(3),
-                                 ws=f(2 * self.lib.pvae_num_partials(B) * K),
+            self._bufs[B] = dict(ws=f(self.lib.pvae_lin_step_ws_floats(B, K, D)), loss=f(3),
                                  nws=f(self.lib.pvae_grad_norm_ws_floats()), norm=f(2))
         return self._bufs[B]
 
@@ -157,8 +156,10 @@ class TrainerVAE:
         return out
 
     def launches_per_step(self) -> int:
-        """Kernels of libpvae_b200.so launched by one train_step (the five GEMMs are counted apart)."""
-        n = 6  # sampler fwd, residual, loss, sampler bwd, column-sum finalize, Adamax
+        """Kernels of libpvae_b200.so launched by one train_step."""
+        # 5 tcgen05 GEMMs + 2 split-K reductions (wgrad), sampler fwd, residual, loss, sampler bwd,
+        # column-sum finalize, Adamax
+        n = 13
         if self.model.fc_enc.bias is not None:
             n += 1  # second column-sum finalize (bias gradient)
         if self.cfg.grad_clip is not None:
@@ -209,7 +210,7 @@ class TrainerVAE:
         """x: (B_local, 1, H, W) or (B_local, D) device tensor (this rank's slice of the global batch).
         Returns the device tensor [loss, mse, kl] (global-batch means; no host sync)."""
         cfg, m, lib = self.cfg, self.model, self.lib
-        x2 = x.reshape(x.shape[0], -1)
+        x2 = x.reshape(x.shape[0], -1).contiguous()
         B, D = x2.shape
         K = m.cfg.n_latents
         Bg = B * self.world
@@ -223,26 +224,21 @@ class TrainerVAE:
         seed, offset = next_philox(self.device) if philox is None else philox
         b = self._buffers(B)
         s = _stream()
-        w_enc, w_dec, log_r = self.views['fc_enc.weight'], self.views['fc_dec.weight'], self.views['log_rate']
-        b_enc = self.views.get('fc_enc.bias')
         chk = _lib.check
-        # forward: encoder GEMM -> fused sampler (+KL row sums, r_max) -> decoder GEMM -> residual
-        gemm_nt(x2, w_enc, out=b['h'])
-        self._timed('sampler_fwd', lambda: chk(lib.pvae_sampler_fwd(_ptr(b['h']), _ptr(log_r), _ptr(b_enc), _ptr(b['z']), None, None, None,
-                                 _ptr(b['klrow']), self.r_max.data_ptr() + 4 * (gstep % self.r_max.numel()), B, K, row_offset, n_exp, temp, ind,
-                                 int(m.cfg.exc_only), m.exit_logit, seed, offset, None, s)))
-        gemm_nt(b['z'], w_dec, out=b['y'])
-        chk(lib.pvae_recon_residual(_ptr(b['y']), _ptr(x2), _ptr(b['g_y']), _ptr(b['recon']), B, D, 2.0 / Bg, s))
-        chk(lib.pvae_loss_assemble(_ptr(b['recon']), _ptr(b['klrow']), _ptr(b['loss']), B, beta, Bg, s))
-        # backward (closed form)
-        gemm_tn(b['g_y'], b['z'], out=self.gviews['fc_dec.weight'])  # g_W_dec = g_y^T z
-        gemm_nn(b['g_y'], w_dec, out=b['g_z'])  # g_z = g_y W_dec
-        self._timed('sampler_bwd', lambda: chk(lib.pvae_sampler_bwd(_ptr(b['h']), _ptr(log_r), _ptr(b_enc), _ptr(b['g_z']), None, beta / Bg,
-                                 _ptr(b['g_h']), _ptr(self.gviews['log_rate']),
-                                 None if b_enc is None else _ptr(self.gviews['fc_enc.bias']), _ptr(b['ws']), 0, B, K,
-                                 row_offset, n_exp, temp, ind, int(m.cfg.exc_only), m.exit_logit, seed, offset,
-                                 None, s)))
-        gemm_tn(b['g_h'], x2, out=self.gviews['fc_enc.weight'])  # g_W_enc = g_h^T x
+        events = None
+        if self.kernel_events is not None:  # CUDA events around the two sampler launches (bench.py roofline)
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            for e in evs:
+                e.record()  # materialises the cudaEvent_t; the library re-records it at the right place
+            events = (ctypes.c_void_p * 4)(*[e.cuda_event for e in evs])
+            self.kernel_events.setdefault('sampler_fwd', []).append((evs[0], evs[1]))
+            self.kernel_events.setdefault('sampler_bwd', []).append((evs[2], evs[3]))
+        # forward + loss + backward: one call, every kernel enqueued back to back (csrc/lin_step.cu)
+        chk(lib.pvae_lin_step_fwd_bwd(
+            _ptr(x2), _ptr(self.flat_p), _ptr(self.flat_g), _ptr(b['ws']), _ptr(b['loss']),
+            self.r_max.data_ptr() + 4 * (gstep % self.r_max.numel()), B, Bg, row_offset, K, D,
+            int(m.fc_enc.bias is not None), n_exp, temp, beta, ind, int(m.cfg.exc_only), m.exit_logit,
+            int(linear_mod.PRECISE), seed, offset, None, events, s))
         if self.world > 1:
             dist.all_reduce(self.flat_g, group=self.pg)  # gradients already carry 1 / B_global
             dist.all_reduce(b['loss'], group=self.pg)

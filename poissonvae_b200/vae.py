@@ -280,8 +280,9 @@ class PoissonVAE(nn.Module):
         if new_t is None:
             return
         assert new_t >= 0.0, "must be non-neg"
+        if float(new_t) != self._temp_host:  # the buffer write is a kernel launch: skip it when nothing changes
+            self.temp.fill_(new_t)
         self._temp_host = float(new_t)
-        self.temp.fill_(new_t)
 
     def update_n(self, rate: float):  # main/vae.py:452-459
         if rate is None:

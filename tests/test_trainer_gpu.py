@@ -79,7 +79,7 @@ def test_schedules_and_epoch_loop():
     from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
     from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
     model = PoissonVAE(ConfigPoisVAE(n_latents=64, prior_clamp=-4, seed=0)).cuda()
-    cfg = ConfigTrainVAE(lr=0.005, epochs=10, batch_size=50, grad_clip=None, kl_const_portion=0.0)
+    cfg = ConfigTrainVAE(lr=0.005, epochs=10, batch_size=48, grad_clip=None, kl_const_portion=0.0)
     tr = TrainerVAE(model, cfg, n_batches_per_epoch=4)
     assert tr.n_iters == 40
     assert np.array_equal(tr.temperatures, po.temp_anneal_linear(40, 1.0, 0.05, 0.5))
@@ -87,7 +87,7 @@ def test_schedules_and_epoch_loop():
     assert tr.lr_at(0) == 0.0 and tr.lr_at(39) < tr.lr_at(1)
     with torch.no_grad():
         model.log_rate.add_(4.0)  # rates ~0.1-1 so that the decoder sees spikes from step 0
-    data = torch.randn(200, 1, 16, 16, device="cuda")
+    data = torch.randn(192, 1, 16, 16, device="cuda")
     before = model.fc_dec.weight.detach().clone()
     n0 = int(model.n_exp)
     nelbo = [tr.iteration(data, epoch) for epoch in range(10)]
