@@ -105,10 +105,15 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+
+    def mark(self):
+        """Samples taken before this point (model build, warm-up) are dropped from the summary."""
+        self.f.flush()
+        self.skip = sum(1 for _ in open(self.f.name))
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -121,7 +126,7 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        rows = [r.split(",") for r in self.f.read().strip().splitlines() if r.count(",") >= 7]
+        rows = [r.split(",") for r in self.f.read().strip().splitlines()[getattr(self, "skip", 0):] if r.count(",") >= 7]
         self.f.close()
         os.unlink(self.f.name)
         if not rows:
@@ -154,16 +159,20 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     _lib.load()  # fails loudly if the CUDA extension has not been built
     dev = torch.device("cuda", local)
+    clocks = ClockSampler(local) if rank == 0 else None  # nvidia-smi needs a moment to start sampling
     B, K, K_steps, W = args.batch, args.latents, args.steps, args.warmup
 
     model = PoissonVAE(ConfigPoisVAE(n_latents=K, prior_clamp=-4, seed=0),
                        exit_logit=EXIT_LOSSLESS if args.exit == "lossless" else EXIT_NEVER).to(dev)
     model.n_exp.fill_(args.n_exp)
     model._n_exp_host = args.n_exp
-    cfg = ConfigTrainVAE(lr=0.005, epochs=1_000_000, batch_size=B, warmup_portion=0.0, grad_clip=None,
+    # the reference's own vH16 schedule (main/config_vae.py:433-440: lr .005, 3000 epochs, 1 % linear lr warm-up,
+    # no gradient clipping); 26 batches of 4096 per epoch for ~108 k training patches.  beta and the temperature
+    # are pinned to the values the BASELINE config names.
+    cfg = ConfigTrainVAE(lr=0.005, epochs=3000, batch_size=B, warmup_portion=0.01, grad_clip=None,
                          kl_beta=args.beta, kl_anneal_portion=0.0, kl_const_portion=0.0, temp_anneal_portion=0.0,
                          temp_stop=args.temp)
-    tr = TrainerVAE(model, cfg)
+    tr = TrainerVAE(model, cfg, n_batches_per_epoch=26)
 
     # inputs: 64 distinct batches (268 MB at B=4096 > 126 MB L2) so that no step finds its input in L2
     NB = 64
@@ -179,7 +188,8 @@ def run_ours(args):
     for i in range(W):
         tr.train_step(data[i % NB], i)
     barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks is not None:
+        clocks.mark()
     tr.kernel_events = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -37,8 +37,12 @@ def main():
     ap.add_argument("--K", type=int, default=512)
     ap.add_argument("--n_exp", type=int, default=263)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--single", action="store_true", help="only random_init, temp 1, lossless (for ncu captures)")
+    ap.add_argument("--phase_a", type=int, default=0, help="override pvae_set_phase_a_events")
     args = ap.parse_args()
     lib = _lib.load()
+    if args.phase_a > 0:
+        assert lib.pvae_set_phase_a_events(args.phase_a) == 0
     B, K, n_exp = args.B, args.K, args.n_exp
     s = torch.cuda.current_stream().cuda_stream
     g = torch.Generator("cuda").manual_seed(0)
@@ -55,9 +59,13 @@ def main():
     glr = torch.empty(K, device="cuda")
     ws = torch.empty(2 * lib.pvae_num_partials(B) * K, device="cuda")
     klrow = torch.empty(B, device="cuda")
+    temps = (1.0,) if args.single else (1.0, 0.05)
+    exits = (("lossless", 0.0),) if args.single else (("lossless", 0.0), ("c30", 30.0), ("never", -1.0))
+    if args.single:
+        dists = {"random_init": dists["random_init"]}
     for name, (h, log_r) in dists.items():
-        for temp in (1.0, 0.05):
-            for exit_name, ex in (("lossless", 0.0), ("c30", 30.0), ("never", -1.0)):
+        for temp in temps:
+            for exit_name, ex in exits:
                 def fwd():
                     rc = lib.pvae_sampler_fwd(P(h), P(log_r), None, P(z), None, None, None, P(klrow), None, B, K, 0, n_exp,
                                               temp, 0, 0, ex, 1, 4, None, s)
