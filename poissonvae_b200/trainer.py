@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, dp
 from .distributions import INDICATOR_CODES, _ptr, _stream
 from . import linear as linear_mod
 from .rng import next_philox
@@ -81,8 +81,7 @@ class TrainerVAE:
         if self.device.type != 'cuda':
             raise RuntimeError("TrainerVAE needs the model on a CUDA device (no CPU path)")
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
-        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        self.world, self.rank = dp.world_info(process_group)
         self.n_iters = cfg.epochs * n_batches_per_epoch
         self.betas = beta_anneal_linear(self.n_iters, cfg.kl_beta, cfg.kl_anneal_portion, cfg.kl_const_portion,
                                         cfg.kl_beta_min)  # main/train_vae.py:27-34
@@ -214,7 +213,7 @@ class TrainerVAE:
         B, D = x2.shape
         K = m.cfg.n_latents
         Bg = B * self.world
-        row_offset = self.rank * B
+        row_offset, _ = dp.shard_rows(Bg, self.world, self.rank)
         temp = float(self.temperatures[min(gstep, self.n_iters - 1)])
         beta = float(self.betas[min(gstep, self.n_iters - 1)])
         lr = self.lr_at(gstep)
@@ -239,9 +238,7 @@ class TrainerVAE:
             self.r_max.data_ptr() + 4 * (gstep % self.r_max.numel()), B, Bg, row_offset, K, D,
             int(m.fc_enc.bias is not None), n_exp, temp, beta, ind, int(m.cfg.exc_only), m.exit_logit,
             int(linear_mod.PRECISE), seed, offset, None, events, s))
-        if self.world > 1:
-            dist.all_reduce(self.flat_g, group=self.pg)  # gradients already carry 1 / B_global
-            dist.all_reduce(b['loss'], group=self.pg)
+        dp.allreduce_gradients(self.flat_g, b['loss'], self.pg)  # gradients already carry 1 / B_global
         # clip (main/train_vae.py:365-377) + Adamax (base/adamax.py)
         clip = None
         if cfg.grad_clip is not None:
@@ -268,8 +265,7 @@ class TrainerVAE:
             total += self.train_step(x, epoch * n_batches + i)
         nelbo_mse_kl = (total / max(n_batches, 1)).tolist()
         # end-of-epoch n_exp update from the mean of the per-step rate.max(), main/train_vae.py:388,456-457
-        if self.world > 1:
-            dist.all_reduce(self.r_max, op=dist.ReduceOp.MAX, group=self.pg)
+        dp.allreduce_max(self.r_max, self.pg)
         r_max = self.r_max[:n_batches].mean().item() if n_batches <= self.r_max.numel() else self.r_max.mean().item()
         if r_max > 0:
             self.model.update_n(r_max)
