@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--exit", default="lossless", choices=["lossless", "never"])
     ap.add_argument("--cpu_rows", type=int, default=256, help="rows of the batch the CPU baseline steps on")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_pdl", action="store_true", help="disable programmatic dependent launch (A/B)")
+    ap.add_argument("--tf32", action="store_true", help="single-pass TF32 GEMMs instead of 3xTF32 (A/B)")
     return ap.parse_args()
 
 
@@ -157,7 +159,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    _lib.load()  # fails loudly if the CUDA extension has not been built
+    lib = _lib.load()  # fails loudly if the CUDA extension has not been built
+    if args.no_pdl:
+        lib.pvae_set_pdl(0)
+    if args.tf32:
+        from poissonvae_b200 import linear as _linear
+        _linear.PRECISE = False
     dev = torch.device("cuda", local)
     clocks = ClockSampler(local) if rank == 0 else None  # nvidia-smi needs a moment to start sampling
     B, K, K_steps, W = args.batch, args.latents, args.steps, args.warmup

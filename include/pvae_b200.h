@@ -49,6 +49,9 @@ extern "C" {
 #define PVAE_EXIT_NEVER (-1.0f)
 
 int pvae_version(void);
+/* Programmatic dependent launch for every kernel of the library (default on): a kernel may be scheduled
+ * while its predecessor in the stream drains and waits (griddepcontrol.wait) before touching its data. */
+int pvae_set_pdl(int on);
 const char* pvae_last_error(void);
 
 /* Rows of the (P, K) partial-sum workspaces the backward entry points need for batch size B. */
@@ -116,6 +119,9 @@ int pvae_kl_bwd(const float* log_dr, const float* log_r, const float* g_kl, floa
  * ranges (one CTA each) whose partial tiles are summed in a fixed order; splitk_ws then needs
  * pvae_gemm_ws_floats(M, N, splits) floats. */
 int64_t pvae_gemm_ws_floats(int64_t M, int64_t N, int splits);
+/* Tuning knob (process-wide): 0 = automatic tile choice, 1 = 128-wide tiles with one CTA per SM,
+ * 2 = 64-wide tiles with two co-resident CTAs per SM. */
+int pvae_set_gemm_variant(int v);
 int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t Kd, int a_kmajor, int b_kmajor,
                    int precise, int splits, float* splitk_ws, void* stream);
 
@@ -159,6 +165,9 @@ int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, flo
  * still-unfinished chain is handed to a whole warp (32 events per step).  Default 8.  Results do
  * not depend on the launch geometry, but the float summation order of a chain depends on this value. */
 int pvae_set_phase_a_events(int n);
+/* Tuning knob (process-wide): rows (samples) per thread block of the sampler kernels, 1..4; 0 = automatic.
+ * Changes pvae_num_partials(); results of the forward are unaffected. */
+int pvae_set_rows_per_block(int n);
 
 /* ---- parity harness only: dump the uniforms / exponentials the kernels consume ---------------
  * U, E: (n_exp, B, K).  Either may be NULL.

@@ -40,6 +40,7 @@ _f, _i, _i64, _u64, _p = C.c_float, C.c_int, C.c_int64, C.c_uint64, C.c_void_p
 _SIGNATURES = {
     "pvae_version": (C.c_int, []),
     "pvae_last_error": (C.c_char_p, []),
+    "pvae_set_pdl": (_i, [_i]),
     "pvae_num_partials": (_i64, [_i64]),
     "pvae_sampler_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _f, _i, _i, _f, _u64, _u64, _p, _p]),
     "pvae_sampler_bwd": (_i, [_p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _i, _i64, _i64, _i64, _i, _f, _i, _i, _f, _u64, _u64, _p, _p]),
@@ -48,6 +49,7 @@ _SIGNATURES = {
     "pvae_kl_fwd": (_i, [_p, _p, _p, _i64, _i64, _p]),
     "pvae_kl_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _i64, _p]),
     "pvae_gemm_ws_floats": (_i64, [_i64, _i64, _i]),
+    "pvae_set_gemm_variant": (_i, [_i]),
     "pvae_gemm_tf32": (_i, [_p, _p, _p, _i64, _i64, _i64, _i, _i, _i, _i, _p, _p]),
     "pvae_recon_residual": (_i, [_p, _p, _p, _p, _i64, _i64, _f, _p]),
     "pvae_loss_assemble": (_i, [_p, _p, _p, _i64, _f, _i64, _p]),
@@ -58,6 +60,7 @@ _SIGNATURES = {
     "pvae_lin_step_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i,
                                    _u64, _u64, _p, _p, _p]),
     "pvae_set_phase_a_events": (_i, [_i]),
+    "pvae_set_rows_per_block": (_i, [_i]),
     "pvae_debug_log_check": (_i, [_p, _p]),
     "pvae_debug_draws": (_i, [_p, _p, _i64, _i64, _i64, _i, _u64, _u64, _p, _p]),
 }

@@ -6,7 +6,15 @@ char* last_error_buffer() {
   static thread_local char buf[512] = {0};
   return buf;
 }
+static bool g_pdl = true;
+bool pdl_enabled() { return g_pdl; }
+void set_pdl(bool on) { g_pdl = on; }
 }  // namespace pvae
 
+namespace pvae { void set_pdl(bool); }
+extern "C" int pvae_set_pdl(int on) {
+  pvae::set_pdl(on != 0);
+  return PVAE_OK;
+}
 extern "C" int pvae_version(void) { return 100; }
 extern "C" const char* pvae_last_error(void) { return pvae::last_error_buffer(); }

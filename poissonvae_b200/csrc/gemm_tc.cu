@@ -27,6 +27,7 @@
 #include <tuple>
 
 #include "../../include/pvae_b200.h"
+#include "pvae_device.cuh"
 #include "pvae_host.h"
 
 namespace pvae {
@@ -112,20 +113,21 @@ struct GemmParams {
   long long split_stride;  // M * N when splits > 1
 };
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, int STAGES>
 struct GemmCfg {
   static constexpr uint32_t kABytes = kBM * kBK * 4;  // 16 KB
   static constexpr uint32_t kBBytes = BN * kBK * 4;
   static constexpr uint32_t kTileBytes = kABytes + kBBytes;             // what TMA writes per stage
   static constexpr uint32_t kStageBytes = SPLIT ? 2 * kTileBytes : kTileBytes;  // + the lo planes
-  static constexpr int kStages = SPLIT ? (BN == 128 ? 3 : 4) : 4;
+  static constexpr int kStages = STAGES;
   static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kCtasPerSm = kSmem <= 110 * 1024 ? 2 : 1;
 };
 
-template <int BN, bool SPLIT>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, bool SPLIT, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, GemmCfg<BN, SPLIT, STAGES>::kCtasPerSm)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
-  using Cfg = GemmCfg<BN, SPLIT>;
+  using Cfg = GemmCfg<BN, SPLIT, STAGES>;
   constexpr uint32_t kABytes = Cfg::kABytes, kTileBytes = Cfg::kTileBytes, kStageBytes = Cfg::kStageBytes;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -164,6 +166,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -252,8 +257,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     mbar_wait(accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quarter = warp & 3;  // a warp may only read TMEM lanes [32 * (warp % 4), +32)
-    const int m = m0 + quarter * 32 + lane;
-    float* crow = p.C + static_cast<long long>(blockIdx.z) * p.split_stride + static_cast<long long>(m) * p.N;
+    float* cbase = p.C + static_cast<long long>(blockIdx.z) * p.split_stride;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
@@ -284,14 +288,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       } else {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       }
-      if (m < p.M) {
+      // transpose through shared memory (the operand ring is idle by now) so that a store instruction
+      // writes four full 128-byte row segments instead of 32 scattered 16-byte pieces
+      float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
+      __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + c0 + j;
-          if (n < p.N)  // N is a multiple of 4
-            *reinterpret_cast<float4*>(crow + n) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        }
+      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+      __syncwarp();
+      const int sub = lane >> 3, col = 4 * (lane & 7);
+      const int n = n0 + c0 + col;
+#pragma unroll
+      for (int rr = 0; rr < 32; rr += 4) {
+        const int row = rr + sub;
+        const int mm = m0 + quarter * 32 + row;
+        const float* src = stg + row * 33 + col;
+        if (mm < p.M && n < p.N)  // N is a multiple of 4
+          *reinterpret_cast<float4*>(cbase + static_cast<long long>(mm) * p.N + n) = make_float4(src[0], src[1], src[2], src[3]);
       }
     }
   }
@@ -307,6 +319,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 // fixed-order sum of the split-K partials (loads of eight splits in flight per thread)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, long long n4,
                                                             int splits) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float4* w = reinterpret_cast<const float4*>(ws);
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += gridDim.x * 256ll) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -375,26 +389,33 @@ static int make_map(CUtensorMap* out, const float* base, long long rows, long lo
   return PVAE_OK;
 }
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, int STAGES>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int splits, cudaStream_t s) {
-  constexpr int smem = GemmCfg<BN, SPLIT>::kSmem;
+  constexpr int smem = GemmCfg<BN, SPLIT, STAGES>::kSmem;
   static bool configured = false;
   if (!configured) {
-    if (int rc = cuda_ok("cudaFuncSetAttribute", cudaFuncSetAttribute(gemm_tf32_kernel<BN, SPLIT>,
+    if (int rc = cuda_ok("cudaFuncSetAttribute", cudaFuncSetAttribute(gemm_tf32_kernel<BN, SPLIT, STAGES>,
                                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem)))
       return rc;
     configured = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, splits);
-  gemm_tf32_kernel<BN, SPLIT><<<grid, kGemmThreads, smem, s>>>(ma, mb, p);
-  return cuda_ok("gemm_tf32_kernel", cudaGetLastError());
+  return cuda_ok("gemm_tf32_kernel", launch_pdl(gemm_tf32_kernel<BN, SPLIT, STAGES>, grid, dim3(kGemmThreads), smem, s, ma, mb, p));
 }
+
+static int g_gemm_variant = 0;  // tuning: 0 = automatic, 1 = wide tiles / 1 CTA per SM, 2 = narrow tiles / 2 CTAs per SM
 
 }  // namespace pvae
 
 using namespace pvae;
 
 extern "C" int64_t pvae_gemm_ws_floats(int64_t M, int64_t N, int splits) { return splits > 1 ? splits * M * N : 0; }
+
+extern "C" int pvae_set_gemm_variant(int v) {
+  if (v < 0 || v > 2) return fail(PVAE_ERR_INVALID, "pvae_set_gemm_variant: %d not in [0, 2]", v);
+  g_gemm_variant = v;
+  return PVAE_OK;
+}
 
 extern "C" int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t Kd, int a_kmajor,
                               int b_kmajor, int precise, int splits, float* splitk_ws, void* stream) {
@@ -414,7 +435,9 @@ extern "C" int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t 
     splits = static_cast<int>((kblocks + per - 1) / per);
   }
   // 128-wide tiles unless that leaves most of the 148 SMs without a CTA
-  const int BN = (N <= 64 || ((N + 127) / 128) * ((M + kBM - 1) / kBM) * splits < 96) ? 64 : 128;
+  int BN = (N <= 64 || ((N + 127) / 128) * ((M + kBM - 1) / kBM) * splits < 96) ? 64 : 128;
+  const bool narrow = g_gemm_variant == 2 || (g_gemm_variant == 0 && false);
+  if (narrow) BN = 64;
   CUtensorMap ma, mb;
   // K-major operand: (rows, Kd) row-major, box {32 k, rows_per_tile}; MN-major: (Kd, rows) row-major, box {32 rows, 32 k}
   if (int rc = a_kmajor ? make_map(&ma, A, M, Kd, kBK, kBM) : make_map(&ma, A, Kd, M, 32, kBK, true)) return rc;
@@ -427,14 +450,19 @@ extern "C" int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t 
   p.split_stride = splits > 1 ? M * N : 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rc;
-  if (precise) rc = BN == 64 ? launch_gemm<64, true>(ma, mb, p, splits, s) : launch_gemm<128, true>(ma, mb, p, splits, s);
-  else rc = BN == 64 ? launch_gemm<64, false>(ma, mb, p, splits, s) : launch_gemm<128, false>(ma, mb, p, splits, s);
+  if (narrow) {  // 2 CTAs per SM: one CTA's TMA latency hides behind the other's split + MMA work
+    rc = precise ? launch_gemm<64, true, 2>(ma, mb, p, splits, s) : launch_gemm<64, false, 4>(ma, mb, p, splits, s);
+  } else if (precise) {
+    rc = BN == 64 ? launch_gemm<64, true, 4>(ma, mb, p, splits, s) : launch_gemm<128, true, 3>(ma, mb, p, splits, s);
+  } else {
+    rc = BN == 64 ? launch_gemm<64, false, 6>(ma, mb, p, splits, s) : launch_gemm<128, false, 6>(ma, mb, p, splits, s);
+  }
   if (rc) return rc;
   if (splits > 1) {
     const long long n4 = M * N / 4;
     const unsigned grid = static_cast<unsigned>(std::min<long long>((n4 + 255) / 256, 148ll * 16));
-    splitk_reduce_kernel<<<grid, 256, 0, s>>>(splitk_ws, C, n4, splits);
-    return cuda_ok("splitk_reduce_kernel", cudaGetLastError());
+    return cuda_ok("splitk_reduce_kernel", launch_pdl(splitk_reduce_kernel, dim3(grid), dim3(256), 0, s,
+                                                      static_cast<const float*>(splitk_ws), C, n4, splits));
   }
   return PVAE_OK;
 }

@@ -25,4 +25,22 @@ inline int cuda_ok(const char* what, cudaError_t e) {
   return fail(PVAE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream drains;
+// it calls pdl_wait() (griddepcontrol.wait) before touching anything the predecessor produced, and
+// pdl_launch_dependents() early so that its own successor can do the same.  Hides launch latency and
+// kernel prologues behind the previous kernel's tail.  pvae_set_pdl(0) turns the attribute off.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace pvae

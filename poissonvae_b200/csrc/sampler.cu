@@ -6,9 +6,10 @@
 //            arrival chains in lock step - one Philox4x32-10 block per event feeds the four chains.
 //            A chain leaves as soon as every later term is exactly zero (lossless early exit).
 //            Quads still alive after `phase_a` events are parked in shared memory.
-//   Phase B  each warp takes parked quads one at a time and walks the rest of the chain 32 events
-//            per step: lane i draws event n0+i, the arrival times come from a warp prefix sum
-//            (shfl.up), so one long chain costs n/32 steps instead of stalling 31 idle lanes.
+//   Phase B  parked quads are finished by groups of 8 lanes (four quads per warp at a time), 8 events
+//            per step: lane i of a group draws event n0+i, the arrival times come from a prefix sum
+//            over the group (shfl.up), so one long chain costs n/8 steps of 8 busy lanes instead of
+//            n steps of one busy lane.
 // The (n_exp, B, K) tensors of the reference never exist; per-sample KL sums and per-latent
 // (batch) gradient sums are produced without atomics, in a fixed order.
 //
@@ -117,38 +118,12 @@ __device__ __forceinline__ bool phase_a(const SamplerParams& p, uint32_t quad, u
   return n_end >= p.n_exp;
 }
 
-// ---- phase B: one warp finishes one parked quad, 32 events per step ----------------------------
-template <int MODE, int IND>
-__device__ __forceinline__ void phase_b(const SamplerParams& p, uint32_t quad, uint32_t off_lo, uint32_t off_hi,
-                                        const float (&rate)[4], float (&t0)[4], float (&acc)[4], int lane) {
-  float inv_rate[4], part[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) inv_rate[j] = __frcp_rn(rate[j]);
-  for (int n0 = p.phase_a; n0 < p.n_exp; n0 += 32) {
-    const int n = n0 + lane;
-    const bool valid = n < p.n_exp;
-    const uint4 r = philox4x32_10(quad, static_cast<uint32_t>(n), off_lo, off_hi, p.ks);
-    const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float x = valid ? div_by_rate<false>(exponential_from_bits(bits[j]), rate[j], inv_rate[j]) : 0.f;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {  // inclusive prefix sum over the lanes
-        const float y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-      }
-      const float t = t0[j] + x;
-      float f, df;
-      soft_term<IND, MODE == kBwd>(p, t, f, df);
-      const float term = MODE == kBwd ? df * t : f;
-      part[j] += valid ? term : 0.f;
-      t0[j] = __shfl_sync(0xffffffffu, t, 31);
-    }
-    if (fminf(fminf(t0[0], t0[1]), fminf(t0[2], t0[3])) > p.t_exit) break;
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) acc[j] += warp_sum(part[j]);
-}
+// ---- phase B: a group of kGroup lanes finishes one parked quad, kGroup events per step -----------
+// 32 / kGroup quads are walked by a warp at once.  Lane gl of a group draws event n0 + gl; the arrival
+// times come from a prefix sum over the group's lanes (shfl.up).  A group that finishes its quad takes
+// the next one from the block's queue, so long and short chains share a warp without waiting for each
+// other.  Every lane runs every step (the shuffles need them); idle groups contribute exact zeros.
+constexpr int kGroup = 8;
 
 // ---- prologue: encoder output -> log_dr, u, rate (and the clamp derivatives for the backward) ---
 struct Latent {
@@ -198,10 +173,12 @@ template <int MODE, int IND, bool RAW>
 __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p) {
   __shared__ float s_tab[kSlotWords][kSlots];  // parked quads, one word-plane per field
   __shared__ unsigned short s_list[kSlots];
-  __shared__ int s_count;
+  __shared__ int s_count, s_next;
   __shared__ float s_rowsum[kMaxRows][kWarps];
   __shared__ float s_max[kWarps];
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const long long row0 = static_cast<long long>(blockIdx.x) * p.rows_per_block;
@@ -219,7 +196,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
   for (long long k0 = 0; k0 < p.K; k0 += kColsPerPass) {
     const long long k = k0 + 4 * tid;
     const bool act = k < p.K;
-    if (tid == 0) s_count = 0;
+    if (tid == 0) s_count = 0, s_next = 0;
     __syncthreads();
     float lr[4] = {0.f, 0.f, 0.f, 0.f}, bias[4] = {0.f, 0.f, 0.f, 0.f}, elr[4] = {0.f, 0.f, 0.f, 0.f};
     if (!RAW && act) {
@@ -324,21 +301,80 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
 
     // ---------------- phase B ----------------
     const int n_parked = s_count;
-    if (MODE != kFwdHard) {
-      for (int i = warp; i < n_parked; i += kWarps) {
-        const int slot = s_list[i];
-        const int r = slot / kThreads, owner = slot % kThreads;
-        float rate[4], t0[4], acc[4];
+    if (MODE != kFwdHard && n_parked > 0) {
+      const int gl = lane % kGroup;
+      bool has = false, done = true;  // done: this group needs a (new) quad
+      int slot = 0, n0 = 0;
+      uint32_t quad = 0;
+      float rate[4] = {1.f, 1.f, 1.f, 1.f}, inv_rate[4] = {1.f, 1.f, 1.f, 1.f}, t0[4] = {0.f, 0.f, 0.f, 0.f};
+      float acc[4] = {0.f, 0.f, 0.f, 0.f}, part[4] = {0.f, 0.f, 0.f, 0.f};
+      while (true) {
+        if (__any_sync(0xffffffffu, done)) {
+          // retire finished quads (group-wide sum of the per-lane partial sums), then refill from the queue
+          float tot[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rate[j] = s_tab[j][slot], t0[j] = s_tab[4 + j][slot], acc[j] = s_tab[8 + j][slot];
-        const long long base = (row0 + r) * p.K + k0 + 4 * owner;
-        const uint32_t quad = static_cast<uint32_t>(((p.row_offset + row0 + r) * p.K + k0 + 4 * owner) >> 2);
-        phase_b<MODE, IND>(p, quad, off_lo, off_hi, rate, t0, acc, lane);
-        if (MODE == kBwd) {
-          if (lane < 4) s_tab[8 + lane][slot] = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
-        } else if (lane == 0) {
-          stg4(p.z + base, make_float4(acc[0], acc[1], acc[2], acc[3]));
+          for (int j = 0; j < 4; ++j) {
+            float v = part[j];
+#pragma unroll
+            for (int o = kGroup / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, kGroup);
+            tot[j] = acc[j] + v;
+          }
+          int next = 0;
+          if (done && gl == 0) {
+            if (has) {
+              if (MODE == kBwd) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s_tab[8 + j][slot] = tot[j];
+              } else {
+                const int r = slot / kThreads, owner = slot % kThreads;
+                stg4(p.z + (row0 + r) * p.K + k0 + 4 * owner, make_float4(tot[0], tot[1], tot[2], tot[3]));
+              }
+            }
+            next = atomicAdd(&s_next, 1);
+          }
+          next = __shfl_sync(0xffffffffu, next, 0, kGroup);
+          if (done) {
+            has = next < n_parked;
+            if (has) {
+              slot = s_list[next];
+              const int r = slot / kThreads, owner = slot % kThreads;
+              quad = static_cast<uint32_t>(((p.row_offset + row0 + r) * p.K + k0 + 4 * owner) >> 2);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                rate[j] = s_tab[j][slot];
+                inv_rate[j] = __frcp_rn(rate[j]);
+                t0[j] = s_tab[4 + j][slot];
+                acc[j] = s_tab[8 + j][slot];
+                part[j] = 0.f;
+              }
+              n0 = n_a;
+            }
+            done = false;  // queue exhausted: the group idles (has == false) without asking again
+          }
+          if (__all_sync(0xffffffffu, !has)) break;
         }
+        // one step: kGroup events of this group's quad
+        const int n = n0 + gl;
+        const bool valid = has && !done && n < p.n_exp;
+        const uint4 rr = philox4x32_10(quad, static_cast<uint32_t>(n), off_lo, off_hi, p.ks);
+        const uint32_t bits[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float x = valid ? div_by_rate<false>(exponential_from_bits(bits[j]), rate[j], inv_rate[j]) : 0.f;
+#pragma unroll
+          for (int o = 1; o < kGroup; o <<= 1) {  // inclusive prefix sum over the group's lanes
+            const float y = __shfl_up_sync(0xffffffffu, x, o, kGroup);
+            if (gl >= o) x += y;
+          }
+          const float t = t0[j] + x;
+          float f, df;
+          soft_term<IND, MODE == kBwd>(p, t, f, df);
+          const float term = MODE == kBwd ? df * t : f;
+          part[j] += valid ? term : 0.f;
+          t0[j] = __shfl_sync(0xffffffffu, t, kGroup - 1, kGroup);
+        }
+        n0 += kGroup;
+        if (has && (n0 >= p.n_exp || fminf(fminf(t0[0], t0[1]), fminf(t0[2], t0[3])) > p.t_exit)) done = true;
       }
     }
     if (MODE == kBwd) {
@@ -399,6 +435,8 @@ constexpr int kRedX = 32, kRedY = 32;
 __global__ void __launch_bounds__(kRedX* kRedY) colsum_finalize_kernel(const float* __restrict__ part, float* __restrict__ out,
                                                                       long long P, long long K, int accumulate) {
   __shared__ float s[kRedY][kRedX + 1];
+  pdl_launch_dependents();
+  pdl_wait();
   const int tx = threadIdx.x, ty = threadIdx.y;
   const long long k = static_cast<long long>(blockIdx.x) * kRedX + tx;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -425,6 +463,8 @@ __global__ void __launch_bounds__(kRedX* kRedY) colsum_finalize_kernel(const flo
 // ---- standalone KL ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) kl_fwd_kernel(const float* __restrict__ log_dr, const float* __restrict__ log_r,
                                                      float* __restrict__ kl, long long n4, long long K) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += gridDim.x * 256ll) {
     const long long e = 4 * i;
     const float4 d = ldg4(log_dr + e);
@@ -441,6 +481,8 @@ __global__ void __launch_bounds__(256) kl_fwd_kernel(const float* __restrict__ l
 __global__ void __launch_bounds__(kThreads) kl_bwd_kernel(const float* __restrict__ log_dr, const float* __restrict__ log_r,
                                                           const float* __restrict__ g_kl, float* __restrict__ g_log_dr,
                                                           float* __restrict__ part, long long B, long long K, int rows_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long row0 = static_cast<long long>(blockIdx.x) * rows_per_block;
   const int nrows = static_cast<int>(min(static_cast<long long>(rows_per_block), B - row0));
   for (long long k = 4 * threadIdx.x; k < K; k += kColsPerPass) {
@@ -493,7 +535,10 @@ __global__ void debug_log_check_kernel(unsigned long long* mismatches) {
 }
 
 // ---- host-side launch --------------------------------------------------------------------------
+static int g_rows_per_block = 0;  // 0 = automatic
+
 static int rows_per_block_for(long long B) {
+  if (g_rows_per_block > 0) return g_rows_per_block;
   // enough blocks for several waves over 148 SMs, at most kMaxRows rows per block
   const long long target_blocks = 148ll * 8;
   long long r = B / target_blocks;
@@ -505,14 +550,13 @@ static int rows_per_block_for(long long B) {
 template <int MODE, bool RAW>
 static cudaError_t launch_ind(const SamplerParams& p, int indicator, dim3 grid, cudaStream_t s) {
   switch (indicator) {
-    case kSigmoid: sampler_kernel<MODE, kSigmoid, RAW><<<grid, kThreads, 0, s>>>(p); break;
-    case kCosine: sampler_kernel<MODE, kCosine, RAW><<<grid, kThreads, 0, s>>>(p); break;
-    case kLinear: sampler_kernel<MODE, kLinear, RAW><<<grid, kThreads, 0, s>>>(p); break;
-    case kCubic: sampler_kernel<MODE, kCubic, RAW><<<grid, kThreads, 0, s>>>(p); break;
-    case kQuintic: sampler_kernel<MODE, kQuintic, RAW><<<grid, kThreads, 0, s>>>(p); break;
+    case kSigmoid: return launch_pdl(sampler_kernel<MODE, kSigmoid, RAW>, grid, dim3(kThreads), 0, s, p);
+    case kCosine: return launch_pdl(sampler_kernel<MODE, kCosine, RAW>, grid, dim3(kThreads), 0, s, p);
+    case kLinear: return launch_pdl(sampler_kernel<MODE, kLinear, RAW>, grid, dim3(kThreads), 0, s, p);
+    case kCubic: return launch_pdl(sampler_kernel<MODE, kCubic, RAW>, grid, dim3(kThreads), 0, s, p);
+    case kQuintic: return launch_pdl(sampler_kernel<MODE, kQuintic, RAW>, grid, dim3(kThreads), 0, s, p);
     default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
 }
 
 static int g_phase_a_events = 8;
@@ -553,8 +597,7 @@ static int check_common(const char* fn, long long B, long long K, long long row_
 
 static int finalize_cols(const float* part, float* out, long long P, long long K, int accumulate, cudaStream_t s) {
   dim3 grid(static_cast<unsigned>((K + kRedX - 1) / kRedX)), block(kRedX, kRedY);
-  colsum_finalize_kernel<<<grid, block, 0, s>>>(part, out, P, K, accumulate);
-  return cuda_ok("colsum_finalize", cudaGetLastError());
+  return cuda_ok("colsum_finalize", launch_pdl(colsum_finalize_kernel, grid, block, 0, s, part, out, P, K, accumulate));
 }
 
 }  // namespace pvae
@@ -565,6 +608,12 @@ extern "C" int64_t pvae_num_partials(int64_t B) {
   if (B <= 0) return 0;
   const int r = rows_per_block_for(B);
   return (B + r - 1) / r;
+}
+
+extern "C" int pvae_set_rows_per_block(int n) {
+  if (n < 0 || n > kMaxRows) return fail(PVAE_ERR_INVALID, "pvae_set_rows_per_block: n=%d must be in [0, %d]", n, kMaxRows);
+  g_rows_per_block = n;
+  return PVAE_OK;
 }
 
 extern "C" int pvae_set_phase_a_events(int n) {
@@ -668,8 +717,8 @@ extern "C" int pvae_kl_fwd(const float* log_dr, const float* log_r, float* kl, i
   if (!log_dr || !log_r || !kl) return fail(PVAE_ERR_INVALID, "pvae_kl_fwd: null pointer");
   const long long n4 = B * K / 4;
   const unsigned grid = static_cast<unsigned>(std::min<long long>((n4 + 255) / 256, 148ll * 16));
-  kl_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(log_dr, log_r, kl, n4, K);
-  return cuda_ok("pvae_kl_fwd", cudaGetLastError());
+  return cuda_ok("pvae_kl_fwd", launch_pdl(kl_fwd_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), log_dr,
+                                           log_r, kl, n4, static_cast<long long>(K)));
 }
 
 extern "C" int pvae_kl_bwd(const float* log_dr, const float* log_r, const float* g_kl, float* g_log_dr, float* g_log_r,
@@ -680,8 +729,10 @@ extern "C" int pvae_kl_bwd(const float* log_dr, const float* log_r, const float*
   const int rpb = rows_per_block_for(B);
   const long long P = (B + rpb - 1) / rpb;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  kl_bwd_kernel<<<static_cast<unsigned>(P), kThreads, 0, s>>>(log_dr, log_r, g_kl, g_log_dr, partial_ws, B, K, rpb);
-  if (int rc = cuda_ok("pvae_kl_bwd", cudaGetLastError())) return rc;
+  if (int rc = cuda_ok("pvae_kl_bwd", launch_pdl(kl_bwd_kernel, dim3(static_cast<unsigned>(P)), dim3(kThreads), 0, s, log_dr, log_r,
+                                                 g_kl, g_log_dr, partial_ws, static_cast<long long>(B),
+                                                 static_cast<long long>(K), rpb)))
+    return rc;
   return finalize_cols(partial_ws, g_log_r, P, K, accumulate, s);
 }
 

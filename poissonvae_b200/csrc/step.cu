@@ -18,6 +18,8 @@ namespace pvae {
 __global__ void __launch_bounds__(256) recon_kernel(const float* __restrict__ y, const float* __restrict__ x,
                                                     float* __restrict__ g_y, float* __restrict__ recon, long long B,
                                                     long long D, float g_scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   for (long long b = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
@@ -38,6 +40,8 @@ __global__ void __launch_bounds__(256) recon_kernel(const float* __restrict__ y,
 __global__ void __launch_bounds__(1024) loss_kernel(const float* __restrict__ recon, const float* __restrict__ kl_row,
                                                     float* __restrict__ out, long long B, float beta, float inv_bg) {
   __shared__ float s_r[32], s_k[32];
+  pdl_launch_dependents();
+  pdl_wait();
   float r = 0.f, k = 0.f;
   for (long long b = threadIdx.x; b < B; b += 1024) {
     r += recon[b];
@@ -60,6 +64,8 @@ __global__ void __launch_bounds__(1024) loss_kernel(const float* __restrict__ re
 constexpr int kNormBlocks = 148;
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ part) {
   __shared__ float s[8];
+  pdl_launch_dependents();
+  pdl_wait();
   float a = 0.f;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) a = fmaf(g[i], g[i], a);
   a = warp_sum(a);
@@ -74,6 +80,8 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
 }
 // out[0] = ||g||, out[1] = clip coefficient min(1, max_norm / (||g|| + 1e-6)) (torch clip_grad_norm_)
 __global__ void norm_finalize_kernel(const float* __restrict__ part, int nparts, float max_norm, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < nparts; ++i) t += part[i];
@@ -87,6 +95,8 @@ __global__ void norm_finalize_kernel(const float* __restrict__ part, int nparts,
 __global__ void __launch_bounds__(256) adamax_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                      float* __restrict__ u, long long n, float clr, float beta1, float beta2,
                                                      float eps, float weight_decay, const float* __restrict__ clip_coef) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float cc = clip_coef != nullptr ? clip_coef[1] : 1.f;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
     float gi = g[i] * cc;
@@ -110,15 +120,16 @@ extern "C" int pvae_recon_residual(const float* y, const float* x, float* g_y, f
   if (B == 0) return PVAE_OK;
   if (!y || !x) return fail(PVAE_ERR_INVALID, "pvae_recon_residual: null y/x");
   const unsigned grid = static_cast<unsigned>(std::min<long long>((B + 7) / 8, 148ll * 8));
-  recon_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, x, g_y, recon, B, D, g_scale);
-  return cuda_ok("pvae_recon_residual", cudaGetLastError());
+  return cuda_ok("pvae_recon_residual", launch_pdl(recon_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), y, x,
+                                                   g_y, recon, static_cast<long long>(B), static_cast<long long>(D), g_scale));
 }
 
 extern "C" int pvae_loss_assemble(const float* recon, const float* kl_rowsum, float* out3, int64_t B, float beta,
                                   int64_t B_global, void* stream) {
   if (B <= 0 || B_global <= 0 || !recon || !kl_rowsum || !out3) return fail(PVAE_ERR_INVALID, "pvae_loss_assemble: bad argument");
-  loss_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(recon, kl_rowsum, out3, B, beta, 1.f / static_cast<float>(B_global));
-  return cuda_ok("pvae_loss_assemble", cudaGetLastError());
+  return cuda_ok("pvae_loss_assemble", launch_pdl(loss_kernel, dim3(1), dim3(1024), 0, static_cast<cudaStream_t>(stream), recon,
+                                                  kl_rowsum, out3, static_cast<long long>(B), beta,
+                                                  1.f / static_cast<float>(B_global)));
 }
 
 extern "C" int64_t pvae_grad_norm_ws_floats(void) { return kNormBlocks; }
@@ -126,9 +137,10 @@ extern "C" int64_t pvae_grad_norm_ws_floats(void) { return kNormBlocks; }
 extern "C" int pvae_grad_norm(const float* g, int64_t n, float max_norm, float* ws, float* out2, void* stream) {
   if (n <= 0 || !g || !ws || !out2) return fail(PVAE_ERR_INVALID, "pvae_grad_norm: bad argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  sumsq_partial_kernel<<<kNormBlocks, 256, 0, s>>>(g, n, ws);
-  norm_finalize_kernel<<<1, 32, 0, s>>>(ws, kNormBlocks, max_norm, out2);
-  return cuda_ok("pvae_grad_norm", cudaGetLastError());
+  if (int rc = cuda_ok("pvae_grad_norm", launch_pdl(sumsq_partial_kernel, dim3(kNormBlocks), dim3(256), 0, s, g,
+                                                    static_cast<long long>(n), ws)))
+    return rc;
+  return cuda_ok("pvae_grad_norm", launch_pdl(norm_finalize_kernel, dim3(1), dim3(32), 0, s, ws, kNormBlocks, max_norm, out2));
 }
 
 extern "C" int pvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, float lr, int step,
@@ -138,7 +150,7 @@ extern "C" int pvae_adamax_step(float* p, const float* g, float* exp_avg, float*
   const double bias_correction = 1.0 - pow(static_cast<double>(beta1), step);  // base/adamax.py:75-76
   const float clr = static_cast<float>(static_cast<double>(lr) / bias_correction);
   const unsigned grid = static_cast<unsigned>(std::min<long long>((n + 255) / 256, 148ll * 8));
-  adamax_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, exp_avg, exp_inf, n, clr, beta1, beta2, eps,
-                                                                      weight_decay, clip_coef);
-  return cuda_ok("pvae_adamax_step", cudaGetLastError());
+  return cuda_ok("pvae_adamax_step", launch_pdl(adamax_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g,
+                                                exp_avg, exp_inf, static_cast<long long>(n), clr, beta1, beta2, eps,
+                                                weight_decay, clip_coef));
 }

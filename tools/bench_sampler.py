@@ -39,10 +39,13 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--single", action="store_true", help="only random_init, temp 1, lossless (for ncu captures)")
     ap.add_argument("--phase_a", type=int, default=0, help="override pvae_set_phase_a_events")
+    ap.add_argument("--rows", type=int, default=0, help="override pvae_set_rows_per_block")
     args = ap.parse_args()
     lib = _lib.load()
     if args.phase_a > 0:
         assert lib.pvae_set_phase_a_events(args.phase_a) == 0
+    if args.rows > 0:
+        assert lib.pvae_set_rows_per_block(args.rows) == 0
     B, K, n_exp = args.B, args.K, args.n_exp
     s = torch.cuda.current_stream().cuda_stream
     g = torch.Generator("cuda").manual_seed(0)
