@@ -63,25 +63,28 @@ int64_t pvae_num_partials(int64_t B);
  * Poisson.rsample base/distributions.py:55-81 and PoissonVAE.loss_kl main/vae.py:446-450.
  *   h (B,K) = fc_enc(x) WITHOUT bias; b_enc (K) optional bias; log_r (K) prior log-rates.
  *   z (B,K) out.  Optional outputs (NULL to skip): log_dr (B,K), rate (B,K), kl (B,K),
- *   kl_rowsum (B) = kl.sum(1), rate_max (1 float, must be pre-set by the caller, updated with max).
+ *   kl_rowsum (B) = kl.sum(1), rate_max (1 float, must be pre-set by the caller, updated with max),
+ *   dz_acc (B,K) = sum_n f'(logit_n) t_n, accumulated in the same walk of the chain: handing it to
+ *   pvae_sampler_bwd turns the backward into one elementwise pass (12 -> 16 B/latent of L2-resident traffic
+ *   instead of a second walk of the chain).
  *   temp > 0: relaxed counts with `indicator`; temp == 0: hard counts #{t_n <= 1} (the reference
  *   draws torch.poisson there, base/distributions.py:56-57,83-85 - same law, different stream). */
 int pvae_sampler_fwd(const float* h, const float* log_r, const float* b_enc, float* z, float* log_dr,
-                     float* rate, float* kl, float* kl_rowsum, float* rate_max, int64_t B, int64_t K,
+                     float* rate, float* kl, float* kl_rowsum, float* rate_max, float* dz_acc, int64_t B, int64_t K,
                      int64_t row_offset, int n_exp, float temp, int indicator, int exc_only,
                      float exit_logit, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
                      void* stream);
 
-/* ---- backward of the above, recomputing the chain from the Philox counters ------------------
+/* ---- backward of the above: from dz_acc if given, else recomputing the chain from the Philox counters
  * Replaces autograd through base/distributions.py:55-81 and main/vae.py:393-415,446-450
  * (closed form: SURVEY.md section 8 row a13).  Must be called with the same h/log_r/b_enc,
  * shape, n_exp, temp, indicator, exc_only, exit_logit, seed and offset as the forward.
  *   g_z (B,K) upstream gradient wrt z; g_log_dr (B,K) optional upstream gradient wrt the returned
- *   log_dr; kl_scale = beta / B_global fuses the gradient of beta * mean_b(sum_k kl) (0 to skip).
+ *   log_dr; dz_acc (B,K) optional, as written by the forward (NULL: recompute the chain); kl_scale = beta / B_global fuses the gradient of beta * mean_b(sum_k kl) (0 to skip).
  *   g_h (B,K) out; g_log_r (K) and g_b_enc (K, optional) out - overwritten, or added to if
  *   accumulate != 0; partial_ws: workspace of 2 * pvae_num_partials(B) * K floats. */
 int pvae_sampler_bwd(const float* h, const float* log_r, const float* b_enc, const float* g_z,
-                     const float* g_log_dr, float kl_scale, float* g_h, float* g_log_r, float* g_b_enc,
+                     const float* g_log_dr, const float* dz_acc, float kl_scale, float* g_h, float* g_log_r, float* g_b_enc,
                      float* partial_ws, int accumulate, int64_t B, int64_t K, int64_t row_offset,
                      int n_exp, float temp, int indicator, int exc_only, float exit_logit,
                      uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream);
@@ -90,10 +93,10 @@ int pvae_sampler_bwd(const float* h, const float* log_r, const float* b_enc, con
  * Replaces Poisson.__init__ + rsample base/distributions.py:6-30,55-81 for a caller-supplied
  * log_rate of n_rows x K (PoissonVAE.sample main/vae.py:431-444 and standalone use).
  * clamp < 0 means "no clamp" (reference clamp=None), otherwise softclamp_upper(log_rate, clamp). */
-int pvae_rsample_fwd(const float* log_rate, float* z, float* rate, int64_t B, int64_t K, int64_t row_offset,
+int pvae_rsample_fwd(const float* log_rate, float* z, float* rate, float* dz_acc, int64_t B, int64_t K, int64_t row_offset,
                      int n_exp, float temp, int indicator, float clamp, float exit_logit, uint64_t seed,
                      uint64_t offset, const uint64_t* offset_dev, void* stream);
-int pvae_rsample_bwd(const float* log_rate, const float* g_z, float* g_log_rate, int64_t B, int64_t K,
+int pvae_rsample_bwd(const float* log_rate, const float* g_z, const float* dz_acc, float* g_log_rate, int64_t B, int64_t K,
                      int64_t row_offset, int n_exp, float temp, int indicator, float clamp, float exit_logit,
                      uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream);
 

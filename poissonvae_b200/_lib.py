@@ -42,10 +42,10 @@ _SIGNATURES = {
     "pvae_last_error": (C.c_char_p, []),
     "pvae_set_pdl": (_i, [_i]),
     "pvae_num_partials": (_i64, [_i64]),
-    "pvae_sampler_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _f, _i, _i, _f, _u64, _u64, _p, _p]),
-    "pvae_sampler_bwd": (_i, [_p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _i, _i64, _i64, _i64, _i, _f, _i, _i, _f, _u64, _u64, _p, _p]),
-    "pvae_rsample_fwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i, _f, _i, _f, _f, _u64, _u64, _p, _p]),
-    "pvae_rsample_bwd": (_i, [_p, _p, _p, _i64, _i64, _i64, _i, _f, _i, _f, _f, _u64, _u64, _p, _p]),
+    "pvae_sampler_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _f, _i, _i, _f, _u64, _u64, _p, _p]),
+    "pvae_sampler_bwd": (_i, [_p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _i, _i64, _i64, _i64, _i, _f, _i, _i, _f, _u64, _u64, _p, _p]),
+    "pvae_rsample_fwd": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i, _f, _i, _f, _f, _u64, _u64, _p, _p]),
+    "pvae_rsample_bwd": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i, _f, _i, _f, _f, _u64, _u64, _p, _p]),
     "pvae_kl_fwd": (_i, [_p, _p, _p, _i64, _i64, _p]),
     "pvae_kl_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _i64, _p]),
     "pvae_gemm_ws_floats": (_i64, [_i64, _i64, _i]),

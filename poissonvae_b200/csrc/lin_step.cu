@@ -2,12 +2,12 @@
 // forward + loss + backward (closed form) for this rank's slice of the batch.
 //
 //   h   = x W_enc^T                                   tcgen05 GEMM            main/vae.py:44-51
-//   z   = rsample(softclamps(h, log_r)), kl row sums  fused sampler           main/vae.py:393-415, base/distributions.py:55-81
+//   z, dz_acc = rsample(softclamps(h, log_r)), kl sums fused sampler           main/vae.py:393-415, base/distributions.py:55-81
 //   y   = z W_dec^T                                   tcgen05 GEMM            main/vae.py:59-60
 //   g_y = 2 (y - x) / B_global, recon                 residual kernel         main/vae.py:68-72
 //   loss = sum_b(recon + beta kl) / B_global          loss kernel             main/train_vae.py:347-351
 //   g_W_dec = g_y^T z (split-K), g_z = g_y W_dec      tcgen05 GEMMs
-//   g_h, g_log_r (+ g_b_enc)                          sampler backward, chain recomputed from the Philox counters
+//   g_h, g_log_r (+ g_b_enc)                          sampler backward from the dz_acc the forward stored (elementwise)
 //   g_W_enc = g_h^T x (split-K)                       tcgen05 GEMM
 // The caller then all-reduces the flat gradient buffer (data parallel) and calls pvae_grad_norm /
 // pvae_adamax_step.  Parameter and gradient buffers are flat: [log_r (K) | W_enc (K,D) | W_dec (D,K) | b_enc (K)].
@@ -20,7 +20,7 @@
 namespace {
 
 struct Ws {
-  float *h, *z, *y, *g_y, *g_z, *g_h, *recon, *klrow, *partials, *splitk;
+  float *h, *z, *dz, *y, *g_y, *g_z, *g_h, *recon, *klrow, *partials, *splitk;
   int64_t total;
 };
 
@@ -40,7 +40,7 @@ Ws carve(float* base, int64_t B, int64_t K, int64_t D) {
     o += (n + 3) & ~int64_t(3);  // keep every buffer 16-byte aligned
     return p;
   };
-  w.h = take(B * K), w.z = take(B * K), w.y = take(B * D), w.g_y = take(B * D), w.g_z = take(B * K), w.g_h = take(B * K);
+  w.h = take(B * K), w.z = take(B * K), w.dz = take(B * K), w.y = take(B * D), w.g_y = take(B * D), w.g_z = take(B * K), w.g_h = take(B * K);
   w.recon = take(B), w.klrow = take(B);
   w.partials = take(2 * pvae_num_partials(B) * K);
   const int64_t s1 = pvae_gemm_ws_floats(D, K, wgrad_splits(D, K, B)), s2 = pvae_gemm_ws_floats(K, D, wgrad_splits(K, D, B));
@@ -81,7 +81,7 @@ extern "C" int pvae_lin_step_fwd_bwd(const float* x, const float* params, float*
   // ---- forward
   if ((rc = pvae_gemm_tf32(x, w_enc, w.h, B, K, D, 1, 1, precise, 1, nullptr, s))) return rc;
   mark(0);
-  if ((rc = pvae_sampler_fwd(w.h, log_r, b_enc, w.z, nullptr, nullptr, nullptr, w.klrow, rate_max, B, K, row_offset, n_exp,
+  if ((rc = pvae_sampler_fwd(w.h, log_r, b_enc, w.z, nullptr, nullptr, nullptr, w.klrow, rate_max, w.dz, B, K, row_offset, n_exp,
                              temp, indicator, exc_only, exit_logit, seed, offset, offset_dev, s)))
     return rc;
   mark(1);
@@ -92,7 +92,7 @@ extern "C" int pvae_lin_step_fwd_bwd(const float* x, const float* params, float*
   if ((rc = pvae_gemm_tf32(w.g_y, w.z, g_w_dec, D, K, B, 0, 0, precise, wgrad_splits(D, K, B), w.splitk, s))) return rc;
   if ((rc = pvae_gemm_tf32(w.g_y, w_dec, w.g_z, B, K, D, 1, 0, precise, 1, nullptr, s))) return rc;
   mark(2);
-  if ((rc = pvae_sampler_bwd(w.h, log_r, b_enc, w.g_z, nullptr, beta / static_cast<float>(B_global), w.g_h, g_log_r, g_b_enc,
+  if ((rc = pvae_sampler_bwd(w.h, log_r, b_enc, w.g_z, nullptr, w.dz, beta / static_cast<float>(B_global), w.g_h, g_log_r, g_b_enc,
                              w.partials, 0, B, K, row_offset, n_exp, temp, indicator, exc_only, exit_logit, seed, offset,
                              offset_dev, s)))
     return rc;

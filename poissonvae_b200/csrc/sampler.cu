@@ -31,11 +31,13 @@ namespace pvae {
 constexpr int kThreads = 128;               // threads per block
 constexpr int kWarps = kThreads / 32;
 constexpr int kColsPerPass = 4 * kThreads;  // latents of one row a block covers per pass
-constexpr int kMaxRows = 4;                 // rows per block tile
+constexpr int kMaxRows = 3;                 // rows per block tile
 constexpr int kSlots = kMaxRows * kThreads; // parked-quad table: one slot per (row, thread)
-constexpr int kSlotWords = 12;              // rate[4], t[4], acc[4]
+constexpr int kSlotWords = 16;              // rate[4], t[4], acc[4], acc2[4]
 
-enum Mode : int { kFwdSoft = 0, kFwdHard = 1, kBwd = 2 };
+// kFwdSoft: z only.  kFwdBoth: z and dz_acc = sum_n f'(l_n) t_n in one walk of the chain (training forward).
+// kBwd: backward that recomputes the chain from the Philox counters.  kBwdSaved: backward from a stored dz_acc.
+enum Mode : int { kFwdSoft = 0, kFwdHard = 1, kBwd = 2, kFwdBoth = 3, kBwdSaved = 4 };
 
 struct SamplerParams {
   const float* h;         // (B,K) encoder output, or log_rate in RAW mode
@@ -43,6 +45,8 @@ struct SamplerParams {
   const float* b_enc;     // (K) or null
   const float* g_z;       // (B,K) bwd
   const float* g_log_dr;  // (B,K) bwd, optional
+  const float* dz_in;     // (B,K) kBwdSaved: sum_n f'(l_n) t_n written by the forward
+  float* dz_out;          // (B,K) kFwdBoth
   float* z;
   float* log_dr;
   float* rate;
@@ -94,9 +98,9 @@ __device__ __forceinline__ float div_by_rate(float e, float rate, float inv_rate
 template <int MODE, int IND>
 __device__ __forceinline__ bool phase_a(const SamplerParams& p, uint32_t quad, uint32_t off_lo, uint32_t off_hi,
                                         const float (&rate)[4], const float (&inv_rate)[4], float (&t)[4],
-                                        float (&acc)[4], int n_end) {
+                                        float (&acc)[4], float (&acc2)[4], int n_end) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) t[j] = acc[j] = 0.f;
+  for (int j = 0; j < 4; ++j) t[j] = acc[j] = acc2[j] = 0.f;
   const float t_exit = p.t_exit;
   for (int n = 0; n < n_end; ++n) {
     const uint4 r = philox4x32_10(quad, static_cast<uint32_t>(n), off_lo, off_hi, p.ks);
@@ -109,8 +113,9 @@ __device__ __forceinline__ bool phase_a(const SamplerParams& p, uint32_t quad, u
         acc[j] += (t[j] <= 1.f) ? 1.f : 0.f;
       } else {
         float f, df;
-        soft_term<IND, MODE == kBwd>(p, t[j], f, df);
+        soft_term<IND, MODE == kBwd || MODE == kFwdBoth>(p, t[j], f, df);
         acc[j] = MODE == kBwd ? fmaf(df, t[j], acc[j]) : acc[j] + f;
+        if (MODE == kFwdBoth) acc2[j] = fmaf(df, t[j], acc2[j]);
       }
     }
     if (fminf(fminf(t[0], t[1]), fminf(t[2], t[3])) > t_exit) return true;
@@ -188,8 +193,9 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
   const uint32_t off_lo = static_cast<uint32_t>(off), off_hi = static_cast<uint32_t>(off >> 32);
   const int n_a = min(p.phase_a, p.n_exp);
 
+  constexpr bool kIsBwd = MODE == kBwd || MODE == kBwdSaved;
   float rmax = 0.f;
-  const bool want_rowsum = MODE != kBwd && !RAW && p.kl_rowsum != nullptr;
+  const bool want_rowsum = !kIsBwd && !RAW && p.kl_rowsum != nullptr;
   if (tid < kMaxRows * kWarps) (&s_rowsum[0][0])[tid] = 0.f;
 
   // every thread runs every pass so that the block-level steps below see whole warps
@@ -251,11 +257,11 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
         float rate[4], inv_rate[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          q[j] = prologue<RAW, MODE == kBwd>(p, hv[j], lr[j], bias[j]);
+          q[j] = prologue<RAW, kIsBwd>(p, hv[j], lr[j], bias[j]);
           rate[j] = q[j].rate;
-          inv_rate[j] = __frcp_rn(rate[j]);
+          inv_rate[j] = MODE == kBwdSaved ? 0.f : __frcp_rn(rate[j]);
         }
-        if (MODE != kBwd) {  // outputs that do not depend on the chain
+        if (!kIsBwd) {  // outputs that do not depend on the chain
           if (p.rate != nullptr) stg4(p.rate + base, make_float4(rate[0], rate[1], rate[2], rate[3]));
           if (p.rate_max != nullptr) rmax = fmaxf(fmaxf(fmaxf(rate[0], rate[1]), fmaxf(rate[2], rate[3])), rmax);
           if (!RAW) {
@@ -274,11 +280,21 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
           }
         }
         const uint32_t quad = static_cast<uint32_t>(((p.row_offset + row) * p.K + k) >> 2);
-        float t[4], acc[4];
-        const bool done = phase_a<MODE, IND>(p, quad, off_lo, off_hi, rate, inv_rate, t, acc, n_a);
+        float t[4], acc[4], acc2[4];
+        bool done = true;
+        if (MODE == kBwdSaved) {  // the forward already walked the chain
+          const float4 d4 = ldg4(p.dz_in + base);
+          acc[0] = d4.x, acc[1] = d4.y, acc[2] = d4.z, acc[3] = d4.w;
+        } else {
+          done = phase_a<MODE, IND>(p, quad, off_lo, off_hi, rate, inv_rate, t, acc, acc2, n_a);
+        }
         if (done) {
-          if (MODE != kBwd) stg4(p.z + base, make_float4(acc[0], acc[1], acc[2], acc[3]));
-          else bwd_finish(base, q, acc);
+          if (kIsBwd) {
+            bwd_finish(base, q, acc);
+          } else {
+            stg4(p.z + base, make_float4(acc[0], acc[1], acc[2], acc[3]));
+            if (MODE == kFwdBoth) stg4(p.dz_out + base, make_float4(acc2[0], acc2[1], acc2[2], acc2[3]));
+          }
         } else {
           const int slot = r * kThreads + tid;
 #pragma unroll
@@ -286,6 +302,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
             s_tab[j][slot] = rate[j];
             s_tab[4 + j][slot] = t[j];
             s_tab[8 + j][slot] = acc[j];
+            if (MODE == kFwdBoth) s_tab[12 + j][slot] = acc2[j];
           }
           s_list[atomicAdd(&s_count, 1)] = static_cast<unsigned short>(slot);
           parked |= 1u << r;
@@ -301,23 +318,28 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
 
     // ---------------- phase B ----------------
     const int n_parked = s_count;
-    if (MODE != kFwdHard && n_parked > 0) {
+    if (MODE != kFwdHard && MODE != kBwdSaved && n_parked > 0) {
       const int gl = lane % kGroup;
       bool has = false, done = true;  // done: this group needs a (new) quad
       int slot = 0, n0 = 0;
       uint32_t quad = 0;
       float rate[4] = {1.f, 1.f, 1.f, 1.f}, inv_rate[4] = {1.f, 1.f, 1.f, 1.f}, t0[4] = {0.f, 0.f, 0.f, 0.f};
       float acc[4] = {0.f, 0.f, 0.f, 0.f}, part[4] = {0.f, 0.f, 0.f, 0.f};
+      float acc2[4] = {0.f, 0.f, 0.f, 0.f}, part2[4] = {0.f, 0.f, 0.f, 0.f};
       while (true) {
         if (__any_sync(0xffffffffu, done)) {
           // retire finished quads (group-wide sum of the per-lane partial sums), then refill from the queue
-          float tot[4];
+          float tot[4], tot2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float v = part[j];
+            float v = part[j], v2 = part2[j];
 #pragma unroll
-            for (int o = kGroup / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, kGroup);
+            for (int o = kGroup / 2; o > 0; o >>= 1) {
+              v += __shfl_xor_sync(0xffffffffu, v, o, kGroup);
+              if (MODE == kFwdBoth) v2 += __shfl_xor_sync(0xffffffffu, v2, o, kGroup);
+            }
             tot[j] = acc[j] + v;
+            if (MODE == kFwdBoth) tot2[j] = acc2[j] + v2;
           }
           int next = 0;
           if (done && gl == 0) {
@@ -327,7 +349,9 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
                 for (int j = 0; j < 4; ++j) s_tab[8 + j][slot] = tot[j];
               } else {
                 const int r = slot / kThreads, owner = slot % kThreads;
-                stg4(p.z + (row0 + r) * p.K + k0 + 4 * owner, make_float4(tot[0], tot[1], tot[2], tot[3]));
+                const long long base = (row0 + r) * p.K + k0 + 4 * owner;
+                stg4(p.z + base, make_float4(tot[0], tot[1], tot[2], tot[3]));
+                if (MODE == kFwdBoth) stg4(p.dz_out + base, make_float4(tot2[0], tot2[1], tot2[2], tot2[3]));
               }
             }
             next = atomicAdd(&s_next, 1);
@@ -346,6 +370,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
                 t0[j] = s_tab[4 + j][slot];
                 acc[j] = s_tab[8 + j][slot];
                 part[j] = 0.f;
+                if (MODE == kFwdBoth) acc2[j] = s_tab[12 + j][slot], part2[j] = 0.f;
               }
               n0 = n_a;
             }
@@ -368,16 +393,17 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
           }
           const float t = t0[j] + x;
           float f, df;
-          soft_term<IND, MODE == kBwd>(p, t, f, df);
+          soft_term<IND, MODE == kBwd || MODE == kFwdBoth>(p, t, f, df);
           const float term = MODE == kBwd ? df * t : f;
           part[j] += valid ? term : 0.f;
+          if (MODE == kFwdBoth) part2[j] += valid ? df * t : 0.f;
           t0[j] = __shfl_sync(0xffffffffu, t, kGroup - 1, kGroup);
         }
         n0 += kGroup;
         if (has && (n0 >= p.n_exp || fminf(fminf(t0[0], t0[1]), fminf(t0[2], t0[3])) > p.t_exit)) done = true;
       }
     }
-    if (MODE == kBwd) {
+    if (kIsBwd) {
       __syncthreads();
       // the owner finishes its parked quads (prologue recomputed: cheap next to a parked chain)
       for (int r = 0; r < nrows; ++r) {
@@ -404,7 +430,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
     __syncthreads();  // the table is reused by the next pass
   }
 
-  if (MODE != kBwd) {
+  if (!kIsBwd) {
     if (want_rowsum) {
       __syncthreads();
       if (tid < nrows) {
@@ -424,6 +450,72 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
         for (int w = 1; w < kWarps; ++w) mm = fmaxf(mm, s_max[w]);
         atomicMax(reinterpret_cast<int*>(p.rate_max), __float_as_int(mm));  // rates are > 0
       }
+    }
+  }
+}
+
+// ---- backward from a stored dz_acc: one elementwise pass ------------------------------------------
+// A block owns kSavedRows rows and all K columns; a thread owns a quad of columns and keeps every row's
+// loads in flight before it computes (9..24 independent 128-bit loads per thread), then writes its column
+// partial sums.  No chain, no RNG.
+constexpr int kSavedRows = 8;
+
+template <bool RAW>
+__global__ void __launch_bounds__(kThreads) sampler_bwd_saved_kernel(const SamplerParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long row0 = static_cast<long long>(blockIdx.x) * kSavedRows;
+  const int nrows = static_cast<int>(min(static_cast<long long>(kSavedRows), p.B - row0));
+  for (long long k = 4 * threadIdx.x; k < p.K; k += kColsPerPass) {
+    float lr[4] = {0.f, 0.f, 0.f, 0.f}, bias[4] = {0.f, 0.f, 0.f, 0.f}, elr[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!RAW) {
+      const float4 v = ldg4(p.log_r + k);
+      lr[0] = v.x, lr[1] = v.y, lr[2] = v.z, lr[3] = v.w;
+      if (p.b_enc != nullptr) {
+        const float4 b = ldg4(p.b_enc + k);
+        bias[0] = b.x, bias[1] = b.y, bias[2] = b.z, bias[3] = b.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) elr[j] = expf(lr[j]);
+    }
+    float4 hv[kSavedRows], gz[kSavedRows], dz[kSavedRows], gl[kSavedRows];
+    const bool has_gld = !RAW && p.g_log_dr != nullptr;
+#pragma unroll
+    for (int r = 0; r < kSavedRows; ++r) {
+      if (r < nrows) {
+        const long long base = (row0 + r) * p.K + k;
+        hv[r] = ldg4(p.h + base), gz[r] = ldg4(p.g_z + base), dz[r] = ldg4(p.dz_in + base);
+        gl[r] = has_gld ? ldg4(p.g_log_dr + base) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float col_lr[4] = {0.f, 0.f, 0.f, 0.f}, col_b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < kSavedRows; ++r) {
+      if (r < nrows) {
+        const float h4[4] = {hv[r].x, hv[r].y, hv[r].z, hv[r].w}, g4[4] = {gz[r].x, gz[r].y, gz[r].z, gz[r].w};
+        const float d4[4] = {dz[r].x, dz[r].y, dz[r].z, dz[r].w}, l4[4] = {gl[r].x, gl[r].y, gl[r].z, gl[r].w};
+        float gh[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const Latent q = prologue<RAW, true>(p, h4[j], lr[j], bias[j]);
+          // d z / d lambda = (sum_n f'(l_n) t_n) / temp * exp(lambda) / rate; then the clamp chain
+          const float g_u = g4[j] * (d4[j] * p.inv_temp * (q.explam / q.rate)) * q.d_rate;
+          if (RAW) {
+            gh[j] = g_u;
+          } else {
+            const float d = q.log_dr, ed = expf(d);
+            gh[j] = (g_u + p.kl_scale * elr[j] * d * ed + l4[j]) * q.d_dr;
+            col_lr[j] += g_u + p.kl_scale * (elr[j] * (1.f + ed * (d - 1.f)));
+            col_b[j] += gh[j];
+          }
+        }
+        stg4(p.g_h + (row0 + r) * p.K + k, make_float4(gh[0], gh[1], gh[2], gh[3]));
+      }
+    }
+    if (!RAW) {
+      const long long pbase = static_cast<long long>(blockIdx.x) * p.K + k;
+      stg4(p.part_log_r + pbase, make_float4(col_lr[0], col_lr[1], col_lr[2], col_lr[3]));
+      if (p.part_b != nullptr) stg4(p.part_b + pbase, make_float4(col_b[0], col_b[1], col_b[2], col_b[3]));
     }
   }
 }
@@ -623,8 +715,8 @@ extern "C" int pvae_set_phase_a_events(int n) {
 }
 
 extern "C" int pvae_sampler_fwd(const float* h, const float* log_r, const float* b_enc, float* z, float* log_dr,
-                                float* rate, float* kl, float* kl_rowsum, float* rate_max, int64_t B, int64_t K,
-                                int64_t row_offset, int n_exp, float temp, int indicator, int exc_only,
+                                float* rate, float* kl, float* kl_rowsum, float* rate_max, float* dz_acc, int64_t B,
+                                int64_t K, int64_t row_offset, int n_exp, float temp, int indicator, int exc_only,
                                 float exit_logit, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
                                 void* stream) {
   if (int rc = check_common("pvae_sampler_fwd", B, K, row_offset, n_exp, temp, indicator)) return rc;
@@ -632,7 +724,8 @@ extern "C" int pvae_sampler_fwd(const float* h, const float* log_r, const float*
   if (!h || !log_r || !z) return fail(PVAE_ERR_INVALID, "pvae_sampler_fwd: null h/log_r/z");
   SamplerParams p{};
   p.h = h, p.log_r = log_r, p.b_enc = b_enc, p.z = z, p.log_dr = log_dr, p.rate = rate, p.kl = kl;
-  p.kl_rowsum = kl_rowsum, p.rate_max = rate_max;
+  p.kl_rowsum = kl_rowsum, p.rate_max = rate_max, p.dz_out = dz_acc;
+  if (dz_acc && temp == 0.f) return fail(PVAE_ERR_INVALID, "pvae_sampler_fwd: hard counts (temp == 0) have no gradient (dz_acc)");
   p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = rows_per_block_for(B);
   set_chain(p, n_exp, temp, indicator, exit_logit);
   p.clamp_dr = 10.f, p.clamp_rate = 5.f, p.exc_only = exc_only;  // main/vae.py:403-409
@@ -641,12 +734,14 @@ extern "C" int pvae_sampler_fwd(const float* h, const float* log_r, const float*
   dim3 grid(static_cast<unsigned>((B + p.rows_per_block - 1) / p.rows_per_block));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e = temp == 0.f ? launch_ind<kFwdHard, false>(p, kSigmoid, grid, s)
+                  : dz_acc    ? launch_ind<kFwdBoth, false>(p, indicator, grid, s)
                               : launch_ind<kFwdSoft, false>(p, indicator, grid, s);
   return cuda_ok("pvae_sampler_fwd", e);
 }
 
 extern "C" int pvae_sampler_bwd(const float* h, const float* log_r, const float* b_enc, const float* g_z,
-                                const float* g_log_dr, float kl_scale, float* g_h, float* g_log_r, float* g_b_enc,
+                                const float* g_log_dr, const float* dz_acc, float kl_scale, float* g_h, float* g_log_r,
+                                float* g_b_enc,
                                 float* partial_ws, int accumulate, int64_t B, int64_t K, int64_t row_offset,
                                 int n_exp, float temp, int indicator, int exc_only, float exit_logit, uint64_t seed,
                                 uint64_t offset, const uint64_t* offset_dev, void* stream) {
@@ -656,7 +751,7 @@ extern "C" int pvae_sampler_bwd(const float* h, const float* log_r, const float*
   if (!h || !log_r || !g_z || !g_h || !g_log_r || !partial_ws)
     return fail(PVAE_ERR_INVALID, "pvae_sampler_bwd: null h/log_r/g_z/g_h/g_log_r/partial_ws");
   SamplerParams p{};
-  p.h = h, p.log_r = log_r, p.b_enc = b_enc, p.g_z = g_z, p.g_log_dr = g_log_dr, p.g_h = g_h;
+  p.h = h, p.log_r = log_r, p.b_enc = b_enc, p.g_z = g_z, p.g_log_dr = g_log_dr, p.g_h = g_h, p.dz_in = dz_acc;
   p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = rows_per_block_for(B);
   const long long P = (B + p.rows_per_block - 1) / p.rows_per_block;
   p.part_log_r = partial_ws;
@@ -666,21 +761,30 @@ extern "C" int pvae_sampler_bwd(const float* h, const float* log_r, const float*
   p.offset = offset, p.offset_dev = offset_dev;
   philox_key_schedule(seed, p.ks);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (int rc = cuda_ok("pvae_sampler_bwd", launch_ind<kBwd, false>(p, indicator, dim3(static_cast<unsigned>(P)), s))) return rc;
-  if (int rc = finalize_cols(p.part_log_r, g_log_r, P, K, accumulate, s)) return rc;
+  long long Pk = P;  // partial rows actually written
+  if (dz_acc) {
+    Pk = (B + kSavedRows - 1) / kSavedRows;
+    if (int rc = cuda_ok("pvae_sampler_bwd", launch_pdl(sampler_bwd_saved_kernel<false>, dim3(static_cast<unsigned>(Pk)),
+                                                       dim3(kThreads), 0, s, p)))
+      return rc;
+  } else if (int rc = cuda_ok("pvae_sampler_bwd", launch_ind<kBwd, false>(p, indicator, dim3(static_cast<unsigned>(P)), s))) {
+    return rc;
+  }
+  if (int rc = finalize_cols(p.part_log_r, g_log_r, Pk, K, accumulate, s)) return rc;
   if (g_b_enc)
-    if (int rc = finalize_cols(p.part_b, g_b_enc, P, K, accumulate, s)) return rc;
+    if (int rc = finalize_cols(p.part_b, g_b_enc, Pk, K, accumulate, s)) return rc;
   return PVAE_OK;
 }
 
-extern "C" int pvae_rsample_fwd(const float* log_rate, float* z, float* rate, int64_t B, int64_t K, int64_t row_offset,
+extern "C" int pvae_rsample_fwd(const float* log_rate, float* z, float* rate, float* dz_acc, int64_t B, int64_t K, int64_t row_offset,
                                 int n_exp, float temp, int indicator, float clamp, float exit_logit, uint64_t seed,
                                 uint64_t offset, const uint64_t* offset_dev, void* stream) {
   if (int rc = check_common("pvae_rsample_fwd", B, K, row_offset, n_exp, temp, indicator)) return rc;
   if (B == 0) return PVAE_OK;
   if (!log_rate || !z) return fail(PVAE_ERR_INVALID, "pvae_rsample_fwd: null log_rate/z");
   SamplerParams p{};
-  p.h = log_rate, p.z = z, p.rate = rate;
+  p.h = log_rate, p.z = z, p.rate = rate, p.dz_out = dz_acc;
+  if (dz_acc && temp == 0.f) return fail(PVAE_ERR_INVALID, "pvae_rsample_fwd: hard counts (temp == 0) have no gradient (dz_acc)");
   p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = rows_per_block_for(B);
   set_chain(p, n_exp, temp, indicator, exit_logit);
   p.clamp_rate = clamp;
@@ -689,11 +793,12 @@ extern "C" int pvae_rsample_fwd(const float* log_rate, float* z, float* rate, in
   dim3 grid(static_cast<unsigned>((B + p.rows_per_block - 1) / p.rows_per_block));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e = temp == 0.f ? launch_ind<kFwdHard, true>(p, kSigmoid, grid, s)
+                  : dz_acc    ? launch_ind<kFwdBoth, true>(p, indicator, grid, s)
                               : launch_ind<kFwdSoft, true>(p, indicator, grid, s);
   return cuda_ok("pvae_rsample_fwd", e);
 }
 
-extern "C" int pvae_rsample_bwd(const float* log_rate, const float* g_z, float* g_log_rate, int64_t B, int64_t K,
+extern "C" int pvae_rsample_bwd(const float* log_rate, const float* g_z, const float* dz_acc, float* g_log_rate, int64_t B, int64_t K,
                                 int64_t row_offset, int n_exp, float temp, int indicator, float clamp, float exit_logit,
                                 uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream) {
   if (int rc = check_common("pvae_rsample_bwd", B, K, row_offset, n_exp, temp, indicator)) return rc;
@@ -701,14 +806,19 @@ extern "C" int pvae_rsample_bwd(const float* log_rate, const float* g_z, float* 
   if (B == 0) return PVAE_OK;
   if (!log_rate || !g_z || !g_log_rate) return fail(PVAE_ERR_INVALID, "pvae_rsample_bwd: null pointer");
   SamplerParams p{};
-  p.h = log_rate, p.g_z = g_z, p.g_h = g_log_rate;
+  p.h = log_rate, p.g_z = g_z, p.g_h = g_log_rate, p.dz_in = dz_acc;
   p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = rows_per_block_for(B);
   set_chain(p, n_exp, temp, indicator, exit_logit);
   p.clamp_rate = clamp;
   p.offset = offset, p.offset_dev = offset_dev;
   philox_key_schedule(seed, p.ks);
   dim3 grid(static_cast<unsigned>((B + p.rows_per_block - 1) / p.rows_per_block));
-  return cuda_ok("pvae_rsample_bwd", launch_ind<kBwd, true>(p, indicator, grid, static_cast<cudaStream_t>(stream)));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dz_acc)
+    return cuda_ok("pvae_rsample_bwd", launch_pdl(sampler_bwd_saved_kernel<true>,
+                                                  dim3(static_cast<unsigned>((B + kSavedRows - 1) / kSavedRows)),
+                                                  dim3(kThreads), 0, s, p));
+  return cuda_ok("pvae_rsample_bwd", launch_ind<kBwd, true>(p, indicator, grid, s));
 }
 
 extern "C" int pvae_kl_fwd(const float* log_dr, const float* log_r, float* kl, int64_t B, int64_t K, void* stream) {

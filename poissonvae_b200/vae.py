@@ -16,7 +16,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import _lib
+from . import _lib, distributions
 from .distributions import (EXIT_LOSSLESS, INDICATOR_CODES, Poisson, _ptr, _require_cuda_f32, _stream,
                             softclamp, softclamp_upper)
 from .linear import linear
@@ -94,17 +94,19 @@ class _EncodeSampleFn(torch.autograd.Function):
         lr = log_r.reshape(-1).contiguous()
         z = torch.empty_like(h)
         log_dr = torch.empty_like(h)
+        need = any(ctx.needs_input_grad[:3]) and temp > 0.0
+        dz = torch.empty_like(h) if (distributions.SAVE_DERIVATIVE and need) else None
         with torch.cuda.device(h.device):
             _lib.check(_lib.load().pvae_sampler_fwd(
-                _ptr(h), _ptr(lr), _ptr(b_enc), _ptr(z), _ptr(log_dr), None, None, None, None, B, K, 0, n_exp,
+                _ptr(h), _ptr(lr), _ptr(b_enc), _ptr(z), _ptr(log_dr), None, None, None, None, _ptr(dz), B, K, 0, n_exp,
                 temp, indicator, int(exc_only), exit_logit, seed, offset, None, _stream()))
-        ctx.save_for_backward(h, lr, b_enc)
+        ctx.save_for_backward(h, lr, b_enc, dz)
         ctx.args = (B, K, temp, n_exp, indicator, int(exc_only), exit_logit, seed, offset, log_r.shape)
         return z, log_dr
 
     @staticmethod
     def backward(ctx, g_z, g_log_dr):
-        h, lr, b_enc = ctx.saved_tensors
+        h, lr, b_enc, dz = ctx.saved_tensors
         B, K, temp, n_exp, indicator, exc_only, exit_logit, seed, offset, lr_shape = ctx.args
         if temp == 0.0:
             raise RuntimeError("hard counts (temp == 0) are not differentiable")
@@ -117,7 +119,7 @@ class _EncodeSampleFn(torch.autograd.Function):
         ws = torch.empty(2 * lib.pvae_num_partials(B) * K, device=h.device, dtype=torch.float32)
         with torch.cuda.device(h.device):
             _lib.check(lib.pvae_sampler_bwd(
-                _ptr(h), _ptr(lr), _ptr(b_enc), _ptr(g_z), _ptr(g_log_dr), 0.0, _ptr(g_h), _ptr(g_lr), _ptr(g_b),
+                _ptr(h), _ptr(lr), _ptr(b_enc), _ptr(g_z), _ptr(g_log_dr), _ptr(dz), 0.0, _ptr(g_h), _ptr(g_lr), _ptr(g_b),
                 _ptr(ws), 0, B, K, 0, n_exp, temp, indicator, exc_only, exit_logit, seed, offset, None, _stream()))
         return g_h, g_lr.reshape(lr_shape), g_b, None, None, None, None, None, None, None
 

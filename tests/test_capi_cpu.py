@@ -44,10 +44,10 @@ def test_argument_validation_needs_no_gpu(lib_path):
     from poissonvae_b200 import _lib
     lib = _lib.load()
     # rejected before any CUDA call: negative temperature, unknown indicator, K not a multiple of 4
-    assert lib.pvae_rsample_fwd(None, None, None, 4, 8, 0, 4, -1.0, 0, -1.0, 0.0, 1, 0, None, None) == -1
+    assert lib.pvae_rsample_fwd(None, None, None, None, 4, 8, 0, 4, -1.0, 0, -1.0, 0.0, 1, 0, None, None) == -1
     assert b"non-neg" in lib.pvae_last_error()
-    assert lib.pvae_rsample_fwd(None, None, None, 4, 8, 0, 4, 1.0, 7, -1.0, 0.0, 1, 0, None, None) == -1
-    assert lib.pvae_rsample_fwd(None, None, None, 4, 6, 0, 4, 1.0, 0, -1.0, 0.0, 1, 0, None, None) == -2
+    assert lib.pvae_rsample_fwd(None, None, None, None, 4, 8, 0, 4, 1.0, 7, -1.0, 0.0, 1, 0, None, None) == -1
+    assert lib.pvae_rsample_fwd(None, None, None, None, 4, 6, 0, 4, 1.0, 0, -1.0, 0.0, 1, 0, None, None) == -2
     with pytest.raises(ValueError):
         _lib.check(-1)
     with pytest.raises(NotImplementedError):

@@ -41,22 +41,34 @@ def draws(lib, B, K, n_exp, seed, offset, row_offset=0):
 
 
 def rsample(lib, log_rate, n_exp, temp, kind, seed, offset, clamp=-1.0, exit_logit=LOSSLESS, row_offset=0,
-            want_rate=False):
+            want_rate=False, dz=None):
     B, K = log_rate.shape
     z = torch.empty_like(log_rate)
     rate = torch.empty_like(log_rate) if want_rate else None
-    rc = lib.pvae_rsample_fwd(P(log_rate), P(z), P(rate), B, K, row_offset, n_exp, temp, IND[kind], clamp, exit_logit,
-                              seed, offset, None, stream())
+    rc = lib.pvae_rsample_fwd(P(log_rate), P(z), P(rate), P(dz), B, K, row_offset, n_exp, temp, IND[kind], clamp,
+                              exit_logit, seed, offset, None, stream())
     assert rc == 0, lib.pvae_last_error()
     return (z, rate) if want_rate else z
 
 
-def rsample_bwd(lib, log_rate, g_z, n_exp, temp, kind, seed, offset, clamp=-1.0, exit_logit=LOSSLESS):
+def rsample_bwd(lib, log_rate, g_z, n_exp, temp, kind, seed, offset, clamp=-1.0, exit_logit=LOSSLESS, saved=True):
+    """saved=True: the forward stores dz_acc and the backward is elementwise; False: the chain is recomputed.
+    Both are run and must agree (same chain, same summation order) - the caller gets the saved-path result."""
     B, K = log_rate.shape
-    g = torch.empty_like(log_rate)
-    rc = lib.pvae_rsample_bwd(P(log_rate), P(g_z), P(g), B, K, 0, n_exp, temp, IND[kind], clamp, exit_logit, seed,
+    g_re = torch.empty_like(log_rate)
+    rc = lib.pvae_rsample_bwd(P(log_rate), P(g_z), None, P(g_re), B, K, 0, n_exp, temp, IND[kind], clamp, exit_logit, seed,
                               offset, None, stream())
     assert rc == 0, lib.pvae_last_error()
+    if not saved:
+        return g_re
+    dz = torch.empty_like(log_rate)
+    z_both = rsample(lib, log_rate, n_exp, temp, kind, seed, offset, clamp=clamp, exit_logit=exit_logit, dz=dz)
+    assert torch.equal(z_both, rsample(lib, log_rate, n_exp, temp, kind, seed, offset, clamp=clamp, exit_logit=exit_logit))
+    g = torch.empty_like(log_rate)
+    rc = lib.pvae_rsample_bwd(P(log_rate), P(g_z), P(dz), P(g), B, K, 0, n_exp, temp, IND[kind], clamp, exit_logit, seed,
+                              offset, None, stream())
+    assert rc == 0, lib.pvae_last_error()
+    assert torch.equal(g, g_re), "saved-derivative and recompute backward must agree bit for bit"
     return g
 
 
@@ -189,8 +201,9 @@ def fused_fwd(lib, h, log_r, b_enc, n_exp, temp, kind, exc_only, seed, offset, e
     out = {k: torch.empty_like(h) for k in ("z", "log_dr", "rate", "kl")}
     out["kl_rowsum"] = torch.empty(B, device="cuda")
     out["rate_max"] = torch.zeros(1, device="cuda")
+    out["dz"] = torch.empty_like(h) if temp > 0 else None
     rc = lib.pvae_sampler_fwd(P(h), P(log_r), P(b_enc), P(out["z"]), P(out["log_dr"]), P(out["rate"]), P(out["kl"]),
-                              P(out["kl_rowsum"]), P(out["rate_max"]), B, K, row_offset, n_exp, temp, IND[kind],
+                              P(out["kl_rowsum"]), P(out["rate_max"]), P(out["dz"]), B, K, row_offset, n_exp, temp, IND[kind],
                               int(exc_only), exit_logit, seed, offset, None, stream())
     assert rc == 0, lib.pvae_last_error()
     return out
@@ -225,9 +238,20 @@ def test_fused_fwd_bwd_matches_oracle(lib, exc_only, with_bias, K):
     g_b = torch.empty(K, device="cuda") if with_bias else None
     ws = torch.empty(2 * lib.pvae_num_partials(B) * K, device="cuda")
     scale = beta / B
-    rc = lib.pvae_sampler_bwd(P(h), P(log_r), P(b_enc), P(g_z), None, scale, P(g_h), P(g_lr), P(g_b), P(ws), 0, B, K, 0,
-                              n_exp, temp, 0, int(exc_only), LOSSLESS, seed, offset, None, stream())
+    rc = lib.pvae_sampler_bwd(P(h), P(log_r), P(b_enc), P(g_z), None, None, scale, P(g_h), P(g_lr), P(g_b), P(ws), 0, B, K,
+                              0, n_exp, temp, 0, int(exc_only), LOSSLESS, seed, offset, None, stream())
     assert rc == 0, lib.pvae_last_error()
+    # the saved-derivative backward (what the training step uses) gives the same bits as the recompute
+    g_h2, g_lr2 = torch.empty_like(h), torch.empty(K, device="cuda")
+    g_b2 = torch.empty(K, device="cuda") if with_bias else None
+    rc = lib.pvae_sampler_bwd(P(h), P(log_r), P(b_enc), P(g_z), None, P(out["dz"]), scale, P(g_h2), P(g_lr2), P(g_b2), P(ws),
+                              0, B, K, 0, n_exp, temp, 0, int(exc_only), LOSSLESS, seed, offset, None, stream())
+    assert rc == 0, lib.pvae_last_error()
+    assert torch.equal(g_h2, g_h)
+    # the batch sums are taken over 8-row instead of 3-row blocks: same terms, another summation order
+    assert_rel(g_lr2.cpu().numpy(), g_lr.cpu().numpy(), rtol=2e-6, what="g_log_r saved vs recompute")
+    if with_bias:
+        assert_rel(g_b2.cpu().numpy(), g_b.cpu().numpy(), rtol=2e-6, what="g_b saved vs recompute")
     f8 = np.float64
     dz = po.rsample_grad_log_rate(e.astype(f8), r.astype(f8), temp, "sigmoid")
     hb8, lr8 = hb.astype(f8), log_r.cpu().numpy().astype(f8)
@@ -309,14 +333,15 @@ def test_hard_count_law_against_torch_poisson(lib):
 
 def test_error_paths(lib):
     t = torch.zeros(4, 8, device="cuda")
-    assert lib.pvae_rsample_fwd(P(t), P(t), None, 4, 8, 0, 4, -0.5, 0, -1.0, 0.0, 1, 0, None, stream()) == -1
+    assert lib.pvae_rsample_fwd(P(t), P(t), None, None, 4, 8, 0, 4, -0.5, 0, -1.0, 0.0, 1, 0, None, stream()) == -1
     assert b"non-neg" in lib.pvae_last_error()
-    assert lib.pvae_rsample_fwd(P(t), P(t), None, 4, 8, 0, 4, 1.0, 9, -1.0, 0.0, 1, 0, None, stream()) == -1
-    assert lib.pvae_rsample_fwd(P(t), P(t), None, 4, 6, 0, 4, 1.0, 0, -1.0, 0.0, 1, 0, None, stream()) == -2
-    assert lib.pvae_rsample_fwd(None, P(t), None, 4, 8, 0, 4, 1.0, 0, -1.0, 0.0, 1, 0, None, stream()) == -1
-    assert lib.pvae_rsample_fwd(P(t), P(t), None, 0, 8, 0, 4, 1.0, 0, -1.0, 0.0, 1, 0, None, stream()) == 0  # empty batch
-    assert lib.pvae_rsample_bwd(P(t), P(t), P(t), 4, 8, 0, 4, 0.0, 0, -1.0, 0.0, 1, 0, None, stream()) == -1
+    assert lib.pvae_rsample_fwd(P(t), P(t), None, None, 4, 8, 0, 4, 1.0, 9, -1.0, 0.0, 1, 0, None, stream()) == -1
+    assert lib.pvae_rsample_fwd(P(t), P(t), None, None, 4, 6, 0, 4, 1.0, 0, -1.0, 0.0, 1, 0, None, stream()) == -2
+    assert lib.pvae_rsample_fwd(None, P(t), None, None, 4, 8, 0, 4, 1.0, 0, -1.0, 0.0, 1, 0, None, stream()) == -1
+    assert lib.pvae_rsample_fwd(P(t), P(t), None, None, 0, 8, 0, 4, 1.0, 0, -1.0, 0.0, 1, 0, None, stream()) == 0  # empty batch
+    assert lib.pvae_rsample_fwd(P(t), P(t), None, P(t), 4, 8, 0, 4, 0.0, 0, -1.0, 0.0, 1, 0, None, stream()) == -1  # dz at temp 0
+    assert lib.pvae_rsample_bwd(P(t), P(t), None, P(t), 4, 8, 0, 4, 0.0, 0, -1.0, 0.0, 1, 0, None, stream()) == -1
     # n_exp = 0: no events, zero counts
     z = torch.ones(4, 8, device="cuda")
-    assert lib.pvae_rsample_fwd(P(t), P(z), None, 4, 8, 0, 0, 1.0, 0, -1.0, 0.0, 1, 0, None, stream()) == 0
+    assert lib.pvae_rsample_fwd(P(t), P(z), None, None, 4, 8, 0, 0, 1.0, 0, -1.0, 0.0, 1, 0, None, stream()) == 0
     assert z.abs().sum().item() == 0

@@ -62,6 +62,7 @@ def main():
     glr = torch.empty(K, device="cuda")
     ws = torch.empty(2 * lib.pvae_num_partials(B) * K, device="cuda")
     klrow = torch.empty(B, device="cuda")
+    dz = torch.empty(B, K, device="cuda")
     temps = (1.0,) if args.single else (1.0, 0.05)
     exits = (("lossless", 0.0),) if args.single else (("lossless", 0.0), ("c30", 30.0), ("never", -1.0))
     if args.single:
@@ -70,18 +71,30 @@ def main():
         for temp in temps:
             for exit_name, ex in exits:
                 def fwd():
-                    rc = lib.pvae_sampler_fwd(P(h), P(log_r), None, P(z), None, None, None, P(klrow), None, B, K, 0, n_exp,
-                                              temp, 0, 0, ex, 1, 4, None, s)
+                    rc = lib.pvae_sampler_fwd(P(h), P(log_r), None, P(z), None, None, None, P(klrow), None, None, B, K, 0,
+                                              n_exp, temp, 0, 0, ex, 1, 4, None, s)
+                    assert rc == 0
+
+                def fwd_both():
+                    rc = lib.pvae_sampler_fwd(P(h), P(log_r), None, P(z), None, None, None, P(klrow), None, P(dz), B, K, 0,
+                                              n_exp, temp, 0, 0, ex, 1, 4, None, s)
                     assert rc == 0
 
                 def bwd():
-                    rc = lib.pvae_sampler_bwd(P(h), P(log_r), None, P(gz), None, 1.0 / B, P(gh), P(glr), None, P(ws), 0, B, K,
-                                              0, n_exp, temp, 0, 0, ex, 1, 4, None, s)
+                    rc = lib.pvae_sampler_bwd(P(h), P(log_r), None, P(gz), None, None, 1.0 / B, P(gh), P(glr), None, P(ws), 0,
+                                              B, K, 0, n_exp, temp, 0, 0, ex, 1, 4, None, s)
+                    assert rc == 0
+
+                def bwd_saved():
+                    rc = lib.pvae_sampler_bwd(P(h), P(log_r), None, P(gz), None, P(dz), 1.0 / B, P(gh), P(glr), None, P(ws), 0,
+                                              B, K, 0, n_exp, temp, 0, 0, ex, 1, 4, None, s)
                     assert rc == 0
                 it = args.iters if ex >= 0 else 3
                 tf, tb = time_it(fwd, it, 2, flush), time_it(bwd, it, 2, flush)
-                print(json.dumps(dict(dist=name, temp=temp, exit=exit_name, fwd_us=round(tf, 1), bwd_us=round(tb, 1),
-                                      fwd_gbs=round(B * K * 8 / tf / 1e3, 1), bwd_gbs=round(B * K * 12 / tb / 1e3, 1),
+                tfb, tbs = time_it(fwd_both, it, 2, flush), time_it(bwd_saved, it, 2, flush)
+                print(json.dumps(dict(dist=name, temp=temp, exit=exit_name, fwd_us=round(tf, 1), bwd_recompute_us=round(tb, 1),
+                                      fwd_both_us=round(tfb, 1), bwd_saved_us=round(tbs, 1),
+                                      fwd_both_gbs=round(B * K * 12 / tfb / 1e3, 1), bwd_saved_gbs=round(B * K * 16 / tbs / 1e3, 1),
                                       mean_z=round(z.mean().item(), 4))), flush=True)
 
 
