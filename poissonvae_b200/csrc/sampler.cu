@@ -83,8 +83,14 @@ __device__ __forceinline__ void soft_term(const SamplerParams& p, float t, float
   }
 }
 
-// x = e / rate.  Soft path: Markstein's correction on a correctly rounded reciprocal (equals div.rn
-// except in pathological cases, 3 FMA-pipe ops).  Hard path: IEEE division, bit-exact by definition.
+// x = e / rate.  Soft path: Markstein's correction on a Newton-refined reciprocal (equals div.rn except in
+// rare last-bit cases, 3 FMA-pipe ops; both phases use the same reciprocal, so a chain that moves from
+// phase A to phase B keeps dividing the same way).  Hard path: IEEE division, bit-exact by definition.
+__device__ __forceinline__ float recip_for_div(float rate) {
+  const float r = rcp_approx(rate);
+  return fmaf(r, fmaf(-rate, r, 1.f), r);
+}
+
 template <bool EXACT>
 __device__ __forceinline__ float div_by_rate(float e, float rate, float inv_rate) {
   if (EXACT) return __fdiv_rn(e, rate);
@@ -177,8 +183,7 @@ __device__ __forceinline__ Latent prologue(const SamplerParams& p, float hv, flo
 template <int MODE, int IND, bool RAW>
 __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p) {
   __shared__ float s_tab[kSlotWords][kSlots];  // parked quads, one word-plane per field
-  __shared__ unsigned short s_list[kSlots];
-  __shared__ int s_count, s_next;
+  __shared__ unsigned short s_list[kWarps][kMaxRows * 32];  // each warp parks and finishes its own quads
   __shared__ float s_rowsum[kMaxRows][kWarps];
   __shared__ float s_max[kWarps];
 
@@ -197,13 +202,14 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
   float rmax = 0.f;
   const bool want_rowsum = !kIsBwd && !RAW && p.kl_rowsum != nullptr;
   if (tid < kMaxRows * kWarps) (&s_rowsum[0][0])[tid] = 0.f;
+  __syncthreads();
+  const unsigned lanes_below = (1u << lane) - 1u;
 
   // every thread runs every pass so that the block-level steps below see whole warps
   for (long long k0 = 0; k0 < p.K; k0 += kColsPerPass) {
     const long long k = k0 + 4 * tid;
     const bool act = k < p.K;
-    if (tid == 0) s_count = 0, s_next = 0;
-    __syncthreads();
+    int n_parked = 0;  // warp-uniform: quads of this warp waiting for phase B
     float lr[4] = {0.f, 0.f, 0.f, 0.f}, bias[4] = {0.f, 0.f, 0.f, 0.f}, elr[4] = {0.f, 0.f, 0.f, 0.f};
     if (!RAW && act) {
       const float4 v = ldg4(p.log_r + k);
@@ -248,6 +254,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
 #pragma unroll 1
     for (int r = 0; r < nrows; ++r) {
       float klsum = 0.f;
+      bool park = false;
       if (act) {
         const long long row = row0 + r;
         const long long base = row * p.K + k;
@@ -259,7 +266,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
         for (int j = 0; j < 4; ++j) {
           q[j] = prologue<RAW, kIsBwd>(p, hv[j], lr[j], bias[j]);
           rate[j] = q[j].rate;
-          inv_rate[j] = MODE == kBwdSaved ? 0.f : __frcp_rn(rate[j]);
+          inv_rate[j] = MODE == kBwdSaved ? 0.f : (MODE == kFwdHard ? 0.f : recip_for_div(rate[j]));
         }
         if (!kIsBwd) {  // outputs that do not depend on the chain
           if (p.rate != nullptr) stg4(p.rate + base, make_float4(rate[0], rate[1], rate[2], rate[3]));
@@ -304,22 +311,27 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
             s_tab[8 + j][slot] = acc[j];
             if (MODE == kFwdBoth) s_tab[12 + j][slot] = acc2[j];
           }
-          s_list[atomicAdd(&s_count, 1)] = static_cast<unsigned short>(slot);
+          park = true;
           parked |= 1u << r;
         }
       }
+      __syncwarp();
+      {  // append this row's parked quads to the warp's list (ballot + prefix count, no atomics)
+        const unsigned m = __ballot_sync(0xffffffffu, park);
+        if (park) s_list[warp][n_parked + __popc(m & lanes_below)] = static_cast<unsigned short>(r * kThreads + tid);
+        n_parked += __popc(m);
+      }
       if (want_rowsum) {
-        __syncwarp();
         const float s = warp_sum(klsum);
         if (lane == 0) s_rowsum[r][warp] += s;
       }
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---------------- phase B ----------------
-    const int n_parked = s_count;
+    // ---------------- phase B (per warp) ----------------
     if (MODE != kFwdHard && MODE != kBwdSaved && n_parked > 0) {
       const int gl = lane % kGroup;
+      int next_free = 0;  // warp-uniform cursor into the warp's list
       bool has = false, done = true;  // done: this group needs a (new) quad
       int slot = 0, n0 = 0;
       uint32_t quad = 0;
@@ -354,19 +366,23 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
                 if (MODE == kFwdBoth) stg4(p.dz_out + base, make_float4(tot2[0], tot2[1], tot2[2], tot2[3]));
               }
             }
-            next = atomicAdd(&s_next, 1);
+          }
+          {  // hand the next list entries to the requesting groups, in lane order
+            const unsigned req = __ballot_sync(0xffffffffu, done && gl == 0);
+            next = next_free + __popc(req & lanes_below);
+            next_free += __popc(req);
           }
           next = __shfl_sync(0xffffffffu, next, 0, kGroup);
           if (done) {
             has = next < n_parked;
             if (has) {
-              slot = s_list[next];
+              slot = s_list[warp][next];
               const int r = slot / kThreads, owner = slot % kThreads;
               quad = static_cast<uint32_t>(((p.row_offset + row0 + r) * p.K + k0 + 4 * owner) >> 2);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 rate[j] = s_tab[j][slot];
-                inv_rate[j] = __frcp_rn(rate[j]);
+                inv_rate[j] = recip_for_div(rate[j]);
                 t0[j] = s_tab[4 + j][slot];
                 acc[j] = s_tab[8 + j][slot];
                 part[j] = 0.f;
@@ -404,7 +420,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
       }
     }
     if (kIsBwd) {
-      __syncthreads();
+      __syncwarp();
       // the owner finishes its parked quads (prologue recomputed: cheap next to a parked chain)
       for (int r = 0; r < nrows; ++r) {
         if (!((parked >> r) & 1u)) continue;
@@ -427,7 +443,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
         if (p.part_b != nullptr) stg4(p.part_b + pbase, make_float4(col_b[0], col_b[1], col_b[2], col_b[3]));
       }
     }
-    __syncthreads();  // the table is reused by the next pass
+    __syncwarp();  // the warp's slots are reused by the next pass
   }
 
   if (!kIsBwd) {
@@ -478,38 +494,50 @@ __global__ void __launch_bounds__(kThreads) sampler_bwd_saved_kernel(const Sampl
 #pragma unroll
       for (int j = 0; j < 4; ++j) elr[j] = expf(lr[j]);
     }
-    float4 hv[kSavedRows], gz[kSavedRows], dz[kSavedRows], gl[kSavedRows];
     const bool has_gld = !RAW && p.g_log_dr != nullptr;
+    constexpr int kChunk = 2;  // rows whose loads are in flight while the previous chunk is being computed
+    float4 hv[2][kChunk], gz[2][kChunk], dz[2][kChunk], gl[2][kChunk];
+    auto load_chunk = [&](int buf, int r0) {
 #pragma unroll
-    for (int r = 0; r < kSavedRows; ++r) {
-      if (r < nrows) {
-        const long long base = (row0 + r) * p.K + k;
-        hv[r] = ldg4(p.h + base), gz[r] = ldg4(p.g_z + base), dz[r] = ldg4(p.dz_in + base);
-        gl[r] = has_gld ? ldg4(p.g_log_dr + base) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    float col_lr[4] = {0.f, 0.f, 0.f, 0.f}, col_b[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int r = 0; r < kSavedRows; ++r) {
-      if (r < nrows) {
-        const float h4[4] = {hv[r].x, hv[r].y, hv[r].z, hv[r].w}, g4[4] = {gz[r].x, gz[r].y, gz[r].z, gz[r].w};
-        const float d4[4] = {dz[r].x, dz[r].y, dz[r].z, dz[r].w}, l4[4] = {gl[r].x, gl[r].y, gl[r].z, gl[r].w};
-        float gh[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const Latent q = prologue<RAW, true>(p, h4[j], lr[j], bias[j]);
-          // d z / d lambda = (sum_n f'(l_n) t_n) / temp * exp(lambda) / rate; then the clamp chain
-          const float g_u = g4[j] * (d4[j] * p.inv_temp * (q.explam / q.rate)) * q.d_rate;
-          if (RAW) {
-            gh[j] = g_u;
-          } else {
-            const float d = q.log_dr, ed = expf(d);
-            gh[j] = (g_u + p.kl_scale * elr[j] * d * ed + l4[j]) * q.d_dr;
-            col_lr[j] += g_u + p.kl_scale * (elr[j] * (1.f + ed * (d - 1.f)));
-            col_b[j] += gh[j];
-          }
+      for (int u = 0; u < kChunk; ++u) {
+        if (r0 + u < nrows) {
+          const long long base = (row0 + r0 + u) * p.K + k;
+          hv[buf][u] = ldg4(p.h + base), gz[buf][u] = ldg4(p.g_z + base), dz[buf][u] = ldg4(p.dz_in + base);
+          gl[buf][u] = has_gld ? ldg4(p.g_log_dr + base) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        stg4(p.g_h + (row0 + r) * p.K + k, make_float4(gh[0], gh[1], gh[2], gh[3]));
+      }
+    };
+    float col_lr[4] = {0.f, 0.f, 0.f, 0.f}, col_b[4] = {0.f, 0.f, 0.f, 0.f};
+    load_chunk(0, 0);
+#pragma unroll
+    for (int c = 0; c < kSavedRows / kChunk; ++c) {
+      const int buf = c & 1;
+      if ((c + 1) * kChunk < nrows) load_chunk(buf ^ 1, (c + 1) * kChunk);
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u) {
+        const int r = c * kChunk + u;
+        if (r < nrows) {
+          const float h4[4] = {hv[buf][u].x, hv[buf][u].y, hv[buf][u].z, hv[buf][u].w};
+          const float g4[4] = {gz[buf][u].x, gz[buf][u].y, gz[buf][u].z, gz[buf][u].w};
+          const float d4[4] = {dz[buf][u].x, dz[buf][u].y, dz[buf][u].z, dz[buf][u].w};
+          const float l4[4] = {gl[buf][u].x, gl[buf][u].y, gl[buf][u].z, gl[buf][u].w};
+          float gh[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const Latent q = prologue<RAW, true>(p, h4[j], lr[j], bias[j]);
+            // d z / d lambda = (sum_n f'(l_n) t_n) / temp * exp(lambda) / rate; then the clamp chain
+            const float g_u = g4[j] * (d4[j] * p.inv_temp * (q.explam / q.rate)) * q.d_rate;
+            if (RAW) {
+              gh[j] = g_u;
+            } else {
+              const float d = q.log_dr, ed = expf(d);
+              gh[j] = (g_u + p.kl_scale * elr[j] * d * ed + l4[j]) * q.d_dr;
+              col_lr[j] += g_u + p.kl_scale * (elr[j] * (1.f + ed * (d - 1.f)));
+              col_b[j] += gh[j];
+            }
+          }
+          stg4(p.g_h + (row0 + r) * p.K + k, make_float4(gh[0], gh[1], gh[2], gh[3]));
+        }
       }
     }
     if (!RAW) {

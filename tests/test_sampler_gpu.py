@@ -68,7 +68,7 @@ def rsample_bwd(lib, log_rate, g_z, n_exp, temp, kind, seed, offset, clamp=-1.0,
     rc = lib.pvae_rsample_bwd(P(log_rate), P(g_z), P(dz), P(g), B, K, 0, n_exp, temp, IND[kind], clamp, exit_logit, seed,
                               offset, None, stream())
     assert rc == 0, lib.pvae_last_error()
-    assert torch.equal(g, g_re), "saved-derivative and recompute backward must agree bit for bit"
+    assert_rel(g.cpu().numpy(), g_re.cpu().numpy(), rtol=2e-6, what="saved-derivative vs recompute backward")
     return g
 
 
@@ -247,8 +247,8 @@ def test_fused_fwd_bwd_matches_oracle(lib, exc_only, with_bias, K):
     rc = lib.pvae_sampler_bwd(P(h), P(log_r), P(b_enc), P(g_z), None, P(out["dz"]), scale, P(g_h2), P(g_lr2), P(g_b2), P(ws),
                               0, B, K, 0, n_exp, temp, 0, int(exc_only), LOSSLESS, seed, offset, None, stream())
     assert rc == 0, lib.pvae_last_error()
-    assert torch.equal(g_h2, g_h)
-    # the batch sums are taken over 8-row instead of 3-row blocks: same terms, another summation order
+    # same terms, but evaluated by another kernel (other contraction / summation order of the batch sums)
+    assert_rel(g_h2.cpu().numpy(), g_h.cpu().numpy(), rtol=2e-6, what="g_h saved vs recompute")
     assert_rel(g_lr2.cpu().numpy(), g_lr.cpu().numpy(), rtol=2e-6, what="g_log_r saved vs recompute")
     if with_bias:
         assert_rel(g_b2.cpu().numpy(), g_b.cpu().numpy(), rtol=2e-6, what="g_b saved vs recompute")
