@@ -130,13 +130,20 @@ int64_t pvae_gemm_ws_floats(int64_t M, int64_t N, int splits);
 int pvae_set_gemm_variant(int v);
 int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t Kd, int a_kmajor, int b_kmajor,
                    int precise, int splits, float* splitk_ws, void* stream);
+/* Decoder GEMM of the training step with BaseVAE.loss_recon (main/vae.py:68-72) and its gradient fused into the
+ * epilogue: y = A B^T (A (M,Kd), B (N,Kd), both K-major) is never stored; instead G (M,N) = g_scale * (y - X) and
+ * row_part (M, P) with P = pvae_gemm_residual_parts(N): row_part[m, p] = sum over the p-th 64-column tile of (y - X)^2. */
+int64_t pvae_gemm_residual_parts(int64_t N);
+int pvae_gemm_tf32_residual(const float* A, const float* B, const float* X, float* G, float* row_part, int64_t M, int64_t N,
+                            int64_t Kd, float g_scale, int precise, void* stream);
 
 /* ---- training-step pieces around the sampler and the GEMMs -----------------------------------
  * pvae_recon_residual: BaseVAE.loss_recon main/vae.py:68-72 and its gradient in one pass:
  *   recon (B) = sum_d (y - x)^2,  g_y (B,D) = g_scale * (y - x)  (g_scale = 2 / B_global is
  *   d mean_b(recon) / d y).  g_y or recon may be NULL.  D must be a multiple of 4.
  * pvae_loss_assemble: main/train_vae.py:347-351: out3[0] = sum_b(recon + beta * kl_rowsum) / B_global,
- *   out3[1] = sum recon / B_global, out3[2] = sum kl_rowsum / B_global (shards: sum over ranks).
+ *   out3[1] = sum recon / B_global, out3[2] = sum kl_rowsum / B_global (shards: sum over ranks); recon is
+ *   (B, recon_parts): per-sample squared error, possibly as recon_parts partial sums (1 for pvae_recon_residual).
  * pvae_grad_norm: nn.utils.clip_grad_norm_ main/train_vae.py:365-377 without the host sync:
  *   out2[0] = ||g||_2, out2[1] = min(1, max_norm / (||g|| + 1e-6)) (1 if max_norm <= 0);
  *   ws: pvae_grad_norm_ws_floats() floats.
@@ -145,7 +152,7 @@ int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t M, int64_t 
 int pvae_recon_residual(const float* y, const float* x, float* g_y, float* recon, int64_t B, int64_t D, float g_scale,
                         void* stream);
 int pvae_loss_assemble(const float* recon, const float* kl_rowsum, float* out3, int64_t B, float beta, int64_t B_global,
-                       void* stream);
+                       int recon_parts, void* stream);
 int64_t pvae_grad_norm_ws_floats(void);
 int pvae_grad_norm(const float* g, int64_t n, float max_norm, float* ws, float* out2, void* stream);
 int pvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, float lr, int step, float beta1,

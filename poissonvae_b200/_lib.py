@@ -52,7 +52,9 @@ _SIGNATURES = {
     "pvae_set_gemm_variant": (_i, [_i]),
     "pvae_gemm_tf32": (_i, [_p, _p, _p, _i64, _i64, _i64, _i, _i, _i, _i, _p, _p]),
     "pvae_recon_residual": (_i, [_p, _p, _p, _p, _i64, _i64, _f, _p]),
-    "pvae_loss_assemble": (_i, [_p, _p, _p, _i64, _f, _i64, _p]),
+    "pvae_loss_assemble": (_i, [_p, _p, _p, _i64, _f, _i64, _i, _p]),
+    "pvae_gemm_residual_parts": (_i64, [_i64]),
+    "pvae_gemm_tf32_residual": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _i, _p]),
     "pvae_grad_norm_ws_floats": (_i64, []),
     "pvae_grad_norm": (_i, [_p, _i64, _f, _p, _p, _p]),
     "pvae_adamax_step": (_i, [_p, _p, _p, _p, _i64, _f, _i, _f, _f, _f, _f, _p, _p]),

@@ -7,10 +7,11 @@
 //                                commits to the ring's "empty" barriers / the accumulator-full barrier
 //   warps 2-5   epilogue         tcgen05.ld of the accumulator (32 lanes x 32 columns per instruction),
 //                                128-byte row segments stored straight to global memory
-// Precision.  kind::tf32 reads 10 mantissa bits of each operand.  In the default "3xTF32" mode the four
-// epilogue warps first split every landed stage in place into hi = the TF32-representable part and
-// lo = x - hi (exact), and the issuer accumulates hi*hi + lo*hi + hi*lo: the dropped lo*lo term and the
-// rounding of lo are ~2^-22 relative, i.e. fp32-grade products with fp32 accumulation in TMEM.
+// Precision.  kind::tf32 reads 10 mantissa bits of each operand and ignores the 13 below (truncation -
+// measured, tools/probe_tf32_rounding.py).  In the default "3xTF32" mode the four epilogue warps compute, for
+// every landed stage, lo = x - trunc_tf32(x) (exact) into a second plane; the raw tile serves as hi, and the
+// issuer accumulates hi*hi + lo*hi + hi*lo: the dropped lo*lo term and the truncation of lo are ~2^-22
+// relative, i.e. fp32-grade products with fp32 accumulation in TMEM.
 // Both operand majors are supported without any transposed copy in HBM: a K-major operand is a
 // (rows, Kd) row-major matrix loaded as one {32 x 128} box per stage; an MN-major operand is a (Kd, rows)
 // row-major matrix loaded as BN/32 (or 4) {32 x 32} boxes whose 1024-byte swizzle atoms are walked along
@@ -111,6 +112,12 @@ struct GemmParams {
   int k_per_split;       // multiple of kBK
   int a_kmajor, b_kmajor;
   long long split_stride;  // M * N when splits > 1
+  // residual epilogue (decoder GEMM of the training step): instead of C = y the kernel writes
+  // G = g_scale * (y - X) and row_part[m, n_tile] = sum over the tile's columns of (y - X)^2
+  const float* X;
+  float* G;
+  float* row_part;
+  float g_scale;
 };
 
 template <int BN, bool SPLIT, int STAGES>
@@ -230,7 +237,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else {
     if (SPLIT) {
-      // ===== operand splitter: hi = TF32-representable part (in place), lo = x - hi (second plane) =====
+      // ===== operand splitter: lo = x - trunc_tf32(x) into the second plane =====
       const int ct = threadIdx.x - 64;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
@@ -246,8 +253,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           lo.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(hi.y));
           lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(hi.z));
           lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(hi.w));
-          tile[i] = hi;
-          tile_lo[i] = lo;
+          tile_lo[i] = lo;  // the tensor core ignores the 13 low mantissa bits, so the raw tile already is `hi`
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core reads
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv_bar[s])) : "memory");
@@ -258,6 +264,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quarter = warp & 3;  // a warp may only read TMEM lanes [32 * (warp % 4), +32)
     float* cbase = p.C + static_cast<long long>(blockIdx.z) * p.split_stride;
+    const bool residual = p.X != nullptr;
+    float rowacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
@@ -302,8 +310,30 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int row = rr + sub;
         const int mm = m0 + quarter * 32 + row;
         const float* src = stg + row * 33 + col;
-        if (mm < p.M && n < p.N)  // N is a multiple of 4
-          *reinterpret_cast<float4*>(cbase + static_cast<long long>(mm) * p.N + n) = make_float4(src[0], src[1], src[2], src[3]);
+        const bool in = mm < p.M && n < p.N;  // N is a multiple of 4
+        if (!residual) {
+          if (in) *reinterpret_cast<float4*>(cbase + static_cast<long long>(mm) * p.N + n) = make_float4(src[0], src[1], src[2], src[3]);
+        } else {
+          float sq = 0.f;
+          if (in) {
+            const long long o = static_cast<long long>(mm) * p.N + n;
+            const float4 xv = ldg4(p.X + o);
+            const float4 r = make_float4(src[0] - xv.x, src[1] - xv.y, src[2] - xv.z, src[3] - xv.w);
+            stg4(p.G + o, make_float4(p.g_scale * r.x, p.g_scale * r.y, p.g_scale * r.z, p.g_scale * r.w));
+            sq = (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
+          }
+          sq += __shfl_xor_sync(0xffffffffu, sq, 1);  // the 8 lanes that share a row
+          sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+          sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+          rowacc[rr / 4] += sq;
+        }
+      }
+    }
+    if (residual && (lane & 7) == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int mm = m0 + quarter * 32 + 4 * i + (lane >> 3);
+        if (mm < p.M) p.row_part[static_cast<long long>(mm) * gridDim.x + blockIdx.x] = rowacc[i];
       }
     }
   }
@@ -417,14 +447,16 @@ extern "C" int pvae_set_gemm_variant(int v) {
   return PVAE_OK;
 }
 
-extern "C" int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t Kd, int a_kmajor,
-                              int b_kmajor, int precise, int splits, float* splitk_ws, void* stream) {
+static int gemm_impl(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t Kd, int a_kmajor, int b_kmajor,
+                     int precise, int splits, float* splitk_ws, const float* X, float* G, float* row_part, float g_scale,
+                     int force_bn, void* stream) {
   if (M <= 0 || N <= 0 || Kd <= 0) return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)Kd);
   if (M % 4 || N % 4 || Kd % 4)
     return fail(PVAE_ERR_UNSUPPORTED, "pvae_gemm_tf32: M=%lld N=%lld K=%lld must be multiples of 4 (16-byte TMA strides)",
                 (long long)M, (long long)N, (long long)Kd);
-  if (!A || !B || !C) return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: null pointer");
-  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15)
+  if (!A || !B || (!C && !X)) return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: null pointer");
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) |
+       reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(G)) & 15)
     return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: pointers must be 16-byte aligned");
   if (splits < 1) splits = 1;
   const long long kblocks = (Kd + kBK - 1) / kBK;
@@ -438,6 +470,7 @@ extern "C" int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t 
   int BN = (N <= 64 || ((N + 127) / 128) * ((M + kBM - 1) / kBM) * splits < 96) ? 64 : 128;
   const bool narrow = g_gemm_variant == 2 || (g_gemm_variant == 0 && false);
   if (narrow) BN = 64;
+  if (force_bn) BN = force_bn;
   CUtensorMap ma, mb;
   // K-major operand: (rows, Kd) row-major, box {32 k, rows_per_tile}; MN-major: (Kd, rows) row-major, box {32 rows, 32 k}
   if (int rc = a_kmajor ? make_map(&ma, A, M, Kd, kBK, kBM) : make_map(&ma, A, Kd, M, 32, kBK, true)) return rc;
@@ -448,6 +481,7 @@ extern "C" int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t 
   p.k_per_split = static_cast<int>(((kblocks + splits - 1) / splits) * kBK);
   p.a_kmajor = a_kmajor, p.b_kmajor = b_kmajor;
   p.split_stride = splits > 1 ? M * N : 0;
+  p.X = X, p.G = G, p.row_part = row_part, p.g_scale = g_scale;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rc;
   if (narrow) {  // 2 CTAs per SM: one CTA's TMA latency hides behind the other's split + MMA work
@@ -465,4 +499,18 @@ extern "C" int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t 
                                                       static_cast<const float*>(splitk_ws), C, n4, splits));
   }
   return PVAE_OK;
+}
+
+extern "C" int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t Kd, int a_kmajor,
+                              int b_kmajor, int precise, int splits, float* splitk_ws, void* stream) {
+  return gemm_impl(A, B, C, M, N, Kd, a_kmajor, b_kmajor, precise, splits, splitk_ws, nullptr, nullptr, nullptr, 0.f, 0, stream);
+}
+
+// 64-wide tiles: the decoder output is only D = 256 wide, so this keeps 4 * M / 128 CTAs in flight
+extern "C" int64_t pvae_gemm_residual_parts(int64_t N) { return (N + 63) / 64; }
+
+extern "C" int pvae_gemm_tf32_residual(const float* A, const float* B, const float* X, float* G, float* row_part, int64_t M,
+                                       int64_t N, int64_t Kd, float g_scale, int precise, void* stream) {
+  if (!X || !G || !row_part) return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32_residual: null pointer");
+  return gemm_impl(A, B, nullptr, M, N, Kd, 1, 1, precise, 1, nullptr, X, G, row_part, g_scale, 64, stream);
 }

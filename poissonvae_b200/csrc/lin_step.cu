@@ -3,8 +3,8 @@
 //
 //   h   = x W_enc^T                                   tcgen05 GEMM            main/vae.py:44-51
 //   z, dz_acc = rsample(softclamps(h, log_r)), kl sums fused sampler           main/vae.py:393-415, base/distributions.py:55-81
-//   y   = z W_dec^T                                   tcgen05 GEMM            main/vae.py:59-60
-//   g_y = 2 (y - x) / B_global, recon                 residual kernel         main/vae.py:68-72
+//   y   = z W_dec^T; g_y = 2 (y - x) / B_global,      tcgen05 GEMM with the residual fused into its epilogue
+//   recon partial sums                                                        main/vae.py:59-60, 68-72
 //   loss = sum_b(recon + beta kl) / B_global          loss kernel             main/train_vae.py:347-351
 //   g_W_dec = g_y^T z (split-K), g_z = g_y W_dec      tcgen05 GEMMs
 //   g_h, g_log_r (+ g_b_enc)                          sampler backward from the dz_acc the forward stored (elementwise)
@@ -41,7 +41,7 @@ Ws carve(float* base, int64_t B, int64_t K, int64_t D) {
     return p;
   };
   w.h = take(B * K), w.z = take(B * K), w.dz = take(B * K), w.y = take(B * D), w.g_y = take(B * D), w.g_z = take(B * K), w.g_h = take(B * K);
-  w.recon = take(B), w.klrow = take(B);
+  w.recon = take(B * pvae_gemm_residual_parts(D)), w.klrow = take(B);
   w.partials = take(2 * pvae_num_partials(B) * K);
   const int64_t s1 = pvae_gemm_ws_floats(D, K, wgrad_splits(D, K, B)), s2 = pvae_gemm_ws_floats(K, D, wgrad_splits(K, D, B));
   w.splitk = take(s1 > s2 ? s1 : s2);
@@ -85,9 +85,11 @@ extern "C" int pvae_lin_step_fwd_bwd(const float* x, const float* params, float*
                              temp, indicator, exc_only, exit_logit, seed, offset, offset_dev, s)))
     return rc;
   mark(1);
-  if ((rc = pvae_gemm_tf32(w.z, w_dec, w.y, B, D, K, 1, 1, precise, 1, nullptr, s))) return rc;
-  if ((rc = pvae_recon_residual(w.y, x, w.g_y, w.recon, B, D, 2.0f / static_cast<float>(B_global), s))) return rc;
-  if ((rc = pvae_loss_assemble(w.recon, w.klrow, loss3, B, beta, B_global, s))) return rc;
+  // decoder GEMM with the residual fused into its epilogue: g_y and per-tile squared errors, y itself is never stored
+  if ((rc = pvae_gemm_tf32_residual(w.z, w_dec, x, w.g_y, w.recon, B, D, K, 2.0f / static_cast<float>(B_global), precise, s)))
+    return rc;
+  if ((rc = pvae_loss_assemble(w.recon, w.klrow, loss3, B, beta, B_global, static_cast<int>(pvae_gemm_residual_parts(D)), s)))
+    return rc;
   // ---- backward
   if ((rc = pvae_gemm_tf32(w.g_y, w.z, g_w_dec, D, K, B, 0, 0, precise, wgrad_splits(D, K, B), w.splitk, s))) return rc;
   if ((rc = pvae_gemm_tf32(w.g_y, w_dec, w.g_z, B, K, D, 1, 0, precise, 1, nullptr, s))) return rc;

@@ -38,13 +38,16 @@ __global__ void __launch_bounds__(256) recon_kernel(const float* __restrict__ y,
 // ---- loss assembly: out[0] = sum_b(recon + beta * kl_row) / B_global, out[1] = sum recon / Bg,
 // out[2] = sum kl_row / Bg.  Single block, fixed order (deterministic).
 __global__ void __launch_bounds__(1024) loss_kernel(const float* __restrict__ recon, const float* __restrict__ kl_row,
-                                                    float* __restrict__ out, long long B, float beta, float inv_bg) {
+                                                    float* __restrict__ out, long long B, float beta, float inv_bg,
+                                                    int recon_parts) {
   __shared__ float s_r[32], s_k[32];
   pdl_launch_dependents();
   pdl_wait();
   float r = 0.f, k = 0.f;
   for (long long b = threadIdx.x; b < B; b += 1024) {
-    r += recon[b];
+    float rb = 0.f;  // recon may arrive as per-column-tile partial sums (fused decoder epilogue)
+    for (int j = 0; j < recon_parts; ++j) rb += recon[b * recon_parts + j];
+    r += rb;
     k += kl_row[b];
   }
   r = warp_sum(r), k = warp_sum(k);
@@ -125,11 +128,12 @@ extern "C" int pvae_recon_residual(const float* y, const float* x, float* g_y, f
 }
 
 extern "C" int pvae_loss_assemble(const float* recon, const float* kl_rowsum, float* out3, int64_t B, float beta,
-                                  int64_t B_global, void* stream) {
-  if (B <= 0 || B_global <= 0 || !recon || !kl_rowsum || !out3) return fail(PVAE_ERR_INVALID, "pvae_loss_assemble: bad argument");
+                                  int64_t B_global, int recon_parts, void* stream) {
+  if (B <= 0 || B_global <= 0 || recon_parts < 1 || !recon || !kl_rowsum || !out3)
+    return fail(PVAE_ERR_INVALID, "pvae_loss_assemble: bad argument");
   return cuda_ok("pvae_loss_assemble", launch_pdl(loss_kernel, dim3(1), dim3(1024), 0, static_cast<cudaStream_t>(stream), recon,
                                                   kl_rowsum, out3, static_cast<long long>(B), beta,
-                                                  1.f / static_cast<float>(B_global)));
+                                                  1.f / static_cast<float>(B_global), recon_parts));
 }
 
 extern "C" int64_t pvae_grad_norm_ws_floats(void) { return kNormBlocks; }

@@ -156,9 +156,9 @@ class TrainerVAE:
 
     def launches_per_step(self) -> int:
         """Kernels of libpvae_b200.so launched by one train_step."""
-        # 5 tcgen05 GEMMs + 2 split-K reductions (wgrad), sampler fwd, residual, loss, sampler bwd,
-        # column-sum finalize, Adamax
-        n = 13
+        # 5 tcgen05 GEMMs (the decoder one with the residual fused in) + 2 split-K reductions (wgrad),
+        # sampler fwd, loss, sampler bwd, column-sum finalize, Adamax
+        n = 12
         if self.model.fc_enc.bias is not None:
             n += 1  # second column-sum finalize (bias gradient)
         if self.cfg.grad_clip is not None:

@@ -103,3 +103,32 @@ def test_argument_checks(lib):
     assert lib.pvae_gemm_tf32(t.data_ptr(), t.data_ptr(), t.data_ptr(), 64, 64, 6, 1, 1, 1, 1, None, s) == -2
     assert lib.pvae_gemm_tf32(None, t.data_ptr(), t.data_ptr(), 64, 64, 64, 1, 1, 1, 1, None, s) == -1
     assert lib.pvae_gemm_tf32(t.data_ptr(), t.data_ptr(), t.data_ptr(), 64, 64, 64, 1, 1, 1, 2, None, s) == -1  # no workspace
+
+
+@pytest.mark.parametrize("shape", [(4096, 256, 512), (200, 256, 64), (12, 136, 100)])
+def test_residual_epilogue_matches_separate_kernels(lib, shape):
+    """Decoder GEMM with loss_recon fused into its epilogue == GEMM, then pvae_recon_residual."""
+    M, N, Kd = shape
+    gen = torch.Generator("cuda").manual_seed(3)
+    z = torch.rand(M, Kd, device="cuda", generator=gen)
+    w = torch.randn(N, Kd, device="cuda", generator=gen) * 0.05
+    x = torch.randn(M, N, device="cuda", generator=gen)
+    s = torch.cuda.current_stream().cuda_stream
+    scale = 2.0 / M
+    y = run(lib, z, w, M, N, Kd, 1, 1, precise=1)
+    g_ref, r_ref = torch.empty_like(x), torch.empty(M, device="cuda")
+    assert lib.pvae_recon_residual(y.data_ptr(), x.data_ptr(), g_ref.data_ptr(), r_ref.data_ptr(), M, N, scale, s) == 0
+    P = lib.pvae_gemm_residual_parts(N)
+    g, parts = torch.full_like(x, float("nan")), torch.full((M, P), float("nan"), device="cuda")
+    rc = lib.pvae_gemm_tf32_residual(z.data_ptr(), w.data_ptr(), x.data_ptr(), g.data_ptr(), parts.data_ptr(), M, N, Kd,
+                                     scale, 1, s)
+    assert rc == 0, lib.pvae_last_error()
+    torch.cuda.synchronize()
+    assert torch.equal(g, g_ref)  # same accumulators, same subtraction
+    assert torch.allclose(parts.sum(1), r_ref, rtol=1e-6, atol=0)
+    # the loss kernel accepts the partial sums
+    kl = torch.rand(M, device="cuda", generator=gen)
+    out_a, out_b = torch.empty(3, device="cuda"), torch.empty(3, device="cuda")
+    assert lib.pvae_loss_assemble(parts.data_ptr(), kl.data_ptr(), out_a.data_ptr(), M, 2.5, M, P, s) == 0
+    assert lib.pvae_loss_assemble(r_ref.data_ptr(), kl.data_ptr(), out_b.data_ptr(), M, 2.5, M, 1, s) == 0
+    assert torch.allclose(out_a, out_b, rtol=1e-6)
