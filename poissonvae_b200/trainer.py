@@ -194,6 +194,55 @@ class TrainerVAE:
         self._cur = 1 - cur
         return out
 
+    def fit_host(self, batches_host: torch.Tensor, first_gstep: int = 0, chunk: int = 16, losses_host: torch.Tensor = None):
+        """Train on `batches_host`, a pinned host tensor (n_steps, B, D): the public entry point for data that lives
+        in host memory.  Batches are uploaded `chunk` at a time on a side stream into two alternating device
+        buffers (one large DMA amortises the per-copy latency that dominates 4 MiB transfers) while the previous
+        chunk trains; every step's [loss, mse, kl] is copied back to pinned memory asynchronously.
+        Returns the pinned (n_steps, 3) tensor of results (valid after torch.cuda.synchronize())."""
+        n_steps = batches_host.shape[0]
+        if losses_host is None:
+            losses_host = torch.empty(n_steps, 3).pin_memory()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        shape = (chunk,) + tuple(batches_host.shape[1:])
+        if getattr(self, "_chunk_bufs", None) is None or self._chunk_bufs[0].shape != shape:
+            self._chunk_bufs = [torch.empty(shape, device=self.device, dtype=torch.float32) for _ in range(2)]
+            self._chunk_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._chunk_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._loss_ring = torch.empty(2 * chunk, 3, device=self.device, dtype=torch.float32)
+            self._loss_ev = [torch.cuda.Event() for _ in range(2 * chunk)]
+        main = torch.cuda.current_stream()
+        cs = self._copy_stream
+
+        def upload(c):  # chunk index -> staging buffer c % 2
+            lo, hi = c * chunk, min((c + 1) * chunk, n_steps)
+            if lo >= n_steps:
+                return
+            slot = c % 2
+            cs.wait_event(self._chunk_free[slot])
+            with torch.cuda.stream(cs):
+                self._chunk_bufs[slot][:hi - lo].copy_(batches_host[lo:hi], non_blocking=True)
+                self._chunk_ready[slot].record(cs)
+
+        upload(0)
+        n_chunks = (n_steps + chunk - 1) // chunk
+        for c in range(n_chunks):
+            upload(c + 1)  # overlaps this chunk's compute
+            slot = c % 2
+            main.wait_event(self._chunk_ready[slot])
+            lo, hi = c * chunk, min((c + 1) * chunk, n_steps)
+            for i in range(lo, hi):
+                k = slot * chunk + (i - lo)  # loss slot: reused two chunks later, after its read-back was enqueued
+                self.train_step(self._chunk_bufs[slot][i - lo], first_gstep + i, loss_out=self._loss_ring[k])
+                # read this step's result back on the side stream: the training stream never waits for PCIe
+                self._loss_ev[k].record(main)
+                cs.wait_event(self._loss_ev[k])
+                with torch.cuda.stream(cs):
+                    losses_host[i].copy_(self._loss_ring[k], non_blocking=True)
+            self._chunk_free[slot].record(main)
+        return losses_host
+
     def _upload(self, slot, x_host, main):
         if self._stage[slot] is None or self._stage[slot].shape != x_host.shape:
             self._stage[slot] = torch.empty(x_host.shape, device=self.device, dtype=torch.float32)
@@ -205,9 +254,10 @@ class TrainerVAE:
         self._stage_src[slot] = x_host
 
     # -- the step ------------------------------------------------------------------------------------
-    def train_step(self, x: torch.Tensor, gstep: int = 0, philox=None):
+    def train_step(self, x: torch.Tensor, gstep: int = 0, philox=None, loss_out: torch.Tensor = None):
         """x: (B_local, 1, H, W) or (B_local, D) device tensor (this rank's slice of the global batch).
-        Returns the device tensor [loss, mse, kl] (global-batch means; no host sync)."""
+        Returns the device tensor [loss, mse, kl] (global-batch means; no host sync); `loss_out` (3 floats on
+        the device) receives it instead of the trainer's own scratch."""
         cfg, m, lib = self.cfg, self.model, self.lib
         x2 = x.reshape(x.shape[0], -1).contiguous()
         B, D = x2.shape
@@ -222,6 +272,7 @@ class TrainerVAE:
         ind = INDICATOR_CODES[m.cfg.indicator_approx]
         seed, offset = next_philox(self.device) if philox is None else philox
         b = self._buffers(B)
+        loss = b['loss'] if loss_out is None else loss_out
         s = _stream()
         chk = _lib.check
         events = None
@@ -234,11 +285,11 @@ class TrainerVAE:
             self.kernel_events.setdefault('sampler_bwd', []).append((evs[2], evs[3]))
         # forward + loss + backward: one call, every kernel enqueued back to back (csrc/lin_step.cu)
         chk(lib.pvae_lin_step_fwd_bwd(
-            _ptr(x2), _ptr(self.flat_p), _ptr(self.flat_g), _ptr(b['ws']), _ptr(b['loss']),
+            _ptr(x2), _ptr(self.flat_p), _ptr(self.flat_g), _ptr(b['ws']), _ptr(loss),
             self.r_max.data_ptr() + 4 * (gstep % self.r_max.numel()), B, Bg, row_offset, K, D,
             int(m.fc_enc.bias is not None), n_exp, temp, beta, ind, int(m.cfg.exc_only), m.exit_logit,
             int(linear_mod.PRECISE), seed, offset, None, events, s))
-        dp.allreduce_gradients(self.flat_g, b['loss'], self.pg)  # gradients already carry 1 / B_global
+        dp.allreduce_gradients(self.flat_g, loss, self.pg)  # gradients already carry 1 / B_global
         # clip (main/train_vae.py:365-377) + Adamax (base/adamax.py)
         clip = None
         if cfg.grad_clip is not None:
@@ -250,7 +301,7 @@ class TrainerVAE:
         chk(lib.pvae_adamax_step(_ptr(self.flat_p), _ptr(self.flat_g), _ptr(self.exp_avg), _ptr(self.exp_inf),
                                  self.flat_p.numel(), lr, self.opt_step, cfg.betas[0], cfg.betas[1], cfg.eps,
                                  cfg.weight_decay, _ptr(clip), s))
-        return b['loss']
+        return loss
 
     def iteration(self, data: torch.Tensor, epoch: int = 0):
         """One epoch over a device-resident dataset (N, 1, H, W), like main/train_vae.py:317-459 with a
