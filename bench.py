@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu_rows", type=int, default=256, help="rows of the batch the CPU baseline steps on")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_pdl", action="store_true", help="disable programmatic dependent launch (A/B)")
+    ap.add_argument("--no_overlap", action="store_true", help="keep the whole step on one stream (A/B)")
     ap.add_argument("--tf32", action="store_true", help="single-pass TF32 GEMMs instead of 3xTF32 (A/B)")
     return ap.parse_args()
 
@@ -162,6 +163,8 @@ def run_ours(args):
     lib = _lib.load()  # fails loudly if the CUDA extension has not been built
     if args.no_pdl:
         lib.pvae_set_pdl(0)
+    if args.no_overlap:
+        lib.pvae_set_step_overlap(0)
     if args.tf32:
         from poissonvae_b200 import linear as _linear
         _linear.PRECISE = False
@@ -195,6 +198,17 @@ def run_ours(args):
     for i in range(W):
         tr.train_step(data[i % NB], i)
     barrier()
+    # every pass below (device-resident, instrumented, end-to-end) trains the same K steps from this state: the
+    # sampler's work depends on the rates, so the passes must not see different stages of training
+    snap = (tr.flat_p.clone(), tr.exp_avg.clone(), tr.exp_inf.clone(), tr.opt_step)
+
+    def restore():
+        tr.flat_p.copy_(snap[0]), tr.exp_avg.copy_(snap[1]), tr.exp_inf.copy_(snap[2])
+        tr.opt_step = snap[3]
+        torch.cuda.manual_seed(4321)
+        barrier()
+
+    restore()
     if clocks is not None:
         clocks.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -209,9 +223,10 @@ def run_ours(args):
     ms_total = ms.item()
     # the same K steps again, now with CUDA events around the two sampler launches (roofline numerator).  Kept out
     # of the pass above because an event record between two kernels defeats their programmatic dependent launch.
+    restore()
     tr.kernel_events = {}
     for i in range(K_steps):
-        tr.train_step(data[(W + K_steps + i) % NB], W + K_steps + i)
+        tr.train_step(data[(W + i) % NB], W + i)
     barrier()
     ktimes = tr.kernel_times_us()
     tr.kernel_events = None
@@ -225,12 +240,13 @@ def run_ours(args):
 
     warm_host = host_steps(0, min(max(W, 1), NB))
     tr.fit_host(warm_host, 0)
+    restore()
     timed_host = host_steps(W % NB, K_steps) if K_steps <= NB else None
     if timed_host is None:  # more steps than distinct batches: cycle through the 64 pinned batches
         timed_host = host.repeat((K_steps + NB - 1) // NB, 1, 1)[:K_steps].pin_memory()
     barrier()
     t0 = time.perf_counter()
-    loss_host = tr.fit_host(timed_host, W + 2 * K_steps)
+    loss_host = tr.fit_host(timed_host, W)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:

@@ -169,6 +169,9 @@ int pvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, i
  *   precise: GEMM mode (see pvae_gemm_tf32); events: NULL or 4 cudaEvent_t recorded before/after the sampler
  *   forward (0,1) and before/after the sampler backward (2,3) - used by bench.py for the roofline timing. */
 int64_t pvae_lin_step_ws_floats(int64_t B, int64_t K, int64_t D);
+/* Tuning knob (process-wide, default on): run the decoder wgrad and the loss assembly of pvae_lin_step_fwd_bwd on
+ * an internal side stream (forked from / joined back into the caller's stream with events). */
+int pvae_set_step_overlap(int on);
 int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, float* ws, float* loss3, float* rate_max,
                           int64_t B, int64_t B_global, int64_t row_offset, int64_t K, int64_t D, int has_bias, int n_exp,
                           float temp, float beta, int indicator, int exc_only, float exit_logit, int precise,

@@ -59,6 +59,7 @@ _SIGNATURES = {
     "pvae_grad_norm": (_i, [_p, _i64, _f, _p, _p, _p]),
     "pvae_adamax_step": (_i, [_p, _p, _p, _p, _i64, _f, _i, _f, _f, _f, _f, _p, _p]),
     "pvae_lin_step_ws_floats": (_i64, [_i64, _i64, _i64]),
+    "pvae_set_step_overlap": (_i, [_i]),
     "pvae_lin_step_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i,
                                    _u64, _u64, _p, _p, _p]),
     "pvae_set_phase_a_events": (_i, [_i]),

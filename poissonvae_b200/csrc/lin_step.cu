@@ -19,8 +19,29 @@
 
 namespace {
 
+// Side stream for the work that is off the critical path (decoder wgrad, loss assembly): created once per device.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+
+SideStream* side_stream() {
+  static SideStream per_device[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& s = per_device[dev];
+  if (!s.stream) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &s;
+}
+
+int g_overlap = 1;
+
 struct Ws {
-  float *h, *z, *dz, *y, *g_y, *g_z, *g_h, *recon, *klrow, *partials, *splitk;
+  float *h, *z, *dz, *y, *g_y, *g_z, *g_h, *recon, *klrow, *partials, *splitk, *splitk2;
   int64_t total;
 };
 
@@ -44,12 +65,18 @@ Ws carve(float* base, int64_t B, int64_t K, int64_t D) {
   w.recon = take(B * pvae_gemm_residual_parts(D)), w.klrow = take(B);
   w.partials = take(2 * pvae_num_partials(B) * K);
   const int64_t s1 = pvae_gemm_ws_floats(D, K, wgrad_splits(D, K, B)), s2 = pvae_gemm_ws_floats(K, D, wgrad_splits(K, D, B));
-  w.splitk = take(s1 > s2 ? s1 : s2);
+  w.splitk = take(s1);   // decoder wgrad (may run on the side stream, concurrently with ...)
+  w.splitk2 = take(s2);  // ... the encoder wgrad
   w.total = o;
   return w;
 }
 
 }  // namespace
+
+extern "C" int pvae_set_step_overlap(int on) {
+  g_overlap = on != 0;
+  return PVAE_OK;
+}
 
 extern "C" int64_t pvae_lin_step_ws_floats(int64_t B, int64_t K, int64_t D) {
   if (B <= 0 || K <= 0 || D <= 0) return 0;
@@ -88,10 +115,18 @@ extern "C" int pvae_lin_step_fwd_bwd(const float* x, const float* params, float*
   // decoder GEMM with the residual fused into its epilogue: g_y and per-tile squared errors, y itself is never stored
   if ((rc = pvae_gemm_tf32_residual(w.z, w_dec, x, w.g_y, w.recon, B, D, K, 2.0f / static_cast<float>(B_global), precise, s)))
     return rc;
-  if ((rc = pvae_loss_assemble(w.recon, w.klrow, loss3, B, beta, B_global, static_cast<int>(pvae_gemm_residual_parts(D)), s)))
+  // ---- backward.  Off the critical path (decoder wgrad, loss assembly) goes to a side stream so that it fills
+  // the SMs the dgrad GEMM leaves idle and overlaps the elementwise sampler backward.
+  SideStream* side = g_overlap ? side_stream() : nullptr;
+  cudaStream_t s2 = side ? side->stream : s;
+  if (side) {
+    if ((rc = pvae::cuda_ok("fork", cudaEventRecord(side->fork, s)))) return rc;
+    if ((rc = pvae::cuda_ok("fork", cudaStreamWaitEvent(s2, side->fork, 0)))) return rc;
+  }
+  if ((rc = pvae_loss_assemble(w.recon, w.klrow, loss3, B, beta, B_global, static_cast<int>(pvae_gemm_residual_parts(D)), s2)))
     return rc;
-  // ---- backward
-  if ((rc = pvae_gemm_tf32(w.g_y, w.z, g_w_dec, D, K, B, 0, 0, precise, wgrad_splits(D, K, B), w.splitk, s))) return rc;
+  if ((rc = pvae_gemm_tf32(w.g_y, w.z, g_w_dec, D, K, B, 0, 0, precise, wgrad_splits(D, K, B), w.splitk, s2))) return rc;
+  if (side && (rc = pvae::cuda_ok("join", cudaEventRecord(side->join, s2)))) return rc;
   if ((rc = pvae_gemm_tf32(w.g_y, w_dec, w.g_z, B, K, D, 1, 0, precise, 1, nullptr, s))) return rc;
   mark(2);
   if ((rc = pvae_sampler_bwd(w.h, log_r, b_enc, w.g_z, nullptr, w.dz, beta / static_cast<float>(B_global), w.g_h, g_log_r, g_b_enc,
@@ -99,6 +134,7 @@ extern "C" int pvae_lin_step_fwd_bwd(const float* x, const float* params, float*
                              offset_dev, s)))
     return rc;
   mark(3);
-  if ((rc = pvae_gemm_tf32(w.g_h, x, g_w_enc, K, D, B, 0, 0, precise, wgrad_splits(K, D, B), w.splitk, s))) return rc;
+  if ((rc = pvae_gemm_tf32(w.g_h, x, g_w_enc, K, D, B, 0, 0, precise, wgrad_splits(K, D, B), w.splitk2, s))) return rc;
+  if (side && (rc = pvae::cuda_ok("join", cudaStreamWaitEvent(s, side->join, 0)))) return rc;
   return PVAE_OK;
 }

@@ -215,10 +215,17 @@ class TrainerVAE:
         main = torch.cuda.current_stream()
         cs = self._copy_stream
 
+        # chunk boundaries: a short first chunk so that training starts after ~0.2 ms of DMA, then full chunks
+        bounds, lo = [], 0
+        while lo < n_steps:
+            hi = min(lo + (min(2, chunk) if not bounds else chunk), n_steps)
+            bounds.append((lo, hi))
+            lo = hi
+
         def upload(c):  # chunk index -> staging buffer c % 2
-            lo, hi = c * chunk, min((c + 1) * chunk, n_steps)
-            if lo >= n_steps:
+            if c >= len(bounds):
                 return
+            lo, hi = bounds[c]
             slot = c % 2
             cs.wait_event(self._chunk_free[slot])
             with torch.cuda.stream(cs):
@@ -226,12 +233,10 @@ class TrainerVAE:
                 self._chunk_ready[slot].record(cs)
 
         upload(0)
-        n_chunks = (n_steps + chunk - 1) // chunk
-        for c in range(n_chunks):
+        for c, (lo, hi) in enumerate(bounds):
             upload(c + 1)  # overlaps this chunk's compute
             slot = c % 2
             main.wait_event(self._chunk_ready[slot])
-            lo, hi = c * chunk, min((c + 1) * chunk, n_steps)
             for i in range(lo, hi):
                 k = slot * chunk + (i - lo)  # loss slot: reused two chunks later, after its read-back was enqueued
                 self.train_step(self._chunk_bufs[slot][i - lo], first_gstep + i, loss_out=self._loss_ring[k])

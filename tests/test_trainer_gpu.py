@@ -94,3 +94,21 @@ def test_schedules_and_epoch_loop():
     assert all(np.isfinite(nelbo)) and np.mean(nelbo[-3:]) < np.mean(nelbo[:3])
     assert not torch.equal(before, model.fc_dec.weight)
     assert int(model.n_exp) < n0  # update_n from the epoch's mean rate.max(), main/train_vae.py:456-457
+
+
+def test_fit_host_equals_resident_steps():
+    """Pinned host batches through the chunked, double-buffered feeder == the same steps on resident batches."""
+    g = np.load(GOLDEN[0])
+    host = torch.randn(11, 16, 256, generator=torch.Generator().manual_seed(5)).pin_memory()
+    results = []
+    for use_host in (False, True):
+        tr = make_trainer(g)
+        torch.cuda.manual_seed(99)
+        if use_host:
+            losses = tr.fit_host(host, 0, chunk=4)
+            torch.cuda.synchronize()
+        else:
+            losses = torch.stack([tr.train_step(host[i].cuda(), i).clone() for i in range(11)]).cpu()
+        results.append((losses.clone(), tr.flat_p.clone()))
+    assert torch.equal(results[0][0], results[1][0])
+    assert torch.equal(results[0][1], results[1][1])
