@@ -247,6 +247,7 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     loss_host = tr.fit_host(timed_host, W)
+    t_enq = time.perf_counter() - t0  # host-side enqueue time (the GPU may still be working)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
@@ -277,7 +278,8 @@ def run_ours(args):
                        parallelism=f"dp{world}", final_loss=round(final_loss, 4)),
         "clocks": clk,
         "e2e": {"value": round(world * B * K_steps / e2e_s.item(), 1), "unit": UNIT,
-                "h2d_bytes_per_step": B * 256 * 4, "d2h_bytes_per_step": 12},
+                "h2d_bytes_per_step": B * 256 * 4, "d2h_bytes_per_step": 12,
+                "host_enqueue_us_per_step": round(t_enq / K_steps * 1e6, 1)},
         "gpu_launches": K_steps * tr.launches_per_step(),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,

@@ -97,6 +97,7 @@ class TrainerVAE:
         self.lib = _lib.load()
         self.r_max = torch.zeros(max(n_batches_per_epoch, 1), device=self.device)  # rate.max() of each step of the epoch
         self.kernel_events = None  # set to {} to record CUDA events around the named launches (bench.py)
+        self._stream_handle = None  # fit_host pins the launch stream for the duration of its loop
         self._copy_stream = None
 
     # -- one flat fp32 buffer for parameters, gradients and Adamax state ------------------------
@@ -194,15 +195,18 @@ class TrainerVAE:
         self._cur = 1 - cur
         return out
 
-    def fit_host(self, batches_host: torch.Tensor, first_gstep: int = 0, chunk: int = 16, losses_host: torch.Tensor = None):
+    def fit_host(self, batches_host: torch.Tensor, first_gstep: int = 0, chunk: int = 8, losses_host: torch.Tensor = None,
+                 direct: bool = None):
         """Train on `batches_host`, a pinned host tensor (n_steps, B, D): the public entry point for data that lives
         in host memory.  Batches are uploaded `chunk` at a time on a side stream into two alternating device
         buffers (one large DMA amortises the per-copy latency that dominates 4 MiB transfers) while the previous
         chunk trains; every step's [loss, mse, kl] is copied back to pinned memory asynchronously.
         Returns the pinned (n_steps, 3) tensor of results (valid after torch.cuda.synchronize())."""
         n_steps = batches_host.shape[0]
-        if losses_host is None:
-            losses_host = torch.empty(n_steps, 3).pin_memory()
+        if losses_host is None:  # pinned allocations cost milliseconds: keep one and grow it when needed
+            if getattr(self, "_losses_host", None) is None or self._losses_host.shape[0] < n_steps:
+                self._losses_host = torch.empty(max(n_steps, 1024), 3).pin_memory()
+            losses_host = self._losses_host[:n_steps]
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         shape = (chunk,) + tuple(batches_host.shape[1:])
@@ -214,13 +218,22 @@ class TrainerVAE:
             self._loss_ev = [torch.cuda.Event() for _ in range(2 * chunk)]
         main = torch.cuda.current_stream()
         cs = self._copy_stream
+        # every step's [loss, mse, kl] lands in a small device ring and is copied back on the side stream, so the
+        # training stream never waits for PCIe.  direct=True (single process only) lets the loss kernel write its
+        # 12 bytes straight into the pinned host row instead (UVA) - measured slightly slower, kept for comparison.
+        if direct is None:
+            direct = False
+        if direct and self.world > 1:
+            raise ValueError("direct host writes are not all-reduced: use direct=False for data-parallel runs")
+        self._stream_handle = main.cuda_stream
 
-        # chunk boundaries: a short first chunk so that training starts after ~0.2 ms of DMA, then full chunks
-        bounds, lo = [], 0
+        # chunk boundaries: 1, 2, 4, ... batches up to `chunk`, so that training starts after ~0.1 ms of DMA and
+        # each upload is hidden behind the (doubling) compute of the chunk before it
+        bounds, lo, size = [], 0, 1
         while lo < n_steps:
-            hi = min(lo + (min(2, chunk) if not bounds else chunk), n_steps)
+            hi = min(lo + size, n_steps)
             bounds.append((lo, hi))
-            lo = hi
+            lo, size = hi, min(2 * size, chunk)
 
         def upload(c):  # chunk index -> staging buffer c % 2
             if c >= len(bounds):
@@ -238,6 +251,9 @@ class TrainerVAE:
             slot = c % 2
             main.wait_event(self._chunk_ready[slot])
             for i in range(lo, hi):
+                if direct:
+                    self.train_step(self._chunk_bufs[slot][i - lo], first_gstep + i, loss_out=losses_host[i])
+                    continue
                 k = slot * chunk + (i - lo)  # loss slot: reused two chunks later, after its read-back was enqueued
                 self.train_step(self._chunk_bufs[slot][i - lo], first_gstep + i, loss_out=self._loss_ring[k])
                 # read this step's result back on the side stream: the training stream never waits for PCIe
@@ -246,6 +262,7 @@ class TrainerVAE:
                 with torch.cuda.stream(cs):
                     losses_host[i].copy_(self._loss_ring[k], non_blocking=True)
             self._chunk_free[slot].record(main)
+        self._stream_handle = None
         return losses_host
 
     def _upload(self, slot, x_host, main):
@@ -272,13 +289,14 @@ class TrainerVAE:
         temp = float(self.temperatures[min(gstep, self.n_iters - 1)])
         beta = float(self.betas[min(gstep, self.n_iters - 1)])
         lr = self.lr_at(gstep)
-        m.update_t(temp)
+        if temp != m._temp_host:
+            m.update_t(temp)
         n_exp = m._n_exp_host
         ind = INDICATOR_CODES[m.cfg.indicator_approx]
         seed, offset = next_philox(self.device) if philox is None else philox
         b = self._buffers(B)
         loss = b['loss'] if loss_out is None else loss_out
-        s = _stream()
+        s = self._stream_handle if self._stream_handle is not None else _stream()
         chk = _lib.check
         events = None
         if self.kernel_events is not None:  # CUDA events around the two sampler launches (bench.py roofline)

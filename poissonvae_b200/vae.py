@@ -205,8 +205,9 @@ class PoissonVAE(nn.Module):
         self._init_prior()
         self._init_weight()
         self.register_buffer('n_exp', torch.tensor(0))  # main/vae.py:378-381
-        self._temp_host = 1.0
-        self._n_exp_host = 0
+        # host mirrors of the two scalar buffers (plain attributes: no device sync to read them)
+        object.__setattr__(self, '_temp_host', 1.0)
+        object.__setattr__(self, '_n_exp_host', 0)
         self.update_n(200.0)  # main/vae.py:382
 
     # ---- reference API -------------------------------------------------------------------
