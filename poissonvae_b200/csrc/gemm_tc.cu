@@ -305,27 +305,38 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       __syncwarp();
       const int sub = lane >> 3, col = 4 * (lane & 7);
       const int n = n0 + c0 + col;
+      if (!residual) {
 #pragma unroll
-      for (int rr = 0; rr < 32; rr += 4) {
-        const int row = rr + sub;
-        const int mm = m0 + quarter * 32 + row;
-        const float* src = stg + row * 33 + col;
-        const bool in = mm < p.M && n < p.N;  // N is a multiple of 4
-        if (!residual) {
-          if (in) *reinterpret_cast<float4*>(cbase + static_cast<long long>(mm) * p.N + n) = make_float4(src[0], src[1], src[2], src[3]);
-        } else {
+        for (int rr = 0; rr < 32; rr += 4) {
+          const int row = rr + sub;
+          const int mm = m0 + quarter * 32 + row;
+          const float* src = stg + row * 33 + col;
+          if (mm < p.M && n < p.N)  // N is a multiple of 4
+            *reinterpret_cast<float4*>(cbase + static_cast<long long>(mm) * p.N + n) = make_float4(src[0], src[1], src[2], src[3]);
+        }
+      } else {
+        float4 xv[8];  // all eight row segments of X in flight before any is used
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int mm = m0 + quarter * 32 + 4 * i + sub;
+          xv[i] = (mm < p.M && n < p.N) ? ldg4(p.X + static_cast<long long>(mm) * p.N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = 4 * i + sub;
+          const int mm = m0 + quarter * 32 + row;
+          const float* src = stg + row * 33 + col;
           float sq = 0.f;
-          if (in) {
-            const long long o = static_cast<long long>(mm) * p.N + n;
-            const float4 xv = ldg4(p.X + o);
-            const float4 r = make_float4(src[0] - xv.x, src[1] - xv.y, src[2] - xv.z, src[3] - xv.w);
-            stg4(p.G + o, make_float4(p.g_scale * r.x, p.g_scale * r.y, p.g_scale * r.z, p.g_scale * r.w));
+          if (mm < p.M && n < p.N) {
+            const float4 r = make_float4(src[0] - xv[i].x, src[1] - xv[i].y, src[2] - xv[i].z, src[3] - xv[i].w);
+            stg4(p.G + static_cast<long long>(mm) * p.N + n,
+                 make_float4(p.g_scale * r.x, p.g_scale * r.y, p.g_scale * r.z, p.g_scale * r.w));
             sq = (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
           }
           sq += __shfl_xor_sync(0xffffffffu, sq, 1);  // the 8 lanes that share a row
           sq += __shfl_xor_sync(0xffffffffu, sq, 2);
           sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-          rowacc[rr / 4] += sq;
+          rowacc[i] += sq;
         }
       }
     }
