@@ -111,7 +111,10 @@ class TrainerVAE:
         params = dict(m.named_parameters())
         n = sum(params[k].numel() for k in names)
         self.flat_p = torch.empty(n, device=self.device, dtype=torch.float32)
-        self.flat_g = torch.zeros_like(self.flat_p)
+        # gradient buffer + 4 trailing floats for [loss, mse, kl, -]: data parallel sums both with ONE all-reduce
+        self._flat_g_ext = torch.zeros(n + 4, device=self.device, dtype=torch.float32)
+        self.flat_g = self._flat_g_ext[:n]
+        self._loss_tail = self._flat_g_ext[n:n + 3]
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_inf = torch.zeros_like(self.flat_p)
         self.views, self.gviews, o = {}, {}, 0
@@ -295,7 +298,11 @@ class TrainerVAE:
         ind = INDICATOR_CODES[m.cfg.indicator_approx]
         seed, offset = next_philox(self.device) if philox is None else philox
         b = self._buffers(B)
-        loss = b['loss'] if loss_out is None else loss_out
+        # data parallel: the step writes its loss shares behind the gradients so that one all-reduce sums both
+        loss = (self._loss_tail if self.world > 1 else b['loss']) if loss_out is None else loss_out
+        loss_target = loss
+        if self.world > 1:
+            loss = self._loss_tail
         s = self._stream_handle if self._stream_handle is not None else _stream()
         chk = _lib.check
         events = None
@@ -312,7 +319,11 @@ class TrainerVAE:
             self.r_max.data_ptr() + 4 * (gstep % self.r_max.numel()), B, Bg, row_offset, K, D,
             int(m.fc_enc.bias is not None), n_exp, temp, beta, ind, int(m.cfg.exc_only), m.exit_logit,
             int(linear_mod.PRECISE), seed, offset, None, events, s))
-        dp.allreduce_gradients(self.flat_g, loss, self.pg)  # gradients already carry 1 / B_global
+        if self.world > 1:
+            dp.allreduce_gradients(self._flat_g_ext, None, self.pg)  # gradients already carry 1 / B_global
+            if loss_target is not loss:
+                loss_target.copy_(loss)
+            loss = loss_target
         # clip (main/train_vae.py:365-377) + Adamax (base/adamax.py)
         clip = None
         if cfg.grad_clip is not None:
