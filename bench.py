@@ -282,7 +282,11 @@ def run_ours(args):
                 "host_enqueue_us_per_step": round(t_enq / K_steps * 1e6, 1)},
         "gpu_launches": K_steps * tr.launches_per_step(),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "frac": round(achieved / peak, 4),
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/README.md);
+                     # only captured for the default workload's forward sampler
+                     "traffic": 8415488 if (dom == "sampler_fwd" and B == 4096 and K == 512) else None,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": B * K * bytes_per_latent,
                      "kernel_us": {k: round(v, 2) for k, v in ktimes.items()},
                      "timed": f"CUDA events on the launch stream around each sampler launch, mean over {K_steps} steps "
