@@ -83,11 +83,16 @@ def cpu_reference_steps(args, steps, warmup):
 
 
 def run_reference(args):
+    """Reference arm: the reference's own step on the host cores (its torch-CPU port, all threads).  Exactly K timed
+    steps after min(W, 3) warm-up steps; every step is a bounded sample of the workload (`rows` of the batch), sized
+    so that the whole run takes about a minute whatever K is."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 8))  # each step is a bounded sample; keep the arm within minutes
-    warmup = max(1, min(args.warmup, 2))
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
+    # ~3.3 ms per row and step on 16 cores at n_exp = 263 (measured); aim at ~60 s of CPU work
+    rows = int(60.0 / (0.0033 * (steps + warmup) * max(args.n_exp, 1) / 263.0))
+    args.cpu_rows = max(8, min(args.cpu_rows, rows - rows % 4))
     v, cores, sps = cpu_reference_steps(args, steps, warmup)
     sample = f"{args.cpu_rows} of {args.batch} rows per step, {steps} steps after {warmup} warm-up, torch CPU {cores} threads"
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus,
