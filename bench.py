@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--cpu_rows", type=int, default=256, help="rows of the batch the CPU baseline steps on")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_pdl", action="store_true", help="disable programmatic dependent launch (A/B)")
+    ap.add_argument("--dp", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: gradient exchange over NVLink peer memory fused with Adamax, or NCCL all-reduce")
     ap.add_argument("--no_overlap", action="store_true", help="keep the whole step on one stream (A/B)")
     ap.add_argument("--tf32", action="store_true", help="single-pass TF32 GEMMs instead of 3xTF32 (A/B)")
     return ap.parse_args()
@@ -187,7 +189,7 @@ def run_ours(args):
     cfg = ConfigTrainVAE(lr=0.005, epochs=3000, batch_size=B, warmup_portion=0.01, grad_clip=None,
                          kl_beta=args.beta, kl_anneal_portion=0.0, kl_const_portion=0.0, temp_anneal_portion=0.0,
                          temp_stop=args.temp)
-    tr = TrainerVAE(model, cfg, n_batches_per_epoch=26)
+    tr = TrainerVAE(model, cfg, n_batches_per_epoch=26, dp_mode=args.dp)
 
     # inputs: 64 distinct batches (268 MB at B=4096 > 126 MB L2) so that no step finds its input in L2
     NB = 64
@@ -280,7 +282,10 @@ def run_ours(args):
         "ms_per_step": round(ms_total / K_steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": dict(workload(args), l2="inputs rotate over 64 distinct batches (268 MB > 126 MB L2)",
-                       parallelism=f"dp{world}", final_loss=round(final_loss, 4)),
+                       parallelism=f"dp{world}", final_loss=round(final_loss, 4),
+                       gradient_exchange=("none (1 GPU)" if world == 1 else
+                                          "NVLink peer-memory all-reduce fused with Adamax" if tr.peer is not None else
+                                          "NCCL all-reduce")),
         "clocks": clk,
         "e2e": {"value": round(world * B * K_steps / e2e_s.item(), 1), "unit": UNIT,
                 "h2d_bytes_per_step": B * 256 * 4, "d2h_bytes_per_step": 12,

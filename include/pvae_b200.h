@@ -158,6 +158,20 @@ int pvae_grad_norm(const float* g, int64_t n, float max_norm, float* ws, float* 
 int pvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, float lr, int step, float beta1,
                      float beta2, float eps, float weight_decay, const float* clip_coef, void* stream);
 
+/* ---- data parallel: gradient all-reduce over NVLink peer memory fused with the Adamax update -------------------
+ * One kernel per step replaces NCCL all-reduce + pvae_adamax_step: every rank publishes a step token to its peers'
+ * flag arrays, waits for theirs, then sums all ranks' gradient buffers (P2P loads, fixed rank order -> bit-identical
+ * sums everywhere) and updates p / exp_avg / exp_inf in the same pass.
+ *   peer_grads[r], peer_flags[r]: HOST arrays of `world` DEVICE pointers - rank r's symmetric gradient buffer for this
+ *   step's parity (n_ext floats: n gradients + a tail of (n_ext - n) statistics that is only summed into tail_out) and
+ *   rank r's flag array (>= world 32-bit words, zero before the first step).  token: the 1-based step count, equal on
+ *   all ranks and increasing by 1 per call; gradients must alternate between two buffers by step parity (the kernel has
+ *   no trailing barrier).  g_sum_out: optional copy of the summed gradients.  No gradient clipping on this path.
+ *   Ranks must sit on different GPUs: the kernels of a step wait on one another. */
+int pvae_allreduce_adamax(float* p, float* exp_avg, float* exp_inf, int64_t n, int64_t n_ext, const void* const* peer_grads,
+                          void* const* peer_flags, int world, int rank, uint32_t token, float* tail_out, float* g_sum_out,
+                          float lr, int step, float beta1, float beta2, float eps, float weight_decay, void* stream);
+
 /* ---- one call per training step of the lin|lin model ------------------------------------------
  * Replaces the forward + loss + backward part of TrainerVAE.iteration main/train_vae.py:342-362 (model forward
  * main/vae.py:384-391, losses :68-72 / :446-450, loss assembly main/train_vae.py:347-351, autograd backward) for

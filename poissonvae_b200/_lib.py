@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpvae_b200.so")
-SOURCES = ["capi.cu", "sampler.cu", "step.cu", "gemm_tc.cu", "lin_step.cu"]
+SOURCES = ["capi.cu", "sampler.cu", "step.cu", "gemm_tc.cu", "lin_step.cu", "peer_allreduce.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -58,6 +58,7 @@ _SIGNATURES = {
     "pvae_grad_norm_ws_floats": (_i64, []),
     "pvae_grad_norm": (_i, [_p, _i64, _f, _p, _p, _p]),
     "pvae_adamax_step": (_i, [_p, _p, _p, _p, _i64, _f, _i, _f, _f, _f, _f, _p, _p]),
+    "pvae_allreduce_adamax": (_i, [_p, _p, _p, _i64, _i64, _p, _p, _i, _i, C.c_uint32, _p, _p, _f, _i, _f, _f, _f, _f, _p]),
     "pvae_lin_step_ws_floats": (_i64, [_i64, _i64, _i64]),
     "pvae_set_step_overlap": (_i, [_i]),
     "pvae_lin_step_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i,

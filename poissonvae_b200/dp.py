@@ -42,3 +42,33 @@ def allreduce_max(t: torch.Tensor, group=None):
     world, _ = world_info(group)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+
+
+class PeerExchange:
+    """Symmetric (peer-mapped) gradient double buffer + flag array for `pvae_allreduce_adamax`: every rank can read
+    every other rank's gradients over NVLink / NVSwitch, so the all-reduce and the optimiser update become one kernel.
+    Built on torch.distributed._symmetric_memory (allocation + handle exchange only - the kernel is ours)."""
+
+    def __init__(self, n_ext: int, device, group=None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = group if group is not None else dist.group.WORLD
+        self.n_ext = n_ext
+        self.buf = symm_mem.empty(2 * n_ext, dtype=torch.float32, device=device)
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)
+        self.buf.zero_()
+        self.flags.zero_()
+        torch.cuda.synchronize(device)
+        h_buf = symm_mem.rendezvous(self.buf, grp)
+        h_flag = symm_mem.rendezvous(self.flags, grp)
+        dist.barrier(grp)  # nobody publishes a token before every rank has zeroed its flags
+        self.world, self.rank = h_buf.world_size, h_buf.rank
+        ptrs = [int(p) for p in h_buf.buffer_ptrs]
+        self.grad_ptrs = [(ctypes.c_void_p * self.world)(*[p + parity * n_ext * 4 for p in ptrs]) for parity in (0, 1)]
+        self.flag_ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in h_flag.buffer_ptrs])
+        self._handles = (h_buf, h_flag)  # keep the mappings alive
+
+    def grads(self, parity: int) -> torch.Tensor:
+        """This rank's gradient buffer (n_ext floats) for the given step parity."""
+        return self.buf[parity * self.n_ext:(parity + 1) * self.n_ext]

@@ -75,7 +75,7 @@ class ConfigTrainVAE:
 
 class TrainerVAE:
     def __init__(self, model: PoissonVAE, cfg: ConfigTrainVAE, n_batches_per_epoch: int = 1,
-                 process_group=None):
+                 process_group=None, dp_mode: str = 'auto'):
         self.model, self.cfg = model, cfg
         self.device = model.log_rate.device
         if self.device.type != 'cuda':
@@ -95,6 +95,21 @@ class TrainerVAE:
         self.stats = {}
         self._bufs = {}
         self.lib = _lib.load()
+        # data-parallel exchange: 'peer' = all-reduce over NVLink peer memory fused with Adamax (one kernel),
+        # 'nccl' = NCCL all-reduce followed by the Adamax kernel; 'auto' prefers 'peer' when it can be set up
+        # (it has no gradient clipping: the norm of the summed gradient would need a second pass)
+        self.peer = None
+        assert dp_mode in ('auto', 'peer', 'nccl')
+        if self.world > 1 and dp_mode != 'nccl' and cfg.grad_clip is None:
+            try:
+                self.peer = dp.PeerExchange(self._flat_g_ext.numel(), self.device, process_group)
+            except Exception as exc:  # no P2P / symmetric memory on this system
+                if dp_mode == 'peer':
+                    raise
+                import warnings
+                warnings.warn(f"peer-memory gradient exchange unavailable ({exc!r}); using NCCL all-reduce")
+        elif dp_mode == 'peer' and self.world > 1:
+            raise ValueError("dp_mode='peer' does not support grad_clip")
         self.r_max = torch.zeros(max(n_batches_per_epoch, 1), device=self.device)  # rate.max() of each step of the epoch
         self.kernel_events = None  # set to {} to record CUDA events around the named launches (bench.py)
         self._stream_handle = None  # fit_host pins the launch stream for the duration of its loop
@@ -114,7 +129,7 @@ class TrainerVAE:
         # gradient buffer + 4 trailing floats for [loss, mse, kl, -]: data parallel sums both with ONE all-reduce
         self._flat_g_ext = torch.zeros(n + 4, device=self.device, dtype=torch.float32)
         self.flat_g = self._flat_g_ext[:n]
-        self._loss_tail = self._flat_g_ext[n:n + 3]
+
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_inf = torch.zeros_like(self.flat_p)
         self.views, self.gviews, o = {}, {}, 0
@@ -130,7 +145,7 @@ class TrainerVAE:
         if B not in self._bufs:
             K, D = self.model.cfg.n_latents, self.model.cfg.input_sz ** 2
             f = lambda *s: torch.empty(*s, device=self.device, dtype=torch.float32)
-            self._bufs[B] = dict(ws=f(self.lib.pvae_lin_step_ws_floats(B, K, D)), loss=f(3),
+            self._bufs[B] = dict(ws=f(self.lib.pvae_lin_step_ws_floats(B, K, D)), loss=f(4),
                                  nws=f(self.lib.pvae_grad_norm_ws_floats()), norm=f(2))
         return self._bufs[B]
 
@@ -217,7 +232,7 @@ class TrainerVAE:
             self._chunk_bufs = [torch.empty(shape, device=self.device, dtype=torch.float32) for _ in range(2)]
             self._chunk_ready = [torch.cuda.Event(), torch.cuda.Event()]
             self._chunk_free = [torch.cuda.Event(), torch.cuda.Event()]
-            self._loss_ring = torch.empty(2 * chunk, 3, device=self.device, dtype=torch.float32)
+            self._loss_ring = torch.empty(2 * chunk, 4, device=self.device, dtype=torch.float32)
             self._loss_ev = [torch.cuda.Event() for _ in range(2 * chunk)]
         main = torch.cuda.current_stream()
         cs = self._copy_stream
@@ -263,7 +278,7 @@ class TrainerVAE:
                 self._loss_ev[k].record(main)
                 cs.wait_event(self._loss_ev[k])
                 with torch.cuda.stream(cs):
-                    losses_host[i].copy_(self._loss_ring[k], non_blocking=True)
+                    losses_host[i].copy_(self._loss_ring[k, :3], non_blocking=True)
             self._chunk_free[slot].record(main)
         self._stream_handle = None
         return losses_host
@@ -298,11 +313,16 @@ class TrainerVAE:
         ind = INDICATOR_CODES[m.cfg.indicator_approx]
         seed, offset = next_philox(self.device) if philox is None else philox
         b = self._buffers(B)
-        # data parallel: the step writes its loss shares behind the gradients so that one all-reduce sums both
-        loss = (self._loss_tail if self.world > 1 else b['loss']) if loss_out is None else loss_out
-        loss_target = loss
-        if self.world > 1:
-            loss = self._loss_tail
+        n = self.flat_p.numel()
+        # where this step's gradients and its [loss, mse, kl] shares go
+        if self.peer is not None:  # symmetric double buffer, alternating with the step parity
+            gbuf = self.peer.grads(self.opt_step & 1)
+            self.flat_g, step_loss = gbuf[:n], gbuf[n:n + 4]
+        elif self.world > 1:  # NCCL: the statistics ride behind the gradients in one all-reduce
+            gbuf, step_loss = self._flat_g_ext, self._flat_g_ext[n:n + 4]
+        else:
+            gbuf, step_loss = self._flat_g_ext, (b['loss'] if loss_out is None else loss_out)
+        loss = (b['loss'] if loss_out is None else loss_out) if self.world > 1 else step_loss
         s = self._stream_handle if self._stream_handle is not None else _stream()
         chk = _lib.check
         events = None
@@ -315,15 +335,25 @@ class TrainerVAE:
             self.kernel_events.setdefault('sampler_bwd', []).append((evs[2], evs[3]))
         # forward + loss + backward: one call, every kernel enqueued back to back (csrc/lin_step.cu)
         chk(lib.pvae_lin_step_fwd_bwd(
-            _ptr(x2), _ptr(self.flat_p), _ptr(self.flat_g), _ptr(b['ws']), _ptr(loss),
+            _ptr(x2), _ptr(self.flat_p), _ptr(gbuf), _ptr(b['ws']), _ptr(step_loss),
             self.r_max.data_ptr() + 4 * (gstep % self.r_max.numel()), B, Bg, row_offset, K, D,
             int(m.fc_enc.bias is not None), n_exp, temp, beta, ind, int(m.cfg.exc_only), m.exit_logit,
             int(linear_mod.PRECISE), seed, offset, None, events, s))
+        self.opt_step += 1
+        if self.peer is not None:
+            # one kernel: publish / wait for the step token, sum all ranks' gradients over NVLink peer memory in rank
+            # order and apply Adamax (csrc/peer_allreduce.cu)
+            tail = loss if loss.numel() >= 4 else b['loss']  # the kernel stores the summed statistics as one float4
+            chk(lib.pvae_allreduce_adamax(_ptr(self.flat_p), _ptr(self.exp_avg), _ptr(self.exp_inf), n, n + 4,
+                                          self.peer.grad_ptrs[(self.opt_step - 1) & 1], self.peer.flag_ptrs, self.world,
+                                          self.rank, self.opt_step, _ptr(tail), None, lr, self.opt_step, cfg.betas[0],
+                                          cfg.betas[1], cfg.eps, cfg.weight_decay, s))
+            if tail is not loss:
+                loss.copy_(tail[:3])
+            return loss[:3]
         if self.world > 1:
             dp.allreduce_gradients(self._flat_g_ext, None, self.pg)  # gradients already carry 1 / B_global
-            if loss_target is not loss:
-                loss_target.copy_(loss)
-            loss = loss_target
+            loss[:3].copy_(step_loss[:3])
         # clip (main/train_vae.py:365-377) + Adamax (base/adamax.py)
         clip = None
         if cfg.grad_clip is not None:
@@ -331,11 +361,10 @@ class TrainerVAE:
             chk(lib.pvae_grad_norm(_ptr(self.flat_g), self.flat_g.numel(), cfg.grad_clip * (3 if warming else 1),
                                    _ptr(b['nws']), _ptr(b['norm']), s))
             clip = b['norm']
-        self.opt_step += 1
         chk(lib.pvae_adamax_step(_ptr(self.flat_p), _ptr(self.flat_g), _ptr(self.exp_avg), _ptr(self.exp_inf),
                                  self.flat_p.numel(), lr, self.opt_step, cfg.betas[0], cfg.betas[1], cfg.eps,
                                  cfg.weight_decay, _ptr(clip), s))
-        return loss
+        return loss[:3]
 
     def iteration(self, data: torch.Tensor, epoch: int = 0):
         """One epoch over a device-resident dataset (N, 1, H, W), like main/train_vae.py:317-459 with a

@@ -15,7 +15,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def run(world, rank, steps, Bg, K):
+def run(world, rank, steps, Bg, K, dp_mode='auto'):
     from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
     from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
     model = PoissonVAE(ConfigPoisVAE(n_latents=K, prior_clamp=-4, seed=0)).cuda()
@@ -25,7 +25,10 @@ def run(world, rank, steps, Bg, K):
     cfg = ConfigTrainVAE(lr=0.005, epochs=100, batch_size=Bg // world, warmup_portion=0.0, scheduler_type=None,
                          grad_clip=200.0, kl_beta=2.5, kl_anneal_portion=0.0, kl_const_portion=0.0,
                          temp_anneal_portion=0.0, temp_stop=0.3)
-    tr = TrainerVAE(model, cfg)
+    cfg.grad_clip = None if dp_mode == 'peer' else cfg.grad_clip
+    tr = TrainerVAE(model, cfg, dp_mode=dp_mode)
+    if rank == 0 and world > 1:
+        print("gradient exchange:", "peer memory (fused all-reduce + Adamax)" if tr.peer is not None else "NCCL all-reduce")
     g = torch.Generator().manual_seed(4321)
     data = torch.randn(steps, Bg, 256, generator=g)
     losses = []
@@ -45,10 +48,11 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--batch", type=int, default=2048)
     ap.add_argument("--latents", type=int, default=512)
+    ap.add_argument("--dp_mode", default="auto", choices=["auto", "peer", "nccl"])
     a = ap.parse_args()
     if a.mode == "single":
         torch.cuda.set_device(0)
-        p, l = run(1, 0, a.steps, a.batch, a.latents)
+        p, l = run(1, 0, a.steps, a.batch, a.latents, a.dp_mode)
         torch.save({"p": p, "l": l}, a.out)
         print("single-GPU reference saved:", l[:, 0].tolist())
         return
@@ -56,7 +60,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    p, l = run(world, rank, a.steps, a.batch, a.latents)
+    p, l = run(world, rank, a.steps, a.batch, a.latents, a.dp_mode)
     ref = torch.load(a.ref)
     dp_err = ((p - ref["p"]).abs().max() / ref["p"].abs().max()).item()
     l_err = ((l - ref["l"]).abs() / ref["l"].abs()).max().item()
