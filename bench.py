@@ -241,19 +241,11 @@ def run_ours(args):
     # ---- end to end: pinned host batches in, loss out, every step --------------------------------
     # public API: TrainerVAE.fit_host(pinned (n_steps, B, D)) - chunked double-buffered uploads on a side stream,
     # every batch crosses PCIe inside the timed region and every step's loss is copied back to pinned memory
-    def host_steps(first, n):
-        idx = [(first + i) % NB for i in range(n)]
-        return host[idx[0]:idx[0] + n] if idx[-1] - idx[0] == n - 1 else torch.stack([host[j] for j in idx]).pin_memory()
-
-    warm_host = host_steps(0, min(max(W, 1), NB))
-    tr.fit_host(warm_host, 0)
+    tr.fit_host(host, 0, n_steps=max(W, 1))
     restore()
-    timed_host = host_steps(W % NB, K_steps) if K_steps <= NB else None
-    if timed_host is None:  # more steps than distinct batches: cycle through the 64 pinned batches
-        timed_host = host.repeat((K_steps + NB - 1) // NB, 1, 1)[:K_steps].pin_memory()
     barrier()
     t0 = time.perf_counter()
-    loss_host = tr.fit_host(timed_host, W)
+    loss_host = tr.fit_host(host, W, n_steps=K_steps, start=W % NB)
     t_enq = time.perf_counter() - t0  # host-side enqueue time (the GPU may still be working)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)

@@ -214,13 +214,15 @@ class TrainerVAE:
         return out
 
     def fit_host(self, batches_host: torch.Tensor, first_gstep: int = 0, chunk: int = 8, losses_host: torch.Tensor = None,
-                 direct: bool = None):
+                 direct: bool = None, n_steps: int = None, start: int = 0):
         """Train on `batches_host`, a pinned host tensor (n_steps, B, D): the public entry point for data that lives
         in host memory.  Batches are uploaded `chunk` at a time on a side stream into two alternating device
         buffers (one large DMA amortises the per-copy latency that dominates 4 MiB transfers) while the previous
         chunk trains; every step's [loss, mse, kl] is copied back to pinned memory asynchronously.
+        `n_steps` / `start`: train n_steps steps cycling through the pool, step i on batch (start + i) % len(pool).
         Returns the pinned (n_steps, 3) tensor of results (valid after torch.cuda.synchronize())."""
-        n_steps = batches_host.shape[0]
+        pool = batches_host.shape[0]
+        n_steps = pool if n_steps is None else n_steps
         if losses_host is None:  # pinned allocations cost milliseconds: keep one and grow it when needed
             if getattr(self, "_losses_host", None) is None or self._losses_host.shape[0] < n_steps:
                 self._losses_host = torch.empty(max(n_steps, 1024), 3).pin_memory()
@@ -249,7 +251,8 @@ class TrainerVAE:
         # each upload is hidden behind the (doubling) compute of the chunk before it
         bounds, lo, size = [], 0, 1
         while lo < n_steps:
-            hi = min(lo + size, n_steps)
+            first = (start + lo) % pool
+            hi = min(lo + size, n_steps, lo + (pool - first))  # a chunk is one contiguous slice of the pool
             bounds.append((lo, hi))
             lo, size = hi, min(2 * size, chunk)
 
@@ -260,7 +263,8 @@ class TrainerVAE:
             slot = c % 2
             cs.wait_event(self._chunk_free[slot])
             with torch.cuda.stream(cs):
-                self._chunk_bufs[slot][:hi - lo].copy_(batches_host[lo:hi], non_blocking=True)
+                first = (start + lo) % pool
+                self._chunk_bufs[slot][:hi - lo].copy_(batches_host[first:first + hi - lo], non_blocking=True)
                 self._chunk_ready[slot].record(cs)
 
         upload(0)

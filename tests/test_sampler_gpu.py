@@ -353,3 +353,37 @@ def test_error_paths(lib):
     z = torch.ones(4, 8, device="cuda")
     assert lib.pvae_rsample_fwd(P(t), P(z), None, None, 4, 8, 0, 0, 1.0, 0, -1.0, 0.0, 1, 0, None, stream()) == 0
     assert z.abs().sum().item() == 0
+
+
+@pytest.mark.parametrize("cfg", ["config4_conv+b|lin_CIFAR16", "config5_conv+b|conv+b_MNIST"])
+def test_baseline_configs_4_and_5_sampler_path(lib, cfg):
+    """BASELINE configs 4-5 differ from the lin|lin ones, on this path, by the encoder bias (`+b`), the
+    temperature-annealed schedule and the hard-count evaluation (temp = 0).  The conv stacks themselves are not
+    built here; their output enters the sampler exactly like fc_enc(x): K = 512 pre-activations
+    per sample plus the fc_enc bias.  Batch 100 is the reference's MNIST default (main/config_vae.py:443-450)."""
+    mnist = "MNIST" in cfg
+    rng = np.random.default_rng(45 if mnist else 44)
+    B, K = (100, 512)
+    n_exp, seed = po.compute_n_exp(20.0), 5
+    h = dev(rng.normal(0.0, 1.5, size=(B, K)).astype(np.float32))
+    b_enc = dev(rng.normal(0.0, 0.5, size=K).astype(np.float32))
+    log_r = dev(rng.uniform(-6, -2 if mnist else -4, size=K).astype(np.float32))  # prior_clamp -2 / -4
+    temps = po.temp_anneal_linear(40, 1.0, 0.05, 0.5)[[0, 10, 19, 39]]  # base/utils_model.py:6-14
+    hb = (h + b_enc[None]).cpu().numpy()
+    for step, temp in enumerate(temps):
+        offset = 4 * step
+        out = fused_fwd(lib, h, log_r, b_enc, n_exp, float(temp), "sigmoid", False, seed, offset)
+        _, E = draws(lib, B, K, n_exp, seed, offset)
+        e, r = E.cpu().numpy(), out["rate"].cpu().numpy()
+        log_dr, u, lam, rate = po.infer(hb, log_r.cpu().numpy())
+        assert_rel(r, rate, what=f"rate t={temp}")
+        assert_rel(out["z"].cpu().numpy(), po.rsample(e, r, float(temp), "sigmoid"), what=f"z t={temp}")
+        assert_rel(out["kl_rowsum"].cpu().numpy(), po.loss_kl(log_r.cpu().numpy(), log_dr).sum(1), what="kl")
+        want_dz = po.rsample_grad_log_rate(e.astype(np.float64), r.astype(np.float64), float(temp), "sigmoid")
+        got_dz = out["dz"].cpu().numpy() / float(temp) * (r - po.F32_EPS) / r
+        assert_rel(got_dz, want_dz, what=f"dz/dlambda t={temp}")
+    # evaluation: hard counts on the same chain, bit-exact against the oracle and torch's CUDA cumsum
+    out = fused_fwd(lib, h, log_r, b_enc, n_exp, 0.0, "sigmoid", False, seed, 400)
+    U, E = draws(lib, B, K, n_exp, seed, 400)
+    assert np.array_equal(out["z"].cpu().numpy(), po.hard_count(E.cpu().numpy(), out["rate"].cpu().numpy()))
+    assert torch.equal(out["z"], (torch.cumsum(-torch.log(U) / out["rate"], 0) <= 1).sum(0).float())
