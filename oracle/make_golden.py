@@ -121,6 +121,31 @@ def gen_vae(ref):
         np.savez_compressed(os.path.join(OUT, f"vae_step_{c['tag']}.npz"), **rec)
 
 
+def gen_exact(ref):
+    """method='exact' (main/vae.py:74-93, main/train_vae.py:703-705): closed-form reconstruction loss, no sampling."""
+    cfg_vae, cfg_tr = ref.cfg.default_configs("vH16", "poisson", "lin|lin")
+    cfg_vae.update(n_latents=64, seed=6)
+    model = ref.vae.PoissonVAE(ref.cfg.ConfigPoisVAE(save=False, **cfg_vae))
+    with torch.no_grad():
+        model.log_rate.add_(4.0)
+    rng = np.random.default_rng(1006)
+    x = rng.standard_normal((16, 1, 16, 16)).astype(np.float32)
+    x = (x - x.mean((1, 2, 3), keepdims=True)) / x.std((1, 2, 3), keepdims=True)
+    p0 = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
+    xt = torch.tensor(x)
+    recon, dist, log_dr = model.loss_recon_exact(xt)
+    kl = model.loss_kl(log_dr)
+    loss = torch.mean(recon + 2.5 * torch.sum(kl, dim=1))
+    loss.backward()
+    rec = dict(x=x, beta=2.5, cfg_seed=6, recon=recon.detach().numpy(), kl=kl.detach().numpy(), loss=loss.detach().numpy(),
+               rate=dist.rate.detach().numpy(), log_dr=log_dr.detach().numpy())
+    for k, v in p0.items():
+        rec["p0_" + k] = v
+    for n, p in model.named_parameters():
+        rec["g_" + n] = p.grad.detach().clone().numpy()
+    np.savez_compressed(os.path.join(OUT, "vae_exact_k64.npz"), **rec)
+
+
 def gen_scalars(ref):
     rec = {}
     rates = np.array([0.05, 0.1, 0.43, 1, 5, 20, 50, 100, 148.4, 200], dtype=np.float64)
@@ -149,6 +174,7 @@ def main():
     gen_sampler(ref)
     gen_hard(ref)
     gen_vae(ref)
+    gen_exact(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

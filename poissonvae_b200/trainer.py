@@ -61,8 +61,8 @@ class ConfigTrainVAE:
                  temp_stop=0.05, lr=0.002, epochs=1200, batch_size=200, warmup_portion=0.01,
                  optimizer='adamax_fast', scheduler_type='cosine', grad_clip=500, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, eta_min=1e-5, **unused):
-        if method != 'mc':
-            raise NotImplementedError("method='exact' is a 'next' row (SURVEY.md 8f)")
+        if method not in ('mc', 'exact'):
+            raise ValueError(method)
         if kl_anneal_cycles != 0:
             raise NotImplementedError("cyclic beta annealing")
         if optimizer not in ('adamax_fast', 'adamax'):
@@ -100,7 +100,7 @@ class TrainerVAE:
         # (it has no gradient clipping: the norm of the summed gradient would need a second pass)
         self.peer = None
         assert dp_mode in ('auto', 'peer', 'nccl')
-        if self.world > 1 and dp_mode != 'nccl' and cfg.grad_clip is None:
+        if self.world > 1 and dp_mode != 'nccl' and cfg.grad_clip is None and cfg.method == 'mc':
             try:
                 self.peer = dp.PeerExchange(self._flat_g_ext.numel(), self.device, process_group)
             except Exception as exc:  # no P2P / symmetric memory on this system
@@ -318,6 +318,8 @@ class TrainerVAE:
         seed, offset = next_philox(self.device) if philox is None else philox
         b = self._buffers(B)
         n = self.flat_p.numel()
+        if cfg.method == 'exact':
+            return self._train_step_exact(x, beta, lr, gstep, b, loss_out)
         # where this step's gradients and its [loss, mse, kl] shares go
         if self.peer is not None:  # symmetric double buffer, alternating with the step parity
             gbuf = self.peer.grads(self.opt_step & 1)
@@ -368,6 +370,42 @@ class TrainerVAE:
         chk(lib.pvae_adamax_step(_ptr(self.flat_p), _ptr(self.flat_g), _ptr(self.exp_avg), _ptr(self.exp_inf),
                                  self.flat_p.numel(), lr, self.opt_step, cfg.betas[0], cfg.betas[1], cfg.eps,
                                  cfg.weight_decay, _ptr(clip), s))
+        return loss[:3]
+
+    def _train_step_exact(self, x, beta, lr, gstep, b, loss_out):
+        """method='exact' (main/train_vae.py:703-705): closed-form reconstruction loss, no sampling.  Not a fused
+        path: the model's own ops (our GEMM / rate / KL kernels under autograd) build the loss, the gradients are
+        gathered into the flat buffer and the usual exchange + clip + Adamax kernels follow."""
+        cfg, m, lib, s = self.cfg, self.model, self.lib, _stream()
+        names = list(self.views)
+        params = dict(m.named_parameters())
+        for k in names:
+            params[k].grad = None
+        recon, dist_, log_dr = m.loss_recon_exact(x.reshape(x.shape[0], *m.shape[1:]))
+        kl = m.loss_kl(log_dr)
+        Bg = x.shape[0] * self.world
+        (torch.sum(recon + beta * torch.sum(kl, dim=1)) / Bg).backward()
+        for k in names:
+            self.gviews[k].copy_(params[k].grad)
+            params[k].grad = None
+        n = self.flat_p.numel()
+        stats = self._flat_g_ext[n:n + 4]
+        stats[0] = (recon.detach().sum() + beta * kl.detach().sum()) / Bg
+        stats[1] = recon.detach().sum() / Bg
+        stats[2] = kl.detach().sum() / Bg
+        if self.world > 1:
+            dp.allreduce_gradients(self._flat_g_ext, None, self.pg)
+        loss = b['loss'] if loss_out is None else loss_out
+        loss[:3].copy_(stats[:3])
+        clip = None
+        if cfg.grad_clip is not None:
+            warming = gstep / self.n_iters < cfg.warmup_portion
+            _lib.check(lib.pvae_grad_norm(_ptr(self._flat_g_ext), n, cfg.grad_clip * (3 if warming else 1), _ptr(b['nws']),
+                                          _ptr(b['norm']), s))
+            clip = b['norm']
+        self.opt_step += 1
+        _lib.check(lib.pvae_adamax_step(_ptr(self.flat_p), _ptr(self._flat_g_ext), _ptr(self.exp_avg), _ptr(self.exp_inf), n,
+                                        lr, self.opt_step, cfg.betas[0], cfg.betas[1], cfg.eps, cfg.weight_decay, _ptr(clip), s))
         return loss[:3]
 
     def iteration(self, data: torch.Tensor, epoch: int = 0):

@@ -124,6 +124,45 @@ class _EncodeSampleFn(torch.autograd.Function):
         return g_h, g_lr.reshape(lr_shape), g_b, None, None, None, None, None, None, None
 
 
+class _InferRateFn(torch.autograd.Function):
+    """(h, log_r[, b_enc]) -> (rate, log_dr) without sampling (method='exact', main/vae.py:74-93 needs only the
+    posterior's mean = variance = rate).  Forward: the fused kernel with zero events.  Backward: the elementwise
+    backward kernel fed dz_acc = rate at temp = 1, for which its chain factor dz_acc / temp * exp(lambda) / rate
+    is d rate / d lambda = exp(lambda), so `g_z` plays the role of d loss / d rate."""
+
+    @staticmethod
+    def forward(ctx, h, log_r, b_enc, exc_only):
+        h = h.contiguous()
+        B, K = h.shape
+        lr = log_r.reshape(-1).contiguous()
+        z = torch.empty_like(h)
+        log_dr = torch.empty_like(h)
+        rate = torch.empty_like(h)
+        with torch.cuda.device(h.device):
+            _lib.check(_lib.load().pvae_sampler_fwd(
+                _ptr(h), _ptr(lr), _ptr(b_enc), _ptr(z), _ptr(log_dr), _ptr(rate), None, None, None, None, B, K, 0, 0,
+                1.0, 0, int(exc_only), -1.0, 0, 0, None, _stream()))
+        ctx.save_for_backward(h, lr, b_enc, rate)
+        ctx.args = (B, K, int(exc_only), log_r.shape)
+        return rate, log_dr
+
+    @staticmethod
+    def backward(ctx, g_rate, g_log_dr):
+        h, lr, b_enc, rate = ctx.saved_tensors
+        B, K, exc_only, lr_shape = ctx.args
+        lib = _lib.load()
+        g_rate = g_rate.contiguous()
+        g_log_dr = None if g_log_dr is None else g_log_dr.contiguous()
+        g_h, g_lr = torch.empty_like(h), torch.empty_like(lr)
+        g_b = None if b_enc is None else torch.empty_like(b_enc)
+        ws = torch.empty(2 * lib.pvae_num_partials(B) * K, device=h.device, dtype=torch.float32)
+        with torch.cuda.device(h.device):
+            _lib.check(lib.pvae_sampler_bwd(
+                _ptr(h), _ptr(lr), _ptr(b_enc), _ptr(g_rate), _ptr(g_log_dr), _ptr(rate), 0.0, _ptr(g_h), _ptr(g_lr),
+                _ptr(g_b), _ptr(ws), 0, B, K, 0, 0, 1.0, 0, exc_only, -1.0, 0, 0, None, _stream()))
+        return g_h, g_lr.reshape(lr_shape), g_b, None
+
+
 class _KLFn(torch.autograd.Function):
     """PoissonVAE.loss_kl main/vae.py:446-450 as one elementwise kernel (+ backward)."""
 
@@ -272,6 +311,19 @@ class PoissonVAE(nn.Module):
 
     def loss_recon(self, y, x):  # main/vae.py:68-72
         return torch.sum((y - x) ** 2, dim=[1, 2, 3])
+
+    def loss_recon_exact(self, x):
+        """main/vae.py:74-93 (method='exact', linear decoder): E_q ||x - z Phi^T||^2 in closed form for a Poisson
+        posterior, mean = variance = rate:  ||x - rate Phi^T||^2 + rate . diag(Phi^T Phi).  No sampling."""
+        _require_cuda_f32(x, "x")
+        h = self.encode_linear(x)
+        rate, log_dr = _InferRateFn.apply(h, self.log_rate, self.fc_enc.bias, self.cfg.exc_only)
+        dist = _PosteriorPoisson(self, h, log_dr, self.temp, self._temp_host, self._n_exp_host, None)
+        dist._rate = rate
+        phi = self.fc_dec.weight
+        gram = phi.pow(2).sum(0)
+        mse = (x.flatten(start_dim=1) - linear(rate, phi)).pow(2).sum(1)
+        return mse + rate @ gram, dist, log_dr
 
     def loss_kl(self, log_dr):  # main/vae.py:446-450
         return _KLFn.apply(log_dr, self.log_rate)

@@ -112,3 +112,23 @@ def test_fit_host_equals_resident_steps():
         results.append((losses.clone(), tr.flat_p.clone()))
     assert torch.equal(results[0][0], results[1][0])
     assert torch.equal(results[0][1], results[1][1])
+
+
+def test_exact_method_step_matches_reference(golden_dir):
+    """One training step with method='exact' reproduces the reference's loss and (through Adamax) its gradients' effect."""
+    g = np.load(os.path.join(golden_dir, "vae_exact_k64.npz"))
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
+    model = PoissonVAE(ConfigPoisVAE(n_latents=64, prior_clamp=-4, seed=int(g["cfg_seed"])))
+    model.load_state_dict({k: torch.tensor(g["p0_" + k]) for k in model.state_dict()})
+    model = model.cuda()
+    cfg = ConfigTrainVAE(method='exact', lr=0.005, epochs=1, batch_size=16, warmup_portion=0.0, scheduler_type=None,
+                         grad_clip=None, kl_beta=float(g["beta"]), kl_anneal_portion=0.0, kl_const_portion=0.0,
+                         temp_anneal_portion=0.0)
+    tr = TrainerVAE(model, cfg)
+    p0 = tr.flat_p.clone()
+    loss = tr.train_step(torch.tensor(g["x"], device="cuda"), 0)
+    assert_rel(loss[0].item(), float(g["loss"]), rtol=2e-5, what="loss")
+    for name in ("log_rate", "fc_enc.weight", "fc_dec.weight"):
+        assert_rel(tr.gviews[name].cpu().numpy(), g["g_" + name], rtol=2e-5, what="grad " + name)
+    assert not torch.equal(p0, tr.flat_p)

@@ -105,3 +105,22 @@ def test_vae_eval_and_prior_sampling():
     assert (s >= 0).all()
     model.update_n(20.0)
     assert int(model.n_exp) == 42
+
+
+def test_exact_method_matches_reference(golden_dir):
+    """method='exact' (closed-form reconstruction loss, main/vae.py:74-93) against the reference's values and autograd."""
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
+    g = np.load(os.path.join(golden_dir, "vae_exact_k64.npz"))
+    model = PoissonVAE(ConfigPoisVAE(n_latents=64, prior_clamp=-4, seed=int(g["cfg_seed"])))
+    model.load_state_dict({k: torch.tensor(g["p0_" + k]) for k in model.state_dict()})
+    model = model.cuda()
+    x = torch.tensor(g["x"], device="cuda")
+    recon, dist, log_dr = model.loss_recon_exact(x)
+    kl = model.loss_kl(log_dr)
+    loss = torch.mean(recon + float(g["beta"]) * torch.sum(kl, dim=1))
+    loss.backward()
+    for name, got in (("recon", recon), ("kl", kl), ("loss", loss), ("rate", dist.rate), ("log_dr", log_dr)):
+        assert_rel(got.detach().cpu().numpy(), g[name], rtol=2e-5, what=name)
+    assert dist.mean is dist.rate and dist.variance is dist.rate
+    for n, p in model.named_parameters():
+        assert_rel(p.grad.cpu().numpy(), g["g_" + n], rtol=2e-5, what="grad " + n)
