@@ -372,6 +372,39 @@ class TrainerVAE:
                                  cfg.weight_decay, _ptr(clip), s))
         return loss[:3]
 
+    @torch.inference_mode()
+    def validate(self, data: torch.Tensor, temp: float = 0.0, batch_size: int = None, full_data: bool = False):
+        """Evaluation pass, main/train_vae.py:461-470, 530-601: hard counts (temp = 0, base/helper.py:15-17) ->
+        decode -> r2 / mse / kl per sample.  Results are gathered on the device and cross to the host once, not
+        eight times per batch.  Returns (data, loss, etc) dicts of numpy arrays with the reference's keys."""
+        m = self.model
+        bs = batch_size or self.cfg.batch_size
+        acc = {k: [] for k in ('x', 'y', 'z', 'r2', 'mse', 'kl', 'kl_diag', 'log_dr', 'rate')}
+        eps = torch.finfo(torch.float32).eps
+        for lo in range(0, data.shape[0], bs):
+            x = data[lo:lo + bs].to(self.device)
+            dist_, log_dr, z, y = m.xtract_ftr(x, temp)
+            kl = m.loss_kl(log_dr)
+            true, pred = x.flatten(start_dim=1), y.flatten(start_dim=1)
+            ss_res = (true - pred).pow(2).sum(-1)  # compute_r2, base/utils_model.py:71-80
+            ss_tot = (true - true.mean(dim=-1, keepdim=True)).pow(2).sum(-1)
+            acc['r2'].append(1.0 - ss_res / (ss_tot + eps))
+            acc['mse'].append(m.loss_recon(y, x))
+            acc['kl'].append(kl.sum(1))
+            acc['kl_diag'].append(kl.mean(0, keepdim=True))
+            acc['z'].append(z)
+            acc['log_dr'].append(log_dr)
+            acc['rate'].append(dist_.rate)
+            if full_data:
+                acc['x'].append(x)
+                acc['y'].append(y)
+        out = {k: torch.cat(v).cpu().numpy() if v else None for k, v in acc.items()}
+        data_out = {'x': out['x'], 'y': out['y'], 'z': out['z'], 'g': None}
+        loss = {'r2': out['r2'], 'mse': out['mse'], 'kl': out['kl'], 'elbo': out['mse'] + out['kl'],
+                'kl_diag': out['kl_diag'].mean(0)}
+        etc = {'log_dr': out['log_dr'], 'r*dr': out['rate']}
+        return data_out, loss, etc
+
     def _train_step_exact(self, x, beta, lr, gstep, b, loss_out):
         """method='exact' (main/train_vae.py:703-705): closed-form reconstruction loss, no sampling.  Not a fused
         path: the model's own ops (our GEMM / rate / KL kernels under autograd) build the loss, the gradients are

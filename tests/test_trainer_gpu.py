@@ -132,3 +132,28 @@ def test_exact_method_step_matches_reference(golden_dir):
     for name in ("log_rate", "fc_enc.weight", "fc_dec.weight"):
         assert_rel(tr.gviews[name].cpu().numpy(), g["g_" + name], rtol=2e-5, what="grad " + name)
     assert not torch.equal(p0, tr.flat_p)
+
+
+def test_validate_pass_hard_counts():
+    """Evaluation (main/train_vae.py:461-601): hard counts at temp = 0, r2 / mse / kl per sample, one host transfer."""
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
+    model = PoissonVAE(ConfigPoisVAE(n_latents=128, prior_clamp=-4, seed=2)).cuda()
+    with torch.no_grad():
+        model.log_rate.add_(3.5)
+    model.update_n(20.0)
+    tr = TrainerVAE(model, ConfigTrainVAE(batch_size=64, epochs=1, grad_clip=None))
+    data = torch.randn(200, 1, 16, 16, device="cuda")
+    d, loss, etc = tr.validate(data, full_data=True)
+    assert d['z'].shape == (200, 128) and np.array_equal(d['z'], np.round(d['z'])) and d['z'].max() >= 1
+    assert d['x'].shape == d['y'].shape == (200, 1, 16, 16)
+    x, y = d['x'].reshape(200, -1).astype(np.float64), d['y'].reshape(200, -1).astype(np.float64)
+    mse = ((y - x) ** 2).sum(1)
+    assert_rel(loss['mse'], mse, what="mse")
+    r2 = 1 - mse / (((x - x.mean(1, keepdims=True)) ** 2).sum(1) + np.finfo(np.float32).eps)
+    assert_rel(loss['r2'], r2, what="r2")
+    assert_rel(loss['elbo'], loss['mse'] + loss['kl'], rtol=1e-6, what="elbo")
+    assert loss['kl_diag'].shape == (128,) and etc['r*dr'].shape == (200, 128) and etc['log_dr'].shape == (200, 128)
+    # the decoder sees the counts: y = z W_dec^T
+    w = model.fc_dec.weight.detach().cpu().numpy().astype(np.float64)
+    assert_rel(y, d['z'].astype(np.float64) @ w.T, rtol=2e-5, what="decode(hard counts)")
