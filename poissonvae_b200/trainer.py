@@ -99,6 +99,7 @@ class TrainerVAE:
         # 'nccl' = NCCL all-reduce followed by the Adamax kernel; 'auto' prefers 'peer' when it can be set up
         # (it has no gradient clipping: the norm of the summed gradient would need a second pass)
         self.peer = None
+        self._peer_token = 0
         assert dp_mode in ('auto', 'peer', 'nccl')
         if self.world > 1 and dp_mode != 'nccl' and cfg.grad_clip is None and cfg.method == 'mc':
             try:
@@ -321,8 +322,9 @@ class TrainerVAE:
         if cfg.method == 'exact':
             return self._train_step_exact(x, beta, lr, gstep, b, loss_out)
         # where this step's gradients and its [loss, mse, kl] shares go
-        if self.peer is not None:  # symmetric double buffer, alternating with the step parity
-            gbuf = self.peer.grads(self.opt_step & 1)
+        if self.peer is not None:  # symmetric double buffer, alternating with the exchange token's parity
+            self._peer_token += 1  # strictly increasing for the life of the exchange (never rewound with opt_step)
+            gbuf = self.peer.grads(self._peer_token & 1)
             self.flat_g, step_loss = gbuf[:n], gbuf[n:n + 4]
         elif self.world > 1:  # NCCL: the statistics ride behind the gradients in one all-reduce
             gbuf, step_loss = self._flat_g_ext, self._flat_g_ext[n:n + 4]
@@ -351,8 +353,8 @@ class TrainerVAE:
             # order and apply Adamax (csrc/peer_allreduce.cu)
             tail = loss if loss.numel() >= 4 else b['loss']  # the kernel stores the summed statistics as one float4
             chk(lib.pvae_allreduce_adamax(_ptr(self.flat_p), _ptr(self.exp_avg), _ptr(self.exp_inf), n, n + 4,
-                                          self.peer.grad_ptrs[(self.opt_step - 1) & 1], self.peer.flag_ptrs, self.world,
-                                          self.rank, self.opt_step, _ptr(tail), None, lr, self.opt_step, cfg.betas[0],
+                                          self.peer.grad_ptrs[self._peer_token & 1], self.peer.flag_ptrs, self.world,
+                                          self.rank, self._peer_token, _ptr(tail), None, lr, self.opt_step, cfg.betas[0],
                                           cfg.betas[1], cfg.eps, cfg.weight_decay, s))
             if tail is not loss:
                 loss.copy_(tail[:3])
