@@ -35,6 +35,8 @@ def run(world, rank, steps, Bg, K, dp_mode='auto'):
     for i in range(steps):
         lo = rank * (Bg // world)
         x = data[i, lo:lo + Bg // world].cuda()
+        if world > 1 and (i + rank) % 2 == 1:
+            torch.cuda._sleep(3_000_000)  # ~1.5 ms: ranks reach the exchange at very different times, alternately
         losses.append(tr.train_step(x, i, philox=(77, 4 * i)).clone())
     torch.cuda.synchronize()
     return tr.flat_p.cpu(), torch.stack(losses).cpu()
@@ -45,7 +47,7 @@ def main():
     ap.add_argument("--mode", required=True, choices=["single", "dp"])
     ap.add_argument("--out", default="/tmp/dp_ref.pt")
     ap.add_argument("--ref", default="/tmp/dp_ref.pt")
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--batch", type=int, default=2048)
     ap.add_argument("--latents", type=int, default=512)
     ap.add_argument("--dp_mode", default="auto", choices=["auto", "peer", "nccl"])
