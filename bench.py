@@ -55,7 +55,9 @@ def workload(args):
     return {"workload": f"poisson lin|lin K={args.latents} beta={args.beta:g} batch {args.batch}/GPU n_exp={args.n_exp} "
                         f"temp={args.temp:g} fp32, fwd+loss+bwd+Adamax, exit={args.exit}",
             "batch_per_gpu": args.batch, "n_latents": args.latents, "n_exp": args.n_exp, "temp": args.temp,
-            "input": "16x16 z-scored N(0,1) patches, seed 1234; weights N(0,0.05^2), log_rate U(-6,-4), cfg.seed 0"}
+            "input": "16x16 z-scored N(0,1) patches, seed 1234; weights N(0,0.05^2), log_rate U(-6,-4), cfg.seed 0",
+            "gemm": "tf32 single pass" if getattr(args, "tf32", False) else "3xTF32 (fp32-grade, tcgen05)",
+            "schedule": "reference vH16 lr warm-up (lr .005, 1 % of 78000 iterations), beta and temp pinned"}
 
 
 def synthetic_patches(n, seed):

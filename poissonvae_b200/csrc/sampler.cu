@@ -33,7 +33,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kColsPerPass = 4 * kThreads;  // latents of one row a block covers per pass
 constexpr int kMaxRows = 3;                 // rows per block tile
 constexpr int kSlots = kMaxRows * kThreads; // parked-quad table: one slot per (row, thread)
-constexpr int kSlotWords = 16;              // rate[4], t[4], acc[4], acc2[4]
+constexpr int kSlotWords = 16;              // rate[4], t[4], acc[4], acc2[4] (one shared-memory plane per word)
 
 // kFwdSoft: z only.  kFwdBoth: z and dz_acc = sum_n f'(l_n) t_n in one walk of the chain (training forward).
 // kBwd: backward that recomputes the chain from the Philox counters.  kBwdSaved: backward from a stored dz_acc.
