@@ -48,6 +48,9 @@ def parse():
                     help="N > 1: gradient exchange over NVLink peer memory fused with Adamax, or NCCL all-reduce")
     ap.add_argument("--no_overlap", action="store_true", help="keep the whole step on one stream (A/B)")
     ap.add_argument("--tf32", action="store_true", help="single-pass TF32 GEMMs instead of 3xTF32 (A/B)")
+    ap.add_argument("--ref_device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: 'cuda' times the same torch port of the reference's step with its "
+                         "tensors on cuda:0 at the full batch (the reference's own CUDA path; north_star's denominator)")
     return ap.parse_args()
 
 
@@ -86,6 +89,28 @@ def cpu_reference_steps(args, steps, warmup):
     return args.cpu_rows * steps / dt, cores, dt / steps
 
 
+def cuda_reference_steps(args, steps, warmup):
+    """The reference's step as it runs on its own CUDA path: the same torch op sequence (oracle/ref_port.py) with the
+    tensors on cuda:0, full batch, materialised (n_exp, B, K) tensors, autograd backward, eager Adamax."""
+    import torch
+    from oracle import ref_port
+    dev = torch.device("cuda", 0)
+    params = {k: v.detach().to(dev).requires_grad_() for k, v in ref_port.make_params(K=args.latents, D=256, seed=0).items()}
+    optim = ref_port.Adamax(params, lr=0.005)
+    x = synthetic_patches(args.batch, 1234).view(-1, 1, 16, 16).to(dev)
+    for _ in range(warmup):
+        ref_port.train_step(params, optim, x, args.n_exp, args.temp, args.beta)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        ref_port.train_step(params, optim, x, args.n_exp, args.temp, args.beta)
+    e1.record()
+    torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) * 1e-3
+    return args.batch * steps / dt, dt / steps, torch.cuda.max_memory_allocated() / 2**30
+
+
 def run_reference(args):
     """Reference arm: the reference's own step on the host cores (its torch-CPU port, all threads).  Exactly K timed
     steps after min(W, 3) warm-up steps; every step is a bounded sample of the workload (`rows` of the batch), sized
@@ -94,6 +119,14 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
+    if args.ref_device == "cuda":
+        v, sps, gib = cuda_reference_steps(args, steps, warmup)
+        line = {"impl": "reference", "device": "cuda", "metric": METRIC, "value": round(v, 1), "unit": UNIT, "n_gpus": 1,
+                "steps": steps, "warmup": warmup, "ms_per_step": round(sps * 1e3, 3), "higher_is_better": True,
+                "dtype": "f32", "data": "synthetic", "config": workload(args), "peak_mem_gib": round(gib, 2),
+                "note": "torch port of the reference step (bit-identical to it on CPU) run eagerly on cuda:0, full batch"}
+        print(json.dumps(line), flush=True)
+        return
     # ~3.3 ms per row and step on 16 cores at n_exp = 263 (measured); aim at ~60 s of CPU work
     rows = int(60.0 / (0.0033 * (steps + warmup) * max(args.n_exp, 1) / 263.0))
     args.cpu_rows = max(8, min(args.cpu_rows, rows - rows % 4))
