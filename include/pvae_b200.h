@@ -191,6 +191,75 @@ int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, flo
                           float temp, float beta, int indicator, int exc_only, float exit_logit, int precise,
                           uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* const* events, void* stream);
 
+/* ---- conv encoder / decoder ----------------------------------------------
+ * Activations are NHWC fp32.  Replaces Conv2D.forward base/common.py:313-323 (F.conv2d on the weight-normalised
+ * filter, `_normalize` :426-431) and the data / weight gradients autograd derives from it, as used by ConvLayer
+ * :195-242, FactorizedReduce / StrideReduce :75-126, Cell :145-192, ResConvPool main/vae.py:682-706.
+ *
+ * pvae_conv_weight_prep: weight (Co, Ci, KH, KW) [torch layout] + lognorm (Co, NULL = no normalisation) ->
+ *   w_fwd [co][tap][ci] and (optional) w_dgrad [ci][tap][co], tap = kh * KW + kw.  groups > 1 (= ntaps): the four
+ *   1x1 stride-2 filters of FactorizedReduce stored back to back as (Co, Ci); output channel co only sees tap
+ *   co / (Co / groups) of a 2x2 window.
+ * pvae_conv_weight_grad: g_wp (ntaps * Ci, Co) [rows (tap, ci), as written by pvae_conv_wgrad] -> g_weight in the
+ *   torch layout and g_lognorm, through the normalisation.
+ * pvae_conv_igemm: out[n, oh*out_step+out_off_h, ow*out_step+out_off_w, :] = epilogue(sum_taps in[n, oh*stride+dy,
+ *   ow*stride+dx, :] . w_packed[:, widx, :] + bias) over the (OH, OW) grid; `out` is an (NI, OHf, OWf, Co) tensor.
+ *   Out-of-range input coordinates read zeros (padding).  Epilogue, in this order, each optional: += add_pre,
+ *   *= silu'(dsilu_src), += add_post (all shaped like `out`); out_act receives silu(out).  A forward convolution is
+ *   one call; the data gradient of a stride-1 convolution is one call on g_out with w_dgrad and mirrored offsets;
+ *   of a stride-2 convolution one call per parity class of the input grid (out_step 2, the class's taps).
+ *   wtaps = number of taps in w_packed's row.  Ci, Co multiples of 32.  precise: 3xTF32 (1) or single-pass TF32 (0).
+ * pvae_conv_wgrad: g_wp[(widx, ci), co] = sum_{n, oh, ow} in[n, oh*stride+dy, ow*stride+dx, ci] g_out[n, oh, ow, co];
+ *   ws: pvae_conv_wgrad_ws_floats(Ci, Co, ntaps) floats (split-K partials, fixed-order reduction). */
+int pvae_conv_weight_prep(const float* weight, const float* lognorm, float* w_fwd, float* w_dgrad, int Co, int Ci, int ntaps,
+                          int groups, void* stream);
+int pvae_conv_weight_grad(const float* g_wp, const float* weight, const float* lognorm, float* g_weight, float* g_lognorm,
+                          int Co, int Ci, int ntaps, int groups, void* stream);
+int pvae_conv_igemm(const float* in, const float* w_packed, float* out, float* out_act, const float* bias,
+                    const float* add_pre, const float* dsilu_src, const float* add_post, int NI, int IH, int IW, int Ci,
+                    int Co, int OH, int OW, int OHf, int OWf, int out_step, int out_off_h, int out_off_w, int stride,
+                    int ntaps, const int* tap_dy, const int* tap_dx, const int* tap_widx, int wtaps, int precise,
+                    void* stream);
+int64_t pvae_conv_wgrad_ws_floats(int Ci, int Co, int ntaps);
+int pvae_conv_wgrad(const float* in, const float* g_out, float* g_wp, float* ws, int NI, int IH, int IW, int Ci, int Co,
+                    int OH, int OW, int stride, int ntaps, const int* tap_dy, const int* tap_dx, const int* tap_widx,
+                    int precise, void* stream);
+
+/* Memory-bound pieces around the convolutions (csrc/conv_misc.cu).  All reductions are two fixed-order stages;
+ * `ws` arguments need pvae_reduce_ws_floats(number of outputs) floats.
+ *   pvae_stem_fwd / pvae_stem_wgrad: 3x3 weight-normalised convolution of the single-channel input, main/vae.py:211-218
+ *     (pad 1 or 0); g_wpb (10, Co): rows 0..8 = tap-major gradient of the normalised filter (feed to
+ *     pvae_conv_weight_grad with Ci = 1), row 9 = bias gradient.
+ *   pvae_se_fwd / pvae_se_bwd: SELayer base/common.py:129-142 fused with the cell's residual, Cell.forward :187-192:
+ *     y = skip + eps_res * c * sigmoid(W2 relu(W1 mean_hw(c) + b1) + b2); saves pool (N,C), hid (N,hd), gate (N,C);
+ *     backward returns g_c and the per-image pre-activation gradients d2 (N,C), d1 (N,hd) (g_skip = g_y).
+ *   pvae_avgpool_fwd, pvae_pool_silu_bwd: ResConvPool main/vae.py:682-706 skip path and its backward fused with silu'.
+ *   pvae_bias_act, pvae_relu_bwd: bias + ReLU + dropout (Philox mask) of ResDenseLayer main/vae.py:657-679.
+ *   pvae_layernorm_fwd / bwd: nn.LayerNorm over the last dimension of a + b. */
+int64_t pvae_reduce_ws_floats(int64_t n_out);
+int pvae_silu_fwd(const float* x, float* out, int64_t n, void* stream);
+int pvae_add(const float* a, const float* b, float* out, int64_t n, void* stream);
+int pvae_stem_fwd(const float* x, const float* weight, const float* lognorm, const float* bias, float* out, float* out_act,
+                  int N, int IH, int IW, int Co, int pad, void* stream);
+int pvae_stem_wgrad(const float* x, const float* g_out, float* g_wpb, float* ws, int N, int IH, int IW, int Co, int pad,
+                    void* stream);
+int pvae_colsum(const float* x, float* out, float* ws, int64_t R, int C, void* stream);
+int pvae_small_tn(const float* a, const float* b, float* out, float* ws, int64_t R, int Ca, int Cb, void* stream);
+int pvae_se_fwd(const float* c, const float* skip, const float* W1, const float* b1, const float* W2, const float* b2,
+                float eps_res, float* y, float* y_act, float* pool, float* hid, float* gate, int N, int HW, int C, int hd,
+                void* stream);
+int pvae_se_bwd(const float* g_y, const float* c, const float* gate, const float* hid, const float* W1, const float* W2,
+                float eps_res, float* g_c, float* d2, float* d1, int N, int HW, int C, int hd, void* stream);
+int pvae_avgpool_fwd(const float* x, float* pool, int N, int HW, int C, void* stream);
+int pvae_pool_silu_bwd(const float* g_a, const float* x, const float* g_pool, float* g_x, int N, int HW, int C, void* stream);
+int pvae_bias_act(float* y, const float* bias, const float* add, int64_t R, int C, int relu, float drop_p, uint64_t seed,
+                  uint64_t offset, void* stream);
+int pvae_relu_bwd(float* g, const float* y_saved, int64_t n, float drop_p, void* stream);
+int pvae_layernorm_fwd(const float* a, const float* b, const float* gamma, const float* beta, float* out, float* xhat,
+                       float* rstd, int64_t R, int C, float eps, void* stream);
+int pvae_layernorm_bwd(const float* g, const float* xhat, const float* rstd, const float* gamma, float* g_s,
+                       float* g_gamma_beta, float* ws, int64_t R, int C, void* stream);
+
 /* Tuning knob (process-wide): number of events each quad of latents walks thread-per-quad before a
  * still-unfinished chain is handed to a whole warp (32 events per step).  Default 8.  Results do
  * not depend on the launch geometry, but the float summation order of a chain depends on this value. */

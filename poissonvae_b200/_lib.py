@@ -11,7 +11,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpvae_b200.so")
-SOURCES = ["capi.cu", "sampler.cu", "step.cu", "gemm_tc.cu", "lin_step.cu", "peer_allreduce.cu"]
+SOURCES = ["capi.cu", "sampler.cu", "step.cu", "gemm_tc.cu", "lin_step.cu", "peer_allreduce.cu", "conv_tc.cu",
+           "conv_misc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -63,6 +64,26 @@ _SIGNATURES = {
     "pvae_set_step_overlap": (_i, [_i]),
     "pvae_lin_step_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i,
                                    _u64, _u64, _p, _p, _p]),
+    "pvae_conv_weight_prep": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "pvae_conv_weight_grad": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "pvae_conv_igemm": (_i, [_p] * 8 + [_i] * 14 + [_p, _p, _p, _i, _i, _p]),
+    "pvae_conv_wgrad_ws_floats": (_i64, [_i, _i, _i]),
+    "pvae_conv_wgrad": (_i, [_p, _p, _p, _p] + [_i] * 9 + [_p, _p, _p, _i, _p]),
+    "pvae_reduce_ws_floats": (_i64, [_i64]),
+    "pvae_silu_fwd": (_i, [_p, _p, _i64, _p]),
+    "pvae_add": (_i, [_p, _p, _p, _i64, _p]),
+    "pvae_stem_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "pvae_stem_wgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "pvae_colsum": (_i, [_p, _p, _p, _i64, _i, _p]),
+    "pvae_small_tn": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p]),
+    "pvae_se_fwd": (_i, [_p] * 6 + [_f] + [_p] * 5 + [_i, _i, _i, _i, _p]),
+    "pvae_se_bwd": (_i, [_p] * 6 + [_f] + [_p] * 3 + [_i, _i, _i, _i, _p]),
+    "pvae_avgpool_fwd": (_i, [_p, _p, _i, _i, _i, _p]),
+    "pvae_pool_silu_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "pvae_bias_act": (_i, [_p, _p, _p, _i64, _i, _i, _f, _u64, _u64, _p]),
+    "pvae_relu_bwd": (_i, [_p, _p, _i64, _f, _p]),
+    "pvae_layernorm_fwd": (_i, [_p] * 7 + [_i64, _i, _f, _p]),
+    "pvae_layernorm_bwd": (_i, [_p] * 7 + [_i64, _i, _p]),
     "pvae_set_phase_a_events": (_i, [_i]),
     "pvae_set_absorb_exit": (_i, [_i]),
     "pvae_set_rows_per_block": (_i, [_i]),

@@ -1,0 +1,539 @@
+"""Host-side mirror of the reference's conv encoder / decoder blocks:
+`Conv2D`, `ConvLayer`, `SELayer`, `FactorizedReduce`, `StrideReduce`, `Cell` (base/common.py:75-340),
+`ResConvPool`, `ResDenseLayer`, `_build_conv_enc` (main/vae.py:657-756) and the stem (main/vae.py:211-218).
+
+Same module tree, constructor order (-> same initial parameters under the same seed) and state_dict keys
+as the reference.  Every block is ONE autograd Function whose forward and hand-derived backward enqueue the
+sm_100a kernels of csrc/conv_tc.cu (implicit-GEMM convolutions on tcgen05) and csrc/conv_misc.cu through the
+C-ABI; activations are NHWC fp32 between blocks.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+from torch import nn
+
+from . import _lib
+from .linear import gemm_nn, gemm_nt, gemm_tn
+from .rng import next_philox
+
+MULT = 2
+PRECISE = True  # 3xTF32 operand splitting in the convolutions (fp32-grade); False = single-pass TF32
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ints(v):
+    return (C.c_int * max(1, len(v)))(*v)
+
+
+_ws = {}
+
+
+def _workspace(dev, floats: int) -> torch.Tensor:
+    """Scratch for the fixed-order reductions (stream-ordered reuse: every consumer runs before the next producer)."""
+    t = _ws.get(dev)
+    if t is None or t.numel() < floats:
+        t = _ws[dev] = torch.empty(max(floats, 1 << 20), device=dev, dtype=torch.float32)
+    return t
+
+
+# ------------------------------------------------------------------------------------------------------
+# thin wrappers over the C entry points
+# ------------------------------------------------------------------------------------------------------
+def out_size(i: int, k: int, stride: int, pad: int) -> int:
+    return (i + 2 * pad - k) // stride + 1
+
+
+def weight_prep(weight, lognorm, ntaps: int, groups: int = 1, need_dgrad: bool = True):
+    """-> (w_fwd [co][tap][ci], w_dgrad [ci][tap][co]) of the weight-normalised filter, base/common.py:426-431."""
+    co = weight.shape[0]
+    ci = weight.shape[1]
+    w_fwd = torch.empty(co, ntaps * ci, device=weight.device, dtype=torch.float32)
+    w_dg = torch.empty(ci, ntaps * co, device=weight.device, dtype=torch.float32) if need_dgrad else None
+    with torch.cuda.device(weight.device):
+        _lib.check(_lib.load().pvae_conv_weight_prep(_p(weight), _p(lognorm), _p(w_fwd), _p(w_dg), co, ci, ntaps, groups, _s()))
+    return w_fwd, w_dg
+
+
+def weight_grad(g_wp, weight, lognorm, ntaps: int, groups: int = 1):
+    co, ci = weight.shape[0], weight.shape[1]
+    g_w = torch.empty_like(weight)
+    g_ln = torch.empty_like(lognorm) if lognorm is not None else None
+    with torch.cuda.device(weight.device):
+        _lib.check(_lib.load().pvae_conv_weight_grad(_p(g_wp), _p(weight), _p(lognorm), _p(g_w), _p(g_ln), co, ci, ntaps, groups,
+                                                     _s()))
+    return g_w, g_ln
+
+
+def _igemm(inp, w, out, out_act, bias, add_pre, dsilu_src, add_post, oh, ow, out_step, off_h, off_w, stride, taps, wtaps):
+    n, ih, iw, ci = inp.shape
+    _, ohf, owf, co = out.shape
+    dy, dx, wi = _ints([t[0] for t in taps]), _ints([t[1] for t in taps]), _ints([t[2] for t in taps])
+    with torch.cuda.device(inp.device):
+        _lib.check(_lib.load().pvae_conv_igemm(_p(inp), _p(w), _p(out), _p(out_act), _p(bias), _p(add_pre), _p(dsilu_src),
+                                               _p(add_post), n, ih, iw, ci, co, oh, ow, ohf, owf, out_step, off_h, off_w, stride,
+                                               len(taps), dy, dx, wi, wtaps, int(PRECISE), _s()))
+
+
+def conv_fwd(x_act, w_fwd, bias, k: int, stride: int, pad: int, co: int, want_act: bool = False):
+    """x_act (N,IH,IW,Ci) NHWC -> conv + bias (N,OH,OW,Co) [, silu of it]"""
+    n, ih, iw, ci = x_act.shape
+    oh, ow = out_size(ih, k, stride, pad), out_size(iw, k, stride, pad)
+    out = torch.empty(n, oh, ow, co, device=x_act.device, dtype=torch.float32)
+    act = torch.empty_like(out) if want_act else None
+    taps = [(r - pad, s - pad, r * k + s) for r in range(k) for s in range(k)]
+    _igemm(x_act, w_fwd, out, act, bias, None, None, None, oh, ow, 1, 0, 0, stride, taps, k * k)
+    return out, act
+
+
+def conv_dgrad(g_out, w_dgrad, in_shape, k: int, stride: int, pad: int, add_pre=None, dsilu_src=None, add_post=None):
+    """gradient wrt the convolution's (activated) input, with the fused epilogue
+    g_in = (conv^T(g_out) + add_pre) * silu'(dsilu_src) + add_post"""
+    n, ih, iw, ci = in_shape
+    _, oh, ow, co = g_out.shape
+    g_in = torch.empty(n, ih, iw, ci, device=g_out.device, dtype=torch.float32)
+    if stride == 1:
+        taps = [(pad - r, pad - s, r * k + s) for r in range(k) for s in range(k)]
+        _igemm(g_out, w_dgrad, g_in, None, None, add_pre, dsilu_src, add_post, ih, iw, 1, 0, 0, 1, taps, k * k)
+        return g_in
+    assert stride == 2
+    for ph in range(2):  # one launch per parity class of the input grid
+        for pw in range(2):
+            qh, qw = (ih - ph + 1) // 2, (iw - pw + 1) // 2
+            if qh <= 0 or qw <= 0:
+                continue
+            taps = [((ph + pad - r) // 2, (pw + pad - s) // 2, r * k + s) for r in range(k) for s in range(k)
+                    if (ph + pad - r) % 2 == 0 and (pw + pad - s) % 2 == 0]
+            _igemm(g_out, w_dgrad, g_in, None, None, add_pre, dsilu_src, add_post, qh, qw, 2, ph, pw, 1, taps, k * k)
+    return g_in
+
+
+def conv_wgrad(x_act, g_out, k: int, stride: int, pad: int):
+    """-> g_wp (k*k*Ci, Co), rows (tap, ci)"""
+    n, ih, iw, ci = x_act.shape
+    _, oh, ow, co = g_out.shape
+    lib = _lib.load()
+    g_wp = torch.empty(k * k * ci, co, device=x_act.device, dtype=torch.float32)
+    ws = _workspace(x_act.device, lib.pvae_conv_wgrad_ws_floats(ci, co, k * k))
+    taps = [(r - pad, s - pad, r * k + s) for r in range(k) for s in range(k)]
+    dy, dx, wi = _ints([t[0] for t in taps]), _ints([t[1] for t in taps]), _ints([t[2] for t in taps])
+    with torch.cuda.device(x_act.device):
+        _lib.check(lib.pvae_conv_wgrad(_p(x_act), _p(g_out), _p(g_wp), _p(ws), n, ih, iw, ci, co, oh, ow, stride, len(taps), dy, dx,
+                                       wi, int(PRECISE), _s()))
+    return g_wp
+
+
+def colsum(x2d):
+    r, c = x2d.shape
+    lib = _lib.load()
+    out = torch.empty(c, device=x2d.device, dtype=torch.float32)
+    ws = _workspace(x2d.device, lib.pvae_reduce_ws_floats(c))
+    with torch.cuda.device(x2d.device):
+        _lib.check(lib.pvae_colsum(_p(x2d), _p(out), _p(ws), r, c, _s()))
+    return out
+
+
+def small_tn(a, b):
+    """(R,Ca)^T (R,Cb) -> (Ca,Cb) for tiny Ca*Cb (squeeze-excitation weights)"""
+    r, ca = a.shape
+    cb = b.shape[1]
+    lib = _lib.load()
+    out = torch.empty(ca, cb, device=a.device, dtype=torch.float32)
+    ws = _workspace(a.device, lib.pvae_reduce_ws_floats(ca * cb))
+    with torch.cuda.device(a.device):
+        _lib.check(lib.pvae_small_tn(_p(a), _p(b), _p(out), _p(ws), r, ca, cb, _s()))
+    return out
+
+
+def silu(x):
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().pvae_silu_fwd(_p(x), _p(out), x.numel(), _s()))
+    return out
+
+
+def _check_input(x, name="x"):
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be a CUDA float32 tensor (poissonvae_b200 has no CPU path)")
+    return x.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------
+# autograd Functions: one per block
+# ------------------------------------------------------------------------------------------------------
+class _StemFn(torch.autograd.Function):
+    """x (N,1,H,W) -> (y, silu(y)) NHWC, main/vae.py:211-218 (x carries no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, lognorm, bias, pad):
+        x = _check_input(x)
+        n, _, ih, iw = x.shape
+        co = weight.shape[0]
+        oh, ow = ih + 2 * pad - 2, iw + 2 * pad - 2
+        y = torch.empty(n, oh, ow, co, device=x.device, dtype=torch.float32)
+        y_act = torch.empty_like(y)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().pvae_stem_fwd(_p(x), _p(weight), _p(lognorm), _p(bias), _p(y), _p(y_act), n, ih, iw, co, pad, _s()))
+        ctx.save_for_backward(x, weight, lognorm)
+        ctx.pad = pad
+        ctx.mark_non_differentiable(y_act)
+        return y, y_act
+
+    @staticmethod
+    def backward(ctx, g_y, _g_act):
+        x, weight, lognorm = ctx.saved_tensors
+        n, _, ih, iw = x.shape
+        co = weight.shape[0]
+        lib = _lib.load()
+        g_y = g_y.contiguous()
+        g_wpb = torch.empty(10, co, device=x.device, dtype=torch.float32)
+        ws = _workspace(x.device, lib.pvae_reduce_ws_floats(10 * co))
+        with torch.cuda.device(x.device):
+            _lib.check(lib.pvae_stem_wgrad(_p(x), _p(g_y), _p(g_wpb), _p(ws), n, ih, iw, co, ctx.pad, _s()))
+        g_w, g_ln = weight_grad(g_wpb, weight, lognorm, 9)
+        return None, g_w, g_ln, g_wpb[9], None
+
+
+def _se_forward(c2, skip, se_w1, se_b1, se_w2, se_b2, eps_res):
+    n, h, w, ch = c2.shape
+    hd = se_w1.shape[0]
+    y = torch.empty_like(c2)
+    y_act = torch.empty_like(c2)
+    pool = torch.empty(n, ch, device=c2.device, dtype=torch.float32)
+    hid = torch.empty(n, hd, device=c2.device, dtype=torch.float32)
+    gate = torch.empty(n, ch, device=c2.device, dtype=torch.float32)
+    with torch.cuda.device(c2.device):
+        _lib.check(_lib.load().pvae_se_fwd(_p(c2), _p(skip), _p(se_w1), _p(se_b1), _p(se_w2), _p(se_b2), eps_res, _p(y), _p(y_act),
+                                           _p(pool), _p(hid), _p(gate), n, h * w, ch, hd, _s()))
+    return y, y_act, pool, hid, gate
+
+
+def _se_backward(g_y, c2, gate, hid, pool, se_w1, se_w2, eps_res):
+    n, h, w, ch = c2.shape
+    hd = se_w1.shape[0]
+    g_c2 = torch.empty_like(c2)
+    d2 = torch.empty(n, ch, device=c2.device, dtype=torch.float32)
+    d1 = torch.empty(n, hd, device=c2.device, dtype=torch.float32)
+    with torch.cuda.device(c2.device):
+        _lib.check(_lib.load().pvae_se_bwd(_p(g_y), _p(c2), _p(gate), _p(hid), _p(se_w1), _p(se_w2), eps_res, _p(g_c2), _p(d2),
+                                           _p(d1), n, h * w, ch, hd, _s()))
+    g_w2, g_b2 = small_tn(d2, hid), colsum(d2)
+    g_w1, g_b1 = small_tn(d1, pool), colsum(d1)
+    return g_c2, g_w1, g_b1, g_w2, g_b2
+
+
+class _CellFn(torch.autograd.Function):
+    """Cell.forward base/common.py:187-192 for the encoder cell types 'normal_pre' (stride 1, identity skip) and
+    'down_enc' (stride 2, FactorizedReduce or StrideReduce skip), n_nodes = 2, SiLU, squeeze-excitation on.
+    Inputs: x and the hint x_act = silu(x) (produced by the previous block's epilogue; carries no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, x_act, w1, ln1, b1, w2, ln2, b2, se_w1, se_b1, se_w2, se_b2, skip_w, skip_ln, skip_b, stride, skip_groups,
+                eps_res):
+        x = _check_input(x)
+        co = w1.shape[0]
+        if x_act is None:
+            x_act = silu(x)
+        wf1, wd1 = weight_prep(w1, ln1, 9)
+        wf2, wd2 = weight_prep(w2, ln2, 9)
+        c1, a2 = conv_fwd(x_act, wf1, b1, 3, stride, 1, co, want_act=True)
+        c2, _ = conv_fwd(a2, wf2, b2, 3, 1, 1, co)
+        if stride == 1:
+            skip, wfs, wds = x, None, None
+        else:
+            ks = 2 if skip_groups > 1 else 1
+            wfs, wds = weight_prep(skip_w, skip_ln, ks * ks, skip_groups)
+            skip, _ = conv_fwd(x_act, wfs, skip_b, ks, 2, 0, co)
+        y, y_act, pool, hid, gate = _se_forward(c2, skip, se_w1, se_b1, se_w2, se_b2, eps_res)
+        ctx.save_for_backward(x, x_act, c1, a2, c2, pool, hid, gate, w1, ln1, w2, ln2, se_w1, se_w2, skip_w, skip_ln, wd1, wd2, wds)
+        ctx.cfg = (stride, skip_groups, eps_res)
+        ctx.mark_non_differentiable(y_act)
+        return y, y_act
+
+    @staticmethod
+    def backward(ctx, g_y, _g_act):
+        x, x_act, c1, a2, c2, pool, hid, gate, w1, ln1, w2, ln2, se_w1, se_w2, skip_w, skip_ln, wd1, wd2, wds = ctx.saved_tensors
+        stride, skip_groups, eps_res = ctx.cfg
+        g_y = g_y.contiguous()
+        n, oh, ow, co = c2.shape
+        g_c2, g_sw1, g_sb1, g_sw2, g_sb2 = _se_backward(g_y, c2, gate, hid, pool, se_w1, se_w2, eps_res)
+        # second convolution
+        g_w2, g_ln2 = weight_grad(conv_wgrad(a2, g_c2, 3, 1, 1), w2, ln2, 9)
+        g_b2 = colsum(g_c2.view(-1, co))
+        g_c1 = conv_dgrad(g_c2, wd2, c1.shape, 3, 1, 1, dsilu_src=c1)
+        # first convolution (+ skip branch)
+        g_w1, g_ln1 = weight_grad(conv_wgrad(x_act, g_c1, 3, stride, 1), w1, ln1, 9)
+        g_b1 = colsum(g_c1.view(-1, co))
+        if stride == 1:
+            g_x = conv_dgrad(g_c1, wd1, x.shape, 3, 1, 1, dsilu_src=x, add_post=g_y)
+            g_sw = g_sln = g_sb = None
+        else:
+            ks = 2 if skip_groups > 1 else 1
+            g_sw, g_sln = weight_grad(conv_wgrad(x_act, g_y, ks, 2, 0), skip_w, skip_ln, ks * ks, skip_groups)
+            g_sb = colsum(g_y.view(-1, co))
+            g_a = conv_dgrad(g_c1, wd1, x.shape, 3, 2, 1)
+            g_x = conv_dgrad(g_y, wds, x.shape, ks, 2, 0, add_pre=g_a, dsilu_src=x)
+        return (g_x, None, g_w1, g_ln1, g_b1, g_w2, g_ln2, g_b2, g_sw1, g_sb1, g_sw2, g_sb2, g_sw, g_sln, g_sb, None, None, None)
+
+
+class _ResConvPoolFn(torch.autograd.Function):
+    """ResConvPool main/vae.py:682-706: mean over the (k x k) map + eps * 'valid' k x k convolution of silu(x) -> (N, C)."""
+
+    @staticmethod
+    def forward(ctx, x, x_act, weight, lognorm, bias, eps_res):
+        x = _check_input(x)
+        n, h, w, ch = x.shape
+        co = weight.shape[0]
+        if x_act is None:
+            x_act = silu(x)
+        assert weight.shape[2] == h and weight.shape[3] == w, "ResConvPool expects the 'valid' convolution to cover the whole map"
+        assert eps_res == 1.0
+        wf, _ = weight_prep(weight, lognorm, h * w, need_dgrad=False)
+        pool = torch.empty(n, ch, device=x.device, dtype=torch.float32)
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.pvae_avgpool_fwd(_p(x), _p(pool), n, h * w, ch, _s()))
+        y = gemm_nt(x_act.view(n, h * w * ch), wf)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.pvae_bias_act(_p(y), _p(bias), _p(pool), n, co, 0, 0.0, 0, 0, _s()))
+        ctx.save_for_backward(x, x_act, weight, lognorm, wf)
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        x, x_act, weight, lognorm, wf = ctx.saved_tensors
+        n, h, w, ch = x.shape
+        co = weight.shape[0]
+        g_y = g_y.contiguous()
+        g_wp = gemm_tn(x_act.view(n, h * w * ch), g_y)  # (taps * Ci, Co)
+        g_w, g_ln = weight_grad(g_wp, weight, lognorm, h * w)
+        g_b = colsum(g_y)
+        g_a = gemm_nn(g_y, wf)  # (N, taps * Ci)
+        g_x = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().pvae_pool_silu_bwd(_p(g_a), _p(x), _p(g_y), _p(g_x), n, h * w, ch, _s()))
+        return g_x, None, g_w, g_ln, g_b, None
+
+
+class _ResDenseFn(torch.autograd.Function):
+    """ResDenseLayer main/vae.py:657-679: LayerNorm(x + fc2(dropout(relu(fc1(x)))))."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, gamma, beta, drop_p, seed, offset):
+        x = _check_input(x)
+        n, ch = x.shape
+        lib = _lib.load()
+        f1 = gemm_nt(x, w1.contiguous())
+        f2 = torch.empty(n, ch, device=x.device, dtype=torch.float32)
+        out, xhat = torch.empty_like(x), torch.empty_like(x)
+        rstd = torch.empty(n, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.pvae_bias_act(_p(f1), _p(b1), None, n, f1.shape[1], 1, drop_p, seed, offset, _s()))
+            gemm_nt(f1, w2.contiguous(), out=f2)
+            _lib.check(lib.pvae_bias_act(_p(f2), _p(b2), None, n, ch, 0, 0.0, 0, 0, _s()))
+            _lib.check(lib.pvae_layernorm_fwd(_p(f2), _p(x), _p(gamma), _p(beta), _p(out), _p(xhat), _p(rstd), n, ch, 1e-5, _s()))
+        ctx.save_for_backward(x, f1, xhat, rstd, w1, w2, gamma)
+        ctx.drop_p = drop_p
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, f1, xhat, rstd, w1, w2, gamma = ctx.saved_tensors
+        n, ch = x.shape
+        lib = _lib.load()
+        g = g.contiguous()
+        g_s = torch.empty_like(x)
+        g_gb = torch.empty(2 * ch, device=x.device, dtype=torch.float32)
+        ws = _workspace(x.device, lib.pvae_reduce_ws_floats(2 * ch))
+        with torch.cuda.device(x.device):
+            _lib.check(lib.pvae_layernorm_bwd(_p(g), _p(xhat), _p(rstd), _p(gamma), _p(g_s), _p(g_gb), _p(ws), n, ch, _s()))
+        g_w2 = gemm_tn(g_s, f1)
+        g_b2 = colsum(g_s)
+        g_f1 = gemm_nn(g_s, w2.contiguous())
+        with torch.cuda.device(x.device):
+            _lib.check(lib.pvae_relu_bwd(_p(g_f1), _p(f1), g_f1.numel(), ctx.drop_p, _s()))
+        g_w1 = gemm_tn(g_f1, x)
+        g_b1 = colsum(g_f1)
+        g_x = gemm_nn(g_f1, w1.contiguous())
+        with torch.cuda.device(x.device):
+            _lib.check(lib.pvae_add(_p(g_x), _p(g_s), _p(g_x), g_x.numel(), _s()))
+        return g_x, g_w1, g_b1, g_w2, g_b2, g_gb[:ch], g_gb[ch:], None, None, None
+
+
+# ------------------------------------------------------------------------------------------------------
+# modules: parameter holders with the reference's names, construction order and initialisation
+# ------------------------------------------------------------------------------------------------------
+class Conv2D(nn.Conv2d):
+    """base/common.py:295-340: nn.Conv2d parameters + `lognorm`; the filter the kernels use is
+    exp(lognorm) * weight / (||weight|| + eps) per output channel."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, reg_lognorm: bool = True, init_scale: float = 1.0, **kwargs):
+        kwargs = {k: v for k, v in kwargs.items() if k in ('stride', 'padding', 'dilation', 'groups', 'bias', 'padding_mode')}
+        super().__init__(in_channels=in_channels, out_channels=out_channels, kernel_size=kernel_size, **kwargs)
+        assert init_scale > 0
+        self.lognorm = nn.Parameter(torch.log(torch.ones(out_channels).mul(init_scale)), requires_grad=reg_lognorm)
+
+    def forward(self, x):
+        raise RuntimeError("Conv2D is a parameter holder here; the enclosing block runs the fused kernels")
+
+
+class ConvLayer(nn.Module):
+    """base/common.py:195-242 (use_bn off): activation -> [upsample] -> Conv2D."""
+
+    def __init__(self, ci, co, stride, act_fn='swish', init_scale=1.0, reg_lognorm=True):
+        super().__init__()
+        assert act_fn in ('swish', 'silu')
+        self.stride = stride
+        self.conv = Conv2D(ci, co, 3, reg_lognorm=reg_lognorm, init_scale=init_scale, stride=abs(stride), padding=1, bias=True)
+
+
+class SELayer(nn.Module):
+    """base/common.py:129-142."""
+
+    def __init__(self, ci, reduc=16):
+        super().__init__()
+        self.hdim = max(ci // reduc, 4)
+        self.fc = nn.Sequential(nn.Linear(ci, self.hdim), nn.ReLU(inplace=True), nn.Linear(self.hdim, ci), nn.Sigmoid())
+
+
+class FactorizedReduce(nn.Module):
+    """base/common.py:98-126: four 1x1 stride-2 convolutions on the four pixel phases, concatenated."""
+
+    def __init__(self, ci, co, reg_lognorm=True):
+        super().__init__()
+        assert co % 2 == 0 and co > 4
+        co_each = co // 4
+        self.ops = nn.ModuleList()
+        for _ in range(3):
+            self.ops.append(Conv2D(ci, co_each, 1, reg_lognorm=reg_lognorm, stride=co // ci, padding=0, bias=True))
+        self.ops.append(Conv2D(ci, co - 3 * co_each, 1, reg_lognorm=reg_lognorm, stride=co // ci, padding=0, bias=True))
+
+    def packed(self):
+        return (torch.cat([op.weight.flatten(1) for op in self.ops]), torch.cat([op.lognorm for op in self.ops]),
+                torch.cat([op.bias for op in self.ops]))
+
+
+class StrideReduce(nn.Module):
+    """base/common.py:75-95: SiLU -> 1x1 stride-2 convolution."""
+
+    def __init__(self, ci, co, reg_lognorm=True):
+        super().__init__()
+        self.conv = Conv2D(ci, co, 1, reg_lognorm=reg_lognorm, stride=co // ci, padding=0, bias=True)
+
+
+class Cell(nn.Module):
+    """base/common.py:145-192, encoder cell types."""
+
+    def __init__(self, ci, co, cell_type, n_nodes=2, act_fn='swish', use_bn=False, use_se=True, scale=1.0, eps=1.0,
+                 reg_lognorm=True, factorized=True):
+        super().__init__()
+        if cell_type not in ('normal_pre', 'down_enc'):
+            raise NotImplementedError(f"cell type {cell_type}: the conv decoder is not built yet")
+        if use_bn or not use_se or n_nodes != 2:
+            raise NotImplementedError("Cell: only n_nodes=2, use_se=True, use_bn=False (the reference defaults)")
+        self.stride = 1 if cell_type.startswith('normal') else MULT
+        if self.stride == 1:
+            assert ci == co
+            self.skip = nn.Identity()
+        else:
+            self.skip = FactorizedReduce(ci, co, reg_lognorm) if factorized else StrideReduce(ci, co, reg_lognorm)
+        self.ops = nn.ModuleList()
+        for i in range(n_nodes):
+            self.ops.append(ConvLayer(ci if i == 0 else co, co, self.stride if i == 0 else 1, act_fn,
+                                      init_scale=scale if i + 1 == n_nodes else 1.0, reg_lognorm=reg_lognorm))
+        self.se = SELayer(co)
+        self.eps = eps
+
+    def forward(self, xs):
+        x, x_act = xs if isinstance(xs, tuple) else (xs, None)
+        c1, c2 = self.ops[0].conv, self.ops[1].conv
+        if self.stride == 1:
+            sw = sln = sb = None
+            groups = 1
+        elif isinstance(self.skip, FactorizedReduce):
+            sw, sln, sb = self.skip.packed()
+            groups = 4
+        else:
+            sw, sln, sb = self.skip.conv.weight, self.skip.conv.lognorm, self.skip.conv.bias
+            groups = 1
+        fc = self.se.fc
+        return _CellFn.apply(x, x_act, c1.weight, c1.lognorm, c1.bias, c2.weight, c2.lognorm, c2.bias, fc[0].weight, fc[0].bias,
+                             fc[2].weight, fc[2].bias, sw, sln, sb, self.stride, groups, float(self.eps))
+
+
+class ResConvPool(nn.Module):
+    """main/vae.py:682-706."""
+
+    def __init__(self, dim, act_fn='swish', eps=1.0, kernel_size=4, reg_lognorm=True):
+        super().__init__()
+        self.conv = Conv2D(dim, dim, kernel_size, reg_lognorm=reg_lognorm, padding='valid')
+        self.eps = eps
+
+    def forward(self, xs):
+        x, x_act = xs if isinstance(xs, tuple) else (xs, None)
+        return _ResConvPoolFn.apply(x, x_act, self.conv.weight, self.conv.lognorm, self.conv.bias, float(self.eps))
+
+
+class ResDenseLayer(nn.Module):
+    """main/vae.py:657-679.  In training mode the dropout mask comes from this library's Philox stream (seeded by torch's
+    CUDA generator), not from torch's dropout kernel: same law, different draws."""
+
+    def __init__(self, dim, expand=8, drop=0.1):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, dim * expand)
+        self.fc2 = nn.Linear(dim * expand, dim)
+        self.layer_norm = nn.LayerNorm(dim)
+        self.drop = nn.Dropout(drop)
+        self.relu = nn.ReLU()
+        self.dim = dim
+
+    def forward(self, x):
+        p = float(self.drop.p) if self.training else 0.0
+        seed, offset = next_philox(x.device) if p > 0.0 else (0, 0)
+        return _ResDenseFn.apply(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, self.layer_norm.weight,
+                                 self.layer_norm.bias, p, seed, offset)
+
+
+class Stem(Conv2D):
+    """main/vae.py:211-218: 3x3 convolution of the single-channel image (padding 1, or 'valid' for MNIST)."""
+
+    def forward(self, x):
+        pad = 0 if self.padding in ('valid', (0, 0)) else 1
+        return _StemFn.apply(x, self.weight, self.lognorm, self.bias, pad)
+
+
+class _Flatten(nn.Module):
+    """nn.Flatten(start_dim=1) placeholder (keeps the reference's nn.Sequential indices); ResConvPool already returns (N, C)."""
+
+    def forward(self, x):
+        return x.flatten(1)
+
+
+def build_conv_enc(nch: int, dataset: str, act_fn='swish', eps=1.0, reg_lognorm=True) -> nn.Sequential:
+    """main/vae.py:710-756 (`_build_conv_enc`, add_fc off)."""
+    factorized = True
+    if dataset.endswith('MNIST'):
+        factorized, n_layers = False, 3
+    elif dataset in ('vH16', 'CIFAR16'):
+        n_layers = 2
+    elif dataset.startswith('BALLS'):
+        n_layers = 4
+    else:
+        raise ValueError(dataset)
+    kws = dict(n_nodes=2, act_fn=act_fn, use_bn=False, use_se=True, scale=1.0, eps=eps, reg_lognorm=reg_lognorm,
+               factorized=factorized)
+    layers = [Cell(nch, nch, 'normal_pre', **kws)]
+    for _ in range(n_layers):
+        layers.extend([Cell(nch, nch * MULT, 'down_enc', **kws), Cell(nch * MULT, nch * MULT, 'normal_pre', **kws)])
+        nch *= MULT
+    layers.extend([ResConvPool(nch, act_fn=act_fn, eps=eps, kernel_size=4, reg_lognorm=reg_lognorm), _Flatten()])
+    return nn.Sequential(*layers, ResDenseLayer(nch))

@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <array>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -30,81 +31,9 @@
 #include "../../include/pvae_b200.h"
 #include "pvae_device.cuh"
 #include "pvae_host.h"
+#include "tc_common.cuh"
 
 namespace pvae {
-
-constexpr int kBM = 128;       // output rows per CTA  (= UMMA M, one TMEM lane per row)
-constexpr int kBK = 32;        // K elements per stage (32 fp32 = one 128-byte swizzle row)
-constexpr int kGemmThreads = 192;
-constexpr int kUmmaK = 8;      // K per tcgen05.mma for 32-bit operands
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// Shared-memory matrix descriptor (tcgen05): start address, leading / stride byte offsets (16-byte units),
-// descriptor version 1, swizzle mode (2 = SWIZZLE_128B with 16-byte atoms, 1 = SWIZZLE_128B with 32-byte
-// atoms - the only layout the hardware accepts for MN-major 32-bit operands).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= static_cast<uint64_t>(1) << 46;  // version
-  d |= static_cast<uint64_t>(layout) << 61;
-  return d;
-}
-
-// Instruction descriptor: D fp32, A/B tf32, majors, N >> 3, M >> 4.
-__host__ __device__ inline uint32_t make_idesc(int m, int n, bool a_mn_major, bool b_mn_major) {
-  uint32_t d = 0;
-  d |= 1u << 4;   // c_format = F32
-  d |= 2u << 7;   // a_format = TF32
-  d |= 2u << 10;  // b_format = TF32
-  d |= (a_mn_major ? 1u : 0u) << 15;
-  d |= (b_mn_major ? 1u : 0u) << 16;
-  d |= static_cast<uint32_t>(n >> 3) << 17;
-  d |= static_cast<uint32_t>(m >> 4) << 24;
-  return d;
-}
 
 struct GemmParams {
   float* C;              // (M,N) row-major, or the split-K workspace (splits, M, N)
@@ -399,15 +328,18 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// 2-D fp32 row-major (rows, cols) tensor, box {box_cols (inner), box_rows}, 128-byte swizzle with 16-byte
-// atoms (K-major operands) or 32-byte atoms (MN-major operands), OOB = 0.
-static int make_map(CUtensorMap* out, const float* base, long long rows, long long cols, int box_cols, int box_rows,
-                    bool atom32 = false) {
-  if (atom32) box_rows = -box_rows;  // distinct cache key
-  typedef std::tuple<const void*, long long, long long, int, int> Key;
+int make_tensor_map(CUtensorMap* out, const float* base, int rank, const long long* dims, const long long* strides_bytes,
+                    const int* box, const int* estr, int swizzle) {
+  if (rank < 2 || rank > 4) return fail(PVAE_ERR_INVALID, "make_tensor_map: rank %d", rank);
+  typedef std::tuple<const void*, int, std::array<long long, 4>, std::array<long long, 3>, std::array<int, 4>, std::array<int, 4>, int> Key;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
-  const Key key(base, rows, cols, box_cols, box_rows);
+  std::array<long long, 4> kd = {0, 0, 0, 0};
+  std::array<long long, 3> ks = {0, 0, 0};
+  std::array<int, 4> kb = {0, 0, 0, 0}, ke = {0, 0, 0, 0};
+  for (int i = 0; i < rank; ++i) kd[i] = dims[i], kb[i] = box[i], ke[i] = estr[i];
+  for (int i = 0; i + 1 < rank; ++i) ks[i] = strides_bytes[i];
+  const Key key(base, rank, kd, ks, kb, ke, swizzle);
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) {
@@ -416,18 +348,26 @@ static int make_map(CUtensorMap* out, const float* base, long long rows, long lo
   }
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(PVAE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 4};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(atom32 ? -box_rows : box_rows)};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  cuuint64_t gdims[4], gstr[3];
+  cuuint32_t gbox[4], gest[4];
+  for (int i = 0; i < rank; ++i) gdims[i] = static_cast<cuuint64_t>(dims[i]), gbox[i] = static_cast<cuuint32_t>(box[i]), gest[i] = static_cast<cuuint32_t>(estr[i]);
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = static_cast<cuuint64_t>(strides_bytes[i]);
+  const CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, static_cast<cuuint32_t>(rank), const_cast<float*>(base), gdims, gstr, gbox,
+                         gest, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) return fail(PVAE_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(rc));
   if (cache.size() > 4096) cache.clear();
   cache[key] = *out;
   return PVAE_OK;
+}
+
+// 2-D fp32 row-major (rows, cols) tensor, box {box_cols (inner), box_rows}, 128-byte swizzle with 16-byte
+// atoms (K-major operands) or 32-byte atoms (MN-major operands), OOB = 0.
+static int make_map(CUtensorMap* out, const float* base, long long rows, long long cols, int box_cols, int box_rows,
+                    bool atom32 = false) {
+  const long long dims[2] = {cols, rows}, strides[1] = {cols * 4};
+  const int box[2] = {box_cols, box_rows}, estr[2] = {1, 1};
+  return make_tensor_map(out, base, 2, dims, strides, box, estr, atom32 ? 1 : 0);
 }
 
 template <int BN, bool SPLIT, int STAGES>
@@ -442,6 +382,12 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmP
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, splits);
   return cuda_ok("gemm_tf32_kernel", launch_pdl(gemm_tf32_kernel<BN, SPLIT, STAGES>, grid, dim3(kGemmThreads), smem, s, ma, mb, p));
+}
+
+int launch_splitk_reduce(const float* ws, float* C, long long n, int splits, cudaStream_t s) {
+  const long long n4 = n / 4;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((n4 + 255) / 256, 148ll * 16));
+  return cuda_ok("splitk_reduce_kernel", launch_pdl(splitk_reduce_kernel, dim3(grid), dim3(256), 0, s, ws, C, n4, splits));
 }
 
 static int g_gemm_variant = 0;  // tuning: 0 = automatic, 1 = wide tiles / 1 CTA per SM, 2 = narrow tiles / 2 CTAs per SM
@@ -504,10 +450,7 @@ static int gemm_impl(const float* A, const float* B, float* C, int64_t M, int64_
   }
   if (rc) return rc;
   if (splits > 1) {
-    const long long n4 = M * N / 4;
-    const unsigned grid = static_cast<unsigned>(std::min<long long>((n4 + 255) / 256, 148ll * 16));
-    return cuda_ok("splitk_reduce_kernel", launch_pdl(splitk_reduce_kernel, dim3(grid), dim3(256), 0, s,
-                                                      static_cast<const float*>(splitk_ws), C, n4, splits));
+    return launch_splitk_reduce(splitk_ws, C, M * N, splits, s);
   }
   return PVAE_OK;
 }

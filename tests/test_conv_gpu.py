@@ -1,0 +1,242 @@
+"""GPU: the conv encoder's kernels (csrc/conv_tc.cu, csrc/conv_misc.cu) against plain
+torch float64 CPU references of the same ops: implicit-GEMM convolution forward / data gradient / weight gradient
+on tcgen05 (3x3 stride 1 and 2, the 2x2 FactorizedReduce window, 1x1 stride 2, odd and non-power-of-two maps),
+weight normalisation, and every block of the encoder with its hand-derived backward against autograd of
+oracle/conv_oracle.py.
+
+Tolerance: the north_star's 1e-5 relative for single ops; for whole blocks (several GEMMs deep, 3xTF32 products)
+5e-5 - stated per test."""
+import numpy as np
+import pytest
+import torch
+from torch.nn import functional as F
+
+from tests.helpers import assert_rel
+
+pytestmark = pytest.mark.gpu
+
+
+def nhwc(t):  # NCHW cpu -> NHWC cuda fp32
+    return t.permute(0, 2, 3, 1).contiguous().float().cuda()
+
+
+def nchw(t):  # NHWC cuda -> NCHW cpu f64
+    return t.detach().permute(0, 3, 1, 2).double().cpu()
+
+
+def normalized(weight, lognorm):
+    from oracle.conv_oracle import normalize
+    return normalize(weight, lognorm)
+
+
+CONV_CASES = [
+    # N, H, W, Ci, Co, k, stride, pad
+    (8, 16, 16, 32, 32, 3, 1, 1),
+    (8, 16, 16, 32, 64, 3, 2, 1),
+    (6, 8, 8, 64, 64, 3, 1, 1),
+    (12, 4, 4, 128, 128, 3, 1, 1),
+    (4, 8, 8, 64, 128, 3, 2, 1),
+    (3, 26, 26, 32, 32, 3, 1, 1),   # map wider than any power-of-two tile: boxes overhang the tensor
+    (5, 13, 13, 64, 128, 3, 2, 1),  # odd map, stride 2 -> 7x7
+    (4, 7, 7, 128, 256, 3, 2, 1),   # -> 4x4, two column tiles of 128 channels
+    (4, 16, 16, 32, 64, 1, 2, 0),   # StrideReduce
+    (2, 2, 2, 256, 256, 3, 1, 1),   # decoder-sized map
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_forward_dgrad_wgrad(case):
+    from poissonvae_b200 import conv
+    N, H, W, Ci, Co, k, stride, pad = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, Ci, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    weight = (torch.randn(Co, Ci, k, k, generator=g, dtype=torch.float64) * 0.2).requires_grad_()
+    lognorm = (torch.randn(Co, generator=g, dtype=torch.float64) * 0.3).requires_grad_()
+    bias = torch.randn(Co, generator=g, dtype=torch.float64, requires_grad=True)
+    y_ref = F.conv2d(x, normalized(weight, lognorm), bias, stride=stride, padding=pad)
+    gy = torch.randn(y_ref.shape, generator=g, dtype=torch.float64)
+    y_ref.backward(gy)
+
+    wf, wd = conv.weight_prep(weight.detach().float().cuda(), lognorm.detach().float().cuda(), k * k)
+    y, y_act = conv.conv_fwd(nhwc(x.detach()), wf, bias.detach().float().cuda(), k, stride, pad, Co, want_act=True)
+    assert_rel(nchw(y), y_ref.detach(), what="conv forward")
+    assert_rel(nchw(y_act), F.silu(y_ref.detach()), what="fused silu output")
+
+    gy_d = nhwc(gy)
+    gx = conv.conv_dgrad(gy_d, wd, (N, H, W, Ci), k, stride, pad)
+    assert_rel(nchw(gx), x.grad, what="conv dgrad")
+    # fused epilogue: (dgrad + add_pre) * silu'(src) + add_post
+    a_pre, src, a_post = (torch.randn(N, Ci, H, W, generator=g, dtype=torch.float64) for _ in range(3))
+    gx2 = conv.conv_dgrad(gy_d, wd, (N, H, W, Ci), k, stride, pad, add_pre=nhwc(a_pre), dsilu_src=nhwc(src), add_post=nhwc(a_post))
+    sg = torch.sigmoid(src)
+    assert_rel(nchw(gx2), (x.grad + a_pre) * (sg * (1 + src * (1 - sg))) + a_post, what="dgrad epilogue")
+
+    gwp = conv.conv_wgrad(nhwc(x.detach()), gy_d, k, stride, pad)
+    gw, gln = conv.weight_grad(gwp, weight.detach().float().cuda(), lognorm.detach().float().cuda(), k * k)
+    assert_rel(gw.double().cpu(), weight.grad, rtol=2e-5, what="weight gradient")
+    assert_rel(gln.double().cpu(), lognorm.grad, rtol=2e-5, what="lognorm gradient")
+    assert_rel(conv.colsum(gy_d.view(-1, Co)).double().cpu(), bias.grad, what="bias gradient")
+
+
+def test_factorized_reduce_window():
+    """FactorizedReduce base/common.py:98-126 as ONE 2x2 stride-2 implicit GEMM with a block-sparse packed filter."""
+    from poissonvae_b200 import conv
+    N, H, W, Ci, Co = 6, 16, 16, 32, 64
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, Ci, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    ws = [(torch.randn(Co // 4, Ci, 1, 1, generator=g, dtype=torch.float64) * 0.3).requires_grad_() for _ in range(4)]
+    lns = [(torch.randn(Co // 4, generator=g, dtype=torch.float64) * 0.3).requires_grad_() for _ in range(4)]
+    bs = [torch.randn(Co // 4, generator=g, dtype=torch.float64, requires_grad=True) for _ in range(4)]
+    outs = []
+    for idx in range(4):
+        i, j = idx // 2, idx % 2
+        outs.append(F.conv2d(x[..., i:, j:], normalized(ws[idx], lns[idx]), bs[idx], stride=2))
+    y_ref = torch.cat(outs, 1)
+    gy = torch.randn(y_ref.shape, generator=g, dtype=torch.float64)
+    y_ref.backward(gy)
+    w_all = torch.cat([w.detach().flatten(1) for w in ws]).float().cuda()
+    ln_all = torch.cat([l.detach() for l in lns]).float().cuda()
+    b_all = torch.cat([b.detach() for b in bs]).float().cuda()
+    wf, wd = conv.weight_prep(w_all, ln_all, 4, groups=4)
+    y, _ = conv.conv_fwd(nhwc(x.detach()), wf, b_all, 2, 2, 0, Co)
+    assert_rel(nchw(y), y_ref.detach(), what="factorized reduce forward")
+    gx = conv.conv_dgrad(nhwc(gy), wd, (N, H, W, Ci), 2, 2, 0)
+    assert_rel(nchw(gx), x.grad, what="factorized reduce dgrad")
+    gwp = conv.conv_wgrad(nhwc(x.detach()), nhwc(gy), 2, 2, 0)
+    gw, gln = conv.weight_grad(gwp, w_all, ln_all, 4, groups=4)
+    assert_rel(gw.double().cpu(), torch.cat([w.grad.flatten(1) for w in ws]), rtol=2e-5, what="factorized weight gradient")
+    assert_rel(gln.double().cpu(), torch.cat([l.grad for l in lns]), rtol=2e-5, what="factorized lognorm gradient")
+
+
+def test_conv_single_pass_tf32_is_coarser():
+    from poissonvae_b200 import conv
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(4, 32, 16, 16, generator=g, dtype=torch.float64)
+    weight = torch.randn(32, 32, 3, 3, generator=g, dtype=torch.float64) * 0.2
+    ref = F.conv2d(x, weight, None, padding=1)
+    wf, _ = conv.weight_prep(weight.float().cuda(), None, 9, need_dgrad=False)
+    errs = {}
+    try:
+        for mode in (True, False):
+            conv.PRECISE = mode
+            y, _ = conv.conv_fwd(nhwc(x), wf, None, 3, 1, 1, 32)
+            errs[mode] = float((nchw(y) - ref).abs().max() / ref.abs().max())
+    finally:
+        conv.PRECISE = True
+    assert errs[True] < 3e-6 and errs[False] > 20 * errs[True], errs
+
+
+# ---- blocks ---------------------------------------------------------------------------------------------
+def _module_state(mod, prefix, dtype=torch.float64):
+    return {f"{prefix}.{k}" if prefix else k: v.detach().cpu().to(dtype).requires_grad_() for k, v in mod.state_dict().items()}
+
+
+def _perturb(mod, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in mod.named_parameters():
+            if name.endswith("lognorm"):
+                p.add_(0.2 * torch.randn(p.shape, generator=g))
+            elif name.endswith("bias"):
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+
+
+def _compare_grads(mod, sd, prefix, rtol):
+    for name, p in mod.named_parameters():
+        ref = sd[f"{prefix}.{name}" if prefix else name].grad
+        assert p.grad is not None, name
+        assert_rel(p.grad.double().cpu(), ref, rtol=rtol, what=f"grad {name}")
+
+
+@pytest.mark.parametrize("kind", ["normal", "down_factorized", "down_stride"])
+def test_cell_forward_backward(kind):
+    from oracle import conv_oracle
+    from poissonvae_b200 import conv
+    torch.manual_seed(11)
+    ci = 32
+    co = ci if kind == "normal" else 64
+    cell = conv.Cell(ci, co, "normal_pre" if kind == "normal" else "down_enc", factorized=(kind != "down_stride"))
+    _perturb(cell, 3)
+    sd = _module_state(cell, "c")
+    g = torch.Generator().manual_seed(2)
+    N, H = 8, 16
+    x = torch.randn(N, ci, H, H, generator=g, dtype=torch.float64, requires_grad=True)
+    y_ref = conv_oracle.cell(x, sd, "c", 1 if kind == "normal" else 2)
+    gy = torch.randn(y_ref.shape, generator=g, dtype=torch.float64)
+    y_ref.backward(gy)
+    cell.cuda()
+    xd = nhwc(x.detach()).requires_grad_()
+    y, y_act = cell(xd)
+    assert_rel(nchw(y), y_ref.detach(), rtol=2e-5, what="cell forward")
+    assert_rel(nchw(y_act), F.silu(y_ref.detach()), rtol=2e-5, what="cell forward (activated copy)")
+    y.backward(nhwc(gy))
+    assert_rel(nchw(xd.grad), x.grad, rtol=5e-5, what="cell input gradient")
+    _compare_grads(cell, sd, "c", 5e-5)
+
+
+def test_stem_res_conv_pool_res_dense():
+    from oracle import conv_oracle
+    from poissonvae_b200 import conv
+    torch.manual_seed(12)
+    g = torch.Generator().manual_seed(4)
+    # stem
+    for pad, hw in ((1, 16), (0, 28)):
+        stem = conv.Stem(1, 32, 3, padding=pad if pad else 'valid')
+        _perturb(stem, 5)
+        sd = _module_state(stem, "stem")
+        x = torch.randn(6, 1, hw, hw, generator=g, dtype=torch.float64)
+        y_ref = conv_oracle.conv2d(x, sd, "stem", padding=pad)
+        gy = torch.randn(y_ref.shape, generator=g, dtype=torch.float64)
+        y_ref.backward(gy)
+        stem.cuda()
+        y, y_act = stem(x.float().cuda())
+        assert_rel(nchw(y), y_ref.detach(), what="stem forward")
+        assert_rel(nchw(y_act), F.silu(y_ref.detach()), what="stem forward (activated copy)")
+        y.backward(nhwc(gy))
+        _compare_grads(stem, sd, "stem", 2e-5)
+    # ResConvPool
+    pool = conv.ResConvPool(128)
+    _perturb(pool, 6)
+    sd = _module_state(pool, "p")
+    x = torch.randn(12, 128, 4, 4, generator=g, dtype=torch.float64, requires_grad=True)
+    y_ref = conv_oracle.res_conv_pool(x, sd, "p").flatten(1)
+    gy = torch.randn(y_ref.shape, generator=g, dtype=torch.float64)
+    y_ref.backward(gy)
+    pool.cuda()
+    xd = nhwc(x.detach()).requires_grad_()
+    y = pool(xd)
+    assert_rel(y.detach().double().cpu(), y_ref.detach(), rtol=2e-5, what="ResConvPool forward")
+    y.backward(gy.float().cuda())
+    assert_rel(nchw(xd.grad), x.grad, rtol=2e-5, what="ResConvPool input gradient")
+    _compare_grads(pool, sd, "p", 2e-5)
+    # ResDenseLayer (eval mode: dropout off)
+    dense = conv.ResDenseLayer(128).eval()
+    sd = _module_state(dense, "d")
+    x = torch.randn(16, 128, generator=g, dtype=torch.float64, requires_grad=True)
+    y_ref = conv_oracle.res_dense(x, sd, "d")
+    gy = torch.randn(y_ref.shape, generator=g, dtype=torch.float64)
+    y_ref.backward(gy)
+    dense.cuda()
+    xd = x.detach().float().cuda().requires_grad_()
+    y = dense(xd)
+    assert_rel(y.detach().double().cpu(), y_ref.detach(), rtol=2e-5, what="ResDenseLayer forward")
+    y.backward(gy.float().cuda())
+    assert_rel(xd.grad.double().cpu(), x.grad, rtol=2e-5, what="ResDenseLayer input gradient")
+    _compare_grads(dense, sd, "d", 2e-5)
+
+
+def test_res_dense_dropout_statistics():
+    """Training mode: the Philox mask keeps ~90 % of the hidden units, scales them by 1/0.9, and the backward uses
+    the same mask (finite-difference check of one coordinate is not possible under a random mask, so check
+    that a second forward with the generator rewound reproduces the output bit for bit)."""
+    from poissonvae_b200 import conv
+    torch.manual_seed(13)
+    dense = conv.ResDenseLayer(128).cuda().train()
+    x = torch.randn(64, 128, device="cuda")
+    state = torch.cuda.get_rng_state()
+    y1 = dense(x)
+    torch.cuda.set_rng_state(state)
+    y2 = dense(x)
+    assert torch.equal(y1, y2)
+    y3 = dense(x)
+    assert not torch.equal(y1, y3)
