@@ -146,6 +146,70 @@ def gen_exact(ref):
     np.savez_compressed(os.path.join(OUT, "vae_exact_k64.npz"), **rec)
 
 
+def digest_stride(size: int) -> int:
+    return 1 if size <= 4096 else max(8, -(-size // 16384))
+
+
+def grad_digest(g: np.ndarray):
+    """Small tensors in full; large ones as every digest_stride-th element plus the L2 norm (keeps fixtures small)."""
+    flat = g.reshape(-1)
+    return flat[::digest_stride(flat.size)].copy(), np.float64(np.linalg.norm(flat.astype(np.float64)))
+
+
+def perturb_conv_params(model, seed):
+    """Move lognorm / biases / LayerNorm affine off their trivial initial values (CPU generator: reproducible anywhere)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("lognorm") or name.endswith("bias") or "layer_norm" in name:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+
+
+def gen_conv(ref):
+    """Conv encoder + linear decoder (BASELINE configs 4 and the encoder of 5): one full forward / loss / backward of the
+    unmodified reference in eval mode (dropout off), with injected exponentials.  Parameters are NOT stored: the
+    mirror model builds bit-identical ones from cfg.seed (tests/test_conv_oracle.py checks that against the reference
+    and against the checksums stored here)."""
+    cases = [dict(tag="cifar16", dataset="CIFAR16", B=8, n_exp=12, temp=0.7, beta=1.5, seed=7),
+             dict(tag="mnist", dataset="MNIST", B=4, n_exp=10, temp=1.0, beta=1.0, seed=8)]
+    for c in cases:
+        cfg_vae, cfg_tr = ref.cfg.default_configs(c["dataset"], "poisson", "conv+b|lin")
+        cfg_vae.update(seed=c["seed"])
+        model = ref.vae.PoissonVAE(ref.cfg.ConfigPoisVAE(save=False, **cfg_vae)).eval()
+        perturb_conv_params(model, 100 + c["seed"])
+        with torch.no_grad():
+            model.log_rate.add_(3.0)
+        model.n_exp.fill_(c["n_exp"])
+        model.update_t(c["temp"])
+        sz = model.cfg.input_sz
+        rng = np.random.default_rng(2000 + c["seed"])
+        x = rng.standard_normal((c["B"], 1, sz, sz)).astype(np.float32)
+        if c["dataset"] == "MNIST":
+            x = rng.uniform(0, 1, size=x.shape).astype(np.float32)  # ToTensor range, base/dataset.py:97-100
+        K = model.cfg.n_latents
+        u, e = _draws(2024, 16, (c["B"], K), c["n_exp"])
+        xt = torch.tensor(x)
+        enc_out = model.encode(xt).detach().numpy()  # main/vae.py:40-52
+        with ref_import.inject_exponentials([e]):
+            dist, log_dr, z, y = model(xt)
+        recon = model.loss_recon(y, xt)
+        kl = model.loss_kl(log_dr)
+        loss = torch.mean(recon + c["beta"] * torch.sum(kl, dim=1))
+        loss.backward()
+        rec = dict(x=x, n_exp=c["n_exp"], temp=c["temp"], beta=c["beta"], cfg_seed=c["seed"], perturb_seed=100 + c["seed"],
+                   philox_seed=2024, philox_offset=16, dataset=c["dataset"], enc_out=enc_out,
+                   log_dr=log_dr.detach().numpy(), z=z.detach().numpy(), y=y.detach().numpy(), recon=recon.detach().numpy(),
+                   kl=kl.detach().numpy(), loss=loss.detach().numpy(), rate=dist.rate.detach().numpy())
+        names = []
+        for n, p in model.named_parameters():
+            names.append(n)
+            d, nrm = grad_digest(p.grad.detach().numpy())
+            rec["g_" + n], rec["gn_" + n] = d, nrm
+            rec["ck_" + n] = np.array([p.detach().double().sum().item(), p.detach().double().abs().sum().item()])
+        rec["param_names"] = np.array(names)
+        np.savez_compressed(os.path.join(OUT, f"conv_enc_{c['tag']}.npz"), **rec)
+
+
 def gen_scalars(ref):
     rec = {}
     rates = np.array([0.05, 0.1, 0.43, 1, 5, 20, 50, 100, 148.4, 200], dtype=np.float64)
@@ -175,6 +239,7 @@ def main():
     gen_hard(ref)
     gen_vae(ref)
     gen_exact(ref)
+    gen_conv(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -1,6 +1,6 @@
-"""Host-side mirror of the reference `PoissonVAE` for the lin|lin architecture (main/vae.py:374-492,
-BaseVAE main/vae.py:9-72) and of the slice of its config the hot path reads
-(main/config_vae.py:172-195, 373-465).
+"""Host-side mirror of the reference `PoissonVAE` (main/vae.py:374-492, BaseVAE main/vae.py:9-72) for the
+lin|lin architecture and the conv+b|lin one (conv encoder of main/vae.py:211-259, 710-756 - see conv.py), and of
+the slice of its config the hot path reads (main/config_vae.py:14-110, 172-195, 373-465).
 
 Same method names, argument meaning, return tuples, parameter/buffer names and state_dict keys
 (`log_rate, temp, n_exp, fc_enc.weight, fc_dec.weight`), so a reference trainer can drive it.
@@ -27,19 +27,29 @@ class ConfigPoisVAE:
     """The fields of the reference ConfigPoisVAE/ConfigVAE that the lin|lin hot path reads.
     Like the reference (base/config_base.py:51-63) constructing it seeds torch, numpy and random."""
 
-    def __init__(self, n_latents: int = 512, input_sz: int = 16, dataset: str = 'vH16',
+    def __init__(self, n_latents: int = 512, input_sz: int = None, dataset: str = 'vH16',
                  enc_type: str = 'lin', dec_type: str = 'lin', enc_bias: bool = False, dec_bias: bool = False,
                  prior_clamp: float = -2.0, prior_log_dist: str = 'uniform', indicator_approx: str = 'sigmoid',
                  exc_only: bool = False, fit_prior: bool = True, init_dist: str = 'Normal',
-                 init_scale: float | None = 0.05, seed: int = 0, **unused):
+                 init_scale: float | None = 0.05, seed: int = 0, n_ch: int = 32, activation_fn: str = 'swish',
+                 res_eps: float = 1.0, use_bn: bool = False, use_se: bool = True, enc_norm: bool = False,
+                 dec_norm: bool = False, **unused):
         assert prior_log_dist in ('cte', 'uniform', 'normal')
         assert indicator_approx in INDICATOR_CODES
-        if enc_type != 'lin' or dec_type != 'lin':
-            raise NotImplementedError("poissonvae_b200 covers the lin|lin architecture (SURVEY.md section 8)")
+        if enc_type not in ('lin', 'conv') or dec_type != 'lin':
+            raise NotImplementedError("poissonvae_b200 covers lin|lin and conv|lin (SURVEY.md section 8); "
+                                      f"got {enc_type}|{dec_type}")
         if init_dist != 'Normal':
             raise NotImplementedError(init_dist)
+        if enc_norm or dec_norm:
+            raise NotImplementedError("weight-normalised fc_enc / fc_dec (off by default in the reference)")
+        if enc_type == 'conv' and (use_bn or not use_se or activation_fn not in ('swish', 'silu') or res_eps != 1.0):
+            raise NotImplementedError("conv encoder: the reference defaults only (swish, SE on, BatchNorm off, res_eps 1)")
+        if input_sz is None:  # ConfigVAE._init_input_sz main/config_vae.py:97-110
+            input_sz = 28 if dataset.endswith('MNIST') else 16
         self.n_latents, self.input_sz, self.dataset = n_latents, input_sz, dataset
         self.enc_type, self.dec_type, self.enc_bias, self.dec_bias = enc_type, dec_type, enc_bias, dec_bias
+        self.n_ch, self.activation_fn, self.res_eps, self.use_bn, self.use_se = n_ch, activation_fn, res_eps, use_bn, use_se
         self.prior_clamp, self.prior_log_dist = prior_clamp, prior_log_dist
         self.indicator_approx, self.exc_only, self.fit_prior = indicator_approx, exc_only, fit_prior
         self.init_dist, self.init_scale = init_dist, init_scale
@@ -61,15 +71,20 @@ class ConfigPoisVAE:
 
 
 def default_configs(dataset: str = 'vH16', model_type: str = 'poisson', archi_type: str = 'lin|lin'):
-    """main/config_vae.py:373-465 restricted to poisson lin|lin on 16x16 patches."""
-    if model_type != 'poisson' or archi_type.strip('<>') != 'lin|lin':
+    """main/config_vae.py:373-465 restricted to poisson with a linear decoder (lin|lin, conv|lin, with or without +b)."""
+    archi = archi_type.strip('<>')
+    if model_type != 'poisson' or archi not in ('lin|lin', 'lin+b|lin', 'conv|lin', 'conv+b|lin'):
         raise NotImplementedError((model_type, archi_type))
-    if dataset not in ('vH16', 'CIFAR16'):
+    enc = archi.split('|')[0]
+    cfg_vae = dict(dataset=dataset, n_ch=32, n_latents=512, prior_clamp=-4, fit_prior=True, enc_type=enc.split('+')[0],
+                   dec_type='lin', enc_bias=enc.endswith('+b'), dec_bias=False, init_dist='Normal', init_scale=0.05)
+    if dataset in ('vH16', 'CIFAR16'):
+        cfg_tr = dict(lr=0.005, batch_size=1000, epochs=3000 if dataset == 'vH16' else 1500, grad_clip=None)
+    elif dataset.endswith('MNIST'):
+        cfg_tr = dict(lr=0.002, epochs=200 if dataset == 'EMNIST' else 400, batch_size=100, warm_restart=0, grad_clip=1000)
+    else:
         raise NotImplementedError(dataset)
-    cfg_vae = dict(dataset=dataset, n_ch=32, n_latents=512, prior_clamp=-4, fit_prior=True, enc_type='lin',
-                   dec_type='lin', enc_bias=False, dec_bias=False, init_dist='Normal', init_scale=0.05)
-    cfg_tr = dict(lr=0.005, batch_size=1000, epochs=3000 if dataset == 'vH16' else 1500, grad_clip=None,
-                  kl_const_portion=0.0)
+    cfg_tr['kl_const_portion'] = 0.0
     return cfg_vae, cfg_tr
 
 
@@ -238,7 +253,13 @@ class PoissonVAE(nn.Module):
         D, K = cfg.input_sz ** 2, cfg.n_latents
         # same construction order as BaseVAE._init (main/vae.py:176-184) so that a given cfg.seed
         # yields the reference's initial parameters
-        self.fc_enc = _Linear(D, K, bias=cfg.enc_bias)  # main/vae.py:253-259
+        if cfg.enc_type == 'conv':  # main/vae.py:209-236
+            from . import conv
+            self.stem = conv.Stem(1, cfg.n_ch, 3, padding='valid' if cfg.dataset.endswith('MNIST') else 1, reg_lognorm=True)
+            self.enc = conv.build_conv_enc(cfg.n_ch, cfg.dataset, cfg.activation_fn, cfg.res_eps)
+            self.fc_enc = _Linear(self.enc[-1].dim, K, bias=cfg.enc_bias)
+        else:
+            self.fc_enc = _Linear(D, K, bias=cfg.enc_bias)  # main/vae.py:253-259
         self.shape = (-1, 1, cfg.input_sz, cfg.input_sz)
         self.fc_dec = _Linear(K, D, bias=cfg.dec_bias)  # main/vae.py:306-312
         self._init_prior()
@@ -299,12 +320,18 @@ class PoissonVAE(nn.Module):
         spks = dist.rsample()
         return self.decode(spks), spks
 
+    def _features(self, x):
+        """What fc_enc sees, main/vae.py:40-50: the flattened input, or the conv encoder's (N, C) output."""
+        if self.cfg.enc_type == 'conv':
+            return self.enc(self.stem(x.reshape(x.shape[0], 1, self.cfg.input_sz, self.cfg.input_sz)))
+        return x.flatten(start_dim=1)
+
     def encode_linear(self, x):
         # bias (if any) is added inside the sampler kernel
-        return linear(x.flatten(start_dim=1), self.fc_enc.weight, None)
+        return linear(self._features(x), self.fc_enc.weight, None)
 
     def encode(self, x):  # main/vae.py:40-52
-        return self.fc_enc(x.flatten(start_dim=1))
+        return self.fc_enc(self._features(x))
 
     def decode(self, z):  # main/vae.py:54-66
         return self.fc_dec(z).view(*self.shape)

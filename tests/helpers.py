@@ -32,3 +32,35 @@ def assert_ulp(a, b, max_ulp=1, max_frac=1.0, what=""):
     assert d.max(initial=0) <= max_ulp, f"{what}: {d.max()} ulp apart at {np.unravel_index(d.argmax(), d.shape)}"
     frac = float((d > 0).mean()) if d.size else 0.0
     assert frac <= max_frac, f"{what}: {frac:.2e} of the entries differ"
+
+
+# ---- conv encoder fixtures (tests/golden/conv_enc_*.npz, oracle/make_golden.py:gen_conv) -----------------
+def digest_stride(size: int) -> int:
+    return 1 if size <= 4096 else max(8, -(-size // 16384))
+
+
+def conv_fixture_model(g):
+    """The mirror model with the parameters the fixture's reference model had: same cfg.seed (-> bit-identical
+    initial parameters), then the same seeded perturbation of lognorm / biases / LayerNorm affine and log_rate + 3."""
+    import torch
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE, default_configs
+    cfg_vae, _ = default_configs(str(g["dataset"]), "poisson", "conv+b|lin")
+    cfg_vae.update(seed=int(g["cfg_seed"]))
+    model = PoissonVAE(ConfigPoisVAE(**cfg_vae)).eval()
+    gen = torch.Generator().manual_seed(int(g["perturb_seed"]))
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("lognorm") or name.endswith("bias") or "layer_norm" in name:
+                p.add_(0.1 * torch.randn(p.shape, generator=gen))
+        model.log_rate.add_(3.0)
+    for name, p in model.named_parameters():  # the reference's parameters, by checksum
+        ck = np.array([p.detach().double().sum().item(), p.detach().double().abs().sum().item()])
+        assert np.allclose(ck, g["ck_" + name], rtol=1e-12, atol=0), name
+    return model
+
+
+def assert_grad_digest(grad, g, name, rtol):
+    flat = np.asarray(grad, dtype=np.float64).reshape(-1)
+    assert_rel(flat[::digest_stride(flat.size)], g["g_" + name], rtol=rtol, what="grad " + name)
+    nrm = float(g["gn_" + name])
+    assert abs(np.linalg.norm(flat) - nrm) <= 10 * rtol * nrm + 1e-30, ("grad norm " + name, np.linalg.norm(flat), nrm)

@@ -240,3 +240,38 @@ def test_res_dense_dropout_statistics():
     assert torch.equal(y1, y2)
     y3 = dense(x)
     assert not torch.equal(y1, y3)
+
+
+# ---- whole model against the unmodified reference ---------------------------------------------------------
+import glob
+import os
+
+GOLDEN_CONV = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "conv_enc_*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN_CONV)
+def test_conv_vae_step_matches_reference(path):
+    """conv+b|lin (BASELINE config 4; MNIST-shaped encoder of config 5): forward, loss and every parameter gradient of one
+    step against the fixture the unmodified reference produced with the same parameters, input and exponential draws.
+    Tolerance 5e-5 relative: ~25 chained 3xTF32 GEMMs deep (each ~2e-6), stated here as the floating-point bound."""
+    from tests.helpers import assert_grad_digest, conv_fixture_model
+    g = np.load(path)
+    model = conv_fixture_model(g).cuda()
+    model.n_exp.fill_(int(g["n_exp"]))
+    model._n_exp_host = int(g["n_exp"])
+    model.update_t(float(g["temp"]))
+    x = torch.tensor(g["x"], device="cuda")
+    with torch.no_grad():
+        assert_rel(model.encode(x).cpu().numpy(), g["enc_out"], rtol=2e-5, what="encoder output")
+    torch.cuda.manual_seed(int(g["philox_seed"]))
+    torch.cuda.default_generators[torch.cuda.current_device()].set_offset(int(g["philox_offset"]))
+    dist, log_dr, z, y = model(x)
+    recon = model.loss_recon(y, x)
+    kl = model.loss_kl(log_dr)
+    loss = torch.mean(recon + float(g["beta"]) * torch.sum(kl, dim=1))
+    loss.backward()
+    for name, got in (("log_dr", log_dr), ("z", z), ("y", y), ("recon", recon), ("kl", kl), ("loss", loss), ("rate", dist.rate)):
+        assert_rel(got.detach().cpu().numpy(), g[name], rtol=5e-5, what=name)
+    for name, p in model.named_parameters():
+        assert p.grad is not None, name
+        assert_grad_digest(p.grad.cpu().numpy(), g, name, 5e-5)
