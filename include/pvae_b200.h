@@ -55,6 +55,8 @@ int pvae_version(void);
 /* Programmatic dependent launch for every kernel of the library (default on): a kernel may be scheduled
  * while its predecessor in the stream drains and waits (griddepcontrol.wait) before touching its data. */
 int pvae_set_pdl(int on);
+/* Number of kernels this library has launched in this process so far (all streams, all entry points). */
+int64_t pvae_launch_count(void);
 const char* pvae_last_error(void);
 
 /* Rows of the (P, K) partial-sum workspaces the backward entry points need for batch size B. */
@@ -155,6 +157,10 @@ int pvae_loss_assemble(const float* recon, const float* kl_rowsum, float* out3, 
                        int recon_parts, void* stream);
 int64_t pvae_grad_norm_ws_floats(void);
 int pvae_grad_norm(const float* g, int64_t n, float max_norm, float* ws, float* out2, void* stream);
+/* Gather n_tensors device arrays into one flat buffer: dst[offsets[i] .. offsets[i+1]) = srcs[i] (zeros where srcs[i] is
+ * NULL).  srcs / offsets are HOST arrays (offsets has n_tensors + 1 entries).  One launch per 96 tensors: the per-parameter
+ * gradients autograd hands out become the flat buffer the all-reduce / clip / Adamax kernels work on. */
+int pvae_gather(const void* const* srcs, const int64_t* offsets, int n_tensors, float* dst, void* stream);
 int pvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, float lr, int step, float beta1,
                      float beta2, float eps, float weight_decay, const float* clip_coef, void* stream);
 

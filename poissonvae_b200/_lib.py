@@ -42,6 +42,7 @@ _SIGNATURES = {
     "pvae_version": (C.c_int, []),
     "pvae_last_error": (C.c_char_p, []),
     "pvae_set_pdl": (_i, [_i]),
+    "pvae_launch_count": (_i64, []),
     "pvae_num_partials": (_i64, [_i64]),
     "pvae_sampler_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _f, _i, _i, _f, _u64, _u64, _p, _p]),
     "pvae_sampler_bwd": (_i, [_p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _i, _i64, _i64, _i64, _i, _f, _i, _i, _f, _u64, _u64, _p, _p]),
@@ -58,6 +59,7 @@ _SIGNATURES = {
     "pvae_gemm_tf32_residual": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _i, _p]),
     "pvae_grad_norm_ws_floats": (_i64, []),
     "pvae_grad_norm": (_i, [_p, _i64, _f, _p, _p, _p]),
+    "pvae_gather": (_i, [_p, _p, _i, _p, _p]),
     "pvae_adamax_step": (_i, [_p, _p, _p, _p, _i64, _f, _i, _f, _f, _f, _f, _p, _p]),
     "pvae_allreduce_adamax": (_i, [_p, _p, _p, _i64, _i64, _p, _p, _i, _i, C.c_uint32, _p, _p, _f, _i, _f, _f, _f, _f, _p]),
     "pvae_lin_step_ws_floats": (_i64, [_i64, _i64, _i64]),

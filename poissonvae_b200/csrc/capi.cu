@@ -1,4 +1,6 @@
 // Library-level C-ABI entry points (version, error string).
+#include <atomic>
+
 #include "pvae_host.h"
 
 namespace pvae {
@@ -9,6 +11,8 @@ char* last_error_buffer() {
 static bool g_pdl = true;
 bool pdl_enabled() { return g_pdl; }
 void set_pdl(bool on) { g_pdl = on; }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace pvae
 
 namespace pvae { void set_pdl(bool); }
@@ -18,3 +22,4 @@ extern "C" int pvae_set_pdl(int on) {
 }
 extern "C" int pvae_version(void) { return 100; }
 extern "C" const char* pvae_last_error(void) { return pvae::last_error_buffer(); }
+extern "C" int64_t pvae_launch_count(void) { return pvae::g_launches.load(std::memory_order_relaxed); }

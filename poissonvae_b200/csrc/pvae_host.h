@@ -30,6 +30,7 @@ inline int cuda_ok(const char* what, cudaError_t e) {
 // pdl_launch_dependents() early so that its own successor can do the same.  Hides launch latency and
 // kernel prologues behind the previous kernel's tail.  pvae_set_pdl(0) turns the attribute off.
 bool pdl_enabled();
+void count_launch();  // every kernel launch of this library is counted (pvae_launch_count)
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
@@ -40,6 +41,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  count_launch();
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

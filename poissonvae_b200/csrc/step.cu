@@ -113,9 +113,47 @@ __global__ void __launch_bounds__(256) adamax_kernel(float* __restrict__ p, cons
   }
 }
 
+// ---- gather up to kGatherMax gradient tensors into the flat buffer (one launch instead of one copy each) ----
+constexpr int kGatherMax = 96;
+struct GatherTable {
+  const float* src[kGatherMax];
+  long long off[kGatherMax + 1];  // destination offsets in floats; off[n] = end
+  int n;
+};
+__global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ GatherTable t, float* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
+  // blockIdx.y = tensor; blocks of a tensor stride over it
+  const int i = blockIdx.y;
+  if (i >= t.n) return;
+  const long long n = t.off[i + 1] - t.off[i];
+  const float* __restrict__ s = t.src[i];
+  float* __restrict__ d = dst + t.off[i];
+  for (long long k = blockIdx.x * 256ll + threadIdx.x; k < n; k += gridDim.x * 256ll) d[k] = s != nullptr ? s[k] : 0.f;
+}
+
 }  // namespace pvae
 
 using namespace pvae;
+
+extern "C" int pvae_gather(const void* const* srcs, const int64_t* offsets, int n_tensors, float* dst, void* stream) {
+  if (!srcs || !offsets || !dst || n_tensors < 0) return fail(PVAE_ERR_INVALID, "pvae_gather: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int base = 0; base < n_tensors; base += kGatherMax) {
+    GatherTable t;
+    t.n = std::min(kGatherMax, n_tensors - base);
+    long long biggest = 1;
+    for (int i = 0; i < t.n; ++i) {
+      t.src[i] = static_cast<const float*>(srcs[base + i]);
+      t.off[i] = offsets[base + i];
+      biggest = std::max<long long>(biggest, offsets[base + i + 1] - offsets[base + i]);
+    }
+    t.off[t.n] = offsets[base + t.n];
+    const unsigned gx = static_cast<unsigned>(std::min<long long>((biggest + 2047) / 2048, 64));
+    if (int rc = cuda_ok("gather_kernel", launch_pdl(gather_kernel, dim3(gx, t.n), dim3(256), 0, s, t, dst))) return rc;
+  }
+  return PVAE_OK;
+}
 
 extern "C" int pvae_recon_residual(const float* y, const float* x, float* g_y, float* recon, int64_t B, int64_t D,
                                    float g_scale, void* stream) {

@@ -101,7 +101,7 @@ class TrainerVAE:
         self.peer = None
         self._peer_token = 0
         assert dp_mode in ('auto', 'peer', 'nccl')
-        if self.world > 1 and dp_mode != 'nccl' and cfg.grad_clip is None and cfg.method == 'mc':
+        if self.world > 1 and dp_mode != 'nccl' and cfg.grad_clip is None and cfg.method == 'mc' and self.fused:
             try:
                 self.peer = dp.PeerExchange(self._flat_g_ext.numel(), self.device, process_group)
             except Exception as exc:  # no P2P / symmetric memory on this system
@@ -112,6 +112,7 @@ class TrainerVAE:
         elif dp_mode == 'peer' and self.world > 1:
             raise ValueError("dp_mode='peer' does not support grad_clip")
         self.r_max = torch.zeros(max(n_batches_per_epoch, 1), device=self.device)  # rate.max() of each step of the epoch
+        self._gather_tab = None
         self.kernel_events = None  # set to {} to record CUDA events around the named launches (bench.py)
         self._stream_handle = None  # fit_host pins the launch stream for the duration of its loop
         self._copy_stream = None
@@ -119,11 +120,17 @@ class TrainerVAE:
     # -- one flat fp32 buffer for parameters, gradients and Adamax state ------------------------
     def _flatten_parameters(self):
         m = self.model
-        names = ['log_rate', 'fc_enc.weight', 'fc_dec.weight']
-        if m.fc_enc.bias is not None:
-            names.append('fc_enc.bias')
+        # the fused single-call step (csrc/lin_step.cu) covers lin|lin; every other architecture runs its blocks'
+        # kernels under autograd and shares the flat-buffer exchange / clip / Adamax kernels
+        self.fused = m.cfg.enc_type == 'lin' and m.cfg.dec_type == 'lin'
         if m.fc_dec.bias is not None:
             raise NotImplementedError("decoder bias")
+        if self.fused:
+            names = ['log_rate', 'fc_enc.weight', 'fc_dec.weight']
+            if m.fc_enc.bias is not None:
+                names.append('fc_enc.bias')
+        else:
+            names = [k for k, p in m.named_parameters() if p.requires_grad]
         params = dict(m.named_parameters())
         n = sum(params[k].numel() for k in names)
         self.flat_p = torch.empty(n, device=self.device, dtype=torch.float32)
@@ -146,7 +153,7 @@ class TrainerVAE:
         if B not in self._bufs:
             K, D = self.model.cfg.n_latents, self.model.cfg.input_sz ** 2
             f = lambda *s: torch.empty(*s, device=self.device, dtype=torch.float32)
-            self._bufs[B] = dict(ws=f(self.lib.pvae_lin_step_ws_floats(B, K, D)), loss=f(4),
+            self._bufs[B] = dict(ws=f(self.lib.pvae_lin_step_ws_floats(B, K, D)) if self.fused else None, loss=f(4),
                                  nws=f(self.lib.pvae_grad_norm_ws_floats()), norm=f(2))
         return self._bufs[B]
 
@@ -175,7 +182,8 @@ class TrainerVAE:
         return out
 
     def launches_per_step(self) -> int:
-        """Kernels of libpvae_b200.so launched by one train_step."""
+        """Kernels of libpvae_b200.so launched by one train_step (fused lin|lin step; for the other architectures
+        difference pvae_launch_count() around a step)."""
         # 5 tcgen05 GEMMs (the decoder one with the residual fused in) + 2 split-K reductions (wgrad),
         # sampler fwd, loss, sampler bwd, column-sum finalize, Adamax
         n = 12
@@ -319,8 +327,8 @@ class TrainerVAE:
         seed, offset = next_philox(self.device) if philox is None else philox
         b = self._buffers(B)
         n = self.flat_p.numel()
-        if cfg.method == 'exact':
-            return self._train_step_exact(x, beta, lr, gstep, b, loss_out)
+        if cfg.method == 'exact' or not self.fused:
+            return self._train_step_autograd(x, beta, lr, gstep, b, loss_out, row_offset, (seed, offset))
         # where this step's gradients and its [loss, mse, kl] shares go
         if self.peer is not None:  # symmetric double buffer, alternating with the exchange token's parity
             self._peer_token += 1  # strictly increasing for the life of the exchange (never rewound with opt_step)
@@ -407,23 +415,41 @@ class TrainerVAE:
         etc = {'log_dr': out['log_dr'], 'r*dr': out['rate']}
         return data_out, loss, etc
 
-    def _train_step_exact(self, x, beta, lr, gstep, b, loss_out):
-        """method='exact' (main/train_vae.py:703-705): closed-form reconstruction loss, no sampling.  Not a fused
-        path: the model's own ops (our GEMM / rate / KL kernels under autograd) build the loss, the gradients are
-        gathered into the flat buffer and the usual exchange + clip + Adamax kernels follow."""
+    def _train_step_autograd(self, x, beta, lr, gstep, b, loss_out, row_offset, philox):
+        """The step for everything but fused lin|lin: method='exact' (main/train_vae.py:703-705, closed-form
+        reconstruction loss, no sampling) and the conv architectures.  The model's own blocks (our kernels under
+        autograd) build the loss; one gather kernel packs the per-parameter gradients into the flat buffer and the
+        usual exchange + clip + Adamax kernels follow."""
         cfg, m, lib, s = self.cfg, self.model, self.lib, _stream()
         names = list(self.views)
         params = dict(m.named_parameters())
         for k in names:
             params[k].grad = None
-        recon, dist_, log_dr = m.loss_recon_exact(x.reshape(x.shape[0], *m.shape[1:]))
-        kl = m.loss_kl(log_dr)
+        xin = x.reshape(x.shape[0], *m.shape[1:])
+        m.row_offset = row_offset  # data parallel: the Philox stream is keyed by the global sample index
+        m.rate_max_out = self.r_max[gstep % self.r_max.numel():][:1]
+        m.philox_override = philox
+        try:
+            if cfg.method == 'exact':
+                recon, dist_, log_dr = m.loss_recon_exact(xin)
+            else:
+                dist_, log_dr, z, y = m(xin)
+                recon = m.loss_recon(y, xin)
+            kl = m.loss_kl(log_dr)
+        finally:
+            m.row_offset, m.rate_max_out, m.philox_override = 0, None, None
         Bg = x.shape[0] * self.world
         (torch.sum(recon + beta * torch.sum(kl, dim=1)) / Bg).backward()
-        for k in names:
-            self.gviews[k].copy_(params[k].grad)
-            params[k].grad = None
         n = self.flat_p.numel()
+        if self._gather_tab is None:
+            offs, o = [], 0
+            for k in names:
+                offs.append(o)
+                o += params[k].numel()
+            offs.append(o)
+            self._gather_tab = (ctypes.c_int64 * len(offs))(*offs)
+        srcs = (ctypes.c_void_p * len(names))(*[None if params[k].grad is None else params[k].grad.data_ptr() for k in names])
+        _lib.check(lib.pvae_gather(srcs, self._gather_tab, len(names), _ptr(self._flat_g_ext), s))
         stats = self._flat_g_ext[n:n + 4]
         stats[0] = (recon.detach().sum() + beta * kl.detach().sum()) / Bg
         stats[1] = recon.detach().sum() / Bg
@@ -441,6 +467,8 @@ class TrainerVAE:
         self.opt_step += 1
         _lib.check(lib.pvae_adamax_step(_ptr(self.flat_p), _ptr(self._flat_g_ext), _ptr(self.exp_avg), _ptr(self.exp_inf), n,
                                         lr, self.opt_step, cfg.betas[0], cfg.betas[1], cfg.eps, cfg.weight_decay, _ptr(clip), s))
+        for k in names:  # the gradient tensors may be recycled now
+            params[k].grad = None
         return loss[:3]
 
     def iteration(self, data: torch.Tensor, epoch: int = 0):

@@ -103,7 +103,8 @@ class _EncodeSampleFn(torch.autograd.Function):
     backward recomputes the chain from the Philox counters."""
 
     @staticmethod
-    def forward(ctx, h, log_r, b_enc, temp, n_exp, indicator, exc_only, exit_logit, seed, offset):
+    def forward(ctx, h, log_r, b_enc, temp, n_exp, indicator, exc_only, exit_logit, seed, offset, row_offset=0,
+                rate_max=None):
         h = h.contiguous()
         B, K = h.shape
         lr = log_r.reshape(-1).contiguous()
@@ -113,16 +114,16 @@ class _EncodeSampleFn(torch.autograd.Function):
         dz = torch.empty_like(h) if (distributions.SAVE_DERIVATIVE and need) else None
         with torch.cuda.device(h.device):
             _lib.check(_lib.load().pvae_sampler_fwd(
-                _ptr(h), _ptr(lr), _ptr(b_enc), _ptr(z), _ptr(log_dr), None, None, None, None, _ptr(dz), B, K, 0, n_exp,
-                temp, indicator, int(exc_only), exit_logit, seed, offset, None, _stream()))
+                _ptr(h), _ptr(lr), _ptr(b_enc), _ptr(z), _ptr(log_dr), None, None, None, _ptr(rate_max), _ptr(dz), B, K,
+                row_offset, n_exp, temp, indicator, int(exc_only), exit_logit, seed, offset, None, _stream()))
         ctx.save_for_backward(h, lr, b_enc, dz)
-        ctx.args = (B, K, temp, n_exp, indicator, int(exc_only), exit_logit, seed, offset, log_r.shape)
+        ctx.args = (B, K, temp, n_exp, indicator, int(exc_only), exit_logit, seed, offset, log_r.shape, row_offset)
         return z, log_dr
 
     @staticmethod
     def backward(ctx, g_z, g_log_dr):
         h, lr, b_enc, dz = ctx.saved_tensors
-        B, K, temp, n_exp, indicator, exc_only, exit_logit, seed, offset, lr_shape = ctx.args
+        B, K, temp, n_exp, indicator, exc_only, exit_logit, seed, offset, lr_shape, row_offset = ctx.args
         if temp == 0.0:
             raise RuntimeError("hard counts (temp == 0) are not differentiable")
         lib = _lib.load()
@@ -135,8 +136,8 @@ class _EncodeSampleFn(torch.autograd.Function):
         with torch.cuda.device(h.device):
             _lib.check(lib.pvae_sampler_bwd(
                 _ptr(h), _ptr(lr), _ptr(b_enc), _ptr(g_z), _ptr(g_log_dr), _ptr(dz), 0.0, _ptr(g_h), _ptr(g_lr), _ptr(g_b),
-                _ptr(ws), 0, B, K, 0, n_exp, temp, indicator, exc_only, exit_logit, seed, offset, None, _stream()))
-        return g_h, g_lr.reshape(lr_shape), g_b, None, None, None, None, None, None, None
+                _ptr(ws), 0, B, K, row_offset, n_exp, temp, indicator, exc_only, exit_logit, seed, offset, None, _stream()))
+        return g_h, g_lr.reshape(lr_shape), g_b, None, None, None, None, None, None, None, None, None
 
 
 class _InferRateFn(torch.autograd.Function):
@@ -268,6 +269,11 @@ class PoissonVAE(nn.Module):
         # host mirrors of the two scalar buffers (plain attributes: no device sync to read them)
         object.__setattr__(self, '_temp_host', 1.0)
         object.__setattr__(self, '_n_exp_host', 0)
+        # set by a data-parallel trainer around a step: global index of the first local sample (keys the Philox stream),
+        # a 1-float device tensor that receives max(rate), and the (seed, offset) to use instead of the generator's next
+        object.__setattr__(self, 'row_offset', 0)
+        object.__setattr__(self, 'rate_max_out', None)
+        object.__setattr__(self, 'philox_override', None)
         self.update_n(200.0)  # main/vae.py:382
 
     # ---- reference API -------------------------------------------------------------------
@@ -294,10 +300,10 @@ class PoissonVAE(nn.Module):
                            indicator_approx=self.cfg.indicator_approx, n_exp=self._n_exp_host,
                            exit_logit=self.exit_logit)
             return dist, log_dr
-        seed, offset = next_philox(x.device)
+        seed, offset = next_philox(x.device) if self.philox_override is None else self.philox_override
         z, log_dr = _EncodeSampleFn.apply(h, self.log_rate, self.fc_enc.bias, temp, self._n_exp_host,
                                           INDICATOR_CODES[self.cfg.indicator_approx], self.cfg.exc_only,
-                                          self.exit_logit, seed, offset)
+                                          self.exit_logit, seed, offset, self.row_offset, self.rate_max_out)
         dist = _PosteriorPoisson(self, h, log_dr, self.temp if t is None else t, temp, self._n_exp_host, z)
         return dist, log_dr
 

@@ -275,3 +275,41 @@ def test_conv_vae_step_matches_reference(path):
     for name, p in model.named_parameters():
         assert p.grad is not None, name
         assert_grad_digest(p.grad.cpu().numpy(), g, name, 5e-5)
+
+
+def test_conv_trainer_steps():
+    """TrainerVAE on conv+b|lin: the flat gradient buffer the gather kernel fills equals the model's autograd
+    gradients for the same Philox state, parameters move, the loss goes down over a few steps, launches are counted."""
+    from poissonvae_b200 import _lib
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE, default_configs
+    cfg_vae, cfg_tr = default_configs("CIFAR16", "poisson", "conv+b|lin")
+    model = PoissonVAE(ConfigPoisVAE(seed=1, **cfg_vae)).cuda()
+    model.update_n(8.0)
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(64, 1, 16, 16, generator=g)
+    x = ((x - x.mean((1, 2, 3), keepdim=True)) / x.std((1, 2, 3), keepdim=True)).cuda()
+    tr = TrainerVAE(model, ConfigTrainVAE(lr=0.002, batch_size=64, epochs=50, warmup_portion=0.0, temp_anneal_portion=0.0,
+                                          temp_stop=1.0, kl_anneal_portion=0.0, kl_const_portion=0.0, kl_beta=1.0),
+                    n_batches_per_epoch=1)
+    assert not tr.fused and len(tr.views) == len(list(model.parameters()))
+    # reference gradients through the model's public API, same Philox state, eval-mode dropout on both sides
+    model.eval()
+    philox = (1234, 8)
+    model.philox_override = philox
+    dist, log_dr, z, y = model(x)
+    loss = torch.mean(model.loss_recon(y, x) + torch.sum(model.loss_kl(log_dr), dim=1))
+    loss.backward()
+    model.philox_override = None
+    want = torch.cat([p.grad.reshape(-1) for _, p in model.named_parameters()]).clone()
+    before = tr.flat_p.clone()
+    c0 = _lib.load().pvae_launch_count()
+    out = tr.train_step(x, 0, philox=philox)
+    launches = _lib.load().pvae_launch_count() - c0
+    assert_rel(tr.flat_g.cpu().numpy(), want.cpu().numpy(), rtol=1e-6, what="flat gradient buffer")
+    assert_rel(out[0].item(), loss.item(), rtol=1e-6, what="loss")
+    assert not torch.equal(before, tr.flat_p) and torch.isfinite(tr.flat_p).all()
+    assert 100 < launches < 400, launches
+    model.train()
+    losses = [tr.train_step(x, i)[0].item() for i in range(1, 40)]
+    assert np.isfinite(losses).all() and np.mean(losses[-5:]) < 0.9 * np.mean(losses[:5]), losses

@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Training-step throughput of the conv+b|lin P-VAE (BASELINE config 4: CIFAR16-shaped 16x16 patches, K = 512,
+implicit-GEMM conv encoder) on one B200, with the CPU restatement of the reference's step timed beside it.
+
+  python tools/bench_conv.py [--batch 1000] [--steps 20] [--warmup 5] [--dataset CIFAR16|MNIST] [--tf32] [--cpu_rows 32]
+
+Prints one JSON line.  Not the headline benchmark (bench.py is); this is the secondary configuration of SURVEY 8d."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def cpu_port(args, x):
+    """oracle/conv_oracle.py + the sampler/loss in plain torch on the host cores (autograd backward, no optimiser)."""
+    import torch
+    from oracle import conv_oracle
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE, default_configs
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg_vae, _ = default_configs(args.dataset, "poisson", "conv+b|lin")
+    model = PoissonVAE(ConfigPoisVAE(seed=0, **cfg_vae))
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in model.state_dict().items()}
+    xs = x[:args.cpu_rows].cpu()
+    sc = lambda v, c: c - torch.nn.functional.softplus(c - v)
+
+    def step():
+        h = conv_oracle.conv_encoder(xs, sd, args.dataset)
+        log_dr = sc(h, 10.0)
+        rate = torch.exp(sc(sd["log_rate"] + log_dr, 5.0)) + 1.19e-7
+        e = rate.new(torch.Size((args.n_exp,)) + rate.shape).exponential_()
+        z = torch.sigmoid((1 - torch.cumsum(e / rate, 0)) / 1.0).sum(0)
+        y = (z @ sd["fc_dec.weight"].T).view(xs.shape)
+        kl = torch.exp(sd["log_rate"]) * (1 + torch.exp(log_dr) * (log_dr - 1))
+        loss = torch.mean(((y - xs) ** 2).sum(dim=[1, 2, 3]) + kl.sum(1))
+        for v in sd.values():
+            v.grad = None
+        loss.backward()
+
+    step()
+    t0 = time.perf_counter()
+    n = 3
+    for _ in range(n):
+        step()
+    return args.cpu_rows * n / (time.perf_counter() - t0), os.cpu_count()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--dataset", default="CIFAR16")
+    ap.add_argument("--n_exp", type=int, default=263)
+    ap.add_argument("--tf32", action="store_true")
+    ap.add_argument("--cpu_rows", type=int, default=32)
+    ap.add_argument("--no_cpu", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="print the per-kernel time table of one step (torch profiler)")
+    args = ap.parse_args()
+    import torch
+    from poissonvae_b200 import _lib, conv, linear
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE, default_configs
+    if args.tf32:
+        conv.PRECISE = False
+        linear.PRECISE = False
+    cfg_vae, cfg_tr = default_configs(args.dataset, "poisson", "conv+b|lin")
+    model = PoissonVAE(ConfigPoisVAE(seed=0, **cfg_vae)).cuda()
+    model.update_n(200.0)
+    model._n_exp_host = args.n_exp
+    sz = model.cfg.input_sz
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(args.batch, 1, sz, sz, generator=g)
+    x = ((x - x.mean((1, 2, 3), keepdim=True)) / x.std((1, 2, 3), keepdim=True)).cuda()
+    tr = TrainerVAE(model, ConfigTrainVAE(batch_size=args.batch, epochs=1000, temp_anneal_portion=0.0, temp_stop=1.0,
+                                          kl_anneal_portion=0.0, kl_const_portion=0.0, **{k: v for k, v in cfg_tr.items()
+                                                                                         if k in ("lr", "grad_clip")}),
+                    n_batches_per_epoch=100)
+    lib = _lib.load()
+    for i in range(args.warmup):
+        tr.train_step(x, i)
+    torch.cuda.synchronize()
+    c0 = lib.pvae_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        out = tr.train_step(x, args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    host_s = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1) / args.steps
+    line = {"metric": "training samples/sec (P-VAE conv+b|lin K=512)", "value": round(args.batch / ms * 1e3, 1), "unit": "samples/s",
+            "ms_per_step": round(ms, 3), "host_ms_per_step": round(host_s / args.steps * 1e3, 3), "batch": args.batch,
+            "dataset": args.dataset, "n_exp": args.n_exp, "gpu_launches_per_step": (lib.pvae_launch_count() - c0) // args.steps,
+            "gemm": "tf32 single pass" if args.tf32 else "3xTF32", "loss": [round(v, 4) for v in out.tolist()],
+            "params": tr.flat_p.numel()}
+    if not args.no_cpu:
+        v, cores = cpu_port(args, x)
+        line["cpu_baseline"] = {"value": round(v, 2), "unit": "samples/s", "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_rows} rows, fwd + autograd bwd, torch CPU"}
+    print(json.dumps(line), flush=True)
+    if args.profile:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            tr.train_step(x, args.warmup + args.steps)
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
+
+
+if __name__ == "__main__":
+    main()
