@@ -215,8 +215,10 @@ int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, flo
  *   one call; the data gradient of a stride-1 convolution is one call on g_out with w_dgrad and mirrored offsets;
  *   of a stride-2 convolution one call per parity class of the input grid (out_step 2, the class's taps).
  *   wtaps = number of taps in w_packed's row.  Ci, Co multiples of 32.  precise: 3xTF32 (1) or single-pass TF32 (0).
- * pvae_conv_wgrad: g_wp[(widx, ci), co] = sum_{n, oh, ow} in[n, oh*stride+dy, ow*stride+dx, ci] g_out[n, oh, ow, co];
- *   ws: pvae_conv_wgrad_ws_floats(Ci, Co, ntaps) floats (split-K partials, fixed-order reduction). */
+ * pvae_conv_wgrad: g_w[co, (widx, ci)] = sum_{n, oh, ow} in[n, oh*stride+dy, ow*stride+dx, ci] g_out[n, oh, ow, co] on the
+ *   tensor cores (split over pixel blocks, partials in ws, summed in split order), then pushed through the weight
+ *   normalisation: g_weight (torch layout of `weight`), g_lognorm (Co), and g_bias (Co) = sum over pixels of g_out (an
+ *   all-ones operand slab in the same GEMM).  ws: pvae_conv_wgrad_ws_floats(Ci, Co, ntaps) floats. */
 int pvae_conv_weight_prep(const float* weight, const float* lognorm, float* w_fwd, float* w_dgrad, int Co, int Ci, int ntaps,
                           int groups, void* stream);
 int pvae_conv_weight_grad(const float* g_wp, const float* weight, const float* lognorm, float* g_weight, float* g_lognorm,
@@ -227,8 +229,9 @@ int pvae_conv_igemm(const float* in, const float* w_packed, float* out, float* o
                     int ntaps, const int* tap_dy, const int* tap_dx, const int* tap_widx, int wtaps, int precise,
                     void* stream);
 int64_t pvae_conv_wgrad_ws_floats(int Ci, int Co, int ntaps);
-int pvae_conv_wgrad(const float* in, const float* g_out, float* g_wp, float* ws, int NI, int IH, int IW, int Ci, int Co,
-                    int OH, int OW, int stride, int ntaps, const int* tap_dy, const int* tap_dx, const int* tap_widx,
+int pvae_conv_wgrad(const float* in, const float* g_out, const float* weight, const float* lognorm, float* g_weight,
+                    float* g_lognorm, float* g_bias, float* ws, int NI, int IH, int IW, int Ci, int Co, int OH, int OW,
+                    int stride, int ntaps, const int* tap_dy, const int* tap_dx, const int* tap_widx, int groups,
                     int precise, void* stream);
 
 /* Memory-bound pieces around the convolutions (csrc/conv_misc.cu).  All reductions are two fixed-order stages;

@@ -70,7 +70,7 @@ _SIGNATURES = {
     "pvae_conv_weight_grad": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "pvae_conv_igemm": (_i, [_p] * 8 + [_i] * 14 + [_p, _p, _p, _i, _i, _p]),
     "pvae_conv_wgrad_ws_floats": (_i64, [_i, _i, _i]),
-    "pvae_conv_wgrad": (_i, [_p, _p, _p, _p] + [_i] * 9 + [_p, _p, _p, _i, _p]),
+    "pvae_conv_wgrad": (_i, [_p] * 8 + [_i] * 9 + [_p, _p, _p, _i, _i, _p]),
     "pvae_reduce_ws_floats": (_i64, [_i64]),
     "pvae_silu_fwd": (_i, [_p, _p, _i64, _p]),
     "pvae_add": (_i, [_p, _p, _p, _i64, _p]),

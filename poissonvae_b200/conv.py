@@ -117,19 +117,22 @@ def conv_dgrad(g_out, w_dgrad, in_shape, k: int, stride: int, pad: int, add_pre=
     return g_in
 
 
-def conv_wgrad(x_act, g_out, k: int, stride: int, pad: int):
-    """-> g_wp (k*k*Ci, Co), rows (tap, ci)"""
+def conv_wgrad(x_act, g_out, weight, lognorm, k: int, stride: int, pad: int, groups: int = 1):
+    """-> (g_weight, g_lognorm, g_bias): weight gradient on the tensor cores, reduced and pushed through the weight
+    normalisation; the bias gradient rides along as an all-ones operand slab."""
     n, ih, iw, ci = x_act.shape
     _, oh, ow, co = g_out.shape
     lib = _lib.load()
-    g_wp = torch.empty(k * k * ci, co, device=x_act.device, dtype=torch.float32)
+    g_w = torch.empty_like(weight)
+    g_ln = torch.empty_like(lognorm) if lognorm is not None else None
+    g_b = torch.empty(co, device=x_act.device, dtype=torch.float32)
     ws = _workspace(x_act.device, lib.pvae_conv_wgrad_ws_floats(ci, co, k * k))
     taps = [(r - pad, s - pad, r * k + s) for r in range(k) for s in range(k)]
     dy, dx, wi = _ints([t[0] for t in taps]), _ints([t[1] for t in taps]), _ints([t[2] for t in taps])
     with torch.cuda.device(x_act.device):
-        _lib.check(lib.pvae_conv_wgrad(_p(x_act), _p(g_out), _p(g_wp), _p(ws), n, ih, iw, ci, co, oh, ow, stride, len(taps), dy, dx,
-                                       wi, int(PRECISE), _s()))
-    return g_wp
+        _lib.check(lib.pvae_conv_wgrad(_p(x_act), _p(g_out), _p(weight), _p(lognorm), _p(g_w), _p(g_ln), _p(g_b), _p(ws), n, ih, iw,
+                                       ci, co, oh, ow, stride, len(taps), dy, dx, wi, groups, int(PRECISE), _s()))
+    return g_w, g_ln, g_b
 
 
 def colsum(x2d):
@@ -267,19 +270,16 @@ class _CellFn(torch.autograd.Function):
         n, oh, ow, co = c2.shape
         g_c2, g_sw1, g_sb1, g_sw2, g_sb2 = _se_backward(g_y, c2, gate, hid, pool, se_w1, se_w2, eps_res)
         # second convolution
-        g_w2, g_ln2 = weight_grad(conv_wgrad(a2, g_c2, 3, 1, 1), w2, ln2, 9)
-        g_b2 = colsum(g_c2.view(-1, co))
+        g_w2, g_ln2, g_b2 = conv_wgrad(a2, g_c2, w2, ln2, 3, 1, 1)
         g_c1 = conv_dgrad(g_c2, wd2, c1.shape, 3, 1, 1, dsilu_src=c1)
         # first convolution (+ skip branch)
-        g_w1, g_ln1 = weight_grad(conv_wgrad(x_act, g_c1, 3, stride, 1), w1, ln1, 9)
-        g_b1 = colsum(g_c1.view(-1, co))
+        g_w1, g_ln1, g_b1 = conv_wgrad(x_act, g_c1, w1, ln1, 3, stride, 1)
         if stride == 1:
             g_x = conv_dgrad(g_c1, wd1, x.shape, 3, 1, 1, dsilu_src=x, add_post=g_y)
             g_sw = g_sln = g_sb = None
         else:
             ks = 2 if skip_groups > 1 else 1
-            g_sw, g_sln = weight_grad(conv_wgrad(x_act, g_y, ks, 2, 0), skip_w, skip_ln, ks * ks, skip_groups)
-            g_sb = colsum(g_y.view(-1, co))
+            g_sw, g_sln, g_sb = conv_wgrad(x_act, g_y, skip_w, skip_ln, ks, 2, 0, skip_groups)
             g_a = conv_dgrad(g_c1, wd1, x.shape, 3, 2, 1)
             g_x = conv_dgrad(g_y, wds, x.shape, ks, 2, 0, add_pre=g_a, dsilu_src=x)
         return (g_x, None, g_w1, g_ln1, g_b1, g_w2, g_ln2, g_b2, g_sw1, g_sb1, g_sw2, g_sb2, g_sw, g_sln, g_sb, None, None, None)

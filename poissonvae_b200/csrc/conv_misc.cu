@@ -114,15 +114,33 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
   }
 }
 
-// out[i] = sum_p part[p * n + i] in index order
+// out[i] = sum_p part[p * n + i]: 32 outputs x 8 slices of p per block, slices combined in a fixed order
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int P, long long n,
                                                            float scale) {
+  __shared__ float s_red[8][33];
   pdl_launch_dependents();
   pdl_wait();
-  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+  for (long long base = blockIdx.x * 32ll; base < n; base += gridDim.x * 32ll) {
+    const long long i = base + lane;
     float s = 0.f;
-    for (int p = 0; p < P; ++p) s += part[p * n + i];
-    out[i] = s * scale;
+    if (i < n) {
+      int p = q;
+      for (; p + 24 < P; p += 32) {  // four independent loads in flight
+        const float v0 = part[p * n + i], v1 = part[(p + 8) * n + i], v2 = part[(p + 16) * n + i], v3 = part[(p + 24) * n + i];
+        s += (v0 + v1) + (v2 + v3);
+      }
+      for (; p < P; p += 8) s += part[p * n + i];
+    }
+    s_red[q][lane] = s;
+    __syncthreads();
+    if (q == 0 && i < n) {
+      float t = s_red[0][lane];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) t += s_red[k][lane];
+      out[i] = t * scale;
+    }
+    __syncthreads();
   }
 }
 
@@ -139,11 +157,19 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
     const int phases = 256 / cols;
     const int c4 = cbase + threadIdx.x % cols, ph = threadIdx.x / cols;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ph < phases)
-      for (long long r = r0 + ph; r < r1; r += phases) {
+    if (ph < phases) {
+      long long r = r0 + ph;
+      for (; r + 3ll * phases < r1; r += 4ll * phases) {  // four loads in flight per thread
+        const float4 v0 = ldg4(x + r * C + 4 * c4), v1 = ldg4(x + (r + phases) * C + 4 * c4),
+                     v2 = ldg4(x + (r + 2ll * phases) * C + 4 * c4), v3 = ldg4(x + (r + 3ll * phases) * C + 4 * c4);
+        a.x += (v0.x + v1.x) + (v2.x + v3.x), a.y += (v0.y + v1.y) + (v2.y + v3.y);
+        a.z += (v0.z + v1.z) + (v2.z + v3.z), a.w += (v0.w + v1.w) + (v2.w + v3.w);
+      }
+      for (; r < r1; r += phases) {
         const float4 v = ldg4(x + r * C + 4 * c4);
         a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
       }
+    }
     s_red[threadIdx.x] = a;
     __syncthreads();
     if (threadIdx.x < cols) {
@@ -168,7 +194,15 @@ __global__ void __launch_bounds__(256) small_tn_partial_kernel(const float* __re
   for (int e = threadIdx.x; e < Ca * Cb; e += 256) {
     const int i = e / Cb, j = e % Cb;
     float s = 0.f;
-    for (long long r = r0; r < r1; ++r) s = fmaf(__ldg(a + r * Ca + i), __ldg(b + r * Cb + j), s);
+    long long r = r0;
+    for (; r + 4 <= r1; r += 4) {  // eight independent loads in flight
+      const float a0 = __ldg(a + r * Ca + i), a1 = __ldg(a + (r + 1) * Ca + i), a2 = __ldg(a + (r + 2) * Ca + i),
+                  a3 = __ldg(a + (r + 3) * Ca + i);
+      const float b0 = __ldg(b + r * Cb + j), b1 = __ldg(b + (r + 1) * Cb + j), b2 = __ldg(b + (r + 2) * Cb + j),
+                  b3 = __ldg(b + (r + 3) * Cb + j);
+      s = fmaf(a0, b0, s), s = fmaf(a1, b1, s), s = fmaf(a2, b2, s), s = fmaf(a3, b3, s);
+    }
+    for (; r < r1; ++r) s = fmaf(__ldg(a + r * Ca + i), __ldg(b + r * Cb + j), s);
     part[static_cast<long long>(blockIdx.x) * Ca * Cb + e] = s;
   }
 }
@@ -518,7 +552,7 @@ extern "C" int pvae_stem_wgrad(const float* x, const float* g_out, float* g_wpb,
   if (int rc = cuda_ok("stem_wgrad_kernel", launch_pdl(stem_wgrad_kernel, dim3(blocks), dim3(256), smem, PVAE_STREAM, x, g_out, ws, N,
                                                        IH, IW, OH, OW, Co, pad, ppb)))
     return rc;
-  return cuda_ok("sum_partials_kernel", launch_pdl(sum_partials_kernel, dim3(grid_for(10 * Co)), dim3(256), 0, PVAE_STREAM,
+  return cuda_ok("sum_partials_kernel", launch_pdl(sum_partials_kernel, dim3(grid_for(10 * Co, 32)), dim3(256), 0, PVAE_STREAM,
                                                    static_cast<const float*>(ws), g_wpb, blocks, 10ll * Co, 1.f));
 }
 
@@ -529,7 +563,7 @@ extern "C" int pvae_colsum(const float* x, float* out, float* ws, int64_t R, int
   if (int rc = cuda_ok("colsum_partial_kernel", launch_pdl(colsum_partial_kernel, dim3(blocks), dim3(256), 0, PVAE_STREAM, x, ws,
                                                            static_cast<long long>(R), C, rpb)))
     return rc;
-  return cuda_ok("sum_partials_kernel", launch_pdl(sum_partials_kernel, dim3(grid_for(C)), dim3(256), 0, PVAE_STREAM,
+  return cuda_ok("sum_partials_kernel", launch_pdl(sum_partials_kernel, dim3(grid_for(C, 32)), dim3(256), 0, PVAE_STREAM,
                                                    static_cast<const float*>(ws), out, blocks, static_cast<long long>(C), 1.f));
 }
 
@@ -540,7 +574,7 @@ extern "C" int pvae_small_tn(const float* a, const float* b, float* out, float* 
   if (int rc = cuda_ok("small_tn_partial_kernel", launch_pdl(small_tn_partial_kernel, dim3(blocks), dim3(256), 0, PVAE_STREAM, a, b, ws,
                                                              static_cast<long long>(R), Ca, Cb, rpb)))
     return rc;
-  return cuda_ok("sum_partials_kernel", launch_pdl(sum_partials_kernel, dim3(grid_for(static_cast<long long>(Ca) * Cb)), dim3(256), 0,
+  return cuda_ok("sum_partials_kernel", launch_pdl(sum_partials_kernel, dim3(grid_for(static_cast<long long>(Ca) * Cb, 32)), dim3(256), 0,
                                                    PVAE_STREAM, static_cast<const float*>(ws), out, blocks,
                                                    static_cast<long long>(Ca) * Cb, 1.f));
 }
@@ -609,6 +643,6 @@ extern "C" int pvae_layernorm_bwd(const float* g, const float* xhat, const float
   if (int rc = cuda_ok("layernorm_bwd_kernel", launch_pdl(layernorm_bwd_kernel, dim3(blocks), dim3(256), 16 * C * sizeof(float),
                                                           PVAE_STREAM, g, xhat, rstd, gamma, g_s, ws, static_cast<long long>(R), C, rpb)))
     return rc;
-  return cuda_ok("sum_partials_kernel", launch_pdl(sum_partials_kernel, dim3(grid_for(2 * C)), dim3(256), 0, PVAE_STREAM,
+  return cuda_ok("sum_partials_kernel", launch_pdl(sum_partials_kernel, dim3(grid_for(2 * C, 32)), dim3(256), 0, PVAE_STREAM,
                                                    static_cast<const float*>(ws), g_gamma_beta, blocks, 2ll * C, 1.f));
 }

@@ -252,7 +252,7 @@ struct WgradParams {
   int ntaps;
   ConvTap taps[kMaxTaps];
   int num_kb, kb_per_split;
-  float* out;  // (splits, ntaps * Ci, Co)
+  float* out;  // (splits, ntaps * Ci + 1, Co): rows (tap, ci), last row = sum over pixels of g_out (bias gradient)
 };
 
 template <int BN, bool SPLIT, int STAGES>
@@ -274,7 +274,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
   const int cblocks = p.Ci >> 5;
   const int npairs = p.ntaps * cblocks;
   const int pair0 = blockIdx.y * 4;
-  const int nslabs = min(4, npairs - pair0);
+  const int nslabs = max(0, min(4, npairs - pair0));  // slabs the TMA engine fills
+  const int ones_slab = npairs - pair0;               // in [0, 4): this row block also carries the all-ones slab whose
+                                                      // output row is sum_pixels g_out = the bias gradient
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int num_kb = max(0, min(p.num_kb, kb_begin + p.kb_per_split) - kb_begin);
 
@@ -294,12 +296,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  // unused slabs of the last row block would hold stale shared memory: zero them once (their rows are dropped
-  // anyway, but NaN bit patterns must not reach the splitter's subtraction traps - keep them finite)
+  // slabs the TMA engine does not fill: the all-ones slab (constant for the whole kernel; its lo plane comes out
+  // as zeros from the splitter) and unused ones (zeros; their rows are dropped)
   if (nslabs < 4) {
+    const uint32_t one = __float_as_uint(1.f);
     for (int s = 0; s < STAGES; ++s) {
       uint4* z = reinterpret_cast<uint4*>(smem + s * kStageBytes + nslabs * 4096);
-      for (int i = threadIdx.x; i < (4 - nslabs) * 256; i += kGemmThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = threadIdx.x; i < (4 - nslabs) * 256; i += kGemmThreads) {
+        const uint32_t v = (nslabs + i / 256 == ones_slab) ? one : 0u;
+        z[i] = make_uint4(v, v, v, v);
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -372,7 +378,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
     }
     const int quarter = warp & 3;  // rows [32 quarter, +32) = slab `quarter`
     const int pair = pair0 + quarter;
-    float* obase = p.out + static_cast<long long>(blockIdx.z) * p.ntaps * p.Ci * p.Co;
+    float* obase = p.out + static_cast<long long>(blockIdx.z) * (p.ntaps * p.Ci + 1) * p.Co;
     if (num_kb > 0) {
       mbar_wait(accum_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -410,6 +416,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
           const float* src = stg + (rr + sub) * 33 + col;
           stg4(obase + static_cast<long long>(row0 + rr + sub) * p.Co + co, make_float4(src[0], src[1], src[2], src[3]));
         }
+      } else if (pair == npairs && co < p.Co && sub == 0) {  // bias row (all 32 rows of the ones slab are equal)
+        const float* src = stg + col;
+        stg4(obase + static_cast<long long>(p.ntaps * p.Ci) * p.Co + co, make_float4(src[0], src[1], src[2], src[3]));
       }
     }
   }
@@ -492,6 +501,86 @@ __global__ void __launch_bounds__(128) conv_weight_grad_kernel(const float* __re
     g_weight[static_cast<long long>(co) * n + i] = scale * g - back * w[i];
   }
   if (threadIdx.x == 0 && g_lognorm != nullptr) g_lognorm[co] = scale * gdotv;  // sum g_w * w, w = scale * weight
+}
+
+// Sum the split partials of conv_wgrad_kernel in split order into the transposed gradient gT[co][R + 1] (row R = bias
+// gradient).  A block owns 16 rows x 32 output channels: 128-byte coalesced reads of every partial, eight in flight
+// per thread, transposed through shared memory for the store.
+__global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __restrict__ ws, int splits, float* __restrict__ gT,
+                                                                int R1, int Co) {
+  __shared__ float s_t[16][33];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int col = threadIdx.x & 31, rl = threadIdx.x >> 5;  // 8 row lanes x 2 rows
+  const int co = blockIdx.x * 32 + col;
+  const long long split_stride = static_cast<long long>(R1) * Co;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = blockIdx.y * 16 + rl + 8 * h;
+    float a = 0.f;
+    if (r < R1 && co < Co) {
+      const float* src = ws + static_cast<long long>(r) * Co + co;
+      int z = 0;
+      for (; z + 8 <= splits; z += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (z + u) * split_stride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a += v[u];
+      }
+      for (; z < splits; ++z) a += __ldg(src + z * split_stride);
+    }
+    s_t[rl + 8 * h][col] = a;
+  }
+  __syncthreads();
+  // store: thread -> (co_l = t / 8, four rows apart by 8 lanes... ) 16 consecutive r per output channel
+  const int co_l = threadIdx.x >> 3, r4 = (threadIdx.x & 7) * 2;
+  const int co_o = blockIdx.x * 32 + co_l;
+  if (co_o < Co) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int r = blockIdx.y * 16 + r4 + k;
+      if (r < R1) gT[static_cast<long long>(co_o) * R1 + r] = s_t[r4 + k][co_l];
+    }
+  }
+}
+
+// weight-normalisation backward from the transposed gradient (rows contiguous), one warp per output channel:
+//   g_lognorm[co] = sum g_w w;  g_weight = s g_w - weight s (sum g_w weight) / (r (r + eps)),  s = e^lognorm / (r + eps)
+__global__ void __launch_bounds__(256) conv_wgrad_finish_kernel(const float* __restrict__ gT, const float* __restrict__ weight,
+                                                                const float* __restrict__ lognorm, float* __restrict__ g_weight,
+                                                                float* __restrict__ g_lognorm, float* __restrict__ g_bias, int Co,
+                                                                int Ci, int ntaps, int groups) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co = blockIdx.x * 8 + warp;
+  if (co >= Co) return;
+  const int R = ntaps * Ci;
+  const float* g = gT + static_cast<long long>(co) * (R + 1);
+  const int wtaps = groups > 1 ? 1 : ntaps;
+  const int n = Ci * wtaps;
+  const int my_tap = groups > 1 ? co / (Co / groups) : 0;
+  const float* w = weight + static_cast<long long>(co) * n;
+  float ss = 0.f, gv = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const int ci = groups > 1 ? i : i / ntaps, t = groups > 1 ? my_tap : i % ntaps;
+    const float wv = __ldg(w + i);
+    ss = fmaf(wv, wv, ss);
+    gv = fmaf(__ldg(g + t * Ci + ci), wv, gv);
+  }
+  ss = warp_sum(ss), gv = warp_sum(gv);
+  const float r = sqrtf(ss);
+  const float scale = lognorm != nullptr ? expf(lognorm[co]) / (r + kF32Eps) : 1.f;
+  const float back = lognorm != nullptr ? scale * gv / (fmaxf(r, 1e-30f) * (r + kF32Eps)) : 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const int ci = groups > 1 ? i : i / ntaps, t = groups > 1 ? my_tap : i % ntaps;
+    g_weight[static_cast<long long>(co) * n + i] = scale * __ldg(g + t * Ci + ci) - back * __ldg(w + i);
+  }
+  if (lane == 0) {
+    if (g_lognorm != nullptr) g_lognorm[co] = scale * gv;
+    if (g_bias != nullptr) g_bias[co] = g[R];
+  }
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -602,7 +691,7 @@ extern "C" int pvae_conv_igemm(const float* in, const float* w_packed, float* ou
   if (precise) {
     if (BN == 128) return launch_conv<128, true, 3>(ma, mb, p, tiles, s);
     if (BN == 64) return launch_conv<64, true, 4>(ma, mb, p, tiles, s);
-    return launch_conv<32, true, 4>(ma, mb, p, tiles, s);
+    return launch_conv<32, true, 2>(ma, mb, p, tiles, s);
   }
   if (BN == 128) return launch_conv<128, false, 6>(ma, mb, p, tiles, s);
   if (BN == 64) return launch_conv<64, false, 6>(ma, mb, p, tiles, s);
@@ -611,22 +700,24 @@ extern "C" int pvae_conv_igemm(const float* in, const float* w_packed, float* ou
 
 static int wgrad_bn(int Co) { return Co % 128 == 0 ? 128 : (Co % 64 == 0 ? 64 : 32); }
 static int wgrad_max_splits(int Ci, int Co, int ntaps) {
-  const int ctas = ((ntaps * (Ci / 32) + 3) / 4) * (Co / wgrad_bn(Co));
+  const int ctas = ((ntaps * (Ci / 32) + 1 + 3) / 4) * (Co / wgrad_bn(Co));
   return std::max(1, std::min(64, (2 * 148 + ctas - 1) / ctas));
 }
 
 extern "C" int64_t pvae_conv_wgrad_ws_floats(int Ci, int Co, int ntaps) {
-  if (Ci < 32 || Co < 32 || ntaps < 1) return 0;
-  return static_cast<int64_t>(wgrad_max_splits(Ci, Co, ntaps)) * ntaps * Ci * Co;
+  if (Ci < 32 || Co < 32 || ntaps < 1) return 0;  // split partials + the reduced, transposed gradient
+  return static_cast<int64_t>(wgrad_max_splits(Ci, Co, ntaps) + 1) * (ntaps * Ci + 1) * Co;
 }
 
-extern "C" int pvae_conv_wgrad(const float* in, const float* g_out, float* g_wp, float* ws, int NI, int IH, int IW, int Ci,
-                               int Co, int OH, int OW, int stride, int ntaps, const int* tap_dy, const int* tap_dx,
-                               const int* tap_widx, int precise, void* stream) {
-  if (!in || !g_out || !g_wp || !ws) return fail(PVAE_ERR_INVALID, "pvae_conv_wgrad: null pointer");
+extern "C" int pvae_conv_wgrad(const float* in, const float* g_out, const float* weight, const float* lognorm, float* g_weight,
+                               float* g_lognorm, float* g_bias, float* ws, int NI, int IH, int IW, int Ci, int Co, int OH,
+                               int OW, int stride, int ntaps, const int* tap_dy, const int* tap_dx, const int* tap_widx,
+                               int groups, int precise, void* stream) {
+  if (!in || !g_out || !weight || !g_weight || !ws) return fail(PVAE_ERR_INVALID, "pvae_conv_wgrad: null pointer");
   if (Ci % 32 || Co % 32 || Ci < 32 || Co < 32)
     return fail(PVAE_ERR_UNSUPPORTED, "pvae_conv_wgrad: Ci=%d Co=%d must be multiples of 32", Ci, Co);
-  if (NI < 1 || stride < 1 || stride > 2) return fail(PVAE_ERR_INVALID, "pvae_conv_wgrad: bad shape");
+  if (NI < 1 || stride < 1 || stride > 2 || ntaps < 1 || groups < 1 || (groups > 1 && groups != ntaps))
+    return fail(PVAE_ERR_INVALID, "pvae_conv_wgrad: bad shape");
   WgradParams p = {};
   {
     ConvParams tmp = {};
@@ -641,11 +732,11 @@ extern "C" int pvae_conv_wgrad(const float* in, const float* g_out, float* g_wp,
   p.tiles_w = (OW + pw - 1) / pw, p.tiles_h = (OH + ph - 1) / ph;
   p.num_kb = p.tiles_w * p.tiles_h * ((NI + pi - 1) / pi);
   const int BN = wgrad_bn(Co);
-  const int row_blocks = (ntaps * (Ci / 32) + 3) / 4;
+  const int row_blocks = (ntaps * (Ci / 32) + 1 + 3) / 4;  // + the all-ones slab (bias gradient)
   int splits = std::min(p.num_kb, wgrad_max_splits(Ci, Co, ntaps));
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
-  p.out = splits > 1 ? ws : g_wp;
+  p.out = ws;
   CUtensorMap mx, mg;
   if (int rc = make_nhwc_map(&mx, in, NI, IH, IW, Ci, pw, ph, pi, stride, 1)) return rc;
   if (int rc = make_nhwc_map(&mg, g_out, NI, OH, OW, Co, pw, ph, pi, 1, 1)) return rc;
@@ -661,6 +752,12 @@ extern "C" int pvae_conv_wgrad(const float* in, const float* g_out, float* g_wp,
                                : launch_wgrad<32, false, 6>(mx, mg, p, row_blocks, splits, s));
   }
   if (rc) return rc;
-  if (splits > 1) return launch_splitk_reduce(ws, g_wp, static_cast<long long>(ntaps) * Ci * Co, splits, s);
-  return PVAE_OK;
+  const int R1 = ntaps * Ci + 1;
+  float* gT = ws + static_cast<long long>(splits) * R1 * Co;
+  if (int rc2 = cuda_ok("conv_wgrad_reduce_kernel", launch_pdl(conv_wgrad_reduce_kernel, dim3(Co / 32, (R1 + 15) / 16), dim3(256), 0, s,
+                                                               static_cast<const float*>(ws), splits, gT, R1, Co)))
+    return rc2;
+  return cuda_ok("conv_wgrad_finish_kernel", launch_pdl(conv_wgrad_finish_kernel, dim3((Co + 7) / 8), dim3(256), 0, s,
+                                                        static_cast<const float*>(gT), weight, lognorm, g_weight, g_lognorm, g_bias,
+                                                        Co, Ci, ntaps, groups));
 }

@@ -58,6 +58,8 @@ def main():
     ap.add_argument("--tf32", action="store_true")
     ap.add_argument("--cpu_rows", type=int, default=32)
     ap.add_argument("--no_cpu", action="store_true")
+    ap.add_argument("--no_pdl", action="store_true", help="disable programmatic dependent launch (per-kernel times in a "
+                    "profile are only meaningful without it: a dependent kernel's span includes its wait)")
     ap.add_argument("--profile", action="store_true", help="print the per-kernel time table of one step (torch profiler)")
     args = ap.parse_args()
     import torch
@@ -80,6 +82,8 @@ def main():
                                                                                          if k in ("lr", "grad_clip")}),
                     n_batches_per_epoch=100)
     lib = _lib.load()
+    if args.no_pdl:
+        lib.pvae_set_pdl(0)
     for i in range(args.warmup):
         tr.train_step(x, i)
     torch.cuda.synchronize()
@@ -90,11 +94,13 @@ def main():
     for i in range(args.steps):
         out = tr.train_step(x, args.warmup + i)
     e1.record()
+    enqueue_s = time.perf_counter() - t0
     torch.cuda.synchronize()
     host_s = time.perf_counter() - t0
     ms = e0.elapsed_time(e1) / args.steps
     line = {"metric": "training samples/sec (P-VAE conv+b|lin K=512)", "value": round(args.batch / ms * 1e3, 1), "unit": "samples/s",
-            "ms_per_step": round(ms, 3), "host_ms_per_step": round(host_s / args.steps * 1e3, 3), "batch": args.batch,
+            "ms_per_step": round(ms, 3), "host_ms_per_step": round(host_s / args.steps * 1e3, 3),
+            "enqueue_ms_per_step": round(enqueue_s / args.steps * 1e3, 3), "batch": args.batch,
             "dataset": args.dataset, "n_exp": args.n_exp, "gpu_launches_per_step": (lib.pvae_launch_count() - c0) // args.steps,
             "gemm": "tf32 single pass" if args.tf32 else "3xTF32", "loss": [round(v, 4) for v in out.tolist()],
             "params": tr.flat_p.numel()}
