@@ -205,7 +205,9 @@ int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, flo
  * pvae_conv_weight_prep: weight (Co, Ci, KH, KW) [torch layout] + lognorm (Co, NULL = no normalisation) ->
  *   w_fwd [co][tap][ci] and (optional) w_dgrad [ci][tap][co], tap = kh * KW + kw.  groups > 1 (= ntaps): the four
  *   1x1 stride-2 filters of FactorizedReduce stored back to back as (Co, Ci); output channel co only sees tap
- *   co / (Co / groups) of a 2x2 window.
+ *   co / (Co / groups) of a 2x2 window.  Co_pad / Ci_pad >= Co / Ci: channel counts of the packed matrices (the tensor-core
+ *   kernels want multiples of 32; the 16-channel decoder layers are zero-padded to 32); bias_pad (Co_pad, optional) receives
+ *   the zero-padded bias.  pvae_conv_wgrad's Ci / Co are the padded tensor dimensions, Ci_real / Co_real the parameter's.
  * pvae_conv_weight_grad: g_wp (ntaps * Ci, Co) [rows (tap, ci), as written by pvae_conv_wgrad] -> g_weight in the
  *   torch layout and g_lognorm, through the normalisation.
  * pvae_conv_igemm: out[n, oh*out_step+out_off_h, ow*out_step+out_off_w, :] = epilogue(sum_taps in[n, oh*stride+dy,
@@ -219,8 +221,8 @@ int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, flo
  *   tensor cores (split over pixel blocks, partials in ws, summed in split order), then pushed through the weight
  *   normalisation: g_weight (torch layout of `weight`), g_lognorm (Co), and g_bias (Co) = sum over pixels of g_out (an
  *   all-ones operand slab in the same GEMM).  ws: pvae_conv_wgrad_ws_floats(Ci, Co, ntaps) floats. */
-int pvae_conv_weight_prep(const float* weight, const float* lognorm, float* w_fwd, float* w_dgrad, int Co, int Ci, int ntaps,
-                          int groups, void* stream);
+int pvae_conv_weight_prep(const float* weight, const float* lognorm, const float* bias, float* w_fwd, float* w_dgrad,
+                          float* bias_pad, int Co, int Ci, int Co_pad, int Ci_pad, int ntaps, int groups, void* stream);
 int pvae_conv_weight_grad(const float* g_wp, const float* weight, const float* lognorm, float* g_weight, float* g_lognorm,
                           int Co, int Ci, int ntaps, int groups, void* stream);
 int pvae_conv_igemm(const float* in, const float* w_packed, float* out, float* out_act, const float* bias,
@@ -232,7 +234,7 @@ int64_t pvae_conv_wgrad_ws_floats(int Ci, int Co, int ntaps);
 int pvae_conv_wgrad(const float* in, const float* g_out, const float* weight, const float* lognorm, float* g_weight,
                     float* g_lognorm, float* g_bias, float* ws, int NI, int IH, int IW, int Ci, int Co, int OH, int OW,
                     int stride, int ntaps, const int* tap_dy, const int* tap_dx, const int* tap_widx, int groups,
-                    int precise, void* stream);
+                    int Ci_real, int Co_real, int precise, void* stream);
 
 /* Memory-bound pieces around the convolutions (csrc/conv_misc.cu).  All reductions are two fixed-order stages;
  * `ws` arguments need pvae_reduce_ws_floats(number of outputs) floats.
@@ -255,10 +257,24 @@ int pvae_stem_wgrad(const float* x, const float* g_out, float* g_wpb, float* ws,
 int pvae_colsum(const float* x, float* out, float* ws, int64_t R, int C, void* stream);
 int pvae_small_tn(const float* a, const float* b, float* out, float* ws, int64_t R, int Ca, int Cb, void* stream);
 int pvae_se_fwd(const float* c, const float* skip, const float* W1, const float* b1, const float* W2, const float* b2,
-                float eps_res, float* y, float* y_act, float* pool, float* hid, float* gate, int N, int HW, int C, int hd,
-                void* stream);
+                float eps_res, float* y, float* y_act, float* pool, float* hid, float* gate, int N, int H, int W, int C,
+                int C_real, int hd, int skip_up, void* stream);
 int pvae_se_bwd(const float* g_y, const float* c, const float* gate, const float* hid, const float* W1, const float* W2,
-                float eps_res, float* g_c, float* d2, float* d1, int N, int HW, int C, int hd, void* stream);
+                float eps_res, float* g_c, float* d2, float* d1, int N, int HW, int C, int C_real, int hd, void* stream);
+/* Decoder pieces (main/vae.py:760-789, base/common.py:35-47,211-217): nearest-neighbour resampling with ATen's index
+ * map (scale_factor 2 of the 'up' cells, size=14 for MNIST) and its gather backward (optionally times silu'(src));
+ * (N, C, P) <-> (N, P, C) permutation of fc_dec's output (+ bias, + silu copy); the final 1x1 convolution to one channel
+ * (g_wb: C + 1 floats, gradient of the normalised filter then of the bias).  C = channels in memory, C_real = the
+ * parameters' (16-channel layers are stored zero-padded to 32); pool / gate / d2 are (N, C_real). */
+int pvae_upsample_fwd(const float* x, float* out, int N, int IH, int IW, int OH, int OW, int C, void* stream);
+int pvae_upsample_bwd(const float* g_out, const float* dsilu_src, float* g_in, int N, int IH, int IW, int OH, int OW, int C,
+                      void* stream);
+int pvae_permute_cp(const float* in, const float* bias, float* out, float* out_act, int64_t N, int C, int P, int to_nhwc,
+                    void* stream);
+int pvae_head_fwd(const float* x, const float* weight, const float* lognorm, const float* bias, float* y, int64_t R, int C,
+                  int C_real, void* stream);
+int pvae_head_bwd(const float* x, const float* g_y, const float* weight, const float* lognorm, float* g_x, float* g_wb, float* ws,
+                  int64_t R, int C, int C_real, void* stream);
 int pvae_avgpool_fwd(const float* x, float* pool, int N, int HW, int C, void* stream);
 int pvae_pool_silu_bwd(const float* g_a, const float* x, const float* g_pool, float* g_x, int N, int HW, int C, void* stream);
 int pvae_bias_act(float* y, const float* bias, const float* add, int64_t R, int C, int relu, float drop_p, uint64_t seed,

@@ -1,4 +1,4 @@
-"""CPU restatement of the reference's conv encoder.  TEST INFRASTRUCTURE ONLY.
+"""CPU restatement of the reference's conv encoder and decoder.  TEST INFRASTRUCTURE ONLY.
 
 Plain torch-CPU functional code over a state_dict with the reference's key names, NCHW like the reference, any
 dtype (float64 for tight comparisons).  Each function cites the reference lines it follows.  Pinned to the
@@ -81,3 +81,34 @@ def conv_encoder(x, sd, dataset: str):
     h = res_conv_pool(h, sd, f"enc.{i}").flatten(1)
     h = res_dense(h, sd, f"enc.{i + 2}")
     return F.linear(h, sd["fc_enc.weight"], sd.get("fc_enc.bias"))
+
+
+def dec_cell(x, sd, prefix, up: bool, eps=1.0):
+    """Cell.forward base/common.py:187-192 for 'normal_dec' / 'up_dec' (n_nodes = 1): ConvLayer.forward :233-242
+    (SiLU -> [nearest 2x up-sampling] -> conv), skip = identity or up-sampling -> 1x1 conv (base/common.py:35-47)."""
+    h = F.silu(x)
+    if up:
+        skip = conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), sd, prefix + ".skip.1")
+        h = F.interpolate(h, scale_factor=2, mode="nearest")
+    else:
+        skip = x
+    h = conv2d(h, sd, prefix + ".ops.0.conv", padding=1)
+    h = se_layer(h, sd, prefix + ".se")
+    return skip + eps * h
+
+
+def conv_decoder(z, sd, dataset: str):
+    """BaseVAE.decode conv branch main/vae.py:54-58 with `_build_conv_dec` main/vae.py:760-789: z (N, K) -> (N, 1, S, S)."""
+    nch = sd["fc_dec.weight"].shape[0] // 4
+    h = F.linear(z, sd["fc_dec.weight"], sd.get("fc_dec.bias")).view(-1, nch, 2, 2)
+    n_layers = 4 if dataset.endswith("MNIST") else 3
+    h = dec_cell(h, sd, "dec.0", False)
+    i = 1
+    for layer in range(n_layers):
+        h = dec_cell(h, sd, f"dec.{i}", True)
+        h = dec_cell(h, sd, f"dec.{i + 1}", False)
+        i += 2
+        if dataset.endswith("MNIST") and layer == 2:
+            h = F.interpolate(h, size=14, mode="nearest")  # nn.Upsample(size=14)
+            i += 1
+    return conv2d(h, sd, f"dec.{i}")

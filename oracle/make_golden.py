@@ -171,10 +171,14 @@ def gen_conv(ref):
     mirror model builds bit-identical ones from cfg.seed (tests/test_conv_oracle.py checks that against the reference
     and against the checksums stored here)."""
     cases = [dict(tag="cifar16", dataset="CIFAR16", B=8, n_exp=12, temp=0.7, beta=1.5, seed=7),
-             dict(tag="mnist", dataset="MNIST", B=4, n_exp=10, temp=1.0, beta=1.0, seed=8)]
+             dict(tag="mnist", dataset="MNIST", B=4, n_exp=10, temp=1.0, beta=1.0, seed=8),
+             # conv decoder too (BASELINE config 5: conv+b|conv+b, MNIST-shaped 28x28, K = 512; and its 16x16 variant)
+             dict(tag="mnist_convdec", dataset="MNIST", B=4, n_exp=10, temp=0.5, beta=1.0, seed=9, archi="conv+b|conv+b"),
+             dict(tag="cifar16_convdec", dataset="CIFAR16", B=4, n_exp=10, temp=1.0, beta=2.0, seed=10, archi="conv+b|conv+b")]
     for c in cases:
-        cfg_vae, cfg_tr = ref.cfg.default_configs(c["dataset"], "poisson", "conv+b|lin")
-        cfg_vae.update(seed=c["seed"])
+        archi = c.get("archi", "conv+b|lin")
+        cfg_vae, cfg_tr = ref.cfg.default_configs(c["dataset"], "poisson", archi)
+        cfg_vae.update(seed=c["seed"], n_latents=512)
         model = ref.vae.PoissonVAE(ref.cfg.ConfigPoisVAE(save=False, **cfg_vae)).eval()
         perturb_conv_params(model, 100 + c["seed"])
         with torch.no_grad():
@@ -197,7 +201,7 @@ def gen_conv(ref):
         loss = torch.mean(recon + c["beta"] * torch.sum(kl, dim=1))
         loss.backward()
         rec = dict(x=x, n_exp=c["n_exp"], temp=c["temp"], beta=c["beta"], cfg_seed=c["seed"], perturb_seed=100 + c["seed"],
-                   philox_seed=2024, philox_offset=16, dataset=c["dataset"], enc_out=enc_out,
+                   philox_seed=2024, philox_offset=16, dataset=c["dataset"], archi=archi, enc_out=enc_out,
                    log_dr=log_dr.detach().numpy(), z=z.detach().numpy(), y=y.detach().numpy(), recon=recon.detach().numpy(),
                    kl=kl.detach().numpy(), loss=loss.detach().numpy(), rate=dist.rate.detach().numpy())
         names = []
@@ -207,7 +211,7 @@ def gen_conv(ref):
             rec["g_" + n], rec["gn_" + n] = d, nrm
             rec["ck_" + n] = np.array([p.detach().double().sum().item(), p.detach().double().abs().sum().item()])
         rec["param_names"] = np.array(names)
-        np.savez_compressed(os.path.join(OUT, f"conv_enc_{c['tag']}.npz"), **rec)
+        np.savez_compressed(os.path.join(OUT, f"conv_{'vae' if 'archi' in c else 'enc'}_{c['tag']}.npz"), **rec)
 
 
 def gen_scalars(ref):

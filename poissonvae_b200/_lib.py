@@ -66,11 +66,11 @@ _SIGNATURES = {
     "pvae_set_step_overlap": (_i, [_i]),
     "pvae_lin_step_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i,
                                    _u64, _u64, _p, _p, _p]),
-    "pvae_conv_weight_prep": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "pvae_conv_weight_prep": (_i, [_p] * 6 + [_i] * 6 + [_p]),
     "pvae_conv_weight_grad": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "pvae_conv_igemm": (_i, [_p] * 8 + [_i] * 14 + [_p, _p, _p, _i, _i, _p]),
     "pvae_conv_wgrad_ws_floats": (_i64, [_i, _i, _i]),
-    "pvae_conv_wgrad": (_i, [_p] * 8 + [_i] * 9 + [_p, _p, _p, _i, _i, _p]),
+    "pvae_conv_wgrad": (_i, [_p] * 8 + [_i] * 9 + [_p, _p, _p, _i, _i, _i, _i, _p]),
     "pvae_reduce_ws_floats": (_i64, [_i64]),
     "pvae_silu_fwd": (_i, [_p, _p, _i64, _p]),
     "pvae_add": (_i, [_p, _p, _p, _i64, _p]),
@@ -78,8 +78,13 @@ _SIGNATURES = {
     "pvae_stem_wgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "pvae_colsum": (_i, [_p, _p, _p, _i64, _i, _p]),
     "pvae_small_tn": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p]),
-    "pvae_se_fwd": (_i, [_p] * 6 + [_f] + [_p] * 5 + [_i, _i, _i, _i, _p]),
-    "pvae_se_bwd": (_i, [_p] * 6 + [_f] + [_p] * 3 + [_i, _i, _i, _i, _p]),
+    "pvae_se_fwd": (_i, [_p] * 6 + [_f] + [_p] * 5 + [_i] * 7 + [_p]),
+    "pvae_se_bwd": (_i, [_p] * 6 + [_f] + [_p] * 3 + [_i] * 5 + [_p]),
+    "pvae_upsample_fwd": (_i, [_p, _p] + [_i] * 6 + [_p]),
+    "pvae_upsample_bwd": (_i, [_p, _p, _p] + [_i] * 6 + [_p]),
+    "pvae_permute_cp": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _p]),
+    "pvae_head_fwd": (_i, [_p] * 5 + [_i64, _i, _i, _p]),
+    "pvae_head_bwd": (_i, [_p] * 7 + [_i64, _i, _i, _p]),
     "pvae_avgpool_fwd": (_i, [_p, _p, _i, _i, _i, _p]),
     "pvae_pool_silu_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "pvae_bias_act": (_i, [_p, _p, _p, _i64, _i, _i, _f, _u64, _u64, _p]),

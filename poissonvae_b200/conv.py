@@ -53,15 +53,23 @@ def out_size(i: int, k: int, stride: int, pad: int) -> int:
     return (i + 2 * pad - k) // stride + 1
 
 
-def weight_prep(weight, lognorm, ntaps: int, groups: int = 1, need_dgrad: bool = True):
-    """-> (w_fwd [co][tap][ci], w_dgrad [ci][tap][co]) of the weight-normalised filter, base/common.py:426-431."""
-    co = weight.shape[0]
-    ci = weight.shape[1]
-    w_fwd = torch.empty(co, ntaps * ci, device=weight.device, dtype=torch.float32)
-    w_dg = torch.empty(ci, ntaps * co, device=weight.device, dtype=torch.float32) if need_dgrad else None
+def pad32(c: int) -> int:
+    """Channel count in memory: the tensor-core kernels work on multiples of 32 (16-channel decoder layers are zero-padded)."""
+    return (c + 31) // 32 * 32
+
+
+def weight_prep(weight, lognorm, bias, ntaps: int, groups: int = 1, need_dgrad: bool = True):
+    """-> (w_fwd [co][tap][ci], w_dgrad [ci][tap][co], bias) of the weight-normalised filter (base/common.py:426-431),
+    channel counts zero-padded to multiples of 32."""
+    co, ci = weight.shape[0], weight.shape[1]
+    cop, cip = pad32(co), pad32(ci)
+    w_fwd = torch.empty(cop, ntaps * cip, device=weight.device, dtype=torch.float32)
+    w_dg = torch.empty(cip, ntaps * cop, device=weight.device, dtype=torch.float32) if need_dgrad else None
+    b_pad = torch.empty(cop, device=weight.device, dtype=torch.float32) if bias is not None else None
     with torch.cuda.device(weight.device):
-        _lib.check(_lib.load().pvae_conv_weight_prep(_p(weight), _p(lognorm), _p(w_fwd), _p(w_dg), co, ci, ntaps, groups, _s()))
-    return w_fwd, w_dg
+        _lib.check(_lib.load().pvae_conv_weight_prep(_p(weight), _p(lognorm), _p(bias), _p(w_fwd), _p(w_dg), _p(b_pad), co, ci, cop,
+                                                     cip, ntaps, groups, _s()))
+    return w_fwd, w_dg, b_pad
 
 
 def weight_grad(g_wp, weight, lognorm, ntaps: int, groups: int = 1):
@@ -131,8 +139,9 @@ def conv_wgrad(x_act, g_out, weight, lognorm, k: int, stride: int, pad: int, gro
     dy, dx, wi = _ints([t[0] for t in taps]), _ints([t[1] for t in taps]), _ints([t[2] for t in taps])
     with torch.cuda.device(x_act.device):
         _lib.check(lib.pvae_conv_wgrad(_p(x_act), _p(g_out), _p(weight), _p(lognorm), _p(g_w), _p(g_ln), _p(g_b), _p(ws), n, ih, iw,
-                                       ci, co, oh, ow, stride, len(taps), dy, dx, wi, groups, int(PRECISE), _s()))
-    return g_w, g_ln, g_b
+                                       ci, co, oh, ow, stride, len(taps), dy, dx, wi, groups, weight.shape[1], weight.shape[0],
+                                       int(PRECISE), _s()))
+    return g_w, g_ln, g_b[:weight.shape[0]]
 
 
 def colsum(x2d):
@@ -162,6 +171,23 @@ def silu(x):
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().pvae_silu_fwd(_p(x), _p(out), x.numel(), _s()))
     return out
+
+
+def upsample(x, oh: int, ow: int):
+    """nearest-neighbour resampling of an NHWC map (nn.Upsample(mode='nearest'))"""
+    n, ih, iw, c = x.shape
+    out = torch.empty(n, oh, ow, c, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().pvae_upsample_fwd(_p(x), _p(out), n, ih, iw, oh, ow, c, _s()))
+    return out
+
+
+def upsample_bwd(g_out, ih: int, iw: int, dsilu_src=None):
+    n, oh, ow, c = g_out.shape
+    g_in = torch.empty(n, ih, iw, c, device=g_out.device, dtype=torch.float32)
+    with torch.cuda.device(g_out.device):
+        _lib.check(_lib.load().pvae_upsample_bwd(_p(g_out), _p(dsilu_src), _p(g_in), n, ih, iw, oh, ow, c, _s()))
+    return g_in
 
 
 def _check_input(x, name="x"):
@@ -206,29 +232,29 @@ class _StemFn(torch.autograd.Function):
         return None, g_w, g_ln, g_wpb[9], None
 
 
-def _se_forward(c2, skip, se_w1, se_b1, se_w2, se_b2, eps_res):
+def _se_forward(c2, skip, se_w1, se_b1, se_w2, se_b2, eps_res, skip_up=False):
     n, h, w, ch = c2.shape
-    hd = se_w1.shape[0]
+    hd, cr = se_w1.shape[0], se_w2.shape[0]
     y = torch.empty_like(c2)
     y_act = torch.empty_like(c2)
-    pool = torch.empty(n, ch, device=c2.device, dtype=torch.float32)
+    pool = torch.empty(n, cr, device=c2.device, dtype=torch.float32)
     hid = torch.empty(n, hd, device=c2.device, dtype=torch.float32)
-    gate = torch.empty(n, ch, device=c2.device, dtype=torch.float32)
+    gate = torch.empty(n, cr, device=c2.device, dtype=torch.float32)
     with torch.cuda.device(c2.device):
         _lib.check(_lib.load().pvae_se_fwd(_p(c2), _p(skip), _p(se_w1), _p(se_b1), _p(se_w2), _p(se_b2), eps_res, _p(y), _p(y_act),
-                                           _p(pool), _p(hid), _p(gate), n, h * w, ch, hd, _s()))
+                                           _p(pool), _p(hid), _p(gate), n, h, w, ch, cr, hd, int(skip_up), _s()))
     return y, y_act, pool, hid, gate
 
 
 def _se_backward(g_y, c2, gate, hid, pool, se_w1, se_w2, eps_res):
     n, h, w, ch = c2.shape
-    hd = se_w1.shape[0]
+    hd, cr = se_w1.shape[0], se_w2.shape[0]
     g_c2 = torch.empty_like(c2)
-    d2 = torch.empty(n, ch, device=c2.device, dtype=torch.float32)
+    d2 = torch.empty(n, cr, device=c2.device, dtype=torch.float32)
     d1 = torch.empty(n, hd, device=c2.device, dtype=torch.float32)
     with torch.cuda.device(c2.device):
         _lib.check(_lib.load().pvae_se_bwd(_p(g_y), _p(c2), _p(gate), _p(hid), _p(se_w1), _p(se_w2), eps_res, _p(g_c2), _p(d2),
-                                           _p(d1), n, h * w, ch, hd, _s()))
+                                           _p(d1), n, h * w, ch, cr, hd, _s()))
     g_w2, g_b2 = small_tn(d2, hid), colsum(d2)
     g_w1, g_b1 = small_tn(d1, pool), colsum(d1)
     return g_c2, g_w1, g_b1, g_w2, g_b2
@@ -246,16 +272,16 @@ class _CellFn(torch.autograd.Function):
         co = w1.shape[0]
         if x_act is None:
             x_act = silu(x)
-        wf1, wd1 = weight_prep(w1, ln1, 9)
-        wf2, wd2 = weight_prep(w2, ln2, 9)
-        c1, a2 = conv_fwd(x_act, wf1, b1, 3, stride, 1, co, want_act=True)
-        c2, _ = conv_fwd(a2, wf2, b2, 3, 1, 1, co)
+        wf1, wd1, bp1 = weight_prep(w1, ln1, b1, 9)
+        wf2, wd2, bp2 = weight_prep(w2, ln2, b2, 9)
+        c1, a2 = conv_fwd(x_act, wf1, bp1, 3, stride, 1, co, want_act=True)
+        c2, _ = conv_fwd(a2, wf2, bp2, 3, 1, 1, co)
         if stride == 1:
             skip, wfs, wds = x, None, None
         else:
             ks = 2 if skip_groups > 1 else 1
-            wfs, wds = weight_prep(skip_w, skip_ln, ks * ks, skip_groups)
-            skip, _ = conv_fwd(x_act, wfs, skip_b, ks, 2, 0, co)
+            wfs, wds, bps = weight_prep(skip_w, skip_ln, skip_b, ks * ks, skip_groups)
+            skip, _ = conv_fwd(x_act, wfs, bps, ks, 2, 0, co)
         y, y_act, pool, hid, gate = _se_forward(c2, skip, se_w1, se_b1, se_w2, se_b2, eps_res)
         ctx.save_for_backward(x, x_act, c1, a2, c2, pool, hid, gate, w1, ln1, w2, ln2, se_w1, se_w2, skip_w, skip_ln, wd1, wd2, wds)
         ctx.cfg = (stride, skip_groups, eps_res)
@@ -285,6 +311,129 @@ class _CellFn(torch.autograd.Function):
         return (g_x, None, g_w1, g_ln1, g_b1, g_w2, g_ln2, g_b2, g_sw1, g_sb1, g_sw2, g_sb2, g_sw, g_sln, g_sb, None, None, None)
 
 
+class _DecCellFn(torch.autograd.Function):
+    """Cell.forward base/common.py:187-192 for the decoder cell types, n_nodes = 1: 'normal_dec' (SiLU -> 3x3 conv, identity
+    skip) and 'up_dec' (SiLU -> nearest 2x up-sampling -> 3x3 conv; skip = up-sampling -> 1x1 conv, base/common.py:35-47,
+    211-217).  The 1x1 skip convolution commutes with the nearest up-sampling, so it runs on the small map and the
+    squeeze-excitation kernel reads it through the up-sampling index map."""
+
+    @staticmethod
+    def forward(ctx, x, x_act, w, ln, b, se_w1, se_b1, se_w2, se_b2, skip_w, skip_ln, skip_b, up, eps_res):
+        x = _check_input(x)
+        n, h, wd_, _ = x.shape
+        cop = pad32(w.shape[0])
+        if x_act is None:
+            x_act = silu(x)
+        wf, wd, bp = weight_prep(w, ln, b, 9)
+        if up:
+            au = upsample(x_act, 2 * h, 2 * wd_)
+            c, _ = conv_fwd(au, wf, bp, 3, 1, 1, cop)
+            wfs, wds, bps = weight_prep(skip_w, skip_ln, skip_b, 1)
+            skip, _ = conv_fwd(x, wfs, bps, 1, 1, 0, cop)
+        else:
+            au, wds = None, None
+            c, _ = conv_fwd(x_act, wf, bp, 3, 1, 1, cop)
+            skip = x
+        y, y_act, pool, hid, gate = _se_forward(c, skip, se_w1, se_b1, se_w2, se_b2, eps_res, skip_up=bool(up))
+        ctx.save_for_backward(x, x_act, au, c, pool, hid, gate, w, ln, se_w1, se_w2, skip_w, skip_ln, wd, wds)
+        ctx.cfg = (bool(up), eps_res)
+        ctx.mark_non_differentiable(y_act)
+        return y, y_act
+
+    @staticmethod
+    def backward(ctx, g_y, _g_act):
+        x, x_act, au, c, pool, hid, gate, w, ln, se_w1, se_w2, skip_w, skip_ln, wd, wds = ctx.saved_tensors
+        up, eps_res = ctx.cfg
+        g_y = g_y.contiguous()
+        n, h, wd_, _ = x.shape
+        g_c, g_sw1, g_sb1, g_sw2, g_sb2 = _se_backward(g_y, c, gate, hid, pool, se_w1, se_w2, eps_res)
+        if up:
+            g_w, g_ln, g_b = conv_wgrad(au, g_c, w, ln, 3, 1, 1)
+            g_au = conv_dgrad(g_c, wd, au.shape, 3, 1, 1)
+            t = upsample_bwd(g_au, h, wd_, dsilu_src=x)  # gradient through SiLU -> up-sampling
+            g_s = upsample_bwd(g_y, h, wd_)
+            g_kw, g_kln, g_kb = conv_wgrad(x, g_s, skip_w, skip_ln, 1, 1, 0)
+            g_x = conv_dgrad(g_s, wds, x.shape, 1, 1, 0, add_post=t)
+        else:
+            g_w, g_ln, g_b = conv_wgrad(x_act, g_c, w, ln, 3, 1, 1)
+            g_x = conv_dgrad(g_c, wd, x.shape, 3, 1, 1, dsilu_src=x, add_post=g_y)
+            g_kw = g_kln = g_kb = None
+        return g_x, None, g_w, g_ln, g_b, g_sw1, g_sb1, g_sw2, g_sb2, g_kw, g_kln, g_kb, None, None
+
+
+class _UpsampleFn(torch.autograd.Function):
+    """nn.Upsample(size=...) between decoder cells (main/vae.py:779-780): resamples the map and its SiLU hint."""
+
+    @staticmethod
+    def forward(ctx, x, x_act, oh, ow):
+        x = _check_input(x)
+        ctx.in_hw = (x.shape[1], x.shape[2])
+        out = upsample(x, oh, ow)
+        out_act = upsample(x_act, oh, ow) if x_act is not None else silu(out)
+        ctx.mark_non_differentiable(out_act)
+        return out, out_act
+
+    @staticmethod
+    def backward(ctx, g, _g_act):
+        return upsample_bwd(g.contiguous(), *ctx.in_hw), None, None, None
+
+
+class _DecInputFn(torch.autograd.Function):
+    """fc_dec's output (N, C * P) + bias, viewed as (N, C, 2, 2) NCHW by the reference (main/vae.py:56-57), into the NHWC
+    map the decoder cells work on (+ its SiLU hint)."""
+
+    @staticmethod
+    def forward(ctx, h, bias, ch, p):
+        h = _check_input(h)
+        n = h.shape[0]
+        side = int(round(math.sqrt(p)))
+        y = torch.empty(n, side, side, ch, device=h.device, dtype=torch.float32)
+        y_act = torch.empty_like(y)
+        with torch.cuda.device(h.device):
+            _lib.check(_lib.load().pvae_permute_cp(_p(h), _p(bias), _p(y), _p(y_act), n, ch, p, 1, _s()))
+        ctx.dims = (n, ch, p, bias is not None)
+        ctx.mark_non_differentiable(y_act)
+        return y, y_act
+
+    @staticmethod
+    def backward(ctx, g_y, _g_act):
+        n, ch, p, has_bias = ctx.dims
+        g_y = g_y.contiguous()
+        g_h = torch.empty(n, ch * p, device=g_y.device, dtype=torch.float32)
+        with torch.cuda.device(g_y.device):
+            _lib.check(_lib.load().pvae_permute_cp(_p(g_y), None, _p(g_h), None, n, ch, p, 0, _s()))
+        return g_h, (colsum(g_h) if has_bias else None), None, None
+
+
+class _HeadFn(torch.autograd.Function):
+    """The decoder's last layer: weight-normalised 1x1 convolution to one channel (main/vae.py:782-789) -> (N, 1, H, W)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, lognorm, bias):
+        x = _check_input(x)
+        n, h, w, cm = x.shape
+        y = torch.empty(n, 1, h, w, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().pvae_head_fwd(_p(x), _p(weight), _p(lognorm), _p(bias), _p(y), n * h * w, cm, weight.shape[1], _s()))
+        ctx.save_for_backward(x, weight, lognorm)
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        x, weight, lognorm = ctx.saved_tensors
+        n, h, w, cm = x.shape
+        cr = weight.shape[1]
+        lib = _lib.load()
+        g_y = g_y.contiguous()
+        g_x = torch.empty_like(x)
+        g_wb = torch.empty(cm + 1, device=x.device, dtype=torch.float32)
+        ws = _workspace(x.device, lib.pvae_reduce_ws_floats(cm + 1))
+        with torch.cuda.device(x.device):
+            _lib.check(lib.pvae_head_bwd(_p(x), _p(g_y), _p(weight), _p(lognorm), _p(g_x), _p(g_wb), _p(ws), n * h * w, cm, cr, _s()))
+        g_w, g_ln = weight_grad(g_wb, weight, lognorm, 1)
+        return g_x, g_w, g_ln, g_wb[cm:cm + 1]
+
+
 class _ResConvPoolFn(torch.autograd.Function):
     """ResConvPool main/vae.py:682-706: mean over the (k x k) map + eps * 'valid' k x k convolution of silu(x) -> (N, C)."""
 
@@ -297,7 +446,7 @@ class _ResConvPoolFn(torch.autograd.Function):
             x_act = silu(x)
         assert weight.shape[2] == h and weight.shape[3] == w, "ResConvPool expects the 'valid' convolution to cover the whole map"
         assert eps_res == 1.0
-        wf, _ = weight_prep(weight, lognorm, h * w, need_dgrad=False)
+        wf, _, _ = weight_prep(weight, lognorm, None, h * w, need_dgrad=False)
         pool = torch.empty(n, ch, device=x.device, dtype=torch.float32)
         lib = _lib.load()
         with torch.cuda.device(x.device):
@@ -431,19 +580,23 @@ class StrideReduce(nn.Module):
 
 
 class Cell(nn.Module):
-    """base/common.py:145-192, encoder cell types."""
+    """base/common.py:145-192: 'normal_pre' / 'down_enc' (encoder, n_nodes = 2) and 'normal_dec' / 'up_dec' (decoder, n_nodes = 1)."""
 
     def __init__(self, ci, co, cell_type, n_nodes=2, act_fn='swish', use_bn=False, use_se=True, scale=1.0, eps=1.0,
                  reg_lognorm=True, factorized=True):
         super().__init__()
-        if cell_type not in ('normal_pre', 'down_enc'):
-            raise NotImplementedError(f"cell type {cell_type}: the conv decoder is not built yet")
-        if use_bn or not use_se or n_nodes != 2:
-            raise NotImplementedError("Cell: only n_nodes=2, use_se=True, use_bn=False (the reference defaults)")
-        self.stride = 1 if cell_type.startswith('normal') else MULT
+        if cell_type not in ('normal_pre', 'down_enc', 'normal_dec', 'up_dec'):
+            raise NotImplementedError(f"cell type {cell_type}")
+        self.decoder = cell_type.endswith('_dec')
+        if use_bn or not use_se or n_nodes != (1 if self.decoder else 2):
+            raise NotImplementedError("Cell: use_se=True, use_bn=False, n_nodes 2 (encoder) / 1 (decoder): the reference defaults")
+        self.stride = {'normal': 1, 'down': MULT, 'up': -1}[cell_type.split('_')[0]]
         if self.stride == 1:
             assert ci == co
             self.skip = nn.Identity()
+        elif self.stride == -1:  # get_skip_connection base/common.py:35-47
+            self.skip = nn.Sequential(nn.Upsample(scale_factor=MULT, mode='nearest'),
+                                      Conv2D(ci, int(ci / MULT), 1, reg_lognorm=reg_lognorm))
         else:
             self.skip = FactorizedReduce(ci, co, reg_lognorm) if factorized else StrideReduce(ci, co, reg_lognorm)
         self.ops = nn.ModuleList()
@@ -455,7 +608,15 @@ class Cell(nn.Module):
 
     def forward(self, xs):
         x, x_act = xs if isinstance(xs, tuple) else (xs, None)
-        c1, c2 = self.ops[0].conv, self.ops[1].conv
+        fc = self.se.fc
+        c1 = self.ops[0].conv
+        if self.decoder:
+            up = self.stride == -1
+            sk = self.skip[1] if up else None
+            return _DecCellFn.apply(x, x_act, c1.weight, c1.lognorm, c1.bias, fc[0].weight, fc[0].bias, fc[2].weight, fc[2].bias,
+                                    sk.weight if up else None, sk.lognorm if up else None, sk.bias if up else None, up,
+                                    float(self.eps))
+        c2 = self.ops[1].conv
         if self.stride == 1:
             sw = sln = sb = None
             groups = 1
@@ -465,7 +626,6 @@ class Cell(nn.Module):
         else:
             sw, sln, sb = self.skip.conv.weight, self.skip.conv.lognorm, self.skip.conv.bias
             groups = 1
-        fc = self.se.fc
         return _CellFn.apply(x, x_act, c1.weight, c1.lognorm, c1.bias, c2.weight, c2.lognorm, c2.bias, fc[0].weight, fc[0].bias,
                              fc[2].weight, fc[2].bias, sw, sln, sb, self.stride, groups, float(self.eps))
 
@@ -537,3 +697,43 @@ def build_conv_enc(nch: int, dataset: str, act_fn='swish', eps=1.0, reg_lognorm=
         nch *= MULT
     layers.extend([ResConvPool(nch, act_fn=act_fn, eps=eps, kernel_size=4, reg_lognorm=reg_lognorm), _Flatten()])
     return nn.Sequential(*layers, ResDenseLayer(nch))
+
+
+class Resample(nn.Upsample):
+    """nn.Upsample(size=...) inside the decoder's nn.Sequential (main/vae.py:779-780), on (map, SiLU hint) pairs."""
+
+    def forward(self, xs):
+        x, x_act = xs if isinstance(xs, tuple) else (xs, None)
+        size = (self.size, self.size) if isinstance(self.size, int) else tuple(self.size)
+        return _UpsampleFn.apply(x, x_act, size[0], size[1])
+
+
+class Head(Conv2D):
+    """The final Conv2D(nch, 1, kernel_size=1) of the decoder (main/vae.py:782-789)."""
+
+    def forward(self, xs):
+        x = xs[0] if isinstance(xs, tuple) else xs
+        return _HeadFn.apply(x, self.weight, self.lognorm, self.bias)
+
+
+def build_conv_dec(nch: int, dataset: str, act_fn='swish', eps=1.0, reg_lognorm=True) -> nn.Sequential:
+    """main/vae.py:760-789 (`_build_conv_dec`)."""
+    if dataset.endswith('MNIST'):
+        n_layers = 4
+    elif dataset in ('vH16', 'CIFAR16', 'BALLS'):
+        n_layers = 3
+    else:
+        raise ValueError(dataset)
+    kws = dict(n_nodes=1, act_fn=act_fn, use_bn=False, use_se=True, scale=1.0, eps=eps, reg_lognorm=reg_lognorm)
+    layers = [Cell(nch, nch, 'normal_dec', **kws)]
+    for i in range(n_layers):
+        layers.extend([Cell(nch, nch // MULT, 'up_dec', **kws), Cell(nch // MULT, nch // MULT, 'normal_dec', **kws)])
+        nch //= MULT
+        if dataset.endswith('MNIST') and i == 2:
+            layers.append(Resample(size=14))
+    return nn.Sequential(*layers, Head(nch, 1, 1, reg_lognorm=True, padding='valid'))
+
+
+def decoder_input(h, bias, nch: int, spat: int = 2):
+    """fc_dec output (N, nch * spat^2) [+ bias] -> ((N, spat, spat, nch) NHWC map, its SiLU hint)"""
+    return _DecInputFn.apply(h, bias, nch, spat * spat)

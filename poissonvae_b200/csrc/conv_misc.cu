@@ -239,11 +239,14 @@ __device__ __forceinline__ void image_channel_sums(const float* __restrict__ v1,
 }
 
 // ---- squeeze-excitation gate + residual: y = skip + eps * c * sigmoid(W2 relu(W1 mean_hw(c) + b1) + b2) -----
+// C = channels in memory (multiple of 32), Cr <= C = channels of the parameters (the rest is zero padding).
+// skip_up: skip is a (N, H/2, W/2, C) map read with nearest-neighbour 2x up-sampling (decoder 'up' cells).
 __global__ void __launch_bounds__(256) se_fwd_kernel(const float* __restrict__ c, const float* __restrict__ skip,
                                                      const float* __restrict__ W1, const float* __restrict__ b1,
                                                      const float* __restrict__ W2, const float* __restrict__ b2, float eps_res,
                                                      float* __restrict__ y, float* __restrict__ y_act, float* __restrict__ pool,
-                                                     float* __restrict__ hid, float* __restrict__ gate, int HW, int C, int hd) {
+                                                     float* __restrict__ hid, float* __restrict__ gate, int H, int W, int C, int Cr,
+                                                     int hd, int skip_up) {
   __shared__ __align__(16) float s_red[1024];
   __shared__ __align__(16) float s_pool[256];
   __shared__ float s_hid[32];
@@ -251,34 +254,43 @@ __global__ void __launch_bounds__(256) se_fwd_kernel(const float* __restrict__ c
   pdl_launch_dependents();
   pdl_wait();
   const long long n = blockIdx.x;
+  const int HW = H * W;
   const float* cn = c + n * HW * C;
   image_channel_sums(cn, nullptr, HW, C, s_red, s_pool);
   if (threadIdx.x < C) {
     s_pool[threadIdx.x] *= 1.f / static_cast<float>(HW);
-    pool[n * C + threadIdx.x] = s_pool[threadIdx.x];
+    if (threadIdx.x < Cr) pool[n * Cr + threadIdx.x] = s_pool[threadIdx.x];
   }
   __syncthreads();
   if (threadIdx.x < hd) {
     float a = b1[threadIdx.x];
-    for (int k = 0; k < C; ++k) a = fmaf(W1[threadIdx.x * C + k], s_pool[k], a);
+    for (int k = 0; k < Cr; ++k) a = fmaf(W1[threadIdx.x * Cr + k], s_pool[k], a);
     a = fmaxf(a, 0.f);
     s_hid[threadIdx.x] = a;
     hid[n * hd + threadIdx.x] = a;
   }
   __syncthreads();
   if (threadIdx.x < C) {
-    float a = b2[threadIdx.x];
-    for (int j = 0; j < hd; ++j) a = fmaf(W2[threadIdx.x * hd + j], s_hid[j], a);
-    a = sigmoid_m(a);
+    float a = 0.f;
+    if (threadIdx.x < Cr) {
+      a = b2[threadIdx.x];
+      for (int j = 0; j < hd; ++j) a = fmaf(W2[threadIdx.x * hd + j], s_hid[j], a);
+      a = sigmoid_m(a);
+      gate[n * Cr + threadIdx.x] = a;
+    }
     s_gate[threadIdx.x] = a;
-    gate[n * C + threadIdx.x] = a;
   }
   __syncthreads();
   const int c4n = C >> 2;
   for (int i = threadIdx.x; i < HW * c4n; i += 256) {
     const int c4 = i % c4n;
     const long long off = n * HW * C + 4ll * i;
-    const float4 cv = ldg4(c + off), sv = ldg4(skip + off);
+    long long soff = off;
+    if (skip_up) {
+      const int pix = i / c4n, h = pix / W, w = pix % W;
+      soff = ((n * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)) * C + 4ll * c4;
+    }
+    const float4 cv = ldg4(c + off), sv = ldg4(skip + soff);
     const float4 gt = reinterpret_cast<const float4*>(s_gate)[c4];
     const float4 r = make_float4(fmaf(eps_res * cv.x, gt.x, sv.x), fmaf(eps_res * cv.y, gt.y, sv.y),
                                  fmaf(eps_res * cv.z, gt.z, sv.z), fmaf(eps_res * cv.w, gt.w, sv.w));
@@ -292,25 +304,30 @@ __global__ void __launch_bounds__(256) se_bwd_kernel(const float* __restrict__ g
                                                      const float* __restrict__ gate, const float* __restrict__ hid,
                                                      const float* __restrict__ W1, const float* __restrict__ W2, float eps_res,
                                                      float* __restrict__ g_c, float* __restrict__ d2, float* __restrict__ d1, int HW,
-                                                     int C, int hd) {
+                                                     int C, int Cr, int hd) {
   __shared__ __align__(16) float s_red[1024];
   __shared__ __align__(16) float s_gs[256];
   __shared__ float s_d1[32];
   __shared__ __align__(16) float s_gpool[256];
+  __shared__ __align__(16) float s_gate[256];
   pdl_launch_dependents();
   pdl_wait();
   const long long n = blockIdx.x;
   image_channel_sums(g_y + n * HW * C, c + n * HW * C, HW, C, s_red, s_gs);
   if (threadIdx.x < C) {
-    const float gt = gate[n * C + threadIdx.x];
-    const float v = eps_res * s_gs[threadIdx.x] * gt * (1.f - gt);
+    float v = 0.f, gt = 0.f;
+    if (threadIdx.x < Cr) {
+      gt = gate[n * Cr + threadIdx.x];
+      v = eps_res * s_gs[threadIdx.x] * gt * (1.f - gt);
+      d2[n * Cr + threadIdx.x] = v;
+    }
     s_gs[threadIdx.x] = v;
-    d2[n * C + threadIdx.x] = v;
+    s_gate[threadIdx.x] = gt;
   }
   __syncthreads();
   if (threadIdx.x < hd) {
     float a = 0.f;
-    for (int k = 0; k < C; ++k) a = fmaf(W2[k * hd + threadIdx.x], s_gs[k], a);
+    for (int k = 0; k < Cr; ++k) a = fmaf(W2[k * hd + threadIdx.x], s_gs[k], a);
     a = hid[n * hd + threadIdx.x] > 0.f ? a : 0.f;
     s_d1[threadIdx.x] = a;
     d1[n * hd + threadIdx.x] = a;
@@ -318,7 +335,8 @@ __global__ void __launch_bounds__(256) se_bwd_kernel(const float* __restrict__ g
   __syncthreads();
   if (threadIdx.x < C) {
     float a = 0.f;
-    for (int j = 0; j < hd; ++j) a = fmaf(W1[j * C + threadIdx.x], s_d1[j], a);
+    if (threadIdx.x < Cr)
+      for (int j = 0; j < hd; ++j) a = fmaf(W1[j * Cr + threadIdx.x], s_d1[j], a);
     s_gpool[threadIdx.x] = a / static_cast<float>(HW);
   }
   __syncthreads();
@@ -327,7 +345,7 @@ __global__ void __launch_bounds__(256) se_bwd_kernel(const float* __restrict__ g
     const int c4 = i % c4n;
     const long long off = n * HW * C + 4ll * i;
     const float4 gv = ldg4(g_y + off);
-    const float4 gt = ldg4(gate + n * C + 4 * c4);
+    const float4 gt = reinterpret_cast<const float4*>(s_gate)[c4];
     const float4 gp = reinterpret_cast<const float4*>(s_gpool)[c4];
     stg4(g_c + off, make_float4(fmaf(eps_res * gv.x, gt.x, gp.x), fmaf(eps_res * gv.y, gt.y, gp.y),
                                 fmaf(eps_res * gv.z, gt.z, gp.z), fmaf(eps_res * gv.w, gt.w, gp.w)));
@@ -500,6 +518,149 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
 }
 
+// ---- nearest-neighbour resampling (nn.Upsample(mode='nearest'): scale_factor 2 in the decoder's 'up' cells,
+// size=14 from 16x16 for MNIST, main/vae.py:779-780).  Source index as ATen computes it: min(floorf(dst * scale), in - 1),
+// scale = (float) in / out.
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in) { return min(static_cast<int>(floorf(dst * scale)), in - 1); }
+
+__global__ void __launch_bounds__(256) upsample_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, long long N, int IH,
+                                                           int IW, int OH, int OW, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c4n = C >> 2;
+  const float sh = static_cast<float>(IH) / static_cast<float>(OH), sw = static_cast<float>(IW) / static_cast<float>(OW);
+  const long long total = N * OH * OW * c4n;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const int c4 = static_cast<int>(i % c4n);
+    const long long pix = i / c4n;
+    const int ow = static_cast<int>(pix % OW), oh = static_cast<int>((pix / OW) % OH);
+    const long long n = pix / (static_cast<long long>(OW) * OH);
+    const int ih = nearest_src(oh, sh, IH), iw = nearest_src(ow, sw, IW);
+    stg4(out + 4 * i, ldg4(x + ((n * IH + ih) * IW + iw) * C + 4 * c4));
+  }
+}
+
+// g_in[n, ih, iw, :] = (sum of g_out over the output pixels that read (ih, iw)) * silu'(dsilu_src) : a gather, no atomics
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ dsilu_src,
+                                                           float* __restrict__ g_in, long long N, int IH, int IW, int OH, int OW,
+                                                           int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c4n = C >> 2;
+  const float sh = static_cast<float>(IH) / static_cast<float>(OH), sw = static_cast<float>(IW) / static_cast<float>(OW);
+  const long long total = N * IH * IW * c4n;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const int c4 = static_cast<int>(i % c4n);
+    const long long pix = i / c4n;
+    const int iw = static_cast<int>(pix % IW), ih = static_cast<int>((pix / IW) % IH);
+    const long long n = pix / (static_cast<long long>(IW) * IH);
+    // candidate output range: a little wider than ih / scale, filtered by the exact forward map
+    const int oh_lo = max(0, static_cast<int>(floorf(ih / sh)) - 1), oh_hi = min(OH - 1, static_cast<int>(floorf((ih + 1) / sh)) + 1);
+    const int ow_lo = max(0, static_cast<int>(floorf(iw / sw)) - 1), ow_hi = min(OW - 1, static_cast<int>(floorf((iw + 1) / sw)) + 1);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      if (nearest_src(oh, sh, IH) != ih) continue;
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        if (nearest_src(ow, sw, IW) != iw) continue;
+        const float4 g = ldg4(g_out + ((n * OH + oh) * OW + ow) * C + 4 * c4);
+        a.x += g.x, a.y += g.y, a.z += g.z, a.w += g.w;
+      }
+    }
+    if (dsilu_src != nullptr) {
+      const float4 xv = ldg4(dsilu_src + 4 * i);
+      a.x *= dsilu_m(xv.x), a.y *= dsilu_m(xv.y), a.z *= dsilu_m(xv.z), a.w *= dsilu_m(xv.w);
+    }
+    stg4(g_in + 4 * i, a);
+  }
+}
+
+// ---- (N, C, P) <-> (N, P, C): fc_dec's output viewed as (N, C, 2, 2) NCHW (main/vae.py:56-57) into NHWC, + bias -----
+__global__ void __launch_bounds__(256) permute_cp_kernel(const float* __restrict__ in, const float* __restrict__ bias,
+                                                         float* __restrict__ out, float* __restrict__ out_act, long long N, int C,
+                                                         int P, int to_nhwc) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = N * C * P;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    // i indexes the OUTPUT (coalesced stores)
+    const long long n = i / (static_cast<long long>(C) * P);
+    const int r = static_cast<int>(i % (static_cast<long long>(C) * P));
+    int c, p2;
+    if (to_nhwc) p2 = r / C, c = r % C; else c = r / P, p2 = r % P;
+    const int src = to_nhwc ? c * P + p2 : p2 * C + c;
+    float v = __ldg(in + n * C * P + src);
+    if (bias != nullptr) v += __ldg(bias + (to_nhwc ? src : r));
+    out[i] = v;
+    if (out_act != nullptr) out_act[i] = silu_m(v);
+  }
+}
+
+// ---- decoder head: weight-normalised 1x1 convolution to ONE channel (main/vae.py:782-789) -------------------
+// y[pix] = sum_{c < Cr} x[pix, c] wn[c] + b; x has C >= Cr channels in memory
+__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ weight,
+                                                       const float* __restrict__ lognorm, const float* __restrict__ bias,
+                                                       float* __restrict__ y, long long R, int C, int Cr) {
+  __shared__ float s_w[256];
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x < 32) {
+    float ss = 0.f;
+    for (int k = threadIdx.x; k < Cr; k += 32) ss = fmaf(weight[k], weight[k], ss);
+    ss = warp_sum(ss);
+    const float scale = expf(lognorm[0]) / (sqrtf(ss) + kF32Eps);
+    for (int k = threadIdx.x; k < C; k += 32) s_w[k] = k < Cr ? scale * weight[k] : 0.f;
+  }
+  __syncthreads();
+  const float b = bias != nullptr ? bias[0] : 0.f;
+  const int c4n = Cr >> 2;
+  for (long long r = blockIdx.x * 256ll + threadIdx.x; r < R; r += gridDim.x * 256ll) {
+    float a = b;
+    for (int k = 0; k < c4n; ++k) {
+      const float4 v = ldg4(x + r * C + 4 * k);
+      a = fmaf(v.x, s_w[4 * k], a), a = fmaf(v.y, s_w[4 * k + 1], a), a = fmaf(v.z, s_w[4 * k + 2], a), a = fmaf(v.w, s_w[4 * k + 3], a);
+    }
+    y[r] = a;
+  }
+}
+
+// g_x[pix, c] = g_y[pix] wn[c]; part[b][c] = sum over block b's pixels of g_y x[pix, c] (c < C), part[b][C] = sum g_y
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g_y,
+                                                       const float* __restrict__ weight, const float* __restrict__ lognorm,
+                                                       float* __restrict__ g_x, float* __restrict__ part, long long R, int C, int Cr,
+                                                       long long rows_per_block) {
+  __shared__ float s_w[256];
+  __shared__ float s_red[8][260];
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x < 32) {
+    float ss = 0.f;
+    for (int k = threadIdx.x; k < Cr; k += 32) ss = fmaf(weight[k], weight[k], ss);
+    ss = warp_sum(ss);
+    const float scale = expf(lognorm[0]) / (sqrtf(ss) + kF32Eps);
+    for (int k = threadIdx.x; k < C; k += 32) s_w[k] = k < Cr ? scale * weight[k] : 0.f;
+  }
+  __syncthreads();
+  // C <= 256 a multiple of 32: thread -> channel c = t % C, row phase t / C
+  const int c = threadIdx.x % C, ph = threadIdx.x / C, phases = 256 / C;
+  const long long r0 = blockIdx.x * rows_per_block, r1 = min(R, r0 + rows_per_block);
+  float acc = 0.f, accb = 0.f;
+  for (long long r = r0 + ph; r < r1; r += phases) {
+    const float g = __ldg(g_y + r);
+    acc = fmaf(g, __ldg(x + r * C + c), acc);
+    accb += g;
+    g_x[r * C + c] = g * s_w[c];
+  }
+  s_red[ph][c] = acc;
+  if (c == 0) s_red[ph][256] = accb;
+  __syncthreads();
+  if (threadIdx.x <= C) {
+    const int k = threadIdx.x == C ? 256 : threadIdx.x;
+    float t = 0.f;
+    for (int q = 0; q < phases; ++q) t += s_red[q][k];
+    part[static_cast<long long>(blockIdx.x) * (C + 1) + threadIdx.x] = t;
+  }
+}
+
 static unsigned grid_for(long long work_items, int per_block = 256, int max_blocks = 148 * 8) {
   return static_cast<unsigned>(std::max<long long>(1, std::min<long long>((work_items + per_block - 1) / per_block, max_blocks)));
 }
@@ -580,22 +741,68 @@ extern "C" int pvae_small_tn(const float* a, const float* b, float* out, float* 
 }
 
 extern "C" int pvae_se_fwd(const float* c, const float* skip, const float* W1, const float* b1, const float* W2, const float* b2,
-                           float eps_res, float* y, float* y_act, float* pool, float* hid, float* gate, int N, int HW, int C, int hd,
-                           void* stream) {
+                           float eps_res, float* y, float* y_act, float* pool, float* hid, float* gate, int N, int H, int W, int C,
+                           int C_real, int hd, int skip_up, void* stream) {
   if (!c || !skip || !W1 || !b1 || !W2 || !b2 || !y || !pool || !hid || !gate) return fail(PVAE_ERR_INVALID, "pvae_se_fwd: null pointer");
-  if (N < 1 || HW < 1 || C < 16 || C > 256 || C % 4 || 256 % (C / 4) || hd < 1 || hd > 32)
-    return fail(PVAE_ERR_UNSUPPORTED, "pvae_se_fwd: C=%d hd=%d", C, hd);
+  if (N < 1 || H < 1 || W < 1 || C < 16 || C > 256 || C % 4 || 256 % (C / 4) || hd < 1 || hd > 32 || C_real < 4 || C_real > C ||
+      C_real % 4 || (skip_up && ((H | W) & 1)))
+    return fail(PVAE_ERR_UNSUPPORTED, "pvae_se_fwd: C=%d C_real=%d hd=%d H=%d W=%d", C, C_real, hd, H, W);
   return cuda_ok("se_fwd_kernel", launch_pdl(se_fwd_kernel, dim3(N), dim3(256), 0, PVAE_STREAM, c, skip, W1, b1, W2, b2, eps_res, y,
-                                             y_act, pool, hid, gate, HW, C, hd));
+                                             y_act, pool, hid, gate, H, W, C, C_real, hd, skip_up));
 }
 
 extern "C" int pvae_se_bwd(const float* g_y, const float* c, const float* gate, const float* hid, const float* W1, const float* W2,
-                           float eps_res, float* g_c, float* d2, float* d1, int N, int HW, int C, int hd, void* stream) {
+                           float eps_res, float* g_c, float* d2, float* d1, int N, int HW, int C, int C_real, int hd, void* stream) {
   if (!g_y || !c || !gate || !hid || !W1 || !W2 || !g_c || !d2 || !d1) return fail(PVAE_ERR_INVALID, "pvae_se_bwd: null pointer");
-  if (N < 1 || HW < 1 || C < 16 || C > 256 || C % 4 || 256 % (C / 4) || hd < 1 || hd > 32)
-    return fail(PVAE_ERR_UNSUPPORTED, "pvae_se_bwd: C=%d hd=%d", C, hd);
+  if (N < 1 || HW < 1 || C < 16 || C > 256 || C % 4 || 256 % (C / 4) || hd < 1 || hd > 32 || C_real < 4 || C_real > C || C_real % 4)
+    return fail(PVAE_ERR_UNSUPPORTED, "pvae_se_bwd: C=%d C_real=%d hd=%d", C, C_real, hd);
   return cuda_ok("se_bwd_kernel", launch_pdl(se_bwd_kernel, dim3(N), dim3(256), 0, PVAE_STREAM, g_y, c, gate, hid, W1, W2, eps_res,
-                                             g_c, d2, d1, HW, C, hd));
+                                             g_c, d2, d1, HW, C, C_real, hd));
+}
+
+extern "C" int pvae_upsample_fwd(const float* x, float* out, int N, int IH, int IW, int OH, int OW, int C, void* stream) {
+  if (!x || !out || N < 1 || IH < 1 || IW < 1 || OH < 1 || OW < 1 || C < 4 || C % 4) return fail(PVAE_ERR_INVALID, "pvae_upsample_fwd: bad argument");
+  const long long total = static_cast<long long>(N) * OH * OW * (C / 4);
+  return cuda_ok("upsample_fwd_kernel", launch_pdl(upsample_fwd_kernel, dim3(grid_for(total)), dim3(256), 0, PVAE_STREAM, x, out,
+                                                   static_cast<long long>(N), IH, IW, OH, OW, C));
+}
+
+extern "C" int pvae_upsample_bwd(const float* g_out, const float* dsilu_src, float* g_in, int N, int IH, int IW, int OH, int OW, int C,
+                                 void* stream) {
+  if (!g_out || !g_in || N < 1 || IH < 1 || IW < 1 || OH < 1 || OW < 1 || C < 4 || C % 4) return fail(PVAE_ERR_INVALID, "pvae_upsample_bwd: bad argument");
+  const long long total = static_cast<long long>(N) * IH * IW * (C / 4);
+  return cuda_ok("upsample_bwd_kernel", launch_pdl(upsample_bwd_kernel, dim3(grid_for(total)), dim3(256), 0, PVAE_STREAM, g_out,
+                                                   dsilu_src, g_in, static_cast<long long>(N), IH, IW, OH, OW, C));
+}
+
+extern "C" int pvae_permute_cp(const float* in, const float* bias, float* out, float* out_act, int64_t N, int C, int P, int to_nhwc,
+                               void* stream) {
+  if (!in || !out || N < 1 || C < 1 || P < 1) return fail(PVAE_ERR_INVALID, "pvae_permute_cp: bad argument");
+  return cuda_ok("permute_cp_kernel", launch_pdl(permute_cp_kernel, dim3(grid_for(N * C * P)), dim3(256), 0, PVAE_STREAM, in, bias, out,
+                                                 out_act, static_cast<long long>(N), C, P, to_nhwc));
+}
+
+extern "C" int pvae_head_fwd(const float* x, const float* weight, const float* lognorm, const float* bias, float* y, int64_t R, int C,
+                             int C_real, void* stream) {
+  if (!x || !weight || !lognorm || !y || R < 1 || C < 4 || C > 256 || C % 4 || C_real < 4 || C_real > C || C_real % 4)
+    return fail(PVAE_ERR_INVALID, "pvae_head_fwd: bad argument");
+  return cuda_ok("head_fwd_kernel", launch_pdl(head_fwd_kernel, dim3(grid_for(R)), dim3(256), 0, PVAE_STREAM, x, weight, lognorm, bias, y,
+                                               static_cast<long long>(R), C, C_real));
+}
+
+// g_wb (C + 1): gradient of the normalised filter (first C_real entries meaningful) and, last, of the bias;
+// ws >= pvae_reduce_ws_floats(C + 1)
+extern "C" int pvae_head_bwd(const float* x, const float* g_y, const float* weight, const float* lognorm, float* g_x, float* g_wb,
+                             float* ws, int64_t R, int C, int C_real, void* stream) {
+  if (!x || !g_y || !weight || !lognorm || !g_x || !g_wb || !ws || R < 1 || C < 32 || C > 256 || 256 % C || C_real < 4 || C_real > C)
+    return fail(PVAE_ERR_INVALID, "pvae_head_bwd: bad argument");
+  long long rpb;
+  const int blocks = partial_blocks(R, 256, &rpb);
+  if (int rc = cuda_ok("head_bwd_kernel", launch_pdl(head_bwd_kernel, dim3(blocks), dim3(256), 0, PVAE_STREAM, x, g_y, weight, lognorm,
+                                                     g_x, ws, static_cast<long long>(R), C, C_real, rpb)))
+    return rc;
+  return cuda_ok("sum_partials_kernel", launch_pdl(sum_partials_kernel, dim3(grid_for(C + 1, 32)), dim3(256), 0, PVAE_STREAM,
+                                                   static_cast<const float*>(ws), g_wb, blocks, static_cast<long long>(C + 1), 1.f));
 }
 
 extern "C" int pvae_avgpool_fwd(const float* x, float* pool, int N, int HW, int C, void* stream) {

@@ -439,33 +439,38 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
 // One block per output channel.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) conv_weight_prep_kernel(const float* __restrict__ weight, const float* __restrict__ lognorm,
-                                                               float* __restrict__ w_fwd, float* __restrict__ w_dgrad, int Co,
-                                                               int Ci, int ntaps, int groups) {
+                                                               const float* __restrict__ bias, float* __restrict__ w_fwd,
+                                                               float* __restrict__ w_dgrad, float* __restrict__ bias_pad, int Co,
+                                                               int Ci, int CoP, int CiP, int ntaps, int groups) {
   __shared__ float s_part[4];
   pdl_launch_dependents();
   pdl_wait();
-  const int co = blockIdx.x;
+  const int co = blockIdx.x;  // < CoP; channels >= Co are padding (the tensor-core kernels want multiples of 32): zeros
+  const bool real = co < Co;
   const int wtaps = groups > 1 ? 1 : ntaps;  // taps stored in `weight`
   const int n = Ci * wtaps;
-  const float* w = weight + static_cast<long long>(co) * n;  // (ci, tap) order, torch (Co, Ci, KH, KW)
+  const float* w = weight + static_cast<long long>(real ? co : 0) * n;  // (ci, tap) order, torch (Co, Ci, KH, KW)
   float ss = 0.f;
   for (int i = threadIdx.x; i < n; i += 128) ss = fmaf(w[i], w[i], ss);
   ss = warp_sum(ss);
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = ss;
   __syncthreads();
   const float nrm = sqrtf((s_part[0] + s_part[1]) + (s_part[2] + s_part[3]));
-  const float scale = lognorm != nullptr ? expf(lognorm[co]) / (nrm + kF32Eps) : 1.f;
+  const float scale = !real ? 0.f : (lognorm != nullptr ? expf(lognorm[co]) / (nrm + kF32Eps) : 1.f);
   const int my_tap = groups > 1 ? co / (Co / groups) : -1;
-  for (int i = threadIdx.x; i < Ci * ntaps; i += 128) {
-    const int t = i / Ci, ci = i % Ci;
-    float v;
-    if (groups > 1)
-      v = t == my_tap ? scale * w[ci] : 0.f;
-    else
-      v = scale * w[ci * ntaps + t];
-    w_fwd[(static_cast<long long>(co) * ntaps + t) * Ci + ci] = v;
-    if (w_dgrad != nullptr) w_dgrad[(static_cast<long long>(ci) * ntaps + t) * Co + co] = v;
+  for (int i = threadIdx.x; i < CiP * ntaps; i += 128) {
+    const int t = i / CiP, ci = i % CiP;
+    float v = 0.f;
+    if (real && ci < Ci) {
+      if (groups > 1)
+        v = t == my_tap ? scale * w[ci] : 0.f;
+      else
+        v = scale * w[ci * ntaps + t];
+    }
+    w_fwd[(static_cast<long long>(co) * ntaps + t) * CiP + ci] = v;
+    if (w_dgrad != nullptr) w_dgrad[(static_cast<long long>(ci) * ntaps + t) * CoP + co] = v;
   }
+  if (threadIdx.x == 0 && bias_pad != nullptr) bias_pad[co] = (real && bias != nullptr) ? bias[co] : 0.f;
 }
 
 // backward of the above: from g_w packed as (ntaps * Ci, Co) rows (tap, ci):
@@ -550,13 +555,13 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
 __global__ void __launch_bounds__(256) conv_wgrad_finish_kernel(const float* __restrict__ gT, const float* __restrict__ weight,
                                                                 const float* __restrict__ lognorm, float* __restrict__ g_weight,
                                                                 float* __restrict__ g_lognorm, float* __restrict__ g_bias, int Co,
-                                                                int Ci, int ntaps, int groups) {
+                                                                int Ci, int CiP, int ntaps, int groups) {
   pdl_launch_dependents();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co = blockIdx.x * 8 + warp;
-  if (co >= Co) return;
-  const int R = ntaps * Ci;
+  if (co >= Co) return;       // Co, Ci: the parameter's real channel counts; CiP: padded rows per tap in gT
+  const int R = ntaps * CiP;
   const float* g = gT + static_cast<long long>(co) * (R + 1);
   const int wtaps = groups > 1 ? 1 : ntaps;
   const int n = Ci * wtaps;
@@ -567,7 +572,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_finish_kernel(const float* __r
     const int ci = groups > 1 ? i : i / ntaps, t = groups > 1 ? my_tap : i % ntaps;
     const float wv = __ldg(w + i);
     ss = fmaf(wv, wv, ss);
-    gv = fmaf(__ldg(g + t * Ci + ci), wv, gv);
+    gv = fmaf(__ldg(g + t * CiP + ci), wv, gv);
   }
   ss = warp_sum(ss), gv = warp_sum(gv);
   const float r = sqrtf(ss);
@@ -575,7 +580,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_finish_kernel(const float* __r
   const float back = lognorm != nullptr ? scale * gv / (fmaxf(r, 1e-30f) * (r + kF32Eps)) : 0.f;
   for (int i = lane; i < n; i += 32) {
     const int ci = groups > 1 ? i : i / ntaps, t = groups > 1 ? my_tap : i % ntaps;
-    g_weight[static_cast<long long>(co) * n + i] = scale * __ldg(g + t * Ci + ci) - back * __ldg(w + i);
+    g_weight[static_cast<long long>(co) * n + i] = scale * __ldg(g + t * CiP + ci) - back * __ldg(w + i);
   }
   if (lane == 0) {
     if (g_lognorm != nullptr) g_lognorm[co] = scale * gv;
@@ -643,12 +648,14 @@ static int fill_taps(ConvParams& p, int ntaps, const int* dy, const int* dx, con
 
 using namespace pvae;
 
-extern "C" int pvae_conv_weight_prep(const float* weight, const float* lognorm, float* w_fwd, float* w_dgrad, int Co, int Ci,
-                                     int ntaps, int groups, void* stream) {
-  if (!weight || !w_fwd || Co < 1 || Ci < 1 || ntaps < 1 || ntaps > kMaxTaps || groups < 1 || (groups > 1 && (groups != ntaps || Co % groups)))
+extern "C" int pvae_conv_weight_prep(const float* weight, const float* lognorm, const float* bias, float* w_fwd, float* w_dgrad,
+                                     float* bias_pad, int Co, int Ci, int Co_pad, int Ci_pad, int ntaps, int groups, void* stream) {
+  if (!weight || !w_fwd || Co < 1 || Ci < 1 || Co_pad < Co || Ci_pad < Ci || ntaps < 1 || ntaps > kMaxTaps || groups < 1 ||
+      (groups > 1 && (groups != ntaps || Co % groups)))
     return fail(PVAE_ERR_INVALID, "pvae_conv_weight_prep: bad argument");
-  return cuda_ok("conv_weight_prep_kernel", launch_pdl(conv_weight_prep_kernel, dim3(Co), dim3(128), 0, static_cast<cudaStream_t>(stream),
-                                                       weight, lognorm, w_fwd, w_dgrad, Co, Ci, ntaps, groups));
+  return cuda_ok("conv_weight_prep_kernel", launch_pdl(conv_weight_prep_kernel, dim3(Co_pad), dim3(128), 0, static_cast<cudaStream_t>(stream),
+                                                       weight, lognorm, bias, w_fwd, w_dgrad, bias_pad, Co, Ci, Co_pad, Ci_pad, ntaps,
+                                                       groups));
 }
 
 extern "C" int pvae_conv_weight_grad(const float* g_wp, const float* weight, const float* lognorm, float* g_weight,
@@ -712,8 +719,9 @@ extern "C" int64_t pvae_conv_wgrad_ws_floats(int Ci, int Co, int ntaps) {
 extern "C" int pvae_conv_wgrad(const float* in, const float* g_out, const float* weight, const float* lognorm, float* g_weight,
                                float* g_lognorm, float* g_bias, float* ws, int NI, int IH, int IW, int Ci, int Co, int OH,
                                int OW, int stride, int ntaps, const int* tap_dy, const int* tap_dx, const int* tap_widx,
-                               int groups, int precise, void* stream) {
+                               int groups, int Ci_real, int Co_real, int precise, void* stream) {
   if (!in || !g_out || !weight || !g_weight || !ws) return fail(PVAE_ERR_INVALID, "pvae_conv_wgrad: null pointer");
+  if (Ci_real < 1 || Ci_real > Ci || Co_real < 1 || Co_real > Co) return fail(PVAE_ERR_INVALID, "pvae_conv_wgrad: bad real channel counts");
   if (Ci % 32 || Co % 32 || Ci < 32 || Co < 32)
     return fail(PVAE_ERR_UNSUPPORTED, "pvae_conv_wgrad: Ci=%d Co=%d must be multiples of 32", Ci, Co);
   if (NI < 1 || stride < 1 || stride > 2 || ntaps < 1 || groups < 1 || (groups > 1 && groups != ntaps))
@@ -757,7 +765,7 @@ extern "C" int pvae_conv_wgrad(const float* in, const float* g_out, const float*
   if (int rc2 = cuda_ok("conv_wgrad_reduce_kernel", launch_pdl(conv_wgrad_reduce_kernel, dim3(Co / 32, (R1 + 15) / 16), dim3(256), 0, s,
                                                                static_cast<const float*>(ws), splits, gT, R1, Co)))
     return rc2;
-  return cuda_ok("conv_wgrad_finish_kernel", launch_pdl(conv_wgrad_finish_kernel, dim3((Co + 7) / 8), dim3(256), 0, s,
+  return cuda_ok("conv_wgrad_finish_kernel", launch_pdl(conv_wgrad_finish_kernel, dim3((Co_real + 7) / 8), dim3(256), 0, s,
                                                         static_cast<const float*>(gT), weight, lognorm, g_weight, g_lognorm, g_bias,
-                                                        Co, Ci, ntaps, groups));
+                                                        Co_real, Ci_real, Ci, ntaps, groups));
 }

@@ -123,8 +123,8 @@ class TrainerVAE:
         # the fused single-call step (csrc/lin_step.cu) covers lin|lin; every other architecture runs its blocks'
         # kernels under autograd and shares the flat-buffer exchange / clip / Adamax kernels
         self.fused = m.cfg.enc_type == 'lin' and m.cfg.dec_type == 'lin'
-        if m.fc_dec.bias is not None:
-            raise NotImplementedError("decoder bias")
+        if self.fused and m.fc_dec.bias is not None:
+            raise NotImplementedError("decoder bias on the fused lin|lin step")
         if self.fused:
             names = ['log_rate', 'fc_enc.weight', 'fc_dec.weight']
             if m.fc_enc.bias is not None:
@@ -425,7 +425,7 @@ class TrainerVAE:
         params = dict(m.named_parameters())
         for k in names:
             params[k].grad = None
-        xin = x.reshape(x.shape[0], *m.shape[1:])
+        xin = x.reshape(x.shape[0], 1, m.cfg.input_sz, m.cfg.input_sz)
         m.row_offset = row_offset  # data parallel: the Philox stream is keyed by the global sample index
         m.rate_max_out = self.r_max[gstep % self.r_max.numel():][:1]
         m.philox_override = philox

@@ -36,14 +36,14 @@ class ConfigPoisVAE:
                  dec_norm: bool = False, **unused):
         assert prior_log_dist in ('cte', 'uniform', 'normal')
         assert indicator_approx in INDICATOR_CODES
-        if enc_type not in ('lin', 'conv') or dec_type != 'lin':
-            raise NotImplementedError("poissonvae_b200 covers lin|lin and conv|lin (SURVEY.md section 8); "
+        if enc_type not in ('lin', 'conv') or dec_type not in ('lin', 'conv'):
+            raise NotImplementedError("poissonvae_b200 covers the lin and conv encoders / decoders (SURVEY.md section 8); "
                                       f"got {enc_type}|{dec_type}")
         if init_dist != 'Normal':
             raise NotImplementedError(init_dist)
         if enc_norm or dec_norm:
             raise NotImplementedError("weight-normalised fc_enc / fc_dec (off by default in the reference)")
-        if enc_type == 'conv' and (use_bn or not use_se or activation_fn not in ('swish', 'silu') or res_eps != 1.0):
+        if 'conv' in (enc_type, dec_type) and (use_bn or not use_se or activation_fn not in ('swish', 'silu') or res_eps != 1.0):
             raise NotImplementedError("conv encoder: the reference defaults only (swish, SE on, BatchNorm off, res_eps 1)")
         if input_sz is None:  # ConfigVAE._init_input_sz main/config_vae.py:97-110
             input_sz = 28 if dataset.endswith('MNIST') else 16
@@ -71,20 +71,22 @@ class ConfigPoisVAE:
 
 
 def default_configs(dataset: str = 'vH16', model_type: str = 'poisson', archi_type: str = 'lin|lin'):
-    """main/config_vae.py:373-465 restricted to poisson with a linear decoder (lin|lin, conv|lin, with or without +b)."""
+    """main/config_vae.py:373-465 restricted to poisson with lin / conv encoders and decoders (with or without +b)."""
     archi = archi_type.strip('<>')
-    if model_type != 'poisson' or archi not in ('lin|lin', 'lin+b|lin', 'conv|lin', 'conv+b|lin'):
+    enc, _, dec = archi.partition('|')
+    if model_type != 'poisson' or enc.split('+')[0] not in ('lin', 'conv') or dec.split('+')[0] not in ('lin', 'conv'):
         raise NotImplementedError((model_type, archi_type))
-    enc = archi.split('|')[0]
-    cfg_vae = dict(dataset=dataset, n_ch=32, n_latents=512, prior_clamp=-4, fit_prior=True, enc_type=enc.split('+')[0],
-                   dec_type='lin', enc_bias=enc.endswith('+b'), dec_bias=False, init_dist='Normal', init_scale=0.05)
+    lin_dec = dec.split('+')[0] == 'lin'
+    cfg_vae = dict(dataset=dataset, n_ch=32, n_latents=512 if lin_dec else 10, prior_clamp=-4 if lin_dec else -2,
+                   fit_prior=True, enc_type=enc.split('+')[0], dec_type=dec.split('+')[0], enc_bias=enc.endswith('+b'),
+                   dec_bias=dec.endswith('+b'), init_dist='Normal', init_scale=0.05 if lin_dec else 0.1)
     if dataset in ('vH16', 'CIFAR16'):
         cfg_tr = dict(lr=0.005, batch_size=1000, epochs=3000 if dataset == 'vH16' else 1500, grad_clip=None)
     elif dataset.endswith('MNIST'):
         cfg_tr = dict(lr=0.002, epochs=200 if dataset == 'EMNIST' else 400, batch_size=100, warm_restart=0, grad_clip=1000)
     else:
         raise NotImplementedError(dataset)
-    cfg_tr['kl_const_portion'] = 0.0
+    cfg_tr['kl_const_portion'] = 0.0 if lin_dec else 0.01
     return cfg_vae, cfg_tr
 
 
@@ -261,8 +263,15 @@ class PoissonVAE(nn.Module):
             self.fc_enc = _Linear(self.enc[-1].dim, K, bias=cfg.enc_bias)
         else:
             self.fc_enc = _Linear(D, K, bias=cfg.enc_bias)  # main/vae.py:253-259
-        self.shape = (-1, 1, cfg.input_sz, cfg.input_sz)
-        self.fc_dec = _Linear(K, D, bias=cfg.dec_bias)  # main/vae.py:306-312
+        if cfg.dec_type == 'conv':  # main/vae.py:264-279
+            from . import conv
+            nch = cfg.n_ch * 8
+            self.shape = (-1, nch, 2, 2)
+            self.fc_dec = _Linear(K, nch * 4, bias=cfg.dec_bias)
+            self.dec = conv.build_conv_dec(nch, cfg.dataset, cfg.activation_fn, cfg.res_eps)
+        else:
+            self.shape = (-1, 1, cfg.input_sz, cfg.input_sz)
+            self.fc_dec = _Linear(K, D, bias=cfg.dec_bias)  # main/vae.py:306-312
         self._init_prior()
         self._init_weight()
         self.register_buffer('n_exp', torch.tensor(0))  # main/vae.py:378-381
@@ -340,6 +349,10 @@ class PoissonVAE(nn.Module):
         return self.fc_enc(self._features(x))
 
     def decode(self, z):  # main/vae.py:54-66
+        if self.cfg.dec_type == 'conv':
+            from . import conv
+            h = linear(z, self.fc_dec.weight, None)  # the bias joins in the NCHW -> NHWC kernel
+            return self.dec(conv.decoder_input(h, self.fc_dec.bias, self.shape[1], self.shape[2]))
         return self.fc_dec(z).view(*self.shape)
 
     def loss_recon(self, y, x):  # main/vae.py:68-72
@@ -408,6 +421,7 @@ class PoissonVAE(nn.Module):
             return
         dist = torch.distributions.Normal(loc=0, scale=self.cfg.init_scale)
         self.fc_enc.weight.copy_(dist.sample(self.fc_enc.weight.shape))
-        self.fc_dec.weight.copy_(dist.sample(self.fc_dec.weight.shape))
+        if self.cfg.dec_type == 'lin':
+            self.fc_dec.weight.copy_(dist.sample(self.fc_dec.weight.shape))
         if self.fc_enc.bias is not None:
             nn.init.zeros_(self.fc_enc.bias)

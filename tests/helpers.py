@@ -44,8 +44,8 @@ def conv_fixture_model(g):
     initial parameters), then the same seeded perturbation of lognorm / biases / LayerNorm affine and log_rate + 3."""
     import torch
     from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE, default_configs
-    cfg_vae, _ = default_configs(str(g["dataset"]), "poisson", "conv+b|lin")
-    cfg_vae.update(seed=int(g["cfg_seed"]))
+    cfg_vae, _ = default_configs(str(g["dataset"]), "poisson", str(g["archi"]) if "archi" in g else "conv+b|lin")
+    cfg_vae.update(seed=int(g["cfg_seed"]), n_latents=512)
     model = PoissonVAE(ConfigPoisVAE(**cfg_vae)).eval()
     gen = torch.Generator().manual_seed(int(g["perturb_seed"]))
     with torch.no_grad():

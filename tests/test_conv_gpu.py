@@ -57,8 +57,8 @@ def test_conv_forward_dgrad_wgrad(case):
     gy = torch.randn(y_ref.shape, generator=g, dtype=torch.float64)
     y_ref.backward(gy)
 
-    wf, wd = conv.weight_prep(weight.detach().float().cuda(), lognorm.detach().float().cuda(), k * k)
-    y, y_act = conv.conv_fwd(nhwc(x.detach()), wf, bias.detach().float().cuda(), k, stride, pad, Co, want_act=True)
+    wf, wd, bp = conv.weight_prep(weight.detach().float().cuda(), lognorm.detach().float().cuda(), bias.detach().float().cuda(), k * k)
+    y, y_act = conv.conv_fwd(nhwc(x.detach()), wf, bp, k, stride, pad, Co, want_act=True)
     assert_rel(nchw(y), y_ref.detach(), what="conv forward")
     assert_rel(nchw(y_act), F.silu(y_ref.detach()), what="fused silu output")
 
@@ -97,8 +97,8 @@ def test_factorized_reduce_window():
     w_all = torch.cat([w.detach().flatten(1) for w in ws]).float().cuda()
     ln_all = torch.cat([l.detach() for l in lns]).float().cuda()
     b_all = torch.cat([b.detach() for b in bs]).float().cuda()
-    wf, wd = conv.weight_prep(w_all, ln_all, 4, groups=4)
-    y, _ = conv.conv_fwd(nhwc(x.detach()), wf, b_all, 2, 2, 0, Co)
+    wf, wd, bp = conv.weight_prep(w_all, ln_all, b_all, 4, groups=4)
+    y, _ = conv.conv_fwd(nhwc(x.detach()), wf, bp, 2, 2, 0, Co)
     assert_rel(nchw(y), y_ref.detach(), what="factorized reduce forward")
     gx = conv.conv_dgrad(nhwc(gy), wd, (N, H, W, Ci), 2, 2, 0)
     assert_rel(nchw(gx), x.grad, what="factorized reduce dgrad")
@@ -114,7 +114,7 @@ def test_conv_single_pass_tf32_is_coarser():
     x = torch.randn(4, 32, 16, 16, generator=g, dtype=torch.float64)
     weight = torch.randn(32, 32, 3, 3, generator=g, dtype=torch.float64) * 0.2
     ref = F.conv2d(x, weight, None, padding=1)
-    wf, _ = conv.weight_prep(weight.float().cuda(), None, 9, need_dgrad=False)
+    wf, _, _ = conv.weight_prep(weight.float().cuda(), None, None, 9, need_dgrad=False)
     errs = {}
     try:
         for mode in (True, False):
@@ -172,6 +172,88 @@ def test_cell_forward_backward(kind):
     y.backward(nhwc(gy))
     assert_rel(nchw(xd.grad), x.grad, rtol=5e-5, what="cell input gradient")
     _compare_grads(cell, sd, "c", 5e-5)
+
+
+@pytest.mark.parametrize("kind", ["normal_dec", "up_dec", "up_dec_16", "normal_dec_16"])
+def test_decoder_cell_forward_backward(kind):
+    """Decoder cells incl. the 16-channel 28x28 layers of the MNIST decoder (stored zero-padded to 32 channels)."""
+    from oracle import conv_oracle
+    from poissonvae_b200 import conv
+    torch.manual_seed(21)
+    up = kind.startswith("up")
+    ci = {"normal_dec": 64, "up_dec": 64, "up_dec_16": 32, "normal_dec_16": 16}[kind]
+    co = ci // 2 if up else ci
+    H = 14 if kind == "up_dec_16" else (28 if kind == "normal_dec_16" else 8)
+    cell = conv.Cell(ci, co, "up_dec" if up else "normal_dec", n_nodes=1)
+    _perturb(cell, 7)
+    sd = _module_state(cell, "c")
+    g = torch.Generator().manual_seed(3)
+    N = 4
+    x = torch.randn(N, ci, H, H, generator=g, dtype=torch.float64, requires_grad=True)
+    y_ref = conv_oracle.dec_cell(x, sd, "c", up)
+    gy = torch.randn(y_ref.shape, generator=g, dtype=torch.float64)
+    y_ref.backward(gy)
+    cell.cuda()
+
+    def padded(t):  # NCHW f64 -> NHWC cuda fp32 with the channel count padded to a multiple of 32
+        t = nhwc(t)
+        cp = conv.pad32(t.shape[-1])
+        return t if cp == t.shape[-1] else torch.nn.functional.pad(t, (0, cp - t.shape[-1])).contiguous()
+
+    xd = padded(x.detach()).requires_grad_()
+    y, y_act = cell(xd)
+    assert_rel(nchw(y)[:, :co], y_ref.detach(), rtol=2e-5, what="decoder cell forward")
+    assert_rel(nchw(y_act)[:, :co], F.silu(y_ref.detach()), rtol=2e-5, what="decoder cell forward (activated copy)")
+    assert float(y[..., co:].abs().max()) == 0.0 if y.shape[-1] > co else True
+    y.backward(padded(gy))
+    assert_rel(nchw(xd.grad)[:, :ci], x.grad, rtol=5e-5, what="decoder cell input gradient")
+    _compare_grads(cell, sd, "c", 5e-5)
+
+
+def test_resample_input_permute_and_head():
+    from oracle import conv_oracle
+    from poissonvae_b200 import conv
+    g = torch.Generator().manual_seed(8)
+    # nn.Upsample(size=14) from 16x16, and 2x
+    for (ih, oh) in ((16, 14), (7, 14), (4, 8)):
+        x = torch.randn(3, 32, ih, ih, generator=g, dtype=torch.float64, requires_grad=True)
+        y_ref = F.interpolate(x, size=oh, mode="nearest")
+        gy = torch.randn(y_ref.shape, generator=g, dtype=torch.float64)
+        y_ref.backward(gy)
+        y = conv.upsample(nhwc(x.detach()), oh, oh)
+        assert torch.equal(nchw(y), y_ref.detach().float().double())
+        gx = conv.upsample_bwd(nhwc(gy), ih, ih)
+        assert_rel(nchw(gx), x.grad, rtol=1e-6, what=f"resample backward {ih}->{oh}")
+    # fc_dec output (N, C*4) NCHW-flat + bias -> NHWC
+    h = torch.randn(6, 256 * 4, generator=g, dtype=torch.float64, requires_grad=True)
+    b = torch.randn(256 * 4, generator=g, dtype=torch.float64, requires_grad=True)
+    ref = (h + b).view(6, 256, 2, 2)
+    gy = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    ref.backward(gy)
+    hd, bd = h.detach().float().cuda().requires_grad_(), b.detach().float().cuda().requires_grad_()
+    y, y_act = conv.decoder_input(hd, bd, 256, 2)
+    assert_rel(nchw(y), ref.detach(), rtol=1e-6, what="decoder input")
+    assert_rel(nchw(y_act), F.silu(ref.detach()), rtol=1e-6, what="decoder input (activated copy)")
+    y.backward(nhwc(gy))
+    assert_rel(hd.grad.double().cpu(), h.grad, rtol=1e-6, what="decoder input gradient")
+    assert_rel(bd.grad.double().cpu(), b.grad, rtol=1e-5, what="fc_dec bias gradient")
+    # head: 1x1 convolution to one channel from a 16-channel map stored with 32
+    torch.manual_seed(5)
+    head = conv.Head(16, 1, 1, padding='valid')
+    _perturb(head, 9)
+    sd = _module_state(head, "h")
+    x = torch.randn(5, 16, 28, 28, generator=g, dtype=torch.float64, requires_grad=True)
+    y_ref = conv_oracle.conv2d(x, sd, "h")
+    gy = torch.randn(y_ref.shape, generator=g, dtype=torch.float64)
+    y_ref.backward(gy)
+    head.cuda()
+    xd = torch.nn.functional.pad(nhwc(x.detach()), (0, 16)).contiguous().requires_grad_()
+    y = head(xd)
+    assert_rel(y.detach().double().cpu(), y_ref.detach(), what="head forward")
+    y.backward(gy.float().cuda())
+    assert_rel(nchw(xd.grad)[:, :16], x.grad, what="head input gradient")
+    assert float(xd.grad[..., 16:].abs().max()) == 0.0
+    _compare_grads(head, sd, "h", 2e-5)
 
 
 def test_stem_res_conv_pool_res_dense():
@@ -246,13 +328,14 @@ def test_res_dense_dropout_statistics():
 import glob
 import os
 
-GOLDEN_CONV = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "conv_enc_*.npz")))
+GOLDEN_CONV = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "conv_enc_*.npz")) +
+                     glob.glob(os.path.join(os.path.dirname(__file__), "golden", "conv_vae_*.npz")))
 
 
 @pytest.mark.parametrize("path", GOLDEN_CONV)
 def test_conv_vae_step_matches_reference(path):
-    """conv+b|lin (BASELINE config 4; MNIST-shaped encoder of config 5): forward, loss and every parameter gradient of one
-    step against the fixture the unmodified reference produced with the same parameters, input and exponential draws.
+    """conv+b|lin (BASELINE config 4, MNIST-shaped encoder) and conv+b|conv+b (BASELINE config 5: MNIST-shaped 28x28; and
+    its 16x16 variant): forward, loss and every parameter gradient of one step against the fixture the unmodified reference produced with the same parameters, input and exponential draws.
     Tolerance 5e-5 relative: ~25 chained 3xTF32 GEMMs deep (each ~2e-6), stated here as the floating-point bound."""
     from tests.helpers import assert_grad_digest, conv_fixture_model
     g = np.load(path)

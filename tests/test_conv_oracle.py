@@ -1,6 +1,7 @@
 """CPU: the conv encoder's oracle (oracle/conv_oracle.py) and the mirror's parameter construction against fixtures of
 the UNMODIFIED reference (tests/golden/conv_enc_*.npz, oracle/make_golden.py:gen_conv): CIFAR16-shaped conv+b|lin
-(BASELINE config 4) and the MNIST-shaped 28x28 encoder of config 5 in front of a linear decoder."""
+(BASELINE config 4), the MNIST-shaped 28x28 encoder in front of a linear decoder, and conv+b|conv+b on MNIST-shaped 28x28
+(BASELINE config 5) and CIFAR16-shaped inputs."""
 import glob
 import os
 
@@ -11,7 +12,8 @@ import torch
 from oracle import conv_oracle, pvae_oracle as po
 from tests.helpers import assert_grad_digest, assert_rel, conv_fixture_model
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "conv_enc_*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "conv_enc_*.npz")) +
+                glob.glob(os.path.join(os.path.dirname(__file__), "golden", "conv_vae_*.npz")))
 
 
 @pytest.mark.parametrize("path", GOLDEN)
@@ -32,7 +34,10 @@ def test_conv_oracle_matches_reference(path):
     log_dr = sc(h, 10.0)
     rate = torch.exp(sc(sd["log_rate"] + log_dr, 5.0)) + torch.finfo(torch.float32).eps
     z = torch.sigmoid((1 - torch.cumsum(e / rate, 0)) / float(g["temp"])).sum(0)
-    y = (z @ sd["fc_dec.weight"].T).view(x.shape)
+    if "conv+b|conv" in str(g["archi"]):
+        y = conv_oracle.conv_decoder(z, sd, str(g["dataset"]))
+    else:
+        y = (z @ sd["fc_dec.weight"].T).view(x.shape)
     recon = ((y - x) ** 2).sum(dim=[1, 2, 3])
     kl = torch.exp(sd["log_rate"]) * (1 + torch.exp(log_dr) * (log_dr - 1))
     loss = torch.mean(recon + float(g["beta"]) * kl.sum(1))
@@ -44,13 +49,14 @@ def test_conv_oracle_matches_reference(path):
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/base"), reason="reference checkout not present")
-@pytest.mark.parametrize("dataset", ["CIFAR16", "MNIST"])
-def test_mirror_parameters_equal_reference(dataset):
+@pytest.mark.parametrize("dataset,archi", [("CIFAR16", "conv+b|lin"), ("MNIST", "conv+b|lin"), ("MNIST", "conv+b|conv+b"),
+                                           ("CIFAR16", "conv+b|conv+b"), ("vH16", "conv|conv")])
+def test_mirror_parameters_equal_reference(dataset, archi):
     from oracle import ref_import
     from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE, default_configs
     ref = ref_import.load()
-    kws, tr = ref.cfg.default_configs(dataset, "poisson", "conv+b|lin")
-    kws2, tr2 = default_configs(dataset, "poisson", "conv+b|lin")
+    kws, tr = ref.cfg.default_configs(dataset, "poisson", archi)
+    kws2, tr2 = default_configs(dataset, "poisson", archi)
     assert {k: kws2[k] for k in kws} == kws and tr == tr2
     a = ref.vae.PoissonVAE(ref.cfg.ConfigPoisVAE(save=False, seed=3, **kws)).state_dict()
     b = PoissonVAE(ConfigPoisVAE(seed=3, **kws2)).state_dict()
