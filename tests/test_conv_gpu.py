@@ -396,3 +396,33 @@ def test_conv_trainer_steps():
     model.train()
     losses = [tr.train_step(x, i)[0].item() for i in range(1, 40)]
     assert np.isfinite(losses).all() and np.mean(losses[-5:]) < 0.995 * np.mean(losses[:5]), losses
+
+
+def test_config5_temperature_annealed_training_and_hard_count_eval():
+    """BASELINE config 5: poisson conv+b|conv+b on MNIST-shaped 28x28 inputs, K = 512, linear temperature annealing
+    1 -> 0.05 over the first half (main/config_vae.py:278-281), gradient clipping at 1000, then the evaluation pass at
+    temp = 0 (hard spike counts, base/helper.py:15-17)."""
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE, default_configs
+    cfg_vae, cfg_tr = default_configs("MNIST", "poisson", "conv+b|conv+b")
+    cfg_vae.update(n_latents=512, seed=2)
+    model = PoissonVAE(ConfigPoisVAE(**cfg_vae)).cuda()
+    model.update_n(12.0)
+    g = torch.Generator().manual_seed(5)
+    data = torch.rand(64, 1, 28, 28, generator=g).cuda()
+    tr = TrainerVAE(model, ConfigTrainVAE(epochs=20, **cfg_tr), n_batches_per_epoch=2)
+    assert tr.temperatures[0] == 1.0 and abs(tr.temperatures[-1] - 0.05) < 1e-12
+    first = last = None
+    for ep in range(20):
+        for i in range(2):
+            out = tr.train_step(data[32 * i:32 * (i + 1)], 2 * ep + i)
+            if first is None:
+                first = out.clone()
+            last = out
+    assert abs(model._temp_host - 0.05) < 1e-6 and torch.isfinite(tr.flat_p).all()
+    assert last[1].item() < first[1].item(), (first.tolist(), last.tolist())  # reconstruction error went down
+    model.eval()
+    data_out, loss, etc = tr.validate(data, temp=0.0, batch_size=32)
+    z = data_out["z"]
+    assert z.shape == (64, 512) and np.array_equal(z, np.round(z)) and z.min() >= 0
+    assert loss["mse"].shape == (64,) and np.isfinite(loss["mse"]).all() and np.isfinite(loss["kl"]).all()

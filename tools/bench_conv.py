@@ -21,7 +21,8 @@ def cpu_port(args, x):
     from oracle import conv_oracle
     from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE, default_configs
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg_vae, _ = default_configs(args.dataset, "poisson", "conv+b|lin")
+    cfg_vae, _ = default_configs(args.dataset, "poisson", args.archi)
+    cfg_vae.update(n_latents=args.latents)
     model = PoissonVAE(ConfigPoisVAE(seed=0, **cfg_vae))
     sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in model.state_dict().items()}
     xs = x[:args.cpu_rows].cpu()
@@ -33,7 +34,10 @@ def cpu_port(args, x):
         rate = torch.exp(sc(sd["log_rate"] + log_dr, 5.0)) + 1.19e-7
         e = rate.new(torch.Size((args.n_exp,)) + rate.shape).exponential_()
         z = torch.sigmoid((1 - torch.cumsum(e / rate, 0)) / 1.0).sum(0)
-        y = (z @ sd["fc_dec.weight"].T).view(xs.shape)
+        if model.cfg.dec_type == "conv":
+            y = conv_oracle.conv_decoder(z, sd, args.dataset)
+        else:
+            y = (z @ sd["fc_dec.weight"].T).view(xs.shape)
         kl = torch.exp(sd["log_rate"]) * (1 + torch.exp(log_dr) * (log_dr - 1))
         loss = torch.mean(((y - xs) ** 2).sum(dim=[1, 2, 3]) + kl.sum(1))
         for v in sd.values():
@@ -54,6 +58,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--dataset", default="CIFAR16")
+    ap.add_argument("--archi", default="conv+b|lin", help="conv+b|lin (BASELINE config 4) or conv+b|conv+b (config 5 with --dataset MNIST)")
+    ap.add_argument("--latents", type=int, default=512)
     ap.add_argument("--n_exp", type=int, default=263)
     ap.add_argument("--tf32", action="store_true")
     ap.add_argument("--cpu_rows", type=int, default=32)
@@ -69,7 +75,8 @@ def main():
     if args.tf32:
         conv.PRECISE = False
         linear.PRECISE = False
-    cfg_vae, cfg_tr = default_configs(args.dataset, "poisson", "conv+b|lin")
+    cfg_vae, cfg_tr = default_configs(args.dataset, "poisson", args.archi)
+    cfg_vae.update(n_latents=args.latents)
     model = PoissonVAE(ConfigPoisVAE(seed=0, **cfg_vae)).cuda()
     model.update_n(200.0)
     model._n_exp_host = args.n_exp
@@ -98,7 +105,7 @@ def main():
     torch.cuda.synchronize()
     host_s = time.perf_counter() - t0
     ms = e0.elapsed_time(e1) / args.steps
-    line = {"metric": "training samples/sec (P-VAE conv+b|lin K=512)", "value": round(args.batch / ms * 1e3, 1), "unit": "samples/s",
+    line = {"metric": f"training samples/sec (P-VAE {args.archi} K={args.latents})", "value": round(args.batch / ms * 1e3, 1), "unit": "samples/s",
             "ms_per_step": round(ms, 3), "host_ms_per_step": round(host_s / args.steps * 1e3, 3),
             "enqueue_ms_per_step": round(enqueue_s / args.steps * 1e3, 3), "batch": args.batch,
             "dataset": args.dataset, "n_exp": args.n_exp, "gpu_launches_per_step": (lib.pvae_launch_count() - c0) // args.steps,

@@ -15,10 +15,12 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def run(world, rank, steps, Bg, K, dp_mode='auto'):
+def run(world, rank, steps, Bg, K, dp_mode='auto', archi='lin|lin', dataset='vH16'):
     from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
-    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
-    model = PoissonVAE(ConfigPoisVAE(n_latents=K, prior_clamp=-4, seed=0)).cuda()
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE, default_configs
+    cfg_vae, _ = default_configs(dataset, 'poisson', archi)
+    cfg_vae.update(n_latents=K, seed=0)
+    model = PoissonVAE(ConfigPoisVAE(**cfg_vae)).cuda().eval()  # eval: dropout off (its mask is not keyed by the sample index)
     with torch.no_grad():
         model.log_rate.add_(3.0)
     model.update_n(20.0)
@@ -30,7 +32,7 @@ def run(world, rank, steps, Bg, K, dp_mode='auto'):
     if rank == 0 and world > 1:
         print("gradient exchange:", "peer memory (fused all-reduce + Adamax)" if tr.peer is not None else "NCCL all-reduce")
     g = torch.Generator().manual_seed(4321)
-    data = torch.randn(steps, Bg, 256, generator=g)
+    data = torch.randn(steps, Bg, model.cfg.input_sz ** 2, generator=g)
     losses = []
     for i in range(steps):
         lo = rank * (Bg // world)
@@ -51,10 +53,12 @@ def main():
     ap.add_argument("--batch", type=int, default=2048)
     ap.add_argument("--latents", type=int, default=512)
     ap.add_argument("--dp_mode", default="auto", choices=["auto", "peer", "nccl"])
+    ap.add_argument("--archi", default="lin|lin")
+    ap.add_argument("--dataset", default="vH16")
     a = ap.parse_args()
     if a.mode == "single":
         torch.cuda.set_device(0)
-        p, l = run(1, 0, a.steps, a.batch, a.latents, a.dp_mode)
+        p, l = run(1, 0, a.steps, a.batch, a.latents, a.dp_mode, a.archi, a.dataset)
         torch.save({"p": p, "l": l}, a.out)
         print("single-GPU reference saved:", l[:, 0].tolist())
         return
@@ -62,7 +66,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    p, l = run(world, rank, a.steps, a.batch, a.latents, a.dp_mode)
+    p, l = run(world, rank, a.steps, a.batch, a.latents, a.dp_mode, a.archi, a.dataset)
     ref = torch.load(a.ref)
     dp_err = ((p - ref["p"]).abs().max() / ref["p"].abs().max()).item()
     l_err = ((l - ref["l"]).abs() / ref["l"].abs()).max().item()
@@ -75,7 +79,8 @@ def main():
     if rank == 0:
         print(f"world={world}: max rel param diff vs single GPU {dp_err:.2e}, loss diff {l_err:.2e}, ranks identical: {same}")
     dist.destroy_process_group()
-    assert dp_err < 2e-5 and l_err < 2e-5 and same
+    tol = 2e-5 if a.archi == 'lin|lin' else 2e-4  # conv: ~25 GEMMs deep, summation order differs between 1 and N shards
+    assert dp_err < tol and l_err < tol and same
     if rank == 0:
         print("DP CHECK OK")
 
