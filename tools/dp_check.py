@@ -22,9 +22,9 @@ def run(world, rank, steps, Bg, K, dp_mode='auto', archi='lin|lin', dataset='vH1
     cfg_vae.update(n_latents=K, seed=0)
     model = PoissonVAE(ConfigPoisVAE(**cfg_vae)).cuda().eval()  # eval: dropout off (its mask is not keyed by the sample index)
     with torch.no_grad():
-        model.log_rate.add_(3.0)
+        model.log_rate.add_(3.0 if model.cfg.dec_type == 'lin' else 0.0)
     model.update_n(20.0)
-    cfg = ConfigTrainVAE(lr=0.005, epochs=100, batch_size=Bg // world, warmup_portion=0.0, scheduler_type=None,
+    cfg = ConfigTrainVAE(lr=0.005 if model.cfg.dec_type == 'lin' else 0.0005, epochs=100, batch_size=Bg // world, warmup_portion=0.0, scheduler_type=None,
                          grad_clip=200.0, kl_beta=2.5, kl_anneal_portion=0.0, kl_const_portion=0.0,
                          temp_anneal_portion=0.0, temp_stop=0.3)
     cfg.grad_clip = None if dp_mode == 'peer' else cfg.grad_clip
