@@ -285,6 +285,33 @@ int pvae_layernorm_fwd(const float* a, const float* b, const float* gamma, const
 int pvae_layernorm_bwd(const float* g, const float* xhat, const float* rstd, const float* gamma, float* g_s,
                        float* g_gamma_beta, float* ws, int64_t R, int C, void* stream);
 
+/* ---- one call per residual cell (csrc/conv_net.cu) -----------------------------------------------------------------
+ * Cell.forward base/common.py:187-192 (ConvLayer :233-242, SELayer :138-142, FactorizedReduce / StrideReduce :75-126, the
+ * up-sampling skip :35-47) and its whole backward, every kernel enqueued from C++.  x / y are NHWC maps with channel
+ * counts padded to multiples of 32; x_act = silu(x) if the producer already has it (NULL: computed here); y_act = silu(y).
+ * `saved` (pvae_cell_saved_floats(c, x_act == NULL) floats) carries the forward's intermediates to the backward; `scratch`
+ * (pvae_cell_scratch_floats) is only used inside pvae_cell_bwd, which writes the g_* gradients of the descriptor and g_x.
+ * skip_w / skip_ln / skip_b: PVAE_CELL_DOWN_FACTORIZED: the four 1x1 filters back to back as (Co, Ci), (Co), (Co);
+ * PVAE_CELL_DOWN_STRIDE / PVAE_CELL_UP_DEC: the 1x1 filter (Co, Ci, 1, 1). */
+enum { PVAE_CELL_NORMAL_PRE = 0, PVAE_CELL_DOWN_FACTORIZED = 1, PVAE_CELL_DOWN_STRIDE = 2, PVAE_CELL_NORMAL_DEC = 3, PVAE_CELL_UP_DEC = 4 };
+typedef struct pvae_cell {
+  int kind;
+  int N, H, W; /* input map */
+  int Ci, Co;  /* channel counts of the parameters */
+  float eps_res;
+  int precise;
+  const float *w1, *ln1, *b1; /* first 3x3 convolution (the only one of a decoder cell) */
+  const float *w2, *ln2, *b2; /* second 3x3 convolution (encoder cells) */
+  const float *se_w1, *se_b1, *se_w2, *se_b2;
+  const float *skip_w, *skip_ln, *skip_b;
+  float *g_w1, *g_ln1, *g_b1, *g_w2, *g_ln2, *g_b2, *g_se_w1, *g_se_b1, *g_se_w2, *g_se_b2, *g_skip_w, *g_skip_ln, *g_skip_b;
+} pvae_cell;
+int64_t pvae_cell_saved_floats(const pvae_cell* c, int own_act);
+int64_t pvae_cell_scratch_floats(const pvae_cell* c);
+int pvae_cell_fwd(const pvae_cell* c, const float* x, const float* x_act, float* y, float* y_act, float* saved, void* stream);
+int pvae_cell_bwd(const pvae_cell* c, const float* x, const float* x_act, const float* g_y, float* g_x, float* saved,
+                  float* scratch, void* stream);
+
 /* Tuning knob (process-wide): number of events each quad of latents walks thread-per-quad before a
  * still-unfinished chain is handed to a whole warp (32 events per step).  Default 8.  Results do
  * not depend on the launch geometry, but the float summation order of a chain depends on this value. */

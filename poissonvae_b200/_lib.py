@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpvae_b200.so")
 SOURCES = ["capi.cu", "sampler.cu", "step.cu", "gemm_tc.cu", "lin_step.cu", "peer_allreduce.cu", "conv_tc.cu",
-           "conv_misc.cu"]
+           "conv_misc.cu", "conv_net.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -37,6 +37,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 _f, _i, _i64, _u64, _p = C.c_float, C.c_int, C.c_int64, C.c_uint64, C.c_void_p
+
+class Cell(C.Structure):
+    """pvae_cell of include/pvae_b200.h"""
+    _fields_ = ([("kind", C.c_int), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Ci", C.c_int), ("Co", C.c_int),
+                 ("eps_res", C.c_float), ("precise", C.c_int)] +
+                [(n, C.c_void_p) for n in ("w1", "ln1", "b1", "w2", "ln2", "b2", "se_w1", "se_b1", "se_w2", "se_b2", "skip_w",
+                                           "skip_ln", "skip_b", "g_w1", "g_ln1", "g_b1", "g_w2", "g_ln2", "g_b2", "g_se_w1",
+                                           "g_se_b1", "g_se_w2", "g_se_b2", "g_skip_w", "g_skip_ln", "g_skip_b")])
+
 
 _SIGNATURES = {
     "pvae_version": (C.c_int, []),
@@ -71,6 +80,10 @@ _SIGNATURES = {
     "pvae_conv_igemm": (_i, [_p] * 8 + [_i] * 14 + [_p, _p, _p, _i, _i, _p]),
     "pvae_conv_wgrad_ws_floats": (_i64, [_i, _i, _i]),
     "pvae_conv_wgrad": (_i, [_p] * 8 + [_i] * 9 + [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "pvae_cell_saved_floats": (_i64, [_p, _i]),
+    "pvae_cell_scratch_floats": (_i64, [_p]),
+    "pvae_cell_fwd": (_i, [_p] * 6 + [_p]),
+    "pvae_cell_bwd": (_i, [_p] * 7 + [_p]),
     "pvae_reduce_ws_floats": (_i64, [_i64]),
     "pvae_silu_fwd": (_i, [_p, _p, _i64, _p]),
     "pvae_add": (_i, [_p, _p, _p, _i64, _p]),

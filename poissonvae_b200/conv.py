@@ -21,6 +21,10 @@ from .rng import next_philox
 
 MULT = 2
 PRECISE = True  # 3xTF32 operand splitting in the convolutions (fp32-grade); False = single-pass TF32
+# True: a cell's forward / backward is ONE C call that enqueues all of its kernels (csrc/conv_net.cu).  False: the same
+# kernels in the same order, one ctypes call each, from the Functions below (bit-identical results; kept as the readable
+# statement of the algorithm and as the cross-check of the native path).
+NATIVE_CELLS = True
 
 
 def _p(t):
@@ -260,6 +264,52 @@ def _se_backward(g_y, c2, gate, hid, pool, se_w1, se_w2, eps_res):
     return g_c2, g_w1, g_b1, g_w2, g_b2
 
 
+_CELL_FIELDS = ("w1", "ln1", "b1", "w2", "ln2", "b2", "se_w1", "se_b1", "se_w2", "se_b2", "skip_w", "skip_ln", "skip_b")
+
+
+def _native_cell_forward(ctx, kind, x, x_act, params, eps_res):
+    """params: the 13 parameter tensors of pvae_cell in _CELL_FIELDS order (None where the cell kind has none)."""
+    lib = _lib.load()
+    n, h, w, _ = x.shape
+    w1 = params[0]
+    d = _lib.Cell()
+    d.kind, d.N, d.H, d.W, d.Ci, d.Co, d.eps_res, d.precise = kind, n, h, w, w1.shape[1], w1.shape[0], eps_res, int(PRECISE)
+    for name, t in zip(_CELL_FIELDS, params):
+        setattr(d, name, _p(t))
+    own_act = x_act is None
+    up, down = kind == 4, kind in (1, 2)
+    oh, ow = (2 * h, 2 * w) if up else ((out_size(h, 3, 2, 1), out_size(w, 3, 2, 1)) if down else (h, w))
+    saved = torch.empty(lib.pvae_cell_saved_floats(C.byref(d), int(own_act)), device=x.device, dtype=torch.float32)
+    y = torch.empty(n, oh, ow, pad32(w1.shape[0]), device=x.device, dtype=torch.float32)
+    y_act = torch.empty_like(y)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.pvae_cell_fwd(C.byref(d), _p(x), _p(x_act), _p(y), _p(y_act), _p(saved), _s()))
+    ctx.save_for_backward(x, x_act, saved, *params)
+    ctx.native = (kind, eps_res)
+    ctx.mark_non_differentiable(y_act)
+    return y, y_act
+
+
+def _native_cell_backward(ctx, g_y):
+    lib = _lib.load()
+    x, x_act, saved, *params = ctx.saved_tensors
+    kind, eps_res = ctx.native
+    n, h, w, _ = x.shape
+    w1 = params[0]
+    d = _lib.Cell()
+    d.kind, d.N, d.H, d.W, d.Ci, d.Co, d.eps_res, d.precise = kind, n, h, w, w1.shape[1], w1.shape[0], eps_res, int(PRECISE)
+    grads = [None if t is None else torch.empty_like(t) for t in params]
+    for name, t, g in zip(_CELL_FIELDS, params, grads):
+        setattr(d, name, _p(t))
+        setattr(d, "g_" + name, _p(g))
+    g_y = g_y.contiguous()
+    g_x = torch.empty_like(x)
+    scratch = _workspace(x.device, lib.pvae_cell_scratch_floats(C.byref(d)))
+    with torch.cuda.device(x.device):
+        _lib.check(lib.pvae_cell_bwd(C.byref(d), _p(x), _p(x_act), _p(g_y), _p(g_x), _p(saved), _p(scratch), _s()))
+    return g_x, grads
+
+
 class _CellFn(torch.autograd.Function):
     """Cell.forward base/common.py:187-192 for the encoder cell types 'normal_pre' (stride 1, identity skip) and
     'down_enc' (stride 2, FactorizedReduce or StrideReduce skip), n_nodes = 2, SiLU, squeeze-excitation on.
@@ -270,6 +320,11 @@ class _CellFn(torch.autograd.Function):
                 eps_res):
         x = _check_input(x)
         co = w1.shape[0]
+        if NATIVE_CELLS:
+            kind = 0 if stride == 1 else (1 if skip_groups > 1 else 2)
+            return _native_cell_forward(ctx, kind, x, x_act, (w1, ln1, b1, w2, ln2, b2, se_w1, se_b1, se_w2, se_b2, skip_w, skip_ln,
+                                                              skip_b), eps_res)
+        ctx.native = None
         if x_act is None:
             x_act = silu(x)
         wf1, wd1, bp1 = weight_prep(w1, ln1, b1, 9)
@@ -290,6 +345,9 @@ class _CellFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_y, _g_act):
+        if ctx.native is not None:
+            g_x, g = _native_cell_backward(ctx, g_y)
+            return (g_x, None, *g, None, None, None)
         x, x_act, c1, a2, c2, pool, hid, gate, w1, ln1, w2, ln2, se_w1, se_w2, skip_w, skip_ln, wd1, wd2, wds = ctx.saved_tensors
         stride, skip_groups, eps_res = ctx.cfg
         g_y = g_y.contiguous()
@@ -322,6 +380,10 @@ class _DecCellFn(torch.autograd.Function):
         x = _check_input(x)
         n, h, wd_, _ = x.shape
         cop = pad32(w.shape[0])
+        if NATIVE_CELLS:
+            return _native_cell_forward(ctx, 4 if up else 3, x, x_act, (w, ln, b, None, None, None, se_w1, se_b1, se_w2, se_b2, skip_w,
+                                                                          skip_ln, skip_b), eps_res)
+        ctx.native = None
         if x_act is None:
             x_act = silu(x)
         wf, wd, bp = weight_prep(w, ln, b, 9)
@@ -342,6 +404,9 @@ class _DecCellFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_y, _g_act):
+        if ctx.native is not None:
+            g_x, g = _native_cell_backward(ctx, g_y)
+            return (g_x, None, g[0], g[1], g[2], g[6], g[7], g[8], g[9], g[10], g[11], g[12], None, None)
         x, x_act, au, c, pool, hid, gate, w, ln, se_w1, se_w2, skip_w, skip_ln, wd, wds = ctx.saved_tensors
         up, eps_res = ctx.cfg
         g_y = g_y.contiguous()

@@ -427,3 +427,41 @@ def test_config5_temperature_annealed_training_and_hard_count_eval():
     z = data_out["z"]
     assert z.shape == (64, 512) and np.array_equal(z, np.round(z)) and z.min() >= 0
     assert loss["mse"].shape == (64,) and np.isfinite(loss["mse"]).all() and np.isfinite(loss["kl"]).all()
+
+
+@pytest.mark.parametrize("kind", ["normal_pre", "down_enc", "down_enc_stride", "normal_dec", "up_dec", "up_dec_16"])
+def test_native_cell_call_equals_per_kernel_path(kind):
+    """pvae_cell_fwd / pvae_cell_bwd (one C call per cell, csrc/conv_net.cu) enqueue the same kernels in the same order
+    as the per-kernel Python path: outputs and every gradient are bit-identical."""
+    from poissonvae_b200 import conv
+    torch.manual_seed(31)
+    dec = kind.endswith("dec") or kind == "up_dec_16"
+    ci = 32 if kind != "normal_dec" else 64
+    co = {"normal_pre": 32, "down_enc": 64, "down_enc_stride": 64, "normal_dec": 64, "up_dec": 16 if False else 16, "up_dec_16": 16}[kind]
+    if kind == "up_dec":
+        ci, co = 64, 32
+    cell_type = {"normal_pre": "normal_pre", "down_enc": "down_enc", "down_enc_stride": "down_enc", "normal_dec": "normal_dec",
+                 "up_dec": "up_dec", "up_dec_16": "up_dec"}[kind]
+    cell = conv.Cell(ci, co, cell_type, n_nodes=1 if dec else 2, factorized=(kind != "down_enc_stride")).cuda()
+    _perturb(cell, 3)
+    H = 13 if kind == "down_enc_stride" else 14
+    if kind == "down_enc":
+        H = 16
+    x = torch.randn(6, H, H, conv.pad32(ci), device="cuda")
+    gy = None
+    results = {}
+    try:
+        for native in (True, False):
+            conv.NATIVE_CELLS = native
+            for p in cell.parameters():
+                p.grad = None
+            xd = x.clone().requires_grad_()
+            y, y_act = cell(xd)
+            if gy is None:
+                gy = torch.randn_like(y)
+            y.backward(gy)
+            results[native] = [y.detach(), y_act.detach(), xd.grad] + [p.grad.clone() for p in cell.parameters()]
+    finally:
+        conv.NATIVE_CELLS = True
+    for a, b in zip(results[True], results[False]):
+        assert torch.equal(a, b)
