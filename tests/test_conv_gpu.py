@@ -437,13 +437,14 @@ def test_native_cell_call_equals_per_kernel_path(kind):
     torch.manual_seed(31)
     dec = kind.endswith("dec") or kind == "up_dec_16"
     ci = 32 if kind != "normal_dec" else 64
-    co = {"normal_pre": 32, "down_enc": 64, "down_enc_stride": 64, "normal_dec": 64, "up_dec": 16 if False else 16, "up_dec_16": 16}[kind]
+    co = {"normal_pre": 32, "down_enc": 64, "down_enc_stride": 64, "normal_dec": 64, "up_dec": 32, "up_dec_16": 16}[kind]
     if kind == "up_dec":
         ci, co = 64, 32
     cell_type = {"normal_pre": "normal_pre", "down_enc": "down_enc", "down_enc_stride": "down_enc", "normal_dec": "normal_dec",
                  "up_dec": "up_dec", "up_dec_16": "up_dec"}[kind]
-    cell = conv.Cell(ci, co, cell_type, n_nodes=1 if dec else 2, factorized=(kind != "down_enc_stride")).cuda()
+    cell = conv.Cell(ci, co, cell_type, n_nodes=1 if dec else 2, factorized=(kind != "down_enc_stride"))
     _perturb(cell, 3)
+    cell.cuda()
     H = 13 if kind == "down_enc_stride" else 14
     if kind == "down_enc":
         H = 16
