@@ -311,6 +311,9 @@ int64_t pvae_cell_scratch_floats(const pvae_cell* c);
 int pvae_cell_fwd(const pvae_cell* c, const float* x, const float* x_act, float* y, float* y_act, float* saved, void* stream);
 int pvae_cell_bwd(const pvae_cell* c, const float* x, const float* x_act, const float* g_y, float* g_x, float* saved,
                   float* scratch, void* stream);
+/* Tuning knob (process-wide, default on): pvae_cell_bwd runs the parameter-gradient kernels on an internal side stream
+ * (forked from / joined back into the caller's stream with events) next to the data-gradient chain. */
+int pvae_set_cell_overlap(int on);
 
 /* Tuning knob (process-wide): number of events each quad of latents walks thread-per-quad before a
  * still-unfinished chain is handed to a whole warp (32 events per step).  Default 8.  Results do

@@ -107,6 +107,38 @@ static Scratch carve_scratch(const pvae_cell& c, float* base) {
   return s;
 }
 
+// Side stream for the weight-gradient work of a cell's backward (off the g_y -> g_x critical path); one per device.
+struct CellSide {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork[3] = {nullptr, nullptr, nullptr}, join = nullptr;
+};
+static CellSide* cell_side() {
+  static CellSide per_device[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  CellSide& s = per_device[dev];
+  if (!s.stream) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (auto& e : s.fork)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &s;
+}
+static int g_cell_overlap = 1;
+
+// the side stream waits for everything enqueued on `main` so far
+static int fork_to(CellSide* side, int i, void* main_stream) {
+  if (!side) return PVAE_OK;
+  if (int rc = cuda_ok("fork", cudaEventRecord(side->fork[i], static_cast<cudaStream_t>(main_stream)))) return rc;
+  return cuda_ok("fork", cudaStreamWaitEvent(side->stream, side->fork[i], 0));
+}
+static int join_from(CellSide* side, void* main_stream) {
+  if (!side) return PVAE_OK;
+  if (int rc = cuda_ok("join", cudaEventRecord(side->join, side->stream))) return rc;
+  return cuda_ok("join", cudaStreamWaitEvent(static_cast<cudaStream_t>(main_stream), side->join, 0));
+}
+
 struct Taps {
   int n = 0;
   int dy[16], dx[16], wi[16];
@@ -237,39 +269,57 @@ extern "C" int pvae_cell_bwd(const pvae_cell* c, const float* x, const float* x_
   const Scratch w = carve_scratch(*c, scratch);
   if (x_act == nullptr) x_act = s.x_act;
   const int pr = c->precise;
-  // gate + residual: g_c2 (w.r.t. the gated convolution output), SE parameter gradients
+  // Critical path (caller's stream): se_bwd -> dgrad(s) -> g_x.  Everything that only produces parameter gradients
+  // (SE weights, wgrad + split reduction + weight-norm backward of every convolution) goes to the side stream as soon as
+  // its inputs exist, and is joined before returning.  Same kernels either way: results do not depend on the overlap.
+  CellSide* side = g_cell_overlap ? cell_side() : nullptr;
+  void* s2 = side ? static_cast<void*>(side->stream) : stream;
   TRY(pvae_se_bwd(g_y, s.c2, s.gate, s.hid, c->se_w1, c->se_w2, c->eps_res, w.g_c2, w.d2, w.d1, g.N, g.OH * g.OW, g.CoP, c->Co, g.hd, stream));
-  TRY(pvae_small_tn(w.d2, s.hid, c->g_se_w2, w.rws, g.N, c->Co, g.hd, stream));
-  TRY(pvae_colsum(w.d2, c->g_se_b2, w.rws, g.N, c->Co, stream));
-  TRY(pvae_small_tn(w.d1, s.pool, c->g_se_w1, w.rws, g.N, g.hd, c->Co, stream));
-  TRY(pvae_colsum(w.d1, c->g_se_b1, w.rws, g.N, g.hd, stream));
+  TRY(fork_to(side, 0, stream));
+  TRY(pvae_small_tn(w.d2, s.hid, c->g_se_w2, w.rws, g.N, c->Co, g.hd, s2));
+  TRY(pvae_colsum(w.d2, c->g_se_b2, w.rws, g.N, c->Co, s2));
+  TRY(pvae_small_tn(w.d1, s.pool, c->g_se_w1, w.rws, g.N, g.hd, c->Co, s2));
+  TRY(pvae_colsum(w.d1, c->g_se_b1, w.rws, g.N, g.hd, s2));
   if (!g.dec) {
     if (!c->g_w2 || !c->g_ln2 || !c->g_b2) return fail(PVAE_ERR_INVALID, "pvae_cell_bwd: null gradient pointer");
+    if (g.down && (!c->g_skip_w || !c->g_skip_ln || !c->g_skip_b)) return fail(PVAE_ERR_INVALID, "pvae_cell_bwd: null skip gradient pointer");
     TRY(conv_wgrad(s.a2, w.g_c2, c->w2, c->ln2, c->g_w2, c->g_ln2, c->g_b2, w.ws, g.N, g.OH, g.OW, g.CoP, g.CoP, g.OH, g.OW, 3, 1, 1, 1, c->Co,
-                   c->Co, pr, stream));
+                   c->Co, pr, s2));
+    if (g.down)
+      TRY(conv_wgrad(x_act, g_y, c->skip_w, c->skip_ln, c->g_skip_w, c->g_skip_ln, c->g_skip_b, w.ws, g.N, g.H, g.W, g.CiP, g.CoP, g.OH, g.OW,
+                     g.ks, 2, 0, g.groups, c->Ci, c->Co, pr, s2));
     TRY(conv_dgrad(w.g_c2, s.wd2, w.g_c1, g.N, g.OH, g.OW, g.CoP, g.OH, g.OW, g.CoP, 3, 1, 1, nullptr, s.c1, nullptr, pr, stream));
+    TRY(fork_to(side, 1, stream));
     TRY(conv_wgrad(x_act, w.g_c1, c->w1, c->ln1, c->g_w1, c->g_ln1, c->g_b1, w.ws, g.N, g.H, g.W, g.CiP, g.CoP, g.OH, g.OW, 3, g.stride, 1, 1,
-                   c->Ci, c->Co, pr, stream));
-    if (!g.down)
-      return conv_dgrad(w.g_c1, s.wd1, g_x, g.N, g.H, g.W, g.CiP, g.OH, g.OW, g.CoP, 3, 1, 1, nullptr, x, g_y, pr, stream);
-    if (!c->g_skip_w || !c->g_skip_ln || !c->g_skip_b) return fail(PVAE_ERR_INVALID, "pvae_cell_bwd: null skip gradient pointer");
-    TRY(conv_wgrad(x_act, g_y, c->skip_w, c->skip_ln, c->g_skip_w, c->g_skip_ln, c->g_skip_b, w.ws, g.N, g.H, g.W, g.CiP, g.CoP, g.OH, g.OW,
-                   g.ks, 2, 0, g.groups, c->Ci, c->Co, pr, stream));
-    TRY(conv_dgrad(w.g_c1, s.wd1, w.g_a, g.N, g.H, g.W, g.CiP, g.OH, g.OW, g.CoP, 3, 2, 1, nullptr, nullptr, nullptr, pr, stream));
-    return conv_dgrad(g_y, s.wds, g_x, g.N, g.H, g.W, g.CiP, g.OH, g.OW, g.CoP, g.ks, 2, 0, w.g_a, x, nullptr, pr, stream);
+                   c->Ci, c->Co, pr, s2));
+    if (!g.down) {
+      TRY(conv_dgrad(w.g_c1, s.wd1, g_x, g.N, g.H, g.W, g.CiP, g.OH, g.OW, g.CoP, 3, 1, 1, nullptr, x, g_y, pr, stream));
+    } else {
+      TRY(conv_dgrad(w.g_c1, s.wd1, w.g_a, g.N, g.H, g.W, g.CiP, g.OH, g.OW, g.CoP, 3, 2, 1, nullptr, nullptr, nullptr, pr, stream));
+      TRY(conv_dgrad(g_y, s.wds, g_x, g.N, g.H, g.W, g.CiP, g.OH, g.OW, g.CoP, g.ks, 2, 0, w.g_a, x, nullptr, pr, stream));
+    }
+    return join_from(side, stream);
   }
   if (g.up) {
     if (!c->g_skip_w || !c->g_skip_ln || !c->g_skip_b) return fail(PVAE_ERR_INVALID, "pvae_cell_bwd: null skip gradient pointer");
     TRY(conv_wgrad(s.au, w.g_c2, c->w1, c->ln1, c->g_w1, c->g_ln1, c->g_b1, w.ws, g.N, g.OH, g.OW, g.CiP, g.CoP, g.OH, g.OW, 3, 1, 1, 1, c->Ci,
-                   c->Co, pr, stream));
+                   c->Co, pr, s2));
+    TRY(pvae_upsample_bwd(g_y, nullptr, w.g_s, g.N, g.H, g.W, g.OH, g.OW, g.CoP, stream));  // skip branch, small map
+    TRY(fork_to(side, 1, stream));
+    TRY(conv_wgrad(x, w.g_s, c->skip_w, c->skip_ln, c->g_skip_w, c->g_skip_ln, c->g_skip_b, w.ws, g.N, g.H, g.W, g.CiP, g.CoP, g.H, g.W, 1, 1,
+                   0, 1, c->Ci, c->Co, pr, s2));
     TRY(conv_dgrad(w.g_c2, s.wd1, w.g_au, g.N, g.OH, g.OW, g.CiP, g.OH, g.OW, g.CoP, 3, 1, 1, nullptr, nullptr, nullptr, pr, stream));
     TRY(pvae_upsample_bwd(w.g_au, x, w.t, g.N, g.H, g.W, g.OH, g.OW, g.CiP, stream));      // through SiLU -> up-sampling
-    TRY(pvae_upsample_bwd(g_y, nullptr, w.g_s, g.N, g.H, g.W, g.OH, g.OW, g.CoP, stream));  // skip branch, small map
-    TRY(conv_wgrad(x, w.g_s, c->skip_w, c->skip_ln, c->g_skip_w, c->g_skip_ln, c->g_skip_b, w.ws, g.N, g.H, g.W, g.CiP, g.CoP, g.H, g.W, 1, 1,
-                   0, 1, c->Ci, c->Co, pr, stream));
-    return conv_dgrad(w.g_s, s.wds, g_x, g.N, g.H, g.W, g.CiP, g.H, g.W, g.CoP, 1, 1, 0, nullptr, nullptr, w.t, pr, stream);
+    TRY(conv_dgrad(w.g_s, s.wds, g_x, g.N, g.H, g.W, g.CiP, g.H, g.W, g.CoP, 1, 1, 0, nullptr, nullptr, w.t, pr, stream));
+    return join_from(side, stream);
   }
   TRY(conv_wgrad(x_act, w.g_c2, c->w1, c->ln1, c->g_w1, c->g_ln1, c->g_b1, w.ws, g.N, g.H, g.W, g.CiP, g.CoP, g.OH, g.OW, 3, 1, 1, 1, c->Ci,
-                 c->Co, pr, stream));
-  return conv_dgrad(w.g_c2, s.wd1, g_x, g.N, g.H, g.W, g.CiP, g.OH, g.OW, g.CoP, 3, 1, 1, nullptr, x, g_y, pr, stream);
+                 c->Co, pr, s2));
+  TRY(conv_dgrad(w.g_c2, s.wd1, g_x, g.N, g.H, g.W, g.CiP, g.OH, g.OW, g.CoP, 3, 1, 1, nullptr, x, g_y, pr, stream));
+  return join_from(side, stream);
+}
+
+extern "C" int pvae_set_cell_overlap(int on) {
+  g_cell_overlap = on != 0;
+  return PVAE_OK;
 }
