@@ -17,6 +17,7 @@ from torch import nn
 
 from . import _lib
 from .linear import gemm_nn, gemm_nt, gemm_tn
+from . import rng
 from .rng import next_philox
 
 MULT = 2
@@ -31,8 +32,7 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def _s():
-    return torch.cuda.current_stream().cuda_stream
+_s = rng.launch_stream
 
 
 def _ints(v):

@@ -10,6 +10,7 @@ import torch
 from torch.nn import functional as F
 
 from . import _lib
+from . import rng
 from .rng import next_philox
 
 INDICATOR_CODES = {"sigmoid": 0, "cosine": 1, "linear": 2, "cubic": 3, "quintic": 4}  # base/distributions.py:294-300
@@ -40,8 +41,7 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+_stream = rng.launch_stream
 
 
 def _as_rows(t: torch.Tensor):

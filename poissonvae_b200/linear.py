@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
+from . import _lib, rng
 
 # 3xTF32 operand splitting (fp32-grade products).  False = single-pass TF32 (10-bit operands).
 PRECISE = True
@@ -36,7 +36,7 @@ def _gemm(a, b, out, m, n, kd, a_kmajor, b_kmajor):
     with torch.cuda.device(a.device):
         _lib.check(lib.pvae_gemm_tf32(a.data_ptr(), b.data_ptr(), out.data_ptr(), m, n, kd, a_kmajor, b_kmajor,
                                       int(PRECISE), splits, None if ws is None else ws.data_ptr(),
-                                      torch.cuda.current_stream().cuda_stream))
+                                      rng.launch_stream()))
     return out
 
 

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import _lib, dp
+from . import _lib, dp, rng
 from .distributions import INDICATOR_CODES, _ptr, _stream
 from . import linear as linear_mod
 from .rng import next_philox
@@ -140,6 +140,7 @@ class TrainerVAE:
 
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_inf = torch.zeros_like(self.flat_p)
+        self._names, self._params = names, params
         self.views, self.gviews, o = {}, {}, 0
         for k in names:
             p = params[k]
@@ -420,9 +421,13 @@ class TrainerVAE:
         reconstruction loss, no sampling) and the conv architectures.  The model's own blocks (our kernels under
         autograd) build the loss; one gather kernel packs the per-parameter gradients into the flat buffer and the
         usual exchange + clip + Adamax kernels follow."""
+        with rng.pinned_launch_stream():
+            return self._autograd_step(x, beta, lr, gstep, b, loss_out, row_offset, philox)
+
+    def _autograd_step(self, x, beta, lr, gstep, b, loss_out, row_offset, philox):
         cfg, m, lib, s = self.cfg, self.model, self.lib, _stream()
-        names = list(self.views)
-        params = dict(m.named_parameters())
+        names = self._names
+        params = self._params
         for k in names:
             params[k].grad = None
         xin = x.reshape(x.shape[0], 1, m.cfg.input_sz, m.cfg.input_sz)
