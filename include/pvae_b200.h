@@ -314,6 +314,8 @@ int pvae_cell_bwd(const pvae_cell* c, const float* x, const float* x_act, const 
 /* Tuning knob (process-wide, default on): pvae_cell_bwd runs the parameter-gradient kernels on an internal side stream
  * (forked from / joined back into the caller's stream with events) next to the data-gradient chain. */
 int pvae_set_cell_overlap(int on);
+/* Tuning knob (A/B measurements): pipeline depth / CTAs per SM of the narrow convolution tiles.  0 = default. */
+int pvae_set_conv_variant(int v);
 
 /* Tuning knob (process-wide): number of events each quad of latents walks thread-per-quad before a
  * still-unfinished chain is handed to a whole warp (32 events per step).  Default 8.  Results do

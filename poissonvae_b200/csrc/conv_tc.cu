@@ -51,7 +51,9 @@ struct ConvParams {
   const float* add_post;   // nullable: v += add_post[idx]
 };
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+// MUFU-based sigmoid (ex2.approx + rcp.approx, relative error ~3e-7): the epilogue evaluates it for every output element
+// while the tensor pipe idles, so its instruction count matters
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 __device__ __forceinline__ float dsilu_f(float x) {
   const float s = sigmoid_f(x);
@@ -637,6 +639,10 @@ static int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mg, const Wgra
 // fixed-order sum of split partials (gemm_tc.cu)
 int launch_splitk_reduce(const float* ws, float* C, long long n, int splits, cudaStream_t s);
 
+// tuning (A/B): 0 = default (narrow tiles: 2 stages, 2 CTAs per SM); 1 = 64-wide tiles with 4 stages / 1 CTA per SM;
+// 2 = 32-wide tiles with 4 stages / 1 CTA; 3 = 64-wide tiles also where 128-wide ones would fit
+static int g_conv_variant = 0;
+
 static int fill_taps(ConvParams& p, int ntaps, const int* dy, const int* dx, const int* widx) {
   if (ntaps < 0 || ntaps > kMaxTaps) return fail(PVAE_ERR_INVALID, "conv: %d taps not in [0, %d]", ntaps, kMaxTaps);
   p.ntaps = ntaps;
@@ -647,6 +653,12 @@ static int fill_taps(ConvParams& p, int ntaps, const int* dy, const int* dx, con
 }  // namespace pvae
 
 using namespace pvae;
+
+extern "C" int pvae_set_conv_variant(int v) {
+  if (v < 0 || v > 3) return fail(PVAE_ERR_INVALID, "pvae_set_conv_variant: %d not in [0, 3]", v);
+  g_conv_variant = v;
+  return PVAE_OK;
+}
 
 extern "C" int pvae_conv_weight_prep(const float* weight, const float* lognorm, const float* bias, float* w_fwd, float* w_dgrad,
                                      float* bias_pad, int Co, int Ci, int Co_pad, int Ci_pad, int ntaps, int groups, void* stream) {
@@ -688,7 +700,7 @@ extern "C" int pvae_conv_igemm(const float* in, const float* w_packed, float* ou
   p.out = out, p.out_act = out_act, p.bias = bias, p.add_pre = add_pre, p.dsilu_src = dsilu_src, p.add_post = add_post;
   CUtensorMap ma, mb;
   if (int rc = make_nhwc_map(&ma, in, NI, IH, IW, Ci, bw, bh, bi, stride, 0)) return rc;
-  const int BN = Co % 128 == 0 ? 128 : (Co % 64 == 0 ? 64 : 32);
+  const int BN = (Co % 128 == 0 && g_conv_variant != 3) ? 128 : (Co % 64 == 0 ? 64 : 32);
   {
     const long long dims[2] = {static_cast<long long>(wtaps) * Ci, Co}, strides[1] = {4ll * wtaps * Ci};
     const int box[2] = {32, BN}, estr[2] = {1, 1};
@@ -697,8 +709,8 @@ extern "C" int pvae_conv_igemm(const float* in, const float* w_packed, float* ou
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (precise) {
     if (BN == 128) return launch_conv<128, true, 3>(ma, mb, p, tiles, s);
-    if (BN == 64) return launch_conv<64, true, 4>(ma, mb, p, tiles, s);
-    return launch_conv<32, true, 2>(ma, mb, p, tiles, s);
+    if (BN == 64) return g_conv_variant == 1 ? launch_conv<64, true, 4>(ma, mb, p, tiles, s) : launch_conv<64, true, 2>(ma, mb, p, tiles, s);
+    return g_conv_variant == 2 ? launch_conv<32, true, 4>(ma, mb, p, tiles, s) : launch_conv<32, true, 2>(ma, mb, p, tiles, s);
   }
   if (BN == 128) return launch_conv<128, false, 6>(ma, mb, p, tiles, s);
   if (BN == 64) return launch_conv<64, false, 6>(ma, mb, p, tiles, s);

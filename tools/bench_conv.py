@@ -67,6 +67,7 @@ def main():
     ap.add_argument("--no_pdl", action="store_true", help="disable programmatic dependent launch (per-kernel times in a "
                     "profile are only meaningful without it: a dependent kernel's span includes its wait)")
     ap.add_argument("--no_overlap", action="store_true", help="keep a cell's weight-gradient kernels on the main stream (A/B)")
+    ap.add_argument("--conv_variant", type=int, default=0)
     ap.add_argument("--profile", action="store_true", help="print the per-kernel time table of one step (torch profiler)")
     args = ap.parse_args()
     import torch
@@ -94,6 +95,8 @@ def main():
         lib.pvae_set_pdl(0)
     if args.no_overlap:
         lib.pvae_set_cell_overlap(0)
+    if args.conv_variant:
+        lib.pvae_set_conv_variant(args.conv_variant)
     for i in range(args.warmup):
         tr.train_step(x, i)
     torch.cuda.synchronize()
