@@ -322,6 +322,10 @@ int pvae_set_conv_variant(int v);
  * not depend on the launch geometry, but the float summation order of a chain depends on this value. */
 int pvae_set_phase_a_events(int n);
 int pvae_set_absorb_exit(int on);
+/* Tuning knob (process-wide, default on): forward sampler schedule.  1: every lane of a warp takes the next quad of the
+ * warp's rows x 32 pool the moment its own chain ends (work-efficient under heavy-tailed chain lengths); 0: one row at a
+ * time in lock step.  Results are bit-identical. */
+int pvae_set_pool(int on);
 /* Tuning knob (process-wide): rows (samples) per thread block of the sampler kernels, 1..4; 0 = automatic.
  * Changes pvae_num_partials(); results of the forward are unaffected. */
 int pvae_set_rows_per_block(int n);

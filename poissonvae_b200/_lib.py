@@ -108,6 +108,7 @@ _SIGNATURES = {
     "pvae_layernorm_bwd": (_i, [_p] * 7 + [_i64, _i, _p]),
     "pvae_set_phase_a_events": (_i, [_i]),
     "pvae_set_absorb_exit": (_i, [_i]),
+    "pvae_set_pool": (_i, [_i]),
     "pvae_set_rows_per_block": (_i, [_i]),
     "pvae_debug_log_check": (_i, [_p, _p]),
     "pvae_debug_draws": (_i, [_p, _p, _i64, _i64, _i64, _i, _u64, _u64, _p, _p]),

@@ -60,6 +60,7 @@ struct SamplerParams {
   int rows_per_block;
   int n_exp;
   int phase_a;        // events walked thread-per-quad before a quad is parked for phase B
+  int pool;           // forward modes: lanes take the next quad of the warp's pool as soon as theirs ends
   float inv_temp;     // 1 / temp
   float sig_a;        // log2(e) / temp: sigmoid((1 - t) / temp) = 1 / (1 + 2^(sig_a * (t - 1)))
   float t_exit;       // leave a chain once every arrival time exceeds this (+inf: never)
@@ -191,10 +192,11 @@ __device__ __forceinline__ Latent prologue(const SamplerParams& p, float hv, flo
   return q;
 }
 
-template <int MODE, int IND, bool RAW>
+template <int MODE, int IND, bool RAW, bool POOL = false>
 __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p) {
   __shared__ float s_tab[kSlotWords][kSlots];  // parked quads, one word-plane per field
-  __shared__ unsigned short s_list[kWarps][kMaxRows * 32];  // each warp parks and finishes its own quads
+  __shared__ unsigned short s_list[kWarps][POOL ? kSlots : kMaxRows * 32];  // each warp finishes the quads it parked
+  __shared__ int s_next;                                    // POOL: cursor into the block's pool of quads
   __shared__ float s_rowsum[kMaxRows][kWarps];
   __shared__ float s_max[kWarps];
 
@@ -262,6 +264,140 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
     };
 
     // ---------------- phase A ----------------
+    if (POOL) {
+      // Work pool per warp.  Chain lengths are heavy-tailed (most quads need 1-2 events, some 8+): walking one row at
+      // a time in lock step leaves half of the lanes idle waiting for the slowest quad of the row.  Instead:
+      // stage 1 runs the prologue for all rows (uniform, coalesced) and leaves the rates in the warp's shared-memory
+      // slots; stage 2 lets every lane walk one quad and, the moment it ends, take the next one of the warp's
+      // nrows x 32 quads (ballot + prefix count, no atomics).  Per-chain arithmetic, Philox counters and exit rules
+      // are those of phase_a(): results are bit-identical to the row-by-row schedule.
+#pragma unroll 1
+      for (int r = 0; r < nrows; ++r) {
+        float klsum = 0.f;
+        if (act) {
+          const long long row = row0 + r;
+          const long long base = row * p.K + k;
+          const float4 hv4 = ldg4(p.h + base);
+          const float hv[4] = {hv4.x, hv4.y, hv4.z, hv4.w};
+          Latent q[4];
+          float rate[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            q[j] = prologue<RAW, false>(p, hv[j], lr[j], bias[j]);
+            rate[j] = q[j].rate;
+          }
+          if (p.rate != nullptr) stg4(p.rate + base, make_float4(rate[0], rate[1], rate[2], rate[3]));
+          if (p.rate_max != nullptr) rmax = fmaxf(fmaxf(fmaxf(rate[0], rate[1]), fmaxf(rate[2], rate[3])), rmax);
+          if (!RAW) {
+            if (p.log_dr != nullptr)
+              stg4(p.log_dr + base, make_float4(q[0].log_dr, q[1].log_dr, q[2].log_dr, q[3].log_dr));
+            if (p.kl != nullptr || p.kl_rowsum != nullptr) {
+              float klv[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float d = q[j].log_dr;
+                klv[j] = elr[j] * (1.f + expf(d) * (d - 1.f));  // main/vae.py:448-449
+              }
+              if (p.kl != nullptr) stg4(p.kl + base, make_float4(klv[0], klv[1], klv[2], klv[3]));
+              klsum = (klv[0] + klv[1]) + (klv[2] + klv[3]);
+            }
+          }
+          const int slot = r * kThreads + tid;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s_tab[j][slot] = rate[j];
+        }
+        if (want_rowsum) {
+          const float sum = warp_sum(klsum);
+          if (lane == 0) s_rowsum[r][warp] += sum;
+        }
+      }
+      // stage 2: the block's nrows x kThreads quads form one pool (entry index == slot index); a shared cursor hands
+      // out the next entries, one atomicAdd per warp and refill round
+      if (tid == 0) s_next = kThreads;
+      __syncthreads();
+      const int pool_n = nrows * kThreads;
+      const float t_exit = p.t_exit, absorb = p.absorb;
+      const int Kq = static_cast<int>(p.K >> 2), k0q = static_cast<int>(k0 >> 2);
+      const uint32_t quad0 = static_cast<uint32_t>(((p.row_offset + row0) * p.K) >> 2);
+      float* const z0 = p.z + row0 * p.K;
+      float* const dz0 = MODE == kFwdBoth ? p.dz_out + row0 * p.K : nullptr;
+      int cur = tid;  // this lane's pool entry: row cur / kThreads, column quad cur % kThreads
+      bool has = cur < pool_n, live = false;
+      int n = 0, ebase = 0;
+      uint32_t quad = 0;
+      float rate[4], inv_rate[4], t[4], acc[4], acc2[4];
+      auto fetch = [&]() {
+        live = false;
+        if (has) {
+          const int r = cur / kThreads, cq = k0q + cur % kThreads;  // row, column quad
+          if (cq < Kq) {
+            live = true;
+            ebase = (r * Kq + cq) << 2;
+            quad = quad0 + static_cast<uint32_t>(r * Kq + cq);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              rate[j] = s_tab[j][cur];
+              inv_rate[j] = recip_for_div(rate[j]);
+              t[j] = acc[j] = acc2[j] = 0.f;
+            }
+            n = 0;
+          }
+        }
+      };
+      fetch();
+      while (__any_sync(0xffffffffu, has)) {
+        bool fin = has && !live;  // an entry beyond the last column: nothing to do
+        bool park = false;
+        if (live) {
+          const uint4 rr = philox4x32_10(quad, static_cast<uint32_t>(n), off_lo, off_hi, p.ks);
+          const uint32_t bits[4] = {rr.x, rr.y, rr.z, rr.w};
+          float excess = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float e = exponential_from_bits(bits[j]);
+            t[j] = __fadd_rn(t[j], div_by_rate<false>(e, rate[j], inv_rate[j]));
+            float f, df = 0.f;
+            soft_term<IND, MODE == kFwdBoth>(p, t[j], f, df);
+            acc[j] += f;
+            excess = fmaxf(excess, fmaf(-absorb, acc[j], f));
+            if (MODE == kFwdBoth) {
+              const float g = df * t[j];
+              acc2[j] += g;
+              excess = fmaxf(excess, fmaf(-absorb, acc2[j], g));
+            }
+          }
+          ++n;
+          const float tmin = fminf(fminf(t[0], t[1]), fminf(t[2], t[3]));
+          if (tmin > t_exit || (tmin > 1.f && excess <= 0.f) || n >= p.n_exp) {  // chain complete
+            stg4(z0 + ebase, make_float4(acc[0], acc[1], acc[2], acc[3]));
+            if (MODE == kFwdBoth) stg4(dz0 + ebase, make_float4(acc2[0], acc2[1], acc2[2], acc2[3]));
+            fin = true;
+          } else if (n >= n_a) {  // a long chain: hand it to phase B
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              s_tab[4 + j][cur] = t[j];
+              s_tab[8 + j][cur] = acc[j];
+              if (MODE == kFwdBoth) s_tab[12 + j][cur] = acc2[j];
+            }
+            fin = park = true;
+          }
+        }
+        const unsigned fm = __ballot_sync(0xffffffffu, fin);
+        if (fm != 0u) {
+          const unsigned pm = __ballot_sync(0xffffffffu, park);
+          if (park) s_list[warp][n_parked + __popc(pm & lanes_below)] = static_cast<unsigned short>(cur);
+          n_parked += __popc(pm);
+          int first = 0;
+          if (lane == 0) first = atomicAdd(&s_next, __popc(fm));
+          first = __shfl_sync(0xffffffffu, first, 0);
+          if (fin) {
+            cur = first + __popc(fm & lanes_below);
+            has = cur < pool_n;
+            fetch();
+          }
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int r = 0; r < nrows; ++r) {
       float klsum = 0.f;
@@ -339,6 +475,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
     }
     __syncwarp();
 
+    }
     // ---------------- phase B (per warp) ----------------
     if (MODE != kFwdHard && MODE != kBwdSaved && n_parked > 0) {
       const int gl = lane % kGroup;
@@ -463,7 +600,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
         if (p.part_b != nullptr) stg4(p.part_b + pbase, make_float4(col_b[0], col_b[1], col_b[2], col_b[3]));
       }
     }
-    __syncwarp();  // the warp's slots are reused by the next pass
+    if (POOL) __syncthreads(); else __syncwarp();  // the slots are reused by the next pass
   }
 
   if (!kIsBwd) {
@@ -689,6 +826,17 @@ static int rows_per_block_for(long long B) {
 
 template <int MODE, bool RAW>
 static cudaError_t launch_ind(const SamplerParams& p, int indicator, dim3 grid, cudaStream_t s) {
+  if ((MODE == kFwdSoft || MODE == kFwdBoth) && p.pool) {  // work-pool schedule (forward modes)
+    constexpr int M = (MODE == kFwdSoft || MODE == kFwdBoth) ? MODE : kFwdSoft;
+    switch (indicator) {
+      case kSigmoid: return launch_pdl(sampler_kernel<M, kSigmoid, RAW, true>, grid, dim3(kThreads), 0, s, p);
+      case kCosine: return launch_pdl(sampler_kernel<M, kCosine, RAW, true>, grid, dim3(kThreads), 0, s, p);
+      case kLinear: return launch_pdl(sampler_kernel<M, kLinear, RAW, true>, grid, dim3(kThreads), 0, s, p);
+      case kCubic: return launch_pdl(sampler_kernel<M, kCubic, RAW, true>, grid, dim3(kThreads), 0, s, p);
+      case kQuintic: return launch_pdl(sampler_kernel<M, kQuintic, RAW, true>, grid, dim3(kThreads), 0, s, p);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (indicator) {
     case kSigmoid: return launch_pdl(sampler_kernel<MODE, kSigmoid, RAW>, grid, dim3(kThreads), 0, s, p);
     case kCosine: return launch_pdl(sampler_kernel<MODE, kCosine, RAW>, grid, dim3(kThreads), 0, s, p);
@@ -700,6 +848,7 @@ static cudaError_t launch_ind(const SamplerParams& p, int indicator, dim3 grid, 
 }
 
 static int g_phase_a_events = 8;
+static int g_pool = 1;  // forward modes: per-warp work pool (0: row-by-row lock step, the previous schedule)
 static bool g_absorb_exit = true;
 
 // Chain-control fields: temperature constants, early-exit threshold and the phase split.
@@ -708,6 +857,7 @@ static void set_chain(SamplerParams& p, int n_exp, float temp, int indicator, fl
   p.n_exp = n_exp;
   p.inv_temp = hard ? 0.f : 1.f / temp;
   p.sig_a = hard ? 0.f : 1.4426950408889634f / temp;
+  p.pool = g_pool && n_exp > 0;
   const int split = g_phase_a_events < n_exp ? g_phase_a_events : n_exp;
   p.absorb = 0.f;
   if (hard) {  // sequential fp32 running sum (bit-exact against torch's CUDA cumsum)
@@ -752,6 +902,11 @@ extern "C" int64_t pvae_num_partials(int64_t B) {
   if (B <= 0) return 0;
   const int r = rows_per_block_for(B);
   return (B + r - 1) / r;
+}
+
+extern "C" int pvae_set_pool(int on) {
+  g_pool = on != 0;
+  return PVAE_OK;
 }
 
 extern "C" int pvae_set_rows_per_block(int n) {
