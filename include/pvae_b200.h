@@ -324,7 +324,8 @@ int pvae_set_phase_a_events(int n);
 int pvae_set_absorb_exit(int on);
 /* Tuning knob (process-wide, default on): forward sampler schedule.  1: every lane of a warp takes the next quad of the
  * warp's rows x 32 pool the moment its own chain ends (work-efficient under heavy-tailed chain lengths); 0: one row at a
- * time in lock step.  Results are bit-identical. */
+ * time in lock step; 2: the pool on a grid of exactly one wave of resident blocks, each walking several row tiles (A/B:
+ * measured slower).  Results are bit-identical. */
 int pvae_set_pool(int on);
 /* Tuning knob (process-wide): rows (samples) per thread block of the sampler kernels, 1..4; 0 = automatic.
  * Changes pvae_num_partials(); results of the forward are unaffected. */

@@ -57,7 +57,8 @@ struct SamplerParams {
   float* part_log_r;  // (P,K)
   float* part_b;      // (P,K) or null
   long long B, K, row_offset;
-  int rows_per_block;
+  int rows_per_block;  // rows per tile (<= kMaxRows)
+  int rows_block;      // rows per block (a multiple of tiles)
   int n_exp;
   int phase_a;        // events walked thread-per-quad before a quad is parked for phase B
   int pool;           // forward modes: lanes take the next quad of the warp's pool as soon as theirs ends
@@ -204,8 +205,10 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
   pdl_wait();
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const long long row0 = static_cast<long long>(blockIdx.x) * p.rows_per_block;
-  const int nrows = static_cast<int>(min(static_cast<long long>(p.rows_per_block), p.B - row0));
+  // A block owns `rows_block` consecutive rows and walks them in tiles of up to `rows_per_block` rows (the shared-memory
+  // tables hold one tile).  rows_block == rows_per_block except with the optional one-wave grid (launch_pool).
+  const long long blk_row0 = static_cast<long long>(blockIdx.x) * p.rows_block;
+  const int blk_rows = static_cast<int>(min(static_cast<long long>(p.rows_block), p.B - blk_row0));
   uint64_t off = p.offset;
   if (p.offset_dev != nullptr) off += *p.offset_dev;
   const uint32_t off_lo = static_cast<uint32_t>(off), off_hi = static_cast<uint32_t>(off >> 32);
@@ -214,9 +217,13 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
   constexpr bool kIsBwd = MODE == kBwd || MODE == kBwdSaved;
   float rmax = 0.f;
   const bool want_rowsum = !kIsBwd && !RAW && p.kl_rowsum != nullptr;
+  const unsigned lanes_below = (1u << lane) - 1u;
+#pragma unroll 1
+  for (int tile_row = 0; tile_row < blk_rows; tile_row += p.rows_per_block) {
+  const long long row0 = blk_row0 + tile_row;
+  const int nrows = min(p.rows_per_block, blk_rows - tile_row);
   if (tid < kMaxRows * kWarps) (&s_rowsum[0][0])[tid] = 0.f;
   __syncthreads();
-  const unsigned lanes_below = (1u << lane) - 1u;
 
   // every thread runs every pass so that the block-level steps below see whole warps
   for (long long k0 = 0; k0 < p.K; k0 += kColsPerPass) {
@@ -603,16 +610,18 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
     if (POOL) __syncthreads(); else __syncwarp();  // the slots are reused by the next pass
   }
 
-  if (!kIsBwd) {
-    if (want_rowsum) {
-      __syncthreads();
-      if (tid < nrows) {
-        float s = 0.f;
+  if (!kIsBwd && want_rowsum) {
+    __syncthreads();
+    if (tid < nrows) {
+      float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += s_rowsum[tid][w];
-        p.kl_rowsum[row0 + tid] = s;
-      }
+      for (int w = 0; w < kWarps; ++w) s += s_rowsum[tid][w];
+      p.kl_rowsum[row0 + tid] = s;
     }
+  }
+  }  // tiles of this block's rows
+
+  if (!kIsBwd) {
     if (p.rate_max != nullptr) {
       const float m = warp_max(rmax);
       if (lane == 0) s_max[warp] = m;
@@ -824,16 +833,42 @@ static int rows_per_block_for(long long B) {
   return static_cast<int>(r);
 }
 
+static int g_one_wave = 0;  // work-pool schedule: size the grid to one wave of resident blocks (A/B knob, measured slower)
+
+// Work-pool forward.  Optional (pvae_set_pool(2)): a grid of ONE wave of resident blocks (occupancy x SM count, queried
+// once per kernel), a block owning ceil(B / resident) rows walked in equal tiles of at most kMaxRows rows.  Measured at
+// config 2: 49 us against 40 us for the plain grid of 3-row blocks - the hardware's dynamic block scheduling over 1366
+// short blocks balances the heavy-tailed work better than 1024 long ones - so it is off by default.
+template <typename Kern>
+static cudaError_t launch_pool(Kern kern, SamplerParams p, cudaStream_t s) {
+  static int resident = 0;  // one copy per kernel instantiation
+  if (resident == 0) {
+    int per_sm = 0, dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0) != cudaSuccess || per_sm < 1 || sms < 1)
+      per_sm = 4, sms = 148;
+    resident = per_sm * sms;
+  }
+  if (g_one_wave) {
+    const long long rows_block = std::max<long long>(1, (p.B + resident - 1) / resident);
+    const long long ntiles = (rows_block + kMaxRows - 1) / kMaxRows;
+    p.rows_block = static_cast<int>(rows_block);
+    p.rows_per_block = static_cast<int>((rows_block + ntiles - 1) / ntiles);
+  }
+  const dim3 grid(static_cast<unsigned>((p.B + p.rows_block - 1) / p.rows_block));
+  return launch_pdl(kern, grid, dim3(kThreads), 0, s, p);
+}
+
 template <int MODE, bool RAW>
 static cudaError_t launch_ind(const SamplerParams& p, int indicator, dim3 grid, cudaStream_t s) {
   if ((MODE == kFwdSoft || MODE == kFwdBoth) && p.pool) {  // work-pool schedule (forward modes)
     constexpr int M = (MODE == kFwdSoft || MODE == kFwdBoth) ? MODE : kFwdSoft;
     switch (indicator) {
-      case kSigmoid: return launch_pdl(sampler_kernel<M, kSigmoid, RAW, true>, grid, dim3(kThreads), 0, s, p);
-      case kCosine: return launch_pdl(sampler_kernel<M, kCosine, RAW, true>, grid, dim3(kThreads), 0, s, p);
-      case kLinear: return launch_pdl(sampler_kernel<M, kLinear, RAW, true>, grid, dim3(kThreads), 0, s, p);
-      case kCubic: return launch_pdl(sampler_kernel<M, kCubic, RAW, true>, grid, dim3(kThreads), 0, s, p);
-      case kQuintic: return launch_pdl(sampler_kernel<M, kQuintic, RAW, true>, grid, dim3(kThreads), 0, s, p);
+      case kSigmoid: return launch_pool(sampler_kernel<M, kSigmoid, RAW, true>, p, s);
+      case kCosine: return launch_pool(sampler_kernel<M, kCosine, RAW, true>, p, s);
+      case kLinear: return launch_pool(sampler_kernel<M, kLinear, RAW, true>, p, s);
+      case kCubic: return launch_pool(sampler_kernel<M, kCubic, RAW, true>, p, s);
+      case kQuintic: return launch_pool(sampler_kernel<M, kQuintic, RAW, true>, p, s);
       default: return cudaErrorInvalidValue;
     }
   }
@@ -904,8 +939,10 @@ extern "C" int64_t pvae_num_partials(int64_t B) {
   return (B + r - 1) / r;
 }
 
-extern "C" int pvae_set_pool(int on) {
+extern "C" int pvae_set_pool(int on) {  // 0: row-by-row lock step; 1: work pool (default); 2: work pool + one-wave grid
+  if (on < 0 || on > 2) return fail(PVAE_ERR_INVALID, "pvae_set_pool: %d not in [0, 2]", on);
   g_pool = on != 0;
+  g_one_wave = on == 2;
   return PVAE_OK;
 }
 
@@ -938,7 +975,7 @@ extern "C" int pvae_sampler_fwd(const float* h, const float* log_r, const float*
   p.h = h, p.log_r = log_r, p.b_enc = b_enc, p.z = z, p.log_dr = log_dr, p.rate = rate, p.kl = kl;
   p.kl_rowsum = kl_rowsum, p.rate_max = rate_max, p.dz_out = dz_acc;
   if (dz_acc && temp == 0.f) return fail(PVAE_ERR_INVALID, "pvae_sampler_fwd: hard counts (temp == 0) have no gradient (dz_acc)");
-  p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = rows_per_block_for(B);
+  p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = p.rows_block = rows_per_block_for(B);
   set_chain(p, n_exp, temp, indicator, exit_logit);
   p.clamp_dr = 10.f, p.clamp_rate = 5.f, p.exc_only = exc_only;  // main/vae.py:403-409
   p.offset = offset, p.offset_dev = offset_dev;
@@ -964,7 +1001,7 @@ extern "C" int pvae_sampler_bwd(const float* h, const float* log_r, const float*
     return fail(PVAE_ERR_INVALID, "pvae_sampler_bwd: null h/log_r/g_z/g_h/g_log_r/partial_ws");
   SamplerParams p{};
   p.h = h, p.log_r = log_r, p.b_enc = b_enc, p.g_z = g_z, p.g_log_dr = g_log_dr, p.g_h = g_h, p.dz_in = dz_acc;
-  p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = rows_per_block_for(B);
+  p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = p.rows_block = rows_per_block_for(B);
   const long long P = (B + p.rows_per_block - 1) / p.rows_per_block;
   p.part_log_r = partial_ws;
   p.part_b = g_b_enc ? partial_ws + P * K : nullptr;
@@ -997,7 +1034,7 @@ extern "C" int pvae_rsample_fwd(const float* log_rate, float* z, float* rate, fl
   SamplerParams p{};
   p.h = log_rate, p.z = z, p.rate = rate, p.dz_out = dz_acc;
   if (dz_acc && temp == 0.f) return fail(PVAE_ERR_INVALID, "pvae_rsample_fwd: hard counts (temp == 0) have no gradient (dz_acc)");
-  p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = rows_per_block_for(B);
+  p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = p.rows_block = rows_per_block_for(B);
   set_chain(p, n_exp, temp, indicator, exit_logit);
   p.clamp_rate = clamp;
   p.offset = offset, p.offset_dev = offset_dev;
@@ -1019,7 +1056,7 @@ extern "C" int pvae_rsample_bwd(const float* log_rate, const float* g_z, const f
   if (!log_rate || !g_z || !g_log_rate) return fail(PVAE_ERR_INVALID, "pvae_rsample_bwd: null pointer");
   SamplerParams p{};
   p.h = log_rate, p.g_z = g_z, p.g_h = g_log_rate, p.dz_in = dz_acc;
-  p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = rows_per_block_for(B);
+  p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = p.rows_block = rows_per_block_for(B);
   set_chain(p, n_exp, temp, indicator, exit_logit);
   p.clamp_rate = clamp;
   p.offset = offset, p.offset_dev = offset_dev;

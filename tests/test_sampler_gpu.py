@@ -403,13 +403,14 @@ def test_work_pool_schedule_is_bit_identical(lib, K):
             assert lib.pvae_set_phase_a_events(cap) == 0
             for temp in (1.0, 0.1):
                 outs = []
-                for pool in (1, 0):
+                for pool in (1, 0, 2):
                     assert lib.pvae_set_pool(pool) == 0
                     o = fused_fwd(lib, h, log_r, None, n_exp, temp, "sigmoid", False, seed, offset)
                     zs = rsample(lib, h, n_exp, temp, "cubic", seed, offset, clamp=5.0)  # z-only mode, another indicator
                     outs.append([o[k] for k in ("z", "dz", "log_dr", "rate", "kl", "kl_rowsum", "rate_max")] + [zs])
-                for a, b in zip(*outs):
-                    assert torch.equal(a, b)
+                for other in outs[1:]:
+                    for a, b in zip(outs[0], other):
+                        assert torch.equal(a, b)
     finally:
         lib.pvae_set_pool(1)
         lib.pvae_set_phase_a_events(8)
