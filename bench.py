@@ -32,8 +32,8 @@ UNIT = "samples/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
     ap.add_argument("--latents", type=int, default=512)
@@ -254,10 +254,12 @@ def run_ours(args):
     if clocks is not None:
         clocks.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = tr.lib.pvae_launch_count()
     e0.record()
     for i in range(K_steps):
         tr.train_step(data[(W + i) % NB], W + i)
     e1.record()
+    launches = tr.lib.pvae_launch_count() - launches0  # counted by the library itself, every launch of the timed region
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
@@ -317,7 +319,7 @@ def run_ours(args):
         "e2e": {"value": round(world * B * K_steps / e2e_s.item(), 1), "unit": UNIT,
                 "h2d_bytes_per_step": B * 256 * 4, "d2h_bytes_per_step": 12,
                 "host_enqueue_us_per_step": round(t_enq / K_steps * 1e6, 1)},
-        "gpu_launches": K_steps * tr.launches_per_step(),
+        "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4),
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/README.md);
