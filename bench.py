@@ -48,6 +48,10 @@ def parse():
                     help="N > 1: gradient exchange over NVLink peer memory fused with Adamax, or NCCL all-reduce")
     ap.add_argument("--no_overlap", action="store_true", help="keep the whole step on one stream (A/B)")
     ap.add_argument("--tf32", action="store_true", help="single-pass TF32 GEMMs instead of 3xTF32 (A/B)")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config4", "config5"],
+                    help="config2 (default): the BASELINE metric, lin|lin K=512.  config4 / config5: the secondary conv "
+                         "configurations (conv+b|lin CIFAR16-shaped; conv+b|conv+b MNIST-shaped 28x28), 1 GPU, with the CPU "
+                         "restatement of the reference's step beside them - not the driver's bench line")
     ap.add_argument("--ref_device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: 'cuda' times the same torch port of the reference's step with its "
                          "tensors on cuda:0 at the full batch (the reference's own CUDA path; north_star's denominator)")
@@ -141,6 +145,65 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
+def conv_cpu_port(dataset, archi, latents, n_exp, x_rows):
+    """The reference's conv step restated in plain torch on the host cores (oracle/conv_oracle.py, pinned to the
+    unmodified reference by tests/test_conv_oracle.py): forward + loss + autograd backward.  Returns (samples/s, cores)."""
+    import torch
+    from oracle import conv_oracle
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE, default_configs
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg_vae, _ = default_configs(dataset, "poisson", archi)
+    cfg_vae.update(n_latents=latents)
+    model = PoissonVAE(ConfigPoisVAE(seed=0, **cfg_vae))  # parameters only (CPU tensors); no kernel runs here
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in model.state_dict().items()}
+    xs = x_rows.cpu()
+    sc = lambda v, c: c - torch.nn.functional.softplus(c - v)
+
+    def step():
+        h = conv_oracle.conv_encoder(xs, sd, dataset)
+        log_dr = sc(h, 10.0)
+        rate = torch.exp(sc(sd["log_rate"] + log_dr, 5.0)) + 1.19e-7
+        e = rate.new(torch.Size((n_exp,)) + rate.shape).exponential_()
+        z = torch.sigmoid((1 - torch.cumsum(e / rate, 0)) / 1.0).sum(0)
+        y = conv_oracle.conv_decoder(z, sd, dataset) if model.cfg.dec_type == "conv" else (z @ sd["fc_dec.weight"].T).view(xs.shape)
+        kl = torch.exp(sd["log_rate"]) * (1 + torch.exp(log_dr) * (log_dr - 1))
+        loss = torch.mean(((y - xs) ** 2).sum(dim=[1, 2, 3]) + kl.sum(1))
+        for v in sd.values():
+            v.grad = None
+        loss.backward()
+
+    step()
+    t0 = time.perf_counter()
+    n = 3
+    for _ in range(n):
+        step()
+    return len(xs) * n / (time.perf_counter() - t0), os.cpu_count()
+
+
+def run_conv_workload(args):
+    """Secondary configurations 4 and 5: GPU timing by tools/bench_conv.run, CPU leg from the oracle."""
+    import types
+
+    import torch
+    from tools import bench_conv
+    cfg = {"config4": dict(dataset="CIFAR16", archi="conv+b|lin", batch=args.batch),
+           "config5": dict(dataset="MNIST", archi="conv+b|conv+b", batch=args.batch if args.batch != 4096 else 100)}[args.workload]
+    a = types.SimpleNamespace(batch=cfg["batch"], steps=args.steps, warmup=args.warmup, dataset=cfg["dataset"], archi=cfg["archi"],
+                              latents=args.latents, n_exp=args.n_exp, tf32=args.tf32, no_pdl=args.no_pdl, no_overlap=False,
+                              conv_variant=0, profile=False)
+    line = bench_conv.run(a)
+    line.update({"workload": args.workload, "n_gpus": 1, "higher_is_better": True, "dtype": "f32", "data": "synthetic"})
+    if not args.no_cpu_baseline:
+        sz = 28 if cfg["dataset"] == "MNIST" else 16
+        rows = max(4, min(args.cpu_rows, 32))
+        x = torch.randn(rows, 1, sz, sz, generator=torch.Generator().manual_seed(1234))
+        v, cores = conv_cpu_port(cfg["dataset"], cfg["archi"], args.latents, args.n_exp, x)
+        line["cpu_baseline"] = {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{rows} rows, 3 steps after 1 warm-up, fwd + loss + autograd bwd, torch CPU "
+                                          "restatement (oracle/conv_oracle.py)"}
+    print(json.dumps(line), flush=True)
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -344,6 +407,9 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse()
+    if a.workload != "config2" and a.impl == "ours":
+        run_conv_workload(a)
+        sys.exit(0)
     if a.impl == "reference":
         run_reference(a)
     else:

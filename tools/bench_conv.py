@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""Training-step throughput of the conv+b|lin P-VAE (BASELINE config 4: CIFAR16-shaped 16x16 patches, K = 512,
-implicit-GEMM conv encoder) on one B200, with the CPU restatement of the reference's step timed beside it.
+"""Training-step throughput of the conv P-VAEs (BASELINE config 4: conv+b|lin on CIFAR16-shaped 16x16 patches; config 5:
+conv+b|conv+b on MNIST-shaped 28x28, K = 512) on one B200.  GPU side only, with A/B knobs and a per-kernel profile;
+`python bench.py --workload config4|config5` runs the same measurement with the CPU restatement of the reference's
+step timed beside it.
 
-  python tools/bench_conv.py [--batch 1000] [--steps 20] [--warmup 5] [--dataset CIFAR16|MNIST] [--tf32] [--cpu_rows 32]
+  python tools/bench_conv.py [--batch 1000] [--steps 20] [--warmup 5] [--dataset CIFAR16|MNIST] [--archi ...] [--tf32]
 
-Prints one JSON line.  Not the headline benchmark (bench.py is); this is the secondary configuration of SURVEY 8d."""
+Prints one JSON line.  Not the headline benchmark (bench.py is): the secondary configurations of SURVEY 8d."""
 import argparse
 import json
 import os
@@ -13,43 +15,6 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-
-
-def cpu_port(args, x):
-    """oracle/conv_oracle.py + the sampler/loss in plain torch on the host cores (autograd backward, no optimiser)."""
-    import torch
-    from oracle import conv_oracle
-    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE, default_configs
-    torch.set_num_threads(os.cpu_count() or 1)
-    cfg_vae, _ = default_configs(args.dataset, "poisson", args.archi)
-    cfg_vae.update(n_latents=args.latents)
-    model = PoissonVAE(ConfigPoisVAE(seed=0, **cfg_vae))
-    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in model.state_dict().items()}
-    xs = x[:args.cpu_rows].cpu()
-    sc = lambda v, c: c - torch.nn.functional.softplus(c - v)
-
-    def step():
-        h = conv_oracle.conv_encoder(xs, sd, args.dataset)
-        log_dr = sc(h, 10.0)
-        rate = torch.exp(sc(sd["log_rate"] + log_dr, 5.0)) + 1.19e-7
-        e = rate.new(torch.Size((args.n_exp,)) + rate.shape).exponential_()
-        z = torch.sigmoid((1 - torch.cumsum(e / rate, 0)) / 1.0).sum(0)
-        if model.cfg.dec_type == "conv":
-            y = conv_oracle.conv_decoder(z, sd, args.dataset)
-        else:
-            y = (z @ sd["fc_dec.weight"].T).view(xs.shape)
-        kl = torch.exp(sd["log_rate"]) * (1 + torch.exp(log_dr) * (log_dr - 1))
-        loss = torch.mean(((y - xs) ** 2).sum(dim=[1, 2, 3]) + kl.sum(1))
-        for v in sd.values():
-            v.grad = None
-        loss.backward()
-
-    step()
-    t0 = time.perf_counter()
-    n = 3
-    for _ in range(n):
-        step()
-    return args.cpu_rows * n / (time.perf_counter() - t0), os.cpu_count()
 
 
 def main():
@@ -62,14 +27,19 @@ def main():
     ap.add_argument("--latents", type=int, default=512)
     ap.add_argument("--n_exp", type=int, default=263)
     ap.add_argument("--tf32", action="store_true")
-    ap.add_argument("--cpu_rows", type=int, default=32)
-    ap.add_argument("--no_cpu", action="store_true")
+    ap.add_argument("--no_cpu", action="store_true", help="(accepted for compatibility; the CPU leg lives in bench.py --workload)")
     ap.add_argument("--no_pdl", action="store_true", help="disable programmatic dependent launch (per-kernel times in a "
                     "profile are only meaningful without it: a dependent kernel's span includes its wait)")
     ap.add_argument("--no_overlap", action="store_true", help="keep a cell's weight-gradient kernels on the main stream (A/B)")
     ap.add_argument("--conv_variant", type=int, default=0)
     ap.add_argument("--profile", action="store_true", help="print the per-kernel time table of one step (torch profiler)")
     args = ap.parse_args()
+    line = run(args)
+    print(json.dumps(line), flush=True)
+
+
+def run(args):
+    """Times `args.steps` training steps; returns the result dict (also used by bench.py --workload)."""
     import torch
     from poissonvae_b200 import _lib, conv, linear
     from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
@@ -117,17 +87,13 @@ def main():
             "dataset": args.dataset, "n_exp": args.n_exp, "gpu_launches_per_step": (lib.pvae_launch_count() - c0) // args.steps,
             "gemm": "tf32 single pass" if args.tf32 else "3xTF32", "loss": [round(v, 4) for v in out.tolist()],
             "params": tr.flat_p.numel()}
-    if not args.no_cpu:
-        v, cores = cpu_port(args, x)
-        line["cpu_baseline"] = {"value": round(v, 2), "unit": "samples/s", "cores": cores, "kind": "port",
-                                "sample": f"{args.cpu_rows} rows, fwd + autograd bwd, torch CPU"}
-    print(json.dumps(line), flush=True)
     if args.profile:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             tr.train_step(x, args.warmup + args.steps)
             torch.cuda.synchronize()
         print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
+    return line
 
 
 if __name__ == "__main__":
