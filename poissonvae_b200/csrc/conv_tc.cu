@@ -636,9 +636,6 @@ static int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mg, const Wgra
   return cuda_ok("conv_wgrad_kernel", launch_pdl(conv_wgrad_kernel<BN, SPLIT, STAGES>, grid, dim3(kGemmThreads), smem, s, mx, mg, p));
 }
 
-// fixed-order sum of split partials (gemm_tc.cu)
-int launch_splitk_reduce(const float* ws, float* C, long long n, int splits, cudaStream_t s);
-
 // tuning (A/B): 0 = default (narrow tiles: 2 stages, 2 CTAs per SM); 1 = 64-wide tiles with 4 stages / 1 CTA per SM;
 // 2 = 32-wide tiles with 4 stages / 1 CTA; 3 = 64-wide tiles also where 128-wide ones would fit
 static int g_conv_variant = 0;
