@@ -48,6 +48,10 @@ def parse():
                     help="N > 1: gradient exchange over NVLink peer memory fused with Adamax, or NCCL all-reduce")
     ap.add_argument("--no_overlap", action="store_true", help="keep the whole step on one stream (A/B)")
     ap.add_argument("--tf32", action="store_true", help="single-pass TF32 GEMMs instead of 3xTF32 (A/B)")
+    ap.add_argument("--graph", default="off", choices=["auto", "on", "off"],
+                    help="CUDA-graph replay of the fused step (1 GPU; A/B - measured slower than the eager launches with "
+                         "programmatic dependent launch, so off by default): auto = small batches and the static staging "
+                         "buffers of the end-to-end path; on forces it")
     ap.add_argument("--workload", default="config2", choices=["config2", "config4", "config5"],
                     help="config2 (default): the BASELINE metric, lin|lin K=512.  config4 / config5: the secondary conv "
                          "configurations (conv+b|lin CIFAR16-shaped; conv+b|conv+b MNIST-shaped 28x28), 1 GPU, with the CPU "
@@ -64,7 +68,8 @@ def workload(args):
             "batch_per_gpu": args.batch, "n_latents": args.latents, "n_exp": args.n_exp, "temp": args.temp,
             "input": "16x16 z-scored N(0,1) patches, seed 1234; weights N(0,0.05^2), log_rate U(-6,-4), cfg.seed 0",
             "gemm": "tf32 single pass" if getattr(args, "tf32", False) else "3xTF32 (fp32-grade, tcgen05)",
-            "schedule": "reference vH16 lr warm-up (lr .005, 1 % of 78000 iterations), beta and temp pinned"}
+            "schedule": "reference vH16 lr warm-up (lr .005, 1 % of 78000 iterations), beta and temp pinned",
+            "graph": getattr(args, "graph", "off")}
 
 
 def synthetic_patches(n, seed):
@@ -288,6 +293,7 @@ def run_ours(args):
                          kl_beta=args.beta, kl_anneal_portion=0.0, kl_const_portion=0.0, temp_anneal_portion=0.0,
                          temp_stop=args.temp)
     tr = TrainerVAE(model, cfg, n_batches_per_epoch=26, dp_mode=args.dp)
+    tr.graph = {"auto": "auto", "on": True, "off": False}[args.graph]
 
     # inputs: 64 distinct batches (268 MB at B=4096 > 126 MB L2) so that no step finds its input in L2
     NB = 64

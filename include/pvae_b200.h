@@ -157,6 +157,14 @@ int pvae_loss_assemble(const float* recon, const float* kl_rowsum, float* out3, 
                        int recon_parts, void* stream);
 int64_t pvae_grad_norm_ws_floats(void);
 int pvae_grad_norm(const float* g, int64_t n, float max_norm, float* ws, float* out2, void* stream);
+/* Adamax with every step-dependent scalar on the device, for CUDA-graph replay of a whole training step: `state` is 4 ints on
+ * the device: [optimiser steps taken so far, -, Philox offset (uint64 in ints 2..3)]; lr_sched[i] is the learning rate of
+ * optimiser step i + 1 (clamped at n_sched - 1).  A one-thread kernel enqueued right behind the update advances the step
+ * counter by 1 and the Philox offset by philox_increment, so the sampler launches of the next replay (which read the offset
+ * through their offset_dev argument) draw fresh numbers without any host-side parameter. */
+int pvae_adamax_step_dev(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, const float* lr_sched, int n_sched,
+                         int* state, float beta1, float beta2, float eps, float weight_decay, const float* clip_coef,
+                         uint64_t philox_increment, void* stream);
 /* Gather n_tensors device arrays into one flat buffer: dst[offsets[i] .. offsets[i+1]) = srcs[i] (zeros where srcs[i] is
  * NULL).  srcs / offsets are HOST arrays (offsets has n_tensors + 1 entries).  One launch per 96 tensors: the per-parameter
  * gradients autograd hands out become the flat buffer the all-reduce / clip / Adamax kernels work on. */

@@ -68,6 +68,7 @@ _SIGNATURES = {
     "pvae_gemm_tf32_residual": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _i, _p]),
     "pvae_grad_norm_ws_floats": (_i64, []),
     "pvae_grad_norm": (_i, [_p, _i64, _f, _p, _p, _p]),
+    "pvae_adamax_step_dev": (_i, [_p, _p, _p, _p, _i64, _p, _i, _p, _f, _f, _f, _f, _p, _u64, _p]),
     "pvae_gather": (_i, [_p, _p, _i, _p, _p]),
     "pvae_adamax_step": (_i, [_p, _p, _p, _p, _i64, _f, _i, _f, _f, _f, _f, _p, _p]),
     "pvae_allreduce_adamax": (_i, [_p, _p, _p, _i64, _i64, _p, _p, _i, _i, C.c_uint32, _p, _p, _f, _i, _f, _f, _f, _f, _p]),

@@ -113,6 +113,40 @@ __global__ void __launch_bounds__(256) adamax_kernel(float* __restrict__ p, cons
   }
 }
 
+// ---- Adamax with the step-dependent scalars on the device (CUDA-graph replay of a training step) -------------
+// state[0] = number of optimiser steps taken so far (int), state[2..3] = Philox offset of the step (uint64).
+// lr_sched[i] = learning rate of optimiser step i + 1.  The kernel reads the counter, the advance kernel that follows
+// it in the stream bumps the counter and the Philox offset - so a captured graph replays step after step with no
+// host-side parameter at all.
+__global__ void __launch_bounds__(256) adamax_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ u, long long n, const float* __restrict__ lr_sched,
+                                                         int n_sched, const int* __restrict__ state, float beta1, float beta2,
+                                                         float eps, float weight_decay, const float* __restrict__ clip_coef) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int step = state[0] + 1;
+  const float lr = lr_sched[min(step - 1, n_sched - 1)];
+  const float clr = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(beta1), step)));  // base/adamax.py:75-76
+  const float cc = clip_coef != nullptr ? clip_coef[1] : 1.f;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
+    float gi = g[i] * cc;
+    const float pi = p[i];
+    if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
+    const float mi = m[i] * beta1 + (1.f - beta1) * gi;
+    const float ui = fmaxf(u[i] * beta2, fabsf(gi) + eps);
+    m[i] = mi;
+    u[i] = ui;
+    p[i] = pi - clr * (mi / ui);
+  }
+}
+__global__ void advance_state_kernel(int* __restrict__ state, unsigned long long philox_increment) {
+  pdl_wait();  // every reader of this step's counters has been launched before us and the predecessor has finished
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    state[0] += 1;
+    *reinterpret_cast<unsigned long long*>(state + 2) += philox_increment;
+  }
+}
+
 // ---- gather up to kGatherMax gradient tensors into the flat buffer (one launch instead of one copy each) ----
 constexpr int kGatherMax = 96;
 struct GatherTable {
@@ -135,6 +169,24 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
 }  // namespace pvae
 
 using namespace pvae;
+
+extern "C" int pvae_adamax_step_dev(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, const float* lr_sched,
+                                    int n_sched, int* state, float beta1, float beta2, float eps, float weight_decay,
+                                    const float* clip_coef, uint64_t philox_increment, void* stream) {
+  if (n <= 0 || !p || !g || !exp_avg || !exp_inf || !lr_sched || n_sched < 1 || !state)
+    return fail(PVAE_ERR_INVALID, "pvae_adamax_step_dev: bad argument");
+  if (reinterpret_cast<uintptr_t>(state) & 7) return fail(PVAE_ERR_INVALID, "pvae_adamax_step_dev: state must be 8-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((n + 255) / 256, 148ll * 8));
+  if (int rc = cuda_ok("pvae_adamax_step_dev", launch_pdl(adamax_dev_kernel, dim3(grid), dim3(256), 0, s, p, g, exp_avg, exp_inf,
+                                                          static_cast<long long>(n), lr_sched, n_sched, static_cast<const int*>(state),
+                                                          beta1, beta2, eps, weight_decay, clip_coef)))
+    return rc;
+  // plain launch (no programmatic overlap): it must not run before the Adamax kernel has read the counter
+  advance_state_kernel<<<1, 32, 0, s>>>(state, static_cast<unsigned long long>(philox_increment));
+  count_launch();
+  return cuda_ok("advance_state_kernel", cudaGetLastError());
+}
 
 extern "C" int pvae_gather(const void* const* srcs, const int64_t* offsets, int n_tensors, float* dst, void* stream) {
   if (!srcs || !offsets || !dst || n_tensors < 0) return fail(PVAE_ERR_INVALID, "pvae_gather: bad argument");

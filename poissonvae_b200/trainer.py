@@ -113,6 +113,15 @@ class TrainerVAE:
             raise ValueError("dp_mode='peer' does not support grad_clip")
         self.r_max = torch.zeros(max(n_batches_per_epoch, 1), device=self.device)  # rate.max() of each step of the epoch
         self._gather_tab = None
+        # CUDA-graph replay of the fused lin|lin step (single GPU), see _graph_step.  OFF by default: measured slower than
+        # the eager launches (73.7 vs 69.6 us per step at batch 200, 104 vs 78 us at batch 1024, end-to-end 31.6 M vs 34.0 M
+        # samples/s at batch 4096) although the host enqueue time halves (91 -> 49 us): the step is bound by the GPU, and
+        # between the kernel nodes of a replayed graph the programmatic-dependent-launch overlap of the eager stream
+        # (every kernel's prologue under its predecessor's tail) is lost.  True forces it; 'auto' = small or static inputs.
+        self.graph = False
+        self._graphs = {}
+        self._graph_static = set()  # data_ptr() of input buffers that stay put (fit_host's staging slots)
+        self._gstate = None
         self.kernel_events = None  # set to {} to record CUDA events around the named launches (bench.py)
         self._stream_handle = None  # fit_host pins the launch stream for the duration of its loop
         self._copy_stream = None
@@ -246,6 +255,13 @@ class TrainerVAE:
             self._chunk_free = [torch.cuda.Event(), torch.cuda.Event()]
             self._loss_ring = torch.empty(2 * chunk, 4, device=self.device, dtype=torch.float32)
             self._loss_ev = [torch.cuda.Event() for _ in range(2 * chunk)]
+            for buf in self._chunk_bufs:  # static input buffers: their steps can be replayed as CUDA graphs
+                for j in range(chunk):
+                    self._graph_static.add(buf[j].data_ptr())
+        if self.fused and self.world == 1 and self.graph is not False and self.cfg.method == 'mc' and not direct:
+            for slot in range(2):
+                for j in range(chunk):
+                    self.precapture(self._chunk_bufs[slot][j].reshape(shape[1], -1), first_gstep, self._loss_ring[slot * chunk + j])
         main = torch.cuda.current_stream()
         cs = self._copy_stream
         # every step's [loss, mse, kl] lands in a small device ring and is copied back on the side stream, so the
@@ -330,6 +346,8 @@ class TrainerVAE:
         n = self.flat_p.numel()
         if cfg.method == 'exact' or not self.fused:
             return self._train_step_autograd(x, beta, lr, gstep, b, loss_out, row_offset, (seed, offset))
+        if philox is None and self._graph_wanted(x2, gstep):
+            return self._graph_step(x2, gstep, temp, beta, n_exp, ind, seed, offset, loss_out)
         # where this step's gradients and its [loss, mse, kl] shares go
         if self.peer is not None:  # symmetric double buffer, alternating with the exchange token's parity
             self._peer_token += 1  # strictly increasing for the life of the exchange (never rewound with opt_step)
@@ -415,6 +433,110 @@ class TrainerVAE:
                 'kl_diag': out['kl_diag'].mean(0)}
         etc = {'log_dr': out['log_dr'], 'r*dr': out['rate']}
         return data_out, loss, etc
+
+    # -- CUDA-graph replay of the fused step ---------------------------------------------------------
+    def _graph_wanted(self, x2, gstep):
+        if self.graph is False or self.world > 1 or self.kernel_events is not None or gstep != self.opt_step:
+            return False
+        nxt = min(gstep + 1, self.n_iters - 1)
+        if self.temperatures[min(gstep, self.n_iters - 1)] != self.temperatures[nxt] or self.betas[min(gstep, self.n_iters - 1)] != self.betas[nxt]:
+            return False  # annealing: this step's scalars are used once - a graph would be captured for nothing
+        if self.graph is True:
+            return True
+        # 'auto': where the 12-14 launches, not the kernels, set the pace (small batches), or where the caller promised
+        # static input buffers (fit_host registers its staging slots)
+        return x2.data_ptr() in self._graph_static or x2.numel() <= (1 << 18)
+
+    def _graph_step(self, x2, gstep, temp, beta, n_exp, ind, seed, offset, loss_out):
+        """One training step as ONE cudaGraphLaunch.  The graph holds the 12-14 kernels of the fused step (forward, loss,
+        backward, clip, Adamax) with the step-dependent scalars on the device: the learning-rate schedule is a device
+        array indexed by a device step counter, the Philox offset is a device word read by the sampler kernels
+        (`offset_dev`); a one-thread kernel at the end of the graph advances both.  A graph is specific to (input
+        buffer, batch, temp, beta, n_exp, clip threshold): while the temperature anneals every step differs and the
+        eager path runs instead; inputs that are neither registered static buffers nor small are stepped eagerly too."""
+        cfg, m, lib = self.cfg, self.model, self.lib
+        B, D = x2.shape
+        if self._gstate is None:
+            self._gstate = torch.zeros(4, device=self.device, dtype=torch.int32)
+            self._gstate_host = [-1, -1]  # what the device words hold (step count, Philox offset)
+            self._lr_sched = torch.tensor([self.lr_at(i) for i in range(self.n_iters)], device=self.device, dtype=torch.float32)
+            self._gstate_pin = torch.zeros(2, dtype=torch.int64).pin_memory()  # [step count | Philox offset] = the 4 device ints
+        static_in = x2.data_ptr() in self._graph_static
+        warming = cfg.grad_clip is not None and gstep / self.n_iters < cfg.warmup_portion
+        key = (x2.data_ptr() if static_in else 0, B, temp, beta, n_exp, seed, warming,
+               0 if loss_out is None else loss_out.data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= 256:
+                self._graphs.clear()
+            g = self._graphs[key] = self._capture(x2 if static_in else None, B, D, temp, beta, n_exp, ind, seed, warming, loss_out)
+        # device counters: rewritten only when they are not what the previous replay left behind (first use, restore,
+        # a generator that was re-seeded or advanced by somebody else)
+        if self._gstate_host != [self.opt_step, offset]:
+            self._gstate_pin[0] = self.opt_step
+            self._gstate_pin[1] = offset
+            self._gstate.view(torch.int64).copy_(self._gstate_pin, non_blocking=True)
+        if not static_in:
+            g['x'].copy_(x2, non_blocking=True)
+        g['graph'].replay()
+        self.opt_step += 1
+        self._gstate_host = [self.opt_step, offset + 4]
+        return g['loss'][:3]
+
+    def precapture(self, x2, gstep, loss_out=None):
+        """Build the graph a later train_step(x2, gstep, loss_out=loss_out) would replay, without running it (captures
+        cost about a millisecond each: callers with static buffers pay that before their loop, not inside it)."""
+        if not (self.fused and self.cfg.method == 'mc' and self.world == 1 and self.graph is not False):
+            return
+        m = self.model
+        temp = float(self.temperatures[min(gstep, self.n_iters - 1)])
+        beta = float(self.betas[min(gstep, self.n_iters - 1)])
+        seed = torch.cuda.default_generators[self.device.index].initial_seed()
+        if self._gstate is None:
+            self._gstate = torch.zeros(4, device=self.device, dtype=torch.int32)
+            self._gstate_host = [-1, -1]
+            self._lr_sched = torch.tensor([self.lr_at(i) for i in range(self.n_iters)], device=self.device, dtype=torch.float32)
+            self._gstate_pin = torch.zeros(2, dtype=torch.int64).pin_memory()
+        warming = self.cfg.grad_clip is not None and gstep / self.n_iters < self.cfg.warmup_portion
+        static_in = x2.data_ptr() in self._graph_static
+        key = (x2.data_ptr() if static_in else 0, x2.shape[0], temp, beta, m._n_exp_host, seed, warming,
+               0 if loss_out is None else loss_out.data_ptr())
+        if key not in self._graphs:
+            self._graphs[key] = self._capture(x2 if static_in else None, x2.shape[0], x2.shape[1], temp, beta, m._n_exp_host,
+                                              INDICATOR_CODES[m.cfg.indicator_approx], seed, warming, loss_out)
+
+    def _capture(self, x_static, B, D, temp, beta, n_exp, ind, seed, warming, loss_out):
+        cfg, m, lib = self.cfg, self.model, self.lib
+        K, n = m.cfg.n_latents, self.flat_p.numel()
+        b = self._buffers(B)
+        x = x_static if x_static is not None else torch.empty(B, D, device=self.device, dtype=torch.float32)
+        loss = loss_out if loss_out is not None else torch.zeros(4, device=self.device, dtype=torch.float32)
+        rmax = self.r_max[:1]
+        off_dev = self._gstate.data_ptr() + 8
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        graph = torch.cuda.CUDAGraph()
+        pinned, self._stream_handle = self._stream_handle, None
+        try:
+            with torch.cuda.graph(graph, stream=side):
+                s = torch.cuda.current_stream().cuda_stream
+                _lib.check(lib.pvae_lin_step_fwd_bwd(
+                    _ptr(x), _ptr(self.flat_p), _ptr(self._flat_g_ext), _ptr(b['ws']), _ptr(loss), _ptr(rmax), B, B, 0, K, D,
+                    int(m.fc_enc.bias is not None), n_exp, temp, beta, ind, int(m.cfg.exc_only), m.exit_logit,
+                    int(linear_mod.PRECISE), seed, 0, off_dev, None, s))
+                clip = None
+                if cfg.grad_clip is not None:
+                    _lib.check(lib.pvae_grad_norm(_ptr(self._flat_g_ext), n, cfg.grad_clip * (3 if warming else 1), _ptr(b['nws']),
+                                                  _ptr(b['norm']), s))
+                    clip = b['norm']
+                _lib.check(lib.pvae_adamax_step_dev(_ptr(self.flat_p), _ptr(self._flat_g_ext), _ptr(self.exp_avg), _ptr(self.exp_inf),
+                                                    n, _ptr(self._lr_sched), self._lr_sched.numel(), _ptr(self._gstate), cfg.betas[0],
+                                                    cfg.betas[1], cfg.eps, cfg.weight_decay, _ptr(clip), 4, s))
+        finally:
+            self._stream_handle = pinned
+        cur.wait_stream(side)
+        return dict(graph=graph, x=x, loss=loss)
 
     def _train_step_autograd(self, x, beta, lr, gstep, b, loss_out, row_offset, philox):
         """The step for everything but fused lin|lin: method='exact' (main/train_vae.py:703-705, closed-form

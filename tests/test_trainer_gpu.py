@@ -157,3 +157,46 @@ def test_validate_pass_hard_counts():
     # the decoder sees the counts: y = z W_dec^T
     w = model.fc_dec.weight.detach().cpu().numpy().astype(np.float64)
     assert_rel(y, d['z'].astype(np.float64) @ w.T, rtol=2e-5, what="decode(hard counts)")
+
+
+def test_graph_replay_matches_eager_steps():
+    """CUDA-graph replay of the fused step (device-side step counter, lr schedule and Philox offset) against the
+    eager launches: same parameters and losses step after step, through a change of n_exp (re-capture), a restore of
+    the optimiser state (counters rewritten) and the hand-over back to the eager path."""
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
+    g = torch.Generator().manual_seed(9)
+    data = torch.randn(12, 64, 256, generator=g).cuda()
+    out = {}
+    for mode in (True, False):
+        model = PoissonVAE(ConfigPoisVAE(n_latents=128, prior_clamp=-4, seed=3)).cuda()
+        with torch.no_grad():
+            model.log_rate.add_(3.0)
+        model.update_n(30.0)
+        tr = TrainerVAE(model, ConfigTrainVAE(lr=0.01, epochs=40, batch_size=64, temp_anneal_portion=0.0, temp_stop=0.5,
+                                              kl_anneal_portion=0.0, kl_const_portion=0.0, grad_clip=50.0, warmup_portion=0.1),
+                        n_batches_per_epoch=1)
+        tr.graph = mode
+        torch.cuda.manual_seed(77)
+        losses = []
+        for i in range(8):  # crosses the lr warm-up boundary (clip threshold changes -> another graph)
+            if i == 5:
+                model.update_n(12.0)
+            losses.append(tr.train_step(data[i], i).clone())
+        snap = (tr.flat_p.clone(), tr.exp_avg.clone(), tr.exp_inf.clone(), tr.opt_step)
+        for i in range(8, 10):
+            losses.append(tr.train_step(data[i], i).clone())
+        tr.flat_p.copy_(snap[0]), tr.exp_avg.copy_(snap[1]), tr.exp_inf.copy_(snap[2])  # rewind two steps
+        tr.opt_step = snap[3]
+        torch.cuda.default_generators[0].set_offset(torch.cuda.default_generators[0].get_offset() - 8)
+        for i in range(8, 10):
+            losses.append(tr.train_step(data[i], i).clone())
+        tr.graph = False  # hand over to the eager path
+        losses.append(tr.train_step(data[10], 10).clone())
+        if mode:
+            assert len(tr._graphs) >= 3
+        out[mode] = (tr.flat_p.clone(), torch.stack(losses))
+    assert_rel(out[True][1].cpu().numpy(), out[False][1].cpu().numpy(), rtol=1e-6, what="losses graph vs eager")
+    assert_rel(out[True][0].cpu().numpy(), out[False][0].cpu().numpy(), rtol=1e-6, what="parameters graph vs eager")
+    l = out[True][1]
+    assert torch.equal(l[8:10], l[10:12])  # the rewound steps reproduce themselves bit for bit
