@@ -157,6 +157,24 @@ int pvae_loss_assemble(const float* recon, const float* kl_rowsum, float* out3, 
                        int recon_parts, void* stream);
 int64_t pvae_grad_norm_ws_floats(void);
 int pvae_grad_norm(const float* g, int64_t n, float max_norm, float* ws, float* out2, void* stream);
+/* Gradient reduction fused with Adamax (single GPU, no clipping): a parameter segment [offset, offset + length) of the flat
+ * buffer takes its gradient from `n_partials` partial sums - columnar = 1: rows of `length` floats (column partials of
+ * the sampler backward; reduced like its own column-sum kernel), columnar = 0: split-K partials `stride` floats apart
+ * (pvae_gemm_tf32 called with C = NULL leaves them in the workspace), partials = NULL: g_out already holds it.  One
+ * kernel reduces (bit-identical to the stand-alone reductions), stores the gradient into g_out and updates p / exp_avg /
+ * exp_inf as pvae_adamax_step does. */
+typedef struct pvae_grad_segment {
+  int64_t offset, length;
+  const float* partials;
+  int n_partials;
+  int columnar;
+  int64_t stride;
+} pvae_grad_segment;
+int pvae_adamax_from_partials(float* p, float* g_out, float* exp_avg, float* exp_inf, const pvae_grad_segment* segs, int n_segs,
+                              float lr, int step, float beta1, float beta2, float eps, float weight_decay, void* stream);
+int pvae_gemm_effective_splits(int64_t Kd, int splits);
+int64_t pvae_sampler_bwd_partial_rows(int64_t B);
+int64_t pvae_sampler_bwd_bias_offset_rows(int64_t B);
 /* Adamax with every step-dependent scalar on the device, for CUDA-graph replay of a whole training step: `state` is 4 ints on
  * the device: [optimiser steps taken so far, -, Philox offset (uint64 in ints 2..3)]; lr_sched[i] is the learning rate of
  * optimiser step i + 1 (clamped at n_sched - 1).  A one-thread kernel enqueued right behind the update advances the step
@@ -197,6 +215,15 @@ int pvae_allreduce_adamax(float* p, float* exp_avg, float* exp_inf, int64_t n, i
  *   precise: GEMM mode (see pvae_gemm_tf32); events: NULL or 4 cudaEvent_t recorded before/after the sampler
  *   forward (0,1) and before/after the sampler backward (2,3) - used by bench.py for the roofline timing. */
 int64_t pvae_lin_step_ws_floats(int64_t B, int64_t K, int64_t D);
+/* pvae_lin_step_fwd_bwd followed by the optimiser in the same call: the wgrad split partials and the sampler's column
+ * partials are reduced inside ONE Adamax kernel (pvae_adamax_from_partials) instead of three reduction kernels + Adamax.
+ * Single GPU (B_global == B), no gradient clipping.  grads receives the gradient as before; results are bit-identical to
+ * pvae_lin_step_fwd_bwd + pvae_adamax_step. */
+int pvae_lin_step_train(const float* x, float* params, float* grads, float* exp_avg, float* exp_inf, float* ws, float* loss3,
+                        float* rate_max, int64_t B, int64_t K, int64_t D, int has_bias, int n_exp, float temp, float beta,
+                        int indicator, int exc_only, float exit_logit, int precise, uint64_t seed, uint64_t offset,
+                        const uint64_t* offset_dev, void* const* events, float lr, int step, float beta1, float beta2, float eps,
+                        float weight_decay, void* stream);
 /* Tuning knob (process-wide, default on): run the decoder wgrad and the loss assembly of pvae_lin_step_fwd_bwd on
  * an internal side stream (forked from / joined back into the caller's stream with events). */
 int pvae_set_step_overlap(int on);

@@ -68,6 +68,11 @@ _SIGNATURES = {
     "pvae_gemm_tf32_residual": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _i, _p]),
     "pvae_grad_norm_ws_floats": (_i64, []),
     "pvae_grad_norm": (_i, [_p, _i64, _f, _p, _p, _p]),
+    "pvae_adamax_from_partials": (_i, [_p, _p, _p, _p, _p, _i, _f, _i, _f, _f, _f, _f, _p]),
+    "pvae_gemm_effective_splits": (_i, [_i64, _i]),
+    "pvae_sampler_bwd_partial_rows": (_i64, [_i64]),
+    "pvae_sampler_bwd_bias_offset_rows": (_i64, [_i64]),
+    "pvae_lin_step_train": (_i, [_p] * 8 + [_i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i, _u64, _u64, _p, _p, _f, _i, _f, _f, _f, _f, _p]),
     "pvae_adamax_step_dev": (_i, [_p, _p, _p, _p, _i64, _p, _i, _p, _f, _f, _f, _f, _p, _u64, _p]),
     "pvae_gather": (_i, [_p, _p, _i, _p, _p]),
     "pvae_adamax_step": (_i, [_p, _p, _p, _p, _i64, _f, _i, _f, _f, _f, _f, _p, _p]),

@@ -398,6 +398,14 @@ using namespace pvae;
 
 extern "C" int64_t pvae_gemm_ws_floats(int64_t M, int64_t N, int splits) { return splits > 1 ? splits * M * N : 0; }
 
+extern "C" int pvae_gemm_effective_splits(int64_t Kd, int splits) {
+  if (splits < 1) splits = 1;
+  const long long kblocks = (Kd + kBK - 1) / kBK;
+  if (splits > kblocks) splits = static_cast<int>(kblocks);
+  const long long per = (kblocks + splits - 1) / splits;  // every split owns at least one K block
+  return static_cast<int>((kblocks + per - 1) / per);
+}
+
 extern "C" int pvae_set_gemm_variant(int v) {
   if (v < 0 || v > 2) return fail(PVAE_ERR_INVALID, "pvae_set_gemm_variant: %d not in [0, 2]", v);
   g_gemm_variant = v;
@@ -411,7 +419,7 @@ static int gemm_impl(const float* A, const float* B, float* C, int64_t M, int64_
   if (M % 4 || N % 4 || Kd % 4)
     return fail(PVAE_ERR_UNSUPPORTED, "pvae_gemm_tf32: M=%lld N=%lld K=%lld must be multiples of 4 (16-byte TMA strides)",
                 (long long)M, (long long)N, (long long)Kd);
-  if (!A || !B || (!C && !X)) return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: null pointer");
+  if (!A || !B || (!C && !X && !(splits > 1 && splitk_ws))) return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: null pointer");
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) |
        reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(G)) & 15)
     return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: pointers must be 16-byte aligned");
@@ -450,6 +458,7 @@ static int gemm_impl(const float* A, const float* B, float* C, int64_t M, int64_
   }
   if (rc) return rc;
   if (splits > 1) {
+    if (!C) return PVAE_OK;  // partials only: the caller reduces them (pvae_adamax_from_partials)
     return launch_splitk_reduce(splitk_ws, C, M * N, splits, s);
   }
   return PVAE_OK;

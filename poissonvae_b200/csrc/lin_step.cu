@@ -83,11 +83,18 @@ extern "C" int64_t pvae_lin_step_ws_floats(int64_t B, int64_t K, int64_t D) {
   return carve(nullptr, B, K, D).total;
 }
 
-extern "C" int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, float* ws, float* loss3,
-                                     float* rate_max, int64_t B, int64_t B_global, int64_t row_offset, int64_t K, int64_t D,
-                                     int has_bias, int n_exp, float temp, float beta, int indicator, int exc_only,
-                                     float exit_logit, int precise, uint64_t seed, uint64_t offset,
-                                     const uint64_t* offset_dev, void* const* events, void* stream) {
+namespace {
+struct Update {  // optimiser fused into the step (pvae_lin_step_train); p == nullptr: gradients only
+  float *p = nullptr, *exp_avg = nullptr, *exp_inf = nullptr;
+  float lr = 0.f, beta1 = 0.f, beta2 = 0.f, eps = 0.f, weight_decay = 0.f;
+  int step = 0;
+};
+}  // namespace
+
+static int lin_step_impl(const float* x, const float* params, float* grads, float* ws, float* loss3, float* rate_max, int64_t B,
+                         int64_t B_global, int64_t row_offset, int64_t K, int64_t D, int has_bias, int n_exp, float temp,
+                         float beta, int indicator, int exc_only, float exit_logit, int precise, uint64_t seed, uint64_t offset,
+                         const uint64_t* offset_dev, void* const* events, void* stream, const Update& up) {
   using pvae::fail;
   if (B <= 0 || B_global < B || K <= 0 || D <= 0) return fail(PVAE_ERR_INVALID, "pvae_lin_step_fwd_bwd: bad shape");
   if (B % 4 || K % 4 || D % 4)
@@ -125,16 +132,52 @@ extern "C" int pvae_lin_step_fwd_bwd(const float* x, const float* params, float*
   }
   if ((rc = pvae_loss_assemble(w.recon, w.klrow, loss3, B, beta, B_global, static_cast<int>(pvae_gemm_residual_parts(D)), s2)))
     return rc;
-  if ((rc = pvae_gemm_tf32(w.g_y, w.z, g_w_dec, D, K, B, 0, 0, precise, wgrad_splits(D, K, B), w.splitk, s2))) return rc;
+  // fused update: the split partials stay in the workspace (C = NULL) and are reduced inside the Adamax kernel
+  const int sp_dec = wgrad_splits(D, K, B), sp_enc = wgrad_splits(K, D, B);
+  const bool fuse = up.p != nullptr && sp_dec > 1 && sp_enc > 1;
+  if ((rc = pvae_gemm_tf32(w.g_y, w.z, fuse ? nullptr : g_w_dec, D, K, B, 0, 0, precise, sp_dec, w.splitk, s2))) return rc;
   if (side && (rc = pvae::cuda_ok("join", cudaEventRecord(side->join, s2)))) return rc;
   if ((rc = pvae_gemm_tf32(w.g_y, w_dec, w.g_z, B, K, D, 1, 0, precise, 1, nullptr, s))) return rc;
   mark(2);
   if ((rc = pvae_sampler_bwd(w.h, log_r, b_enc, w.g_z, nullptr, w.dz, beta / static_cast<float>(B_global), w.g_h, g_log_r, g_b_enc,
-                             w.partials, 0, B, K, row_offset, n_exp, temp, indicator, exc_only, exit_logit, seed, offset,
+                             w.partials, fuse ? -1 : 0, B, K, row_offset, n_exp, temp, indicator, exc_only, exit_logit, seed, offset,
                              offset_dev, s)))
     return rc;
   mark(3);
-  if ((rc = pvae_gemm_tf32(w.g_h, x, g_w_enc, K, D, B, 0, 0, precise, wgrad_splits(K, D, B), w.splitk2, s))) return rc;
+  if ((rc = pvae_gemm_tf32(w.g_h, x, fuse ? nullptr : g_w_enc, K, D, B, 0, 0, precise, sp_enc, w.splitk2, s))) return rc;
   if (side && (rc = pvae::cuda_ok("join", cudaStreamWaitEvent(s, side->join, 0)))) return rc;
-  return PVAE_OK;
+  if (up.p == nullptr) return PVAE_OK;
+  const int64_t n = K + 2 * K * D + (has_bias ? K : 0);
+  if (!fuse)
+    return pvae_adamax_step(up.p, grads, up.exp_avg, up.exp_inf, n, up.lr, up.step, up.beta1, up.beta2, up.eps, up.weight_decay, nullptr, s);
+  const int prow = static_cast<int>(pvae_sampler_bwd_partial_rows(B));
+  pvae_grad_segment seg[4];
+  seg[0] = pvae_grad_segment{0, K, w.partials, prow, 1, K};
+  seg[1] = pvae_grad_segment{K, K * D, w.splitk2, pvae_gemm_effective_splits(B, sp_enc), 0, K * D};
+  seg[2] = pvae_grad_segment{K + K * D, D * K, w.splitk, pvae_gemm_effective_splits(B, sp_dec), 0, D * K};
+  if (has_bias) seg[3] = pvae_grad_segment{K + 2 * K * D, K, w.partials + pvae_sampler_bwd_bias_offset_rows(B) * K, prow, 1, K};
+  return pvae_adamax_from_partials(up.p, grads, up.exp_avg, up.exp_inf, seg, has_bias ? 4 : 3, up.lr, up.step, up.beta1, up.beta2, up.eps,
+                                   up.weight_decay, s);
+}
+
+extern "C" int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, float* ws, float* loss3,
+                                     float* rate_max, int64_t B, int64_t B_global, int64_t row_offset, int64_t K, int64_t D,
+                                     int has_bias, int n_exp, float temp, float beta, int indicator, int exc_only,
+                                     float exit_logit, int precise, uint64_t seed, uint64_t offset,
+                                     const uint64_t* offset_dev, void* const* events, void* stream) {
+  return lin_step_impl(x, params, grads, ws, loss3, rate_max, B, B_global, row_offset, K, D, has_bias, n_exp, temp, beta, indicator,
+                       exc_only, exit_logit, precise, seed, offset, offset_dev, events, stream, Update{});
+}
+
+extern "C" int pvae_lin_step_train(const float* x, float* params, float* grads, float* exp_avg, float* exp_inf, float* ws,
+                                   float* loss3, float* rate_max, int64_t B, int64_t K, int64_t D, int has_bias, int n_exp,
+                                   float temp, float beta, int indicator, int exc_only, float exit_logit, int precise, uint64_t seed,
+                                   uint64_t offset, const uint64_t* offset_dev, void* const* events, float lr, int step, float beta1,
+                                   float beta2, float eps, float weight_decay, void* stream) {
+  if (!params || !exp_avg || !exp_inf || step < 1) return pvae::fail(PVAE_ERR_INVALID, "pvae_lin_step_train: bad optimiser argument");
+  Update up;
+  up.p = params, up.exp_avg = exp_avg, up.exp_inf = exp_inf;
+  up.lr = lr, up.beta1 = beta1, up.beta2 = beta2, up.eps = eps, up.weight_decay = weight_decay, up.step = step;
+  return lin_step_impl(x, params, grads, ws, loss3, rate_max, B, B, 0, K, D, has_bias, n_exp, temp, beta, indicator, exc_only,
+                       exit_logit, precise, seed, offset, offset_dev, events, stream, up);
 }

@@ -1019,11 +1019,16 @@ extern "C" int pvae_sampler_bwd(const float* h, const float* log_r, const float*
   } else if (int rc = cuda_ok("pvae_sampler_bwd", launch_ind<kBwd, false>(p, indicator, dim3(static_cast<unsigned>(P)), s))) {
     return rc;
   }
+  if (accumulate < 0) return PVAE_OK;  // partials only: pvae_sampler_bwd_partial_rows(B) rows of K (log_r), then of K (b_enc)
   if (int rc = finalize_cols(p.part_log_r, g_log_r, Pk, K, accumulate, s)) return rc;
   if (g_b_enc)
     if (int rc = finalize_cols(p.part_b, g_b_enc, Pk, K, accumulate, s)) return rc;
   return PVAE_OK;
 }
+
+// rows of column partials the saved-derivative backward writes (dz_acc given), and where the b_enc partials start
+extern "C" int64_t pvae_sampler_bwd_partial_rows(int64_t B) { return B <= 0 ? 0 : (B + kSavedRows - 1) / kSavedRows; }
+extern "C" int64_t pvae_sampler_bwd_bias_offset_rows(int64_t B) { return pvae_num_partials(B); }
 
 extern "C" int pvae_rsample_fwd(const float* log_rate, float* z, float* rate, float* dz_acc, int64_t B, int64_t K, int64_t row_offset,
                                 int n_exp, float temp, int indicator, float clamp, float exit_logit, uint64_t seed,

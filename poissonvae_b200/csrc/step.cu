@@ -113,6 +113,96 @@ __global__ void __launch_bounds__(256) adamax_kernel(float* __restrict__ p, cons
   }
 }
 
+// ---- gradient reduction fused with Adamax (single GPU, no clipping) --------------------------------------------
+// The step's gradients arrive as partial sums: split-K partials of the two wgrad GEMMs and per-block column partials
+// of the sampler backward.  Instead of three reduction kernels followed by Adamax, ONE kernel reduces each parameter's
+// partials (in the order the stand-alone reductions use, so the result is bit-identical), stores the gradient and
+// applies the update.  blockDim = (32, 32).
+constexpr int kMaxSegments = 8;
+struct SegTable {
+  long long offset[kMaxSegments], length[kMaxSegments], stride[kMaxSegments];
+  const float* partials[kMaxSegments];
+  int n_partials[kMaxSegments], columnar[kMaxSegments], first_block[kMaxSegments + 1];
+  int n;
+};
+__device__ __forceinline__ void adamax_update(float* p, float* m, float* u, long long i, float gi, float clr, float beta1, float beta2,
+                                              float eps, float weight_decay) {
+  const float pi = p[i];
+  if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
+  const float mi = m[i] * beta1 + (1.f - beta1) * gi;
+  const float ui = fmaxf(u[i] * beta2, fabsf(gi) + eps);
+  m[i] = mi;
+  u[i] = ui;
+  p[i] = pi - clr * (mi / ui);
+}
+__global__ void __launch_bounds__(1024) adamax_partials_kernel(const __grid_constant__ SegTable t, float* __restrict__ p,
+                                                               float* __restrict__ g_out, float* __restrict__ m,
+                                                               float* __restrict__ u, float clr, float beta1, float beta2, float eps,
+                                                               float weight_decay) {
+  __shared__ float s[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
+  int seg = 0;
+  while (seg + 1 < t.n && static_cast<int>(blockIdx.x) >= t.first_block[seg + 1]) ++seg;
+  const int blk = blockIdx.x - t.first_block[seg];
+  const float* __restrict__ part = t.partials[seg];
+  const long long off = t.offset[seg], len = t.length[seg];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  if (t.columnar[seg]) {  // (n_partials, len) row partials: the reduction of colsum_finalize_kernel (sampler.cu)
+    const long long k = static_cast<long long>(blk) * 32 + tx, P = t.n_partials[seg];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (k < len) {
+      long long r = ty;
+      for (; r + 3 * 32 < P; r += 4 * 32) {
+        a0 += __ldg(part + r * len + k);
+        a1 += __ldg(part + (r + 32) * len + k);
+        a2 += __ldg(part + (r + 64) * len + k);
+        a3 += __ldg(part + (r + 96) * len + k);
+      }
+      for (; r < P; r += 32) a0 += __ldg(part + r * len + k);
+    }
+    s[ty][tx] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (ty == 0 && k < len) {
+      float v = s[0][tx];
+#pragma unroll
+      for (int y = 1; y < 32; ++y) v += s[y][tx];
+      g_out[off + k] = v;
+      adamax_update(p, m, u, off + k, v, clr, beta1, beta2, eps, weight_decay);
+    }
+    return;
+  }
+  // dense split-K partials (n_partials, stride): the sum of splitk_reduce_kernel (gemm_tc.cu), four elements per thread
+  const long long i4 = static_cast<long long>(blk) * 1024 + ty * 32 + tx;
+  if (4 * i4 >= len) return;
+  const int splits = t.n_partials[seg];
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (part == nullptr) {
+    a = *reinterpret_cast<const float4*>(g_out + off + 4 * i4);  // already reduced
+  } else {
+    const float4* w = reinterpret_cast<const float4*>(part);
+    const long long n4 = t.stride[seg] >> 2;
+    int sp = 0;
+    for (; sp + 8 <= splits; sp += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = __ldg(w + (sp + q) * n4 + i4);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a.x += v[q].x, a.y += v[q].y, a.z += v[q].z, a.w += v[q].w;
+    }
+    for (; sp < splits; ++sp) {
+      const float4 b = __ldg(w + sp * n4 + i4);
+      a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+    }
+    *reinterpret_cast<float4*>(g_out + off + 4 * i4) = a;
+  }
+  const long long i = off + 4 * i4;
+  adamax_update(p, m, u, i, a.x, clr, beta1, beta2, eps, weight_decay);
+  adamax_update(p, m, u, i + 1, a.y, clr, beta1, beta2, eps, weight_decay);
+  adamax_update(p, m, u, i + 2, a.z, clr, beta1, beta2, eps, weight_decay);
+  adamax_update(p, m, u, i + 3, a.w, clr, beta1, beta2, eps, weight_decay);
+}
+
 // ---- Adamax with the step-dependent scalars on the device (CUDA-graph replay of a training step) -------------
 // state[0] = number of optimiser steps taken so far (int), state[2..3] = Philox offset of the step (uint64).
 // lr_sched[i] = learning rate of optimiser step i + 1.  The kernel reads the counter, the advance kernel that follows
@@ -169,6 +259,31 @@ __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ Gat
 }  // namespace pvae
 
 using namespace pvae;
+
+extern "C" int pvae_adamax_from_partials(float* p, float* g_out, float* exp_avg, float* exp_inf, const pvae_grad_segment* segs,
+                                         int n_segs, float lr, int step, float beta1, float beta2, float eps, float weight_decay,
+                                         void* stream) {
+  if (!p || !g_out || !exp_avg || !exp_inf || !segs || n_segs < 1 || n_segs > kMaxSegments || step < 1)
+    return fail(PVAE_ERR_INVALID, "pvae_adamax_from_partials: bad argument");
+  SegTable t = {};
+  t.n = n_segs;
+  int blocks = 0;
+  for (int i = 0; i < n_segs; ++i) {
+    const pvae_grad_segment& g = segs[i];
+    if (g.length <= 0 || g.offset < 0 || (g.partials && g.n_partials < 1) || (!g.columnar && (g.length % 4 || g.offset % 4 || g.stride % 4)))
+      return fail(PVAE_ERR_INVALID, "pvae_adamax_from_partials: bad segment %d", i);
+    if (g.columnar && !g.partials) return fail(PVAE_ERR_INVALID, "pvae_adamax_from_partials: a columnar segment needs partials");
+    t.offset[i] = g.offset, t.length[i] = g.length, t.stride[i] = g.stride, t.partials[i] = g.partials;
+    t.n_partials[i] = g.n_partials, t.columnar[i] = g.columnar, t.first_block[i] = blocks;
+    blocks += static_cast<int>(g.columnar ? (g.length + 31) / 32 : (g.length / 4 + 1023) / 1024);
+  }
+  t.first_block[n_segs] = blocks;
+  const double bias_correction = 1.0 - pow(static_cast<double>(beta1), step);  // base/adamax.py:75-76
+  const float clr = static_cast<float>(static_cast<double>(lr) / bias_correction);
+  return cuda_ok("pvae_adamax_from_partials", launch_pdl(adamax_partials_kernel, dim3(blocks), dim3(32, 32), 0,
+                                                         static_cast<cudaStream_t>(stream), t, p, g_out, exp_avg, exp_inf, clr, beta1,
+                                                         beta2, eps, weight_decay));
+}
 
 extern "C" int pvae_adamax_step_dev(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, const float* lr_sched,
                                     int n_sched, int* state, float beta1, float beta2, float eps, float weight_decay,

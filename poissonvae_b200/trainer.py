@@ -119,6 +119,9 @@ class TrainerVAE:
         # between the kernel nodes of a replayed graph the programmatic-dependent-launch overlap of the eager stream
         # (every kernel's prologue under its predecessor's tail) is lost.  True forces it; 'auto' = small or static inputs.
         self.graph = False
+        # single GPU without clipping: reduce the gradient partials inside the Adamax kernel (pvae_lin_step_train); False
+        # keeps the stand-alone reduction kernels (bit-identical results, A/B)
+        self.fuse_update = True
         self._graphs = {}
         self._graph_static = set()  # data_ptr() of input buffers that stay put (fit_host's staging slots)
         self._gstate = None
@@ -195,7 +198,9 @@ class TrainerVAE:
         """Kernels of libpvae_b200.so launched by one train_step (fused lin|lin step; for the other architectures
         difference pvae_launch_count() around a step)."""
         # 5 tcgen05 GEMMs (the decoder one with the residual fused in) + 2 split-K reductions (wgrad),
-        # sampler fwd, loss, sampler bwd, column-sum finalize, Adamax
+        # sampler fwd, loss, sampler bwd, column-sum finalize, Adamax; the fused update drops the three reductions
+        if self.world == 1 and self.cfg.grad_clip is None and self.fuse_update:
+            return 9
         n = 12
         if self.model.fc_enc.bias is not None:
             n += 1  # second column-sum finalize (bias gradient)
@@ -368,6 +373,15 @@ class TrainerVAE:
             events = (ctypes.c_void_p * 4)(*[e.cuda_event for e in evs])
             self.kernel_events.setdefault('sampler_fwd', []).append((evs[0], evs[1]))
             self.kernel_events.setdefault('sampler_bwd', []).append((evs[2], evs[3]))
+        if self.world == 1 and cfg.grad_clip is None and self.fuse_update:
+            # forward + loss + backward + optimiser in one call; the gradient reductions happen inside the Adamax kernel
+            self.opt_step += 1
+            chk(lib.pvae_lin_step_train(
+                _ptr(x2), _ptr(self.flat_p), _ptr(gbuf), _ptr(self.exp_avg), _ptr(self.exp_inf), _ptr(b['ws']), _ptr(step_loss),
+                self.r_max.data_ptr() + 4 * (gstep % self.r_max.numel()), B, K, D, int(m.fc_enc.bias is not None), n_exp, temp,
+                beta, ind, int(m.cfg.exc_only), m.exit_logit, int(linear_mod.PRECISE), seed, offset, None, events, lr,
+                self.opt_step, cfg.betas[0], cfg.betas[1], cfg.eps, cfg.weight_decay, s))
+            return loss[:3]
         # forward + loss + backward: one call, every kernel enqueued back to back (csrc/lin_step.cu)
         chk(lib.pvae_lin_step_fwd_bwd(
             _ptr(x2), _ptr(self.flat_p), _ptr(gbuf), _ptr(b['ws']), _ptr(step_loss),

@@ -200,3 +200,28 @@ def test_graph_replay_matches_eager_steps():
     assert_rel(out[True][0].cpu().numpy(), out[False][0].cpu().numpy(), rtol=1e-6, what="parameters graph vs eager")
     l = out[True][1]
     assert torch.equal(l[8:10], l[10:12])  # the rewound steps reproduce themselves bit for bit
+
+
+@pytest.mark.parametrize("bias", [False, True])
+def test_fused_update_is_bit_identical(bias):
+    """pvae_lin_step_train (gradient partials reduced inside the Adamax kernel) against the stand-alone reductions +
+    Adamax: same parameters, optimiser state, stored gradients and losses, bit for bit."""
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
+    g = torch.Generator().manual_seed(19)
+    data = torch.randn(5, 1024, 256, generator=g).cuda()
+    out = {}
+    for fuse in (True, False):
+        model = PoissonVAE(ConfigPoisVAE(n_latents=256, prior_clamp=-4, seed=4, enc_bias=bias)).cuda()
+        with torch.no_grad():
+            model.log_rate.add_(3.0)
+        model.update_n(25.0)
+        tr = TrainerVAE(model, ConfigTrainVAE(lr=0.01, epochs=40, batch_size=1024, temp_anneal_portion=0.0, temp_stop=0.7,
+                                              kl_anneal_portion=0.0, kl_const_portion=0.0, grad_clip=None), n_batches_per_epoch=1)
+        tr.fuse_update = fuse
+        torch.cuda.manual_seed(5)
+        losses = [tr.train_step(data[i], i).clone() for i in range(5)]
+        out[fuse] = (tr.flat_p.clone(), tr.exp_avg.clone(), tr.exp_inf.clone(), tr.flat_g.clone(), torch.stack(losses))
+        assert tr.launches_per_step() == (9 if fuse else 12) + (1 if bias and not fuse else 0)
+    for a, b in zip(out[True], out[False]):
+        assert torch.equal(a, b)
