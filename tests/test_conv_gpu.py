@@ -466,3 +466,39 @@ def test_native_cell_call_equals_per_kernel_path(kind):
         conv.NATIVE_CELLS = True
     for a, b in zip(results[True], results[False]):
         assert torch.equal(a, b)
+
+
+def test_conv_public_api_paths():
+    """The remaining public entry points on a conv model: prior sampling through the conv decoder, a state_dict round
+    trip, an epoch over a device-resident dataset (`iteration`, with the end-of-epoch n_exp update) and host-fed training
+    (`fit_host`: pinned batches in, losses out)."""
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE, default_configs
+    cfg_vae, cfg_tr = default_configs("CIFAR16", "poisson", "conv+b|conv+b")
+    cfg_vae.update(n_latents=64, seed=5)
+    model = PoissonVAE(ConfigPoisVAE(**cfg_vae)).cuda()
+    model.update_n(10.0)
+    xs, spks = model.sample(8, t=0.0)  # main/vae.py:431-444
+    assert xs.shape == (8, 1, 16, 16) and spks.shape == (8, 64) and torch.equal(spks, spks.round())
+    assert torch.isfinite(xs).all()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    twin = PoissonVAE(ConfigPoisVAE(**{**cfg_vae, "seed": 6})).cuda()
+    twin.load_state_dict(sd)
+    twin.eval(), model.eval()
+    x = torch.randn(8, 1, 16, 16, device="cuda")
+    torch.cuda.manual_seed(3)
+    y1 = model(x)[3]
+    torch.cuda.manual_seed(3)
+    y2 = twin(x)[3]
+    assert torch.equal(y1, y2)
+    model.train()
+    cfg_tr.update(epochs=3, batch_size=16)
+    tr = TrainerVAE(model, ConfigTrainVAE(**cfg_tr), n_batches_per_epoch=4)
+    data = torch.randn(64, 1, 16, 16, device="cuda")
+    n0 = model._n_exp_host
+    nelbo = tr.iteration(data, epoch=0)
+    assert np.isfinite(nelbo) and model._n_exp_host != n0  # r_max of the epoch -> new n_exp (main/train_vae.py:456-457)
+    host = torch.randn(6, 16, 256).pin_memory()
+    losses = tr.fit_host(host, first_gstep=4)
+    torch.cuda.synchronize()
+    assert losses.shape == (6, 3) and torch.isfinite(losses).all()
