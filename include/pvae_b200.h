@@ -162,7 +162,7 @@ int pvae_grad_norm(const float* g, int64_t n, float max_norm, float* ws, float* 
  * the sampler backward; reduced like its own column-sum kernel), columnar = 0: split-K partials `stride` floats apart
  * (pvae_gemm_tf32 called with C = NULL leaves them in the workspace), partials = NULL: g_out already holds it.  One
  * kernel reduces (bit-identical to the stand-alone reductions), stores the gradient into g_out and updates p / exp_avg /
- * exp_inf as pvae_adamax_step does. */
+ * exp_inf as pvae_adamax_step does.  p = NULL: reduction only (data parallel: the gradient exchange applies the update). */
 typedef struct pvae_grad_segment {
   int64_t offset, length;
   const float* partials;
@@ -227,6 +227,9 @@ int pvae_lin_step_train(const float* x, float* params, float* grads, float* exp_
 /* Tuning knob (process-wide, default on): run the decoder wgrad and the loss assembly of pvae_lin_step_fwd_bwd on
  * an internal side stream (forked from / joined back into the caller's stream with events). */
 int pvae_set_step_overlap(int on);
+/* Tuning knob (process-wide, default on): pvae_lin_step_fwd_bwd reduces the wgrad split partials and the sampler's column
+ * partials with ONE kernel instead of two split-K reductions + one or two column-sum kernels (bit-identical results). */
+int pvae_set_fuse_reduce(int on);
 int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, float* ws, float* loss3, float* rate_max,
                           int64_t B, int64_t B_global, int64_t row_offset, int64_t K, int64_t D, int has_bias, int n_exp,
                           float temp, float beta, int indicator, int exc_only, float exit_logit, int precise,

@@ -39,6 +39,7 @@ SideStream* side_stream() {
 }
 
 int g_overlap = 1;
+int g_fuse_reduce = 1;  // pvae_lin_step_fwd_bwd: reduce all gradient partials with one kernel (bit-identical to the three)
 
 struct Ws {
   float *h, *z, *dz, *y, *g_y, *g_z, *g_h, *recon, *klrow, *partials, *splitk, *splitk2;
@@ -85,6 +86,7 @@ extern "C" int64_t pvae_lin_step_ws_floats(int64_t B, int64_t K, int64_t D) {
 
 namespace {
 struct Update {  // optimiser fused into the step (pvae_lin_step_train); p == nullptr: gradients only
+  bool fuse_reduce = false;  // gradients only, but all partials reduced by ONE kernel instead of three
   float *p = nullptr, *exp_avg = nullptr, *exp_inf = nullptr;
   float lr = 0.f, beta1 = 0.f, beta2 = 0.f, eps = 0.f, weight_decay = 0.f;
   int step = 0;
@@ -134,7 +136,7 @@ static int lin_step_impl(const float* x, const float* params, float* grads, floa
     return rc;
   // fused update: the split partials stay in the workspace (C = NULL) and are reduced inside the Adamax kernel
   const int sp_dec = wgrad_splits(D, K, B), sp_enc = wgrad_splits(K, D, B);
-  const bool fuse = up.p != nullptr && sp_dec > 1 && sp_enc > 1;
+  const bool fuse = (up.p != nullptr || up.fuse_reduce) && sp_dec > 1 && sp_enc > 1;
   if ((rc = pvae_gemm_tf32(w.g_y, w.z, fuse ? nullptr : g_w_dec, D, K, B, 0, 0, precise, sp_dec, w.splitk, s2))) return rc;
   if (side && (rc = pvae::cuda_ok("join", cudaEventRecord(side->join, s2)))) return rc;
   if ((rc = pvae_gemm_tf32(w.g_y, w_dec, w.g_z, B, K, D, 1, 0, precise, 1, nullptr, s))) return rc;
@@ -146,7 +148,7 @@ static int lin_step_impl(const float* x, const float* params, float* grads, floa
   mark(3);
   if ((rc = pvae_gemm_tf32(w.g_h, x, fuse ? nullptr : g_w_enc, K, D, B, 0, 0, precise, sp_enc, w.splitk2, s))) return rc;
   if (side && (rc = pvae::cuda_ok("join", cudaStreamWaitEvent(s, side->join, 0)))) return rc;
-  if (up.p == nullptr) return PVAE_OK;
+  if (up.p == nullptr && !fuse) return PVAE_OK;
   const int64_t n = K + 2 * K * D + (has_bias ? K : 0);
   if (!fuse)
     return pvae_adamax_step(up.p, grads, up.exp_avg, up.exp_inf, n, up.lr, up.step, up.beta1, up.beta2, up.eps, up.weight_decay, nullptr, s);
@@ -165,8 +167,15 @@ extern "C" int pvae_lin_step_fwd_bwd(const float* x, const float* params, float*
                                      int has_bias, int n_exp, float temp, float beta, int indicator, int exc_only,
                                      float exit_logit, int precise, uint64_t seed, uint64_t offset,
                                      const uint64_t* offset_dev, void* const* events, void* stream) {
+  Update up;
+  up.fuse_reduce = g_fuse_reduce != 0;
   return lin_step_impl(x, params, grads, ws, loss3, rate_max, B, B_global, row_offset, K, D, has_bias, n_exp, temp, beta, indicator,
-                       exc_only, exit_logit, precise, seed, offset, offset_dev, events, stream, Update{});
+                       exc_only, exit_logit, precise, seed, offset, offset_dev, events, stream, up);
+}
+
+extern "C" int pvae_set_fuse_reduce(int on) {
+  g_fuse_reduce = on != 0;
+  return PVAE_OK;
 }
 
 extern "C" int pvae_lin_step_train(const float* x, float* params, float* grads, float* exp_avg, float* exp_inf, float* ws,

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(1024) adamax_partials_kernel(const __grid_cons
 #pragma unroll
       for (int y = 1; y < 32; ++y) v += s[y][tx];
       g_out[off + k] = v;
-      adamax_update(p, m, u, off + k, v, clr, beta1, beta2, eps, weight_decay);
+      if (p != nullptr) adamax_update(p, m, u, off + k, v, clr, beta1, beta2, eps, weight_decay);
     }
     return;
   }
@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(1024) adamax_partials_kernel(const __grid_cons
     }
     *reinterpret_cast<float4*>(g_out + off + 4 * i4) = a;
   }
+  if (p == nullptr) return;  // reduction only (data parallel: the exchange kernel applies the update)
   const long long i = off + 4 * i4;
   adamax_update(p, m, u, i, a.x, clr, beta1, beta2, eps, weight_decay);
   adamax_update(p, m, u, i + 1, a.y, clr, beta1, beta2, eps, weight_decay);
@@ -263,8 +264,9 @@ using namespace pvae;
 extern "C" int pvae_adamax_from_partials(float* p, float* g_out, float* exp_avg, float* exp_inf, const pvae_grad_segment* segs,
                                          int n_segs, float lr, int step, float beta1, float beta2, float eps, float weight_decay,
                                          void* stream) {
-  if (!p || !g_out || !exp_avg || !exp_inf || !segs || n_segs < 1 || n_segs > kMaxSegments || step < 1)
+  if (!g_out || !segs || n_segs < 1 || n_segs > kMaxSegments || (p && (!exp_avg || !exp_inf || step < 1)))
     return fail(PVAE_ERR_INVALID, "pvae_adamax_from_partials: bad argument");
+  if (!p) step = 1;  // p == NULL: reduce the partials into g_out only
   SegTable t = {};
   t.n = n_segs;
   int blocks = 0;

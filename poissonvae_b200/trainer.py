@@ -201,9 +201,7 @@ class TrainerVAE:
         # sampler fwd, loss, sampler bwd, column-sum finalize, Adamax; the fused update drops the three reductions
         if self.world == 1 and self.cfg.grad_clip is None and self.fuse_update:
             return 9
-        n = 12
-        if self.model.fc_enc.bias is not None:
-            n += 1  # second column-sum finalize (bias gradient)
+        n = 10  # one kernel reduces all gradient partials (pvae_set_fuse_reduce(0): three or four stand-alone reductions)
         if self.cfg.grad_clip is not None:
             n += 2  # sum of squares partials + finalize
         return n

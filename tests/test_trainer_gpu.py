@@ -210,18 +210,26 @@ def test_fused_update_is_bit_identical(bias):
     from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
     g = torch.Generator().manual_seed(19)
     data = torch.randn(5, 1024, 256, generator=g).cuda()
+    from poissonvae_b200 import _lib
+    lib = _lib.load()
     out = {}
-    for fuse in (True, False):
+    for fuse in (True, False, "three kernels"):
+        lib.pvae_set_fuse_reduce(0 if fuse == "three kernels" else 1)
         model = PoissonVAE(ConfigPoisVAE(n_latents=256, prior_clamp=-4, seed=4, enc_bias=bias)).cuda()
         with torch.no_grad():
             model.log_rate.add_(3.0)
         model.update_n(25.0)
         tr = TrainerVAE(model, ConfigTrainVAE(lr=0.01, epochs=40, batch_size=1024, temp_anneal_portion=0.0, temp_stop=0.7,
                                               kl_anneal_portion=0.0, kl_const_portion=0.0, grad_clip=None), n_batches_per_epoch=1)
-        tr.fuse_update = fuse
+        tr.fuse_update = fuse is True
         torch.cuda.manual_seed(5)
+        c0 = lib.pvae_launch_count()
         losses = [tr.train_step(data[i], i).clone() for i in range(5)]
+        per_step = (lib.pvae_launch_count() - c0) // 5
         out[fuse] = (tr.flat_p.clone(), tr.exp_avg.clone(), tr.exp_inf.clone(), tr.flat_g.clone(), torch.stack(losses))
-        assert tr.launches_per_step() == (9 if fuse else 12) + (1 if bias and not fuse else 0)
-    for a, b in zip(out[True], out[False]):
-        assert torch.equal(a, b)
+        # fused update: 9; one reduction kernel + Adamax: 10; two split-K reductions + column sums (+ bias) + Adamax: 12 (13)
+        assert per_step == {True: 9, False: 10, "three kernels": 13 if bias else 12}[fuse], per_step
+    lib.pvae_set_fuse_reduce(1)
+    for other in (False, "three kernels"):
+        for a, b in zip(out[True], out[other]):
+            assert torch.equal(a, b)
