@@ -60,10 +60,22 @@ __global__ void __launch_bounds__(256) allreduce_adamax_kernel(const PeerPtrs pp
   }
   __syncthreads();
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4_ext; i += gridDim.x * 256ll) {
-    float4 g = ld_peer4(pp.grad[0] + 4 * i);
-    for (int r = 1; r < world; ++r) {
-      const float4 v = ld_peer4(pp.grad[r] + 4 * i);
-      g.x += v.x, g.y += v.y, g.z += v.z, g.w += v.w;
+    // all peers' loads in flight at once (one NVLink round trip instead of `world` dependent ones), eight at a time,
+    // then the sum in rank order - every rank forms the same bits
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r0 = 0; r0 < kMaxPeers; r0 += 8) {
+      if (r0 >= world) break;
+      float4 v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (r0 + q < world) v[q] = ld_peer4(pp.grad[r0 + q] + 4 * i);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (r0 + q < world) {
+          if (r0 + q == 0) g = v[q];
+          else g.x += v[q].x, g.y += v[q].y, g.z += v[q].z, g.w += v[q].w;
+        }
     }
     if (i >= n4) {  // trailing statistics ([loss, mse, kl, -]) ride along
       reinterpret_cast<float4*>(tail_out)[i - n4] = g;
