@@ -15,7 +15,6 @@ import math
 
 import numpy as np
 import torch
-import torch.distributed as dist
 
 from . import _lib, dp, rng
 from .distributions import INDICATOR_CODES, _ptr, _stream
