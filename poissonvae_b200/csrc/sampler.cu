@@ -137,7 +137,7 @@ __device__ __forceinline__ bool phase_a(const SamplerParams& p, uint32_t quad, u
     if (tmin > t_exit) return true;
     // past the threshold (t > 1) the terms only shrink: once each is below 2^-34 of its running sum, all the
     // remaining ones together (<= n_exp < 2^9 of them) stay below half an ulp of the sum
-    if (MODE != kFwdHard && tmin > 1.f && excess <= 0.f) return true;
+    if (MODE != kFwdHard && absorb > 0.f && tmin > 1.f && excess <= 0.f) return true;  // absorb == 0: rule off (NEVER walks on)
   }
   return n_end >= p.n_exp;
 }
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
           }
           ++n;
           const float tmin = fminf(fminf(t[0], t[1]), fminf(t[2], t[3]));
-          if (tmin > t_exit || (tmin > 1.f && excess <= 0.f) || n >= p.n_exp) {  // chain complete
+          if (tmin > t_exit || (absorb > 0.f && tmin > 1.f && excess <= 0.f) || n >= p.n_exp) {  // chain complete
             stg4(z0 + ebase, make_float4(acc[0], acc[1], acc[2], acc[3]));
             if (MODE == kFwdBoth) stg4(dz0 + ebase, make_float4(acc2[0], acc2[1], acc2[2], acc2[3]));
             fin = true;
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
         }
         n0 += kGroup;
         const float tmin = fminf(fminf(t0[0], t0[1]), fminf(t0[2], t0[3]));
-        const bool absorbed = __shfl_sync(0xffffffffu, excess <= 0.f ? 1 : 0, kGroup - 1, kGroup) != 0 && tmin > 1.f;
+        const bool absorbed = p.absorb > 0.f && __shfl_sync(0xffffffffu, excess <= 0.f ? 1 : 0, kGroup - 1, kGroup) != 0 && tmin > 1.f;
         if (has && (n0 >= p.n_exp || tmin > p.t_exit || absorbed)) done = true;
       }
     }

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--n_exp", type=int, default=263)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--single", action="store_true", help="only random_init, temp 1, lossless (for ncu captures)")
+    ap.add_argument("--single_exit", default="lossless", choices=["lossless", "never"], help="exit policy of --single")
     ap.add_argument("--phase_a", type=int, default=0, help="override pvae_set_phase_a_events")
     ap.add_argument("--rows", type=int, default=0, help="override pvae_set_rows_per_block")
     args = ap.parse_args()
@@ -64,7 +65,7 @@ def main():
     klrow = torch.empty(B, device="cuda")
     dz = torch.empty(B, K, device="cuda")
     temps = (1.0,) if args.single else (1.0, 0.05)
-    exits = (("lossless", 0.0),) if args.single else (("lossless", 0.0), ("c30", 30.0), ("never", -1.0))
+    exits = ((args.single_exit, 0.0 if args.single_exit == "lossless" else -1.0),) if args.single else (("lossless", 0.0), ("c30", 30.0), ("never", -1.0))
     if args.single:
         dists = {"random_init": dists["random_init"]}
     for name, (h, log_r) in dists.items():
