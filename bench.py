@@ -48,6 +48,7 @@ def parse():
                     help="N > 1: gradient exchange over NVLink peer memory fused with Adamax, or NCCL all-reduce")
     ap.add_argument("--no_overlap", action="store_true", help="keep the whole step on one stream (A/B)")
     ap.add_argument("--tf32", action="store_true", help="single-pass TF32 GEMMs instead of 3xTF32 (A/B)")
+    ap.add_argument("--dec_splits", type=int, default=-1, help="K-splits of the decoder GEMM (A/B; default: the library's choice)")
     ap.add_argument("--no_fuse_update", action="store_true", help="keep the stand-alone gradient reductions + Adamax (A/B)")
     ap.add_argument("--graph", default="off", choices=["auto", "on", "off"],
                     help="CUDA-graph replay of the fused step (1 GPU; A/B - measured slower than the eager launches with "
@@ -296,6 +297,8 @@ def run_ours(args):
     tr = TrainerVAE(model, cfg, n_batches_per_epoch=26, dp_mode=args.dp)
     tr.graph = {"auto": "auto", "on": True, "off": False}[args.graph]
     tr.fuse_update = not args.no_fuse_update
+    if args.dec_splits >= 0:
+        tr.lib.pvae_set_dec_splits(args.dec_splits)
 
     # inputs: 64 distinct batches (268 MB at B=4096 > 126 MB L2) so that no step finds its input in L2
     NB = 64

@@ -153,6 +153,10 @@ int pvae_gemm_tf32_residual(const float* A, const float* B, const float* X, floa
  *   1-based update count (bias correction 1 - beta1^step); clip_coef = out2 of pvae_grad_norm or NULL. */
 int pvae_recon_residual(const float* y, const float* x, float* g_y, float* recon, int64_t B, int64_t D, float g_scale,
                         void* stream);
+/* pvae_recon_residual on a decoder output that arrives as n_parts split-K partial sums (n_parts x (B, D), as left in the
+ * workspace by pvae_gemm_tf32 with C = NULL), summed in order. */
+int pvae_recon_residual_parts(const float* y_parts, int n_parts, const float* x, float* g_y, float* recon, int64_t B, int64_t D,
+                              float g_scale, void* stream);
 int pvae_loss_assemble(const float* recon, const float* kl_rowsum, float* out3, int64_t B, float beta, int64_t B_global,
                        int recon_parts, void* stream);
 int64_t pvae_grad_norm_ws_floats(void);
@@ -230,6 +234,10 @@ int pvae_set_step_overlap(int on);
 /* Tuning knob (process-wide, default on): pvae_lin_step_fwd_bwd reduces the wgrad split partials and the sampler's column
  * partials with ONE kernel instead of two split-K reductions + one or two column-sum kernels (bit-identical results). */
 int pvae_set_fuse_reduce(int on);
+/* Tuning knob (process-wide): K-splits of the decoder GEMM of the training step.  1: one fused GEMM + residual epilogue;
+ * 2 (or more): split-K partials + a residual kernel that sums them (halves the GEMM's serial K loop); 0 (default):
+ * automatic - two splits when K >= 512 and both halves of every tile fit one wave of CTAs. */
+int pvae_set_dec_splits(int n);
 int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, float* ws, float* loss3, float* rate_max,
                           int64_t B, int64_t B_global, int64_t row_offset, int64_t K, int64_t D, int has_bias, int n_exp,
                           float temp, float beta, int indicator, int exc_only, float exit_logit, int precise,

@@ -92,6 +92,8 @@ _SIGNATURES = {
     "pvae_cell_bwd": (_i, [_p] * 7 + [_p]),
     "pvae_set_cell_overlap": (_i, [_i]),
     "pvae_set_fuse_reduce": (_i, [_i]),
+    "pvae_set_dec_splits": (_i, [_i]),
+    "pvae_recon_residual_parts": (_i, [_p, _i, _p, _p, _p, _i64, _i64, _f, _p]),
     "pvae_set_conv_variant": (_i, [_i]),
     "pvae_reduce_ws_floats": (_i64, [_i64]),
     "pvae_silu_fwd": (_i, [_p, _p, _i64, _p]),

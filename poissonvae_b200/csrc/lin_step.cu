@@ -39,10 +39,11 @@ SideStream* side_stream() {
 }
 
 int g_overlap = 1;
+int g_dec_splits = 0;   // K-splits of the decoder GEMM (pvae_set_dec_splits); 0 = automatic
 int g_fuse_reduce = 1;  // pvae_lin_step_fwd_bwd: reduce all gradient partials with one kernel (bit-identical to the three)
 
 struct Ws {
-  float *h, *z, *dz, *y, *g_y, *g_z, *g_h, *recon, *klrow, *partials, *splitk, *splitk2;
+  float *h, *z, *dz, *y, *g_y, *g_z, *g_h, *recon, *klrow, *partials, *splitk, *splitk2, *ydec;
   int64_t total;
 };
 
@@ -68,6 +69,7 @@ Ws carve(float* base, int64_t B, int64_t K, int64_t D) {
   const int64_t s1 = pvae_gemm_ws_floats(D, K, wgrad_splits(D, K, B)), s2 = pvae_gemm_ws_floats(K, D, wgrad_splits(K, D, B));
   w.splitk = take(s1);   // decoder wgrad (may run on the side stream, concurrently with ...)
   w.splitk2 = take(s2);  // ... the encoder wgrad
+  w.ydec = take(8 * B * D);  // split-K partials of the decoder output (pvae_set_dec_splits, at most 8)
   w.total = o;
   return w;
 }
@@ -122,8 +124,20 @@ static int lin_step_impl(const float* x, const float* params, float* grads, floa
     return rc;
   mark(1);
   // decoder GEMM with the residual fused into its epilogue: g_y and per-tile squared errors, y itself is never stored
-  if ((rc = pvae_gemm_tf32_residual(w.z, w_dec, x, w.g_y, w.recon, B, D, K, 2.0f / static_cast<float>(B_global), precise, s)))
+  int recon_parts = static_cast<int>(pvae_gemm_residual_parts(D));
+  // automatic: the decoder's K loop (K / 32 blocks of ~1 us each in 3xTF32 mode) is the longest serial stretch of any GEMM
+  // of the step; when two K-halves of every 128 x 128 tile still fit one wave of CTAs, split it (measured at config 2:
+  // 115.0 -> 111.6 us per step; four splits: 116.9)
+  int want = g_dec_splits;
+  if (want == 0) want = (K >= 512 && ((B + 127) / 128) * ((D + 127) / 128) * 2 <= 160) ? 2 : 1;
+  const int dsp = want > 1 ? pvae_gemm_effective_splits(K, want) : 1;
+  if (dsp > 1) {  // split-K partials (in the not-yet-used wgrad workspace) + one kernel that sums them into the residual
+    if ((rc = pvae_gemm_tf32(w.z, w_dec, nullptr, B, D, K, 1, 1, precise, dsp, w.ydec, s))) return rc;
+    if ((rc = pvae_recon_residual_parts(w.ydec, dsp, x, w.g_y, w.recon, B, D, 2.0f / static_cast<float>(B_global), s))) return rc;
+    recon_parts = 1;
+  } else if ((rc = pvae_gemm_tf32_residual(w.z, w_dec, x, w.g_y, w.recon, B, D, K, 2.0f / static_cast<float>(B_global), precise, s))) {
     return rc;
+  }
   // ---- backward.  Off the critical path (decoder wgrad, loss assembly) goes to a side stream so that it fills
   // the SMs the dgrad GEMM leaves idle and overlaps the elementwise sampler backward.
   SideStream* side = g_overlap ? side_stream() : nullptr;
@@ -132,8 +146,7 @@ static int lin_step_impl(const float* x, const float* params, float* grads, floa
     if ((rc = pvae::cuda_ok("fork", cudaEventRecord(side->fork, s)))) return rc;
     if ((rc = pvae::cuda_ok("fork", cudaStreamWaitEvent(s2, side->fork, 0)))) return rc;
   }
-  if ((rc = pvae_loss_assemble(w.recon, w.klrow, loss3, B, beta, B_global, static_cast<int>(pvae_gemm_residual_parts(D)), s2)))
-    return rc;
+  if ((rc = pvae_loss_assemble(w.recon, w.klrow, loss3, B, beta, B_global, recon_parts, s2))) return rc;
   // fused update: the split partials stay in the workspace (C = NULL) and are reduced inside the Adamax kernel
   const int sp_dec = wgrad_splits(D, K, B), sp_enc = wgrad_splits(K, D, B);
   const bool fuse = (up.p != nullptr || up.fuse_reduce) && sp_dec > 1 && sp_enc > 1;
@@ -171,6 +184,12 @@ extern "C" int pvae_lin_step_fwd_bwd(const float* x, const float* params, float*
   up.fuse_reduce = g_fuse_reduce != 0;
   return lin_step_impl(x, params, grads, ws, loss3, rate_max, B, B_global, row_offset, K, D, has_bias, n_exp, temp, beta, indicator,
                        exc_only, exit_logit, precise, seed, offset, offset_dev, events, stream, up);
+}
+
+extern "C" int pvae_set_dec_splits(int n) {
+  if (n < 0 || n > 8) return pvae::fail(PVAE_ERR_INVALID, "pvae_set_dec_splits: %d not in [0, 8]", n);
+  g_dec_splits = n;
+  return PVAE_OK;
 }
 
 extern "C" int pvae_set_fuse_reduce(int on) {

@@ -15,9 +15,10 @@ namespace pvae {
 
 // ---- residual: g_y = (2 / B_global) * (y - x), recon[b] = sum_d (y - x)^2 -----------------------
 // One warp per sample; D is a multiple of 4.
+// y_parts > 1: y arrives as split-K partial sums y_parts * (B, D) apart (pvae_gemm_tf32 with C = NULL), summed here in order
 __global__ void __launch_bounds__(256) recon_kernel(const float* __restrict__ y, const float* __restrict__ x,
                                                     float* __restrict__ g_y, float* __restrict__ recon, long long B,
-                                                    long long D, float g_scale) {
+                                                    long long D, float g_scale, int y_parts) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -25,7 +26,12 @@ __global__ void __launch_bounds__(256) recon_kernel(const float* __restrict__ y,
   for (long long b = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
     float acc = 0.f;
     for (long long d = 4 * lane; d < D; d += 128) {
-      const float4 yv = ldg4(y + b * D + d), xv = ldg4(x + b * D + d);
+      float4 yv = ldg4(y + b * D + d);
+      const float4 xv = ldg4(x + b * D + d);
+      for (int s = 1; s < y_parts; ++s) {
+        const float4 w = ldg4(y + s * B * D + b * D + d);
+        yv.x += w.x, yv.y += w.y, yv.z += w.z, yv.w += w.w;
+      }
       const float4 r = make_float4(yv.x - xv.x, yv.y - xv.y, yv.z - xv.z, yv.w - xv.w);
       acc += (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
       if (g_y != nullptr) stg4(g_y + b * D + d, make_float4(g_scale * r.x, g_scale * r.y, g_scale * r.z, g_scale * r.w));
@@ -324,6 +330,16 @@ extern "C" int pvae_gather(const void* const* srcs, const int64_t* offsets, int 
   return PVAE_OK;
 }
 
+extern "C" int pvae_recon_residual_parts(const float* y_parts, int n_parts, const float* x, float* g_y, float* recon, int64_t B,
+                                         int64_t D, float g_scale, void* stream) {
+  if (B <= 0 || D <= 0 || D % 4 != 0 || n_parts < 1 || !y_parts || !x)
+    return fail(PVAE_ERR_INVALID, "pvae_recon_residual_parts: bad argument");
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((B + 7) / 8, 148ll * 8));
+  return cuda_ok("pvae_recon_residual_parts", launch_pdl(recon_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                                                         y_parts, x, g_y, recon, static_cast<long long>(B), static_cast<long long>(D),
+                                                         g_scale, n_parts));
+}
+
 extern "C" int pvae_recon_residual(const float* y, const float* x, float* g_y, float* recon, int64_t B, int64_t D,
                                    float g_scale, void* stream) {
   if (B < 0 || D <= 0 || D % 4 != 0) return fail(PVAE_ERR_INVALID, "pvae_recon_residual: bad shape B=%lld D=%lld", (long long)B, (long long)D);
@@ -331,7 +347,7 @@ extern "C" int pvae_recon_residual(const float* y, const float* x, float* g_y, f
   if (!y || !x) return fail(PVAE_ERR_INVALID, "pvae_recon_residual: null y/x");
   const unsigned grid = static_cast<unsigned>(std::min<long long>((B + 7) / 8, 148ll * 8));
   return cuda_ok("pvae_recon_residual", launch_pdl(recon_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), y, x,
-                                                   g_y, recon, static_cast<long long>(B), static_cast<long long>(D), g_scale));
+                                                   g_y, recon, static_cast<long long>(B), static_cast<long long>(D), g_scale, 1));
 }
 
 extern "C" int pvae_loss_assemble(const float* recon, const float* kl_rowsum, float* out3, int64_t B, float beta,
