@@ -254,6 +254,9 @@ int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, flo
  *   co / (Co / groups) of a 2x2 window.  Co_pad / Ci_pad >= Co / Ci: channel counts of the packed matrices (the tensor-core
  *   kernels want multiples of 32; the 16-channel decoder layers are zero-padded to 32); bias_pad (Co_pad, optional) receives
  *   the zero-padded bias.  pvae_conv_wgrad's Ci / Co are the padded tensor dimensions, Ci_real / Co_real the parameter's.
+ *   with_lo = 1: w_fwd / w_dgrad have TWICE the rows; the second half holds x - trunc_tf32(x) of the first, the low parts of
+ *   the 3xTF32 operand split, so that pvae_conv_igemm (w_has_lo = 1) loads them with TMA instead of splitting the filter
+ *   tile in shared memory at every K step (the activation tile is still split in the kernel).  Same bits either way.
  * pvae_conv_weight_grad: g_wp (ntaps * Ci, Co) [rows (tap, ci), as written by pvae_conv_wgrad] -> g_weight in the
  *   torch layout and g_lognorm, through the normalisation.
  * pvae_conv_igemm: out[n, oh*out_step+out_off_h, ow*out_step+out_off_w, :] = epilogue(sum_taps in[n, oh*stride+dy,
@@ -268,14 +271,15 @@ int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, flo
  *   normalisation: g_weight (torch layout of `weight`), g_lognorm (Co), and g_bias (Co) = sum over pixels of g_out (an
  *   all-ones operand slab in the same GEMM).  ws: pvae_conv_wgrad_ws_floats(Ci, Co, ntaps) floats. */
 int pvae_conv_weight_prep(const float* weight, const float* lognorm, const float* bias, float* w_fwd, float* w_dgrad,
-                          float* bias_pad, int Co, int Ci, int Co_pad, int Ci_pad, int ntaps, int groups, void* stream);
+                          float* bias_pad, int Co, int Ci, int Co_pad, int Ci_pad, int ntaps, int groups, int with_lo,
+                          void* stream);
 int pvae_conv_weight_grad(const float* g_wp, const float* weight, const float* lognorm, float* g_weight, float* g_lognorm,
                           int Co, int Ci, int ntaps, int groups, void* stream);
 int pvae_conv_igemm(const float* in, const float* w_packed, float* out, float* out_act, const float* bias,
                     const float* add_pre, const float* dsilu_src, const float* add_post, int NI, int IH, int IW, int Ci,
                     int Co, int OH, int OW, int OHf, int OWf, int out_step, int out_off_h, int out_off_w, int stride,
-                    int ntaps, const int* tap_dy, const int* tap_dx, const int* tap_widx, int wtaps, int precise,
-                    void* stream);
+                    int ntaps, const int* tap_dy, const int* tap_dx, const int* tap_widx, int wtaps, int w_has_lo,
+                    int precise, void* stream);
 int64_t pvae_conv_wgrad_ws_floats(int Ci, int Co, int ntaps);
 int pvae_conv_wgrad(const float* in, const float* g_out, const float* weight, const float* lognorm, float* g_weight,
                     float* g_lognorm, float* g_bias, float* ws, int NI, int IH, int IW, int Ci, int Co, int OH, int OW,

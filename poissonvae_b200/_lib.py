@@ -81,9 +81,9 @@ _SIGNATURES = {
     "pvae_set_step_overlap": (_i, [_i]),
     "pvae_lin_step_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i,
                                    _u64, _u64, _p, _p, _p]),
-    "pvae_conv_weight_prep": (_i, [_p] * 6 + [_i] * 6 + [_p]),
+    "pvae_conv_weight_prep": (_i, [_p] * 6 + [_i] * 7 + [_p]),
     "pvae_conv_weight_grad": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
-    "pvae_conv_igemm": (_i, [_p] * 8 + [_i] * 14 + [_p, _p, _p, _i, _i, _p]),
+    "pvae_conv_igemm": (_i, [_p] * 8 + [_i] * 14 + [_p, _p, _p, _i, _i, _i, _p]),
     "pvae_conv_wgrad_ws_floats": (_i64, [_i, _i, _i]),
     "pvae_conv_wgrad": (_i, [_p] * 8 + [_i] * 9 + [_p, _p, _p, _i, _i, _i, _i, _p]),
     "pvae_cell_saved_floats": (_i64, [_p, _i]),

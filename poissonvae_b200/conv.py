@@ -62,17 +62,19 @@ def pad32(c: int) -> int:
     return (c + 31) // 32 * 32
 
 
-def weight_prep(weight, lognorm, bias, ntaps: int, groups: int = 1, need_dgrad: bool = True):
+def weight_prep(weight, lognorm, bias, ntaps: int, groups: int = 1, need_dgrad: bool = True, with_lo: bool = True):
     """-> (w_fwd [co][tap][ci], w_dgrad [ci][tap][co], bias) of the weight-normalised filter (base/common.py:426-431),
-    channel counts zero-padded to multiples of 32."""
+    channel counts zero-padded to multiples of 32.  with_lo: each packed matrix has twice the rows - the second half holds
+    the TF32 low parts x - trunc_tf32(x) of the first, which the convolution kernel then loads instead of computing."""
     co, ci = weight.shape[0], weight.shape[1]
     cop, cip = pad32(co), pad32(ci)
-    w_fwd = torch.empty(cop, ntaps * cip, device=weight.device, dtype=torch.float32)
-    w_dg = torch.empty(cip, ntaps * cop, device=weight.device, dtype=torch.float32) if need_dgrad else None
+    rep = 2 if with_lo else 1
+    w_fwd = torch.empty(rep * cop, ntaps * cip, device=weight.device, dtype=torch.float32)
+    w_dg = torch.empty(rep * cip, ntaps * cop, device=weight.device, dtype=torch.float32) if need_dgrad else None
     b_pad = torch.empty(cop, device=weight.device, dtype=torch.float32) if bias is not None else None
     with torch.cuda.device(weight.device):
         _lib.check(_lib.load().pvae_conv_weight_prep(_p(weight), _p(lognorm), _p(bias), _p(w_fwd), _p(w_dg), _p(b_pad), co, ci, cop,
-                                                     cip, ntaps, groups, _s()))
+                                                     cip, ntaps, groups, int(with_lo), _s()))
     return w_fwd, w_dg, b_pad
 
 
@@ -93,7 +95,7 @@ def _igemm(inp, w, out, out_act, bias, add_pre, dsilu_src, add_post, oh, ow, out
     with torch.cuda.device(inp.device):
         _lib.check(_lib.load().pvae_conv_igemm(_p(inp), _p(w), _p(out), _p(out_act), _p(bias), _p(add_pre), _p(dsilu_src),
                                                _p(add_post), n, ih, iw, ci, co, oh, ow, ohf, owf, out_step, off_h, off_w, stride,
-                                               len(taps), dy, dx, wi, wtaps, int(PRECISE), _s()))
+                                               len(taps), dy, dx, wi, wtaps, int(w.shape[0] == 2 * co), int(PRECISE), _s()))
 
 
 def conv_fwd(x_act, w_fwd, bias, k: int, stride: int, pad: int, co: int, want_act: bool = False):
@@ -511,7 +513,7 @@ class _ResConvPoolFn(torch.autograd.Function):
             x_act = silu(x)
         assert weight.shape[2] == h and weight.shape[3] == w, "ResConvPool expects the 'valid' convolution to cover the whole map"
         assert eps_res == 1.0
-        wf, _, _ = weight_prep(weight, lognorm, None, h * w, need_dgrad=False)
+        wf, _, _ = weight_prep(weight, lognorm, None, h * w, need_dgrad=False, with_lo=False)
         pool = torch.empty(n, ch, device=x.device, dtype=torch.float32)
         lib = _lib.load()
         with torch.cuda.device(x.device):

@@ -63,19 +63,20 @@ static Saved carve_saved(const pvae_cell& c, float* base, bool own_act) {
   Bump b(base);
   Saved s = {};
   s.x_act = own_act ? b.take(g.in_px * g.CiP) : nullptr;
-  s.wf1 = b.take(9ll * g.CoP * g.CiP), s.wd1 = b.take(9ll * g.CoP * g.CiP), s.bp1 = b.take(g.CoP);
+  // packed filters carry their TF32 low parts as a second block of rows (pvae_conv_weight_prep with_lo = 1): 2x
+  s.wf1 = b.take(18ll * g.CoP * g.CiP), s.wd1 = b.take(18ll * g.CoP * g.CiP), s.bp1 = b.take(g.CoP);
   if (!g.dec) {
-    s.wf2 = b.take(9ll * g.CoP * g.CoP), s.wd2 = b.take(9ll * g.CoP * g.CoP), s.bp2 = b.take(g.CoP);
+    s.wf2 = b.take(18ll * g.CoP * g.CoP), s.wd2 = b.take(18ll * g.CoP * g.CoP), s.bp2 = b.take(g.CoP);
     s.c1 = b.take(g.out_px * g.CoP), s.a2 = b.take(g.out_px * g.CoP);
   }
   s.c2 = b.take(g.out_px * g.CoP);  // the convolution output the gate multiplies (decoder: the only one)
   if (g.down) {
-    s.wfs = b.take(static_cast<long long>(g.ks) * g.ks * g.CoP * g.CiP), s.wds = b.take(static_cast<long long>(g.ks) * g.ks * g.CoP * g.CiP);
+    s.wfs = b.take(2ll * g.ks * g.ks * g.CoP * g.CiP), s.wds = b.take(2ll * g.ks * g.ks * g.CoP * g.CiP);
     s.bps = b.take(g.CoP);
     s.skip = b.take(g.out_px * g.CoP);
   }
   if (g.up) {
-    s.wfs = b.take(static_cast<long long>(g.CoP) * g.CiP), s.wds = b.take(static_cast<long long>(g.CoP) * g.CiP), s.bps = b.take(g.CoP);
+    s.wfs = b.take(2ll * g.CoP * g.CiP), s.wds = b.take(2ll * g.CoP * g.CiP), s.bps = b.take(g.CoP);
     s.skip = b.take(g.in_px * g.CoP);  // 1x1 convolution on the small map
     s.au = b.take(g.out_px * g.CiP);
   }
@@ -153,7 +154,7 @@ static int conv_forward(const float* in, const float* wf, const float* bias_p, f
   for (int r = 0; r < k; ++r)
     for (int q = 0; q < k; ++q) t.add(r - pad, q - pad, r * k + q);
   return pvae_conv_igemm(in, wf, out, out_act, bias_p, nullptr, nullptr, nullptr, N, IH, IW, CiP, CoP, OH, OW, OH, OW, 1, 0, 0, stride,
-                         t.n, t.dy, t.dx, t.wi, k * k, precise, s);
+                         t.n, t.dy, t.dx, t.wi, k * k, 1, precise, s);
 }
 
 // data gradient with the fused epilogue g_in = (conv^T(g_out) + add_pre) * silu'(dsilu_src) + add_post
@@ -164,7 +165,7 @@ static int conv_dgrad(const float* g_out, const float* wd, float* g_in, int N, i
     for (int r = 0; r < k; ++r)
       for (int q = 0; q < k; ++q) t.add(pad - r, pad - q, r * k + q);
     return pvae_conv_igemm(g_out, wd, g_in, nullptr, nullptr, add_pre, dsilu_src, add_post, N, OH, OW, CoP, CiP, IH, IW, IH, IW, 1, 0, 0, 1,
-                           t.n, t.dy, t.dx, t.wi, k * k, precise, s);
+                           t.n, t.dy, t.dx, t.wi, k * k, 1, precise, s);
   }
   for (int ph = 0; ph < 2; ++ph)  // one launch per parity class of the input grid
     for (int pw = 0; pw < 2; ++pw) {
@@ -179,7 +180,7 @@ static int conv_dgrad(const float* g_out, const float* wd, float* g_in, int N, i
             t.add(a >= 0 ? a / 2 : -((-a) / 2), b2 >= 0 ? b2 / 2 : -((-b2) / 2), r * k + q);
           }
       if (int rc = pvae_conv_igemm(g_out, wd, g_in, nullptr, nullptr, add_pre, dsilu_src, add_post, N, OH, OW, CoP, CiP, qh, qw, IH, IW,
-                                   2, ph, pw, 1, t.n, t.dy, t.dx, t.wi, k * k, precise, s))
+                                   2, ph, pw, 1, t.n, t.dy, t.dx, t.wi, k * k, 1, precise, s))
         return rc;
     }
   return PVAE_OK;
@@ -230,15 +231,15 @@ extern "C" int pvae_cell_fwd(const pvae_cell* c, const float* x, const float* x_
     TRY(pvae_silu_fwd(x, s.x_act, g.in_px * g.CiP, stream));
     x_act = s.x_act;
   }
-  TRY(pvae_conv_weight_prep(c->w1, c->ln1, c->b1, s.wf1, s.wd1, s.bp1, c->Co, c->Ci, g.CoP, g.CiP, 9, 1, stream));
+  TRY(pvae_conv_weight_prep(c->w1, c->ln1, c->b1, s.wf1, s.wd1, s.bp1, c->Co, c->Ci, g.CoP, g.CiP, 9, 1, 1, stream));
   if (!g.dec) {
-    TRY(pvae_conv_weight_prep(c->w2, c->ln2, c->b2, s.wf2, s.wd2, s.bp2, c->Co, c->Co, g.CoP, g.CoP, 9, 1, stream));
+    TRY(pvae_conv_weight_prep(c->w2, c->ln2, c->b2, s.wf2, s.wd2, s.bp2, c->Co, c->Co, g.CoP, g.CoP, 9, 1, 1, stream));
     TRY(conv_forward(x_act, s.wf1, s.bp1, s.c1, s.a2, g.N, g.H, g.W, g.CiP, g.CoP, 3, g.stride, 1, c->precise, stream));
     TRY(conv_forward(s.a2, s.wf2, s.bp2, s.c2, nullptr, g.N, g.OH, g.OW, g.CoP, g.CoP, 3, 1, 1, c->precise, stream));
     const float* skip = x;
     if (g.down) {
       TRY(pvae_conv_weight_prep(c->skip_w, c->skip_ln, c->skip_b, s.wfs, s.wds, s.bps, c->Co, c->Ci, g.CoP, g.CiP, g.ks * g.ks, g.groups,
-                                stream));
+                                1, stream));
       TRY(conv_forward(x_act, s.wfs, s.bps, s.skip, nullptr, g.N, g.H, g.W, g.CiP, g.CoP, g.ks, 2, 0, c->precise, stream));
       skip = s.skip;
     }
@@ -248,7 +249,7 @@ extern "C" int pvae_cell_fwd(const pvae_cell* c, const float* x, const float* x_
   if (g.up) {
     TRY(pvae_upsample_fwd(x_act, s.au, g.N, g.H, g.W, g.OH, g.OW, g.CiP, stream));
     TRY(conv_forward(s.au, s.wf1, s.bp1, s.c2, nullptr, g.N, g.OH, g.OW, g.CiP, g.CoP, 3, 1, 1, c->precise, stream));
-    TRY(pvae_conv_weight_prep(c->skip_w, c->skip_ln, c->skip_b, s.wfs, s.wds, s.bps, c->Co, c->Ci, g.CoP, g.CiP, 1, 1, stream));
+    TRY(pvae_conv_weight_prep(c->skip_w, c->skip_ln, c->skip_b, s.wfs, s.wds, s.bps, c->Co, c->Ci, g.CoP, g.CiP, 1, 1, 1, stream));
     TRY(conv_forward(x, s.wfs, s.bps, s.skip, nullptr, g.N, g.H, g.W, g.CiP, g.CoP, 1, 1, 0, c->precise, stream));
     return pvae_se_fwd(s.c2, s.skip, c->se_w1, c->se_b1, c->se_w2, c->se_b2, c->eps_res, y, y_act, s.pool, s.hid, s.gate, g.N, g.OH, g.OW,
                        g.CoP, c->Co, g.hd, 1, stream);

@@ -40,6 +40,7 @@ struct ConvParams {
   int tiles_w, tiles_h;
   int stride;
   int ntaps;
+  int w_lo_row;              // > 0: the packed filter carries its TF32 low parts in rows [w_lo_row, 2 w_lo_row) (prep kernel)
   ConvTap taps[kMaxTaps];
   // output pixel (n, oh, ow) -> ((n * OHf + oh * os + ooh) * OWf + ow * os + oow) * Co
   int OHf, OWf, os, ooh, oow;
@@ -125,10 +126,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const int s = kb % STAGES;
         mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
         uint8_t* sa = smem + s * kStageBytes;
-        mbar_expect_tx(&full_bar[s], kTileBytes);
+        const bool w_lo = SPLIT && p.w_lo_row > 0;  // the filter's low parts come precomputed: only A is split in the kernel
+        mbar_expect_tx(&full_bar[s], kTileBytes + (w_lo ? Cfg::kBBytes : 0u));
         const ConvTap tap = p.taps[t];
         tma_load_4d(&tma_a, &full_bar[s], sa, cb * 32, ow0 * p.stride + tap.dx, oh0 * p.stride + tap.dy, img0);
         tma_load_2d(&tma_b, &full_bar[s], sa + kABytes, tap.widx * p.Ci + cb * 32, co0);
+        if (w_lo) tma_load_2d(&tma_b, &full_bar[s], sa + kTileBytes + kABytes, tap.widx * p.Ci + cb * 32, p.w_lo_row + co0);
         if (++cb == cblocks) cb = 0, ++t;
       }
     }
@@ -165,7 +168,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const uint4* tile_hi = reinterpret_cast<const uint4*>(smem + s * kStageBytes);
         uint4* tile_lo = reinterpret_cast<uint4*>(smem + s * kStageBytes + kTileBytes);
 #pragma unroll 4
-        for (int i = ct; i < static_cast<int>(kTileBytes / 16); i += kGemmThreads - 64) tile_lo[i] = tf32_lo4(tile_hi[i]);
+        const int n16 = static_cast<int>((p.w_lo_row > 0 ? kABytes : kTileBytes) / 16);
+        for (int i = ct; i < n16; i += kGemmThreads - 64) tile_lo[i] = tf32_lo4(tile_hi[i]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv_bar[s])) : "memory");
       }
@@ -443,7 +447,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
 __global__ void __launch_bounds__(128) conv_weight_prep_kernel(const float* __restrict__ weight, const float* __restrict__ lognorm,
                                                                const float* __restrict__ bias, float* __restrict__ w_fwd,
                                                                float* __restrict__ w_dgrad, float* __restrict__ bias_pad, int Co,
-                                                               int Ci, int CoP, int CiP, int ntaps, int groups) {
+                                                               int Ci, int CoP, int CiP, int ntaps, int groups, int with_lo) {
   __shared__ float s_part[4];
   pdl_launch_dependents();
   pdl_wait();
@@ -471,6 +475,11 @@ __global__ void __launch_bounds__(128) conv_weight_prep_kernel(const float* __re
     }
     w_fwd[(static_cast<long long>(co) * ntaps + t) * CiP + ci] = v;
     if (w_dgrad != nullptr) w_dgrad[(static_cast<long long>(ci) * ntaps + t) * CoP + co] = v;
+    if (with_lo) {  // low part of the 3xTF32 split, x - trunc_tf32(x), as rows [rows, 2 rows) of the same matrices
+      const float lo = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      w_fwd[(static_cast<long long>(CoP + co) * ntaps + t) * CiP + ci] = lo;
+      if (w_dgrad != nullptr) w_dgrad[(static_cast<long long>(CiP + ci) * ntaps + t) * CoP + co] = lo;
+    }
   }
   if (threadIdx.x == 0 && bias_pad != nullptr) bias_pad[co] = (real && bias != nullptr) ? bias[co] : 0.f;
 }
@@ -658,13 +667,14 @@ extern "C" int pvae_set_conv_variant(int v) {
 }
 
 extern "C" int pvae_conv_weight_prep(const float* weight, const float* lognorm, const float* bias, float* w_fwd, float* w_dgrad,
-                                     float* bias_pad, int Co, int Ci, int Co_pad, int Ci_pad, int ntaps, int groups, void* stream) {
+                                     float* bias_pad, int Co, int Ci, int Co_pad, int Ci_pad, int ntaps, int groups, int with_lo,
+                                     void* stream) {
   if (!weight || !w_fwd || Co < 1 || Ci < 1 || Co_pad < Co || Ci_pad < Ci || ntaps < 1 || ntaps > kMaxTaps || groups < 1 ||
       (groups > 1 && (groups != ntaps || Co % groups)))
     return fail(PVAE_ERR_INVALID, "pvae_conv_weight_prep: bad argument");
   return cuda_ok("conv_weight_prep_kernel", launch_pdl(conv_weight_prep_kernel, dim3(Co_pad), dim3(128), 0, static_cast<cudaStream_t>(stream),
                                                        weight, lognorm, bias, w_fwd, w_dgrad, bias_pad, Co, Ci, Co_pad, Ci_pad, ntaps,
-                                                       groups));
+                                                       groups, with_lo));
 }
 
 extern "C" int pvae_conv_weight_grad(const float* g_wp, const float* weight, const float* lognorm, float* g_weight,
@@ -679,7 +689,7 @@ extern "C" int pvae_conv_igemm(const float* in, const float* w_packed, float* ou
                                const float* add_pre, const float* dsilu_src, const float* add_post, int NI, int IH, int IW,
                                int Ci, int Co, int OH, int OW, int OHf, int OWf, int out_step, int out_off_h, int out_off_w,
                                int stride, int ntaps, const int* tap_dy, const int* tap_dx, const int* tap_widx,
-                               int wtaps, int precise, void* stream) {
+                               int wtaps, int w_has_lo, int precise, void* stream) {
   if (!in || !w_packed || !out) return fail(PVAE_ERR_INVALID, "pvae_conv_igemm: null pointer");
   if (NI < 1 || IH < 1 || IW < 1 || OH < 1 || OW < 1 || stride < 1 || stride > 2 || out_step < 1)
     return fail(PVAE_ERR_INVALID, "pvae_conv_igemm: bad shape");
@@ -699,7 +709,8 @@ extern "C" int pvae_conv_igemm(const float* in, const float* w_packed, float* ou
   if (int rc = make_nhwc_map(&ma, in, NI, IH, IW, Ci, bw, bh, bi, stride, 0)) return rc;
   const int BN = (Co % 128 == 0 && g_conv_variant != 3) ? 128 : (Co % 64 == 0 ? 64 : 32);
   {
-    const long long dims[2] = {static_cast<long long>(wtaps) * Ci, Co}, strides[1] = {4ll * wtaps * Ci};
+    p.w_lo_row = w_has_lo ? Co : 0;
+    const long long dims[2] = {static_cast<long long>(wtaps) * Ci, w_has_lo ? 2ll * Co : Co}, strides[1] = {4ll * wtaps * Ci};
     const int box[2] = {32, BN}, estr[2] = {1, 1};
     if (int rc = make_tensor_map(&mb, w_packed, 2, dims, strides, box, estr, 0)) return rc;
   }

@@ -115,6 +115,10 @@ def test_conv_single_pass_tf32_is_coarser():
     weight = torch.randn(32, 32, 3, 3, generator=g, dtype=torch.float64) * 0.2
     ref = F.conv2d(x, weight, None, padding=1)
     wf, _, _ = conv.weight_prep(weight.float().cuda(), None, None, 9, need_dgrad=False)
+    wf_plain, _, _ = conv.weight_prep(weight.float().cuda(), None, None, 9, need_dgrad=False, with_lo=False)
+    y_lo, _ = conv.conv_fwd(nhwc(x), wf, None, 3, 1, 1, 32)        # filter low parts precomputed by the prep kernel
+    y_in, _ = conv.conv_fwd(nhwc(x), wf_plain, None, 3, 1, 1, 32)  # ... split in shared memory inside the kernel
+    assert torch.equal(y_lo, y_in)
     errs = {}
     try:
         for mode in (True, False):
