@@ -87,7 +87,10 @@ int pvae_sampler_fwd(const float* h, const float* log_r, const float* b_enc, flo
  *   g_z (B,K) upstream gradient wrt z; g_log_dr (B,K) optional upstream gradient wrt the returned
  *   log_dr; dz_acc (B,K) optional, as written by the forward (NULL: recompute the chain); kl_scale = beta / B_global fuses the gradient of beta * mean_b(sum_k kl) (0 to skip).
  *   g_h (B,K) out; g_log_r (K) and g_b_enc (K, optional) out - overwritten, or added to if
- *   accumulate != 0; partial_ws: workspace of 2 * pvae_num_partials(B) * K floats. */
+ *   accumulate > 0; accumulate < 0: the column partials are LEFT in partial_ws for pvae_adamax_from_partials
+ *   (pvae_sampler_bwd_partial_rows(B) rows of K floats for log_r, and the same for b_enc starting at row
+ *   pvae_sampler_bwd_bias_offset_rows(B)) and g_log_r / g_b_enc are not written;
+ *   partial_ws: workspace of 2 * pvae_num_partials(B) * K floats. */
 int pvae_sampler_bwd(const float* h, const float* log_r, const float* b_enc, const float* g_z,
                      const float* g_log_dr, const float* dz_acc, float kl_scale, float* g_h, float* g_log_r, float* g_b_enc,
                      float* partial_ws, int accumulate, int64_t B, int64_t K, int64_t row_offset,
