@@ -314,6 +314,13 @@ int pvae_se_fwd(const float* c, const float* skip, const float* W1, const float*
                 int C_real, int hd, int skip_up, void* stream);
 int pvae_se_bwd(const float* g_y, const float* c, const float* gate, const float* hid, const float* W1, const float* W2,
                 float eps_res, float* g_c, float* d2, float* d1, int N, int HW, int C, int C_real, int hd, void* stream);
+/* Parameter gradients of the squeeze-excitation layer from the per-image vectors pvae_se_fwd / pvae_se_bwd produced, in one
+ * launch (partial sums per block of images, combined in block order by the block that finishes last):
+ * g_w2 (C_real, hd) = d2^T hid, g_b2 = colsum d2, g_w1 (hd, C_real) = d1^T pool, g_b1 = colsum d1.
+ * ws: pvae_reduce_ws_floats(2 C_real hd + C_real + hd) floats.  Launches of this kernel on one device must be
+ * stream-ordered (it keeps one ticket counter). */
+int pvae_se_param_grads(const float* d2, const float* hid, const float* d1, const float* pool, float* g_w2, float* g_b2,
+                        float* g_w1, float* g_b1, float* ws, int N, int C_real, int hd, void* stream);
 /* Decoder pieces (main/vae.py:760-789, base/common.py:35-47,211-217): nearest-neighbour resampling with ATen's index
  * map (scale_factor 2 of the 'up' cells, size=14 for MNIST) and its gather backward (optionally times silu'(src));
  * (N, C, P) <-> (N, P, C) permutation of fc_dec's output (+ bias, + silu copy); the final 1x1 convolution to one channel

@@ -104,6 +104,7 @@ _SIGNATURES = {
     "pvae_small_tn": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p]),
     "pvae_se_fwd": (_i, [_p] * 6 + [_f] + [_p] * 5 + [_i] * 7 + [_p]),
     "pvae_se_bwd": (_i, [_p] * 6 + [_f] + [_p] * 3 + [_i] * 5 + [_p]),
+    "pvae_se_param_grads": (_i, [_p] * 9 + [_i, _i, _i, _p]),
     "pvae_upsample_fwd": (_i, [_p, _p] + [_i] * 6 + [_p]),
     "pvae_upsample_bwd": (_i, [_p, _p, _p] + [_i] * 6 + [_p]),
     "pvae_permute_cp": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _p]),

@@ -261,8 +261,13 @@ def _se_backward(g_y, c2, gate, hid, pool, se_w1, se_w2, eps_res):
     with torch.cuda.device(c2.device):
         _lib.check(_lib.load().pvae_se_bwd(_p(g_y), _p(c2), _p(gate), _p(hid), _p(se_w1), _p(se_w2), eps_res, _p(g_c2), _p(d2),
                                            _p(d1), n, h * w, ch, cr, hd, _s()))
-    g_w2, g_b2 = small_tn(d2, hid), colsum(d2)
-    g_w1, g_b1 = small_tn(d1, pool), colsum(d1)
+    lib = _lib.load()
+    g_w2, g_b2 = torch.empty(cr, hd, device=c2.device, dtype=torch.float32), torch.empty(cr, device=c2.device, dtype=torch.float32)
+    g_w1, g_b1 = torch.empty(hd, cr, device=c2.device, dtype=torch.float32), torch.empty(hd, device=c2.device, dtype=torch.float32)
+    ws = _workspace(c2.device, lib.pvae_reduce_ws_floats(2 * cr * hd + cr + hd))
+    with torch.cuda.device(c2.device):
+        _lib.check(lib.pvae_se_param_grads(_p(d2), _p(hid), _p(d1), _p(pool), _p(g_w2), _p(g_b2), _p(g_w1), _p(g_b1), _p(ws), n, cr, hd,
+                                           _s()))
     return g_c2, g_w1, g_b1, g_w2, g_b2
 
 

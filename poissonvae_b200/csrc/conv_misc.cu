@@ -661,6 +661,62 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   }
 }
 
+// ---- squeeze-excitation parameter gradients in ONE launch ------------------------------------------------------------
+// g_w2 (Cr, hd) = d2^T hid, g_b2 (Cr) = colsum d2, g_w1 (hd, Cr) = d1^T pool, g_b1 (hd) = colsum d1 over the N images.
+// Stage 1: every block sums its chunk of images into ws[block][n_out]; stage 2: the block that finishes last (ticket
+// counter) adds the partials in block order - deterministic, and one launch instead of eight.
+__device__ unsigned int g_se_ticket = 0;
+__global__ void __launch_bounds__(256) se_param_grads_kernel(const float* __restrict__ d2, const float* __restrict__ hid,
+                                                             const float* __restrict__ d1, const float* __restrict__ pool,
+                                                             float* __restrict__ g_w2, float* __restrict__ g_b2,
+                                                             float* __restrict__ g_w1, float* __restrict__ g_b1,
+                                                             float* __restrict__ ws, int N, int Cr, int hd, int rows_per_block) {
+  __shared__ bool s_last;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n_w = Cr * hd, n_out = 2 * n_w + Cr + hd;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(N, r0 + rows_per_block);
+  float* mine = ws + static_cast<long long>(blockIdx.x) * n_out;
+  for (int e = threadIdx.x; e < n_out; e += 256) {
+    float acc = 0.f;
+    if (e < n_w) {  // g_w2[c][j]
+      const int c = e / hd, j = e % hd;
+      for (int r = r0; r < r1; ++r) acc = fmaf(__ldg(d2 + r * Cr + c), __ldg(hid + r * hd + j), acc);
+    } else if (e < 2 * n_w) {  // g_w1[j][c]
+      const int j = (e - n_w) / Cr, c = (e - n_w) % Cr;
+      for (int r = r0; r < r1; ++r) acc = fmaf(__ldg(d1 + r * hd + j), __ldg(pool + r * Cr + c), acc);
+    } else if (e < 2 * n_w + Cr) {  // g_b2[c]
+      const int c = e - 2 * n_w;
+      for (int r = r0; r < r1; ++r) acc += __ldg(d2 + r * Cr + c);
+    } else {  // g_b1[j]
+      const int j = e - 2 * n_w - Cr;
+      for (int r = r0; r < r1; ++r) acc += __ldg(d1 + r * hd + j);
+    }
+    mine[e] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&g_se_ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int e = threadIdx.x; e < n_out; e += 256) {
+    float t = 0.f;
+    int b = 0;
+    for (; b + 4 <= static_cast<int>(gridDim.x); b += 4) {
+      const float v0 = ws[static_cast<long long>(b) * n_out + e], v1 = ws[static_cast<long long>(b + 1) * n_out + e],
+                  v2 = ws[static_cast<long long>(b + 2) * n_out + e], v3 = ws[static_cast<long long>(b + 3) * n_out + e];
+      t += v0, t += v1, t += v2, t += v3;
+    }
+    for (; b < static_cast<int>(gridDim.x); ++b) t += ws[static_cast<long long>(b) * n_out + e];
+    if (e < n_w) g_w2[e] = t;
+    else if (e < 2 * n_w) g_w1[e - n_w] = t;
+    else if (e < 2 * n_w + Cr) g_b2[e - 2 * n_w] = t;
+    else g_b1[e - 2 * n_w - Cr] = t;
+  }
+  if (threadIdx.x == 0) g_se_ticket = 0;  // ready for the next launch (launches of this kernel are stream-ordered)
+}
+
 static unsigned grid_for(long long work_items, int per_block = 256, int max_blocks = 148 * 8) {
   return static_cast<unsigned>(std::max<long long>(1, std::min<long long>((work_items + per_block - 1) / per_block, max_blocks)));
 }
@@ -758,6 +814,17 @@ extern "C" int pvae_se_bwd(const float* g_y, const float* c, const float* gate, 
     return fail(PVAE_ERR_UNSUPPORTED, "pvae_se_bwd: C=%d C_real=%d hd=%d", C, C_real, hd);
   return cuda_ok("se_bwd_kernel", launch_pdl(se_bwd_kernel, dim3(N), dim3(256), 0, PVAE_STREAM, g_y, c, gate, hid, W1, W2, eps_res,
                                              g_c, d2, d1, HW, C, C_real, hd));
+}
+
+// ws: gridDim * (2 Cr hd + Cr + hd) floats, at most 128 blocks: pvae_reduce_ws_floats(2 Cr hd + Cr + hd) is enough
+extern "C" int pvae_se_param_grads(const float* d2, const float* hid, const float* d1, const float* pool, float* g_w2, float* g_b2,
+                                   float* g_w1, float* g_b1, float* ws, int N, int C_real, int hd, void* stream) {
+  if (!d2 || !hid || !d1 || !pool || !g_w2 || !g_b2 || !g_w1 || !g_b1 || !ws || N < 1 || C_real < 1 || hd < 1)
+    return fail(PVAE_ERR_INVALID, "pvae_se_param_grads: bad argument");
+  const int blocks = std::max(1, std::min(128, (N + 31) / 32));
+  const int rows = (N + blocks - 1) / blocks;
+  return cuda_ok("se_param_grads_kernel", launch_pdl(se_param_grads_kernel, dim3((N + rows - 1) / rows), dim3(256), 0, PVAE_STREAM, d2,
+                                                     hid, d1, pool, g_w2, g_b2, g_w1, g_b1, ws, N, C_real, hd, rows));
 }
 
 extern "C" int pvae_upsample_fwd(const float* x, float* out, int N, int IH, int IW, int OH, int OW, int C, void* stream) {

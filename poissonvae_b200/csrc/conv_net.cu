@@ -103,7 +103,7 @@ static Scratch carve_scratch(const pvae_cell& c, float* base) {
   long long w = std::max(pvae_conv_wgrad_ws_floats(g.CiP, g.CoP, 9), pvae_conv_wgrad_ws_floats(g.CoP, g.CoP, 9));
   w = std::max<long long>(w, pvae_conv_wgrad_ws_floats(g.CiP, g.CoP, g.ks * g.ks));
   s.ws = b.take(w);
-  s.rws = b.take(pvae_reduce_ws_floats(static_cast<long long>(g.Co) * g.hd));
+  s.rws = b.take(pvae_reduce_ws_floats(2ll * g.Co * g.hd + g.Co + g.hd));
   s.total = b.used;
   return s;
 }
@@ -277,10 +277,7 @@ extern "C" int pvae_cell_bwd(const pvae_cell* c, const float* x, const float* x_
   void* s2 = side ? static_cast<void*>(side->stream) : stream;
   TRY(pvae_se_bwd(g_y, s.c2, s.gate, s.hid, c->se_w1, c->se_w2, c->eps_res, w.g_c2, w.d2, w.d1, g.N, g.OH * g.OW, g.CoP, c->Co, g.hd, stream));
   TRY(fork_to(side, 0, stream));
-  TRY(pvae_small_tn(w.d2, s.hid, c->g_se_w2, w.rws, g.N, c->Co, g.hd, s2));
-  TRY(pvae_colsum(w.d2, c->g_se_b2, w.rws, g.N, c->Co, s2));
-  TRY(pvae_small_tn(w.d1, s.pool, c->g_se_w1, w.rws, g.N, g.hd, c->Co, s2));
-  TRY(pvae_colsum(w.d1, c->g_se_b1, w.rws, g.N, g.hd, s2));
+  TRY(pvae_se_param_grads(w.d2, s.hid, w.d1, s.pool, c->g_se_w2, c->g_se_b2, c->g_se_w1, c->g_se_b1, w.rws, g.N, c->Co, g.hd, s2));
   if (!g.dec) {
     if (!c->g_w2 || !c->g_ln2 || !c->g_b2) return fail(PVAE_ERR_INVALID, "pvae_cell_bwd: null gradient pointer");
     if (g.down && (!c->g_skip_w || !c->g_skip_ln || !c->g_skip_b)) return fail(PVAE_ERR_INVALID, "pvae_cell_bwd: null skip gradient pointer");
