@@ -271,6 +271,11 @@ def _se_backward(g_y, c2, gate, hid, pool, se_w1, se_w2, eps_res):
     return g_c2, g_w1, g_b1, g_w2, g_b2
 
 
+# A trainer that keeps all gradients in one flat buffer sets this to {parameter data_ptr: gradient view} around its step:
+# the cells' backward then writes those gradients in place and hands autograd None for them (no per-parameter
+# allocation, no AccumulateGrad node, nothing to gather).  None: gradients are returned to autograd as usual.
+GRAD_SINK = None
+
 _CELL_FIELDS = ("w1", "ln1", "b1", "w2", "ln2", "b2", "se_w1", "se_b1", "se_w2", "se_b2", "skip_w", "skip_ln", "skip_b")
 
 
@@ -305,7 +310,12 @@ def _native_cell_backward(ctx, g_y):
     w1 = params[0]
     d = _lib.Cell()
     d.kind, d.N, d.H, d.W, d.Ci, d.Co, d.eps_res, d.precise = kind, n, h, w, w1.shape[1], w1.shape[0], eps_res, int(PRECISE)
-    grads = [None if t is None else torch.empty_like(t) for t in params]
+    grads, ret = [], []  # where the kernels write / what autograd gets
+    for t in params:
+        sink = None if (t is None or GRAD_SINK is None) else GRAD_SINK.get(t.data_ptr())
+        g = None if t is None else (sink if sink is not None else torch.empty_like(t))
+        grads.append(g)
+        ret.append(None if sink is not None else g)
     for name, t, g in zip(_CELL_FIELDS, params, grads):
         setattr(d, name, _p(t))
         setattr(d, "g_" + name, _p(g))
@@ -314,7 +324,7 @@ def _native_cell_backward(ctx, g_y):
     scratch = _workspace(x.device, lib.pvae_cell_scratch_floats(C.byref(d)))
     with torch.cuda.device(x.device):
         _lib.check(lib.pvae_cell_bwd(C.byref(d), _p(x), _p(x_act), _p(g_y), _p(g_x), _p(saved), _p(scratch), _s()))
-    return g_x, grads
+    return g_x, ret
 
 
 class _CellFn(torch.autograd.Function):

@@ -112,6 +112,7 @@ class TrainerVAE:
             raise ValueError("dp_mode='peer' does not support grad_clip")
         self.r_max = torch.zeros(max(n_batches_per_epoch, 1), device=self.device)  # rate.max() of each step of the epoch
         self._gather_tab = None
+        self._sink = None
         # CUDA-graph replay of the fused lin|lin step (single GPU), see _graph_step.  OFF by default: measured slower than
         # the eager launches (73.7 vs 69.6 us per step at batch 200, 104 vs 78 us at batch 1024, end-to-end 31.6 M vs 34.0 M
         # samples/s at batch 4096) although the host enqueue time halves (91 -> 49 us): the step is bound by the GPU, and
@@ -577,7 +578,14 @@ class TrainerVAE:
         finally:
             m.row_offset, m.rate_max_out, m.philox_override = 0, None, None
         Bg = x.shape[0] * self.world
-        (torch.sum(recon + beta * torch.sum(kl, dim=1)) / Bg).backward()
+        from . import conv
+        if self._sink is None:  # the conv cells write their parameter gradients straight into the flat buffer
+            self._sink = {self.views[k].data_ptr(): self.gviews[k] for k in names}
+        conv.GRAD_SINK = self._sink
+        try:
+            (torch.sum(recon + beta * torch.sum(kl, dim=1)) / Bg).backward()
+        finally:
+            conv.GRAD_SINK = None
         n = self.flat_p.numel()
         if self._gather_tab is None:
             offs, o = [], 0
@@ -586,7 +594,9 @@ class TrainerVAE:
                 o += params[k].numel()
             offs.append(o)
             self._gather_tab = (ctypes.c_int64 * len(offs))(*offs)
-        srcs = (ctypes.c_void_p * len(names))(*[None if params[k].grad is None else params[k].grad.data_ptr() for k in names])
+        # parameters whose gradient already sits in the flat buffer (written in place by a cell) copy onto themselves
+        srcs = (ctypes.c_void_p * len(names))(*[self.gviews[k].data_ptr() if params[k].grad is None else params[k].grad.data_ptr()
+                                                for k in names])
         _lib.check(lib.pvae_gather(srcs, self._gather_tab, len(names), _ptr(self._flat_g_ext), s))
         stats = self._flat_g_ext[n:n + 4]
         stats[0] = (recon.detach().sum() + beta * kl.detach().sum()) / Bg
