@@ -398,7 +398,7 @@ def run_ours(args):
                      "frac": round(achieved / peak, 4),
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/README.md);
                      # only captured for the default workload's forward sampler
-                     "traffic": 8415488 if (dom == "sampler_fwd" and B == 4096 and K == 512) else None,
+                     "traffic": 8441600 if (dom == "sampler_fwd" and B == 4096 and K == 512) else None,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": B * K * bytes_per_latent,
                      "kernel_us": {k: round(v, 2) for k, v in ktimes.items()},
