@@ -25,8 +25,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "training samples/sec (P-VAE lin|lin K=512)"
 UNIT = "samples/s"
+
+
+def metric_name(args):
+    return f"training samples/sec (P-VAE lin|lin K={args.latents})"
 
 
 def parse():
@@ -41,7 +44,9 @@ def parse():
     ap.add_argument("--temp", type=float, default=1.0)
     ap.add_argument("--beta", type=float, default=1.0)
     ap.add_argument("--exit", default="lossless", choices=["lossless", "never"])
-    ap.add_argument("--cpu_rows", type=int, default=256, help="rows of the batch the CPU baseline steps on")
+    ap.add_argument("--cpu_rows", type=int, default=200,
+                    help="rows of the batch the CPU baseline steps on: 200 = BASELINE config 1's batch (the reference's own "
+                         "CPU-runnable case), stepped in full")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_pdl", action="store_true", help="disable programmatic dependent launch (A/B)")
     ap.add_argument("--dp", default="auto", choices=["auto", "peer", "nccl"],
@@ -54,24 +59,37 @@ def parse():
                     help="CUDA-graph replay of the fused step (1 GPU; A/B - measured slower than the eager launches with "
                          "programmatic dependent launch, so off by default): auto = small batches and the static staging "
                          "buffers of the end-to-end path; on forces it")
-    ap.add_argument("--workload", default="config2", choices=["config2", "config4", "config5"],
-                    help="config2 (default): the BASELINE metric, lin|lin K=512.  config4 / config5: the secondary conv "
-                         "configurations (conv+b|lin CIFAR16-shaped; conv+b|conv+b MNIST-shaped 28x28), 1 GPU, with the CPU "
-                         "restatement of the reference's step beside them - not the driver's bench line")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"],
+                    help="config2 (default): the BASELINE metric, lin|lin K=512 beta=1, batch 4096 per GPU.  config3: BASELINE "
+                         "configs[2], lin|lin K=1024 beta=2.5, 8192 samples per GPU (65536 on 8 GPUs).  config4 / config5: the "
+                         "secondary conv configurations (conv+b|lin CIFAR16-shaped; conv+b|conv+b MNIST-shaped 28x28), 1 GPU, "
+                         "with the CPU restatement of the reference's step beside them - not the driver's bench line")
+    ap.add_argument("--min_region_ms", type=float, default=200.0,
+                    help="the K-step timed region is repeated (from the same training state) until the regions add up to this "
+                         "much device time; the MEDIAN region is reported")
+    ap.add_argument("--no_ref_cuda", action="store_true", help="skip the reference-on-CUDA leg of the default line")
+    ap.add_argument("--no_dp_check", action="store_true", help="N > 1: skip the correctness check of the gradient exchange")
     ap.add_argument("--ref_device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: 'cuda' times the same torch port of the reference's step with its "
                          "tensors on cuda:0 at the full batch (the reference's own CUDA path; north_star's denominator)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.workload == "config3":
+        a.latents, a.beta, a.batch = 1024, 2.5, 8192
+    return a
 
 
-def workload(args):
+def workload(args, world=None):
+    """`config` of the JSON line - the same dict on the product arm and on the reference arm."""
+    world = args.gpus if world is None else world
     return {"workload": f"poisson lin|lin K={args.latents} beta={args.beta:g} batch {args.batch}/GPU n_exp={args.n_exp} "
                         f"temp={args.temp:g} fp32, fwd+loss+bwd+Adamax, exit={args.exit}",
-            "batch_per_gpu": args.batch, "n_latents": args.latents, "n_exp": args.n_exp, "temp": args.temp,
+            "batch_per_gpu": args.batch, "n_latents": args.latents, "n_exp": args.n_exp, "temp": args.temp, "beta": args.beta,
             "input": "16x16 z-scored N(0,1) patches, seed 1234; weights N(0,0.05^2), log_rate U(-6,-4), cfg.seed 0",
             "gemm": "tf32 single pass" if getattr(args, "tf32", False) else "3xTF32 (fp32-grade, tcgen05)",
             "schedule": "reference vH16 lr warm-up (lr .005, 1 % of 78000 iterations), beta and temp pinned",
-            "graph": getattr(args, "graph", "off")}
+            "graph": getattr(args, "graph", "off"),
+            "l2": "inputs rotate over 64 distinct batches (>= 268 MB > 126 MB L2)",
+            "parallelism": f"dp{world}"}
 
 
 def synthetic_patches(n, seed):
@@ -123,27 +141,30 @@ def cuda_reference_steps(args, steps, warmup):
 
 
 def run_reference(args):
-    """Reference arm: the reference's own step on the host cores (its torch-CPU port, all threads).  Exactly K timed
-    steps after min(W, 3) warm-up steps; every step is a bounded sample of the workload (`rows` of the batch), sized
-    so that the whole run takes about a minute whatever K is."""
+    """Reference arm: the reference's own step on the host cores (its torch-CPU port, all threads): exactly K timed
+    steps after W warm-up steps (the same K and W as the product arm).  Every step is a bounded sample of the workload:
+    `cpu_rows` = 200 rows of the batch, i.e. BASELINE config 1 - the reference's own CPU-runnable case - stepped IN
+    FULL (no scaling of a partial batch); the row count only shrinks when K + W steps of 200 rows would not fit a few
+    minutes of CPU time."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     if args.ref_device == "cuda":
-        v, sps, gib = cuda_reference_steps(args, steps, warmup)
-        line = {"impl": "reference", "device": "cuda", "metric": METRIC, "value": round(v, 1), "unit": UNIT, "n_gpus": 1,
+        v, sps, gib = cuda_reference_steps(args, steps, max(warmup, 1))
+        line = {"impl": "reference", "device": "cuda", "metric": metric_name(args), "value": round(v, 1), "unit": UNIT, "n_gpus": 1,
                 "steps": steps, "warmup": warmup, "ms_per_step": round(sps * 1e3, 3), "higher_is_better": True,
-                "dtype": "f32", "data": "synthetic", "config": workload(args), "peak_mem_gib": round(gib, 2),
+                "dtype": "f32", "data": "synthetic", "config": workload(args, 1), "peak_mem_gib": round(gib, 2),
                 "note": "torch port of the reference step (bit-identical to it on CPU) run eagerly on cuda:0, full batch"}
         print(json.dumps(line), flush=True)
         return
-    # ~3.3 ms per row and step on 16 cores at n_exp = 263 (measured); aim at ~60 s of CPU work
-    rows = int(60.0 / (0.0033 * (steps + warmup) * max(args.n_exp, 1) / 263.0))
-    args.cpu_rows = max(8, min(args.cpu_rows, rows - rows % 4))
+    # ~3.3 ms per row and step on 16 cores at n_exp = 263, K = 512 (measured); keep the whole run under ~4 minutes
+    budget_rows = int(240.0 / (0.0033 * (steps + warmup) * max(args.n_exp, 1) / 263.0 * args.latents / 512.0))
+    args.cpu_rows = max(8, min(args.cpu_rows, budget_rows - budget_rows % 4))
     v, cores, sps = cpu_reference_steps(args, steps, warmup)
-    sample = f"{args.cpu_rows} of {args.batch} rows per step, {steps} steps after {warmup} warm-up, torch CPU {cores} threads"
-    line = {"impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus,
+    sample = (f"{args.cpu_rows} rows per step (BASELINE config 1 batch = 200) of the {args.batch}-row workload batch, "
+              f"{steps} steps after {warmup} warm-up, torch CPU port of the reference step (oracle/ref_port.py), {cores} threads")
+    line = {"impl": "reference", "metric": metric_name(args), "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": round(sps * 1e3, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(args),
             "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -301,7 +322,7 @@ def run_ours(args):
         tr.lib.pvae_set_dec_splits(args.dec_splits)
 
     # inputs: 64 distinct batches (268 MB at B=4096 > 126 MB L2) so that no step finds its input in L2
-    NB = 64
+    NB = 64 if B * 256 * 4 * 64 <= (1 << 30) else 32
     host = synthetic_patches(NB * B, 1234 + rank).view(NB, B, 256).pin_memory()
     data = host.to(dev)
 
@@ -314,7 +335,7 @@ def run_ours(args):
     for i in range(W):
         tr.train_step(data[i % NB], i)
     barrier()
-    # every pass below (device-resident, instrumented, end-to-end) trains the same K steps from this state: the
+    # every pass below (device-resident regions, instrumented, end-to-end) trains the same K steps from this state: the
     # sampler's work depends on the rates, so the passes must not see different stages of training
     snap = (tr.flat_p.clone(), tr.exp_avg.clone(), tr.exp_inf.clone(), tr.opt_step)
 
@@ -324,23 +345,31 @@ def run_ours(args):
         torch.cuda.manual_seed(4321)
         barrier()
 
-    restore()
     if clocks is not None:
         clocks.mark()
+    # A region = EXACTLY K steps between barrier + synchronize on both sides, timed with CUDA events on the launch
+    # stream, max over ranks.  K steps of ~0.1 ms are a thin sample, so the region is repeated (each time from the same
+    # training state) until the regions add up to min_region_ms of device time; the MEDIAN region is the reported one.
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = tr.lib.pvae_launch_count()
-    e0.record()
-    for i in range(K_steps):
-        tr.train_step(data[(W + i) % NB], W + i)
-    e1.record()
-    launches = tr.lib.pvae_launch_count() - launches0  # counted by the library itself, every launch of the timed region
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = ms.item()
+    regions, launches = [], 0
+    while True:
+        restore()
+        launches0 = tr.lib.pvae_launch_count()
+        e0.record()
+        for i in range(K_steps):
+            tr.train_step(data[(W + i) % NB], W + i)
+        e1.record()
+        launches = tr.lib.pvae_launch_count() - launches0  # counted by the library itself, every launch of the region
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        regions.append(ms.item())  # identical on every rank: all ranks leave the loop together
+        if sum(regions) >= args.min_region_ms or len(regions) >= 200:
+            break
+    ms_total = sorted(regions)[len(regions) // 2]
     # the same K steps again, now with CUDA events around the two sampler launches (roofline numerator).  Kept out
-    # of the pass above because an event record between two kernels defeats their programmatic dependent launch.
+    # of the regions above because an event record between two kernels defeats their programmatic dependent launch.
     restore()
     tr.kernel_events = {}
     for i in range(K_steps):
@@ -365,6 +394,11 @@ def run_ours(args):
     clk = clocks.stop() if clocks is not None else None
     final_loss = loss_host[K_steps - 1][0].item()
 
+    # ---- N > 1: correctness of the gradient exchange that just ran, outside every timed region ------
+    dp_check = None
+    if world > 1 and not args.no_dp_check:
+        dp_check = exchange_check(args, world, rank, dev, tr.peer is not None)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -375,50 +409,133 @@ def run_ours(args):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    dom = max(("sampler_fwd", "sampler_bwd"), key=lambda k: ktimes.get(k, 0.0))
-    # forward: read h, write z and dz_acc; backward: read h, g_z, dz_acc, write g_h
-    bytes_per_latent = {"sampler_fwd": 12, "sampler_bwd": 16}[dom]
-    achieved = B * K * bytes_per_latent / (ktimes[dom] * 1e-6) / 1e9
+    # ALGORITHMIC bytes per latent, SURVEY.md 8(d): forward read h + write z = 8 B; backward read h, g_z + write g_h =
+    # 12 B.  The implementation also moves dz_acc (written by the forward, read by the backward: +4 B each, L2-resident)
+    # and the TF32 low planes of z / g_h for the GEMMs; that is reported as implementation traffic, not credited.
+    alg = {"sampler_fwd": 8, "sampler_bwd": 12}
+    impl_extra = {"sampler_fwd": 4 + (4 if tr.planes else 0), "sampler_bwd": 4 + (4 if tr.planes else 0)}
+    dom = "sampler_fwd" if ktimes.get("sampler_fwd", 0.0) >= ktimes.get("sampler_bwd", 0.0) else "sampler_bwd"
+    gbs = {k: B * K * alg[k] / (ktimes[k] * 1e-6) / 1e9 for k in alg if ktimes.get(k)}
     value = world * B * K_steps / (ms_total * 1e-3)
+    step_us = ms_total / K_steps * 1e3
     line = {
-        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": W,
+        "metric": metric_name(args), "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": W,
         "ms_per_step": round(ms_total / K_steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": dict(workload(args), l2="inputs rotate over 64 distinct batches (268 MB > 126 MB L2)",
-                       parallelism=f"dp{world}", final_loss=round(final_loss, 4),
-                       gradient_exchange=("none (1 GPU)" if world == 1 else
-                                          "NVLink peer-memory all-reduce fused with Adamax" if tr.peer is not None else
-                                          "NCCL all-reduce")),
+        "config": workload(args, world),
+        "final_loss": round(final_loss, 4),
+        "gradient_exchange": ("none (1 GPU)" if world == 1 else
+                              "NVLink peer-memory all-reduce fused with Adamax" if tr.peer is not None else "NCCL all-reduce"),
+        "regions": {"n": len(regions), "steps_each": K_steps, "ms_median": round(ms_total, 4), "ms_min": round(min(regions), 4),
+                    "ms_max": round(max(regions), 4), "note": "every region restarts from the same training state"},
         "clocks": clk,
         "e2e": {"value": round(world * B * K_steps / e2e_s.item(), 1), "unit": UNIT,
                 "h2d_bytes_per_step": B * 256 * 4, "d2h_bytes_per_step": 12,
                 "host_enqueue_us_per_step": round(t_enq / K_steps * 1e6, 1)},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4),
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/README.md);
-                     # only captured for the default workload's forward sampler
-                     "traffic": 8441600 if (dom == "sampler_fwd" and B == 4096 and K == 512) else None,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(gbs[dom], 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(gbs[dom] / peak, 4),
+                     "traffic": committed_traffic(dom, B, K),
                      "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": B * K * bytes_per_latent,
+                     "algorithmic_bytes_per_latent": alg, "algorithmic_bytes_per_launch": B * K * alg[dom],
+                     "implementation_extra_bytes_per_latent": impl_extra,
                      "kernel_us": {k: round(v, 2) for k, v in ktimes.items()},
+                     "kernels": {k: {"achieved": round(v, 1), "frac": round(v / peak, 4)} for k, v in gbs.items()},
+                     "sampler_fwd_plus_bwd": {"achieved": round(B * K * 20 / ((ktimes["sampler_fwd"] + ktimes["sampler_bwd"]) * 1e-6) / 1e9, 1),
+                                              "frac": round(B * K * 20 / ((ktimes["sampler_fwd"] + ktimes["sampler_bwd"]) * 1e-6) / 1e9 / peak, 4)},
+                     "whole_step": {"achieved": round(B * K * 20 / (step_us * 1e-6) / 1e9, 1),
+                                    "frac": round(B * K * 20 / (step_us * 1e-6) / 1e9 / peak, 4),
+                                    "note": "20 B/latent (sampler fwd + bwd) over the whole step's time"},
                      "timed": f"CUDA events on the launch stream around each sampler launch, mean over {K_steps} steps "
-                              "run right after the timed region"},
+                              "run right after the timed regions"},
     }
+    if dp_check is not None:
+        line["dp_check"] = dp_check
+    ref_bytes = 4.0 * args.n_exp * B * K  # one materialised (n_exp, B, K) fp32 tensor of the reference path
+    if world == 1 and not args.no_ref_cuda and ref_bytes * 16 > 150e9:
+        line["ref_cuda"] = {"skipped": f"the reference path materialises ~16 tensors of {ref_bytes / 1e9:.1f} GB at this shape"}
+    elif world == 1 and not args.no_ref_cuda:
+        # north_star's denominator: the reference's own CUDA path on this same B200 (its op sequence - bit-identical
+        # to the unmodified reference on CPU, tests/test_ref_port.py - run eagerly with the tensors on cuda:0, full batch)
+        torch.cuda.empty_cache()
+        ref_steps = 10
+        rv, rsps, rgib = cuda_reference_steps(args, ref_steps, 3)
+        line["ref_cuda"] = {"value": round(rv, 1), "unit": UNIT, "ms_per_step": round(rsps * 1e3, 3), "steps": ref_steps, "warmup": 3,
+                            "peak_mem_gib": round(rgib, 2), "x_over_ref_cuda": round(value / rv, 1),
+                            "what": "oracle/ref_port.py (the reference's torch op sequence: materialised (n_exp,B,K) tensors, "
+                                    "autograd backward, eager Adamax) on cuda:0 at the same batch, CUDA-event timed"}
     if world == 1 and not args.no_cpu_baseline:
-        steps_cpu = 3
-        v, cores, _ = cpu_reference_steps(args, steps_cpu, 1)
+        steps_cpu, warm_cpu = 10, 3
+        args.cpu_rows = min(args.cpu_rows, 200)
+        v, cores, _ = cpu_reference_steps(args, steps_cpu, warm_cpu)
         line["cpu_baseline"] = {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{args.cpu_rows} of {B} rows per step, {steps_cpu} steps after 1 warm-up, "
-                                          f"torch CPU port of the reference step (oracle/ref_port.py)"}
+                                "sample": f"BASELINE config 1 exactly: batch {args.cpu_rows} stepped in full (no row sampling of "
+                                          f"a larger batch), K={K}, n_exp={args.n_exp}, {steps_cpu} steps after {warm_cpu} warm-up, "
+                                          f"torch CPU port of the reference step (oracle/ref_port.py), {cores} threads"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def committed_traffic(kernel, B, K):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the named kernel at this shape, from the ncu --set
+    full capture committed under profiles/ (profiles/traffic.json names the capture and the commit it was taken at);
+    null when no capture of this kernel + shape is committed.  Never a number of this run."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    rec = json.load(open(path)).get(f"{kernel}:B{B}:K{K}")
+    return None if rec is None else rec["dram_bytes"]
+
+
+def exchange_check(args, world, rank, dev, peer):
+    """Data-parallel correctness, run once outside the timed regions: `world` ranks stepping 4 times (both gradient
+    buffer parities, twice) on contiguous shards of a global batch, through the same exchange path the benchmark used,
+    against ONE GPU stepping on the full global batch (every rank computes that reference itself).  Returns
+    {"ranks_identical", "rel_vs_1gpu", ...}."""
+    import torch
+    import torch.distributed as dist
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
+    K, Bl, steps = args.latents, 512, 4
+    Bg = Bl * world
+    data = torch.randn(steps, Bg, 256, generator=torch.Generator().manual_seed(99)).to(dev)
+
+    def run(dp_mode):
+        model = PoissonVAE(ConfigPoisVAE(n_latents=K, prior_clamp=-4, seed=0)).to(dev)
+        with torch.no_grad():
+            model.log_rate.add_(3.0)
+        model.update_n(20.0)
+        cfg = ConfigTrainVAE(lr=0.005, epochs=100, batch_size=Bl if dp_mode != "off" else Bg, warmup_portion=0.0,
+                             scheduler_type=None, grad_clip=None, kl_beta=args.beta, kl_anneal_portion=0.0, kl_const_portion=0.0,
+                             temp_anneal_portion=0.0, temp_stop=0.3)
+        tr = TrainerVAE(model, cfg, dp_mode=dp_mode)
+        losses = []
+        for i in range(steps):
+            x = data[i] if dp_mode == "off" else data[i, rank * Bl:(rank + 1) * Bl]
+            if dp_mode != "off" and (i + rank) % 2 == 1:
+                torch.cuda._sleep(2_000_000)  # ~1 ms of skew, alternating between the ranks
+            losses.append(tr.train_step(x, i, philox=(77, 4 * i)).clone())
+        torch.cuda.synchronize()
+        return tr.flat_p.clone(), torch.stack(losses), tr.peer is not None
+
+    p_dp, l_dp, used_peer = run("peer" if peer else "nccl")
+    p_1, l_1, _ = run("off")
+    lo, hi = p_dp.clone(), p_dp.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    rel = ((p_dp - p_1).abs().max() / p_1.abs().max()).reshape(1)
+    lrel = ((l_dp - l_1).abs() / l_1.abs()).max().reshape(1)
+    dist.all_reduce(rel, op=dist.ReduceOp.MAX)
+    dist.all_reduce(lrel, op=dist.ReduceOp.MAX)
+    return {"ranks_identical": bool(torch.equal(lo, hi)), "rel_vs_1gpu": float(rel.item()), "loss_rel_vs_1gpu": float(lrel.item()),
+            "steps": steps, "global_batch": Bg, "path": "peer" if used_peer else "nccl",
+            "ok": bool(torch.equal(lo, hi)) and rel.item() < 2e-5 and lrel.item() < 2e-5}
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.workload != "config2" and a.impl == "ours":
+    if a.workload in ("config4", "config5") and a.impl == "ours":
         run_conv_workload(a)
         sys.exit(0)
     if a.impl == "reference":

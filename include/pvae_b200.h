@@ -186,10 +186,13 @@ int64_t pvae_sampler_bwd_bias_offset_rows(int64_t B);
  * the device: [optimiser steps taken so far, -, Philox offset (uint64 in ints 2..3)]; lr_sched[i] is the learning rate of
  * optimiser step i + 1 (clamped at n_sched - 1).  A one-thread kernel enqueued right behind the update advances the step
  * counter by 1 and the Philox offset by philox_increment, so the sampler launches of the next replay (which read the offset
- * through their offset_dev argument) draw fresh numbers without any host-side parameter. */
+ * through their offset_dev argument) draw fresh numbers without any host-side parameter.  rmax_step / rmax_ring / ring_n
+ * (optional): the same kernel moves the step's rate.max() from the fixed word the captured sampler max-reduces into to slot
+ * (steps taken so far) % ring_n of the epoch's ring and zeroes the word, like the eager path's per-step slot
+ * (`r_max.update(dist.rate.max())`, main/train_vae.py:388). */
 int pvae_adamax_step_dev(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, const float* lr_sched, int n_sched,
                          int* state, float beta1, float beta2, float eps, float weight_decay, const float* clip_coef,
-                         uint64_t philox_increment, void* stream);
+                         uint64_t philox_increment, float* rmax_step, float* rmax_ring, int ring_n, void* stream);
 /* Gather n_tensors device arrays into one flat buffer: dst[offsets[i] .. offsets[i+1]) = srcs[i] (zeros where srcs[i] is
  * NULL).  srcs / offsets are HOST arrays (offsets has n_tensors + 1 entries).  One launch per 96 tensors: the per-parameter
  * gradients autograd hands out become the flat buffer the all-reduce / clip / Adamax kernels work on. */
@@ -222,6 +225,9 @@ int pvae_allreduce_adamax(float* p, float* exp_avg, float* exp_inf, int64_t n, i
  *   precise: GEMM mode (see pvae_gemm_tf32); events: NULL or 4 cudaEvent_t recorded before/after the sampler
  *   forward (0,1) and before/after the sampler backward (2,3) - used by bench.py for the roofline timing. */
 int64_t pvae_lin_step_ws_floats(int64_t B, int64_t K, int64_t D);
+/* Offsets (in floats from the start of ws) of the step's intermediates, for parity tests that read them back after a step:
+ * out7 = [h (B,K), z (B,K), dz_acc (B,K), g_y (B,D), g_z (B,K), g_h (B,K), kl_rowsum (B)]. */
+int pvae_lin_step_ws_offsets(int64_t B, int64_t K, int64_t D, int64_t* out7);
 /* pvae_lin_step_fwd_bwd followed by the optimiser in the same call: the wgrad split partials and the sampler's column
  * partials are reduced inside ONE Adamax kernel (pvae_adamax_from_partials) instead of three reduction kernels + Adamax.
  * Single GPU (B_global == B), no gradient clipping.  grads receives the gradient as before; results are bit-identical to

@@ -17,6 +17,7 @@ Fixtures (all fp32 CPU; sizes kept small so the files stay a few hundred KB):
 from __future__ import annotations
 
 import os
+import sys
 
 import numpy as np
 import torch
@@ -234,11 +235,47 @@ def gen_scalars(ref):
     np.savez_compressed(os.path.join(OUT, "scalars.npz"), **rec)
 
 
+def gen_lr(ref):
+    """Learning rate seen by every optimiser step of the reference loop: the reference's own Adamax
+    (base/adamax.py) under torch's CosineAnnealingLR with the T_max override of base/train_base.py:282-287,
+    driven exactly like main/train_vae.py:326-337 (warm-up overwrites param_group['lr']) and :391-400 (the
+    scheduler only steps outside warm-up).  CosineAnnealingLR is recursive on the group's current lr, so the
+    cosine starts from the LAST warm-up value, not from cfg.lr."""
+    rec = {}
+    cases = [("a", 0.005, 400, 0.1, 1e-5), ("b", 0.002, 90, 0.05, 1e-5), ("c", 0.002, 64, 0.0, 1e-5),
+             ("d", 0.005, 26 * 30, 0.01, 1e-5)]
+    for tag, lr, n_iters, warmup_portion, eta_min in cases:
+        w = torch.nn.Parameter(torch.zeros(3))
+        optim = ref.adamax.Adamax(params=[w], lr=lr)
+        sched = torch.optim.lr_scheduler.CosineAnnealingLR(optim, T_max=n_iters, eta_min=eta_min)
+        sched.T_max = n_iters - n_iters * warmup_portion
+        lrs = []
+        for gstep in range(n_iters):
+            progress = gstep / n_iters
+            is_warming_up = progress < warmup_portion
+            if is_warming_up:
+                for group in optim.param_groups:
+                    group['lr'] = lr * progress / warmup_portion
+            lrs.append(optim.param_groups[0]['lr'])  # the lr optim.step() uses at this gstep
+            w.grad = torch.ones(3)
+            optim.step()
+            if not is_warming_up:
+                sched.step()
+        rec[f"lr_{tag}"] = np.array(lrs, dtype=np.float64)
+        rec[f"cfg_{tag}"] = np.array([lr, n_iters, warmup_portion, eta_min], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "lr_schedule.npz"), **rec)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
     ref = ref_import.load()
+    if len(sys.argv) > 1:  # regenerate selected fixtures only: python oracle/make_golden.py lr scalars ...
+        for name in sys.argv[1:]:
+            globals()["gen_" + name](ref)
+        return
     gen_scalars(ref)
+    gen_lr(ref)
     gen_sampler(ref)
     gen_hard(ref)
     gen_vae(ref)

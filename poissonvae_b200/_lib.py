@@ -14,25 +14,45 @@ LIB_PATH = os.path.join(_HERE, "libpvae_b200.so")
 SOURCES = ["capi.cu", "sampler.cu", "step.cu", "gemm_tc.cu", "lin_step.cu", "peer_allreduce.cu", "conv_tc.cu",
            "conv_misc.cu", "conv_net.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
 
 _lib = None
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into libpvae_b200.so (nvcc cross-compiles without a GPU)."""
+    """Compile every CUDA source for sm_100a into libpvae_b200.so (nvcc cross-compiles without a GPU).  One object per
+    source, compiled in parallel and re-used while the source and the shared headers are unchanged, then one link."""
+    from concurrent.futures import ThreadPoolExecutor
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
-    deps.append(os.path.join(os.path.dirname(_HERE), "include", "pvae_b200.h"))
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    hdrs.append(os.path.join(os.path.dirname(_HERE), "include", "pvae_b200.h"))
+    hdrs.append(os.path.abspath(__file__))  # the flags live here
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in srcs + hdrs):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    objdir = os.path.join(_HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    newest_hdr = max(os.path.getmtime(h) for h in hdrs)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), newest_hdr):
+            return obj, ""
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, srcs))
+    if verbose:
+        print("".join(log for _, log in results))
+    cmd = [nvcc] + LINK_FLAGS + ["-o", LIB_PATH] + [obj for obj, _ in results]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 
@@ -73,11 +93,12 @@ _SIGNATURES = {
     "pvae_sampler_bwd_partial_rows": (_i64, [_i64]),
     "pvae_sampler_bwd_bias_offset_rows": (_i64, [_i64]),
     "pvae_lin_step_train": (_i, [_p] * 8 + [_i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i, _u64, _u64, _p, _p, _f, _i, _f, _f, _f, _f, _p]),
-    "pvae_adamax_step_dev": (_i, [_p, _p, _p, _p, _i64, _p, _i, _p, _f, _f, _f, _f, _p, _u64, _p]),
+    "pvae_adamax_step_dev": (_i, [_p, _p, _p, _p, _i64, _p, _i, _p, _f, _f, _f, _f, _p, _u64, _p, _p, _i, _p]),
     "pvae_gather": (_i, [_p, _p, _i, _p, _p]),
     "pvae_adamax_step": (_i, [_p, _p, _p, _p, _i64, _f, _i, _f, _f, _f, _f, _p, _p]),
     "pvae_allreduce_adamax": (_i, [_p, _p, _p, _i64, _i64, _p, _p, _i, _i, C.c_uint32, _p, _p, _f, _i, _f, _f, _f, _f, _p]),
     "pvae_lin_step_ws_floats": (_i64, [_i64, _i64, _i64]),
+    "pvae_lin_step_ws_offsets": (_i, [_i64, _i64, _i64, _p]),
     "pvae_set_step_overlap": (_i, [_i]),
     "pvae_lin_step_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i,
                                    _u64, _u64, _p, _p, _p]),

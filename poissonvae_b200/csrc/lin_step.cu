@@ -86,6 +86,16 @@ extern "C" int64_t pvae_lin_step_ws_floats(int64_t B, int64_t K, int64_t D) {
   return carve(nullptr, B, K, D).total;
 }
 
+// where the step's intermediates sit in the workspace (floats from its start): parity tests read z, h, ... back
+extern "C" int pvae_lin_step_ws_offsets(int64_t B, int64_t K, int64_t D, int64_t* out7) {
+  if (B <= 0 || K <= 0 || D <= 0 || !out7) return pvae::fail(PVAE_ERR_INVALID, "pvae_lin_step_ws_offsets: bad argument");
+  float* const base = reinterpret_cast<float*>(uintptr_t(1) << 20);  // any non-null base: only differences are used
+  const Ws w = carve(base, B, K, D);
+  const float* f[7] = {w.h, w.z, w.dz, w.g_y, w.g_z, w.g_h, w.klrow};
+  for (int i = 0; i < 7; ++i) out7[i] = f[i] - base;
+  return PVAE_OK;
+}
+
 namespace {
 struct Update {  // optimiser fused into the step (pvae_lin_step_train); p == nullptr: gradients only
   bool fuse_reduce = false;  // gradients only, but all partials reduced by ONE kernel instead of three

@@ -236,9 +236,16 @@ __global__ void __launch_bounds__(256) adamax_dev_kernel(float* __restrict__ p, 
     p[i] = pi - clr * (mi / ui);
   }
 }
-__global__ void advance_state_kernel(int* __restrict__ state, unsigned long long philox_increment) {
+__global__ void advance_state_kernel(int* __restrict__ state, unsigned long long philox_increment, float* __restrict__ rmax_step,
+                                     float* __restrict__ rmax_ring, int ring_n) {
   pdl_wait();  // every reader of this step's counters has been launched before us and the predecessor has finished
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (rmax_step != nullptr && rmax_ring != nullptr && ring_n > 0) {
+      // the replayed sampler max-reduces rate.max() into one fixed word: move it to this step's slot of the epoch ring
+      // (the eager path writes slot gstep % ring_n directly, main/train_vae.py:388) and reset the word
+      rmax_ring[state[0] % ring_n] = *rmax_step;
+      *rmax_step = 0.f;
+    }
     state[0] += 1;
     *reinterpret_cast<unsigned long long*>(state + 2) += philox_increment;
   }
@@ -295,7 +302,8 @@ extern "C" int pvae_adamax_from_partials(float* p, float* g_out, float* exp_avg,
 
 extern "C" int pvae_adamax_step_dev(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, const float* lr_sched,
                                     int n_sched, int* state, float beta1, float beta2, float eps, float weight_decay,
-                                    const float* clip_coef, uint64_t philox_increment, void* stream) {
+                                    const float* clip_coef, uint64_t philox_increment, float* rmax_step, float* rmax_ring,
+                                    int ring_n, void* stream) {
   if (n <= 0 || !p || !g || !exp_avg || !exp_inf || !lr_sched || n_sched < 1 || !state)
     return fail(PVAE_ERR_INVALID, "pvae_adamax_step_dev: bad argument");
   if (reinterpret_cast<uintptr_t>(state) & 7) return fail(PVAE_ERR_INVALID, "pvae_adamax_step_dev: state must be 8-byte aligned");
@@ -306,7 +314,7 @@ extern "C" int pvae_adamax_step_dev(float* p, const float* g, float* exp_avg, fl
                                                           beta1, beta2, eps, weight_decay, clip_coef)))
     return rc;
   // plain launch (no programmatic overlap): it must not run before the Adamax kernel has read the counter
-  advance_state_kernel<<<1, 32, 0, s>>>(state, static_cast<unsigned long long>(philox_increment));
+  advance_state_kernel<<<1, 32, 0, s>>>(state, static_cast<unsigned long long>(philox_increment), rmax_step, rmax_ring, ring_n);
   count_launch();
   return cuda_ok("advance_state_kernel", cudaGetLastError());
 }

@@ -51,6 +51,28 @@ def beta_anneal_linear(n_iters, beta=1.0, anneal_portion=0.3, constant_portion=0
     return betas
 
 
+def lr_schedule(gstep, n_iters, lr, warmup_portion=0.01, scheduler_type='cosine', eta_min=1e-5):
+    """Learning rate of the optimiser step at `gstep`: linear warm-up (main/train_vae.py:329-337), then torch's
+    CosineAnnealingLR with T_max = n_iters - n_iters * warmup_portion (base/train_base.py:282-287), stepped only
+    outside warm-up (main/train_vae.py:391-400).  That scheduler is recursive on the group's current lr, so the
+    cosine starts from the LAST warm-up value - which is also the lr of the first step after warm-up - not from
+    cfg.lr.  Pinned to the reference optimiser + torch scheduler by tests/golden/lr_schedule.npz."""
+    progress = gstep / n_iters
+    if progress < warmup_portion:
+        return lr * progress / warmup_portion
+    warm = math.ceil(warmup_portion * n_iters)  # first gstep with progress >= warmup_portion
+    while warm > 0 and (warm - 1) / n_iters >= warmup_portion:
+        warm -= 1
+    while warm / n_iters < warmup_portion:
+        warm += 1
+    lr_warm = lr * ((warm - 1) / n_iters) / warmup_portion if warm >= 1 else lr
+    if scheduler_type is None:
+        return lr_warm
+    t_max = n_iters - n_iters * warmup_portion
+    s = gstep - warm  # scheduler steps taken before this iteration
+    return eta_min + (lr_warm - eta_min) * (1 + math.cos(math.pi * s / t_max)) / 2
+
+
 class ConfigTrainVAE:
     """The fields of the reference ConfigTrainVAE / BaseConfigTrain the step reads
     (main/config_vae.py:267-330, base/config_base.py:66-110)."""
@@ -80,7 +102,8 @@ class TrainerVAE:
         if self.device.type != 'cuda':
             raise RuntimeError("TrainerVAE needs the model on a CUDA device (no CPU path)")
         self.pg = process_group
-        self.world, self.rank = dp.world_info(process_group)
+        # dp_mode='off': a single-GPU trainer inside a distributed process (reference runs of the exchange checks)
+        self.world, self.rank = (1, 0) if dp_mode == 'off' else dp.world_info(process_group)
         self.n_iters = cfg.epochs * n_batches_per_epoch
         self.betas = beta_anneal_linear(self.n_iters, cfg.kl_beta, cfg.kl_anneal_portion, cfg.kl_const_portion,
                                         cfg.kl_beta_min)  # main/train_vae.py:27-34
@@ -99,17 +122,25 @@ class TrainerVAE:
         # (it has no gradient clipping: the norm of the summed gradient would need a second pass)
         self.peer = None
         self._peer_token = 0
-        assert dp_mode in ('auto', 'peer', 'nccl')
+        assert dp_mode in ('auto', 'peer', 'nccl', 'off')
         if self.world > 1 and dp_mode != 'nccl' and cfg.grad_clip is None and cfg.method == 'mc' and self.fused:
+            err = None
             try:
                 self.peer = dp.PeerExchange(self._flat_g_ext.numel(), self.device, process_group)
             except Exception as exc:  # no P2P / symmetric memory on this system
+                err = exc
+            # every rank must end up in the same mode (the peer kernels wait on one another): agree on the minimum
+            ok = torch.tensor([0 if err is not None else 1], device=self.device, dtype=torch.int32)
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=process_group)
+            if int(ok.item()) == 0:
+                self.peer = None
                 if dp_mode == 'peer':
-                    raise
+                    raise RuntimeError(f"peer-memory gradient exchange unavailable on at least one rank ({err!r})")
                 import warnings
-                warnings.warn(f"peer-memory gradient exchange unavailable ({exc!r}); using NCCL all-reduce")
+                warnings.warn(f"peer-memory gradient exchange unavailable on at least one rank ({err!r}); using NCCL all-reduce")
         elif dp_mode == 'peer' and self.world > 1:
             raise ValueError("dp_mode='peer' does not support grad_clip")
+        self.planes = False  # set by _setup_planes(): the TF32 low planes of the GEMM operands are kept by their producers
         self.r_max = torch.zeros(max(n_batches_per_epoch, 1), device=self.device)  # rate.max() of each step of the epoch
         self._gather_tab = None
         self._sink = None
@@ -173,15 +204,7 @@ class TrainerVAE:
     # -- schedules, main/train_vae.py:326-345, 391-400 -------------------------------------------
     def lr_at(self, gstep: int) -> float:
         cfg = self.cfg
-        progress = gstep / self.n_iters
-        if progress < cfg.warmup_portion:
-            return cfg.lr * progress / cfg.warmup_portion
-        if cfg.scheduler_type is None:
-            return cfg.lr
-        warm = math.ceil(cfg.warmup_portion * self.n_iters)  # first gstep with progress >= warmup_portion
-        t_max = self.n_iters - self.n_iters * cfg.warmup_portion  # base/train_base.py:286-287
-        s = gstep - warm  # scheduler steps taken before this iteration
-        return cfg.eta_min + (cfg.lr - cfg.eta_min) * (1 + math.cos(math.pi * s / t_max)) / 2
+        return lr_schedule(gstep, self.n_iters, cfg.lr, cfg.warmup_portion, cfg.scheduler_type, cfg.eta_min)
 
     def _timed(self, name, fn, *args):
         """Launch `fn(*args)`; when kernel_events is a dict, bracket it with CUDA events on the launch stream."""
@@ -419,6 +442,15 @@ class TrainerVAE:
         decode -> r2 / mse / kl per sample.  Results are gathered on the device and cross to the host once, not
         eight times per batch.  Returns (data, loss, etc) dicts of numpy arrays with the reference's keys."""
         m = self.model
+        was_training = m.training
+        m.eval()  # select_model() returns model.eval(), base/train_base.py:197-198: no dropout in the conv encoder's dense layers
+        try:
+            return self._validate(data, temp, batch_size, full_data)
+        finally:
+            m.train(was_training)
+
+    def _validate(self, data, temp, batch_size, full_data):
+        m = self.model
         bs = batch_size or self.cfg.batch_size
         acc = {k: [] for k in ('x', 'y', 'z', 'r2', 'mse', 'kl', 'kl_diag', 'log_dr', 'rate')}
         eps = torch.finfo(torch.float32).eps
@@ -523,7 +555,9 @@ class TrainerVAE:
         b = self._buffers(B)
         x = x_static if x_static is not None else torch.empty(B, D, device=self.device, dtype=torch.float32)
         loss = loss_out if loss_out is not None else torch.zeros(4, device=self.device, dtype=torch.float32)
-        rmax = self.r_max[:1]
+        if getattr(self, "_rmax_step", None) is None:
+            self._rmax_step = torch.zeros(1, device=self.device)  # the captured sampler's rate.max() word (moved per replay)
+        rmax = self._rmax_step
         off_dev = self._gstate.data_ptr() + 8
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream(device=self.device)
@@ -544,7 +578,8 @@ class TrainerVAE:
                     clip = b['norm']
                 _lib.check(lib.pvae_adamax_step_dev(_ptr(self.flat_p), _ptr(self._flat_g_ext), _ptr(self.exp_avg), _ptr(self.exp_inf),
                                                     n, _ptr(self._lr_sched), self._lr_sched.numel(), _ptr(self._gstate), cfg.betas[0],
-                                                    cfg.betas[1], cfg.eps, cfg.weight_decay, _ptr(clip), 4, s))
+                                                    cfg.betas[1], cfg.eps, cfg.weight_decay, _ptr(clip), 4, _ptr(rmax), _ptr(self.r_max),
+                                                    self.r_max.numel(), s))
         finally:
             self._stream_handle = pinned
         cur.wait_stream(side)
@@ -623,6 +658,7 @@ class TrainerVAE:
         """One epoch over a device-resident dataset (N, 1, H, W), like main/train_vae.py:317-459 with a
         batched index-select instead of the DataLoader; returns the epoch's mean nelbo (one host sync)."""
         B = self.cfg.batch_size
+        self.model.train()  # main/train_vae.py:318
         n_batches = data.shape[0] // B  # drop_last
         perm = torch.randperm(data.shape[0], device=data.device)
         self.r_max.zero_()

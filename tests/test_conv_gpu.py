@@ -506,3 +506,42 @@ def test_conv_public_api_paths():
     losses = tr.fit_host(host, first_gstep=4)
     torch.cuda.synchronize()
     assert losses.shape == (6, 3) and torch.isfinite(losses).all()
+
+
+def test_validate_runs_the_conv_encoder_in_eval_mode():
+    """the reference evaluates model.eval() (base/train_base.py:197-198).  validate() on a conv+b|lin model
+    that is in train mode must not apply the ResDenseLayer dropout: two passes agree bit for bit (same Philox state),
+    equal the pass of a model put in eval mode by hand, leave the training flag alone, and differ from a pass that
+    really drops activations."""
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE, default_configs
+    cfg_vae, _ = default_configs("CIFAR16", "poisson", "conv+b|lin")
+    model = PoissonVAE(ConfigPoisVAE(seed=1, **cfg_vae)).cuda()
+    with torch.no_grad():
+        model.log_rate.add_(3.0)
+    model.update_n(20.0)
+    tr = TrainerVAE(model, ConfigTrainVAE(batch_size=32, epochs=1, grad_clip=None))
+    data = torch.randn(64, 1, 16, 16, generator=torch.Generator().manual_seed(5)).cuda()
+    gen = torch.cuda.default_generators[0]
+
+    def run(fn):
+        torch.cuda.manual_seed(21)
+        out = fn()
+        return out, gen.get_offset()
+
+    model.train()
+    (d1, l1, e1), off1 = run(lambda: tr.validate(data))
+    assert model.training  # restored
+    (d2, l2, e2), off2 = run(lambda: tr.validate(data))
+    model.eval()
+    (d3, l3, e3), off3 = run(lambda: tr.validate(data))
+    for a, b in ((d1, d2), (d1, d3)):
+        assert np.array_equal(a['z'], b['z'])
+    assert np.array_equal(e1['log_dr'], e2['log_dr']) and np.array_equal(e1['log_dr'], e3['log_dr'])
+    assert np.array_equal(l1['mse'], l3['mse']) and off1 == off2 == off3  # no dropout draws consumed
+    # a pass with dropout really on moves log_dr
+    model.train()
+    torch.cuda.manual_seed(21)
+    with torch.no_grad():
+        _, log_dr_drop = model.infer(data[:32])
+    assert not np.array_equal(log_dr_drop.cpu().numpy(), e1['log_dr'][:32])

@@ -106,3 +106,15 @@ def test_indicator_grads_numeric():
         ana = po.indicator_grad(l, kind)
         mask = (np.abs(np.abs(l) - 1) > 1e-3)  # kinks of the finite-support indicators
         assert np.max(np.abs(num - ana)[mask]) < 1e-6, kind
+
+
+def test_lr_schedule_matches_reference_optimizer(golden_dir):
+    """trainer.lr_schedule vs the reference Adamax under torch's CosineAnnealingLR driven like the reference loop
+    (oracle/make_golden.py:gen_lr): warm-up, the hand-over step and the recursive cosine."""
+    from poissonvae_b200.trainer import lr_schedule
+    g = np.load(os.path.join(golden_dir, "lr_schedule.npz"))
+    for tag in "abcd":
+        lr, n_iters, portion, eta_min = g[f"cfg_{tag}"]
+        want = g[f"lr_{tag}"]
+        got = np.array([lr_schedule(i, int(n_iters), lr, portion, 'cosine', eta_min) for i in range(int(n_iters))])
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=0, err_msg=tag)

@@ -233,3 +233,34 @@ def test_fused_update_is_bit_identical(bias):
     for other in (False, "three kernels"):
         for a, b in zip(out[True], out[other]):
             assert torch.equal(a, b)
+
+
+def test_graph_replay_fills_the_same_r_max_slots_and_n_exp():
+    """a replayed graph must leave every step's rate.max() in that step's slot of the epoch ring (the
+    eager path writes slot gstep % n directly), so that iteration()'s mean of the per-step maxima - and the n_exp
+    update_n derives from it (main/train_vae.py:388, 456-457) - do not depend on the graph switch."""
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
+    data = torch.randn(6 * 64, 1, 16, 16, generator=torch.Generator().manual_seed(3)).cuda()
+    out = {}
+    for mode in (True, False):
+        model = PoissonVAE(ConfigPoisVAE(n_latents=128, prior_clamp=-4, seed=3)).cuda()
+        with torch.no_grad():
+            model.log_rate.add_(5.0)
+        tr = TrainerVAE(model, ConfigTrainVAE(lr=0.02, epochs=4, batch_size=64, temp_anneal_portion=0.0, temp_stop=0.5,
+                                              kl_anneal_portion=0.0, kl_const_portion=0.0, grad_clip=None, warmup_portion=0.0),
+                        n_batches_per_epoch=6)
+        tr.graph = mode
+        torch.manual_seed(11)  # iteration() draws its permutation from the global generators
+        torch.cuda.manual_seed(11)
+        n_exps, rings = [], []
+        for epoch in range(2):
+            tr.iteration(data, epoch)
+            rings.append(tr.r_max.clone())
+            n_exps.append(int(model.n_exp))
+        if mode:
+            assert len(tr._graphs) >= 1
+        out[mode] = (n_exps, torch.stack(rings))
+    assert out[True][0] == out[False][0], out
+    assert (out[True][1] > 0).all()  # every slot of the ring was written, none holds a running maximum of the epoch
+    assert torch.equal(out[True][1], out[False][1])

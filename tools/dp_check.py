@@ -41,7 +41,7 @@ def run(world, rank, steps, Bg, K, dp_mode='auto', archi='lin|lin', dataset='vH1
             torch.cuda._sleep(3_000_000)  # ~1.5 ms: ranks reach the exchange at very different times, alternately
         losses.append(tr.train_step(x, i, philox=(77, 4 * i)).clone())
     torch.cuda.synchronize()
-    return tr.flat_p.cpu(), torch.stack(losses).cpu()
+    return tr.flat_p.cpu(), torch.stack(losses).cpu(), tr.peer is not None
 
 
 def main():
@@ -58,7 +58,7 @@ def main():
     a = ap.parse_args()
     if a.mode == "single":
         torch.cuda.set_device(0)
-        p, l = run(1, 0, a.steps, a.batch, a.latents, a.dp_mode, a.archi, a.dataset)
+        p, l, _ = run(1, 0, a.steps, a.batch, a.latents, a.dp_mode, a.archi, a.dataset)
         torch.save({"p": p, "l": l}, a.out)
         print("single-GPU reference saved:", l[:, 0].tolist())
         return
@@ -66,7 +66,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    p, l = run(world, rank, a.steps, a.batch, a.latents, a.dp_mode, a.archi, a.dataset)
+    p, l, _ = run(world, rank, a.steps, a.batch, a.latents, a.dp_mode, a.archi, a.dataset)
     ref = torch.load(a.ref)
     dp_err = ((p - ref["p"]).abs().max() / ref["p"].abs().max()).item()
     l_err = ((l - ref["l"]).abs() / ref["l"].abs()).max().item()
