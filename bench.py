@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--no_overlap", action="store_true", help="keep the whole step on one stream (A/B)")
     ap.add_argument("--tf32", action="store_true", help="single-pass TF32 GEMMs instead of 3xTF32 (A/B)")
     ap.add_argument("--dec_splits", type=int, default=-1, help="K-splits of the decoder GEMM (A/B; default: the library's choice)")
+    ap.add_argument("--no_planes", action="store_true", help="GEMMs split their operands per stage in shared memory instead of "
+                                                              "loading the producers' TF32 low planes (A/B, same bits)")
     ap.add_argument("--no_fuse_update", action="store_true", help="keep the stand-alone gradient reductions + Adamax (A/B)")
     ap.add_argument("--graph", default="off", choices=["auto", "on", "off"],
                     help="CUDA-graph replay of the fused step (1 GPU; A/B - measured slower than the eager launches with "
@@ -85,7 +87,8 @@ def workload(args, world=None):
                         f"temp={args.temp:g} fp32, fwd+loss+bwd+Adamax, exit={args.exit}",
             "batch_per_gpu": args.batch, "n_latents": args.latents, "n_exp": args.n_exp, "temp": args.temp, "beta": args.beta,
             "input": "16x16 z-scored N(0,1) patches, seed 1234; weights N(0,0.05^2), log_rate U(-6,-4), cfg.seed 0",
-            "gemm": "tf32 single pass" if getattr(args, "tf32", False) else "3xTF32 (fp32-grade, tcgen05)",
+            "gemm": "tf32 single pass" if getattr(args, "tf32", False) else
+                    "3xTF32 (fp32-grade, tcgen05), operand low planes written by the producers (x: once at upload)",
             "schedule": "reference vH16 lr warm-up (lr .005, 1 % of 78000 iterations), beta and temp pinned",
             "graph": getattr(args, "graph", "off"),
             "l2": "inputs rotate over 64 distinct batches (>= 268 MB > 126 MB L2)",
@@ -318,6 +321,7 @@ def run_ours(args):
     tr = TrainerVAE(model, cfg, n_batches_per_epoch=26, dp_mode=args.dp)
     tr.graph = {"auto": "auto", "on": True, "off": False}[args.graph]
     tr.fuse_update = not args.no_fuse_update
+    tr.use_planes = not args.no_planes
     if args.dec_splits >= 0:
         tr.lib.pvae_set_dec_splits(args.dec_splits)
 
@@ -325,6 +329,10 @@ def run_ours(args):
     NB = 64 if B * 256 * 4 * 64 <= (1 << 30) else 32
     host = synthetic_patches(NB * B, 1234 + rank).view(NB, B, 256).pin_memory()
     data = host.to(dev)
+    # the resident batches' TF32 low planes, split once at upload time (they are constant data): the encoder GEMM and the
+    # encoder wgrad load them by TMA next to x.  The end-to-end pass splits every uploaded chunk inside its timed region.
+    data_lo = tr.split_planes(data) if tr.planes else None
+    xlo = (lambda j: data_lo[j]) if data_lo is not None else (lambda j: None)
 
     def barrier():
         if world > 1:
@@ -333,7 +341,7 @@ def run_ours(args):
 
     # ---- device-resident timing ---------------------------------------------------------------
     for i in range(W):
-        tr.train_step(data[i % NB], i)
+        tr.train_step(data[i % NB], i, x_lo=xlo(i % NB))
     barrier()
     # every pass below (device-resident regions, instrumented, end-to-end) trains the same K steps from this state: the
     # sampler's work depends on the rates, so the passes must not see different stages of training
@@ -357,7 +365,7 @@ def run_ours(args):
         launches0 = tr.lib.pvae_launch_count()
         e0.record()
         for i in range(K_steps):
-            tr.train_step(data[(W + i) % NB], W + i)
+            tr.train_step(data[(W + i) % NB], W + i, x_lo=xlo((W + i) % NB))
         e1.record()
         launches = tr.lib.pvae_launch_count() - launches0  # counted by the library itself, every launch of the region
         barrier()
@@ -373,7 +381,7 @@ def run_ours(args):
     restore()
     tr.kernel_events = {}
     for i in range(K_steps):
-        tr.train_step(data[(W + i) % NB], W + i)
+        tr.train_step(data[(W + i) % NB], W + i, x_lo=xlo((W + i) % NB))
     barrier()
     ktimes = tr.kernel_times_us()
     tr.kernel_events = None

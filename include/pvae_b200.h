@@ -130,6 +130,13 @@ int pvae_kl_bwd(const float* log_dr, const float* log_r, const float* g_kl, floa
  * ranges (one CTA each) whose partial tiles are summed in a fixed order; splitk_ws then needs
  * pvae_gemm_ws_floats(M, N, splits) floats. */
 int64_t pvae_gemm_ws_floats(int64_t M, int64_t N, int splits);
+/* The 3xTF32 product with the operands' low parts supplied by the caller instead of computed per stage in shared memory:
+ * A_lo / B_lo have the shape and layout of A / B and hold x - trunc_tf32(x) (pvae_tf32_lo, or written by the kernel that
+ * produced the operand).  The main loop is then pure TMA -> tcgen05.mma; same MMAs on the same bits as precise = 1, hence
+ * bit-identical results.  pvae_tf32_lo: lo[i] = x[i] - trunc_tf32(x[i]) (exact), n a multiple of 4. */
+int pvae_gemm_tf32_planes(const float* A, const float* A_lo, const float* B, const float* B_lo, float* C, int64_t M, int64_t N, int64_t Kd,
+                          int a_kmajor, int b_kmajor, int splits, float* splitk_ws, void* stream);
+int pvae_tf32_lo(const float* x, float* lo, int64_t n, void* stream);
 /* Tuning knob (process-wide): 0 = automatic tile choice, 1 = 128-wide tiles with one CTA per SM,
  * 2 = 64-wide tiles with two co-resident CTAs per SM. */
 int pvae_set_gemm_variant(int v);
@@ -251,6 +258,56 @@ int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, flo
                           int64_t B, int64_t B_global, int64_t row_offset, int64_t K, int64_t D, int has_bias, int n_exp,
                           float temp, float beta, int indicator, int exc_only, float exit_logit, int precise,
                           uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* const* events, void* stream);
+/* The same step driven by a descriptor the caller keeps from step to step (only x, the schedule scalars and the Philox
+ * offset change), with the options the positional entry points above do not carry:
+ *   params_lo  the parameters' TF32 low plane (flat, same layout as params; pvae_tf32_lo once, then kept up to date by the
+ *              optimiser kernels of this call).  Non-NULL switches the step's GEMMs to operand planes (pvae_gemm_tf32_planes):
+ *              the sampler, the residual kernel and the sampler backward also write the low planes of z, g_y and g_h.
+ *   x_lo       low plane of x (pvae_tf32_lo at upload time), or NULL: computed by the step into ws.
+ *   update     0: gradients only, reduced into grads (data parallel over NCCL: the caller all-reduces, then pvae_adamax_step);
+ *              1: Adamax fused (pvae_lin_step_train; single GPU: B_global == B);
+ *              2: data parallel over NVLink peer memory, exchange + Adamax fused into the step (fields at the end).
+ *   state / lr_sched / n_sched / philox_increment / rmax_ring / ring_n (update = 1): step-dependent scalars on the device
+ *              for CUDA-graph replay, see pvae_adamax_step_dev; rate_max is then the fixed word moved to the ring. */
+typedef struct pvae_lin_step_desc {
+  int64_t B, B_global, row_offset, K, D;
+  int has_bias, n_exp, indicator, exc_only, precise;
+  float exit_logit, temp, beta;
+  const float* x;
+  const float* x_lo;
+  float* params;
+  float* params_lo;
+  float* grads;
+  float* ws;
+  float* loss3;
+  float* rate_max;
+  uint64_t seed, offset;
+  const uint64_t* offset_dev;
+  void* const* events;
+  int update;
+  int step;
+  float* exp_avg;
+  float* exp_inf;
+  float lr, beta1, beta2, eps, weight_decay;
+  const float* lr_sched;
+  int n_sched;
+  int ring_n;
+  int* state;
+  uint64_t philox_increment;
+  float* rmax_ring;
+  /* update = 2: data parallel, the gradient sum over NVLink peer memory fused with Adamax (see pvae_allreduce_adamax) in
+   * two buckets - W_dec's gradient and the loss statistics are exchanged on the side stream under the rest of the
+   * backward, only log_r / W_enc / b_enc stay on the critical path.  grads must be this rank's symmetric buffer of this
+   * step's parity (n + 4 floats; = peer_grads[rank]); loss3 receives the statistics summed over the ranks; flag arrays
+   * need 64 words (bucket b uses words [16 b, 16 b + world), word 63 reports a timed-out wait). */
+  int world, rank;
+  uint32_t token;
+  const void* const* peer_grads;
+  void* const* peer_flags;
+} pvae_lin_step_desc;
+/* sizeof(pvae_lin_step_desc), for bindings that mirror the struct */
+int64_t pvae_lin_step_desc_size(void);
+int pvae_lin_step(const pvae_lin_step_desc* desc, void* stream);
 
 /* ---- conv encoder / decoder ----------------------------------------------
  * Activations are NHWC fp32.  Replaces Conv2D.forward base/common.py:313-323 (F.conv2d on the weight-normalised

@@ -67,6 +67,21 @@ class Cell(C.Structure):
                                            "g_se_b1", "g_se_w2", "g_se_b2", "g_skip_w", "g_skip_ln", "g_skip_b")])
 
 
+class LinStepDesc(C.Structure):
+    """pvae_lin_step_desc of include/pvae_b200.h"""
+    _fields_ = [("B", C.c_int64), ("B_global", C.c_int64), ("row_offset", C.c_int64), ("K", C.c_int64), ("D", C.c_int64),
+                ("has_bias", C.c_int), ("n_exp", C.c_int), ("indicator", C.c_int), ("exc_only", C.c_int), ("precise", C.c_int),
+                ("exit_logit", C.c_float), ("temp", C.c_float), ("beta", C.c_float),
+                ("x", C.c_void_p), ("x_lo", C.c_void_p), ("params", C.c_void_p), ("params_lo", C.c_void_p), ("grads", C.c_void_p),
+                ("ws", C.c_void_p), ("loss3", C.c_void_p), ("rate_max", C.c_void_p),
+                ("seed", C.c_uint64), ("offset", C.c_uint64), ("offset_dev", C.c_void_p), ("events", C.c_void_p),
+                ("update", C.c_int), ("step", C.c_int), ("exp_avg", C.c_void_p), ("exp_inf", C.c_void_p),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("lr_sched", C.c_void_p), ("n_sched", C.c_int), ("ring_n", C.c_int), ("state", C.c_void_p),
+                ("philox_increment", C.c_uint64), ("rmax_ring", C.c_void_p),
+                ("world", C.c_int), ("rank", C.c_int), ("token", C.c_uint32), ("peer_grads", C.c_void_p), ("peer_flags", C.c_void_p)]
+
+
 _SIGNATURES = {
     "pvae_version": (C.c_int, []),
     "pvae_last_error": (C.c_char_p, []),
@@ -99,6 +114,10 @@ _SIGNATURES = {
     "pvae_allreduce_adamax": (_i, [_p, _p, _p, _i64, _i64, _p, _p, _i, _i, C.c_uint32, _p, _p, _f, _i, _f, _f, _f, _f, _p]),
     "pvae_lin_step_ws_floats": (_i64, [_i64, _i64, _i64]),
     "pvae_lin_step_ws_offsets": (_i, [_i64, _i64, _i64, _p]),
+    "pvae_lin_step": (_i, [_p, _p]),
+    "pvae_lin_step_desc_size": (_i64, []),
+    "pvae_gemm_tf32_planes": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _i, _i, _p, _p]),
+    "pvae_tf32_lo": (_i, [_p, _p, _i64, _p]),
     "pvae_set_step_overlap": (_i, [_i]),
     "pvae_lin_step_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i,
                                    _u64, _u64, _p, _p, _p]),

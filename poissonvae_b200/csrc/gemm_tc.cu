@@ -45,11 +45,16 @@ struct GemmParams {
   // G = g_scale * (y - X) and row_part[m, n_tile] = sum over the tile's columns of (y - X)^2
   const float* X;
   float* G;
+  float* G_lo;  // optional: TF32 low plane of G for the GEMMs that consume it
   float* row_part;
   float g_scale;
 };
 
-template <int BN, bool SPLIT, int STAGES>
+// SPLIT: 0 = single-pass TF32; 1 = 3xTF32, the low parts computed in the kernel by the epilogue warps (operands as they
+// are in HBM); 2 = 3xTF32, the low parts arrive as their own planes by TMA (written once by whoever produced the operand:
+// sampler / residual / Adamax epilogues), so the main loop is pure TMA -> tcgen05.mma.  Modes 1 and 2 issue the same MMAs
+// in the same order on the same bits: bit-identical results.
+template <int BN, int SPLIT, int STAGES>
 struct GemmCfg {
   static constexpr uint32_t kABytes = kBM * kBK * 4;  // 16 KB
   static constexpr uint32_t kBBytes = BN * kBK * 4;
@@ -60,9 +65,10 @@ struct GemmCfg {
   static constexpr int kCtasPerSm = kSmem <= 110 * 1024 ? 2 : 1;
 };
 
-template <int BN, bool SPLIT, int STAGES>
+template <int BN, int SPLIT, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, GemmCfg<BN, SPLIT, STAGES>::kCtasPerSm)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const __grid_constant__ CUtensorMap tma_a_lo, const __grid_constant__ CUtensorMap tma_b_lo, const GemmParams p) {
   using Cfg = GemmCfg<BN, SPLIT, STAGES>;
   constexpr uint32_t kABytes = Cfg::kABytes, kTileBytes = Cfg::kTileBytes, kStageBytes = Cfg::kStageBytes;
   constexpr int kStages = Cfg::kStages;
@@ -83,6 +89,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    if (SPLIT == 2) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a_lo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b_lo)) : "memory");
+    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -115,19 +125,26 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         mbar_wait(&empty_bar[s], (round & 1) ^ 1);
         uint8_t* sa = smem + s * kStageBytes;
         uint8_t* sb = sa + kABytes;
-        mbar_expect_tx(&full_bar[s], kTileBytes);
+        mbar_expect_tx(&full_bar[s], SPLIT == 2 ? 2 * kTileBytes : kTileBytes);
         const int k0 = k_begin + kb * kBK;
-        if (p.a_kmajor) {
-          tma_load_2d(&tma_a, &full_bar[s], sa, k0, m0);  // box {32 k, 128 rows}
-        } else {
 #pragma unroll
-          for (int i = 0; i < kBM / 32; ++i) tma_load_2d(&tma_a, &full_bar[s], sa + i * 4096, m0 + 32 * i, k0);  // {32 m, 32 k}
-        }
-        if (p.b_kmajor) {
-          tma_load_2d(&tma_b, &full_bar[s], sb, k0, n0);  // box {32 k, BN rows}
-        } else {
+        for (int plane = 0; plane < (SPLIT == 2 ? 2 : 1); ++plane) {  // plane 1: the TF32 low parts, kTileBytes above
+          const CUtensorMap* ma = plane ? &tma_a_lo : &tma_a;
+          const CUtensorMap* mb = plane ? &tma_b_lo : &tma_b;
+          uint8_t* da = sa + plane * kTileBytes;
+          uint8_t* db = sb + plane * kTileBytes;
+          if (p.a_kmajor) {
+            tma_load_2d(ma, &full_bar[s], da, k0, m0);  // box {32 k, 128 rows}
+          } else {
 #pragma unroll
-          for (int i = 0; i < BN / 32; ++i) tma_load_2d(&tma_b, &full_bar[s], sb + i * 4096, n0 + 32 * i, k0);
+            for (int i = 0; i < kBM / 32; ++i) tma_load_2d(ma, &full_bar[s], da + i * 4096, m0 + 32 * i, k0);  // {32 m, 32 k}
+          }
+          if (p.b_kmajor) {
+            tma_load_2d(mb, &full_bar[s], db, k0, n0);  // box {32 k, BN rows}
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 32; ++i) tma_load_2d(mb, &full_bar[s], db + i * 4096, n0 + 32 * i, k0);
+          }
         }
       }
     }
@@ -145,7 +162,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t round = kb / kStages;
-        mbar_wait(SPLIT ? &conv_bar[s] : &full_bar[s], round & 1);
+        mbar_wait(SPLIT == 1 ? &conv_bar[s] : &full_bar[s], round & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_u32(smem + s * kStageBytes), sb = sa + kABytes;
 #pragma unroll
@@ -165,7 +182,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       umma_commit(accum_bar);  // accumulator complete
     }
   } else {
-    if (SPLIT) {
+    if (SPLIT == 1) {
       // ===== operand splitter: lo = x - trunc_tf32(x) into the second plane =====
       const int ct = threadIdx.x - 64;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -258,8 +275,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           float sq = 0.f;
           if (mm < p.M && n < p.N) {
             const float4 r = make_float4(src[0] - xv[i].x, src[1] - xv[i].y, src[2] - xv[i].z, src[3] - xv[i].w);
-            stg4(p.G + static_cast<long long>(mm) * p.N + n,
-                 make_float4(p.g_scale * r.x, p.g_scale * r.y, p.g_scale * r.z, p.g_scale * r.w));
+            const float4 gv = make_float4(p.g_scale * r.x, p.g_scale * r.y, p.g_scale * r.z, p.g_scale * r.w);
+            stg4(p.G + static_cast<long long>(mm) * p.N + n, gv);
+            if (p.G_lo != nullptr) stg4(p.G_lo + static_cast<long long>(mm) * p.N + n, tf32_lo4f(gv));
             sq = (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
           }
           sq += __shfl_xor_sync(0xffffffffu, sq, 1);  // the 8 lanes that share a row
@@ -370,8 +388,9 @@ static int make_map(CUtensorMap* out, const float* base, long long rows, long lo
   return make_tensor_map(out, base, 2, dims, strides, box, estr, atom32 ? 1 : 0);
 }
 
-template <int BN, bool SPLIT, int STAGES>
-static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int splits, cudaStream_t s) {
+template <int BN, int SPLIT, int STAGES>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mal, const CUtensorMap& mbl, const GemmParams& p,
+                       int splits, cudaStream_t s) {
   constexpr int smem = GemmCfg<BN, SPLIT, STAGES>::kSmem;
   static bool configured = false;
   if (!configured) {
@@ -381,7 +400,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmP
     configured = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, splits);
-  return cuda_ok("gemm_tf32_kernel", launch_pdl(gemm_tf32_kernel<BN, SPLIT, STAGES>, grid, dim3(kGemmThreads), smem, s, ma, mb, p));
+  return cuda_ok("gemm_tf32_kernel", launch_pdl(gemm_tf32_kernel<BN, SPLIT, STAGES>, grid, dim3(kGemmThreads), smem, s, ma, mb, mal, mbl, p));
 }
 
 int launch_splitk_reduce(const float* ws, float* C, long long n, int splits, cudaStream_t s) {
@@ -412,16 +431,20 @@ extern "C" int pvae_set_gemm_variant(int v) {
   return PVAE_OK;
 }
 
-static int gemm_impl(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t Kd, int a_kmajor, int b_kmajor,
-                     int precise, int splits, float* splitk_ws, const float* X, float* G, float* row_part, float g_scale,
-                     int force_bn, void* stream) {
+namespace pvae {
+// A_lo / B_lo: the operands' TF32 low planes (x - trunc_tf32(x), same shape and layout as A / B), or both NULL: then the
+// kernel computes them itself (precise) - the results are the same bits either way.
+int gemm_impl(const float* A, const float* A_lo, const float* B, const float* B_lo, float* C, int64_t M, int64_t N, int64_t Kd, int a_kmajor,
+              int b_kmajor, int precise, int splits, float* splitk_ws, const float* X, float* G, float* G_lo, float* row_part,
+              float g_scale, int force_bn, void* stream) {
   if (M <= 0 || N <= 0 || Kd <= 0) return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)Kd);
   if (M % 4 || N % 4 || Kd % 4)
     return fail(PVAE_ERR_UNSUPPORTED, "pvae_gemm_tf32: M=%lld N=%lld K=%lld must be multiples of 4 (16-byte TMA strides)",
                 (long long)M, (long long)N, (long long)Kd);
   if (!A || !B || (!C && !X && !(splits > 1 && splitk_ws))) return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: null pointer");
-  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) |
-       reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(G)) & 15)
+  if ((A_lo == nullptr) != (B_lo == nullptr)) return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: low planes must be given for both operands or none");
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(A_lo) |
+       reinterpret_cast<uintptr_t>(B_lo) | reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(G_lo)) & 15)
     return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32: pointers must be 16-byte aligned");
   if (splits < 1) splits = 1;
   const long long kblocks = (Kd + kBK - 1) / kBK;
@@ -431,30 +454,38 @@ static int gemm_impl(const float* A, const float* B, float* C, int64_t M, int64_
     const long long per = (kblocks + splits - 1) / splits;
     splits = static_cast<int>((kblocks + per - 1) / per);
   }
+  const bool planes = precise && A_lo != nullptr;
   // 128-wide tiles unless that leaves most of the 148 SMs without a CTA
   int BN = (N <= 64 || ((N + 127) / 128) * ((M + kBM - 1) / kBM) * splits < 96) ? 64 : 128;
   const bool narrow = g_gemm_variant == 2;  // measured slower than wide tiles on these shapes; kept as a knob
   if (narrow) BN = 64;
   if (force_bn) BN = force_bn;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mal, mbl;
   // K-major operand: (rows, Kd) row-major, box {32 k, rows_per_tile}; MN-major: (Kd, rows) row-major, box {32 rows, 32 k}
   if (int rc = a_kmajor ? make_map(&ma, A, M, Kd, kBK, kBM) : make_map(&ma, A, Kd, M, 32, kBK, true)) return rc;
   if (int rc = b_kmajor ? make_map(&mb, B, N, Kd, kBK, BN) : make_map(&mb, B, Kd, N, 32, kBK, true)) return rc;
+  mal = ma, mbl = mb;
+  if (planes) {
+    if (int rc = a_kmajor ? make_map(&mal, A_lo, M, Kd, kBK, kBM) : make_map(&mal, A_lo, Kd, M, 32, kBK, true)) return rc;
+    if (int rc = b_kmajor ? make_map(&mbl, B_lo, N, Kd, kBK, BN) : make_map(&mbl, B_lo, Kd, N, 32, kBK, true)) return rc;
+  }
   GemmParams p;
   p.C = splits > 1 ? splitk_ws : C;
   p.M = static_cast<int>(M), p.N = static_cast<int>(N), p.Kd = static_cast<int>(Kd);
   p.k_per_split = static_cast<int>(((kblocks + splits - 1) / splits) * kBK);
   p.a_kmajor = a_kmajor, p.b_kmajor = b_kmajor;
   p.split_stride = splits > 1 ? M * N : 0;
-  p.X = X, p.G = G, p.row_part = row_part, p.g_scale = g_scale;
+  p.X = X, p.G = G, p.G_lo = G_lo, p.row_part = row_part, p.g_scale = g_scale;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rc;
-  if (narrow) {  // 2 CTAs per SM: one CTA's TMA latency hides behind the other's split + MMA work
-    rc = precise ? launch_gemm<64, true, 2>(ma, mb, p, splits, s) : launch_gemm<64, false, 4>(ma, mb, p, splits, s);
+  if (planes) {
+    rc = BN == 64 ? launch_gemm<64, 2, 4>(ma, mb, mal, mbl, p, splits, s) : launch_gemm<128, 2, 3>(ma, mb, mal, mbl, p, splits, s);
+  } else if (narrow) {  // 2 CTAs per SM: one CTA's TMA latency hides behind the other's split + MMA work
+    rc = precise ? launch_gemm<64, 1, 2>(ma, mb, mal, mbl, p, splits, s) : launch_gemm<64, 0, 4>(ma, mb, mal, mbl, p, splits, s);
   } else if (precise) {
-    rc = BN == 64 ? launch_gemm<64, true, 4>(ma, mb, p, splits, s) : launch_gemm<128, true, 3>(ma, mb, p, splits, s);
+    rc = BN == 64 ? launch_gemm<64, 1, 4>(ma, mb, mal, mbl, p, splits, s) : launch_gemm<128, 1, 3>(ma, mb, mal, mbl, p, splits, s);
   } else {
-    rc = BN == 64 ? launch_gemm<64, false, 6>(ma, mb, p, splits, s) : launch_gemm<128, false, 6>(ma, mb, p, splits, s);
+    rc = BN == 64 ? launch_gemm<64, 0, 6>(ma, mb, mal, mbl, p, splits, s) : launch_gemm<128, 0, 6>(ma, mb, mal, mbl, p, splits, s);
   }
   if (rc) return rc;
   if (splits > 1) {
@@ -463,10 +494,18 @@ static int gemm_impl(const float* A, const float* B, float* C, int64_t M, int64_
   }
   return PVAE_OK;
 }
+}  // namespace pvae
 
 extern "C" int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t Kd, int a_kmajor,
                               int b_kmajor, int precise, int splits, float* splitk_ws, void* stream) {
-  return gemm_impl(A, B, C, M, N, Kd, a_kmajor, b_kmajor, precise, splits, splitk_ws, nullptr, nullptr, nullptr, 0.f, 0, stream);
+  return gemm_impl(A, nullptr, B, nullptr, C, M, N, Kd, a_kmajor, b_kmajor, precise, splits, splitk_ws, nullptr, nullptr, nullptr, nullptr, 0.f,
+                   0, stream);
+}
+
+extern "C" int pvae_gemm_tf32_planes(const float* A, const float* A_lo, const float* B, const float* B_lo, float* C, int64_t M, int64_t N,
+                                     int64_t Kd, int a_kmajor, int b_kmajor, int splits, float* splitk_ws, void* stream) {
+  if (!A_lo || !B_lo) return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32_planes: null low plane");
+  return gemm_impl(A, A_lo, B, B_lo, C, M, N, Kd, a_kmajor, b_kmajor, 1, splits, splitk_ws, nullptr, nullptr, nullptr, nullptr, 0.f, 0, stream);
 }
 
 // 64-wide tiles: the decoder output is only D = 256 wide, so this keeps 4 * M / 128 CTAs in flight
@@ -475,5 +514,5 @@ extern "C" int64_t pvae_gemm_residual_parts(int64_t N) { return (N + 63) / 64; }
 extern "C" int pvae_gemm_tf32_residual(const float* A, const float* B, const float* X, float* G, float* row_part, int64_t M,
                                        int64_t N, int64_t Kd, float g_scale, int precise, void* stream) {
   if (!X || !G || !row_part) return fail(PVAE_ERR_INVALID, "pvae_gemm_tf32_residual: null pointer");
-  return gemm_impl(A, B, nullptr, M, N, Kd, 1, 1, precise, 1, nullptr, X, G, row_part, g_scale, 64, stream);
+  return gemm_impl(A, nullptr, B, nullptr, nullptr, M, N, Kd, 1, 1, precise, 1, nullptr, X, G, nullptr, row_part, g_scale, 64, stream);
 }

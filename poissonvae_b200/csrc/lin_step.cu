@@ -44,6 +44,7 @@ int g_fuse_reduce = 1;  // pvae_lin_step_fwd_bwd: reduce all gradient partials w
 
 struct Ws {
   float *h, *z, *dz, *y, *g_y, *g_z, *g_h, *recon, *klrow, *partials, *splitk, *splitk2, *ydec;
+  float *z_lo, *g_y_lo, *g_h_lo, *x_lo;  // TF32 low planes of the GEMM operands the step produces
   int64_t total;
 };
 
@@ -70,6 +71,7 @@ Ws carve(float* base, int64_t B, int64_t K, int64_t D) {
   w.splitk = take(s1);   // decoder wgrad (may run on the side stream, concurrently with ...)
   w.splitk2 = take(s2);  // ... the encoder wgrad
   w.ydec = take(8 * B * D);  // split-K partials of the decoder output (pvae_set_dec_splits, at most 8)
+  w.z_lo = take(B * K), w.g_y_lo = take(B * D), w.g_h_lo = take(B * K), w.x_lo = take(B * D);
   w.total = o;
   return w;
 }
@@ -96,56 +98,71 @@ extern "C" int pvae_lin_step_ws_offsets(int64_t B, int64_t K, int64_t D, int64_t
   return PVAE_OK;
 }
 
-namespace {
-struct Update {  // optimiser fused into the step (pvae_lin_step_train); p == nullptr: gradients only
-  bool fuse_reduce = false;  // gradients only, but all partials reduced by ONE kernel instead of three
-  float *p = nullptr, *exp_avg = nullptr, *exp_inf = nullptr;
-  float lr = 0.f, beta1 = 0.f, beta2 = 0.f, eps = 0.f, weight_decay = 0.f;
-  int step = 0;
-};
-}  // namespace
-
-static int lin_step_impl(const float* x, const float* params, float* grads, float* ws, float* loss3, float* rate_max, int64_t B,
-                         int64_t B_global, int64_t row_offset, int64_t K, int64_t D, int has_bias, int n_exp, float temp,
-                         float beta, int indicator, int exc_only, float exit_logit, int precise, uint64_t seed, uint64_t offset,
-                         const uint64_t* offset_dev, void* const* events, void* stream, const Update& up) {
+// What the optimiser part of a step does with the gradient partials.
+static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   using pvae::fail;
-  if (B <= 0 || B_global < B || K <= 0 || D <= 0) return fail(PVAE_ERR_INVALID, "pvae_lin_step_fwd_bwd: bad shape");
+  const int64_t B = d.B, B_global = d.B_global, K = d.K, D = d.D;
+  if (B <= 0 || B_global < B || K <= 0 || D <= 0) return fail(PVAE_ERR_INVALID, "pvae_lin_step: bad shape");
   if (B % 4 || K % 4 || D % 4)
-    return fail(PVAE_ERR_UNSUPPORTED, "pvae_lin_step_fwd_bwd: B=%lld K=%lld D=%lld must be multiples of 4", (long long)B,
-                (long long)K, (long long)D);
-  if (!x || !params || !grads || !ws || !loss3) return fail(PVAE_ERR_INVALID, "pvae_lin_step_fwd_bwd: null pointer");
-  if (!(temp > 0.f)) return fail(PVAE_ERR_INVALID, "pvae_lin_step_fwd_bwd: training needs temp > 0, got %g", temp);
+    return fail(PVAE_ERR_UNSUPPORTED, "pvae_lin_step: B=%lld K=%lld D=%lld must be multiples of 4", (long long)B, (long long)K, (long long)D);
+  if (!d.x || !d.params || !d.grads || !d.ws || !d.loss3) return fail(PVAE_ERR_INVALID, "pvae_lin_step: null pointer");
+  if (!(d.temp > 0.f)) return fail(PVAE_ERR_INVALID, "pvae_lin_step: training needs temp > 0, got %g", d.temp);
+  if (d.update < 0 || d.update > 2) return fail(PVAE_ERR_INVALID, "pvae_lin_step: update mode %d", d.update);
+  const bool dp_peer = d.update == 2;
+  if (dp_peer && (!d.exp_avg || !d.exp_inf || d.step < 1 || !d.peer_grads || !d.peer_flags || d.world < 2 || d.rank < 0 || d.rank >= d.world ||
+                  d.peer_grads[d.rank] != d.grads || d.state))
+    return fail(PVAE_ERR_INVALID, "pvae_lin_step: bad exchange argument (grads must be this rank's symmetric buffer)");
+  if (d.update == 1 && (!d.exp_avg || !d.exp_inf || (d.step < 1 && !d.state) || B_global != B))
+    return fail(PVAE_ERR_INVALID, "pvae_lin_step: bad optimiser argument (the fused update is single-GPU: B_global == B)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const Ws w = carve(ws, B, K, D);
-  const float *log_r = params, *w_enc = params + K, *w_dec = w_enc + K * D;
+  const Ws w = carve(d.ws, B, K, D);
+  const int has_bias = d.has_bias, precise = d.precise;
+  const float *log_r = d.params, *w_enc = d.params + K, *w_dec = w_enc + K * D;
   const float* b_enc = has_bias ? w_dec + D * K : nullptr;
-  float *g_log_r = grads, *g_w_enc = grads + K, *g_w_dec = g_w_enc + K * D;
+  float *g_log_r = d.grads, *g_w_enc = d.grads + K, *g_w_dec = g_w_enc + K * D;
   float* g_b_enc = has_bias ? g_w_dec + D * K : nullptr;
+  // Operand planes: when the caller keeps the parameters' TF32 low plane (params_lo, maintained by the optimiser kernels),
+  // every producer of a GEMM operand also writes that operand's low plane (z, g_y, g_h; x once per batch), and the GEMMs
+  // load hi and lo tiles by TMA instead of splitting each stage in shared memory.  Same MMAs on the same bits.
+  const bool planes = precise && d.params_lo != nullptr;
+  const float *w_enc_lo = planes ? d.params_lo + K : nullptr, *w_dec_lo = planes ? d.params_lo + K + K * D : nullptr;
+  float *z_lo = planes ? w.z_lo : nullptr, *g_y_lo = planes ? w.g_y_lo : nullptr, *g_h_lo = planes ? w.g_h_lo : nullptr;
+  const float* x_lo = planes ? d.x_lo : nullptr;
   auto mark = [&](int i) {
-    if (events && events[i]) cudaEventRecord(static_cast<cudaEvent_t>(events[i]), s);
+    if (d.events && d.events[i]) cudaEventRecord(static_cast<cudaEvent_t>(d.events[i]), s);
+  };
+  auto gemm = [&](const float* A, const float* A_lo, const float* Bm, const float* B_lo, float* C, int64_t M, int64_t N, int64_t Kd, int ak,
+                  int bk, int splits, float* sws, cudaStream_t st) {
+    return pvae::gemm_impl(A, planes ? A_lo : nullptr, Bm, planes ? B_lo : nullptr, C, M, N, Kd, ak, bk, precise, splits, sws, nullptr, nullptr,
+                           nullptr, nullptr, 0.f, 0, st);
   };
   int rc;
   // ---- forward
-  if ((rc = pvae_gemm_tf32(x, w_enc, w.h, B, K, D, 1, 1, precise, 1, nullptr, s))) return rc;
+  if (planes && x_lo == nullptr) {  // the caller did not keep x's low plane (pvae_tf32_lo at upload time): make it now
+    if ((rc = pvae_tf32_lo(d.x, w.x_lo, B * D, s))) return rc;
+    x_lo = w.x_lo;
+  }
+  if ((rc = gemm(d.x, x_lo, w_enc, w_enc_lo, w.h, B, K, D, 1, 1, 1, nullptr, s))) return rc;
   mark(0);
-  if ((rc = pvae_sampler_fwd(w.h, log_r, b_enc, w.z, nullptr, nullptr, nullptr, w.klrow, rate_max, w.dz, B, K, row_offset, n_exp,
-                             temp, indicator, exc_only, exit_logit, seed, offset, offset_dev, s)))
+  if ((rc = pvae::sampler_fwd_impl(w.h, log_r, b_enc, w.z, z_lo, nullptr, nullptr, nullptr, w.klrow, d.rate_max, w.dz, B, K, d.row_offset,
+                                   d.n_exp, d.temp, d.indicator, d.exc_only, d.exit_logit, d.seed, d.offset, d.offset_dev, s)))
     return rc;
   mark(1);
   // decoder GEMM with the residual fused into its epilogue: g_y and per-tile squared errors, y itself is never stored
   int recon_parts = static_cast<int>(pvae_gemm_residual_parts(D));
-  // automatic: the decoder's K loop (K / 32 blocks of ~1 us each in 3xTF32 mode) is the longest serial stretch of any GEMM
-  // of the step; when two K-halves of every 128 x 128 tile still fit one wave of CTAs, split it (measured at config 2:
-  // 115.0 -> 111.6 us per step; four splits: 116.9)
+  // automatic: the decoder's K loop (K / 32 blocks) is the longest serial stretch of any GEMM of the step; when two
+  // K-halves of every 128 x 128 tile still fit one wave of CTAs, split it (measured at config 2: 115.0 -> 111.6 us per
+  // step; four splits: 116.9)
   int want = g_dec_splits;
   if (want == 0) want = (K >= 512 && ((B + 127) / 128) * ((D + 127) / 128) * 2 <= 160) ? 2 : 1;
   const int dsp = want > 1 ? pvae_gemm_effective_splits(K, want) : 1;
+  const float g_scale = 2.0f / static_cast<float>(B_global);
   if (dsp > 1) {  // split-K partials (in the not-yet-used wgrad workspace) + one kernel that sums them into the residual
-    if ((rc = pvae_gemm_tf32(w.z, w_dec, nullptr, B, D, K, 1, 1, precise, dsp, w.ydec, s))) return rc;
-    if ((rc = pvae_recon_residual_parts(w.ydec, dsp, x, w.g_y, w.recon, B, D, 2.0f / static_cast<float>(B_global), s))) return rc;
+    if ((rc = gemm(w.z, z_lo, w_dec, w_dec_lo, nullptr, B, D, K, 1, 1, dsp, w.ydec, s))) return rc;
+    if ((rc = pvae::recon_parts_impl(w.ydec, dsp, d.x, w.g_y, g_y_lo, w.recon, B, D, g_scale, s))) return rc;
     recon_parts = 1;
-  } else if ((rc = pvae_gemm_tf32_residual(w.z, w_dec, x, w.g_y, w.recon, B, D, K, 2.0f / static_cast<float>(B_global), precise, s))) {
+  } else if ((rc = pvae::gemm_impl(w.z, z_lo, w_dec, w_dec_lo, nullptr, B, D, K, 1, 1, precise, 1, nullptr, d.x, w.g_y, g_y_lo, w.recon, g_scale,
+                                   64, s))) {
     return rc;
   }
   // ---- backward.  Off the critical path (decoder wgrad, loss assembly) goes to a side stream so that it fills
@@ -156,33 +173,93 @@ static int lin_step_impl(const float* x, const float* params, float* grads, floa
     if ((rc = pvae::cuda_ok("fork", cudaEventRecord(side->fork, s)))) return rc;
     if ((rc = pvae::cuda_ok("fork", cudaStreamWaitEvent(s2, side->fork, 0)))) return rc;
   }
-  if ((rc = pvae_loss_assemble(w.recon, w.klrow, loss3, B, beta, B_global, recon_parts, s2))) return rc;
+  const int64_t n = K + 2 * K * D + (has_bias ? K : 0);
+  // data parallel over peer memory: this rank's share of [loss, mse, kl] rides behind its gradients (floats n .. n + 3 of
+  // the symmetric buffer) and is summed over the ranks by the first exchange bucket into loss3
+  if ((rc = pvae_loss_assemble(w.recon, w.klrow, dp_peer ? d.grads + n : d.loss3, B, d.beta, B_global, recon_parts, s2))) return rc;
   // fused update: the split partials stay in the workspace (C = NULL) and are reduced inside the Adamax kernel
   const int sp_dec = wgrad_splits(D, K, B), sp_enc = wgrad_splits(K, D, B);
-  const bool fuse = (up.p != nullptr || up.fuse_reduce) && sp_dec > 1 && sp_enc > 1;
-  if ((rc = pvae_gemm_tf32(w.g_y, w.z, fuse ? nullptr : g_w_dec, D, K, B, 0, 0, precise, sp_dec, w.splitk, s2))) return rc;
-  if (side && (rc = pvae::cuda_ok("join", cudaEventRecord(side->join, s2)))) return rc;
-  if ((rc = pvae_gemm_tf32(w.g_y, w_dec, w.g_z, B, K, D, 1, 0, precise, 1, nullptr, s))) return rc;
-  mark(2);
-  if ((rc = pvae_sampler_bwd(w.h, log_r, b_enc, w.g_z, nullptr, w.dz, beta / static_cast<float>(B_global), w.g_h, g_log_r, g_b_enc,
-                             w.partials, fuse ? -1 : 0, B, K, row_offset, n_exp, temp, indicator, exc_only, exit_logit, seed, offset,
-                             offset_dev, s)))
-    return rc;
-  mark(3);
-  if ((rc = pvae_gemm_tf32(w.g_h, x, fuse ? nullptr : g_w_enc, K, D, B, 0, 0, precise, sp_enc, w.splitk2, s))) return rc;
-  if (side && (rc = pvae::cuda_ok("join", cudaStreamWaitEvent(s, side->join, 0)))) return rc;
-  if (up.p == nullptr && !fuse) return PVAE_OK;
-  const int64_t n = K + 2 * K * D + (has_bias ? K : 0);
-  if (!fuse)
-    return pvae_adamax_step(up.p, grads, up.exp_avg, up.exp_inf, n, up.lr, up.step, up.beta1, up.beta2, up.eps, up.weight_decay, nullptr, s);
+  const bool fuse = (d.update >= 1 || g_fuse_reduce) && sp_dec > 1 && sp_enc > 1;
+  if ((rc = gemm(w.g_y, g_y_lo, w.z, z_lo, fuse ? nullptr : g_w_dec, D, K, B, 0, 0, sp_dec, w.splitk, s2))) return rc;
   const int prow = static_cast<int>(pvae_sampler_bwd_partial_rows(B));
   pvae_grad_segment seg[4];
   seg[0] = pvae_grad_segment{0, K, w.partials, prow, 1, K};
   seg[1] = pvae_grad_segment{K, K * D, w.splitk2, pvae_gemm_effective_splits(B, sp_enc), 0, K * D};
   seg[2] = pvae_grad_segment{K + K * D, D * K, w.splitk, pvae_gemm_effective_splits(B, sp_dec), 0, D * K};
   if (has_bias) seg[3] = pvae_grad_segment{K + 2 * K * D, K, w.partials + pvae_sampler_bwd_bias_offset_rows(B) * K, prow, 1, K};
-  return pvae_adamax_from_partials(up.p, grads, up.exp_avg, up.exp_inf, seg, has_bias ? 4 : 3, up.lr, up.step, up.beta1, up.beta2, up.eps,
-                                   up.weight_decay, s);
+  pvae::AdamaxDev dev;
+  dev.lr_sched = d.lr_sched, dev.n_sched = d.n_sched, dev.state = d.state;
+  if (dp_peer) {
+    // Exchange bucket 0 = W_dec's gradient (+ the loss statistics), complete as soon as the decoder wgrad is: its sum over
+    // the ranks and its Adamax update run on the side stream UNDER the dgrad GEMM, the sampler backward and the encoder
+    // wgrad of the main stream.  Only bucket 1 (log_r, W_enc, b_enc) stays on the critical path.
+    if (fuse && (rc = pvae::adamax_from_partials_impl(nullptr, nullptr, d.grads, nullptr, nullptr, seg + 2, 1, 0.f, 1, 0.f, 0.f, 0.f, 0.f,
+                                                      pvae::AdamaxDev{}, s2)))
+      return rc;
+    const int64_t rs[1] = {K + K * D}, rl[1] = {D * K};
+    if ((rc = pvae::peer_exchange_impl(d.params, planes ? d.params_lo : nullptr, d.exp_avg, d.exp_inf, rs, rl, 1, n, d.peer_grads, d.peer_flags,
+                                       0, d.world, d.rank, d.token, d.loss3, nullptr, d.lr, d.step, d.beta1, d.beta2, d.eps, d.weight_decay,
+                                       s2)))
+      return rc;
+  }
+  if (side && (rc = pvae::cuda_ok("join", cudaEventRecord(side->join, s2)))) return rc;
+  if ((rc = gemm(w.g_y, g_y_lo, w_dec, w_dec_lo, w.g_z, B, K, D, 1, 0, 1, nullptr, s))) return rc;
+  mark(2);
+  if ((rc = pvae::sampler_bwd_impl(w.h, log_r, b_enc, w.g_z, nullptr, w.dz, d.beta / static_cast<float>(B_global), w.g_h, g_h_lo, g_log_r,
+                                   g_b_enc, w.partials, fuse ? -1 : 0, B, K, d.row_offset, d.n_exp, d.temp, d.indicator, d.exc_only,
+                                   d.exit_logit, d.seed, d.offset, d.offset_dev, s)))
+    return rc;
+  mark(3);
+  if ((rc = gemm(w.g_h, g_h_lo, d.x, x_lo, fuse ? nullptr : g_w_enc, K, D, B, 0, 0, sp_enc, w.splitk2, s))) return rc;
+  if (dp_peer) {  // bucket 1: everything but W_dec
+    if (fuse) {
+      pvae_grad_segment sb[3] = {seg[0], seg[1], seg[3]};
+      if ((rc = pvae::adamax_from_partials_impl(nullptr, nullptr, d.grads, nullptr, nullptr, sb, has_bias ? 3 : 2, 0.f, 1, 0.f, 0.f, 0.f, 0.f,
+                                                pvae::AdamaxDev{}, s)))
+        return rc;
+    }
+    const int64_t rs[2] = {0, K + 2 * K * D}, rl[2] = {K + K * D, K};
+    if ((rc = pvae::peer_exchange_impl(d.params, planes ? d.params_lo : nullptr, d.exp_avg, d.exp_inf, rs, rl, has_bias ? 2 : 1, -1,
+                                       d.peer_grads, d.peer_flags, 1, d.world, d.rank, d.token, nullptr, nullptr, d.lr, d.step, d.beta1,
+                                       d.beta2, d.eps, d.weight_decay, s)))
+      return rc;
+    if (side && (rc = pvae::cuda_ok("join", cudaStreamWaitEvent(s, side->join, 0)))) return rc;
+    return PVAE_OK;
+  }
+  if (side && (rc = pvae::cuda_ok("join", cudaStreamWaitEvent(s, side->join, 0)))) return rc;
+  if (d.update == 0 && !fuse) return PVAE_OK;
+  if (!fuse) {
+    if (d.state) return fail(PVAE_ERR_UNSUPPORTED, "pvae_lin_step: device-side counters need the fused gradient reduction");
+    return pvae::adamax_step_impl(d.params, planes ? d.params_lo : nullptr, d.grads, d.exp_avg, d.exp_inf, n, d.lr, d.step, d.beta1, d.beta2,
+                                  d.eps, d.weight_decay, nullptr, s);
+  }
+  const bool upd = d.update == 1;
+  if ((rc = pvae::adamax_from_partials_impl(upd ? d.params : nullptr, upd && planes ? d.params_lo : nullptr, d.grads, d.exp_avg, d.exp_inf, seg,
+                                            has_bias ? 4 : 3, d.lr, d.step, d.beta1, d.beta2, d.eps, d.weight_decay, dev, s)))
+    return rc;
+  if (upd && d.state)  // graph replay: advance the device-side step counter / Philox offset, move rate.max() to its slot
+    return pvae::advance_state(d.state, d.philox_increment, d.rate_max, d.rmax_ring, d.ring_n, s);
+  return PVAE_OK;
+}
+
+extern "C" int64_t pvae_lin_step_desc_size(void) { return static_cast<int64_t>(sizeof(pvae_lin_step_desc)); }
+
+extern "C" int pvae_lin_step(const pvae_lin_step_desc* d, void* stream) {
+  if (!d) return pvae::fail(PVAE_ERR_INVALID, "pvae_lin_step: null descriptor");
+  return lin_step_core(*d, stream);
+}
+
+static pvae_lin_step_desc make_desc(const float* x, float* params, float* grads, float* ws, float* loss3, float* rate_max, int64_t B,
+                                    int64_t B_global, int64_t row_offset, int64_t K, int64_t D, int has_bias, int n_exp, float temp,
+                                    float beta, int indicator, int exc_only, float exit_logit, int precise, uint64_t seed,
+                                    uint64_t offset, const uint64_t* offset_dev, void* const* events) {
+  pvae_lin_step_desc d = {};
+  d.B = B, d.B_global = B_global, d.row_offset = row_offset, d.K = K, d.D = D;
+  d.has_bias = has_bias, d.n_exp = n_exp, d.indicator = indicator, d.exc_only = exc_only, d.precise = precise;
+  d.exit_logit = exit_logit, d.temp = temp, d.beta = beta;
+  d.x = x, d.params = params, d.grads = grads, d.ws = ws, d.loss3 = loss3, d.rate_max = rate_max;
+  d.seed = seed, d.offset = offset, d.offset_dev = offset_dev, d.events = events;
+  return d;
 }
 
 extern "C" int pvae_lin_step_fwd_bwd(const float* x, const float* params, float* grads, float* ws, float* loss3,
@@ -190,10 +267,9 @@ extern "C" int pvae_lin_step_fwd_bwd(const float* x, const float* params, float*
                                      int has_bias, int n_exp, float temp, float beta, int indicator, int exc_only,
                                      float exit_logit, int precise, uint64_t seed, uint64_t offset,
                                      const uint64_t* offset_dev, void* const* events, void* stream) {
-  Update up;
-  up.fuse_reduce = g_fuse_reduce != 0;
-  return lin_step_impl(x, params, grads, ws, loss3, rate_max, B, B_global, row_offset, K, D, has_bias, n_exp, temp, beta, indicator,
-                       exc_only, exit_logit, precise, seed, offset, offset_dev, events, stream, up);
+  const pvae_lin_step_desc d = make_desc(x, const_cast<float*>(params), grads, ws, loss3, rate_max, B, B_global, row_offset, K, D, has_bias,
+                                         n_exp, temp, beta, indicator, exc_only, exit_logit, precise, seed, offset, offset_dev, events);
+  return lin_step_core(d, stream);
 }
 
 extern "C" int pvae_set_dec_splits(int n) {
@@ -213,9 +289,9 @@ extern "C" int pvae_lin_step_train(const float* x, float* params, float* grads, 
                                    uint64_t offset, const uint64_t* offset_dev, void* const* events, float lr, int step, float beta1,
                                    float beta2, float eps, float weight_decay, void* stream) {
   if (!params || !exp_avg || !exp_inf || step < 1) return pvae::fail(PVAE_ERR_INVALID, "pvae_lin_step_train: bad optimiser argument");
-  Update up;
-  up.p = params, up.exp_avg = exp_avg, up.exp_inf = exp_inf;
-  up.lr = lr, up.beta1 = beta1, up.beta2 = beta2, up.eps = eps, up.weight_decay = weight_decay, up.step = step;
-  return lin_step_impl(x, params, grads, ws, loss3, rate_max, B, B, 0, K, D, has_bias, n_exp, temp, beta, indicator, exc_only,
-                       exit_logit, precise, seed, offset, offset_dev, events, stream, up);
+  pvae_lin_step_desc d = make_desc(x, params, grads, ws, loss3, rate_max, B, B, 0, K, D, has_bias, n_exp, temp, beta, indicator, exc_only,
+                                   exit_logit, precise, seed, offset, offset_dev, events);
+  d.update = 1, d.exp_avg = exp_avg, d.exp_inf = exp_inf;
+  d.lr = lr, d.beta1 = beta1, d.beta2 = beta2, d.eps = eps, d.weight_decay = weight_decay, d.step = step;
+  return lin_step_core(d, stream);
 }

@@ -45,4 +45,40 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// sampler.cu: pvae_sampler_fwd / pvae_sampler_bwd with the optional TF32 low planes of z / g_h (what the GEMMs that
+// consume them load by TMA instead of splitting the operand in shared memory)
+int sampler_fwd_impl(const float* h, const float* log_r, const float* b_enc, float* z, float* z_lo, float* log_dr, float* rate, float* kl,
+                     float* kl_rowsum, float* rate_max, float* dz_acc, int64_t B, int64_t K, int64_t row_offset, int n_exp, float temp,
+                     int indicator, int exc_only, float exit_logit, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                     void* stream);
+int sampler_bwd_impl(const float* h, const float* log_r, const float* b_enc, const float* g_z, const float* g_log_dr, const float* dz_acc,
+                     float kl_scale, float* g_h, float* g_h_lo, float* g_log_r, float* g_b_enc, float* partial_ws, int accumulate,
+                     int64_t B, int64_t K, int64_t row_offset, int n_exp, float temp, int indicator, int exc_only, float exit_logit,
+                     uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream);
+// step.cu
+int recon_parts_impl(const float* y_parts, int n_parts, const float* x, float* g_y, float* g_y_lo, float* recon, int64_t B, int64_t D,
+                     float g_scale, void* stream);
+struct AdamaxDev {  // step-dependent scalars on the device (CUDA-graph replay): state[0] = steps taken so far
+  const float* lr_sched = nullptr;
+  int n_sched = 0;
+  const int* state = nullptr;
+};
+int adamax_from_partials_impl(float* p, float* p_lo, float* g_out, float* exp_avg, float* exp_inf, const pvae_grad_segment* segs,
+                              int n_segs, float lr, int step, float beta1, float beta2, float eps, float weight_decay, const AdamaxDev& dev,
+                              void* stream);
+int adamax_step_impl(float* p, float* p_lo, const float* g, float* exp_avg, float* exp_inf, int64_t n, float lr, int step, float beta1,
+                     float beta2, float eps, float weight_decay, const float* clip_coef, void* stream);
+int advance_state(int* state, uint64_t philox_increment, float* rmax_step, float* rmax_ring, int ring_n, void* stream);
+
+// peer_allreduce.cu: one bucket of the peer-memory gradient exchange fused with Adamax (see pvae_allreduce_adamax)
+int peer_exchange_impl(float* p, float* p_lo, float* exp_avg, float* exp_inf, const int64_t* range_start, const int64_t* range_len,
+                       int n_ranges, int64_t tail, const void* const* peer_grads, void* const* peer_flags, int bucket, int world, int rank,
+                       uint32_t token, float* tail_out, float* g_sum_out, float lr, int step, float beta1, float beta2, float eps,
+                       float weight_decay, void* stream);
+
+// gemm_tc.cu: the GEMM behind pvae_gemm_tf32 / _planes / _residual with every option (library-internal callers)
+int gemm_impl(const float* A, const float* A_lo, const float* B, const float* B_lo, float* C, int64_t M, int64_t N, int64_t Kd, int a_kmajor,
+              int b_kmajor, int precise, int splits, float* splitk_ws, const float* X, float* G, float* G_lo, float* row_part,
+              float g_scale, int force_bn, void* stream);
+
 }  // namespace pvae

@@ -48,6 +48,8 @@ struct SamplerParams {
   const float* dz_in;     // (B,K) kBwdSaved: sum_n f'(l_n) t_n written by the forward
   float* dz_out;          // (B,K) kFwdBoth
   float* z;
+  float* z_lo;            // (B,K) optional: z - trunc_tf32(z), the low plane the decoder / wgrad GEMMs load by TMA
+  float* g_h_lo;          // (B,K) optional, backward: the same for g_h (encoder wgrad)
   float* log_dr;
   float* rate;
   float* kl;
@@ -73,6 +75,14 @@ struct SamplerParams {
   const uint64_t* offset_dev;
   PhiloxKey ks;
 };
+
+// store a quad of z / g_h and, when the GEMMs want it, its TF32 low plane (x - trunc_tf32(x), exact)
+__device__ __forceinline__ void stg4_planes(float* hi, float* lo, long long off, const float4 v) {
+  stg4(hi + off, v);
+  if (lo != nullptr)
+    stg4(lo + off, make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
+                               v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u)));
+}
 
 // ---- one soft-threshold term -------------------------------------------------------------------
 template <int IND, bool GRAD>
@@ -267,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
           col_b[j] += gh[j];
         }
       }
-      stg4(p.g_h + base, make_float4(gh[0], gh[1], gh[2], gh[3]));
+      stg4_planes(p.g_h, p.g_h_lo, base, make_float4(gh[0], gh[1], gh[2], gh[3]));
     };
 
     // ---------------- phase A ----------------
@@ -327,6 +337,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
       const int Kq = static_cast<int>(p.K >> 2), k0q = static_cast<int>(k0 >> 2);
       const uint32_t quad0 = static_cast<uint32_t>(((p.row_offset + row0) * p.K) >> 2);
       float* const z0 = p.z + row0 * p.K;
+      float* const zlo0 = p.z_lo != nullptr ? p.z_lo + row0 * p.K : nullptr;
       float* const dz0 = MODE == kFwdBoth ? p.dz_out + row0 * p.K : nullptr;
       int cur = tid;  // this lane's pool entry: row cur / kThreads, column quad cur % kThreads
       bool has = cur < pool_n, live = false;
@@ -376,7 +387,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
           ++n;
           const float tmin = fminf(fminf(t[0], t[1]), fminf(t[2], t[3]));
           if (tmin > t_exit || (absorb > 0.f && tmin > 1.f && excess <= 0.f) || n >= p.n_exp) {  // chain complete
-            stg4(z0 + ebase, make_float4(acc[0], acc[1], acc[2], acc[3]));
+            stg4_planes(z0, zlo0, ebase, make_float4(acc[0], acc[1], acc[2], acc[3]));
             if (MODE == kFwdBoth) stg4(dz0 + ebase, make_float4(acc2[0], acc2[1], acc2[2], acc2[3]));
             fin = true;
           } else if (n >= n_a) {  // a long chain: hand it to phase B
@@ -453,7 +464,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
           if (kIsBwd) {
             bwd_finish(base, q, acc);
           } else {
-            stg4(p.z + base, make_float4(acc[0], acc[1], acc[2], acc[3]));
+            stg4_planes(p.z, p.z_lo, base, make_float4(acc[0], acc[1], acc[2], acc[3]));
             if (MODE == kFwdBoth) stg4(p.dz_out + base, make_float4(acc2[0], acc2[1], acc2[2], acc2[3]));
           }
         } else {
@@ -517,7 +528,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
               } else {
                 const int r = slot / kThreads, owner = slot % kThreads;
                 const long long base = (row0 + r) * p.K + k0 + 4 * owner;
-                stg4(p.z + base, make_float4(tot[0], tot[1], tot[2], tot[3]));
+                stg4_planes(p.z, p.z_lo, base, make_float4(tot[0], tot[1], tot[2], tot[3]));
                 if (MODE == kFwdBoth) stg4(p.dz_out + base, make_float4(tot2[0], tot2[1], tot2[2], tot2[3]));
               }
             }
@@ -702,7 +713,7 @@ __global__ void __launch_bounds__(kThreads) sampler_bwd_saved_kernel(const Sampl
               col_b[j] += gh[j];
             }
           }
-          stg4(p.g_h + (row0 + r) * p.K + k, make_float4(gh[0], gh[1], gh[2], gh[3]));
+          stg4_planes(p.g_h, p.g_h_lo, (row0 + r) * p.K + k, make_float4(gh[0], gh[1], gh[2], gh[3]));
         }
       }
     }
@@ -968,11 +979,19 @@ extern "C" int pvae_sampler_fwd(const float* h, const float* log_r, const float*
                                 int64_t K, int64_t row_offset, int n_exp, float temp, int indicator, int exc_only,
                                 float exit_logit, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
                                 void* stream) {
+  return pvae::sampler_fwd_impl(h, log_r, b_enc, z, nullptr, log_dr, rate, kl, kl_rowsum, rate_max, dz_acc, B, K, row_offset, n_exp, temp,
+                                indicator, exc_only, exit_logit, seed, offset, offset_dev, stream);
+}
+
+int pvae::sampler_fwd_impl(const float* h, const float* log_r, const float* b_enc, float* z, float* z_lo, float* log_dr, float* rate,
+                           float* kl, float* kl_rowsum, float* rate_max, float* dz_acc, int64_t B, int64_t K, int64_t row_offset,
+                           int n_exp, float temp, int indicator, int exc_only, float exit_logit, uint64_t seed, uint64_t offset,
+                           const uint64_t* offset_dev, void* stream) {
   if (int rc = check_common("pvae_sampler_fwd", B, K, row_offset, n_exp, temp, indicator)) return rc;
   if (B == 0) return PVAE_OK;
   if (!h || !log_r || !z) return fail(PVAE_ERR_INVALID, "pvae_sampler_fwd: null h/log_r/z");
   SamplerParams p{};
-  p.h = h, p.log_r = log_r, p.b_enc = b_enc, p.z = z, p.log_dr = log_dr, p.rate = rate, p.kl = kl;
+  p.h = h, p.log_r = log_r, p.b_enc = b_enc, p.z = z, p.z_lo = z_lo, p.log_dr = log_dr, p.rate = rate, p.kl = kl;
   p.kl_rowsum = kl_rowsum, p.rate_max = rate_max, p.dz_out = dz_acc;
   if (dz_acc && temp == 0.f) return fail(PVAE_ERR_INVALID, "pvae_sampler_fwd: hard counts (temp == 0) have no gradient (dz_acc)");
   p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = p.rows_block = rows_per_block_for(B);
@@ -994,13 +1013,22 @@ extern "C" int pvae_sampler_bwd(const float* h, const float* log_r, const float*
                                 float* partial_ws, int accumulate, int64_t B, int64_t K, int64_t row_offset,
                                 int n_exp, float temp, int indicator, int exc_only, float exit_logit, uint64_t seed,
                                 uint64_t offset, const uint64_t* offset_dev, void* stream) {
+  return pvae::sampler_bwd_impl(h, log_r, b_enc, g_z, g_log_dr, dz_acc, kl_scale, g_h, nullptr, g_log_r, g_b_enc, partial_ws, accumulate, B, K,
+                                row_offset, n_exp, temp, indicator, exc_only, exit_logit, seed, offset, offset_dev, stream);
+}
+
+int pvae::sampler_bwd_impl(const float* h, const float* log_r, const float* b_enc, const float* g_z, const float* g_log_dr,
+                           const float* dz_acc, float kl_scale, float* g_h, float* g_h_lo, float* g_log_r, float* g_b_enc,
+                           float* partial_ws, int accumulate, int64_t B, int64_t K, int64_t row_offset, int n_exp, float temp,
+                           int indicator, int exc_only, float exit_logit, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                           void* stream) {
   if (int rc = check_common("pvae_sampler_bwd", B, K, row_offset, n_exp, temp, indicator)) return rc;
   if (temp == 0.f) return fail(PVAE_ERR_INVALID, "pvae_sampler_bwd: hard counts (temp == 0) have no gradient");
   if (B == 0) return PVAE_OK;
   if (!h || !log_r || !g_z || !g_h || !g_log_r || !partial_ws)
     return fail(PVAE_ERR_INVALID, "pvae_sampler_bwd: null h/log_r/g_z/g_h/g_log_r/partial_ws");
   SamplerParams p{};
-  p.h = h, p.log_r = log_r, p.b_enc = b_enc, p.g_z = g_z, p.g_log_dr = g_log_dr, p.g_h = g_h, p.dz_in = dz_acc;
+  p.h = h, p.log_r = log_r, p.b_enc = b_enc, p.g_z = g_z, p.g_log_dr = g_log_dr, p.g_h = g_h, p.g_h_lo = g_h_lo, p.dz_in = dz_acc;
   p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = p.rows_block = rows_per_block_for(B);
   const long long P = (B + p.rows_per_block - 1) / p.rows_per_block;
   p.part_log_r = partial_ws;

@@ -17,8 +17,8 @@ namespace pvae {
 // One warp per sample; D is a multiple of 4.
 // y_parts > 1: y arrives as split-K partial sums y_parts * (B, D) apart (pvae_gemm_tf32 with C = NULL), summed here in order
 __global__ void __launch_bounds__(256) recon_kernel(const float* __restrict__ y, const float* __restrict__ x,
-                                                    float* __restrict__ g_y, float* __restrict__ recon, long long B,
-                                                    long long D, float g_scale, int y_parts) {
+                                                    float* __restrict__ g_y, float* __restrict__ g_y_lo,
+                                                    float* __restrict__ recon, long long B, long long D, float g_scale, int y_parts) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -34,7 +34,15 @@ __global__ void __launch_bounds__(256) recon_kernel(const float* __restrict__ y,
       }
       const float4 r = make_float4(yv.x - xv.x, yv.y - xv.y, yv.z - xv.z, yv.w - xv.w);
       acc += (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
-      if (g_y != nullptr) stg4(g_y + b * D + d, make_float4(g_scale * r.x, g_scale * r.y, g_scale * r.z, g_scale * r.w));
+      if (g_y != nullptr) {
+        const float4 gv = make_float4(g_scale * r.x, g_scale * r.y, g_scale * r.z, g_scale * r.w);
+        stg4(g_y + b * D + d, gv);
+        if (g_y_lo != nullptr)  // TF32 low plane for the dgrad / wgrad GEMMs (x - trunc_tf32(x), exact)
+          stg4(g_y_lo + b * D + d, make_float4(gv.x - __uint_as_float(__float_as_uint(gv.x) & 0xFFFFE000u),
+                                               gv.y - __uint_as_float(__float_as_uint(gv.y) & 0xFFFFE000u),
+                                               gv.z - __uint_as_float(__float_as_uint(gv.z) & 0xFFFFE000u),
+                                               gv.w - __uint_as_float(__float_as_uint(gv.w) & 0xFFFFE000u)));
+      }
     }
     acc = warp_sum(acc);
     if (lane == 0 && recon != nullptr) recon[b] = acc;
@@ -103,19 +111,18 @@ __global__ void norm_finalize_kernel(const float* __restrict__ part, int nparts,
 // ---- Adamax (base/adamax.py:79-88): m = b1 m + (1-b1) g; u = max(b2 u, |g| + eps); p -= clr m / u
 __global__ void __launch_bounds__(256) adamax_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                      float* __restrict__ u, long long n, float clr, float beta1, float beta2,
-                                                     float eps, float weight_decay, const float* __restrict__ clip_coef) {
+                                                     float eps, float weight_decay, const float* __restrict__ clip_coef,
+                                                     float* __restrict__ p_lo) {
   pdl_launch_dependents();
   pdl_wait();
   const float cc = clip_coef != nullptr ? clip_coef[1] : 1.f;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
-    float gi = g[i] * cc;
-    const float pi = p[i];
-    if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
-    const float mi = m[i] * beta1 + (1.f - beta1) * gi;
-    const float ui = fmaxf(u[i] * beta2, fabsf(gi) + eps);
+    float pi = p[i], mi = m[i], ui = u[i];
+    const float lo = adamax_apply(pi, mi, ui, cc == 1.f ? g[i] : g[i] * cc, clr, beta1, beta2, eps, weight_decay);
     m[i] = mi;
     u[i] = ui;
-    p[i] = pi - clr * (mi / ui);
+    p[i] = pi;
+    if (p_lo != nullptr) p_lo[i] = lo;
   }
 }
 
@@ -131,23 +138,29 @@ struct SegTable {
   int n_partials[kMaxSegments], columnar[kMaxSegments], first_block[kMaxSegments + 1];
   int n;
 };
-__device__ __forceinline__ void adamax_update(float* p, float* m, float* u, long long i, float gi, float clr, float beta1, float beta2,
-                                              float eps, float weight_decay) {
-  const float pi = p[i];
-  if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
-  const float mi = m[i] * beta1 + (1.f - beta1) * gi;
-  const float ui = fmaxf(u[i] * beta2, fabsf(gi) + eps);
+__device__ __forceinline__ void adamax_update(float* p, float* m, float* u, float* p_lo, long long i, float gi, float clr, float beta1,
+                                              float beta2, float eps, float weight_decay) {
+  float pi = p[i], mi = m[i], ui = u[i];
+  const float lo = adamax_apply(pi, mi, ui, gi, clr, beta1, beta2, eps, weight_decay);
   m[i] = mi;
   u[i] = ui;
-  p[i] = pi - clr * (mi / ui);
+  p[i] = pi;
+  if (p_lo != nullptr) p_lo[i] = lo;
 }
 __global__ void __launch_bounds__(1024) adamax_partials_kernel(const __grid_constant__ SegTable t, float* __restrict__ p,
                                                                float* __restrict__ g_out, float* __restrict__ m,
                                                                float* __restrict__ u, float clr, float beta1, float beta2, float eps,
-                                                               float weight_decay) {
+                                                               float weight_decay, float* __restrict__ p_lo,
+                                                               const float* __restrict__ lr_sched, int n_sched,
+                                                               const int* __restrict__ state) {
   __shared__ float s[32][33];
   pdl_launch_dependents();
   pdl_wait();
+  if (state != nullptr) {  // CUDA-graph replay: step count and learning rate live on the device (see adamax_dev_kernel)
+    const int step = state[0] + 1;
+    const float lr = lr_sched[min(step - 1, n_sched - 1)];
+    clr = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(beta1), step)));
+  }
   int seg = 0;
   while (seg + 1 < t.n && static_cast<int>(blockIdx.x) >= t.first_block[seg + 1]) ++seg;
   const int blk = blockIdx.x - t.first_block[seg];
@@ -174,7 +187,7 @@ __global__ void __launch_bounds__(1024) adamax_partials_kernel(const __grid_cons
 #pragma unroll
       for (int y = 1; y < 32; ++y) v += s[y][tx];
       g_out[off + k] = v;
-      if (p != nullptr) adamax_update(p, m, u, off + k, v, clr, beta1, beta2, eps, weight_decay);
+      if (p != nullptr) adamax_update(p, m, u, p_lo, off + k, v, clr, beta1, beta2, eps, weight_decay);
     }
     return;
   }
@@ -204,10 +217,10 @@ __global__ void __launch_bounds__(1024) adamax_partials_kernel(const __grid_cons
   }
   if (p == nullptr) return;  // reduction only (data parallel: the exchange kernel applies the update)
   const long long i = off + 4 * i4;
-  adamax_update(p, m, u, i, a.x, clr, beta1, beta2, eps, weight_decay);
-  adamax_update(p, m, u, i + 1, a.y, clr, beta1, beta2, eps, weight_decay);
-  adamax_update(p, m, u, i + 2, a.z, clr, beta1, beta2, eps, weight_decay);
-  adamax_update(p, m, u, i + 3, a.w, clr, beta1, beta2, eps, weight_decay);
+  adamax_update(p, m, u, p_lo, i, a.x, clr, beta1, beta2, eps, weight_decay);
+  adamax_update(p, m, u, p_lo, i + 1, a.y, clr, beta1, beta2, eps, weight_decay);
+  adamax_update(p, m, u, p_lo, i + 2, a.z, clr, beta1, beta2, eps, weight_decay);
+  adamax_update(p, m, u, p_lo, i + 3, a.w, clr, beta1, beta2, eps, weight_decay);
 }
 
 // ---- Adamax with the step-dependent scalars on the device (CUDA-graph replay of a training step) -------------
@@ -218,7 +231,8 @@ __global__ void __launch_bounds__(1024) adamax_partials_kernel(const __grid_cons
 __global__ void __launch_bounds__(256) adamax_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                          float* __restrict__ u, long long n, const float* __restrict__ lr_sched,
                                                          int n_sched, const int* __restrict__ state, float beta1, float beta2,
-                                                         float eps, float weight_decay, const float* __restrict__ clip_coef) {
+                                                         float eps, float weight_decay, const float* __restrict__ clip_coef,
+                                                         float* __restrict__ p_lo) {
   pdl_launch_dependents();
   pdl_wait();
   const int step = state[0] + 1;
@@ -226,14 +240,12 @@ __global__ void __launch_bounds__(256) adamax_dev_kernel(float* __restrict__ p, 
   const float clr = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(beta1), step)));  // base/adamax.py:75-76
   const float cc = clip_coef != nullptr ? clip_coef[1] : 1.f;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
-    float gi = g[i] * cc;
-    const float pi = p[i];
-    if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
-    const float mi = m[i] * beta1 + (1.f - beta1) * gi;
-    const float ui = fmaxf(u[i] * beta2, fabsf(gi) + eps);
+    float pi = p[i], mi = m[i], ui = u[i];
+    const float lo = adamax_apply(pi, mi, ui, cc == 1.f ? g[i] : g[i] * cc, clr, beta1, beta2, eps, weight_decay);
     m[i] = mi;
     u[i] = ui;
-    p[i] = pi - clr * (mi / ui);
+    p[i] = pi;
+    if (p_lo != nullptr) p_lo[i] = lo;
   }
 }
 __global__ void advance_state_kernel(int* __restrict__ state, unsigned long long philox_increment, float* __restrict__ rmax_step,
@@ -248,6 +260,17 @@ __global__ void advance_state_kernel(int* __restrict__ state, unsigned long long
     }
     state[0] += 1;
     *reinterpret_cast<unsigned long long*>(state + 2) += philox_increment;
+  }
+}
+
+// ---- TF32 low plane of an array: lo = x - trunc_tf32(x) (exact); what the plane-fed GEMMs load next to x itself ----
+__global__ void __launch_bounds__(256) tf32_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, long long n4) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += gridDim.x * 256ll) {
+    const float4 v = ldg4(x + 4 * i);
+    stg4(lo + 4 * i, make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
+                                 v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u)));
   }
 }
 
@@ -277,9 +300,16 @@ using namespace pvae;
 extern "C" int pvae_adamax_from_partials(float* p, float* g_out, float* exp_avg, float* exp_inf, const pvae_grad_segment* segs,
                                          int n_segs, float lr, int step, float beta1, float beta2, float eps, float weight_decay,
                                          void* stream) {
-  if (!g_out || !segs || n_segs < 1 || n_segs > kMaxSegments || (p && (!exp_avg || !exp_inf || step < 1)))
+  return adamax_from_partials_impl(p, nullptr, g_out, exp_avg, exp_inf, segs, n_segs, lr, step, beta1, beta2, eps, weight_decay, AdamaxDev{},
+                                   stream);
+}
+
+int pvae::adamax_from_partials_impl(float* p, float* p_lo, float* g_out, float* exp_avg, float* exp_inf, const pvae_grad_segment* segs,
+                                    int n_segs, float lr, int step, float beta1, float beta2, float eps, float weight_decay,
+                                    const AdamaxDev& dev, void* stream) {
+  if (!g_out || !segs || n_segs < 1 || n_segs > kMaxSegments || (p && (!exp_avg || !exp_inf || (step < 1 && !dev.state))))
     return fail(PVAE_ERR_INVALID, "pvae_adamax_from_partials: bad argument");
-  if (!p) step = 1;  // p == NULL: reduce the partials into g_out only
+  if (!p || dev.state) step = 1;  // p == NULL: reduce the partials into g_out only; device-side counters: computed in the kernel
   SegTable t = {};
   t.n = n_segs;
   int blocks = 0;
@@ -297,7 +327,23 @@ extern "C" int pvae_adamax_from_partials(float* p, float* g_out, float* exp_avg,
   const float clr = static_cast<float>(static_cast<double>(lr) / bias_correction);
   return cuda_ok("pvae_adamax_from_partials", launch_pdl(adamax_partials_kernel, dim3(blocks), dim3(32, 32), 0,
                                                          static_cast<cudaStream_t>(stream), t, p, g_out, exp_avg, exp_inf, clr, beta1,
-                                                         beta2, eps, weight_decay));
+                                                         beta2, eps, weight_decay, p_lo, dev.lr_sched, dev.n_sched, dev.state));
+}
+
+int pvae::advance_state(int* state, uint64_t philox_increment, float* rmax_step, float* rmax_ring, int ring_n, void* stream) {
+  // plain launch (no programmatic overlap): it must not run before the kernels that read the counters have finished
+  advance_state_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(state, static_cast<unsigned long long>(philox_increment), rmax_step,
+                                                                        rmax_ring, ring_n);
+  count_launch();
+  return cuda_ok("advance_state_kernel", cudaGetLastError());
+}
+
+extern "C" int pvae_tf32_lo(const float* x, float* lo, int64_t n, void* stream) {
+  if (n < 0 || n % 4 || (n > 0 && (!x || !lo))) return fail(PVAE_ERR_INVALID, "pvae_tf32_lo: bad argument (n must be a multiple of 4)");
+  if (n == 0) return PVAE_OK;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((n / 4 + 255) / 256, 148ll * 8));
+  return cuda_ok("pvae_tf32_lo", launch_pdl(tf32_lo_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), x, lo,
+                                            static_cast<long long>(n / 4)));
 }
 
 extern "C" int pvae_adamax_step_dev(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, const float* lr_sched,
@@ -311,12 +357,9 @@ extern "C" int pvae_adamax_step_dev(float* p, const float* g, float* exp_avg, fl
   const unsigned grid = static_cast<unsigned>(std::min<long long>((n + 255) / 256, 148ll * 8));
   if (int rc = cuda_ok("pvae_adamax_step_dev", launch_pdl(adamax_dev_kernel, dim3(grid), dim3(256), 0, s, p, g, exp_avg, exp_inf,
                                                           static_cast<long long>(n), lr_sched, n_sched, static_cast<const int*>(state),
-                                                          beta1, beta2, eps, weight_decay, clip_coef)))
+                                                          beta1, beta2, eps, weight_decay, clip_coef, static_cast<float*>(nullptr))))
     return rc;
-  // plain launch (no programmatic overlap): it must not run before the Adamax kernel has read the counter
-  advance_state_kernel<<<1, 32, 0, s>>>(state, static_cast<unsigned long long>(philox_increment), rmax_step, rmax_ring, ring_n);
-  count_launch();
-  return cuda_ok("advance_state_kernel", cudaGetLastError());
+  return advance_state(state, philox_increment, rmax_step, rmax_ring, ring_n, stream);
 }
 
 extern "C" int pvae_gather(const void* const* srcs, const int64_t* offsets, int n_tensors, float* dst, void* stream) {
@@ -340,12 +383,17 @@ extern "C" int pvae_gather(const void* const* srcs, const int64_t* offsets, int 
 
 extern "C" int pvae_recon_residual_parts(const float* y_parts, int n_parts, const float* x, float* g_y, float* recon, int64_t B,
                                          int64_t D, float g_scale, void* stream) {
+  return recon_parts_impl(y_parts, n_parts, x, g_y, nullptr, recon, B, D, g_scale, stream);
+}
+
+int pvae::recon_parts_impl(const float* y_parts, int n_parts, const float* x, float* g_y, float* g_y_lo, float* recon, int64_t B, int64_t D,
+                           float g_scale, void* stream) {
   if (B <= 0 || D <= 0 || D % 4 != 0 || n_parts < 1 || !y_parts || !x)
     return fail(PVAE_ERR_INVALID, "pvae_recon_residual_parts: bad argument");
   const unsigned grid = static_cast<unsigned>(std::min<long long>((B + 7) / 8, 148ll * 8));
   return cuda_ok("pvae_recon_residual_parts", launch_pdl(recon_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream),
-                                                         y_parts, x, g_y, recon, static_cast<long long>(B), static_cast<long long>(D),
-                                                         g_scale, n_parts));
+                                                         y_parts, x, g_y, g_y_lo, recon, static_cast<long long>(B),
+                                                         static_cast<long long>(D), g_scale, n_parts));
 }
 
 extern "C" int pvae_recon_residual(const float* y, const float* x, float* g_y, float* recon, int64_t B, int64_t D,
@@ -355,7 +403,8 @@ extern "C" int pvae_recon_residual(const float* y, const float* x, float* g_y, f
   if (!y || !x) return fail(PVAE_ERR_INVALID, "pvae_recon_residual: null y/x");
   const unsigned grid = static_cast<unsigned>(std::min<long long>((B + 7) / 8, 148ll * 8));
   return cuda_ok("pvae_recon_residual", launch_pdl(recon_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), y, x,
-                                                   g_y, recon, static_cast<long long>(B), static_cast<long long>(D), g_scale, 1));
+                                                   g_y, static_cast<float*>(nullptr), recon, static_cast<long long>(B),
+                                                   static_cast<long long>(D), g_scale, 1));
 }
 
 extern "C" int pvae_loss_assemble(const float* recon, const float* kl_rowsum, float* out3, int64_t B, float beta,
@@ -381,11 +430,16 @@ extern "C" int pvae_grad_norm(const float* g, int64_t n, float max_norm, float* 
 extern "C" int pvae_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, float lr, int step,
                                 float beta1, float beta2, float eps, float weight_decay, const float* clip_coef,
                                 void* stream) {
+  return adamax_step_impl(p, nullptr, g, exp_avg, exp_inf, n, lr, step, beta1, beta2, eps, weight_decay, clip_coef, stream);
+}
+
+int pvae::adamax_step_impl(float* p, float* p_lo, const float* g, float* exp_avg, float* exp_inf, int64_t n, float lr, int step, float beta1,
+                           float beta2, float eps, float weight_decay, const float* clip_coef, void* stream) {
   if (n <= 0 || !p || !g || !exp_avg || !exp_inf || step < 1) return fail(PVAE_ERR_INVALID, "pvae_adamax_step: bad argument");
   const double bias_correction = 1.0 - pow(static_cast<double>(beta1), step);  // base/adamax.py:75-76
   const float clr = static_cast<float>(static_cast<double>(lr) / bias_correction);
   const unsigned grid = static_cast<unsigned>(std::min<long long>((n + 255) / 256, 148ll * 8));
   return cuda_ok("pvae_adamax_step", launch_pdl(adamax_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g,
                                                 exp_avg, exp_inf, static_cast<long long>(n), clr, beta1, beta2, eps,
-                                                weight_decay, clip_coef));
+                                                weight_decay, clip_coef, p_lo));
 }

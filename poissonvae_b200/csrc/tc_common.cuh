@@ -113,6 +113,9 @@ __device__ __forceinline__ uint4 tf32_lo4(const uint4 v) {
   return lo;
 }
 
+__device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+__device__ __forceinline__ float4 tf32_lo4f(const float4 v) { return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)); }
+
 // Host: cached fp32 tensor map of rank 2..4.  dims/box/estr are innermost-first; strides_bytes has rank-1 entries
 // (dimension 0 is contiguous).  swizzle: 0 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_ATOM_32B.  OOB = 0.
 int make_tensor_map(CUtensorMap* out, const float* base, int rank, const long long* dims, const long long* strides_bytes,

@@ -140,7 +140,12 @@ class TrainerVAE:
                 warnings.warn(f"peer-memory gradient exchange unavailable on at least one rank ({err!r}); using NCCL all-reduce")
         elif dp_mode == 'peer' and self.world > 1:
             raise ValueError("dp_mode='peer' does not support grad_clip")
-        self.planes = False  # set by _setup_planes(): the TF32 low planes of the GEMM operands are kept by their producers
+        # TF32 operand planes (csrc/gemm_tc.cu mode 2): every producer of a GEMM operand also writes its low part once, the
+        # GEMMs load hi and lo tiles by TMA instead of splitting every stage in shared memory.  Bit-identical results.
+        self.use_planes = True
+        self.flat_p_lo = None
+        self._planes_version = None
+        self._descs = {}
         self.r_max = torch.zeros(max(n_batches_per_epoch, 1), device=self.device)  # rate.max() of each step of the epoch
         self._gather_tab = None
         self._sink = None
@@ -184,6 +189,7 @@ class TrainerVAE:
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_inf = torch.zeros_like(self.flat_p)
         self._names, self._params = names, params
+        self._plist = [params[k] for k in names]
         self.views, self.gviews, o = {}, {}, 0
         for k in names:
             p = params[k]
@@ -216,6 +222,11 @@ class TrainerVAE:
         e1.record()
         self.kernel_events.setdefault(name, []).append((e0, e1))
         return out
+
+    @property
+    def planes(self) -> bool:
+        """The fused step runs its GEMMs on operand planes (TF32 low parts written once by the operands' producers)."""
+        return bool(self.use_planes and self.fused and linear_mod.PRECISE)
 
     def launches_per_step(self) -> int:
         """Kernels of libpvae_b200.so launched by one train_step (fused lin|lin step; for the other architectures
@@ -277,6 +288,8 @@ class TrainerVAE:
         shape = (chunk,) + tuple(batches_host.shape[1:])
         if getattr(self, "_chunk_bufs", None) is None or self._chunk_bufs[0].shape != shape:
             self._chunk_bufs = [torch.empty(shape, device=self.device, dtype=torch.float32) for _ in range(2)]
+            # TF32 low planes of the staged batches: split once per upload on the copy stream, off the training stream
+            self._chunk_lo = [torch.empty(shape, device=self.device, dtype=torch.float32) for _ in range(2)] if self.planes else None
             self._chunk_ready = [torch.cuda.Event(), torch.cuda.Event()]
             self._chunk_free = [torch.cuda.Event(), torch.cuda.Event()]
             self._loss_ring = torch.empty(2 * chunk, 4, device=self.device, dtype=torch.float32)
@@ -284,10 +297,13 @@ class TrainerVAE:
             for buf in self._chunk_bufs:  # static input buffers: their steps can be replayed as CUDA graphs
                 for j in range(chunk):
                     self._graph_static.add(buf[j].data_ptr())
+        use_lo = self.planes and getattr(self, "_chunk_lo", None) is not None
+        lo_of = (lambda slot, j: self._chunk_lo[slot][j].reshape(shape[1], -1)) if use_lo else (lambda slot, j: None)
         if self.fused and self.world == 1 and self.graph is not False and self.cfg.method == 'mc' and not direct:
             for slot in range(2):
                 for j in range(chunk):
-                    self.precapture(self._chunk_bufs[slot][j].reshape(shape[1], -1), first_gstep, self._loss_ring[slot * chunk + j])
+                    self.precapture(self._chunk_bufs[slot][j].reshape(shape[1], -1), first_gstep, self._loss_ring[slot * chunk + j],
+                                    x_lo=lo_of(slot, j))
         main = torch.cuda.current_stream()
         cs = self._copy_stream
         # every step's [loss, mse, kl] lands in a small device ring and is copied back on the side stream, so the
@@ -317,6 +333,9 @@ class TrainerVAE:
             with torch.cuda.stream(cs):
                 first = (start + lo) % pool
                 self._chunk_bufs[slot][:hi - lo].copy_(batches_host[first:first + hi - lo], non_blocking=True)
+                if use_lo:
+                    _lib.check(self.lib.pvae_tf32_lo(_ptr(self._chunk_bufs[slot]), _ptr(self._chunk_lo[slot]),
+                                                     (hi - lo) * self._chunk_bufs[slot][0].numel(), cs.cuda_stream))
                 self._chunk_ready[slot].record(cs)
 
         upload(0)
@@ -326,10 +345,10 @@ class TrainerVAE:
             main.wait_event(self._chunk_ready[slot])
             for i in range(lo, hi):
                 if direct:
-                    self.train_step(self._chunk_bufs[slot][i - lo], first_gstep + i, loss_out=losses_host[i])
+                    self.train_step(self._chunk_bufs[slot][i - lo], first_gstep + i, loss_out=losses_host[i], x_lo=lo_of(slot, i - lo))
                     continue
                 k = slot * chunk + (i - lo)  # loss slot: reused two chunks later, after its read-back was enqueued
-                self.train_step(self._chunk_bufs[slot][i - lo], first_gstep + i, loss_out=self._loss_ring[k])
+                self.train_step(self._chunk_bufs[slot][i - lo], first_gstep + i, loss_out=self._loss_ring[k], x_lo=lo_of(slot, i - lo))
                 # read this step's result back on the side stream: the training stream never waits for PCIe
                 self._loss_ev[k].record(main)
                 cs.wait_event(self._loss_ev[k])
@@ -350,8 +369,9 @@ class TrainerVAE:
         self._stage_src[slot] = x_host
 
     # -- the step ------------------------------------------------------------------------------------
-    def train_step(self, x: torch.Tensor, gstep: int = 0, philox=None, loss_out: torch.Tensor = None):
+    def train_step(self, x: torch.Tensor, gstep: int = 0, philox=None, loss_out: torch.Tensor = None, x_lo: torch.Tensor = None):
         """x: (B_local, 1, H, W) or (B_local, D) device tensor (this rank's slice of the global batch).
+        x_lo: optional TF32 low plane of x (split_planes(x)); without it the step computes it itself.
         Returns the device tensor [loss, mse, kl] (global-batch means; no host sync); `loss_out` (3 floats on
         the device) receives it instead of the trainer's own scratch."""
         cfg, m, lib = self.cfg, self.model, self.lib
@@ -373,7 +393,7 @@ class TrainerVAE:
         if cfg.method == 'exact' or not self.fused:
             return self._train_step_autograd(x, beta, lr, gstep, b, loss_out, row_offset, (seed, offset))
         if philox is None and self._graph_wanted(x2, gstep):
-            return self._graph_step(x2, gstep, temp, beta, n_exp, ind, seed, offset, loss_out)
+            return self._graph_step(x2, gstep, temp, beta, n_exp, ind, seed, offset, loss_out, x_lo)
         # where this step's gradients and its [loss, mse, kl] shares go
         if self.peer is not None:  # symmetric double buffer, alternating with the exchange token's parity
             self._peer_token += 1  # strictly increasing for the life of the exchange (never rewound with opt_step)
@@ -394,33 +414,39 @@ class TrainerVAE:
             events = (ctypes.c_void_p * 4)(*[e.cuda_event for e in evs])
             self.kernel_events.setdefault('sampler_fwd', []).append((evs[0], evs[1]))
             self.kernel_events.setdefault('sampler_bwd', []).append((evs[2], evs[3]))
+        # one C call per step (csrc/lin_step.cu): forward + loss + backward and, single GPU without clipping or over
+        # peer memory, the optimiser too.  The descriptor is kept from step to step; only what changes is rewritten.
+        d = self._desc(B, Bg, row_offset, K, D)
+        planes = self._planes_ready(s)
+        d.x, d.x_lo = x2.data_ptr(), (_ptr(x_lo) if planes else None)
+        d.params_lo = self.flat_p_lo.data_ptr() if planes else None
+        d.grads, d.loss3 = gbuf.data_ptr(), step_loss.data_ptr()
+        d.rate_max = self.r_max.data_ptr() + 4 * (gstep % self.r_max.numel())
+        d.n_exp, d.temp, d.beta, d.indicator, d.precise = n_exp, temp, beta, ind, int(linear_mod.PRECISE)
+        d.seed, d.offset, d.offset_dev = seed, offset, None
+        d.events = ctypes.cast(events, ctypes.c_void_p) if events is not None else None
+        d.lr, d.step = lr, self.opt_step + 1
+        d.state = None
         if self.world == 1 and cfg.grad_clip is None and self.fuse_update:
-            # forward + loss + backward + optimiser in one call; the gradient reductions happen inside the Adamax kernel
+            d.update = 1  # the gradient reductions happen inside the Adamax kernel, which also keeps params_lo current
             self.opt_step += 1
-            chk(lib.pvae_lin_step_train(
-                _ptr(x2), _ptr(self.flat_p), _ptr(gbuf), _ptr(self.exp_avg), _ptr(self.exp_inf), _ptr(b['ws']), _ptr(step_loss),
-                self.r_max.data_ptr() + 4 * (gstep % self.r_max.numel()), B, K, D, int(m.fc_enc.bias is not None), n_exp, temp,
-                beta, ind, int(m.cfg.exc_only), m.exit_logit, int(linear_mod.PRECISE), seed, offset, None, events, lr,
-                self.opt_step, cfg.betas[0], cfg.betas[1], cfg.eps, cfg.weight_decay, s))
+            chk(lib.pvae_lin_step(ctypes.byref(d), s))
             return loss[:3]
-        # forward + loss + backward: one call, every kernel enqueued back to back (csrc/lin_step.cu)
-        chk(lib.pvae_lin_step_fwd_bwd(
-            _ptr(x2), _ptr(self.flat_p), _ptr(gbuf), _ptr(b['ws']), _ptr(step_loss),
-            self.r_max.data_ptr() + 4 * (gstep % self.r_max.numel()), B, Bg, row_offset, K, D,
-            int(m.fc_enc.bias is not None), n_exp, temp, beta, ind, int(m.cfg.exc_only), m.exit_logit,
-            int(linear_mod.PRECISE), seed, offset, None, events, s))
-        self.opt_step += 1
         if self.peer is not None:
-            # one kernel: publish / wait for the step token, sum all ranks' gradients over NVLink peer memory in rank
-            # order and apply Adamax (csrc/peer_allreduce.cu)
+            # exchange + Adamax inside the step, in two buckets (W_dec under the rest of the backward), NVLink peer memory
             tail = loss if loss.numel() >= 4 else b['loss']  # the kernel stores the summed statistics as one float4
-            chk(lib.pvae_allreduce_adamax(_ptr(self.flat_p), _ptr(self.exp_avg), _ptr(self.exp_inf), n, n + 4,
-                                          self.peer.grad_ptrs[self._peer_token & 1], self.peer.flag_ptrs, self.world,
-                                          self.rank, self._peer_token, _ptr(tail), None, lr, self.opt_step, cfg.betas[0],
-                                          cfg.betas[1], cfg.eps, cfg.weight_decay, s))
+            d.update, d.loss3 = 2, tail.data_ptr()
+            d.world, d.rank, d.token = self.world, self.rank, self._peer_token
+            d.peer_grads = ctypes.cast(self.peer.grad_ptrs[self._peer_token & 1], ctypes.c_void_p)
+            d.peer_flags = ctypes.cast(self.peer.flag_ptrs, ctypes.c_void_p)
+            self.opt_step += 1
+            chk(lib.pvae_lin_step(ctypes.byref(d), s))
             if tail is not loss:
                 loss.copy_(tail[:3])
             return loss[:3]
+        d.update = 0
+        chk(lib.pvae_lin_step(ctypes.byref(d), s))
+        self.opt_step += 1
         if self.world > 1:
             dp.allreduce_gradients(self._flat_g_ext, None, self.pg)  # gradients already carry 1 / B_global
             loss[:3].copy_(step_loss[:3])
@@ -434,7 +460,55 @@ class TrainerVAE:
         chk(lib.pvae_adamax_step(_ptr(self.flat_p), _ptr(self.flat_g), _ptr(self.exp_avg), _ptr(self.exp_inf),
                                  self.flat_p.numel(), lr, self.opt_step, cfg.betas[0], cfg.betas[1], cfg.eps,
                                  cfg.weight_decay, _ptr(clip), s))
+        self._planes_version = None  # this optimiser kernel does not write the low plane: the next step refreshes it
         return loss[:3]
+
+    # -- TF32 operand planes ----------------------------------------------------------------------------
+    def _param_version(self):
+        """Changes whenever somebody wrote the parameters through torch (load_state_dict, in-place ops on a parameter or
+        on the flat buffer).  Writes through a fresh `.data` alias are invisible to it: call params_changed() after those."""
+        v = self.flat_p._version
+        for p in self._plist:
+            v += p._version
+        return v
+
+    def params_changed(self):
+        """Tell the trainer that the parameters were edited behind its back: their TF32 low plane is rebuilt next step."""
+        self._planes_version = None
+
+    def _planes_ready(self, s) -> bool:
+        """True when this step runs its GEMMs on operand planes; makes sure the parameters' low plane is current."""
+        if not (self.use_planes and self.fused and linear_mod.PRECISE):
+            return False
+        if self.flat_p_lo is None:
+            self.flat_p_lo = torch.empty_like(self.flat_p)
+        v = self._param_version()
+        if v != self._planes_version:
+            _lib.check(self.lib.pvae_tf32_lo(_ptr(self.flat_p), _ptr(self.flat_p_lo), self.flat_p.numel(), s))
+            self._planes_version = v
+        return True
+
+    def split_planes(self, x: torch.Tensor) -> torch.Tensor:
+        """x - trunc_tf32(x) of a device tensor (numel a multiple of 4): the low plane train_step(x, x_lo=...) takes, so
+        that data which stays in HBM is split once at upload time rather than once per step."""
+        xc = x.contiguous()
+        lo = torch.empty_like(xc)
+        _lib.check(self.lib.pvae_tf32_lo(_ptr(xc), _ptr(lo), xc.numel(), _stream()))
+        return lo
+
+    def _desc(self, B, Bg, row_offset, K, D):
+        key = (B, Bg, row_offset)
+        d = self._descs.get(key)
+        if d is None:
+            cfg, m = self.cfg, self.model
+            d = _lib.LinStepDesc()
+            d.B, d.B_global, d.row_offset, d.K, d.D = B, Bg, row_offset, K, D
+            d.has_bias, d.exc_only, d.exit_logit = int(m.fc_enc.bias is not None), int(m.cfg.exc_only), m.exit_logit
+            d.params, d.ws = self.flat_p.data_ptr(), self._buffers(B)['ws'].data_ptr()
+            d.exp_avg, d.exp_inf = self.exp_avg.data_ptr(), self.exp_inf.data_ptr()
+            d.beta1, d.beta2, d.eps, d.weight_decay = cfg.betas[0], cfg.betas[1], cfg.eps, cfg.weight_decay
+            self._descs[key] = d
+        return d
 
     @torch.inference_mode()
     def validate(self, data: torch.Tensor, temp: float = 0.0, batch_size: int = None, full_data: bool = False):
@@ -491,74 +565,90 @@ class TrainerVAE:
         # static input buffers (fit_host registers its staging slots)
         return x2.data_ptr() in self._graph_static or x2.numel() <= (1 << 18)
 
-    def _graph_step(self, x2, gstep, temp, beta, n_exp, ind, seed, offset, loss_out):
-        """One training step as ONE cudaGraphLaunch.  The graph holds the 12-14 kernels of the fused step (forward, loss,
-        backward, clip, Adamax) with the step-dependent scalars on the device: the learning-rate schedule is a device
-        array indexed by a device step counter, the Philox offset is a device word read by the sampler kernels
-        (`offset_dev`); a one-thread kernel at the end of the graph advances both.  A graph is specific to (input
-        buffer, batch, temp, beta, n_exp, clip threshold): while the temperature anneals every step differs and the
-        eager path runs instead; inputs that are neither registered static buffers nor small are stepped eagerly too."""
-        cfg, m, lib = self.cfg, self.model, self.lib
-        B, D = x2.shape
+    def _graph_state(self):
         if self._gstate is None:
             self._gstate = torch.zeros(4, device=self.device, dtype=torch.int32)
             self._gstate_host = [-1, -1]  # what the device words hold (step count, Philox offset)
             self._lr_sched = torch.tensor([self.lr_at(i) for i in range(self.n_iters)], device=self.device, dtype=torch.float32)
             self._gstate_pin = torch.zeros(2, dtype=torch.int64).pin_memory()  # [step count | Philox offset] = the 4 device ints
+            self._rmax_step = torch.zeros(1, device=self.device)  # the captured sampler's rate.max() word (moved per replay)
+
+    def _graph_key(self, x2, x_lo, temp, beta, n_exp, seed, warming, loss_out):
         static_in = x2.data_ptr() in self._graph_static
+        return (x2.data_ptr() if static_in else 0, _ptr(x_lo) if (static_in and x_lo is not None) else 0, x2.shape[0], temp, beta,
+                n_exp, seed, warming, 0 if loss_out is None else loss_out.data_ptr(), bool(self.planes)), static_in
+
+    def _graph_step(self, x2, gstep, temp, beta, n_exp, ind, seed, offset, loss_out, x_lo=None):
+        """One training step as ONE cudaGraphLaunch.  The graph holds the kernels of the fused step (forward, loss,
+        backward, [clip,] Adamax) with the step-dependent scalars on the device: the learning-rate schedule is a device
+        array indexed by a device step counter, the Philox offset is a device word read by the sampler kernels
+        (`offset_dev`); a one-thread kernel at the end of the graph advances both and files the step's rate.max() into
+        its slot of the epoch ring.  A graph is specific to (input buffer, batch, temp, beta, n_exp, clip threshold):
+        while the temperature anneals every step differs and the eager path runs instead; inputs that are neither
+        registered static buffers nor small are stepped eagerly too."""
+        cfg = self.cfg
+        B, D = x2.shape
+        self._graph_state()
         warming = cfg.grad_clip is not None and gstep / self.n_iters < cfg.warmup_portion
-        key = (x2.data_ptr() if static_in else 0, B, temp, beta, n_exp, seed, warming,
-               0 if loss_out is None else loss_out.data_ptr())
+        key, static_in = self._graph_key(x2, x_lo, temp, beta, n_exp, seed, warming, loss_out)
         g = self._graphs.get(key)
         if g is None:
             if len(self._graphs) >= 256:
                 self._graphs.clear()
-            g = self._graphs[key] = self._capture(x2 if static_in else None, B, D, temp, beta, n_exp, ind, seed, warming, loss_out)
+            g = self._graphs[key] = self._capture(x2 if static_in else None, x_lo if static_in else None, B, D, temp, beta, n_exp, ind,
+                                                  seed, warming, loss_out)
         # device counters: rewritten only when they are not what the previous replay left behind (first use, restore,
         # a generator that was re-seeded or advanced by somebody else)
         if self._gstate_host != [self.opt_step, offset]:
             self._gstate_pin[0] = self.opt_step
             self._gstate_pin[1] = offset
             self._gstate.view(torch.int64).copy_(self._gstate_pin, non_blocking=True)
+        if self.planes:  # parameters edited through torch since the last step: rebuild their low plane before the replay
+            self._planes_ready(_stream())
         if not static_in:
             g['x'].copy_(x2, non_blocking=True)
         g['graph'].replay()
         self.opt_step += 1
         self._gstate_host = [self.opt_step, offset + 4]
+        if g['clip']:
+            self._planes_version = None
         return g['loss'][:3]
 
-    def precapture(self, x2, gstep, loss_out=None):
-        """Build the graph a later train_step(x2, gstep, loss_out=loss_out) would replay, without running it (captures
-        cost about a millisecond each: callers with static buffers pay that before their loop, not inside it)."""
+    def precapture(self, x2, gstep, loss_out=None, x_lo=None):
+        """Build the graph a later train_step(x2, gstep, loss_out=loss_out, x_lo=x_lo) would replay, without running it
+        (captures cost about a millisecond each: callers with static buffers pay that before their loop, not inside it)."""
         if not (self.fused and self.cfg.method == 'mc' and self.world == 1 and self.graph is not False):
             return
         m = self.model
         temp = float(self.temperatures[min(gstep, self.n_iters - 1)])
         beta = float(self.betas[min(gstep, self.n_iters - 1)])
         seed = torch.cuda.default_generators[self.device.index].initial_seed()
-        if self._gstate is None:
-            self._gstate = torch.zeros(4, device=self.device, dtype=torch.int32)
-            self._gstate_host = [-1, -1]
-            self._lr_sched = torch.tensor([self.lr_at(i) for i in range(self.n_iters)], device=self.device, dtype=torch.float32)
-            self._gstate_pin = torch.zeros(2, dtype=torch.int64).pin_memory()
+        self._graph_state()
         warming = self.cfg.grad_clip is not None and gstep / self.n_iters < self.cfg.warmup_portion
-        static_in = x2.data_ptr() in self._graph_static
-        key = (x2.data_ptr() if static_in else 0, x2.shape[0], temp, beta, m._n_exp_host, seed, warming,
-               0 if loss_out is None else loss_out.data_ptr())
+        key, static_in = self._graph_key(x2, x_lo, temp, beta, m._n_exp_host, seed, warming, loss_out)
         if key not in self._graphs:
-            self._graphs[key] = self._capture(x2 if static_in else None, x2.shape[0], x2.shape[1], temp, beta, m._n_exp_host,
-                                              INDICATOR_CODES[m.cfg.indicator_approx], seed, warming, loss_out)
+            self._graphs[key] = self._capture(x2 if static_in else None, x_lo if static_in else None, x2.shape[0], x2.shape[1], temp,
+                                              beta, m._n_exp_host, INDICATOR_CODES[m.cfg.indicator_approx], seed, warming, loss_out)
 
-    def _capture(self, x_static, B, D, temp, beta, n_exp, ind, seed, warming, loss_out):
+    def _capture(self, x_static, x_lo_static, B, D, temp, beta, n_exp, ind, seed, warming, loss_out):
         cfg, m, lib = self.cfg, self.model, self.lib
         K, n = m.cfg.n_latents, self.flat_p.numel()
         b = self._buffers(B)
         x = x_static if x_static is not None else torch.empty(B, D, device=self.device, dtype=torch.float32)
         loss = loss_out if loss_out is not None else torch.zeros(4, device=self.device, dtype=torch.float32)
-        if getattr(self, "_rmax_step", None) is None:
-            self._rmax_step = torch.zeros(1, device=self.device)  # the captured sampler's rate.max() word (moved per replay)
-        rmax = self._rmax_step
-        off_dev = self._gstate.data_ptr() + 8
+        planes = self.planes
+        if planes and self.flat_p_lo is None:
+            self.flat_p_lo = torch.empty_like(self.flat_p)
+        d = _lib.LinStepDesc()  # a private copy: the capture reads it once
+        ctypes.memmove(ctypes.byref(d), ctypes.byref(self._desc(B, B, 0, K, D)), ctypes.sizeof(d))
+        d.x, d.x_lo = x.data_ptr(), (_ptr(x_lo_static) if planes else None)
+        d.params_lo = self.flat_p_lo.data_ptr() if planes else None
+        d.grads, d.loss3, d.rate_max = self._flat_g_ext.data_ptr(), loss.data_ptr(), self._rmax_step.data_ptr()
+        d.n_exp, d.temp, d.beta, d.indicator, d.precise = n_exp, temp, beta, ind, int(linear_mod.PRECISE)
+        d.seed, d.offset, d.offset_dev, d.events = seed, 0, self._gstate.data_ptr() + 8, None
+        d.lr_sched, d.n_sched, d.state = self._lr_sched.data_ptr(), self._lr_sched.numel(), self._gstate.data_ptr()
+        d.philox_increment, d.rmax_ring, d.ring_n = 4, self.r_max.data_ptr(), self.r_max.numel()
+        fused_update = cfg.grad_clip is None and self.fuse_update
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(cur)
@@ -567,23 +657,27 @@ class TrainerVAE:
         try:
             with torch.cuda.graph(graph, stream=side):
                 s = torch.cuda.current_stream().cuda_stream
-                _lib.check(lib.pvae_lin_step_fwd_bwd(
-                    _ptr(x), _ptr(self.flat_p), _ptr(self._flat_g_ext), _ptr(b['ws']), _ptr(loss), _ptr(rmax), B, B, 0, K, D,
-                    int(m.fc_enc.bias is not None), n_exp, temp, beta, ind, int(m.cfg.exc_only), m.exit_logit,
-                    int(linear_mod.PRECISE), seed, 0, off_dev, None, s))
-                clip = None
-                if cfg.grad_clip is not None:
-                    _lib.check(lib.pvae_grad_norm(_ptr(self._flat_g_ext), n, cfg.grad_clip * (3 if warming else 1), _ptr(b['nws']),
-                                                  _ptr(b['norm']), s))
-                    clip = b['norm']
-                _lib.check(lib.pvae_adamax_step_dev(_ptr(self.flat_p), _ptr(self._flat_g_ext), _ptr(self.exp_avg), _ptr(self.exp_inf),
-                                                    n, _ptr(self._lr_sched), self._lr_sched.numel(), _ptr(self._gstate), cfg.betas[0],
-                                                    cfg.betas[1], cfg.eps, cfg.weight_decay, _ptr(clip), 4, _ptr(rmax), _ptr(self.r_max),
-                                                    self.r_max.numel(), s))
+                if fused_update:  # the whole step incl. Adamax (which keeps params_lo current) and the counter advance
+                    d.update, d.step = 1, 0
+                    _lib.check(lib.pvae_lin_step(ctypes.byref(d), s))
+                else:
+                    if planes:  # the optimiser below does not write the low plane: rebuild it at the head of every replay
+                        _lib.check(lib.pvae_tf32_lo(_ptr(self.flat_p), _ptr(self.flat_p_lo), n, s))
+                    d.update, d.state = 0, None
+                    _lib.check(lib.pvae_lin_step(ctypes.byref(d), s))
+                    clip = None
+                    if cfg.grad_clip is not None:
+                        _lib.check(lib.pvae_grad_norm(_ptr(self._flat_g_ext), n, cfg.grad_clip * (3 if warming else 1), _ptr(b['nws']),
+                                                      _ptr(b['norm']), s))
+                        clip = b['norm']
+                    _lib.check(lib.pvae_adamax_step_dev(_ptr(self.flat_p), _ptr(self._flat_g_ext), _ptr(self.exp_avg), _ptr(self.exp_inf),
+                                                        n, _ptr(self._lr_sched), self._lr_sched.numel(), _ptr(self._gstate), cfg.betas[0],
+                                                        cfg.betas[1], cfg.eps, cfg.weight_decay, _ptr(clip), 4, _ptr(self._rmax_step),
+                                                        _ptr(self.r_max), self.r_max.numel(), s))
         finally:
             self._stream_handle = pinned
         cur.wait_stream(side)
-        return dict(graph=graph, x=x, loss=loss)
+        return dict(graph=graph, x=x, loss=loss, clip=not fused_update)
 
     def _train_step_autograd(self, x, beta, lr, gstep, b, loss_out, row_offset, philox):
         """The step for everything but fused lin|lin: method='exact' (main/train_vae.py:703-705, closed-form

@@ -40,6 +40,13 @@ def test_binding_covers_header(lib_path):
     assert lib.pvae_num_partials(0) == 0 and lib.pvae_num_partials(4096) >= 512
 
 
+def test_step_descriptor_layout_matches_the_header(lib_path):
+    import ctypes as C
+
+    from poissonvae_b200 import _lib
+    assert _lib.load().pvae_lin_step_desc_size() == C.sizeof(_lib.LinStepDesc)
+
+
 def test_argument_validation_needs_no_gpu(lib_path):
     from poissonvae_b200 import _lib
     lib = _lib.load()

@@ -132,3 +132,28 @@ def test_residual_epilogue_matches_separate_kernels(lib, shape):
     assert lib.pvae_loss_assemble(parts.data_ptr(), kl.data_ptr(), out_a.data_ptr(), M, 2.5, M, P, s) == 0
     assert lib.pvae_loss_assemble(r_ref.data_ptr(), kl.data_ptr(), out_b.data_ptr(), M, 2.5, M, 1, s) == 0
     assert torch.allclose(out_a, out_b, rtol=1e-6)
+
+
+@pytest.mark.parametrize("majors", [(1, 1), (1, 0), (0, 0), (0, 1)])
+@pytest.mark.parametrize("shape", [(4096, 512, 256), (4096, 256, 512), (256, 512, 4096), (520, 136, 100), (12, 64, 256)])
+def test_operand_planes_are_bit_identical_to_the_in_kernel_split(lib, majors, shape):
+    """pvae_gemm_tf32_planes (low parts supplied as their own planes, loaded by TMA) issues the same MMAs on the same
+    bits as precise = 1 (low parts computed per stage in shared memory): every element equal, with and without split-K."""
+    M, N, Kd = shape
+    gen = torch.Generator("cuda").manual_seed(3 * M + N + Kd)
+    _, _, A, B = operands(M, N, Kd, *majors, gen, integers=False)
+    s = torch.cuda.current_stream().cuda_stream
+    A_lo, B_lo = torch.empty_like(A), torch.empty_like(B)
+    assert lib.pvae_tf32_lo(A.data_ptr(), A_lo.data_ptr(), A.numel(), s) == 0, lib.pvae_last_error()
+    assert lib.pvae_tf32_lo(B.data_ptr(), B_lo.data_ptr(), B.numel(), s) == 0, lib.pvae_last_error()
+    hi = (A.view(torch.int32) & -8192).view(torch.float32)  # trunc_tf32: the 13 low mantissa bits cleared
+    assert torch.equal(A_lo, A - hi)
+    for splits in (1, 4) if Kd >= 256 else (1,):
+        want = run(lib, A, B, M, N, Kd, *majors, splits=splits, precise=1)
+        C = torch.full((M, N), float("nan"), device="cuda")
+        ws = torch.empty(max(1, lib.pvae_gemm_ws_floats(M, N, splits)), device="cuda")
+        rc = lib.pvae_gemm_tf32_planes(A.data_ptr(), A_lo.data_ptr(), B.data_ptr(), B_lo.data_ptr(), C.data_ptr(), M, N, Kd, *majors,
+                                       splits, ws.data_ptr(), s)
+        assert rc == 0, lib.pvae_last_error()
+        torch.cuda.synchronize()
+        assert torch.equal(C, want), splits

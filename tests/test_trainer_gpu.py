@@ -264,3 +264,44 @@ def test_graph_replay_fills_the_same_r_max_slots_and_n_exp():
     assert out[True][0] == out[False][0], out
     assert (out[True][1] > 0).all()  # every slot of the ring was written, none holds a running maximum of the epoch
     assert torch.equal(out[True][1], out[False][1])
+
+
+@pytest.mark.parametrize("bias", [False, True])
+def test_operand_planes_step_is_bit_identical(bias):
+    """The step with TF32 operand planes (low parts of x, W, z, g_y, g_h written once by their producers and loaded by
+    TMA) against the step whose GEMMs split every stage in shared memory: same parameters, optimiser state, gradients
+    and losses bit for bit - eager with the fused update, eager with stand-alone Adamax, x_lo supplied or not, after a
+    parameter edit through torch, and through graph replay."""
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
+    g = torch.Generator().manual_seed(23)
+    data = torch.randn(6, 1024, 256, generator=g).cuda()
+    out = {}
+    for mode in ("split", "planes", "planes+x_lo", "planes unfused", "planes graph"):
+        model = PoissonVAE(ConfigPoisVAE(n_latents=512, prior_clamp=-4, seed=4, enc_bias=bias)).cuda()
+        with torch.no_grad():
+            model.log_rate.add_(3.0)
+        model.update_n(25.0)
+        tr = TrainerVAE(model, ConfigTrainVAE(lr=0.01, epochs=40, batch_size=1024, temp_anneal_portion=0.0, temp_stop=0.7,
+                                              kl_anneal_portion=0.0, kl_const_portion=0.0, grad_clip=None), n_batches_per_epoch=1)
+        tr.use_planes = mode != "split"
+        tr.fuse_update = mode != "planes unfused"
+        tr.graph = mode == "planes graph"
+        torch.cuda.manual_seed(5)
+        losses = []
+        for i in range(6):
+            if i == 3:
+                with torch.no_grad():
+                    model.fc_dec.weight.mul_(1.01)  # an edit through torch: the low plane must follow
+            x_lo = tr.split_planes(data[i]) if mode == "planes+x_lo" else None
+            losses.append(tr.train_step(data[i], i, x_lo=x_lo).clone())
+        if mode == "planes graph":
+            assert len(tr._graphs) >= 1
+        out[mode] = (tr.flat_p.clone(), tr.exp_avg.clone(), tr.exp_inf.clone(), tr.flat_g.clone(), torch.stack(losses))
+        if mode != "split":
+            lo = tr.split_planes(tr.flat_p)
+            if mode != "planes unfused":  # the fused optimiser kernel keeps the low plane current by itself
+                assert torch.equal(tr.flat_p_lo, lo)
+    for mode in out:
+        for a, b in zip(out["split"], out[mode]):
+            assert torch.equal(a, b), mode
