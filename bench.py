@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no_overlap", action="store_true", help="keep the whole step on one stream (A/B)")
     ap.add_argument("--tf32", action="store_true", help="single-pass TF32 GEMMs instead of 3xTF32 (A/B)")
     ap.add_argument("--dec_splits", type=int, default=-1, help="K-splits of the decoder GEMM (A/B; default: the library's choice)")
+    ap.add_argument("--no_carveout", action="store_true", help="leave every kernel's L1 / shared-memory split at the driver default (A/B)")
     ap.add_argument("--no_planes", action="store_true", help="GEMMs split their operands per stage in shared memory instead of "
                                                               "loading the producers' TF32 low planes (A/B, same bits)")
     ap.add_argument("--no_fuse_update", action="store_true", help="keep the stand-alone gradient reductions + Adamax (A/B)")
@@ -299,6 +300,8 @@ def run_ours(args):
     lib = _lib.load()  # fails loudly if the CUDA extension has not been built
     if args.no_pdl:
         lib.pvae_set_pdl(0)
+    if args.no_carveout:
+        lib.pvae_set_carveout(0)
     if args.no_overlap:
         lib.pvae_set_step_overlap(0)
     if args.tf32:

@@ -55,6 +55,9 @@ int pvae_version(void);
 /* Programmatic dependent launch for every kernel of the library (default on): a kernel may be scheduled
  * while its predecessor in the stream drains and waits (griddepcontrol.wait) before touching its data. */
 int pvae_set_pdl(int on);
+/* Tuning knob (process-wide, default on): every kernel asks for the all-shared L1 / shared-memory split, so that an SM never
+ * re-partitions its L1 between two kernels of a step; 0 leaves the driver's per-kernel default. */
+int pvae_set_carveout(int on);
 /* Number of kernels this library has launched in this process so far (all streams, all entry points). */
 int64_t pvae_launch_count(void);
 const char* pvae_last_error(void);
@@ -247,6 +250,11 @@ int pvae_lin_step_train(const float* x, float* params, float* grads, float* exp_
 /* Tuning knob (process-wide, default on): run the decoder wgrad and the loss assembly of pvae_lin_step_fwd_bwd on
  * an internal side stream (forked from / joined back into the caller's stream with events). */
 int pvae_set_step_overlap(int on);
+/* Debugging aid (process-wide): events = HOST array of n cudaEvent_t (kept alive by the caller) recorded on the step's main
+ * stream at: 0 start, 1 after the optional x split, 2 encoder GEMM, 3 sampler forward, 4 decoder GEMM, 5 residual, 6 dgrad,
+ * 7 sampler backward, 8 encoder wgrad, 9 gradient reduction + Adamax (single-GPU paths).  Per-kernel live durations, at
+ * the price of the programmatic overlap between the kernels.  n = 0 switches it off. */
+int pvae_set_step_trace(void* const* events, int n);
 /* Tuning knob (process-wide, default on): pvae_lin_step_fwd_bwd reduces the wgrad split partials and the sampler's column
  * partials with ONE kernel instead of two split-K reductions + one or two column-sum kernels (bit-identical results). */
 int pvae_set_fuse_reduce(int on);

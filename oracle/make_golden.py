@@ -243,7 +243,7 @@ def gen_lr(ref):
     cosine starts from the LAST warm-up value, not from cfg.lr."""
     rec = {}
     cases = [("a", 0.005, 400, 0.1, 1e-5), ("b", 0.002, 90, 0.05, 1e-5), ("c", 0.002, 64, 0.0, 1e-5),
-             ("d", 0.005, 26 * 30, 0.01, 1e-5)]
+             ("d", 0.005, 26 * 30, 0.01, 1e-5), ("e", 0.005, 40, 0.01, 1e-5)]  # e: one warm-up step at lr 0 - the cosine never leaves ~0
     for tag, lr, n_iters, warmup_portion, eta_min in cases:
         w = torch.nn.Parameter(torch.zeros(3))
         optim = ref.adamax.Adamax(params=[w], lr=lr)

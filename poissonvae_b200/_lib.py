@@ -86,6 +86,7 @@ _SIGNATURES = {
     "pvae_version": (C.c_int, []),
     "pvae_last_error": (C.c_char_p, []),
     "pvae_set_pdl": (_i, [_i]),
+    "pvae_set_carveout": (_i, [_i]),
     "pvae_launch_count": (_i64, []),
     "pvae_num_partials": (_i64, [_i64]),
     "pvae_sampler_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _f, _i, _i, _f, _u64, _u64, _p, _p]),
@@ -119,6 +120,7 @@ _SIGNATURES = {
     "pvae_gemm_tf32_planes": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _i, _i, _p, _p]),
     "pvae_tf32_lo": (_i, [_p, _p, _i64, _p]),
     "pvae_set_step_overlap": (_i, [_i]),
+    "pvae_set_step_trace": (_i, [_p, _i]),
     "pvae_lin_step_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i,
                                    _u64, _u64, _p, _p, _p]),
     "pvae_conv_weight_prep": (_i, [_p] * 6 + [_i] * 7 + [_p]),

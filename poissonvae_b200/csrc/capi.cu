@@ -1,5 +1,6 @@
 // Library-level C-ABI entry points (version, error string).
 #include <atomic>
+#include <mutex>
 
 #include "pvae_host.h"
 
@@ -11,6 +12,26 @@ char* last_error_buffer() {
 static bool g_pdl = true;
 bool pdl_enabled() { return g_pdl; }
 void set_pdl(bool on) { g_pdl = on; }
+static bool g_carveout = true;
+bool carveout_enabled() { return g_carveout; }
+void prefer_shared_carveout(const void* kernel) {
+  static const void* seen[512];
+  static std::atomic<int> n_seen{0};
+  const int n = n_seen.load(std::memory_order_acquire);
+  for (int i = 0; i < n; ++i)
+    if (seen[i] == kernel) return;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  const int m = n_seen.load(std::memory_order_acquire);
+  for (int i = 0; i < m; ++i)
+    if (seen[i] == kernel) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaGetLastError();  // a hint: failure is not an error
+  if (m < 512) {
+    seen[m] = kernel;
+    n_seen.store(m + 1, std::memory_order_release);
+  }
+}
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace pvae
@@ -18,6 +39,10 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 namespace pvae { void set_pdl(bool); }
 extern "C" int pvae_set_pdl(int on) {
   pvae::set_pdl(on != 0);
+  return PVAE_OK;
+}
+extern "C" int pvae_set_carveout(int on) {
+  pvae::g_carveout = on != 0;
   return PVAE_OK;
 }
 extern "C" int pvae_version(void) { return 100; }

@@ -38,6 +38,8 @@ SideStream* side_stream() {
   return &s;
 }
 
+void* const* g_trace = nullptr;  // pvae_set_step_trace: CUDA events recorded between the main-stream launches of a step
+int g_trace_n = 0;
 int g_overlap = 1;
 int g_dec_splits = 0;   // K-splits of the decoder GEMM (pvae_set_dec_splits); 0 = automatic
 int g_fuse_reduce = 1;  // pvae_lin_step_fwd_bwd: reduce all gradient partials with one kernel (bit-identical to the three)
@@ -131,6 +133,12 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   auto mark = [&](int i) {
     if (d.events && d.events[i]) cudaEventRecord(static_cast<cudaEvent_t>(d.events[i]), s);
   };
+  int trace_i = 0;
+  auto trace = [&]() {  // debugging aid: per-kernel live durations (defeats the programmatic overlap between the kernels)
+    if (g_trace && trace_i < g_trace_n) cudaEventRecord(static_cast<cudaEvent_t>(g_trace[trace_i]), s);
+    ++trace_i;
+  };
+  trace();
   auto gemm = [&](const float* A, const float* A_lo, const float* Bm, const float* B_lo, float* C, int64_t M, int64_t N, int64_t Kd, int ak,
                   int bk, int splits, float* sws, cudaStream_t st) {
     return pvae::gemm_impl(A, planes ? A_lo : nullptr, Bm, planes ? B_lo : nullptr, C, M, N, Kd, ak, bk, precise, splits, sws, nullptr, nullptr,
@@ -142,12 +150,15 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
     if ((rc = pvae_tf32_lo(d.x, w.x_lo, B * D, s))) return rc;
     x_lo = w.x_lo;
   }
+  trace();  // 1: after the optional x split
   if ((rc = gemm(d.x, x_lo, w_enc, w_enc_lo, w.h, B, K, D, 1, 1, 1, nullptr, s))) return rc;
+  trace();  // 2: encoder GEMM
   mark(0);
   if ((rc = pvae::sampler_fwd_impl(w.h, log_r, b_enc, w.z, z_lo, nullptr, nullptr, nullptr, w.klrow, d.rate_max, w.dz, B, K, d.row_offset,
                                    d.n_exp, d.temp, d.indicator, d.exc_only, d.exit_logit, d.seed, d.offset, d.offset_dev, s)))
     return rc;
   mark(1);
+  trace();  // 3: sampler forward
   // decoder GEMM with the residual fused into its epilogue: g_y and per-tile squared errors, y itself is never stored
   int recon_parts = static_cast<int>(pvae_gemm_residual_parts(D));
   // automatic: the decoder's K loop (K / 32 blocks) is the longest serial stretch of any GEMM of the step; when two
@@ -159,7 +170,9 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   const float g_scale = 2.0f / static_cast<float>(B_global);
   if (dsp > 1) {  // split-K partials (in the not-yet-used wgrad workspace) + one kernel that sums them into the residual
     if ((rc = gemm(w.z, z_lo, w_dec, w_dec_lo, nullptr, B, D, K, 1, 1, dsp, w.ydec, s))) return rc;
+    trace();  // 4: decoder GEMM
     if ((rc = pvae::recon_parts_impl(w.ydec, dsp, d.x, w.g_y, g_y_lo, w.recon, B, D, g_scale, s))) return rc;
+    trace();  // 5: residual
     recon_parts = 1;
   } else if ((rc = pvae::gemm_impl(w.z, z_lo, w_dec, w_dec_lo, nullptr, B, D, K, 1, 1, precise, 1, nullptr, d.x, w.g_y, g_y_lo, w.recon, g_scale,
                                    64, s))) {
@@ -204,13 +217,16 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   }
   if (side && (rc = pvae::cuda_ok("join", cudaEventRecord(side->join, s2)))) return rc;
   if ((rc = gemm(w.g_y, g_y_lo, w_dec, w_dec_lo, w.g_z, B, K, D, 1, 0, 1, nullptr, s))) return rc;
+  trace();  // 6: dgrad
   mark(2);
   if ((rc = pvae::sampler_bwd_impl(w.h, log_r, b_enc, w.g_z, nullptr, w.dz, d.beta / static_cast<float>(B_global), w.g_h, g_h_lo, g_log_r,
                                    g_b_enc, w.partials, fuse ? -1 : 0, B, K, d.row_offset, d.n_exp, d.temp, d.indicator, d.exc_only,
                                    d.exit_logit, d.seed, d.offset, d.offset_dev, s)))
     return rc;
   mark(3);
+  trace();  // 7: sampler backward
   if ((rc = gemm(w.g_h, g_h_lo, d.x, x_lo, fuse ? nullptr : g_w_enc, K, D, B, 0, 0, sp_enc, w.splitk2, s))) return rc;
+  trace();  // 8: encoder wgrad
   if (dp_peer) {  // bucket 1: everything but W_dec
     if (fuse) {
       pvae_grad_segment sb[3] = {seg[0], seg[1], seg[3]};
@@ -228,8 +244,13 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   }
   if (side && (rc = pvae::cuda_ok("join", cudaStreamWaitEvent(s, side->join, 0)))) return rc;
   if (d.update == 0 && !fuse) return PVAE_OK;
-  if (!fuse) {
-    if (d.state) return fail(PVAE_ERR_UNSUPPORTED, "pvae_lin_step: device-side counters need the fused gradient reduction");
+  if (!fuse) {  // small shapes: the wgrad GEMMs did not split, the gradients are already complete in grads
+    if (d.state) {
+      if ((rc = pvae::adamax_step_dev_impl(d.params, planes ? d.params_lo : nullptr, d.grads, d.exp_avg, d.exp_inf, n, dev, d.beta1, d.beta2,
+                                           d.eps, d.weight_decay, nullptr, s)))
+        return rc;
+      return pvae::advance_state(d.state, d.philox_increment, d.rate_max, d.rmax_ring, d.ring_n, s);
+    }
     return pvae::adamax_step_impl(d.params, planes ? d.params_lo : nullptr, d.grads, d.exp_avg, d.exp_inf, n, d.lr, d.step, d.beta1, d.beta2,
                                   d.eps, d.weight_decay, nullptr, s);
   }
@@ -237,8 +258,15 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   if ((rc = pvae::adamax_from_partials_impl(upd ? d.params : nullptr, upd && planes ? d.params_lo : nullptr, d.grads, d.exp_avg, d.exp_inf, seg,
                                             has_bias ? 4 : 3, d.lr, d.step, d.beta1, d.beta2, d.eps, d.weight_decay, dev, s)))
     return rc;
+  trace();  // 9: join + gradient reduction / Adamax
   if (upd && d.state)  // graph replay: advance the device-side step counter / Philox offset, move rate.max() to its slot
     return pvae::advance_state(d.state, d.philox_increment, d.rate_max, d.rmax_ring, d.ring_n, s);
+  return PVAE_OK;
+}
+
+extern "C" int pvae_set_step_trace(void* const* events, int n) {
+  g_trace = n > 0 ? events : nullptr;
+  g_trace_n = n > 0 ? n : 0;
   return PVAE_OK;
 }
 

@@ -32,8 +32,16 @@ inline int cuda_ok(const char* what, cudaError_t e) {
 bool pdl_enabled();
 void count_launch();  // every kernel launch of this library is counted (pvae_launch_count)
 
+// Every kernel of the library asks for the same L1 / shared-memory split (all shared): an SM that has to re-partition its
+// unified L1 between two kernels must drain first, which costs microseconds per kernel boundary and keeps a dependent
+// kernel from becoming resident under its predecessor's tail.  The small kernels here stream their data once and do not
+// miss the L1.  pvae_set_carveout(0) leaves the driver's per-kernel default (A/B).
+bool carveout_enabled();
+void prefer_shared_carveout(const void* kernel);  // once per kernel (capi.cu)
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  if (carveout_enabled()) prefer_shared_carveout(reinterpret_cast<const void*>(kernel));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -68,6 +76,8 @@ int adamax_from_partials_impl(float* p, float* p_lo, float* g_out, float* exp_av
                               void* stream);
 int adamax_step_impl(float* p, float* p_lo, const float* g, float* exp_avg, float* exp_inf, int64_t n, float lr, int step, float beta1,
                      float beta2, float eps, float weight_decay, const float* clip_coef, void* stream);
+int adamax_step_dev_impl(float* p, float* p_lo, const float* g, float* exp_avg, float* exp_inf, int64_t n, const AdamaxDev& dev, float beta1,
+                         float beta2, float eps, float weight_decay, const float* clip_coef, void* stream);
 int advance_state(int* state, uint64_t philox_increment, float* rmax_step, float* rmax_ring, int ring_n, void* stream);
 
 // peer_allreduce.cu: one bucket of the peer-memory gradient exchange fused with Adamax (see pvae_allreduce_adamax)

@@ -346,19 +346,24 @@ extern "C" int pvae_tf32_lo(const float* x, float* lo, int64_t n, void* stream) 
                                             static_cast<long long>(n / 4)));
 }
 
+int pvae::adamax_step_dev_impl(float* p, float* p_lo, const float* g, float* exp_avg, float* exp_inf, int64_t n, const AdamaxDev& dev,
+                               float beta1, float beta2, float eps, float weight_decay, const float* clip_coef, void* stream) {
+  if (n <= 0 || !p || !g || !exp_avg || !exp_inf || !dev.lr_sched || dev.n_sched < 1 || !dev.state)
+    return fail(PVAE_ERR_INVALID, "pvae_adamax_step_dev: bad argument");
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((n + 255) / 256, 148ll * 8));
+  return cuda_ok("pvae_adamax_step_dev", launch_pdl(adamax_dev_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g,
+                                                    exp_avg, exp_inf, static_cast<long long>(n), dev.lr_sched, dev.n_sched, dev.state, beta1,
+                                                    beta2, eps, weight_decay, clip_coef, p_lo));
+}
+
 extern "C" int pvae_adamax_step_dev(float* p, const float* g, float* exp_avg, float* exp_inf, int64_t n, const float* lr_sched,
                                     int n_sched, int* state, float beta1, float beta2, float eps, float weight_decay,
                                     const float* clip_coef, uint64_t philox_increment, float* rmax_step, float* rmax_ring,
                                     int ring_n, void* stream) {
-  if (n <= 0 || !p || !g || !exp_avg || !exp_inf || !lr_sched || n_sched < 1 || !state)
-    return fail(PVAE_ERR_INVALID, "pvae_adamax_step_dev: bad argument");
   if (reinterpret_cast<uintptr_t>(state) & 7) return fail(PVAE_ERR_INVALID, "pvae_adamax_step_dev: state must be 8-byte aligned");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const unsigned grid = static_cast<unsigned>(std::min<long long>((n + 255) / 256, 148ll * 8));
-  if (int rc = cuda_ok("pvae_adamax_step_dev", launch_pdl(adamax_dev_kernel, dim3(grid), dim3(256), 0, s, p, g, exp_avg, exp_inf,
-                                                          static_cast<long long>(n), lr_sched, n_sched, static_cast<const int*>(state),
-                                                          beta1, beta2, eps, weight_decay, clip_coef, static_cast<float*>(nullptr))))
-    return rc;
+  AdamaxDev dev;
+  dev.lr_sched = lr_sched, dev.n_sched = n_sched, dev.state = state;
+  if (int rc = adamax_step_dev_impl(p, nullptr, g, exp_avg, exp_inf, n, dev, beta1, beta2, eps, weight_decay, clip_coef, stream)) return rc;
   return advance_state(state, philox_increment, rmax_step, rmax_ring, ring_n, stream);
 }
 
