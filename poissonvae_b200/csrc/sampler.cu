@@ -647,14 +647,317 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
   }
 }
 
+// ---- forward sampler, one resident wave of blocks, one pool per tile ------------------------------------
+// The schedule of the training forward (modes kFwdSoft / kFwdBoth).  What the per-row-tile pool above left on the table at
+// config 2 (ncu, round 1): 1366 three-row blocks over 888 resident slots = 1.54 waves (the SMs run half empty through the
+// second one: sub-partitions active 81 % of the kernel) and, inside a block, 3 quads per lane are too few to even out chains
+// of 1..8+ events (23 of 32 lanes active).  Here the grid is ONE wave (occupancy x SM count blocks, rows dealt out evenly:
+// B / grid or one more), and a block pools ALL quads of its rows - every column pass of up to kPoolCap / (K / 4) rows - so
+// that a lane keeps pulling work until the block's last quad is taken.  Stage 1 (prologue: softclamps, rate, KL) is
+// uniform and coalesced and parks the rates in shared memory; stage 2 is the refill loop of the pool path above.  Long
+// chains (more than phase_a events) are handed to phase B by entry index only: a group of 8 lanes walks such a chain again
+// from its first event, 8 events per step (the few events phase A already walked are recomputed - it keeps the parked
+// state out of shared memory: 18 KB per block instead of 49 KB).  Chain arithmetic, Philox counters and exit rules are
+// those of sampler_kernel; a quad finished by phase A is bit-identical to it, one finished by phase B is within an ulp
+// (prefix-sum arrival times from event 0 instead of from the parking point).
+constexpr int kPoolCap = 768;  // pool entries (quads) per tile
+constexpr int kPoolRows = kPoolCap / kThreads;  // rows of one column pass that fit the pool (K <= 512: 6 rows)
+
+template <int MODE, int IND, bool RAW>
+__global__ void __launch_bounds__(kThreads) sampler_pool_kernel(const SamplerParams p) {
+  __shared__ float s_rate[4][kPoolCap];
+  __shared__ unsigned short s_list[kWarps][kPoolCap];  // entries each warp handed to phase B
+  __shared__ int s_next;
+  __shared__ float s_rowsum[kPoolRows][kWarps];
+  __shared__ float s_max[kWarps];
+
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  // rows dealt out evenly over the grid: the first B % grid blocks own one row more
+  const long long base_rows = p.B / gridDim.x, extra = p.B % gridDim.x;
+  const long long blk_row0 = blockIdx.x * base_rows + min(static_cast<long long>(blockIdx.x), extra);
+  const int blk_rows = static_cast<int>(base_rows + (blockIdx.x < extra ? 1 : 0));
+  uint64_t off = p.offset;
+  if (p.offset_dev != nullptr) off += *p.offset_dev;
+  const uint32_t off_lo = static_cast<uint32_t>(off), off_hi = static_cast<uint32_t>(off >> 32);
+  const int n_a = min(p.phase_a, p.n_exp);
+  const int Kq = static_cast<int>(p.K >> 2);
+  const int npass = (Kq + kThreads - 1) / kThreads;
+  float rmax = 0.f;
+  const bool want_rowsum = !RAW && p.kl_rowsum != nullptr;
+  const unsigned lanes_below = (1u << lane) - 1u;
+  const float t_exit = p.t_exit, absorb = p.absorb;
+
+#pragma unroll 1
+  for (int tile_row = 0; tile_row < blk_rows; tile_row += p.rows_per_block) {
+    const long long row0 = blk_row0 + tile_row;
+    const int nrows = min(p.rows_per_block, blk_rows - tile_row);
+    if (tid < kPoolRows * kWarps) (&s_rowsum[0][0])[tid] = 0.f;
+    if (tid == 0) s_next = kThreads;
+    __syncthreads();
+    // ---- stage 1: prologue of every (pass, row) of the tile; entry = (pass * nrows + r) * kThreads + tid
+#pragma unroll 1
+    for (int pass = 0; pass < npass; ++pass) {
+      const int cq = pass * kThreads + tid;
+      const bool act = cq < Kq;
+      const long long k = 4ll * cq;
+      float lr[4] = {0.f, 0.f, 0.f, 0.f}, bias[4] = {0.f, 0.f, 0.f, 0.f}, elr[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!RAW && act) {
+        const float4 v = ldg4(p.log_r + k);
+        lr[0] = v.x, lr[1] = v.y, lr[2] = v.z, lr[3] = v.w;
+        if (p.b_enc != nullptr) {
+          const float4 b = ldg4(p.b_enc + k);
+          bias[0] = b.x, bias[1] = b.y, bias[2] = b.z, bias[3] = b.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) elr[j] = expf(lr[j]);
+      }
+#pragma unroll 1
+      for (int r = 0; r < nrows; ++r) {
+        float klsum = 0.f;
+        if (act) {
+          const long long gbase = (row0 + r) * p.K + k;
+          const float4 hv4 = ldg4(p.h + gbase);
+          const float hv[4] = {hv4.x, hv4.y, hv4.z, hv4.w};
+          Latent q[4];
+          float rate[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            q[j] = prologue<RAW, false>(p, hv[j], lr[j], bias[j]);
+            rate[j] = q[j].rate;
+          }
+          if (p.rate != nullptr) stg4(p.rate + gbase, make_float4(rate[0], rate[1], rate[2], rate[3]));
+          if (p.rate_max != nullptr) rmax = fmaxf(fmaxf(fmaxf(rate[0], rate[1]), fmaxf(rate[2], rate[3])), rmax);
+          if (!RAW) {
+            if (p.log_dr != nullptr) stg4(p.log_dr + gbase, make_float4(q[0].log_dr, q[1].log_dr, q[2].log_dr, q[3].log_dr));
+            if (p.kl != nullptr || p.kl_rowsum != nullptr) {
+              float klv[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float d = q[j].log_dr;
+                klv[j] = elr[j] * (1.f + expf(d) * (d - 1.f));  // main/vae.py:448-449
+              }
+              if (p.kl != nullptr) stg4(p.kl + gbase, make_float4(klv[0], klv[1], klv[2], klv[3]));
+              klsum = (klv[0] + klv[1]) + (klv[2] + klv[3]);
+            }
+          }
+          const int slot = (pass * nrows + r) * kThreads + tid;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s_rate[j][slot] = rate[j];
+        }
+        if (want_rowsum) {
+          const float sum = warp_sum(klsum);
+          if (lane == 0) s_rowsum[r][warp] += sum;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- stage 2: the tile's npass * nrows * kThreads quads form one pool (entry index == slot index); a shared
+    // cursor hands out the next entries, one atomicAdd per warp and refill round
+    const int pool_n = npass * nrows * kThreads;
+    const uint32_t quad0 = static_cast<uint32_t>(((p.row_offset + row0) * p.K) >> 2);
+    float* const z0 = p.z + row0 * p.K;
+    float* const zlo0 = p.z_lo != nullptr ? p.z_lo + row0 * p.K : nullptr;
+    float* const dz0 = MODE == kFwdBoth ? p.dz_out + row0 * p.K : nullptr;
+    int n_parked = 0;  // warp-uniform
+    // entry -> quad index relative to the tile's first quad (row r, column quad cq), or -1 for a column beyond K
+    auto locate = [&](int e) -> int {
+      const int t = e % kThreads;
+      int pr = e / kThreads, pass = 0;
+      while (pr >= nrows) pr -= nrows, ++pass;
+      const int cq = pass * kThreads + t;
+      return cq < Kq ? pr * Kq + cq : -1;
+    };
+    {
+      int cur = tid;  // this lane's pool entry
+      bool has = cur < pool_n, live = false;
+      int n = 0, ebase = 0;
+      uint32_t quad = 0;
+      float rate[4], inv_rate[4], t[4], acc[4], acc2[4];
+      auto fetch = [&]() {
+        live = false;
+        if (has) {
+          const int qi = locate(cur);
+          if (qi >= 0) {
+            live = true;
+            ebase = qi << 2;
+            quad = quad0 + static_cast<uint32_t>(qi);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              rate[j] = s_rate[j][cur];
+              inv_rate[j] = recip_for_div(rate[j]);
+              t[j] = acc[j] = acc2[j] = 0.f;
+            }
+            n = 0;
+          }
+        }
+      };
+      fetch();
+      while (__any_sync(0xffffffffu, has)) {
+        bool fin = has && !live;  // an entry beyond the last column: nothing to do
+        bool park = false;
+        if (live) {
+          const uint4 rr = philox4x32_10(quad, static_cast<uint32_t>(n), off_lo, off_hi, p.ks);
+          const uint32_t bits[4] = {rr.x, rr.y, rr.z, rr.w};
+          float excess = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float e = exponential_from_bits(bits[j]);
+            t[j] = __fadd_rn(t[j], div_by_rate<false>(e, rate[j], inv_rate[j]));
+            float f, df = 0.f;
+            soft_term<IND, MODE == kFwdBoth>(p, t[j], f, df);
+            acc[j] += f;
+            excess = fmaxf(excess, fmaf(-absorb, acc[j], f));
+            if (MODE == kFwdBoth) {
+              const float g = df * t[j];
+              acc2[j] += g;
+              excess = fmaxf(excess, fmaf(-absorb, acc2[j], g));
+            }
+          }
+          ++n;
+          const float tmin = fminf(fminf(t[0], t[1]), fminf(t[2], t[3]));
+          if (tmin > t_exit || (absorb > 0.f && tmin > 1.f && excess <= 0.f) || n >= p.n_exp) {  // chain complete
+            stg4_planes(z0, zlo0, ebase, make_float4(acc[0], acc[1], acc[2], acc[3]));
+            if (MODE == kFwdBoth) stg4(dz0 + ebase, make_float4(acc2[0], acc2[1], acc2[2], acc2[3]));
+            fin = true;
+          } else if (n >= n_a) {  // a long chain: phase B walks it again, 8 events per step
+            fin = park = true;
+          }
+        }
+        const unsigned fm = __ballot_sync(0xffffffffu, fin);
+        if (fm != 0u) {
+          const unsigned pm = __ballot_sync(0xffffffffu, park);
+          if (park) s_list[warp][n_parked + __popc(pm & lanes_below)] = static_cast<unsigned short>(cur);
+          n_parked += __popc(pm);
+          int first = 0;
+          if (lane == 0) first = atomicAdd(&s_next, __popc(fm));
+          first = __shfl_sync(0xffffffffu, first, 0);
+          if (fin) {
+            cur = first + __popc(fm & lanes_below);
+            has = cur < pool_n;
+            fetch();
+          }
+        }
+      }
+    }
+    // ---- phase B (per warp): groups of kGroup lanes, kGroup events per step, chains restarted from their first event
+    if (n_parked > 0) {
+      __syncwarp();
+      const int gl = lane % kGroup;
+      int next_free = 0;
+      bool has = false, done = true;
+      int ebase = 0, n0 = 0;
+      uint32_t quad = 0;
+      float rate[4] = {1.f, 1.f, 1.f, 1.f}, inv_rate[4] = {1.f, 1.f, 1.f, 1.f}, t0[4] = {0.f, 0.f, 0.f, 0.f};
+      float part[4] = {0.f, 0.f, 0.f, 0.f}, part2[4] = {0.f, 0.f, 0.f, 0.f};
+      while (true) {
+        if (__any_sync(0xffffffffu, done)) {
+          float tot[4], tot2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float v = part[j], v2 = part2[j];
+#pragma unroll
+            for (int o = kGroup / 2; o > 0; o >>= 1) {
+              v += __shfl_xor_sync(0xffffffffu, v, o, kGroup);
+              if (MODE == kFwdBoth) v2 += __shfl_xor_sync(0xffffffffu, v2, o, kGroup);
+            }
+            tot[j] = v;
+            if (MODE == kFwdBoth) tot2[j] = v2;
+          }
+          if (done && gl == 0 && has) {
+            stg4_planes(z0, zlo0, ebase, make_float4(tot[0], tot[1], tot[2], tot[3]));
+            if (MODE == kFwdBoth) stg4(dz0 + ebase, make_float4(tot2[0], tot2[1], tot2[2], tot2[3]));
+          }
+          int next = 0;
+          {
+            const unsigned req = __ballot_sync(0xffffffffu, done && gl == 0);
+            next = next_free + __popc(req & lanes_below);
+            next_free += __popc(req);
+          }
+          next = __shfl_sync(0xffffffffu, next, 0, kGroup);
+          if (done) {
+            has = next < n_parked;
+            if (has) {
+              const int slot = s_list[warp][next];
+              const int qi = locate(slot);
+              ebase = qi << 2;
+              quad = quad0 + static_cast<uint32_t>(qi);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                rate[j] = s_rate[j][slot];
+                inv_rate[j] = recip_for_div(rate[j]);
+                t0[j] = 0.f, part[j] = 0.f, part2[j] = 0.f;
+              }
+              n0 = 0;
+            }
+            done = false;
+          }
+          if (__all_sync(0xffffffffu, !has)) break;
+        }
+        const int n = n0 + gl;
+        const bool valid = has && !done && n < p.n_exp;
+        const uint4 rr = philox4x32_10(quad, static_cast<uint32_t>(n), off_lo, off_hi, p.ks);
+        const uint32_t bits[4] = {rr.x, rr.y, rr.z, rr.w};
+        float excess = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float x = valid ? div_by_rate<false>(exponential_from_bits(bits[j]), rate[j], inv_rate[j]) : 0.f;
+#pragma unroll
+          for (int o = 1; o < kGroup; o <<= 1) {  // inclusive prefix sum over the group's lanes
+            const float y = __shfl_up_sync(0xffffffffu, x, o, kGroup);
+            if (gl >= o) x += y;
+          }
+          const float t = t0[j] + x;
+          float f, df = 0.f;
+          soft_term<IND, MODE == kFwdBoth>(p, t, f, df);
+          const float g = df * t;
+          part[j] += valid ? f : 0.f;
+          // the group's last lane holds the smallest term of the step, its first lane the largest partial sum (a lower
+          // bound of the chain's running total)
+          excess = fmaxf(excess, fmaf(-absorb, __shfl_sync(0xffffffffu, part[j], 0, kGroup), f));
+          if (MODE == kFwdBoth) {
+            part2[j] += valid ? g : 0.f;
+            excess = fmaxf(excess, fmaf(-absorb, __shfl_sync(0xffffffffu, part2[j], 0, kGroup), g));
+          }
+          t0[j] = __shfl_sync(0xffffffffu, t, kGroup - 1, kGroup);
+        }
+        n0 += kGroup;
+        const float tmin = fminf(fminf(t0[0], t0[1]), fminf(t0[2], t0[3]));
+        const bool absorbed = absorb > 0.f && __shfl_sync(0xffffffffu, excess <= 0.f ? 1 : 0, kGroup - 1, kGroup) != 0 && tmin > 1.f;
+        if (has && (n0 >= p.n_exp || tmin > t_exit || absorbed)) done = true;
+      }
+    }
+    __syncthreads();  // the pool and the row sums are complete; the tables are reused by the next tile
+    if (want_rowsum && tid < nrows) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) sum += s_rowsum[tid][w];
+      p.kl_rowsum[row0 + tid] = sum;
+    }
+  }
+  if (p.rate_max != nullptr) {
+    const float m = warp_max(rmax);
+    if (lane == 0) s_max[warp] = m;
+    __syncthreads();
+    if (tid == 0) {
+      float mm = s_max[0];
+#pragma unroll
+      for (int w = 1; w < kWarps; ++w) mm = fmaxf(mm, s_max[w]);
+      atomicMax(reinterpret_cast<int*>(p.rate_max), __float_as_int(mm));  // rates are > 0
+    }
+  }
+}
+
 // ---- backward from a stored dz_acc: one elementwise pass ------------------------------------------
 // A block owns kSavedRows rows and all K columns; a thread owns a quad of columns and keeps every row's
 // loads in flight before it computes (9..24 independent 128-bit loads per thread), then writes its column
 // partial sums.  No chain, no RNG.
-constexpr int kSavedRows = 8;
+constexpr int kSavedRows = 4;
 
 template <bool RAW>
-__global__ void __launch_bounds__(kThreads) sampler_bwd_saved_kernel(const SamplerParams p) {
+__global__ void __launch_bounds__(kThreads, 7) sampler_bwd_saved_kernel(const SamplerParams p) {
   pdl_launch_dependents();
   pdl_wait();
   const long long row0 = static_cast<long long>(blockIdx.x) * kSavedRows;
@@ -672,32 +975,27 @@ __global__ void __launch_bounds__(kThreads) sampler_bwd_saved_kernel(const Sampl
       for (int j = 0; j < 4; ++j) elr[j] = expf(lr[j]);
     }
     const bool has_gld = !RAW && p.g_log_dr != nullptr;
-    constexpr int kChunk = 2;  // rows whose loads are in flight while the previous chunk is being computed
-    float4 hv[2][kChunk], gz[2][kChunk], dz[2][kChunk], gl[2][kChunk];
-    auto load_chunk = [&](int buf, int r0) {
+    // two rows at a time: 6 (8) independent 128-bit loads per thread in flight, at up to 32 resident warps per SM
+    float col_lr[4] = {0.f, 0.f, 0.f, 0.f}, col_b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int r0 = 0; r0 < nrows; r0 += 2) {
+      float4 hv[2], gz[2], dz[2], gl[2];
 #pragma unroll
-      for (int u = 0; u < kChunk; ++u) {
+      for (int u = 0; u < 2; ++u) {
         if (r0 + u < nrows) {
           const long long base = (row0 + r0 + u) * p.K + k;
-          hv[buf][u] = ldg4(p.h + base), gz[buf][u] = ldg4(p.g_z + base), dz[buf][u] = ldg4(p.dz_in + base);
-          gl[buf][u] = has_gld ? ldg4(p.g_log_dr + base) : make_float4(0.f, 0.f, 0.f, 0.f);
+          hv[u] = ldg4(p.h + base), gz[u] = ldg4(p.g_z + base), dz[u] = ldg4(p.dz_in + base);
+          gl[u] = has_gld ? ldg4(p.g_log_dr + base) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-    };
-    float col_lr[4] = {0.f, 0.f, 0.f, 0.f}, col_b[4] = {0.f, 0.f, 0.f, 0.f};
-    load_chunk(0, 0);
 #pragma unroll
-    for (int c = 0; c < kSavedRows / kChunk; ++c) {
-      const int buf = c & 1;
-      if ((c + 1) * kChunk < nrows) load_chunk(buf ^ 1, (c + 1) * kChunk);
-#pragma unroll
-      for (int u = 0; u < kChunk; ++u) {
-        const int r = c * kChunk + u;
-        if (r < nrows) {
-          const float h4[4] = {hv[buf][u].x, hv[buf][u].y, hv[buf][u].z, hv[buf][u].w};
-          const float g4[4] = {gz[buf][u].x, gz[buf][u].y, gz[buf][u].z, gz[buf][u].w};
-          const float d4[4] = {dz[buf][u].x, dz[buf][u].y, dz[buf][u].z, dz[buf][u].w};
-          const float l4[4] = {gl[buf][u].x, gl[buf][u].y, gl[buf][u].z, gl[buf][u].w};
+      for (int u = 0; u < 2; ++u) {
+        if (r0 + u < nrows) {
+          const long long base = (row0 + r0 + u) * p.K + k;
+          const float h4[4] = {hv[u].x, hv[u].y, hv[u].z, hv[u].w};
+          const float g4[4] = {gz[u].x, gz[u].y, gz[u].z, gz[u].w};
+          const float d4[4] = {dz[u].x, dz[u].y, dz[u].z, dz[u].w};
+          const float l4[4] = {gl[u].x, gl[u].y, gl[u].z, gl[u].w};
           float gh[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -713,7 +1011,7 @@ __global__ void __launch_bounds__(kThreads) sampler_bwd_saved_kernel(const Sampl
               col_b[j] += gh[j];
             }
           }
-          stg4_planes(p.g_h, p.g_h_lo, (row0 + r) * p.K + k, make_float4(gh[0], gh[1], gh[2], gh[3]));
+          stg4_planes(p.g_h, p.g_h_lo, base, make_float4(gh[0], gh[1], gh[2], gh[3]));
         }
       }
     }
@@ -844,35 +1142,48 @@ static int rows_per_block_for(long long B) {
   return static_cast<int>(r);
 }
 
-static int g_one_wave = 0;  // work-pool schedule: size the grid to one wave of resident blocks (A/B knob, measured slower)
+static int g_one_wave = 1;  // forward modes: the one-wave schedule (sampler_pool_kernel); 0: the per-row-tile pool of sampler_kernel
 
-// Work-pool forward.  Optional (pvae_set_pool(2)): a grid of ONE wave of resident blocks (occupancy x SM count, queried
-// once per kernel), a block owning ceil(B / resident) rows walked in equal tiles of at most kMaxRows rows.  Measured at
-// config 2: 49 us against 40 us for the plain grid of 3-row blocks - the hardware's dynamic block scheduling over 1366
-// short blocks balances the heavy-tailed work better than 1024 long ones - so it is off by default.
+// One resident wave: occupancy x SM count blocks (queried once per kernel), rows dealt out evenly in the kernel, tiles
+// of as many rows as fit the pool.
 template <typename Kern>
-static cudaError_t launch_pool(Kern kern, SamplerParams p, cudaStream_t s) {
+static cudaError_t launch_one_wave(Kern kern, SamplerParams p, cudaStream_t s) {
   static int resident = 0;  // one copy per kernel instantiation
   if (resident == 0) {
     int per_sm = 0, dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0) != cudaSuccess || per_sm < 1 || sms < 1)
-      per_sm = 4, sms = 148;
+      per_sm = 6, sms = 148;
     resident = per_sm * sms;
   }
-  if (g_one_wave) {
-    const long long rows_block = std::max<long long>(1, (p.B + resident - 1) / resident);
-    const long long ntiles = (rows_block + kMaxRows - 1) / kMaxRows;
-    p.rows_block = static_cast<int>(rows_block);
-    p.rows_per_block = static_cast<int>((rows_block + ntiles - 1) / ntiles);
-  }
+  const long long grid = std::min<long long>(resident, p.B);
+  const int npass = static_cast<int>((p.K / 4 + kThreads - 1) / kThreads);
+  const long long rows_block = (p.B + grid - 1) / grid;
+  p.rows_per_block = static_cast<int>(std::min<long long>(kPoolRows / npass, rows_block));
+  return launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(kThreads), 0, s, p);
+}
+
+template <typename Kern>
+static cudaError_t launch_pool(Kern kern, SamplerParams p, cudaStream_t s) {
   const dim3 grid(static_cast<unsigned>((p.B + p.rows_block - 1) / p.rows_block));
   return launch_pdl(kern, grid, dim3(kThreads), 0, s, p);
 }
 
 template <int MODE, bool RAW>
 static cudaError_t launch_ind(const SamplerParams& p, int indicator, dim3 grid, cudaStream_t s) {
-  if ((MODE == kFwdSoft || MODE == kFwdBoth) && p.pool) {  // work-pool schedule (forward modes)
+  if ((MODE == kFwdSoft || MODE == kFwdBoth) && p.pool && g_one_wave && p.K / 4 <= kPoolCap && p.K / 4 > 0 &&
+      kPoolRows / static_cast<int>((p.K / 4 + kThreads - 1) / kThreads) >= 1) {  // one-wave pool (forward modes)
+    constexpr int M = (MODE == kFwdSoft || MODE == kFwdBoth) ? MODE : kFwdSoft;
+    switch (indicator) {
+      case kSigmoid: return launch_one_wave(sampler_pool_kernel<M, kSigmoid, RAW>, p, s);
+      case kCosine: return launch_one_wave(sampler_pool_kernel<M, kCosine, RAW>, p, s);
+      case kLinear: return launch_one_wave(sampler_pool_kernel<M, kLinear, RAW>, p, s);
+      case kCubic: return launch_one_wave(sampler_pool_kernel<M, kCubic, RAW>, p, s);
+      case kQuintic: return launch_one_wave(sampler_pool_kernel<M, kQuintic, RAW>, p, s);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  if ((MODE == kFwdSoft || MODE == kFwdBoth) && p.pool) {  // per-row-tile pool (the previous schedule, A/B)
     constexpr int M = (MODE == kFwdSoft || MODE == kFwdBoth) ? MODE : kFwdSoft;
     switch (indicator) {
       case kSigmoid: return launch_pool(sampler_kernel<M, kSigmoid, RAW, true>, p, s);

@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(256) adamax_kernel(float* __restrict__ p, cons
 // partials (in the order the stand-alone reductions use, so the result is bit-identical), stores the gradient and
 // applies the update.  blockDim = (32, 32).
 constexpr int kMaxSegments = 8;
+constexpr int kDenseRows = 8;  // rows of the 32 x 32 block that work on a dense segment (256 threads x 4 elements)
 struct SegTable {
   long long offset[kMaxSegments], length[kMaxSegments], stride[kMaxSegments];
   const float* partials[kMaxSegments];
@@ -191,8 +192,11 @@ __global__ void __launch_bounds__(1024) adamax_partials_kernel(const __grid_cons
     }
     return;
   }
-  // dense split-K partials (n_partials, stride): the sum of splitk_reduce_kernel (gemm_tc.cu), four elements per thread
-  const long long i4 = static_cast<long long>(blk) * 1024 + ty * 32 + tx;
+  // dense split-K partials (n_partials, stride): the sum of splitk_reduce_kernel (gemm_tc.cu), four elements per thread;
+  // only the first kDenseRows rows of the block's 32 x 32 threads work, so that a weight matrix spreads over 4x as many
+  // blocks (128 instead of 32 for 131072 elements: the kernel is latency-bound, it needs the SMs, not the threads)
+  if (ty >= kDenseRows) return;
+  const long long i4 = static_cast<long long>(blk) * (32 * kDenseRows) + ty * 32 + tx;
   if (4 * i4 >= len) return;
   const int splits = t.n_partials[seg];
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -320,7 +324,7 @@ int pvae::adamax_from_partials_impl(float* p, float* p_lo, float* g_out, float* 
     if (g.columnar && !g.partials) return fail(PVAE_ERR_INVALID, "pvae_adamax_from_partials: a columnar segment needs partials");
     t.offset[i] = g.offset, t.length[i] = g.length, t.stride[i] = g.stride, t.partials[i] = g.partials;
     t.n_partials[i] = g.n_partials, t.columnar[i] = g.columnar, t.first_block[i] = blocks;
-    blocks += static_cast<int>(g.columnar ? (g.length + 31) / 32 : (g.length / 4 + 1023) / 1024);
+    blocks += static_cast<int>(g.columnar ? (g.length + 31) / 32 : (g.length / 4 + 32 * kDenseRows - 1) / (32 * kDenseRows));
   }
   t.first_block[n_segs] = blocks;
   const double bias_correction = 1.0 - pow(static_cast<double>(beta1), step);  // base/adamax.py:75-76

@@ -389,28 +389,38 @@ def test_baseline_configs_4_and_5_sampler_path(lib, cfg):
     assert torch.equal(out["z"], (torch.cumsum(-torch.log(U) / out["rate"], 0) <= 1).sum(0).float())
 
 
-@pytest.mark.parametrize("K", [512, 520, 96])
+@pytest.mark.parametrize("K", [512, 520, 96, 1024])
 def test_work_pool_schedule_is_bit_identical(lib, K):
-    """Forward sampler: the per-warp work pool (lanes take the next quad the moment theirs ends) and the row-by-row
-    lock-step schedule walk every chain with the same arithmetic: every output is bit-identical, for rates from tiny
-    to the clamp, ragged K, several phase-A caps and both forward modes (z only; z + dz_acc)."""
+    """Forward sampler schedules: row-by-row lock step (0), the per-row-tile work pool (1) and the one-wave pool
+    (2, default: one resident wave of blocks, all quads of a block's rows in one pool) walk every chain with the same
+    arithmetic.  Every output is bit-identical between 0 and 1, and between them and 2 for every quad phase A finishes
+    (all of them when the cap exceeds n_exp); a chain the one-wave schedule hands to phase B is walked again from its
+    first event by a lane group (prefix-sum arrival times), which may move the last bit of the running sums.  Rates
+    from tiny to the clamp, ragged K, several phase-A caps and both forward modes (z only; z + dz_acc)."""
+    from tests.helpers import assert_ulp
     rng = np.random.default_rng(5)
     B, n_exp, seed, offset = 50, 120, 11, 4
     h = dev(rng.normal(0.0, 2.0, size=(B, K)).astype(np.float32))
     log_r = dev(rng.uniform(-6, 2, size=K).astype(np.float32))
+    names = ("z", "dz", "log_dr", "rate", "kl", "kl_rowsum", "rate_max")
     try:
         for cap in (8, 2, 200):
             assert lib.pvae_set_phase_a_events(cap) == 0
             for temp in (1.0, 0.1):
-                outs = []
+                outs = {}
                 for pool in (1, 0, 2):
                     assert lib.pvae_set_pool(pool) == 0
                     o = fused_fwd(lib, h, log_r, None, n_exp, temp, "sigmoid", False, seed, offset)
                     zs = rsample(lib, h, n_exp, temp, "cubic", seed, offset, clamp=5.0)  # z-only mode, another indicator
-                    outs.append([o[k] for k in ("z", "dz", "log_dr", "rate", "kl", "kl_rowsum", "rate_max")] + [zs])
-                for other in outs[1:]:
-                    for a, b in zip(outs[0], other):
-                        assert torch.equal(a, b)
+                    outs[pool] = dict({k: o[k] for k in names}, zs=zs)
+                for k in outs[1]:
+                    assert torch.equal(outs[1][k], outs[0][k]), (k, cap, temp)
+                    if cap >= n_exp or k not in ("z", "dz", "zs"):
+                        assert torch.equal(outs[1][k], outs[2][k]), (k, cap, temp)
+                    else:
+                        a, b = outs[2][k].cpu().numpy(), outs[1][k].cpu().numpy()
+                        assert_ulp(a, b, max_ulp=4, what=f"{k} one-wave vs tile pool, cap {cap}")
+                        assert (a != b).mean() < 0.5
     finally:
-        lib.pvae_set_pool(1)
+        lib.pvae_set_pool(2)
         lib.pvae_set_phase_a_events(8)

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--tf32", action="store_true")
     ap.add_argument("--no_overlap", action="store_true")
     ap.add_argument("--no_carveout", action="store_true")
+    ap.add_argument("--pool", type=int, default=2, help="forward sampler schedule: 0 row by row, 1 per-row-tile pool, 2 one-wave pool")
     a = ap.parse_args()
     from poissonvae_b200 import _lib, linear
     from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
@@ -38,6 +39,7 @@ def main():
         lib.pvae_set_step_overlap(0)
     if a.no_carveout:
         lib.pvae_set_carveout(0)
+    lib.pvae_set_pool(a.pool)
     B, K = a.batch, a.latents
     model = PoissonVAE(ConfigPoisVAE(n_latents=K, prior_clamp=-4, seed=0)).cuda()
     model.n_exp.fill_(263)
@@ -73,7 +75,7 @@ def main():
         torch.cuda.synchronize()
         for j in range(n - 1):
             tot[j] += evs[j].elapsed_time(evs[j + 1]) * 1e3
-    print(f"B={B} K={K} planes={tr.planes} tf32={a.tf32}: step {plain:.1f} us untraced; traced per kernel (us):")
+    print(f"B={B} K={K} planes={tr.planes} tf32={a.tf32} pool={a.pool} carveout={not a.no_carveout} temp={a.temp}: step {plain:.1f} us untraced; traced per kernel (us):")
     for j, name in enumerate(NAMES):
         print(f"  {name:26s} {tot[j] / a.steps:7.2f}")
     print(f"  {'sum':26s} {sum(tot) / a.steps:7.2f}")
