@@ -186,6 +186,11 @@ typedef struct pvae_grad_segment {
   int n_partials;
   int columnar;
   int64_t stride;
+  /* columnar segments only, optional (NULL): a second set of n_partials2 row partials whose column sums are added with
+   * weight scale2 (the KL part of g_log_r: per-block KL column sums the forward sampler left, times beta / B) */
+  const float* partials2;
+  int n_partials2;
+  float scale2;
 } pvae_grad_segment;
 int pvae_adamax_from_partials(float* p, float* g_out, float* exp_avg, float* exp_inf, const pvae_grad_segment* segs, int n_segs,
                               float lr, int step, float beta1, float beta2, float eps, float weight_decay, void* stream);
@@ -455,8 +460,10 @@ int pvae_set_phase_a_events(int n);
 int pvae_set_absorb_exit(int on);
 /* Tuning knob (process-wide, default on): forward sampler schedule.  1: every lane of a warp takes the next quad of the
  * warp's rows x 32 pool the moment its own chain ends (work-efficient under heavy-tailed chain lengths); 0: one row at a
- * time in lock step; 2: the pool on a grid of exactly one wave of resident blocks, each walking several row tiles (A/B:
- * measured slower).  Results are bit-identical. */
+ * time in lock step - bit-identical results; 2: one resident wave of blocks, every block pooling all quads of its rows
+ * (sampler_pool_kernel; measured 39.2 vs 41.2 us at config 2).  Its long chains are walked again from their first event
+ * by a lane group, so a chain that exceeds the phase-A cap may differ from schedules 0 / 1 in the last bits (~1e-6
+ * relative) and its sum is no longer independent of where the chain exits: opt-in. */
 int pvae_set_pool(int on);
 /* Tuning knob (process-wide): rows (samples) per thread block of the sampler kernels, 1..4; 0 = automatic.
  * Changes pvae_num_partials(); results of the forward are unaffected. */

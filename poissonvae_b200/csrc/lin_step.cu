@@ -47,6 +47,7 @@ int g_fuse_reduce = 1;  // pvae_lin_step_fwd_bwd: reduce all gradient partials w
 struct Ws {
   float *h, *z, *dz, *y, *g_y, *g_z, *g_h, *recon, *klrow, *partials, *splitk, *splitk2, *ydec;
   float *z_lo, *g_y_lo, *g_h_lo, *x_lo;  // TF32 low planes of the GEMM operands the step produces
+  float *c_ddr, *c_ck, *klcol;           // the forward sampler's coefficients for the streaming backward (dz holds A)
   int64_t total;
 };
 
@@ -74,6 +75,7 @@ Ws carve(float* base, int64_t B, int64_t K, int64_t D) {
   w.splitk2 = take(s2);  // ... the encoder wgrad
   w.ydec = take(8 * B * D);  // split-K partials of the decoder output (pvae_set_dec_splits, at most 8)
   w.z_lo = take(B * K), w.g_y_lo = take(B * D), w.g_h_lo = take(B * K), w.x_lo = take(B * D);
+  w.c_ddr = take(B * K), w.c_ck = take(B * K), w.klcol = take(pvae_num_partials(B) * K);
   w.total = o;
   return w;
 }
@@ -154,8 +156,10 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   if ((rc = gemm(d.x, x_lo, w_enc, w_enc_lo, w.h, B, K, D, 1, 1, 1, nullptr, s))) return rc;
   trace();  // 2: encoder GEMM
   mark(0);
-  if ((rc = pvae::sampler_fwd_impl(w.h, log_r, b_enc, w.z, z_lo, nullptr, nullptr, nullptr, w.klrow, d.rate_max, w.dz, B, K, d.row_offset,
-                                   d.n_exp, d.temp, d.indicator, d.exc_only, d.exit_logit, d.seed, d.offset, d.offset_dev, s)))
+  // coefficient mode: the forward leaves d z / d u, the clamp derivative and the KL gradient term per latent and the KL's
+  // column sums per block, so that the backward is a streaming kernel instead of a second evaluation of the prologue
+  if ((rc = pvae::sampler_fwd_coef_impl(w.h, log_r, b_enc, w.z, z_lo, w.klrow, d.rate_max, w.dz, w.c_ddr, w.c_ck, w.klcol, B, K, d.row_offset,
+                                        d.n_exp, d.temp, d.indicator, d.exc_only, d.exit_logit, d.seed, d.offset, d.offset_dev, s)))
     return rc;
   mark(1);
   trace();  // 3: sampler forward
@@ -194,12 +198,13 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   const int sp_dec = wgrad_splits(D, K, B), sp_enc = wgrad_splits(K, D, B);
   const bool fuse = (d.update >= 1 || g_fuse_reduce) && sp_dec > 1 && sp_enc > 1;
   if ((rc = gemm(w.g_y, g_y_lo, w.z, z_lo, fuse ? nullptr : g_w_dec, D, K, B, 0, 0, sp_dec, w.splitk, s2))) return rc;
-  const int prow = static_cast<int>(pvae_sampler_bwd_partial_rows(B));
-  pvae_grad_segment seg[4];
-  seg[0] = pvae_grad_segment{0, K, w.partials, prow, 1, K};
-  seg[1] = pvae_grad_segment{K, K * D, w.splitk2, pvae_gemm_effective_splits(B, sp_enc), 0, K * D};
-  seg[2] = pvae_grad_segment{K + K * D, D * K, w.splitk, pvae_gemm_effective_splits(B, sp_dec), 0, D * K};
-  if (has_bias) seg[3] = pvae_grad_segment{K + 2 * K * D, K, w.partials + pvae_sampler_bwd_bias_offset_rows(B) * K, prow, 1, K};
+  const int prow = static_cast<int>(pvae::sampler_bwd_coef_rows(B));
+  pvae_grad_segment seg[4] = {};
+  // g_log_r = sum_b g_u (the backward's column partials) + beta / B_global * sum_b kl (the forward's per-block column sums)
+  seg[0] = pvae_grad_segment{0, K, w.partials, prow, 1, K, w.klcol, static_cast<int>(pvae_num_partials(B)), d.beta / static_cast<float>(B_global)};
+  seg[1] = pvae_grad_segment{K, K * D, w.splitk2, pvae_gemm_effective_splits(B, sp_enc), 0, K * D, nullptr, 0, 0.f};
+  seg[2] = pvae_grad_segment{K + K * D, D * K, w.splitk, pvae_gemm_effective_splits(B, sp_dec), 0, D * K, nullptr, 0, 0.f};
+  if (has_bias) seg[3] = pvae_grad_segment{K + 2 * K * D, K, w.partials + static_cast<int64_t>(prow) * K, prow, 1, K, nullptr, 0, 0.f};
   pvae::AdamaxDev dev;
   dev.lr_sched = d.lr_sched, dev.n_sched = d.n_sched, dev.state = d.state;
   if (dp_peer) {
@@ -219,9 +224,9 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   if ((rc = gemm(w.g_y, g_y_lo, w_dec, w_dec_lo, w.g_z, B, K, D, 1, 0, 1, nullptr, s))) return rc;
   trace();  // 6: dgrad
   mark(2);
-  if ((rc = pvae::sampler_bwd_impl(w.h, log_r, b_enc, w.g_z, nullptr, w.dz, d.beta / static_cast<float>(B_global), w.g_h, g_h_lo, g_log_r,
-                                   g_b_enc, w.partials, fuse ? -1 : 0, B, K, d.row_offset, d.n_exp, d.temp, d.indicator, d.exc_only,
-                                   d.exit_logit, d.seed, d.offset, d.offset_dev, s)))
+  const float kl_scale = d.beta / static_cast<float>(B_global);
+  if ((rc = pvae::sampler_bwd_coef_impl(w.g_z, w.dz, w.c_ddr, w.c_ck, kl_scale, w.g_h, g_h_lo, w.partials, has_bias, w.klcol,
+                                        pvae_num_partials(B), fuse ? nullptr : g_log_r, g_b_enc, B, K, s)))
     return rc;
   mark(3);
   trace();  // 7: sampler backward

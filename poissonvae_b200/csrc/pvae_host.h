@@ -63,6 +63,14 @@ int sampler_bwd_impl(const float* h, const float* log_r, const float* b_enc, con
                      float kl_scale, float* g_h, float* g_h_lo, float* g_log_r, float* g_b_enc, float* partial_ws, int accumulate,
                      int64_t B, int64_t K, int64_t row_offset, int n_exp, float temp, int indicator, int exc_only, float exit_logit,
                      uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream);
+int sampler_fwd_coef_impl(const float* h, const float* log_r, const float* b_enc, float* z, float* z_lo, float* kl_rowsum, float* rate_max,
+                          float* c_a, float* c_ddr, float* c_ck, float* klcol, int64_t B, int64_t K, int64_t row_offset, int n_exp, float temp,
+                          int indicator, int exc_only, float exit_logit, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                          void* stream);
+int sampler_bwd_coef_impl(const float* g_z, const float* c_a, const float* c_ddr, const float* c_ck, float kl_scale, float* g_h,
+                          float* g_h_lo, float* partial_ws, int want_bias, const float* klcol, int64_t klcol_rows, float* g_log_r,
+                          float* g_b_enc, int64_t B, int64_t K, void* stream);
+int64_t sampler_bwd_coef_rows(int64_t B);  // rows of column partials sampler_bwd_coef_impl writes
 // step.cu
 int recon_parts_impl(const float* y_parts, int n_parts, const float* x, float* g_y, float* g_y_lo, float* recon, int64_t B, int64_t D,
                      float g_scale, void* stream);

@@ -33,7 +33,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kColsPerPass = 4 * kThreads;  // latents of one row a block covers per pass
 constexpr int kMaxRows = 3;                 // rows per block tile
 constexpr int kSlots = kMaxRows * kThreads; // parked-quad table: one slot per (row, thread)
-constexpr int kSlotWords = 16;              // rate[4], t[4], acc[4], acc2[4] (one shared-memory plane per word)
+constexpr int kSlotWords = 20;              // rate[4], t[4], acc[4], acc2[4], cf[4] (one shared-memory plane per word)
 
 // kFwdSoft: z only.  kFwdBoth: z and dz_acc = sum_n f'(l_n) t_n in one walk of the chain (training forward).
 // kBwd: backward that recomputes the chain from the Philox counters.  kBwdSaved: backward from a stored dz_acc.
@@ -50,6 +50,15 @@ struct SamplerParams {
   float* z;
   float* z_lo;            // (B,K) optional: z - trunc_tf32(z), the low plane the decoder / wgrad GEMMs load by TMA
   float* g_h_lo;          // (B,K) optional, backward: the same for g_h (encoder wgrad)
+  // Coefficient mode of the training forward (kFwdBoth, all three non-null): the forward leaves in dz_out, instead of the
+  // raw sum_n f'(l_n) t_n, the finished factor A = d z / d u (that sum times exp(lambda) / (temp rate) times the rate clamp's
+  // derivative), in c_ddr the encoder clamp's derivative d delta / d h and in c_ck the KL term e^{log_r} delta e^{delta};
+  // klcol receives per-block column sums of the KL (P,K).  The backward is then four loads and a handful of FMAs per latent
+  // (sampler_bwd_coef_kernel) instead of a second evaluation of the prologue (~125 instructions, 16 of them MUFU).
+  float* c_ddr;
+  float* c_ck;
+  float* klcol;
+  const float* c_a;       // backward (coef kernel): A
   float* log_dr;
   float* rate;
   float* kl;
@@ -203,6 +212,11 @@ __device__ __forceinline__ Latent prologue(const SamplerParams& p, float hv, flo
   return q;
 }
 
+// d z / d u = (sum_n f'(l_n) t_n) * coef_factor: 1 / temp, exp(lambda) / rate (= 1 - eps / rate), and the rate clamp's derivative
+__device__ __forceinline__ float coef_factor(const SamplerParams& p, const Latent& q) {
+  return p.inv_temp * (q.explam * recip_for_div(q.rate)) * q.d_rate;
+}
+
 template <int MODE, int IND, bool RAW, bool POOL = false>
 __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p) {
   __shared__ float s_tab[kSlotWords][kSlots];  // parked quads, one word-plane per field
@@ -225,6 +239,8 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
   const int n_a = min(p.phase_a, p.n_exp);
 
   constexpr bool kIsBwd = MODE == kBwd || MODE == kBwdSaved;
+  constexpr bool kCoef = MODE == kFwdBoth && !RAW;  // coefficient mode exists for the training forward only
+  const bool coef = kCoef && p.c_ddr != nullptr;
   float rmax = 0.f;
   const bool want_rowsum = !kIsBwd && !RAW && p.kl_rowsum != nullptr;
   const unsigned lanes_below = (1u << lane) - 1u;
@@ -252,6 +268,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
       for (int j = 0; j < 4; ++j) elr[j] = expf(lr[j]);
     }
     float col_lr[4] = {0.f, 0.f, 0.f, 0.f}, col_b[4] = {0.f, 0.f, 0.f, 0.f};
+    float col_kl[4] = {0.f, 0.f, 0.f, 0.f};  // coefficient mode: this thread's KL column sums over the tile's rows
     unsigned parked = 0;  // bit r: this thread's quad of row r waits for phase B
 
     // backward epilogue of one quad: gradients from acc = sum_n f'(l_n) t_n
@@ -300,26 +317,36 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
           float rate[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            q[j] = prologue<RAW, false>(p, hv[j], lr[j], bias[j]);
+            q[j] = kCoef ? prologue<RAW, true>(p, hv[j], lr[j], bias[j]) : prologue<RAW, false>(p, hv[j], lr[j], bias[j]);
             rate[j] = q[j].rate;
           }
           if (p.rate != nullptr) stg4(p.rate + base, make_float4(rate[0], rate[1], rate[2], rate[3]));
           if (p.rate_max != nullptr) rmax = fmaxf(fmaxf(fmaxf(rate[0], rate[1]), fmaxf(rate[2], rate[3])), rmax);
+          const int slot = r * kThreads + tid;
           if (!RAW) {
             if (p.log_dr != nullptr)
               stg4(p.log_dr + base, make_float4(q[0].log_dr, q[1].log_dr, q[2].log_dr, q[3].log_dr));
-            if (p.kl != nullptr || p.kl_rowsum != nullptr) {
-              float klv[4];
+            if (p.kl != nullptr || p.kl_rowsum != nullptr || coef) {
+              float klv[4], ck[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float d = q[j].log_dr;
-                klv[j] = elr[j] * (1.f + expf(d) * (d - 1.f));  // main/vae.py:448-449
+                const float d = q[j].log_dr, ed = expf(d);
+                klv[j] = elr[j] * (1.f + ed * (d - 1.f));  // main/vae.py:448-449
+                ck[j] = elr[j] * d * ed;                   // d kl / d delta
               }
               if (p.kl != nullptr) stg4(p.kl + base, make_float4(klv[0], klv[1], klv[2], klv[3]));
               klsum = (klv[0] + klv[1]) + (klv[2] + klv[3]);
+              if (kCoef && coef) {
+                stg4(p.c_ck + base, make_float4(ck[0], ck[1], ck[2], ck[3]));
+                stg4(p.c_ddr + base, make_float4(q[0].d_dr, q[1].d_dr, q[2].d_dr, q[3].d_dr));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  col_kl[j] += klv[j];
+                  s_tab[16 + j][slot] = coef_factor(p, q[j]);
+                }
+              }
             }
           }
-          const int slot = r * kThreads + tid;
 #pragma unroll
           for (int j = 0; j < 4; ++j) s_tab[j][slot] = rate[j];
         }
@@ -388,7 +415,13 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
           const float tmin = fminf(fminf(t[0], t[1]), fminf(t[2], t[3]));
           if (tmin > t_exit || (absorb > 0.f && tmin > 1.f && excess <= 0.f) || n >= p.n_exp) {  // chain complete
             stg4_planes(z0, zlo0, ebase, make_float4(acc[0], acc[1], acc[2], acc[3]));
-            if (MODE == kFwdBoth) stg4(dz0 + ebase, make_float4(acc2[0], acc2[1], acc2[2], acc2[3]));
+            if (MODE == kFwdBoth) {
+              if (kCoef && coef) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc2[j] *= s_tab[16 + j][cur];
+              }
+              stg4(dz0 + ebase, make_float4(acc2[0], acc2[1], acc2[2], acc2[3]));
+            }
             fin = true;
           } else if (n >= n_a) {  // a long chain: hand it to phase B
 #pragma unroll
@@ -427,11 +460,13 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
         const float hv[4] = {hv4.x, hv4.y, hv4.z, hv4.w};
         Latent q[4];
         float rate[4], inv_rate[4];
+        float cf[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          q[j] = prologue<RAW, kIsBwd>(p, hv[j], lr[j], bias[j]);
+          q[j] = (kIsBwd || kCoef) ? prologue<RAW, true>(p, hv[j], lr[j], bias[j]) : prologue<RAW, false>(p, hv[j], lr[j], bias[j]);
           rate[j] = q[j].rate;
           inv_rate[j] = MODE == kBwdSaved ? 0.f : (MODE == kFwdHard ? 0.f : recip_for_div(rate[j]));
+          if (kCoef && coef) cf[j] = coef_factor(p, q[j]);
         }
         if (!kIsBwd) {  // outputs that do not depend on the chain
           if (p.rate != nullptr) stg4(p.rate + base, make_float4(rate[0], rate[1], rate[2], rate[3]));
@@ -439,15 +474,22 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
           if (!RAW) {
             if (p.log_dr != nullptr)
               stg4(p.log_dr + base, make_float4(q[0].log_dr, q[1].log_dr, q[2].log_dr, q[3].log_dr));
-            if (p.kl != nullptr || p.kl_rowsum != nullptr) {
-              float klv[4];
+            if (p.kl != nullptr || p.kl_rowsum != nullptr || coef) {
+              float klv[4], ck[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float d = q[j].log_dr;
-                klv[j] = elr[j] * (1.f + expf(d) * (d - 1.f));  // main/vae.py:448-449
+                const float d = q[j].log_dr, ed = expf(d);
+                klv[j] = elr[j] * (1.f + ed * (d - 1.f));  // main/vae.py:448-449
+                ck[j] = elr[j] * d * ed;
               }
               if (p.kl != nullptr) stg4(p.kl + base, make_float4(klv[0], klv[1], klv[2], klv[3]));
               klsum = (klv[0] + klv[1]) + (klv[2] + klv[3]);
+              if (kCoef && coef) {
+                stg4(p.c_ck + base, make_float4(ck[0], ck[1], ck[2], ck[3]));
+                stg4(p.c_ddr + base, make_float4(q[0].d_dr, q[1].d_dr, q[2].d_dr, q[3].d_dr));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) col_kl[j] += klv[j];
+              }
             }
           }
         }
@@ -465,7 +507,8 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
             bwd_finish(base, q, acc);
           } else {
             stg4_planes(p.z, p.z_lo, base, make_float4(acc[0], acc[1], acc[2], acc[3]));
-            if (MODE == kFwdBoth) stg4(p.dz_out + base, make_float4(acc2[0], acc2[1], acc2[2], acc2[3]));
+            if (MODE == kFwdBoth)
+              stg4(p.dz_out + base, make_float4(acc2[0] * cf[0], acc2[1] * cf[1], acc2[2] * cf[2], acc2[3] * cf[3]));
           }
         } else {
           const int slot = r * kThreads + tid;
@@ -475,6 +518,7 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
             s_tab[4 + j][slot] = t[j];
             s_tab[8 + j][slot] = acc[j];
             if (MODE == kFwdBoth) s_tab[12 + j][slot] = acc2[j];
+            if (kCoef) s_tab[16 + j][slot] = cf[j];
           }
           park = true;
           parked |= 1u << r;
@@ -529,7 +573,13 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
                 const int r = slot / kThreads, owner = slot % kThreads;
                 const long long base = (row0 + r) * p.K + k0 + 4 * owner;
                 stg4_planes(p.z, p.z_lo, base, make_float4(tot[0], tot[1], tot[2], tot[3]));
-                if (MODE == kFwdBoth) stg4(p.dz_out + base, make_float4(tot2[0], tot2[1], tot2[2], tot2[3]));
+                if (MODE == kFwdBoth) {
+                  if (kCoef && coef) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) tot2[j] *= s_tab[16 + j][slot];
+                  }
+                  stg4(p.dz_out + base, make_float4(tot2[0], tot2[1], tot2[2], tot2[3]));
+                }
               }
             }
           }
@@ -617,6 +667,10 @@ __global__ void __launch_bounds__(kThreads) sampler_kernel(const SamplerParams p
         stg4(p.part_log_r + pbase, make_float4(col_lr[0], col_lr[1], col_lr[2], col_lr[3]));
         if (p.part_b != nullptr) stg4(p.part_b + pbase, make_float4(col_b[0], col_b[1], col_b[2], col_b[3]));
       }
+    }
+    if (kCoef && coef && act) {  // this block tile's KL column sums (rows in order: deterministic)
+      const long long tile = static_cast<long long>(blockIdx.x) * ((p.rows_block + p.rows_per_block - 1) / p.rows_per_block) + tile_row / p.rows_per_block;
+      stg4(p.klcol + tile * p.K + k, make_float4(col_kl[0], col_kl[1], col_kl[2], col_kl[3]));
     }
     if (POOL) __syncthreads(); else __syncwarp();  // the slots are reused by the next pass
   }
@@ -1023,12 +1077,51 @@ __global__ void __launch_bounds__(kThreads, 7) sampler_bwd_saved_kernel(const Sa
   }
 }
 
+// ---- backward from the forward's coefficients (coefficient mode): pure streaming ------------------------------
+//   g_u = g_z A;  g_h = (g_u + kl_scale c_ck) c_ddr;  column partials: sum_b g_u (-> g_log_r, the KL part comes from the
+//   forward's klcol sums) and sum_b g_h (-> g_b_enc).  A block owns kCoefRows rows and all K columns.
+constexpr int kCoefRows = 4;
+__global__ void __launch_bounds__(kThreads, 8) sampler_bwd_coef_kernel(const SamplerParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long row0 = static_cast<long long>(blockIdx.x) * kCoefRows;
+  const int nrows = static_cast<int>(min(static_cast<long long>(kCoefRows), p.B - row0));
+  for (long long k = 4 * threadIdx.x; k < p.K; k += kColsPerPass) {
+    float4 col_lr = make_float4(0.f, 0.f, 0.f, 0.f), col_b = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r0 = 0; r0 < kCoefRows; r0 += 2) {  // two rows (eight 128-bit loads) in flight per thread, 32 warps per SM
+      float4 gz[2], a[2], dd[2], ck[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (r0 + u < nrows) {
+          const long long base = (row0 + r0 + u) * p.K + k;
+          gz[u] = ldg4(p.g_z + base), a[u] = ldg4(p.c_a + base), dd[u] = ldg4(p.c_ddr + base), ck[u] = ldg4(p.c_ck + base);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (r0 + u < nrows) {
+          const float4 gu = make_float4(gz[u].x * a[u].x, gz[u].y * a[u].y, gz[u].z * a[u].z, gz[u].w * a[u].w);
+          const float4 gh = make_float4(fmaf(p.kl_scale, ck[u].x, gu.x) * dd[u].x, fmaf(p.kl_scale, ck[u].y, gu.y) * dd[u].y,
+                                        fmaf(p.kl_scale, ck[u].z, gu.z) * dd[u].z, fmaf(p.kl_scale, ck[u].w, gu.w) * dd[u].w);
+          col_lr.x += gu.x, col_lr.y += gu.y, col_lr.z += gu.z, col_lr.w += gu.w;
+          col_b.x += gh.x, col_b.y += gh.y, col_b.z += gh.z, col_b.w += gh.w;
+          stg4_planes(p.g_h, p.g_h_lo, (row0 + r0 + u) * p.K + k, gh);
+        }
+      }
+    }
+    const long long pbase = static_cast<long long>(blockIdx.x) * p.K + k;
+    stg4(p.part_log_r + pbase, col_lr);
+    if (p.part_b != nullptr) stg4(p.part_b + pbase, col_b);
+  }
+}
+
 // ---- fixed-order column reduction of the (P,K) partials ----------------------------------------
 // One block per 32 columns; 32 row-lanes each keep four independent running sums (rows ty + 32 * (4i + u)),
 // then a fixed-order combine through shared memory.  Deterministic for a given P.
 constexpr int kRedX = 32, kRedY = 32;
 __global__ void __launch_bounds__(kRedX* kRedY) colsum_finalize_kernel(const float* __restrict__ part, float* __restrict__ out,
-                                                                      long long P, long long K, int accumulate) {
+                                                                      long long P, long long K, int accumulate, float scale) {
   __shared__ float s[kRedY][kRedX + 1];
   pdl_launch_dependents();
   pdl_wait();
@@ -1051,7 +1144,7 @@ __global__ void __launch_bounds__(kRedX* kRedY) colsum_finalize_kernel(const flo
     float v = s[0][tx];
 #pragma unroll
     for (int y = 1; y < kRedY; ++y) v += s[y][tx];
-    out[k] = accumulate ? out[k] + v : v;
+    out[k] = accumulate ? fmaf(scale, v, out[k]) : (scale == 1.f ? v : scale * v);
   }
 }
 
@@ -1142,7 +1235,7 @@ static int rows_per_block_for(long long B) {
   return static_cast<int>(r);
 }
 
-static int g_one_wave = 1;  // forward modes: the one-wave schedule (sampler_pool_kernel); 0: the per-row-tile pool of sampler_kernel
+static int g_one_wave = 0;  // forward modes: 1 = the one-wave schedule (sampler_pool_kernel, pvae_set_pool(2)); 0 = the per-row-tile pool of sampler_kernel
 
 // One resident wave: occupancy x SM count blocks (queried once per kernel), rows dealt out evenly in the kernel, tiles
 // of as many rows as fit the pool.
@@ -1246,9 +1339,9 @@ static int check_common(const char* fn, long long B, long long K, long long row_
   return PVAE_OK;
 }
 
-static int finalize_cols(const float* part, float* out, long long P, long long K, int accumulate, cudaStream_t s) {
+static int finalize_cols(const float* part, float* out, long long P, long long K, int accumulate, cudaStream_t s, float scale = 1.f) {
   dim3 grid(static_cast<unsigned>((K + kRedX - 1) / kRedX)), block(kRedX, kRedY);
-  return cuda_ok("colsum_finalize", launch_pdl(colsum_finalize_kernel, grid, block, 0, s, part, out, P, K, accumulate));
+  return cuda_ok("colsum_finalize", launch_pdl(colsum_finalize_kernel, grid, block, 0, s, part, out, P, K, accumulate, scale));
 }
 
 }  // namespace pvae
@@ -1317,6 +1410,55 @@ int pvae::sampler_fwd_impl(const float* h, const float* log_r, const float* b_en
                               : launch_ind<kFwdSoft, false>(p, indicator, grid, s);
   return cuda_ok("pvae_sampler_fwd", e);
 }
+
+// Training forward in coefficient mode (see SamplerParams::c_ddr) and the matching streaming backward.
+int pvae::sampler_fwd_coef_impl(const float* h, const float* log_r, const float* b_enc, float* z, float* z_lo, float* kl_rowsum,
+                                float* rate_max, float* c_a, float* c_ddr, float* c_ck, float* klcol, int64_t B, int64_t K,
+                                int64_t row_offset, int n_exp, float temp, int indicator, int exc_only, float exit_logit, uint64_t seed,
+                                uint64_t offset, const uint64_t* offset_dev, void* stream) {
+  if (int rc = check_common("pvae_sampler_fwd", B, K, row_offset, n_exp, temp, indicator)) return rc;
+  if (B == 0) return PVAE_OK;
+  if (!h || !log_r || !z || !c_a || !c_ddr || !c_ck || !klcol || temp == 0.f)
+    return fail(PVAE_ERR_INVALID, "sampler_fwd_coef: null pointer or temp == 0");
+  SamplerParams p{};
+  p.h = h, p.log_r = log_r, p.b_enc = b_enc, p.z = z, p.z_lo = z_lo, p.kl_rowsum = kl_rowsum, p.rate_max = rate_max;
+  p.dz_out = c_a, p.c_ddr = c_ddr, p.c_ck = c_ck, p.klcol = klcol;
+  p.B = B, p.K = K, p.row_offset = row_offset, p.rows_per_block = p.rows_block = rows_per_block_for(B);
+  set_chain(p, n_exp, temp, indicator, exit_logit);
+  p.clamp_dr = 10.f, p.clamp_rate = 5.f, p.exc_only = exc_only;  // main/vae.py:403-409
+  p.offset = offset, p.offset_dev = offset_dev;
+  philox_key_schedule(seed, p.ks);
+  dim3 grid(static_cast<unsigned>((B + p.rows_per_block - 1) / p.rows_per_block));
+  const bool one_wave = g_one_wave;
+  g_one_wave = 0;  // the one-wave schedule has no coefficient mode
+  const cudaError_t e = launch_ind<kFwdBoth, false>(p, indicator, grid, static_cast<cudaStream_t>(stream));
+  g_one_wave = one_wave;
+  return cuda_ok("pvae_sampler_fwd", e);
+}
+
+int pvae::sampler_bwd_coef_impl(const float* g_z, const float* c_a, const float* c_ddr, const float* c_ck, float kl_scale, float* g_h,
+                                float* g_h_lo, float* partial_ws, int want_bias, const float* klcol, int64_t klcol_rows, float* g_log_r,
+                                float* g_b_enc, int64_t B, int64_t K, void* stream) {
+  if (B <= 0 || K <= 0 || K % 4 || !g_z || !c_a || !c_ddr || !c_ck || !g_h || !partial_ws)
+    return fail(PVAE_ERR_INVALID, "sampler_bwd_coef: bad argument");
+  SamplerParams p{};
+  p.g_z = g_z, p.c_a = c_a, p.c_ddr = const_cast<float*>(c_ddr), p.c_ck = const_cast<float*>(c_ck), p.kl_scale = kl_scale, p.g_h = g_h, p.g_h_lo = g_h_lo;
+  p.B = B, p.K = K;
+  const long long P = (B + kCoefRows - 1) / kCoefRows;
+  p.part_log_r = partial_ws;
+  p.part_b = want_bias ? partial_ws + P * K : nullptr;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = cuda_ok("sampler_bwd_coef", launch_pdl(sampler_bwd_coef_kernel, dim3(static_cast<unsigned>(P)), dim3(kThreads), 0, s, p)))
+    return rc;
+  if (g_log_r == nullptr) return PVAE_OK;  // partials only: the caller reduces them (pvae_adamax_from_partials)
+  // g_log_r = sum_b g_u + kl_scale sum_b kl; g_b_enc = sum_b g_h
+  if (int rc = finalize_cols(p.part_log_r, g_log_r, P, K, 0, s)) return rc;
+  if (int rc = finalize_cols(klcol, g_log_r, klcol_rows, K, 1, s, kl_scale)) return rc;
+  if (want_bias && g_b_enc)
+    if (int rc = finalize_cols(p.part_b, g_b_enc, P, K, 0, s)) return rc;
+  return PVAE_OK;
+}
+int64_t pvae::sampler_bwd_coef_rows(int64_t B) { return B <= 0 ? 0 : (B + kCoefRows - 1) / kCoefRows; }
 
 extern "C" int pvae_sampler_bwd(const float* h, const float* log_r, const float* b_enc, const float* g_z,
                                 const float* g_log_dr, const float* dz_acc, float kl_scale, float* g_h, float* g_log_r,

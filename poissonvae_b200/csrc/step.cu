@@ -136,9 +136,37 @@ constexpr int kDenseRows = 8;  // rows of the 32 x 32 block that work on a dense
 struct SegTable {
   long long offset[kMaxSegments], length[kMaxSegments], stride[kMaxSegments];
   const float* partials[kMaxSegments];
-  int n_partials[kMaxSegments], columnar[kMaxSegments], first_block[kMaxSegments + 1];
+  const float* partials2[kMaxSegments];  // columnar segments: a second set of row partials, added with weight scale2
+  float scale2[kMaxSegments];
+  int n_partials[kMaxSegments], n_partials2[kMaxSegments], columnar[kMaxSegments], first_block[kMaxSegments + 1];
   int n;
 };
+// fixed-order column sum of (P, len) row partials for column k by the 32 x 32 block (the order of colsum_finalize_kernel)
+__device__ __forceinline__ float block_colsum(const float* __restrict__ part, long long P, long long len, long long k, bool in_range,
+                                              float (*s)[33]) {
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (in_range) {
+    long long r = ty;
+    for (; r + 3 * 32 < P; r += 4 * 32) {
+      a0 += __ldg(part + r * len + k);
+      a1 += __ldg(part + (r + 32) * len + k);
+      a2 += __ldg(part + (r + 64) * len + k);
+      a3 += __ldg(part + (r + 96) * len + k);
+    }
+    for (; r < P; r += 32) a0 += __ldg(part + r * len + k);
+  }
+  s[ty][tx] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  float v = 0.f;
+  if (ty == 0 && in_range) {
+    v = s[0][tx];
+#pragma unroll
+    for (int y = 1; y < 32; ++y) v += s[y][tx];
+  }
+  __syncthreads();
+  return v;
+}
 __device__ __forceinline__ void adamax_update(float* p, float* m, float* u, float* p_lo, long long i, float gi, float clr, float beta1,
                                               float beta2, float eps, float weight_decay) {
   float pi = p[i], mi = m[i], ui = u[i];
@@ -169,24 +197,13 @@ __global__ void __launch_bounds__(1024) adamax_partials_kernel(const __grid_cons
   const long long off = t.offset[seg], len = t.length[seg];
   const int tx = threadIdx.x, ty = threadIdx.y;
   if (t.columnar[seg]) {  // (n_partials, len) row partials: the reduction of colsum_finalize_kernel (sampler.cu)
-    const long long k = static_cast<long long>(blk) * 32 + tx, P = t.n_partials[seg];
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    if (k < len) {
-      long long r = ty;
-      for (; r + 3 * 32 < P; r += 4 * 32) {
-        a0 += __ldg(part + r * len + k);
-        a1 += __ldg(part + (r + 32) * len + k);
-        a2 += __ldg(part + (r + 64) * len + k);
-        a3 += __ldg(part + (r + 96) * len + k);
-      }
-      for (; r < P; r += 32) a0 += __ldg(part + r * len + k);
+    const long long k = static_cast<long long>(blk) * 32 + tx;
+    float v = block_colsum(part, t.n_partials[seg], len, k, k < len, s);
+    if (t.partials2[seg] != nullptr) {
+      const float v2 = block_colsum(t.partials2[seg], t.n_partials2[seg], len, k, k < len, s);
+      v = fmaf(t.scale2[seg], v2, v);
     }
-    s[ty][tx] = (a0 + a1) + (a2 + a3);
-    __syncthreads();
     if (ty == 0 && k < len) {
-      float v = s[0][tx];
-#pragma unroll
-      for (int y = 1; y < 32; ++y) v += s[y][tx];
       g_out[off + k] = v;
       if (p != nullptr) adamax_update(p, m, u, p_lo, off + k, v, clr, beta1, beta2, eps, weight_decay);
     }
@@ -324,6 +341,8 @@ int pvae::adamax_from_partials_impl(float* p, float* p_lo, float* g_out, float* 
     if (g.columnar && !g.partials) return fail(PVAE_ERR_INVALID, "pvae_adamax_from_partials: a columnar segment needs partials");
     t.offset[i] = g.offset, t.length[i] = g.length, t.stride[i] = g.stride, t.partials[i] = g.partials;
     t.n_partials[i] = g.n_partials, t.columnar[i] = g.columnar, t.first_block[i] = blocks;
+    t.partials2[i] = g.columnar ? g.partials2 : nullptr, t.n_partials2[i] = g.n_partials2, t.scale2[i] = g.scale2;
+    if (t.partials2[i] && g.n_partials2 < 1) return fail(PVAE_ERR_INVALID, "pvae_adamax_from_partials: bad second source of segment %d", i);
     blocks += static_cast<int>(g.columnar ? (g.length + 31) / 32 : (g.length / 4 + 32 * kDenseRows - 1) / (32 * kDenseRows));
   }
   t.first_block[n_segs] = blocks;

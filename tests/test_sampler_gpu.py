@@ -391,8 +391,8 @@ def test_baseline_configs_4_and_5_sampler_path(lib, cfg):
 
 @pytest.mark.parametrize("K", [512, 520, 96, 1024])
 def test_work_pool_schedule_is_bit_identical(lib, K):
-    """Forward sampler schedules: row-by-row lock step (0), the per-row-tile work pool (1) and the one-wave pool
-    (2, default: one resident wave of blocks, all quads of a block's rows in one pool) walk every chain with the same
+    """Forward sampler schedules: row-by-row lock step (0), the per-row-tile work pool (1, default) and the one-wave pool
+    (2: one resident wave of blocks, all quads of a block's rows in one pool) walk every chain with the same
     arithmetic.  Every output is bit-identical between 0 and 1, and between them and 2 for every quad phase A finishes
     (all of them when the cap exceeds n_exp); a chain the one-wave schedule hands to phase B is walked again from its
     first event by a lane group (prefix-sum arrival times), which may move the last bit of the running sums.  Rates
@@ -419,8 +419,7 @@ def test_work_pool_schedule_is_bit_identical(lib, K):
                         assert torch.equal(outs[1][k], outs[2][k]), (k, cap, temp)
                     else:
                         a, b = outs[2][k].cpu().numpy(), outs[1][k].cpu().numpy()
-                        assert_ulp(a, b, max_ulp=4, what=f"{k} one-wave vs tile pool, cap {cap}")
-                        assert (a != b).mean() < 0.5
+                        assert_rel(a, b, rtol=2e-6, what=f"{k} one-wave vs tile pool, cap {cap}")
     finally:
-        lib.pvae_set_pool(2)
+        lib.pvae_set_pool(1)
         lib.pvae_set_phase_a_events(8)

@@ -233,7 +233,8 @@ def test_fused_update_is_bit_identical(bias):
         # + 1 with operand planes when the caller does not bring x's low plane (the step splits x itself);
         # + 1 when the stand-alone Adamax kernel does not keep the parameters' low plane (rebuilt at the next step's head)
         extra = (1 if tr.planes else 0) + (1 if (tr.planes and fuse is not True) else 0)
-        assert per_step == {True: 9, False: 10, "three kernels": 13 if bias else 12}[fuse] + extra, per_step
+        # "three kernels": g_log_r takes a second column-sum launch (the KL part, from the forward's per-block column sums)
+        assert per_step == {True: 9, False: 10, "three kernels": 14 if bias else 13}[fuse] + extra, per_step
     lib.pvae_set_fuse_reduce(1)
     for other in (False, "three kernels"):
         for a, b in zip(out[True], out[other]):

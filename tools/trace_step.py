@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--tf32", action="store_true")
     ap.add_argument("--no_overlap", action="store_true")
     ap.add_argument("--no_carveout", action="store_true")
-    ap.add_argument("--pool", type=int, default=2, help="forward sampler schedule: 0 row by row, 1 per-row-tile pool, 2 one-wave pool")
+    ap.add_argument("--pool", type=int, default=1, help="forward sampler schedule: 0 row by row, 1 per-row-tile pool, 2 one-wave pool")
     a = ap.parse_args()
     from poissonvae_b200 import _lib, linear
     from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
