@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--tf32", action="store_true", help="single-pass TF32 GEMMs instead of 3xTF32 (A/B)")
     ap.add_argument("--dec_splits", type=int, default=-1, help="K-splits of the decoder GEMM (A/B; default: the library's choice)")
     ap.add_argument("--pool", type=int, default=1, help="forward sampler schedule (A/B): 0 row by row, 1 per-row-tile pool, 2 one-wave pool")
+    ap.add_argument("--coef", action="store_true", help="sampler coefficient mode: streaming backward (A/B, see pvae_set_step_coef)")
     ap.add_argument("--no_carveout", action="store_true", help="leave every kernel's L1 / shared-memory split at the driver default (A/B)")
     ap.add_argument("--no_planes", action="store_true", help="GEMMs split their operands per stage in shared memory instead of "
                                                               "loading the producers' TF32 low planes (A/B, same bits)")
@@ -304,6 +305,7 @@ def run_ours(args):
     if args.no_carveout:
         lib.pvae_set_carveout(0)
     lib.pvae_set_pool(args.pool)
+    lib.pvae_set_step_coef(1 if args.coef else 0)
     if args.no_overlap:
         lib.pvae_set_step_overlap(0)
     if args.tf32:

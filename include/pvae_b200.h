@@ -255,6 +255,11 @@ int pvae_lin_step_train(const float* x, float* params, float* grads, float* exp_
 /* Tuning knob (process-wide, default on): run the decoder wgrad and the loss assembly of pvae_lin_step_fwd_bwd on
  * an internal side stream (forked from / joined back into the caller's stream with events). */
 int pvae_set_step_overlap(int on);
+/* Tuning knob (process-wide, default off): coefficient mode of the step's sampler - the forward also leaves d z / d u, the
+ * encoder clamp's derivative and the KL gradient term per latent (+ per-block KL column sums), and the backward becomes a
+ * streaming kernel (4 loads, a few FMAs) instead of a second evaluation of the prologue.  Same gradients to ~1e-7.
+ * Measured slower at config 2 (+16 MB of working set: 120.9 vs 112 us per step), kept for A/B. */
+int pvae_set_step_coef(int on);
 /* Debugging aid (process-wide): events = HOST array of n cudaEvent_t (kept alive by the caller) recorded on the step's main
  * stream at: 0 start, 1 after the optional x split, 2 encoder GEMM, 3 sampler forward, 4 decoder GEMM, 5 residual, 6 dgrad,
  * 7 sampler backward, 8 encoder wgrad, 9 gradient reduction + Adamax (single-GPU paths).  Per-kernel live durations, at

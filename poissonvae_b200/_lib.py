@@ -121,6 +121,7 @@ _SIGNATURES = {
     "pvae_tf32_lo": (_i, [_p, _p, _i64, _p]),
     "pvae_set_step_overlap": (_i, [_i]),
     "pvae_set_step_trace": (_i, [_p, _i]),
+    "pvae_set_step_coef": (_i, [_i]),
     "pvae_lin_step_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i,
                                    _u64, _u64, _p, _p, _p]),
     "pvae_conv_weight_prep": (_i, [_p] * 6 + [_i] * 7 + [_p]),

@@ -41,6 +41,7 @@ SideStream* side_stream() {
 void* const* g_trace = nullptr;  // pvae_set_step_trace: CUDA events recorded between the main-stream launches of a step
 int g_trace_n = 0;
 int g_overlap = 1;
+int g_coef = 0;  // pvae_set_step_coef: the forward sampler leaves the backward's coefficients (streaming backward); measured slower
 int g_dec_splits = 0;   // K-splits of the decoder GEMM (pvae_set_dec_splits); 0 = automatic
 int g_fuse_reduce = 1;  // pvae_lin_step_fwd_bwd: reduce all gradient partials with one kernel (bit-identical to the three)
 
@@ -67,14 +68,18 @@ Ws carve(float* base, int64_t B, int64_t K, int64_t D) {
     o += (n + 3) & ~int64_t(3);  // keep every buffer 16-byte aligned
     return p;
   };
-  w.h = take(B * K), w.z = take(B * K), w.dz = take(B * K), w.y = take(B * D), w.g_y = take(B * D), w.g_z = take(B * K), w.g_h = take(B * K);
+  w.h = take(B * K), w.z = take(B * K), w.dz = take(B * K), w.y = take(B * D), w.g_y = take(B * D);
   w.recon = take(B * pvae_gemm_residual_parts(D)), w.klrow = take(B);
   w.partials = take(2 * pvae_num_partials(B) * K);
   const int64_t s1 = pvae_gemm_ws_floats(D, K, wgrad_splits(D, K, B)), s2 = pvae_gemm_ws_floats(K, D, wgrad_splits(K, D, B));
   w.splitk = take(s1);   // decoder wgrad (may run on the side stream, concurrently with ...)
   w.splitk2 = take(s2);  // ... the encoder wgrad
-  w.ydec = take(8 * B * D);  // split-K partials of the decoder output (pvae_set_dec_splits, at most 8)
-  w.z_lo = take(B * K), w.g_y_lo = take(B * D), w.g_h_lo = take(B * K), w.x_lo = take(B * D);
+  w.ydec = take(std::max<int64_t>(8 * B * D, B * K));  // split-K partials of the decoder output (pvae_set_dec_splits, at most 8)
+  // The step's working set is what decides whether its intermediates stay in the L2 (126 MB): buffers whose lives do not
+  // overlap share storage.  g_z (dgrad output) reuses the decoder partials the residual kernel has consumed; the sampler
+  // backward writes g_h over the g_z it has just read and g_h's low plane over dz_acc (same index, same thread).
+  w.g_z = w.ydec, w.g_h = w.g_z, w.g_h_lo = w.dz;
+  w.z_lo = take(B * K), w.g_y_lo = take(B * D), w.x_lo = take(B * D);
   w.c_ddr = take(B * K), w.c_ck = take(B * K), w.klcol = take(pvae_num_partials(B) * K);
   w.total = o;
   return w;
@@ -131,6 +136,7 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   const bool planes = precise && d.params_lo != nullptr;
   const float *w_enc_lo = planes ? d.params_lo + K : nullptr, *w_dec_lo = planes ? d.params_lo + K + K * D : nullptr;
   float *z_lo = planes ? w.z_lo : nullptr, *g_y_lo = planes ? w.g_y_lo : nullptr, *g_h_lo = planes ? w.g_h_lo : nullptr;
+  const bool coef = g_coef != 0;
   const float* x_lo = planes ? d.x_lo : nullptr;
   auto mark = [&](int i) {
     if (d.events && d.events[i]) cudaEventRecord(static_cast<cudaEvent_t>(d.events[i]), s);
@@ -156,11 +162,18 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   if ((rc = gemm(d.x, x_lo, w_enc, w_enc_lo, w.h, B, K, D, 1, 1, 1, nullptr, s))) return rc;
   trace();  // 2: encoder GEMM
   mark(0);
-  // coefficient mode: the forward leaves d z / d u, the clamp derivative and the KL gradient term per latent and the KL's
-  // column sums per block, so that the backward is a streaming kernel instead of a second evaluation of the prologue
-  if ((rc = pvae::sampler_fwd_coef_impl(w.h, log_r, b_enc, w.z, z_lo, w.klrow, d.rate_max, w.dz, w.c_ddr, w.c_ck, w.klcol, B, K, d.row_offset,
-                                        d.n_exp, d.temp, d.indicator, d.exc_only, d.exit_logit, d.seed, d.offset, d.offset_dev, s)))
+  if (coef) {
+    // coefficient mode: the forward leaves d z / d u, the clamp derivative and the KL gradient term per latent and the
+    // KL's column sums per block; the backward is then a streaming kernel instead of a second evaluation of the prologue
+    if ((rc = pvae::sampler_fwd_coef_impl(w.h, log_r, b_enc, w.z, z_lo, w.klrow, d.rate_max, w.dz, w.c_ddr, w.c_ck, w.klcol, B, K,
+                                          d.row_offset, d.n_exp, d.temp, d.indicator, d.exc_only, d.exit_logit, d.seed, d.offset,
+                                          d.offset_dev, s)))
+      return rc;
+  } else if ((rc = pvae::sampler_fwd_impl(w.h, log_r, b_enc, w.z, z_lo, nullptr, nullptr, nullptr, w.klrow, d.rate_max, w.dz, B, K,
+                                          d.row_offset, d.n_exp, d.temp, d.indicator, d.exc_only, d.exit_logit, d.seed, d.offset,
+                                          d.offset_dev, s))) {
     return rc;
+  }
   mark(1);
   trace();  // 3: sampler forward
   // decoder GEMM with the residual fused into its epilogue: g_y and per-tile squared errors, y itself is never stored
@@ -198,13 +211,16 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   const int sp_dec = wgrad_splits(D, K, B), sp_enc = wgrad_splits(K, D, B);
   const bool fuse = (d.update >= 1 || g_fuse_reduce) && sp_dec > 1 && sp_enc > 1;
   if ((rc = gemm(w.g_y, g_y_lo, w.z, z_lo, fuse ? nullptr : g_w_dec, D, K, B, 0, 0, sp_dec, w.splitk, s2))) return rc;
-  const int prow = static_cast<int>(pvae::sampler_bwd_coef_rows(B));
+  const float kl_scale = d.beta / static_cast<float>(B_global);
+  const int prow = static_cast<int>(coef ? pvae::sampler_bwd_coef_rows(B) : pvae_sampler_bwd_partial_rows(B));
+  const int64_t bias_row = coef ? prow : pvae_sampler_bwd_bias_offset_rows(B);
   pvae_grad_segment seg[4] = {};
-  // g_log_r = sum_b g_u (the backward's column partials) + beta / B_global * sum_b kl (the forward's per-block column sums)
-  seg[0] = pvae_grad_segment{0, K, w.partials, prow, 1, K, w.klcol, static_cast<int>(pvae_num_partials(B)), d.beta / static_cast<float>(B_global)};
+  seg[0] = pvae_grad_segment{0, K, w.partials, prow, 1, K, nullptr, 0, 0.f};
+  if (coef)  // g_log_r = sum_b g_u (the backward's column partials) + beta / B_global * sum_b kl (the forward's column sums)
+    seg[0].partials2 = w.klcol, seg[0].n_partials2 = static_cast<int>(pvae_num_partials(B)), seg[0].scale2 = kl_scale;
   seg[1] = pvae_grad_segment{K, K * D, w.splitk2, pvae_gemm_effective_splits(B, sp_enc), 0, K * D, nullptr, 0, 0.f};
   seg[2] = pvae_grad_segment{K + K * D, D * K, w.splitk, pvae_gemm_effective_splits(B, sp_dec), 0, D * K, nullptr, 0, 0.f};
-  if (has_bias) seg[3] = pvae_grad_segment{K + 2 * K * D, K, w.partials + static_cast<int64_t>(prow) * K, prow, 1, K, nullptr, 0, 0.f};
+  if (has_bias) seg[3] = pvae_grad_segment{K + 2 * K * D, K, w.partials + bias_row * K, prow, 1, K, nullptr, 0, 0.f};
   pvae::AdamaxDev dev;
   dev.lr_sched = d.lr_sched, dev.n_sched = d.n_sched, dev.state = d.state;
   if (dp_peer) {
@@ -224,10 +240,15 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   if ((rc = gemm(w.g_y, g_y_lo, w_dec, w_dec_lo, w.g_z, B, K, D, 1, 0, 1, nullptr, s))) return rc;
   trace();  // 6: dgrad
   mark(2);
-  const float kl_scale = d.beta / static_cast<float>(B_global);
-  if ((rc = pvae::sampler_bwd_coef_impl(w.g_z, w.dz, w.c_ddr, w.c_ck, kl_scale, w.g_h, g_h_lo, w.partials, has_bias, w.klcol,
-                                        pvae_num_partials(B), fuse ? nullptr : g_log_r, g_b_enc, B, K, s)))
+  if (coef) {
+    if ((rc = pvae::sampler_bwd_coef_impl(w.g_z, w.dz, w.c_ddr, w.c_ck, kl_scale, w.g_h, g_h_lo, w.partials, has_bias, w.klcol,
+                                          pvae_num_partials(B), fuse ? nullptr : g_log_r, g_b_enc, B, K, s)))
+      return rc;
+  } else if ((rc = pvae::sampler_bwd_impl(w.h, log_r, b_enc, w.g_z, nullptr, w.dz, kl_scale, w.g_h, g_h_lo, g_log_r, g_b_enc, w.partials,
+                                          fuse ? -1 : 0, B, K, d.row_offset, d.n_exp, d.temp, d.indicator, d.exc_only, d.exit_logit, d.seed,
+                                          d.offset, d.offset_dev, s))) {
     return rc;
+  }
   mark(3);
   trace();  // 7: sampler backward
   if ((rc = gemm(w.g_h, g_h_lo, d.x, x_lo, fuse ? nullptr : g_w_enc, K, D, B, 0, 0, sp_enc, w.splitk2, s))) return rc;
@@ -266,6 +287,11 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   trace();  // 9: join + gradient reduction / Adamax
   if (upd && d.state)  // graph replay: advance the device-side step counter / Philox offset, move rate.max() to its slot
     return pvae::advance_state(d.state, d.philox_increment, d.rate_max, d.rmax_ring, d.ring_n, s);
+  return PVAE_OK;
+}
+
+extern "C" int pvae_set_step_coef(int on) {
+  g_coef = on != 0;
   return PVAE_OK;
 }
 

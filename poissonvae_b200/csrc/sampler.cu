@@ -1038,7 +1038,8 @@ __global__ void __launch_bounds__(kThreads, 7) sampler_bwd_saved_kernel(const Sa
       for (int u = 0; u < 2; ++u) {
         if (r0 + u < nrows) {
           const long long base = (row0 + r0 + u) * p.K + k;
-          hv[u] = ldg4(p.h + base), gz[u] = ldg4(p.g_z + base), dz[u] = ldg4(p.dz_in + base);
+          // g_h may be written over g_z and its low plane over dz_acc (same index, this thread): coherent loads, not ld.nc
+          hv[u] = ldg4(p.h + base), gz[u] = ld4(p.g_z + base), dz[u] = ld4(p.dz_in + base);
           gl[u] = has_gld ? ldg4(p.g_log_dr + base) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
@@ -1095,7 +1096,7 @@ __global__ void __launch_bounds__(kThreads, 8) sampler_bwd_coef_kernel(const Sam
       for (int u = 0; u < 2; ++u) {
         if (r0 + u < nrows) {
           const long long base = (row0 + r0 + u) * p.K + k;
-          gz[u] = ldg4(p.g_z + base), a[u] = ldg4(p.c_a + base), dd[u] = ldg4(p.c_ddr + base), ck[u] = ldg4(p.c_ck + base);
+          gz[u] = ld4(p.g_z + base), a[u] = ld4(p.c_a + base), dd[u] = ldg4(p.c_ddr + base), ck[u] = ldg4(p.c_ck + base);
         }
       }
 #pragma unroll

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--tf32", action="store_true")
     ap.add_argument("--no_overlap", action="store_true")
     ap.add_argument("--no_carveout", action="store_true")
+    ap.add_argument("--coef", action="store_true")
     ap.add_argument("--pool", type=int, default=1, help="forward sampler schedule: 0 row by row, 1 per-row-tile pool, 2 one-wave pool")
     a = ap.parse_args()
     from poissonvae_b200 import _lib, linear
@@ -40,6 +41,7 @@ def main():
     if a.no_carveout:
         lib.pvae_set_carveout(0)
     lib.pvae_set_pool(a.pool)
+    lib.pvae_set_step_coef(1 if a.coef else 0)
     B, K = a.batch, a.latents
     model = PoissonVAE(ConfigPoisVAE(n_latents=K, prior_clamp=-4, seed=0)).cuda()
     model.n_exp.fill_(263)
