@@ -61,42 +61,6 @@ def _require_cuda_f32(t: torch.Tensor, name: str):
         raise TypeError(f"{name} must be float32, got {t.dtype}")
 
 
-# True: the forward also accumulates dz_acc = sum_n f'(l_n) t_n while it walks the chain and the backward is
-# one elementwise pass over it (4 extra bytes per latent, L2-resident).  False: nothing is saved and the
-# backward walks the chain again from the Philox counters (the memory-minimal variant).
-SAVE_DERIVATIVE = True
-
-
-class _RsampleFn(torch.autograd.Function):
-    """z = Poisson(log_rate).rsample() with the closed-form gradient."""
-
-    @staticmethod
-    def forward(ctx, log_rate, temp, n_exp, indicator, clamp, exit_logit, seed, offset):
-        lr = log_rate.contiguous()
-        B, K = _as_rows(lr)
-        z = torch.empty_like(lr)
-        dz = torch.empty_like(lr) if (SAVE_DERIVATIVE and ctx.needs_input_grad[0]) else None
-        lib = _lib.load()
-        with torch.cuda.device(lr.device):
-            _lib.check(lib.pvae_rsample_fwd(_ptr(lr), _ptr(z), None, _ptr(dz), B, K, 0, n_exp, temp, indicator,
-                                            clamp, exit_logit, seed, offset, None, _stream()))
-        ctx.save_for_backward(lr, dz)
-        ctx.args = (B, K, n_exp, temp, indicator, clamp, exit_logit, seed, offset)
-        return z
-
-    @staticmethod
-    def backward(ctx, g_z):
-        lr, dz = ctx.saved_tensors
-        B, K, n_exp, temp, indicator, clamp, exit_logit, seed, offset = ctx.args
-        g_z = g_z.contiguous()
-        g = torch.empty_like(lr)
-        lib = _lib.load()
-        with torch.cuda.device(lr.device):
-            _lib.check(lib.pvae_rsample_bwd(_ptr(lr), _ptr(g_z), _ptr(dz), _ptr(g), B, K, 0, n_exp, temp, indicator,
-                                            clamp, exit_logit, seed, offset, None, _stream()))
-        return g, None, None, None, None, None, None, None
-
-
 class Poisson:
     """Drop-in for the reference class: same signature (base/distributions.py:6-14).
 
@@ -162,9 +126,12 @@ class Poisson:
         temp = float(self.temp)
         if temp == 0.0:
             return self.sample()
-        n_exp, ind, clamp = self._launch_args()
-        seed, offset = next_philox(self._log_rate_in.device)
-        return _RsampleFn.apply(self._log_rate_in, temp, n_exp, ind, clamp, self.exit_logit, seed, offset)
+        n_exp, _, clamp = self._launch_args()
+        # the registered custom op (poissonvae_b200/ops.py): draws its Philox (seed, offset) from torch's CUDA generator
+        # inside the op, closed-form backward registered with torch.library
+        from . import ops  # noqa: F401  (registers torch.ops.pvae.*)
+        z, _, _ = torch.ops.pvae.poisson_rsample(self._log_rate_in, temp, n_exp, self.indicator_approx, clamp, self.exit_logit)
+        return z
 
     @torch.no_grad()
     def sample(self):

@@ -64,23 +64,7 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor = None) -> torch
     return _gemm(a, b, out, m, n, kd, 0, 0)
 
 
-class _LinearFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, weight):
-        x = x.contiguous()
-        ctx.save_for_backward(x, weight)
-        return gemm_nt(x, weight.contiguous())
-
-    @staticmethod
-    def backward(ctx, g):
-        x, weight = ctx.saved_tensors
-        g = g.contiguous()
-        gx = gemm_nn(g, weight.contiguous()) if ctx.needs_input_grad[0] else None
-        gw = gemm_tn(g, x) if ctx.needs_input_grad[1] else None
-        return gx, gw
-
-
 def linear(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
-    """F.linear for 2-D inputs (base/common.py:409-414)."""
-    y = _LinearFn.apply(x, weight)
-    return y if bias is None else y + bias
+    """F.linear for 2-D inputs (base/common.py:409-414), through the registered custom op torch.ops.pvae.linear."""
+    from . import ops  # noqa: F401  (registers torch.ops.pvae.*)
+    return torch.ops.pvae.linear(x, weight, bias)

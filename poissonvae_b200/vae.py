@@ -16,11 +16,10 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import _lib, distributions
+from . import _lib
 from .distributions import (EXIT_LOSSLESS, INDICATOR_CODES, Poisson, _ptr, _require_cuda_f32, _stream,
                             softclamp, softclamp_upper)
 from .linear import linear
-from .rng import next_philox
 
 
 class ConfigPoisVAE:
@@ -98,48 +97,6 @@ class _Linear(nn.Linear):
 
     def get_weight(self):
         return self.weight
-
-
-class _EncodeSampleFn(torch.autograd.Function):
-    """(h, log_r[, b_enc]) -> (z, log_dr): softclamps + rate + relaxed counts in one kernel;
-    backward recomputes the chain from the Philox counters."""
-
-    @staticmethod
-    def forward(ctx, h, log_r, b_enc, temp, n_exp, indicator, exc_only, exit_logit, seed, offset, row_offset=0,
-                rate_max=None):
-        h = h.contiguous()
-        B, K = h.shape
-        lr = log_r.reshape(-1).contiguous()
-        z = torch.empty_like(h)
-        log_dr = torch.empty_like(h)
-        need = any(ctx.needs_input_grad[:3]) and temp > 0.0
-        dz = torch.empty_like(h) if (distributions.SAVE_DERIVATIVE and need) else None
-        with torch.cuda.device(h.device):
-            _lib.check(_lib.load().pvae_sampler_fwd(
-                _ptr(h), _ptr(lr), _ptr(b_enc), _ptr(z), _ptr(log_dr), None, None, None, _ptr(rate_max), _ptr(dz), B, K,
-                row_offset, n_exp, temp, indicator, int(exc_only), exit_logit, seed, offset, None, _stream()))
-        ctx.save_for_backward(h, lr, b_enc, dz)
-        ctx.args = (B, K, temp, n_exp, indicator, int(exc_only), exit_logit, seed, offset, log_r.shape, row_offset)
-        return z, log_dr
-
-    @staticmethod
-    def backward(ctx, g_z, g_log_dr):
-        h, lr, b_enc, dz = ctx.saved_tensors
-        B, K, temp, n_exp, indicator, exc_only, exit_logit, seed, offset, lr_shape, row_offset = ctx.args
-        if temp == 0.0:
-            raise RuntimeError("hard counts (temp == 0) are not differentiable")
-        lib = _lib.load()
-        g_z = g_z.contiguous()
-        g_log_dr = None if g_log_dr is None else g_log_dr.contiguous()
-        g_h = torch.empty_like(h)
-        g_lr = torch.empty_like(lr)
-        g_b = None if b_enc is None else torch.empty_like(b_enc)
-        ws = torch.empty(2 * lib.pvae_num_partials(B) * K, device=h.device, dtype=torch.float32)
-        with torch.cuda.device(h.device):
-            _lib.check(lib.pvae_sampler_bwd(
-                _ptr(h), _ptr(lr), _ptr(b_enc), _ptr(g_z), _ptr(g_log_dr), _ptr(dz), 0.0, _ptr(g_h), _ptr(g_lr), _ptr(g_b),
-                _ptr(ws), 0, B, K, row_offset, n_exp, temp, indicator, exc_only, exit_logit, seed, offset, None, _stream()))
-        return g_h, g_lr.reshape(lr_shape), g_b, None, None, None, None, None, None, None, None, None
 
 
 class _InferRateFn(torch.autograd.Function):
@@ -309,10 +266,14 @@ class PoissonVAE(nn.Module):
                            indicator_approx=self.cfg.indicator_approx, n_exp=self._n_exp_host,
                            exit_logit=self.exit_logit)
             return dist, log_dr
-        seed, offset = next_philox(x.device) if self.philox_override is None else self.philox_override
-        z, log_dr = _EncodeSampleFn.apply(h, self.log_rate, self.fc_enc.bias, temp, self._n_exp_host,
-                                          INDICATOR_CODES[self.cfg.indicator_approx], self.cfg.exc_only,
-                                          self.exit_logit, seed, offset, self.row_offset, self.rate_max_out)
+        seed, offset = (-1, -1) if self.philox_override is None else self.philox_override  # -1: the op asks torch's generator
+        from . import ops  # noqa: F401  (registers torch.ops.pvae.*)
+        z, log_dr, _, _, _, r_max = torch.ops.pvae.encode_sample_kl(h, self.log_rate, self.fc_enc.bias, temp, self._n_exp_host,
+                                                                    self.cfg.indicator_approx, bool(self.cfg.exc_only),
+                                                                    self.exit_logit, seed, offset, self.row_offset)
+        if self.rate_max_out is not None:  # running max of the rates for update_n, kept on the device
+            with torch.no_grad():
+                torch.maximum(self.rate_max_out, r_max, out=self.rate_max_out)
         dist = _PosteriorPoisson(self, h, log_dr, self.temp if t is None else t, temp, self._n_exp_host, z)
         return dist, log_dr
 
