@@ -265,6 +265,27 @@ int pvae_set_step_coef(int on);
  * 7 sampler backward, 8 encoder wgrad, 9 gradient reduction + Adamax (single-GPU paths).  Per-kernel live durations, at
  * the price of the programmatic overlap between the kernels.  n = 0 switches it off. */
 int pvae_set_step_trace(void* const* events, int n);
+/* ---- fused forward after the encoder GEMM: rsample + KL + decoder GEMM + reconstruction residual in ONE kernel ---------
+ * (csrc/fused_fwd.cu; BASELINE config 2 "fused rsample+KL+decoder GEMM").  Replaces, in one launch: PoissonVAE.infer +
+ * Poisson.rsample (main/vae.py:393-415, base/distributions.py:55-81), loss_kl's per-sample sums (main/vae.py:446-450),
+ * decode (main/vae.py:59-60: y = z W_dec^T on tcgen05, z handed to the tensor core through shared memory k-block by
+ * k-block) and loss_recon + its gradient (main/vae.py:68-72).
+ *   h (B,K) encoder output; w_dec (D,K) and its TF32 low plane w_dec_lo; x (B,D).
+ *   outputs: z, z_lo (optional), dz_acc (B,K) as pvae_sampler_fwd; g_y (B,D) = g_scale (y - x) and g_y_lo (optional);
+ *   recon (B) = sum_d (y - x)^2; kl_rowsum (B, optional); rate_max (optional running max).
+ * Shapes: K a multiple of 256 and <= 1024, D in {128, 256}, B >= 12 rows per SM (pvae_fused_fwd_supported); temp > 0.
+ * z / dz_acc of a chain finished by a single lane equal pvae_sampler_fwd's bit for bit, a chain finished by a lane group
+ * within a few ulp. */
+int pvae_fused_fwd_supported(int64_t B, int64_t K, int64_t D);
+int pvae_fused_fwd(const float* h, const float* log_r, const float* b_enc, const float* w_dec, const float* w_dec_lo, const float* x,
+                   float* z, float* z_lo, float* dz_acc, float* g_y, float* g_y_lo, float* recon, float* kl_rowsum, float* rate_max,
+                   int64_t B, int64_t K, int64_t D, int64_t row_offset, int n_exp, float temp, int indicator, int exc_only,
+                   float exit_logit, float g_scale, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream);
+/* Tuning knob (process-wide, default on): the step uses pvae_fused_fwd where it is supported and the operand planes are kept
+ * (params_lo given); 0 = sampler, decoder GEMM and residual as three kernels. */
+int pvae_set_step_fused(int on);
+/* Timing experiments on pvae_fused_fwd (results are WRONG unless 0): 1 = no W_dec loads / MMAs, 2 = hi x hi product only. */
+int pvae_set_fused_debug(int mode);
 /* Tuning knob (process-wide, default on): pvae_lin_step_fwd_bwd reduces the wgrad split partials and the sampler's column
  * partials with ONE kernel instead of two split-K reductions + one or two column-sum kernels (bit-identical results). */
 int pvae_set_fuse_reduce(int on);

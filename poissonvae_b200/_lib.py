@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpvae_b200.so")
-SOURCES = ["capi.cu", "sampler.cu", "step.cu", "gemm_tc.cu", "lin_step.cu", "peer_allreduce.cu", "conv_tc.cu",
+SOURCES = ["capi.cu", "sampler.cu", "fused_fwd.cu", "step.cu", "gemm_tc.cu", "lin_step.cu", "peer_allreduce.cu", "conv_tc.cu",
            "conv_misc.cu", "conv_net.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -122,6 +122,10 @@ _SIGNATURES = {
     "pvae_set_step_overlap": (_i, [_i]),
     "pvae_set_step_trace": (_i, [_p, _i]),
     "pvae_set_step_coef": (_i, [_i]),
+    "pvae_set_step_fused": (_i, [_i]),
+    "pvae_set_fused_debug": (_i, [_i]),
+    "pvae_fused_fwd_supported": (_i, [_i64, _i64, _i64]),
+    "pvae_fused_fwd": (_i, [_p] * 14 + [_i64, _i64, _i64, _i64, _i, _f, _i, _i, _f, _f, _u64, _u64, _p, _p]),
     "pvae_lin_step_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i,
                                    _u64, _u64, _p, _p, _p]),
     "pvae_conv_weight_prep": (_i, [_p] * 6 + [_i] * 7 + [_p]),

@@ -1,0 +1,643 @@
+// Fused forward of the lin|lin P-VAE after the encoder GEMM (BASELINE config 2: "fused rsample + KL + decoder GEMM"):
+//
+//   h (B,K) -> softclamps, rate, KL row sums            main/vae.py:393-415, 446-450
+//           -> z = Poisson(rate).rsample(), dz_acc      base/distributions.py:55-81
+//           -> y = z W_dec^T                            main/vae.py:59-60   (tcgen05, z read from SHARED memory)
+//           -> g_y = 2 (y - x) / B, sum_d (y - x)^2     main/vae.py:68-72
+//
+// in ONE persistent kernel.  The sampler is instruction-issue bound on the SIMT pipes and leaves the tensor pipe idle, the
+// decoder GEMM is the opposite: here they share the SM.  A CTA owns a unit of <= 32 rows (B / #SMs of them, so that all
+// 148 SMs carry the same sampler load) and ALL K latents of those rows:
+//
+//   warps 0..21  sampler     per batch of 256 latents: uniform prologue (rates parked in shared memory; chains whose rate
+//                            predicts more than 8 events are listed), then groups of 8 lanes walk the listed long chains
+//                            (8 events per step), then a work pool over the batch's other rows x 64 quads (k-block major).
+//                            A finished quad is stored to global memory (z, its TF32 low plane, dz_acc - the backward needs
+//                            them) AND into the 128-byte-swizzled K-major operand tile of its k-block in shared memory;
+//                            then the lane arrives on that k-block's mbarrier (count = rows x 8 quads).
+//   warp 22      TMA + MMA   one thread streams W_dec (hi and lo planes, {32 k, 128 rows} boxes) through a 3-stage ring,
+//                            waits for a k-block of z and issues 3xTF32 tcgen05.mma for y^T = W_dec z^T: A = the W_dec tile
+//                            (M = 128 output columns), B = the z tile (N = 32 rows, no padding), accumulators hi / cross in
+//                            TMEM (lane = output column, column = row) - the tensor work hides under the sampler
+//   warps 0..7               epilogue of a unit: TMEM -> registers (a lane holds one output column of all 32 rows, so every
+//                            global access is a coalesced 128-byte row segment), residual against x, g_y (+ low plane),
+//                            squared error per row
+//
+// Full rows per CTA mean no split-K partials: y is complete in TMEM, so the reconstruction residual is fused too.
+// Per-chain arithmetic, Philox counters and exit rules are those of sampler.cu (sampler_device.cuh): a quad finished by
+// the pool is bit-identical to pvae_sampler_fwd, one finished by a lane group within a few ulp (prefix-sum order).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pvae_b200.h"
+#include "pvae_device.cuh"
+#include "pvae_host.h"
+#include "sampler_device.cuh"
+#include "tc_common.cuh"
+
+namespace pvae {
+
+constexpr int kFsWarps = 22;                  // sampler warps
+constexpr int kFsLanes = kFsWarps * 32;       // 640 sampler threads
+constexpr int kFsThreads = kFsLanes + 32;     // + the TMA / MMA warp
+constexpr int kFsRows = 32;                   // rows per unit = N of the MMA
+constexpr int kFsKb = 8;                      // k-blocks (32 latents) per batch
+constexpr int kFsBatchK = kFsKb * 32;         // 256 latents per batch
+constexpr int kFsPool = kFsRows * kFsKb * 8;  // 2048 pool entries (quads) per batch
+constexpr int kFsMaxK = 1024;
+constexpr int kFsWStages = 3;
+constexpr uint32_t kFsZTile = 32 * 128;       // one plane of a 32-row x 32-latent operand tile
+constexpr uint32_t kFsWTile = 128 * 128;      // one plane of a 128-row x 32-latent W_dec tile
+constexpr uint32_t kFsWStage = 2 * kFsWTile;
+
+constexpr uint32_t kOffZ = 0;                                      // [kb][plane][32 rows x 128 B]
+constexpr uint32_t kOffW = kOffZ + kFsKb * 2 * kFsZTile;           // 64 KB
+constexpr uint32_t kOffRate = kOffW + kFsWStages * kFsWStage;      // + 96 KB
+constexpr uint32_t kOffParked = kOffRate + 4 * kFsPool * 4;        // + 32 KB
+constexpr uint32_t kOffKl = kOffParked + 2 * kFsPool * 2;          // + 8 KB (two lists)
+constexpr uint32_t kOffElr = kOffKl + 2 * kFsMaxK * 4;             // + 8 KB   [2][K / 32][32]
+constexpr uint32_t kOffRecon = kOffElr + kFsMaxK * 4;              // + 4 KB
+constexpr uint32_t kOffMax = kOffRecon + 2 * 8 * 32 * 4;           // + 2 KB
+constexpr uint32_t kOffBar = kOffMax + 128;
+constexpr uint32_t kFsSmem = kOffBar + 256 + 1024;                 // barriers + cursors, alignment slack
+constexpr uint32_t kFsTmemCols = 128;                              // per column half: 32 (hi) + 32 (cross)
+
+struct FusedParams {
+  SamplerParams sp;
+  const float* x;   // (B,D)
+  float* g_y;       // (B,D)  2 (y - x) / B_global
+  float* g_y_lo;    // optional TF32 low plane of g_y
+  float* recon;     // (B)    sum_d (y - x)^2
+  int D;
+  int rows_unit;    // rows per unit (<= 32)
+  int n_units;
+  float g_scale;
+  float t_need;     // arrival time beyond which a chain can end; rate * t_need ~ events a chain walks
+  float park_events;
+  int debug;        // timing experiments: 1 = no W_dec loads / MMAs, 2 = hi x hi product only
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void sts4(uint32_t addr, const float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// one warp reads 32 TMEM lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+
+template <int IND>
+__global__ void __launch_bounds__(kFsThreads, 1)
+fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_w_lo, const __grid_constant__ FusedParams fp) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const SamplerParams& p = fp.sp;
+  float* const s_rate = reinterpret_cast<float*>(smem + kOffRate);  // [4][kFsPool]
+  unsigned short* const s_parked = reinterpret_cast<unsigned short*>(smem + kOffParked);
+  float* const s_kl = reinterpret_cast<float*>(smem + kOffKl);
+  float* const s_elr = reinterpret_cast<float*>(smem + kOffElr);
+  float* const s_recon = reinterpret_cast<float*>(smem + kOffRecon);
+  float* const s_max = reinterpret_cast<float*>(smem + kOffMax);
+  uint64_t* const z_full = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* const w_full = z_full + kFsKb;
+  uint64_t* const w_empty = w_full + kFsWStages;
+  uint64_t* const batch_done = w_empty + kFsWStages;
+  uint64_t* const acc_full = batch_done + 1;
+  uint64_t* const acc_empty = acc_full + 1;
+  // two sets (batch parity) of {pool cursor, long chains listed by the prologue, its cursor, late parks, its cursor}
+  int* const s_cnt = reinterpret_cast<int*>(acc_empty + 1);
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(s_cnt + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = static_cast<int>(p.K), Kq = K >> 2, D = fp.D;
+  const int nkb = K / 32, nbatch = K / kFsBatchK, halves = D / 128;
+  const int R = fp.rows_unit;
+  const int n_ep = halves * 4;  // epilogue warps: (column half, TMEM lane quarter)
+
+  if (warp == kFsWarps) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_w)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_w_lo)) : "memory");
+      for (int i = 0; i < kFsKb; ++i) mbar_init(&z_full[i], static_cast<uint32_t>(R * 8));
+      for (int i = 0; i < kFsWStages; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
+      mbar_init(batch_done, 1);
+      mbar_init(acc_full, 1);
+      mbar_init(acc_empty, static_cast<uint32_t>(n_ep));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kFsTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == kFsWarps) {
+    // ===== W_dec loads (TMA) and MMA issue, one thread: the tile of iteration it + kFsWStages is requested as soon as the
+    // MMAs of iteration it have been committed AND the next iteration's MMAs are queued (the tensor pipe never waits for it)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, kFsRows, false, false);  // M = 128 output columns, N = 32 rows
+      int n_my = 0;
+      for (int u = blockIdx.x; u < fp.n_units; u += gridDim.x) ++n_my;
+      const uint32_t per_unit = static_cast<uint32_t>(nkb * halves), total = per_unit * n_my;
+      auto load = [&](uint32_t j) {  // W_dec tile (hi, lo) of iteration j: k-block (j % per_unit) / halves, column half j % halves
+        const uint32_t s = j % kFsWStages, w = j % per_unit;
+        if (j >= kFsWStages) mbar_wait(&w_empty[s], ((j / kFsWStages) - 1) & 1);
+        uint8_t* dst = smem + kOffW + s * kFsWStage;
+        mbar_expect_tx(&w_full[s], fp.debug == 2 ? kFsWTile : kFsWStage);
+        tma_load_2d(&tma_w, &w_full[s], dst, static_cast<int>(w / halves) * 32, static_cast<int>(w % halves) * 128);
+        if (fp.debug != 2) tma_load_2d(&tma_w_lo, &w_full[s], dst + kFsWTile, static_cast<int>(w / halves) * 32, static_cast<int>(w % halves) * 128);
+      };
+      const bool no_mma = fp.debug == 1, hi_only = fp.debug == 2;
+      for (uint32_t j = 0; j < kFsWStages && j < total && !no_mma; ++j) load(j);
+      uint32_t it = 0, bi = 0, ui = 0;
+      for (int u = blockIdx.x; u < fp.n_units; u += gridDim.x, ++ui) {
+        if (ui > 0) {  // the previous unit's epilogue has read the accumulators
+          mbar_wait(acc_empty, (ui - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        for (int b = 0; b < nbatch; ++b, ++bi) {
+          for (int kb = 0; kb < kFsKb; ++kb) {
+            mbar_wait(&z_full[kb], bi & 1);
+            // the sampler lanes' generic-proxy stores of this k-block, acquired through the barrier, become visible to the
+            // tensor core's (async-proxy) operand reads
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t za = smem_u32(smem + kOffZ + kb * 2 * kFsZTile), zl = za + kFsZTile;
+            for (int hf = 0; hf < halves && !no_mma; ++hf, ++it) {
+              const uint32_t s = it % kFsWStages;
+              mbar_wait(&w_full[s], (it / kFsWStages) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t wb = smem_u32(smem + kOffW + s * kFsWStage), wl = wb + kFsWTile;
+              const uint32_t d_hi = tmem_base + hf * 64, d_x = d_hi + 32;
+#pragma unroll
+              for (int k = 0; k < kBK / kUmmaK; ++k) {
+                const uint64_t da = make_smem_desc(za + k * 32, 16, 1024, 2), dal = make_smem_desc(zl + k * 32, 16, 1024, 2);
+                const uint64_t db = make_smem_desc(wb + k * 32, 16, 1024, 2), dbl = make_smem_desc(wl + k * 32, 16, 1024, 2);
+                const uint32_t acc = (b > 0 || kb > 0 || k > 0) ? 1u : 0u;
+                umma_tf32(d_hi, db, da, idesc, acc);   // hi(W) hi(z)
+                if (!hi_only) {
+                  umma_tf32(d_x, dbl, da, idesc, acc);   // lo(W) hi(z)
+                  umma_tf32(d_x, db, dal, idesc, 1u);    // hi(W) lo(z)
+                }
+              }
+              umma_commit(&w_empty[s]);
+              if (it >= 1 && it - 1 + kFsWStages < total) load(it - 1 + kFsWStages);  // refill the stage of the previous iteration
+            }
+          }
+          umma_commit(batch_done);  // the operand tiles of this batch have been read
+        }
+        umma_commit(acc_full);
+      }
+    }
+  } else {
+    // ===== sampler warps =====
+    uint64_t off = p.offset;
+    if (p.offset_dev != nullptr) off += *p.offset_dev;
+    const uint32_t off_lo = static_cast<uint32_t>(off), off_hi = static_cast<uint32_t>(off >> 32);
+    const int n_a = min(p.phase_a, p.n_exp);
+    const float t_exit = p.t_exit, absorb = p.absorb;
+    const unsigned lanes_below = (1u << lane) - 1u;
+    const uint32_t zst = smem_u32(smem + kOffZ), zbar0 = smem_u32(z_full);
+    const int pool_n = R * kFsKb * 8;  // entries of a batch, k-block major: entry = (kb * R + r) * 8 + cq
+    const int ekb = R * 8;             // entries per k-block
+    const uint32_t rmagic = (65536u + R - 1) / R;  // x / R == (x * rmagic) >> 16 for x < 256, R <= 32
+    float rmax = 0.f;
+
+    for (int k = tid; k < K; k += kFsLanes) s_elr[k] = expf(__ldg(p.log_r + k));
+    if (tid < 16) s_cnt[tid] = (tid & 7) == 0 ? kFsLanes : 0;
+    named_bar_sync(1, kFsLanes);
+
+    uint32_t bi = 0, ui = 0;
+    for (int u = blockIdx.x; u < fp.n_units; u += gridDim.x, ++ui) {
+      const long long row0 = static_cast<long long>(u) * R;
+      const int nrows = static_cast<int>(min(static_cast<long long>(R), p.B - row0));
+      float* const kl_tab = s_kl + (ui & 1) * kFsMaxK;  // [k-block of the row][32 rows]
+      const uint32_t quad0 = static_cast<uint32_t>(((p.row_offset + row0) * p.K) >> 2);
+      float* const z0 = p.z + row0 * p.K;
+      float* const zlo0 = p.z_lo != nullptr ? p.z_lo + row0 * p.K : nullptr;
+      float* const dz0 = p.dz_out + row0 * p.K;
+
+#pragma unroll 1
+      for (int b = 0; b < nbatch; ++b, ++bi) {
+        int* const cnt = s_cnt + (bi & 1) * 8;  // [0] pool cursor, [1] listed long chains, [2] its cursor, [3] late parks, [4] its cursor
+        // ---- stage 1: prologue of the batch (uniform, coalesced: 8 lanes = the 32 latents of one row of one k-block)
+#pragma unroll 1
+        for (int e = tid; e < pool_n; e += kFsLanes) {
+          const int kb = static_cast<int>(((static_cast<uint32_t>(e) >> 3) * rmagic) >> 16), rem = e - kb * ekb, r = rem >> 3, cq = rem & 7;
+          float klsum = 0.f;
+          bool pre = false;
+          if (r < nrows) {
+            const int k = b * kFsBatchK + kb * 32 + cq * 4;
+            const float4 lr4 = ldg4(p.log_r + k);
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.b_enc != nullptr) bias4 = ldg4(p.b_enc + k);
+            const float4 hv4 = ldg4(p.h + (row0 + r) * p.K + k);
+            const float4 elr4 = *reinterpret_cast<const float4*>(s_elr + k);
+            const float hv[4] = {hv4.x, hv4.y, hv4.z, hv4.w}, lr[4] = {lr4.x, lr4.y, lr4.z, lr4.w};
+            const float bias[4] = {bias4.x, bias4.y, bias4.z, bias4.w}, elr[4] = {elr4.x, elr4.y, elr4.z, elr4.w};
+            float klv[4], qmax = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const Latent q = prologue<false, false>(p, hv[j], lr[j], bias[j]);
+              s_rate[j * kFsPool + e] = q.rate;
+              qmax = fmaxf(qmax, q.rate);
+              const float d = q.log_dr;
+              klv[j] = elr[j] * (1.f + expf(d) * (d - 1.f));  // main/vae.py:448-449
+            }
+            rmax = fmaxf(rmax, qmax);
+            klsum = (klv[0] + klv[1]) + (klv[2] + klv[3]);
+            // a chain at this rate walks about rate * t_need events: the long ones are walked by lane groups, first
+            pre = qmax * fp.t_need > fp.park_events;
+          }
+          klsum += __shfl_xor_sync(0xffffffffu, klsum, 1);
+          klsum += __shfl_xor_sync(0xffffffffu, klsum, 2);
+          klsum += __shfl_xor_sync(0xffffffffu, klsum, 4);
+          if (cq == 0 && r < nrows) kl_tab[(b * kFsKb + kb) * 32 + r] = klsum;
+          const unsigned pm = __ballot_sync(0xffffffffu, pre);
+          if (pm != 0u) {
+            int pbase = 0;
+            if (lane == 0) pbase = atomicAdd(&cnt[1], __popc(pm));
+            pbase = __shfl_sync(0xffffffffu, pbase, 0);
+            if (pre) s_parked[pbase + __popc(pm & lanes_below)] = static_cast<unsigned short>(e);
+          }
+        }
+        if (bi > 0) mbar_wait(batch_done, (bi - 1) & 1);  // the tensor core has read the previous batch's operand tiles
+        named_bar_sync(1, kFsLanes);
+        if (tid < 8) s_cnt[((bi + 1) & 1) * 8 + tid] = tid == 0 ? kFsLanes : 0;  // the next batch's counters (idle since batch bi - 1)
+
+        // pass 0: the listed long chains (lane groups).  pass 1: the pool over everything else, then the chains that turned
+        // out long on the way (lane groups again).
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          if (pass == 1) {
+            int cur = tid;
+            bool has = cur < pool_n, live = false, skip = false;
+            int n = 0, ebase = 0;
+            uint32_t quad = 0, zaddr = 0, zbar = 0;
+            float rate[4], inv_rate[4], t[4], acc[4], acc2[4];
+            auto fetch = [&]() {
+              live = false, skip = false;
+              if (has) {
+                const int kb = static_cast<int>(((static_cast<uint32_t>(cur) >> 3) * rmagic) >> 16), rem = cur - kb * ekb, r = rem >> 3, cq = rem & 7;
+                zbar = zbar0 + kb * 8;
+                if (r < nrows) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) rate[j] = s_rate[j * kFsPool + cur];
+                  if (fmaxf(fmaxf(rate[0], rate[1]), fmaxf(rate[2], rate[3])) * fp.t_need > fp.park_events) {
+                    skip = true;  // listed by the prologue, walked in pass 0
+                  } else {
+                    live = true;
+                    const int qi = r * Kq + b * (kFsBatchK / 4) + kb * 8 + cq;
+                    ebase = qi << 2;
+                    quad = quad0 + static_cast<uint32_t>(qi);
+                    zaddr = zst + kb * (2 * kFsZTile) + r * 128 + ((cq ^ (r & 7)) << 4);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      inv_rate[j] = recip_for_div(rate[j]);
+                      t[j] = acc[j] = acc2[j] = 0.f;
+                    }
+                    n = 0;
+                  }
+                }
+              }
+            };
+            fetch();
+            while (__any_sync(0xffffffffu, has)) {
+              bool fin = false, park = false;
+              if (has && !live) {
+                if (!skip) mbar_arrive_u32(zbar);  // a row beyond the batch: nothing to sample, but the k-block's count expects the entry
+                fin = true;
+              } else if (live) {
+                const uint4 rr = philox4x32_10(quad, static_cast<uint32_t>(n), off_lo, off_hi, p.ks);
+                const uint32_t bits[4] = {rr.x, rr.y, rr.z, rr.w};
+                float excess = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float e = exponential_from_bits(bits[j]);
+                  t[j] = __fadd_rn(t[j], div_by_rate<false>(e, rate[j], inv_rate[j]));
+                  float f, df = 0.f;
+                  soft_term<IND, true>(p, t[j], f, df);
+                  acc[j] += f;
+                  excess = fmaxf(excess, fmaf(-absorb, acc[j], f));
+                  const float g = df * t[j];
+                  acc2[j] += g;
+                  excess = fmaxf(excess, fmaf(-absorb, acc2[j], g));
+                }
+                ++n;
+                const float tmin = fminf(fminf(t[0], t[1]), fminf(t[2], t[3]));
+                if (tmin > t_exit || (absorb > 0.f && tmin > 1.f && excess <= 0.f) || n >= p.n_exp) {  // chain complete
+                  const float4 zv = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                  stg4_planes(z0, zlo0, ebase, zv);
+                  stg4(dz0 + ebase, make_float4(acc2[0], acc2[1], acc2[2], acc2[3]));
+                  sts4(zaddr, zv);
+                  sts4(zaddr + kFsZTile, tf32_lo4f(zv));
+                  mbar_arrive_u32(zbar);  // release; the issuer's acquire + proxy fence order these stores before the MMA's reads
+                  fin = true;
+                } else if (n >= n_a) {
+                  fin = park = true;
+                }
+              }
+              const unsigned fm = __ballot_sync(0xffffffffu, fin);
+              if (fm != 0u) {
+                const unsigned pm = __ballot_sync(0xffffffffu, park);
+                int first = 0, pbase = 0;
+                if (lane == 0) {
+                  first = atomicAdd(&cnt[0], __popc(fm));
+                  if (pm != 0u) pbase = atomicAdd(&cnt[3], __popc(pm));
+                }
+                first = __shfl_sync(0xffffffffu, first, 0);
+                pbase = __shfl_sync(0xffffffffu, pbase, 0);
+                if (park) s_parked[kFsPool + pbase + __popc(pm & lanes_below)] = static_cast<unsigned short>(cur);
+                if (fin) {
+                  cur = first + __popc(fm & lanes_below);
+                  has = cur < pool_n;
+                  fetch();
+                }
+              }
+            }
+            named_bar_sync(1, kFsLanes);  // every late long chain is on the list
+          }
+
+          // ---- groups of kGroup lanes walk the listed chains from their first event, kGroup events per step
+          const unsigned short* const list = s_parked + pass * kFsPool;
+          const int n_parked = cnt[1 + 2 * pass];
+          int* const cursor = &cnt[2 + 2 * pass];
+          if (n_parked > 0) {
+            const int gl = lane % kGroup;
+            bool has = false, done = true;
+            int ebase = 0, n0 = 0;
+            uint32_t quad = 0, zaddr = 0, zbar = 0;
+            float rate[4] = {1.f, 1.f, 1.f, 1.f}, inv_rate[4] = {1.f, 1.f, 1.f, 1.f}, t0[4] = {0.f, 0.f, 0.f, 0.f};
+            float part[4] = {0.f, 0.f, 0.f, 0.f}, part2[4] = {0.f, 0.f, 0.f, 0.f};
+            bool exhausted = false;  // warp-uniform: the list has no more entries
+            while (true) {
+              if (__any_sync(0xffffffffu, done)) {
+                float tot[4], tot2[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float v = part[j], v2 = part2[j];
+#pragma unroll
+                  for (int o = kGroup / 2; o > 0; o >>= 1) {
+                    v += __shfl_xor_sync(0xffffffffu, v, o, kGroup);
+                    v2 += __shfl_xor_sync(0xffffffffu, v2, o, kGroup);
+                  }
+                  tot[j] = v, tot2[j] = v2;
+                }
+                if (done && gl == 0 && has) {
+                  const float4 zv = make_float4(tot[0], tot[1], tot[2], tot[3]);
+                  stg4_planes(z0, zlo0, ebase, zv);
+                  stg4(dz0 + ebase, make_float4(tot2[0], tot2[1], tot2[2], tot2[3]));
+                  sts4(zaddr, zv);
+                  sts4(zaddr + kFsZTile, tf32_lo4f(zv));
+                  mbar_arrive_u32(zbar);
+                }
+                int next = 0;
+                {
+                  const unsigned req = __ballot_sync(0xffffffffu, done && gl == 0);
+                  int first = n_parked;
+                  if (lane == 0 && !exhausted) first = atomicAdd(cursor, __popc(req));
+                  first = __shfl_sync(0xffffffffu, first, 0);
+                  next = first + __popc(req & lanes_below);
+                  exhausted = first + __popc(req) >= n_parked;
+                }
+                next = __shfl_sync(0xffffffffu, next, 0, kGroup);
+                if (done) {
+                  has = next < n_parked;
+                  if (has) {
+                    const int cur = list[next];
+                    const int kb = static_cast<int>(((static_cast<uint32_t>(cur) >> 3) * rmagic) >> 16), rem = cur - kb * ekb, r = rem >> 3, cq = rem & 7;
+                    const int qi = r * Kq + b * (kFsBatchK / 4) + kb * 8 + cq;
+                    ebase = qi << 2;
+                    quad = quad0 + static_cast<uint32_t>(qi);
+                    zaddr = zst + kb * (2 * kFsZTile) + r * 128 + ((cq ^ (r & 7)) << 4);
+                    zbar = zbar0 + kb * 8;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      rate[j] = s_rate[j * kFsPool + cur];
+                      inv_rate[j] = recip_for_div(rate[j]);
+                      t0[j] = 0.f, part[j] = 0.f, part2[j] = 0.f;
+                    }
+                    n0 = 0;
+                  }
+                  done = false;
+                }
+                if (__all_sync(0xffffffffu, !has)) break;
+              }
+              const int n = n0 + gl;
+              const bool valid = has && !done && n < p.n_exp;
+              const uint4 rr = philox4x32_10(quad, static_cast<uint32_t>(n), off_lo, off_hi, p.ks);
+              const uint32_t bits[4] = {rr.x, rr.y, rr.z, rr.w};
+              float excess = 0.f;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float x = valid ? div_by_rate<false>(exponential_from_bits(bits[j]), rate[j], inv_rate[j]) : 0.f;
+#pragma unroll
+                for (int o = 1; o < kGroup; o <<= 1) {  // inclusive prefix sum over the group's lanes
+                  const float y = __shfl_up_sync(0xffffffffu, x, o, kGroup);
+                  if (gl >= o) x += y;
+                }
+                const float t = t0[j] + x;
+                float f, df = 0.f;
+                soft_term<IND, true>(p, t, f, df);
+                const float g = df * t;
+                part[j] += valid ? f : 0.f;
+                // the group's last lane holds the smallest term of the step, its first lane the largest partial sum (a lower
+                // bound of the chain's running total)
+                excess = fmaxf(excess, fmaf(-absorb, __shfl_sync(0xffffffffu, part[j], 0, kGroup), f));
+                part2[j] += valid ? g : 0.f;
+                excess = fmaxf(excess, fmaf(-absorb, __shfl_sync(0xffffffffu, part2[j], 0, kGroup), g));
+                t0[j] = __shfl_sync(0xffffffffu, t, kGroup - 1, kGroup);
+              }
+              n0 += kGroup;
+              const float tmin = fminf(fminf(t0[0], t0[1]), fminf(t0[2], t0[3]));
+              const bool absorbed = absorb > 0.f && __shfl_sync(0xffffffffu, excess <= 0.f ? 1 : 0, kGroup - 1, kGroup) != 0 && tmin > 1.f;
+              if (has && (n0 >= p.n_exp || tmin > t_exit || absorbed)) done = true;
+            }
+          }
+        }  // passes
+        named_bar_sync(1, kFsLanes);  // the rate table and the lists are reused by the next batch
+      }  // batches
+
+      // ---- unit epilogue: KL row sums (k-blocks in order: deterministic), then the reconstruction residual from TMEM
+      if (p.kl_rowsum != nullptr && warp == kFsWarps - 1 && lane < nrows) {  // the last sampler warp (not an epilogue warp)
+        float s = 0.f;
+        for (int kbg = 0; kbg < nkb; ++kbg) s += kl_tab[kbg * 32 + lane];
+        p.kl_rowsum[row0 + lane] = s;
+      }
+      if (warp < n_ep) {
+        // accumulator lane = output column, accumulator column = row of the unit: this lane owns column `col` of all rows
+        const int q = warp & 3, hf = warp >> 2;
+        const int col = hf * 128 + q * 32 + lane;
+        mbar_wait(acc_full, ui & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + hf * 64;
+        float* const rec = s_recon + (ui & 1) * 256 + warp * 32;
+#pragma unroll 1
+        for (int r0 = 0; r0 < kFsRows; r0 += 16) {
+          uint32_t v[16], w[16];
+          tmem_ld_32x16(tcol + r0, v);
+          tmem_ld_32x16(tcol + 32 + r0, w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = r0 + i;
+            float sq = 0.f;
+            if (r < nrows) {  // warp-uniform
+              const long long gi = (row0 + r) * D + col;
+              const float res = (__uint_as_float(v[i]) + __uint_as_float(w[i])) - __ldg(fp.x + gi);
+              const float gv = fp.g_scale * res;
+              fp.g_y[gi] = gv;
+              if (fp.g_y_lo != nullptr) fp.g_y_lo[gi] = tf32_lo(gv);
+              sq = res * res;
+            }
+            sq = warp_sum(sq);
+            if (lane == 0) rec[r] = sq;
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_u32(smem_u32(acc_empty));
+        named_bar_sync(2, n_ep * 32);
+        if (warp == 0 && lane < nrows) {
+          const float* all = s_recon + (ui & 1) * 256;
+          float s = all[lane];
+          for (int j = 1; j < n_ep; ++j) s += all[j * 32 + lane];
+          fp.recon[row0 + lane] = s;
+        }
+      }
+    }  // units
+
+    if (p.rate_max != nullptr) {
+      const float m = warp_max(rmax);
+      if (lane == 0) s_max[warp] = m;
+      named_bar_sync(1, kFsLanes);
+      if (tid == 0) {
+        float mm = s_max[0];
+#pragma unroll
+        for (int w = 1; w < kFsWarps; ++w) mm = fmaxf(mm, s_max[w]);
+        atomicMax(reinterpret_cast<int*>(p.rate_max), __float_as_int(mm));  // rates are > 0
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kFsWarps) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kFsTmemCols));
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+static int g_fused_debug = 0;
+
+static int fused_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    sms = n;
+  }
+  return sms;
+}
+
+// rows per unit: the batch dealt out evenly over m units per SM, m the smallest count that keeps a unit within 32 rows
+static int fused_rows_per_unit(int64_t B) {
+  const int64_t sms = fused_sms();
+  const int64_t m = (B + sms * kFsRows - 1) / (sms * kFsRows);
+  return static_cast<int>((B + sms * m - 1) / (sms * m));
+}
+
+int fused_fwd_supported(int64_t B, int64_t K, int64_t D) {
+  if (B <= 0 || K <= 0 || K % kFsBatchK || K > kFsMaxK || (D != 128 && D != 256)) return 0;
+  return fused_rows_per_unit(B) >= 12;  // below that the pool of a batch is too shallow for 640 lanes
+}
+
+template <int IND>
+static cudaError_t launch_fused(const CUtensorMap& mw, const CUtensorMap& mwl, const FusedParams& fp, int grid, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(fused_fwd_kernel<IND>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFsSmem));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  return launch_pdl(fused_fwd_kernel<IND>, dim3(static_cast<unsigned>(grid)), dim3(kFsThreads), kFsSmem, s, mw, mwl, fp);
+}
+
+int fused_fwd_impl(const float* h, const float* log_r, const float* b_enc, const float* w_dec, const float* w_dec_lo, const float* x, float* z,
+                   float* z_lo, float* dz_acc, float* g_y, float* g_y_lo, float* recon, float* kl_rowsum, float* rate_max, int64_t B, int64_t K,
+                   int64_t D, int64_t row_offset, int n_exp, float temp, int indicator, int exc_only, float exit_logit, float g_scale,
+                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream) {
+  if (!fused_fwd_supported(B, K, D))
+    return fail(PVAE_ERR_UNSUPPORTED, "pvae_fused_fwd: B=%lld K=%lld D=%lld outside the fused kernel's shapes (K %% 256 == 0, K <= 1024, D in {128, 256}, B >= 12 rows per SM)",
+                (long long)B, (long long)K, (long long)D);
+  if (!h || !log_r || !w_dec || !w_dec_lo || !x || !z || !dz_acc || !g_y || !recon)
+    return fail(PVAE_ERR_INVALID, "pvae_fused_fwd: null pointer");
+  if (!(temp > 0.f)) return fail(PVAE_ERR_INVALID, "pvae_fused_fwd: the training forward needs temp > 0, got %g", temp);
+  if (n_exp < 1 || indicator < 0 || indicator > 4 || row_offset < 0) return fail(PVAE_ERR_INVALID, "pvae_fused_fwd: bad n_exp / indicator / row_offset");
+  if (((row_offset + B) * K) >> 2 > 0xFFFFFFFFll) return fail(PVAE_ERR_UNSUPPORTED, "pvae_fused_fwd: more than 2^34 latents");
+  FusedParams fp{};
+  SamplerParams& p = fp.sp;
+  p.h = h, p.log_r = log_r, p.b_enc = b_enc, p.z = z, p.z_lo = z_lo, p.dz_out = dz_acc, p.kl_rowsum = kl_rowsum, p.rate_max = rate_max;
+  p.B = B, p.K = K, p.row_offset = row_offset;
+  sampler_set_chain(p, n_exp, temp, indicator, exit_logit);
+  p.clamp_dr = 10.f, p.clamp_rate = 5.f, p.exc_only = exc_only;  // main/vae.py:403-409
+  p.offset = offset, p.offset_dev = offset_dev;
+  philox_key_schedule(seed, p.ks);
+  fp.x = x, fp.g_y = g_y, fp.g_y_lo = g_y_lo, fp.recon = recon, fp.D = static_cast<int>(D), fp.g_scale = g_scale;
+  fp.rows_unit = fused_rows_per_unit(B);
+  fp.n_units = static_cast<int>((B + fp.rows_unit - 1) / fp.rows_unit);
+  // a chain ends once its arrival time passes t_need: the absorbed-exit rule needs terms below 2^-34 of the sum, i.e.
+  // t - 1 > 23.6 temp (sigmoid); without it the chain runs to t_exit
+  fp.t_need = p.absorb > 0.f ? std::min(1.f + 24.f * temp, p.t_exit) : p.t_exit;
+  fp.debug = g_fused_debug;
+  fp.park_events = static_cast<float>((p.phase_a < n_exp ? p.phase_a : n_exp) - 1);
+  CUtensorMap mw, mwl;
+  {
+    const long long dims[2] = {K, D}, strides[1] = {K * 4};
+    const int box[2] = {32, 128}, estr[2] = {1, 1};
+    if (int rc = make_tensor_map(&mw, w_dec, 2, dims, strides, box, estr, 0)) return rc;
+    if (int rc = make_tensor_map(&mwl, w_dec_lo, 2, dims, strides, box, estr, 0)) return rc;
+  }
+  const int grid = std::min(fp.n_units, fused_sms());
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  switch (indicator) {
+    case kSigmoid: e = launch_fused<kSigmoid>(mw, mwl, fp, grid, s); break;
+    case kCosine: e = launch_fused<kCosine>(mw, mwl, fp, grid, s); break;
+    case kLinear: e = launch_fused<kLinear>(mw, mwl, fp, grid, s); break;
+    case kCubic: e = launch_fused<kCubic>(mw, mwl, fp, grid, s); break;
+    default: e = launch_fused<kQuintic>(mw, mwl, fp, grid, s); break;
+  }
+  return cuda_ok("pvae_fused_fwd", e);
+}
+
+}  // namespace pvae
+
+extern "C" int pvae_set_fused_debug(int mode) {
+  pvae::g_fused_debug = mode;
+  return PVAE_OK;
+}
+
+extern "C" int pvae_fused_fwd_supported(int64_t B, int64_t K, int64_t D) { return pvae::fused_fwd_supported(B, K, D); }
+
+extern "C" int pvae_fused_fwd(const float* h, const float* log_r, const float* b_enc, const float* w_dec, const float* w_dec_lo, const float* x,
+                              float* z, float* z_lo, float* dz_acc, float* g_y, float* g_y_lo, float* recon, float* kl_rowsum,
+                              float* rate_max, int64_t B, int64_t K, int64_t D, int64_t row_offset, int n_exp, float temp, int indicator,
+                              int exc_only, float exit_logit, float g_scale, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                              void* stream) {
+  return pvae::fused_fwd_impl(h, log_r, b_enc, w_dec, w_dec_lo, x, z, z_lo, dz_acc, g_y, g_y_lo, recon, kl_rowsum, rate_max, B, K, D,
+                              row_offset, n_exp, temp, indicator, exc_only, exit_logit, g_scale, seed, offset, offset_dev, stream);
+}

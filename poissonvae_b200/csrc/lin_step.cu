@@ -41,6 +41,7 @@ SideStream* side_stream() {
 void* const* g_trace = nullptr;  // pvae_set_step_trace: CUDA events recorded between the main-stream launches of a step
 int g_trace_n = 0;
 int g_overlap = 1;
+int g_fused = 1;  // pvae_set_step_fused: sampler + decoder GEMM + residual in one kernel where supported
 int g_coef = 0;  // pvae_set_step_coef: the forward sampler leaves the backward's coefficients (streaming backward); measured slower
 int g_dec_splits = 0;   // K-splits of the decoder GEMM (pvae_set_dec_splits); 0 = automatic
 int g_fuse_reduce = 1;  // pvae_lin_step_fwd_bwd: reduce all gradient partials with one kernel (bit-identical to the three)
@@ -162,6 +163,21 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   if ((rc = gemm(d.x, x_lo, w_enc, w_enc_lo, w.h, B, K, D, 1, 1, 1, nullptr, s))) return rc;
   trace();  // 2: encoder GEMM
   mark(0);
+  const bool fused = g_fused && planes && !coef && pvae::fused_fwd_supported(B, K, D);
+  int recon_parts = static_cast<int>(pvae_gemm_residual_parts(D));
+  const float g_scale = 2.0f / static_cast<float>(B_global);
+  if (fused) {
+    // one kernel: rsample + KL row sums + decoder GEMM (z through shared memory) + residual; y is complete in TMEM
+    if ((rc = pvae::fused_fwd_impl(w.h, log_r, b_enc, w_dec, w_dec_lo, d.x, w.z, z_lo, w.dz, w.g_y, g_y_lo, w.recon, w.klrow, d.rate_max, B, K,
+                                   D, d.row_offset, d.n_exp, d.temp, d.indicator, d.exc_only, d.exit_logit, g_scale, d.seed, d.offset,
+                                   d.offset_dev, s)))
+      return rc;
+    mark(1);
+    trace();  // 3: fused forward
+    trace();  // 4, 5: (no separate decoder GEMM / residual)
+    trace();
+    recon_parts = 1;
+  } else {
   if (coef) {
     // coefficient mode: the forward leaves d z / d u, the clamp derivative and the KL gradient term per latent and the
     // KL's column sums per block; the backward is then a streaming kernel instead of a second evaluation of the prologue
@@ -177,14 +193,12 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   mark(1);
   trace();  // 3: sampler forward
   // decoder GEMM with the residual fused into its epilogue: g_y and per-tile squared errors, y itself is never stored
-  int recon_parts = static_cast<int>(pvae_gemm_residual_parts(D));
   // automatic: the decoder's K loop (K / 32 blocks) is the longest serial stretch of any GEMM of the step; when two
   // K-halves of every 128 x 128 tile still fit one wave of CTAs, split it (measured at config 2: 115.0 -> 111.6 us per
   // step; four splits: 116.9)
   int want = g_dec_splits;
   if (want == 0) want = (K >= 512 && ((B + 127) / 128) * ((D + 127) / 128) * 2 <= 160) ? 2 : 1;
   const int dsp = want > 1 ? pvae_gemm_effective_splits(K, want) : 1;
-  const float g_scale = 2.0f / static_cast<float>(B_global);
   if (dsp > 1) {  // split-K partials (in the not-yet-used wgrad workspace) + one kernel that sums them into the residual
     if ((rc = gemm(w.z, z_lo, w_dec, w_dec_lo, nullptr, B, D, K, 1, 1, dsp, w.ydec, s))) return rc;
     trace();  // 4: decoder GEMM
@@ -194,6 +208,7 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   } else if ((rc = pvae::gemm_impl(w.z, z_lo, w_dec, w_dec_lo, nullptr, B, D, K, 1, 1, precise, 1, nullptr, d.x, w.g_y, g_y_lo, w.recon, g_scale,
                                    64, s))) {
     return rc;
+  }
   }
   // ---- backward.  Off the critical path (decoder wgrad, loss assembly) goes to a side stream so that it fills
   // the SMs the dgrad GEMM leaves idle and overlaps the elementwise sampler backward.
@@ -287,6 +302,11 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   trace();  // 9: join + gradient reduction / Adamax
   if (upd && d.state)  // graph replay: advance the device-side step counter / Philox offset, move rate.max() to its slot
     return pvae::advance_state(d.state, d.philox_increment, d.rate_max, d.rmax_ring, d.ring_n, s);
+  return PVAE_OK;
+}
+
+extern "C" int pvae_set_step_fused(int on) {
+  g_fused = on != 0;
   return PVAE_OK;
 }
 

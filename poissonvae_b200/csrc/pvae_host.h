@@ -71,6 +71,12 @@ int sampler_bwd_coef_impl(const float* g_z, const float* c_a, const float* c_ddr
                           float* g_h_lo, float* partial_ws, int want_bias, const float* klcol, int64_t klcol_rows, float* g_log_r,
                           float* g_b_enc, int64_t B, int64_t K, void* stream);
 int64_t sampler_bwd_coef_rows(int64_t B);  // rows of column partials sampler_bwd_coef_impl writes
+// fused_fwd.cu: sampler + KL + decoder GEMM + reconstruction residual in one kernel (see pvae_fused_fwd)
+int fused_fwd_supported(int64_t B, int64_t K, int64_t D);
+int fused_fwd_impl(const float* h, const float* log_r, const float* b_enc, const float* w_dec, const float* w_dec_lo, const float* x, float* z,
+                   float* z_lo, float* dz_acc, float* g_y, float* g_y_lo, float* recon, float* kl_rowsum, float* rate_max, int64_t B, int64_t K,
+                   int64_t D, int64_t row_offset, int n_exp, float temp, int indicator, int exc_only, float exit_logit, float g_scale,
+                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream);
 // step.cu
 int recon_parts_impl(const float* y_parts, int n_parts, const float* x, float* g_y, float* g_y_lo, float* recon, int64_t B, int64_t D,
                      float g_scale, void* stream);

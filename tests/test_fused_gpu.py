@@ -1,0 +1,120 @@
+"""GPU: the fused forward kernel (pvae_fused_fwd, csrc/fused_fwd.cu: rsample + KL + decoder GEMM with z handed to the tensor
+core through shared memory + reconstruction residual) against the kernels it replaces - pvae_sampler_fwd for z / dz_acc /
+KL row sums (same Philox stream, same chain arithmetic) - and against float64 torch for the decoder and the residual."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import assert_rel, assert_ulp
+
+pytestmark = pytest.mark.gpu
+
+IND = {"sigmoid": 0, "cosine": 1, "linear": 2, "cubic": 3, "quintic": 4}
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from poissonvae_b200 import _lib
+    return _lib.load()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def P(t):
+    return None if t is None else t.data_ptr()
+
+
+def tf32_lo(t):
+    hi = (t.view(torch.int32) & -8192).view(torch.float32)
+    return t - hi
+
+
+CASES = [
+    # B, K, D, temp, log_r shift, bias, exc_only, indicator
+    (4096, 512, 256, 1.0, 0.0, False, False, "sigmoid"),     # BASELINE config 2: one unit of 28 rows per SM
+    (4096, 512, 256, 0.05, 4.5, True, False, "sigmoid"),     # late training: high rates, long chains -> lane groups
+    (8192, 1024, 256, 1.0, 1.0, False, False, "sigmoid"),    # config 3's per-GPU shape: two units per CTA, four batches
+    (2000, 256, 128, 0.5, 2.0, True, True, "cubic"),         # ragged last unit, one column half, finite-support indicator
+]
+
+
+@pytest.mark.parametrize("B,K,D,temp,shift,bias,exc_only,kind", CASES)
+def test_fused_forward_equals_the_three_kernels_it_replaces(lib, B, K, D, temp, shift, bias, exc_only, kind):
+    assert lib.pvae_fused_fwd_supported(B, K, D) == 1
+    g = torch.Generator("cuda").manual_seed(B + K)
+    h = torch.randn(B, K, device="cuda", generator=g) * 0.9
+    log_r = torch.rand(K, device="cuda", generator=g) * 2 - 6 + shift
+    b_enc = torch.randn(K, device="cuda", generator=g) * 0.2 if bias else None
+    w_dec = torch.randn(D, K, device="cuda", generator=g) * 0.05
+    x = torch.randn(B, D, device="cuda", generator=g)
+    w_lo = torch.empty_like(w_dec)
+    assert lib.pvae_tf32_lo(P(w_dec), P(w_lo), w_dec.numel(), stream()) == 0
+    n_exp, seed, offset, row_offset = 263, 77, 12, 640
+    g_scale = 2.0 / B
+
+    def outs():
+        return dict(z=torch.zeros(B, K, device="cuda"), z_lo=torch.zeros(B, K, device="cuda"), dz=torch.zeros(B, K, device="cuda"),
+                    g_y=torch.zeros(B, D, device="cuda"), g_y_lo=torch.zeros(B, D, device="cuda"), recon=torch.zeros(B, device="cuda"),
+                    kl=torch.zeros(B, device="cuda"), rmax=torch.zeros(1, device="cuda"))
+    f = outs()
+    rc = lib.pvae_fused_fwd(P(h), P(log_r), P(b_enc), P(w_dec), P(w_lo), P(x), P(f["z"]), P(f["z_lo"]), P(f["dz"]), P(f["g_y"]), P(f["g_y_lo"]),
+                            P(f["recon"]), P(f["kl"]), P(f["rmax"]), B, K, D, row_offset, n_exp, temp, IND[kind], int(exc_only), 0.0, g_scale,
+                            seed, offset, None, stream())
+    assert rc == 0, lib.pvae_last_error()
+    u = outs()
+    rc = lib.pvae_sampler_fwd(P(h), P(log_r), P(b_enc), P(u["z"]), None, None, None, P(u["kl"]), P(u["rmax"]), P(u["dz"]), B, K, row_offset,
+                              n_exp, temp, IND[kind], int(exc_only), 0.0, seed, offset, None, stream())
+    assert rc == 0, lib.pvae_last_error()
+    torch.cuda.synchronize()
+    # sampler outputs: the same chains.  A chain finished by one lane is bit-identical; one finished by a lane group sums
+    # its terms in prefix order (and the two kernels do not park the same chains): a few ulp
+    zf, zu = f["z"].cpu().numpy(), u["z"].cpu().numpy()
+    same = float((zf == zu).mean())
+    print(f"z bit-identical entries: {same:.4f}; max |dz - dz_ref| / max|dz| = "
+          f"{float((f['dz'] - u['dz']).abs().max() / u['dz'].abs().max()):.2e}")
+    if shift == 0.0:  # random-init rates: no chain is long enough for the lane groups
+        assert_ulp(zf, zu, max_ulp=16, what="z fused vs pvae_sampler_fwd")
+    # prefix-sum arrival times differ from sequential ones in the last bits; at temp = 0.05 a term amplifies that 20x
+    assert_rel(zf, zu, rtol=1e-5, floor=1e-37, what="z fused vs pvae_sampler_fwd")
+    assert_rel(f["dz"].cpu().numpy(), u["dz"].cpu().numpy(), rtol=2e-6, what="dz_acc")
+    assert_rel(f["kl"].cpu().numpy(), u["kl"].cpu().numpy(), rtol=2e-6, floor=0.0, what="kl row sums")
+    assert torch.equal(f["rmax"], u["rmax"])
+    assert torch.equal(f["z_lo"], tf32_lo(f["z"]))
+    # decoder + residual against float64 on the kernel's own z
+    y = f["z"].double() @ w_dec.double().T
+    r = y - x.double()
+    assert_rel(f["g_y"].cpu().numpy(), (g_scale * r).cpu().numpy(), rtol=5e-6, what="g_y")
+    assert_rel(f["recon"].cpu().numpy(), r.square().sum(1).cpu().numpy(), rtol=5e-6, floor=0.0, what="recon")
+    assert torch.equal(f["g_y_lo"], tf32_lo(f["g_y"]))
+
+
+def test_fused_step_matches_the_unfused_step(lib):
+    """A training step with the fused forward against the same step with sampler / decoder GEMM / residual as separate kernels:
+    same loss statistics, gradients and updated parameters up to the rounding of the regrouped decoder sum."""
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
+    data = torch.randn(3, 4096, 256, generator=torch.Generator().manual_seed(5)).cuda()
+    out = {}
+    try:
+        for fused in (1, 0):
+            lib.pvae_set_step_fused(fused)
+            model = PoissonVAE(ConfigPoisVAE(n_latents=512, prior_clamp=-4, seed=3)).cuda()
+            with torch.no_grad():
+                model.log_rate.add_(2.0)
+            model.update_n(30.0)
+            tr = TrainerVAE(model, ConfigTrainVAE(lr=0.01, epochs=40, batch_size=4096, temp_anneal_portion=0.0, temp_stop=0.5,
+                                                  kl_anneal_portion=0.0, kl_const_portion=0.0, kl_beta=1.5, grad_clip=None),
+                            n_batches_per_epoch=1)
+            assert tr.planes
+            torch.cuda.manual_seed(9)
+            n0 = lib.pvae_launch_count()
+            losses = [tr.train_step(data[i], i).clone() for i in range(3)]
+            per_step = (lib.pvae_launch_count() - n0) // 3
+            out[fused] = (torch.stack(losses), tr.flat_g.clone(), tr.flat_p.clone(), per_step)
+    finally:
+        lib.pvae_set_step_fused(1)
+    assert out[1][3] == out[0][3] - 2, (out[1][3], out[0][3])  # sampler + decoder GEMM + residual -> one launch
+    for name, a, b in zip(("losses", "gradient", "parameters"), out[1], out[0]):
+        assert_rel(a.cpu().numpy(), b.cpu().numpy(), rtol=5e-6, what=name)
