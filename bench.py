@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--tf32", action="store_true", help="single-pass TF32 GEMMs instead of 3xTF32 (A/B)")
     ap.add_argument("--dec_splits", type=int, default=-1, help="K-splits of the decoder GEMM (A/B; default: the library's choice)")
     ap.add_argument("--pool", type=int, default=1, help="forward sampler schedule (A/B): 0 row by row, 1 per-row-tile pool, 2 one-wave pool")
+    ap.add_argument("--fused", action="store_true", help="the fused forward kernel (rsample + KL + decoder GEMM on z in shared memory "
+                                                        "+ residual, one launch) instead of three kernels (A/B, measured slower; "
+                                                        "see pvae_set_step_fused)")
     ap.add_argument("--coef", action="store_true", help="sampler coefficient mode: streaming backward (A/B, see pvae_set_step_coef)")
     ap.add_argument("--no_carveout", action="store_true", help="leave every kernel's L1 / shared-memory split at the driver default (A/B)")
     ap.add_argument("--no_planes", action="store_true", help="GEMMs split their operands per stage in shared memory instead of "
@@ -93,6 +96,8 @@ def workload(args, world=None):
             "gemm": "tf32 single pass" if getattr(args, "tf32", False) else
                     "3xTF32 (fp32-grade, tcgen05), operand low planes written by the producers (x: once at upload)",
             "schedule": "reference vH16 lr warm-up (lr .005, 1 % of 78000 iterations), beta and temp pinned",
+            "forward": "h -> ONE kernel (rsample + KL + decoder GEMM on z in shared memory + residual)" if getattr(args, "fused", False)
+                       else "h -> three kernels (sampler, decoder GEMM, residual)",
             "graph": getattr(args, "graph", "off"),
             "l2": "inputs rotate over 64 distinct batches (>= 268 MB > 126 MB L2)",
             "parallelism": f"dp{world}"}
@@ -306,6 +311,7 @@ def run_ours(args):
         lib.pvae_set_carveout(0)
     lib.pvae_set_pool(args.pool)
     lib.pvae_set_step_coef(1 if args.coef else 0)
+    lib.pvae_set_step_fused(1 if args.fused else 0)
     if args.no_overlap:
         lib.pvae_set_step_overlap(0)
     if args.tf32:
@@ -429,6 +435,9 @@ def run_ours(args):
     # and the TF32 low planes of z / g_h for the GEMMs; that is reported as implementation traffic, not credited.
     alg = {"sampler_fwd": 8, "sampler_bwd": 12}
     impl_extra = {"sampler_fwd": 4 + (4 if tr.planes else 0), "sampler_bwd": 4 + (4 if tr.planes else 0)}
+    # with the fused forward the "sampler_fwd" events bracket ONE kernel that also runs the decoder GEMM and the residual:
+    # it is still credited the sampler's 8 B/latent only (its other algorithmic traffic - x, g_y, W_dec - is listed)
+    fused_fwd = bool(tr.planes and args.fused and tr.lib.pvae_fused_fwd_supported(B, K, 256))
     dom = "sampler_fwd" if ktimes.get("sampler_fwd", 0.0) >= ktimes.get("sampler_bwd", 0.0) else "sampler_bwd"
     gbs = {k: B * K * alg[k] / (ktimes[k] * 1e-6) / 1e9 for k in alg if ktimes.get(k)}
     value = world * B * K_steps / (ms_total * 1e-3)
@@ -454,6 +463,9 @@ def run_ours(args):
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_latent": alg, "algorithmic_bytes_per_launch": B * K * alg[dom],
                      "implementation_extra_bytes_per_latent": impl_extra,
+                     "sampler_fwd_is": ("fused_fwd_kernel: rsample + KL + decoder GEMM + residual (also moves x, g_y: "
+                                        f"{8 * B * 256} B and W_dec: {4 * 256 * K} B per launch, not credited)") if fused_fwd
+                                       else "sampler_kernel (stand-alone)",
                      "kernel_us": {k: round(v, 2) for k, v in ktimes.items()},
                      "kernels": {k: {"achieved": round(v, 1), "frac": round(v / peak, 4)} for k, v in gbs.items()},
                      "sampler_fwd_plus_bwd": {"achieved": round(B * K * 20 / ((ktimes["sampler_fwd"] + ktimes["sampler_bwd"]) * 1e-6) / 1e9, 1),

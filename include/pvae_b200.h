@@ -115,6 +115,12 @@ int pvae_rsample_bwd(const float* log_rate, const float* g_z, const float* dz_ac
  * kl (B,K) = exp(log_r) * (1 + exp(log_dr) * (log_dr - 1)); backward gives g_log_dr (B,K) and
  * g_log_r (K) from g_kl (B,K). */
 int pvae_kl_fwd(const float* log_dr, const float* log_r, float* kl, int64_t B, int64_t K, void* stream);
+/* kl_diag of main/train_vae.py:348 (torch.mean(kl, dim=0), the per-latent KL the reference logs and counts active latents
+ * from, :442-445) straight from the encoder output h (B,K) the fused step leaves in its workspace: kl_diag (K).  Meant for
+ * logging steps.  ws: pvae_kl_diag_ws_floats(B, K) floats. */
+int64_t pvae_kl_diag_ws_floats(int64_t B, int64_t K);
+int pvae_kl_diag(const float* h, const float* log_r, const float* b_enc, float* kl_diag, float* ws, int64_t B, int64_t K, int exc_only,
+                 void* stream);
 int pvae_kl_bwd(const float* log_dr, const float* log_r, const float* g_kl, float* g_log_dr, float* g_log_r,
                 float* partial_ws, int accumulate, int64_t B, int64_t K, void* stream);
 
@@ -281,11 +287,15 @@ int pvae_fused_fwd(const float* h, const float* log_r, const float* b_enc, const
                    float* z, float* z_lo, float* dz_acc, float* g_y, float* g_y_lo, float* recon, float* kl_rowsum, float* rate_max,
                    int64_t B, int64_t K, int64_t D, int64_t row_offset, int n_exp, float temp, int indicator, int exc_only,
                    float exit_logit, float g_scale, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream);
-/* Tuning knob (process-wide, default on): the step uses pvae_fused_fwd where it is supported and the operand planes are kept
- * (params_lo given); 0 = sampler, decoder GEMM and residual as three kernels. */
+/* Tuning knob (process-wide, default OFF): 1 = the step uses pvae_fused_fwd where it is supported and the operand planes are
+ * kept (params_lo given); 0 = sampler, decoder GEMM and residual as three kernels.  Off because it measured slower at config
+ * 2 (98 vs 64 us for the three kernels, DESIGN.md section 4.6 has the phase timeline). */
 int pvae_set_step_fused(int on);
 /* Timing experiments on pvae_fused_fwd (results are WRONG unless 0): 1 = no W_dec loads / MMAs, 2 = hi x hi product only. */
 int pvae_set_fused_debug(int mode);
+/* Debugging aid: ts_dev = 1024 device words that CTA 0 of pvae_fused_fwd fills with %globaltimer stamps of its phases
+ * (tools/fused_timeline.py decodes them); NULL switches it off. */
+int pvae_set_fused_timeline(uint64_t* ts_dev);
 /* Tuning knob (process-wide, default on): pvae_lin_step_fwd_bwd reduces the wgrad split partials and the sampler's column
  * partials with ONE kernel instead of two split-K reductions + one or two column-sum kernels (bit-identical results). */
 int pvae_set_fuse_reduce(int on);

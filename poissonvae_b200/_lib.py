@@ -123,7 +123,10 @@ _SIGNATURES = {
     "pvae_set_step_trace": (_i, [_p, _i]),
     "pvae_set_step_coef": (_i, [_i]),
     "pvae_set_step_fused": (_i, [_i]),
+    "pvae_kl_diag_ws_floats": (_i64, [_i64, _i64]),
+    "pvae_kl_diag": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _p]),
     "pvae_set_fused_debug": (_i, [_i]),
+    "pvae_set_fused_timeline": (_i, [_p]),
     "pvae_fused_fwd_supported": (_i, [_i64, _i64, _i64]),
     "pvae_fused_fwd": (_i, [_p] * 14 + [_i64, _i64, _i64, _i64, _i, _f, _i, _i, _f, _f, _u64, _u64, _p, _p]),
     "pvae_lin_step_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i,

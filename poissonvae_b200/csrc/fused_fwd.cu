@@ -6,20 +6,24 @@
 //           -> g_y = 2 (y - x) / B, sum_d (y - x)^2     main/vae.py:68-72
 //
 // in ONE persistent kernel.  The sampler is instruction-issue bound on the SIMT pipes and leaves the tensor pipe idle, the
-// decoder GEMM is the opposite: here they share the SM.  A CTA owns a unit of <= 32 rows (B / #SMs of them, so that all
-// 148 SMs carry the same sampler load) and ALL K latents of those rows:
+// decoder GEMM is the opposite: here they share the SM.  A CTA owns a unit of <= 28 rows (B / #SMs of them, so that all
+// 148 SMs carry the same sampler load) and ALL K latents of those rows, walked in batches of 256 latents (8 k-blocks):
 //
-//   warps 0..21  sampler     per batch of 256 latents: uniform prologue (rates parked in shared memory; chains whose rate
-//                            predicts more than 8 events are listed), then groups of 8 lanes walk the listed long chains
-//                            (8 events per step), then a work pool over the batch's other rows x 64 quads (k-block major).
-//                            A finished quad is stored to global memory (z, its TF32 low plane, dz_acc - the backward needs
-//                            them) AND into the 128-byte-swizzled K-major operand tile of its k-block in shared memory;
-//                            then the lane arrives on that k-block's mbarrier (count = rows x 8 quads).
-//   warp 22      TMA + MMA   one thread streams W_dec (hi and lo planes, {32 k, 128 rows} boxes) through a 3-stage ring,
-//                            waits for a k-block of z and issues 3xTF32 tcgen05.mma for y^T = W_dec z^T: A = the W_dec tile
+//   warps 0..20  sampler     seven independent groups of three warps; a group owns 4 rows of the unit and runs, per batch,
+//                            the schedule of the stand-alone sampler on them: uniform prologue (rates parked in shared memory;
+//                            chains whose rate predicts more than a few events are listed), lane groups of 8 walk the listed
+//                            long chains 8 events per step, then a work pool over the other quads (k-block major).  Groups
+//                            only synchronise among themselves (named barriers): while one group drains the tail of its pool
+//                            the others keep the SM's issue slots busy - heavy-tailed chain lengths make CTA-wide barriers
+//                            expensive (measured: 65 vs 39 us for the sampler part).  A finished quad is stored to global
+//                            memory (z, its TF32 low plane, dz_acc - the backward needs them) AND into the 128-byte-swizzled
+//                            K-major operand tile of its k-block in shared memory (a ring of 8 k-block slots, released by the
+//                            tensor core as it consumes them); then the lane arrives on that k-block's mbarrier.
+//   warp 22      TMA         one thread streams W_dec tiles ({32 k, 128 rows} boxes, hi plane then lo plane) through a ring
+//   warp 21      MMA         one thread waits for a k-block of z and issues 3xTF32 tcgen05.mma for y^T = W_dec z^T: A = the W_dec tile
 //                            (M = 128 output columns), B = the z tile (N = 32 rows, no padding), accumulators hi / cross in
 //                            TMEM (lane = output column, column = row) - the tensor work hides under the sampler
-//   warps 0..7               epilogue of a unit: TMEM -> registers (a lane holds one output column of all 32 rows, so every
+//   warps 0..7               epilogue of a unit: TMEM -> registers (a lane holds one output column of all rows, so every
 //                            global access is a coalesced 128-byte row segment), residual against x, g_y (+ low plane),
 //                            squared error per row
 //
@@ -38,30 +42,38 @@
 
 namespace pvae {
 
-constexpr int kFsWarps = 22;                  // sampler warps
-constexpr int kFsLanes = kFsWarps * 32;       // 640 sampler threads
-constexpr int kFsThreads = kFsLanes + 32;     // + the TMA / MMA warp
-constexpr int kFsRows = 32;                   // rows per unit = N of the MMA
-constexpr int kFsKb = 8;                      // k-blocks (32 latents) per batch
-constexpr int kFsBatchK = kFsKb * 32;         // 256 latents per batch
-constexpr int kFsPool = kFsRows * kFsKb * 8;  // 2048 pool entries (quads) per batch
+constexpr int kFsGroups = 7;                       // independent sampler groups
+constexpr int kFsGroupWarps = 3;
+constexpr int kFsGroupLanes = kFsGroupWarps * 32;  // three warps each (704 threads in all: 80 registers per thread)
+constexpr int kFsWarps = kFsGroups * kFsGroupWarps; // sampler warps
+constexpr int kFsLanes = kFsWarps * 32;
+constexpr int kFsThreads = kFsLanes + 64;          // + the TMA warp and the MMA warp
+constexpr int kFsRows = 32;                        // N of the MMA (rows of the operand tile)
+constexpr int kFsMaxUnitRows = 28;                 // rows per unit: at most 4 per group
+constexpr int kFsGroupRows = 4;
+constexpr int kFsKb = 8;                           // k-blocks (32 latents) per batch
+constexpr int kFsBatchK = kFsKb * 32;              // 256 latents per batch
+constexpr int kFsGPool = kFsGroupRows * kFsKb * 8; // 256 pool entries (quads) per group and batch
 constexpr int kFsMaxK = 1024;
-constexpr int kFsWStages = 3;
-constexpr uint32_t kFsZTile = 32 * 128;       // one plane of a 32-row x 32-latent operand tile
-constexpr uint32_t kFsWTile = 128 * 128;      // one plane of a 128-row x 32-latent W_dec tile
-constexpr uint32_t kFsWStage = 2 * kFsWTile;
+constexpr int kFsWStages = 7;                        // 16 KB each.  A stage is free again a TMA latency + an MMA completion latency
+                                                     // (~1 us, measured) after its request: the ring must cover that at the issuer's pace
+constexpr int kFsZSlots = 8;                         // operand-tile ring: k-blocks a group may run ahead of the tensor core
+constexpr uint32_t kFsZTile = 32 * 128;            // one plane of a 32-row x 32-latent operand tile
+constexpr uint32_t kFsWTile = 128 * 128;           // one plane of a 128-row x 32-latent W_dec tile = one ring stage
 
-constexpr uint32_t kOffZ = 0;                                      // [kb][plane][32 rows x 128 B]
-constexpr uint32_t kOffW = kOffZ + kFsKb * 2 * kFsZTile;           // 64 KB
-constexpr uint32_t kOffRate = kOffW + kFsWStages * kFsWStage;      // + 96 KB
-constexpr uint32_t kOffParked = kOffRate + 4 * kFsPool * 4;        // + 32 KB
-constexpr uint32_t kOffKl = kOffParked + 2 * kFsPool * 2;          // + 8 KB (two lists)
-constexpr uint32_t kOffElr = kOffKl + 2 * kFsMaxK * 4;             // + 8 KB   [2][K / 32][32]
-constexpr uint32_t kOffRecon = kOffElr + kFsMaxK * 4;              // + 4 KB
-constexpr uint32_t kOffMax = kOffRecon + 2 * 8 * 32 * 4;           // + 2 KB
-constexpr uint32_t kOffBar = kOffMax + 128;
-constexpr uint32_t kFsSmem = kOffBar + 256 + 1024;                 // barriers + cursors, alignment slack
-constexpr uint32_t kFsTmemCols = 128;                              // per column half: 32 (hi) + 32 (cross)
+constexpr uint32_t kOffZ = 0;                                           // [slot][plane][32 rows x 128 B]
+constexpr uint32_t kOffW = kOffZ + kFsZSlots * 2 * kFsZTile;            // 64 KB
+constexpr uint32_t kOffRate = kOffW + kFsWStages * kFsWTile;            // + 112 KB
+constexpr uint32_t kOffList = kOffRate + kFsGroups * 4 * kFsGPool * 4;  // + 28 KB   [group][4][256]
+constexpr uint32_t kOffKl = kOffList + kFsGroups * kFsGPool * 2;        // + 3.75 KB [group][256]: listed from the front, late parks from the back
+constexpr uint32_t kOffElr = kOffKl + kFsGroups * 32 * kFsGroupRows * 4;  // + 3.75 KB [group][k-block][row]
+constexpr uint32_t kOffRecon = kOffElr + kFsMaxK * 4;                   // + 4 KB
+constexpr uint32_t kOffMax = kOffRecon + 2 * 8 * 32 * 4;                // + 2 KB
+constexpr uint32_t kOffCnt = kOffMax + 128;                             // [group][2 sets][8]
+constexpr uint32_t kOffBar = kOffCnt + kFsGroups * 16 * 4;
+constexpr uint32_t kFsSmem = kOffBar + 256 + 1024;                      // barriers, alignment slack
+constexpr uint32_t kFsTmemCols = 128;                                   // per column half: 32 (hi) + 32 (cross)
+static_assert(kFsSmem <= 232448, "fused forward: shared memory");
 
 struct FusedParams {
   SamplerParams sp;
@@ -70,16 +82,45 @@ struct FusedParams {
   float* g_y_lo;    // optional TF32 low plane of g_y
   float* recon;     // (B)    sum_d (y - x)^2
   int D;
-  int rows_unit;    // rows per unit (<= 32)
+  int rows_unit;    // rows per unit (<= 30)
   int n_units;
   float g_scale;
   float t_need;     // arrival time beyond which a chain can end; rate * t_need ~ events a chain walks
   float park_events;
   int debug;        // timing experiments: 1 = no W_dec loads / MMAs, 2 = hi x hi product only
+  unsigned long long* dbg_ts;  // optional (1024 words): globaltimer stamps of CTA 0's phases (pvae_set_fused_timeline)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void stamp(const FusedParams& fp, int idx) {
+  if (fp.dbg_ts != nullptr && blockIdx.x == 0 && idx < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    fp.dbg_ts[idx] = t;
+  }
+}
+// extreme over all CTAs: idx even = earliest, odd = latest
+__device__ __forceinline__ void stamp_all(const FusedParams& fp, int idx) {
+  if (fp.dbg_ts != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    if (idx & 1) atomicMax(fp.dbg_ts + idx, t); else atomicMin(fp.dbg_ts + idx, t);
+  }
+}
 __device__ __forceinline__ void sts4(uint32_t addr, const float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -99,21 +140,16 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const SamplerParams& p = fp.sp;
-  float* const s_rate = reinterpret_cast<float*>(smem + kOffRate);  // [4][kFsPool]
-  unsigned short* const s_parked = reinterpret_cast<unsigned short*>(smem + kOffParked);
-  float* const s_kl = reinterpret_cast<float*>(smem + kOffKl);
   float* const s_elr = reinterpret_cast<float*>(smem + kOffElr);
   float* const s_recon = reinterpret_cast<float*>(smem + kOffRecon);
   float* const s_max = reinterpret_cast<float*>(smem + kOffMax);
-  uint64_t* const z_full = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* const w_full = z_full + kFsKb;
+  uint64_t* const z_full = reinterpret_cast<uint64_t*>(smem + kOffBar);  // [kFsZSlots]: all quads of the k-block in the slot have arrived
+  uint64_t* const z_empty = z_full + kFsZSlots;                          // [kFsZSlots]: the tensor core has read the slot
+  uint64_t* const w_full = z_empty + kFsZSlots;
   uint64_t* const w_empty = w_full + kFsWStages;
-  uint64_t* const batch_done = w_empty + kFsWStages;
-  uint64_t* const acc_full = batch_done + 1;
+  uint64_t* const acc_full = w_empty + kFsWStages;
   uint64_t* const acc_empty = acc_full + 1;
-  // two sets (batch parity) of {pool cursor, long chains listed by the prologue, its cursor, late parks, its cursor}
-  int* const s_cnt = reinterpret_cast<int*>(acc_empty + 1);
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(s_cnt + 16);
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = static_cast<int>(p.K), Kq = K >> 2, D = fp.D;
@@ -125,9 +161,8 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_w)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_w_lo)) : "memory");
-      for (int i = 0; i < kFsKb; ++i) mbar_init(&z_full[i], static_cast<uint32_t>(R * 8));
+      for (int i = 0; i < kFsZSlots; ++i) mbar_init(&z_full[i], static_cast<uint32_t>(R * 8)), mbar_init(&z_empty[i], 1);
       for (int i = 0; i < kFsWStages; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
-      mbar_init(batch_done, 1);
       mbar_init(acc_full, 1);
       mbar_init(acc_empty, static_cast<uint32_t>(n_ep));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -143,98 +178,120 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
   pdl_launch_dependents();
   pdl_wait();
 
-  if (warp == kFsWarps) {
-    // ===== W_dec loads (TMA) and MMA issue, one thread: the tile of iteration it + kFsWStages is requested as soon as the
-    // MMAs of iteration it have been committed AND the next iteration's MMAs are queued (the tensor pipe never waits for it)
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, kFsRows, false, false);  // M = 128 output columns, N = 32 rows
+  if (warp == kFsWarps + 1) {
+    // ===== TMA producer.  A ring stage holds ONE plane of a W_dec tile; the stages of a (k-block, column half) come hi plane
+    // first, then lo plane.  (Issuing the loads from the MMA thread made every iteration wait for the completion of the
+    // previous iteration's MMAs, ~1 us: the whole decoder then took 54 us per unit instead of hiding under the sampler.)
+    if (lane == 0 && fp.debug != 1) {
       int n_my = 0;
       for (int u = blockIdx.x; u < fp.n_units; u += gridDim.x) ++n_my;
-      const uint32_t per_unit = static_cast<uint32_t>(nkb * halves), total = per_unit * n_my;
-      auto load = [&](uint32_t j) {  // W_dec tile (hi, lo) of iteration j: k-block (j % per_unit) / halves, column half j % halves
-        const uint32_t s = j % kFsWStages, w = j % per_unit;
-        if (j >= kFsWStages) mbar_wait(&w_empty[s], ((j / kFsWStages) - 1) & 1);
-        uint8_t* dst = smem + kOffW + s * kFsWStage;
-        mbar_expect_tx(&w_full[s], fp.debug == 2 ? kFsWTile : kFsWStage);
-        tma_load_2d(&tma_w, &w_full[s], dst, static_cast<int>(w / halves) * 32, static_cast<int>(w % halves) * 128);
-        if (fp.debug != 2) tma_load_2d(&tma_w_lo, &w_full[s], dst + kFsWTile, static_cast<int>(w / halves) * 32, static_cast<int>(w % halves) * 128);
-      };
+      const uint32_t nplanes = fp.debug == 2 ? 1 : 2;
+      const uint32_t per_unit = static_cast<uint32_t>(nkb * halves) * nplanes, total = per_unit * n_my;
+      for (uint32_t j = 0; j < total; ++j) {
+        const uint32_t s = j % kFsWStages, w = j % per_unit, plane = w % nplanes, tile = w / nplanes;
+        mbar_wait(&w_empty[s], ((j / kFsWStages) & 1) ^ 1);
+        mbar_expect_tx(&w_full[s], kFsWTile);
+        tma_load_2d(plane ? &tma_w_lo : &tma_w, &w_full[s], smem + kOffW + s * kFsWTile, static_cast<int>(tile / halves) * 32,
+                    static_cast<int>(tile % halves) * 128);
+      }
+    }
+  } else if (warp == kFsWarps) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, kFsRows, false, false);  // M = 128 output columns, N = 32 rows
       const bool no_mma = fp.debug == 1, hi_only = fp.debug == 2;
-      for (uint32_t j = 0; j < kFsWStages && j < total && !no_mma; ++j) load(j);
-      uint32_t it = 0, bi = 0, ui = 0;
+      const uint32_t nplanes = hi_only ? 1 : 2;
+      stamp(fp, 1);
+      uint32_t it = 0, gk = 0, ui = 0;  // gk: k-blocks consumed so far (slot gk % kFsZSlots, phase gk / kFsZSlots)
       for (int u = blockIdx.x; u < fp.n_units; u += gridDim.x, ++ui) {
         if (ui > 0) {  // the previous unit's epilogue has read the accumulators
           mbar_wait(acc_empty, (ui - 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        for (int b = 0; b < nbatch; ++b, ++bi) {
-          for (int kb = 0; kb < kFsKb; ++kb) {
-            mbar_wait(&z_full[kb], bi & 1);
+        for (int b = 0; b < nbatch; ++b) {
+          for (int kb = 0; kb < kFsKb; ++kb, ++gk) {
+            const uint32_t slot = gk % kFsZSlots;
+            mbar_wait(&z_full[slot], (gk / kFsZSlots) & 1);
+            stamp(fp, 100 + gk);
             // the sampler lanes' generic-proxy stores of this k-block, acquired through the barrier, become visible to the
             // tensor core's (async-proxy) operand reads
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t za = smem_u32(smem + kOffZ + kb * 2 * kFsZTile), zl = za + kFsZTile;
-            for (int hf = 0; hf < halves && !no_mma; ++hf, ++it) {
+            const uint32_t za = smem_u32(smem + kOffZ + slot * 2 * kFsZTile), zl = za + kFsZTile;
+            for (uint32_t sub = 0; sub < static_cast<uint32_t>(halves) * nplanes && !no_mma; ++sub, ++it) {
+              const uint32_t hf = sub / nplanes, plane = sub % nplanes;
               const uint32_t s = it % kFsWStages;
               mbar_wait(&w_full[s], (it / kFsWStages) & 1);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              const uint32_t wb = smem_u32(smem + kOffW + s * kFsWStage), wl = wb + kFsWTile;
+              const uint32_t wb = smem_u32(smem + kOffW + s * kFsWTile);
               const uint32_t d_hi = tmem_base + hf * 64, d_x = d_hi + 32;
 #pragma unroll
               for (int k = 0; k < kBK / kUmmaK; ++k) {
-                const uint64_t da = make_smem_desc(za + k * 32, 16, 1024, 2), dal = make_smem_desc(zl + k * 32, 16, 1024, 2);
-                const uint64_t db = make_smem_desc(wb + k * 32, 16, 1024, 2), dbl = make_smem_desc(wl + k * 32, 16, 1024, 2);
+                const uint64_t dz = make_smem_desc(za + k * 32, 16, 1024, 2), dzl = make_smem_desc(zl + k * 32, 16, 1024, 2);
+                const uint64_t dw = make_smem_desc(wb + k * 32, 16, 1024, 2);
                 const uint32_t acc = (b > 0 || kb > 0 || k > 0) ? 1u : 0u;
-                umma_tf32(d_hi, db, da, idesc, acc);   // hi(W) hi(z)
-                if (!hi_only) {
-                  umma_tf32(d_x, dbl, da, idesc, acc);   // lo(W) hi(z)
-                  umma_tf32(d_x, db, dal, idesc, 1u);    // hi(W) lo(z)
+                if (plane == 0) {
+                  umma_tf32(d_hi, dw, dz, idesc, acc);               // hi(W) hi(z)
+                  if (!hi_only) umma_tf32(d_x, dw, dzl, idesc, acc);  // hi(W) lo(z)
+                } else {
+                  umma_tf32(d_x, dw, dz, idesc, 1u);                 // lo(W) hi(z)
                 }
               }
-              umma_commit(&w_empty[s]);
-              if (it >= 1 && it - 1 + kFsWStages < total) load(it - 1 + kFsWStages);  // refill the stage of the previous iteration
+              umma_commit(&w_empty[s]);  // frees the ring stage once these MMAs have read it
             }
+            umma_commit(&z_empty[slot]);  // the operand tiles of this k-block have been read
+            stamp(fp, 200 + gk);
           }
-          umma_commit(batch_done);  // the operand tiles of this batch have been read
         }
         umma_commit(acc_full);
       }
     }
   } else {
-    // ===== sampler warps =====
+    // ===== sampler warps: group g = warps 3 g .. 3 g + 2 =====
+    const int g = warp / kFsGroupWarps, gtid = tid - g * kFsGroupLanes;
+    float* const s_rate = reinterpret_cast<float*>(smem + kOffRate) + g * (4 * kFsGPool);  // [4][kFsGPool]
+    unsigned short* const s_list = reinterpret_cast<unsigned short*>(smem + kOffList) + g * kFsGPool;
+    float* const kl_tab = reinterpret_cast<float*>(smem + kOffKl) + g * (32 * kFsGroupRows);  // [k-block][row of the group]
+    int* const s_cnt = reinterpret_cast<int*>(smem + kOffCnt) + g * 16;
+    const int bar_id = 1 + g;
+    // rows of the unit are dealt out evenly: the first R % 7 groups own one more
+    const int rows_g = R / kFsGroups + (g < R % kFsGroups ? 1 : 0);
+    const int grow0 = g * (R / kFsGroups) + min(g, R % kFsGroups);  // first row of the group inside the unit
+    const int pool_n = rows_g * kFsKb * 8;  // entries of a batch, k-block major: entry = (kb * rows_g + r) * 8 + cq
+    const int ekb = rows_g * 8;             // entries per k-block
+    const uint32_t rmagic = rows_g > 0 ? (65536u + rows_g - 1) / rows_g : 0u;  // x / rows_g == (x * rmagic) >> 16 for x < 256
+
     uint64_t off = p.offset;
     if (p.offset_dev != nullptr) off += *p.offset_dev;
     const uint32_t off_lo = static_cast<uint32_t>(off), off_hi = static_cast<uint32_t>(off >> 32);
     const int n_a = min(p.phase_a, p.n_exp);
     const float t_exit = p.t_exit, absorb = p.absorb;
     const unsigned lanes_below = (1u << lane) - 1u;
-    const uint32_t zst = smem_u32(smem + kOffZ), zbar0 = smem_u32(z_full);
-    const int pool_n = R * kFsKb * 8;  // entries of a batch, k-block major: entry = (kb * R + r) * 8 + cq
-    const int ekb = R * 8;             // entries per k-block
-    const uint32_t rmagic = (65536u + R - 1) / R;  // x / R == (x * rmagic) >> 16 for x < 256, R <= 32
+    const uint32_t zst = smem_u32(smem + kOffZ), zbar0 = smem_u32(z_full), zebar0 = smem_u32(z_empty);
     float rmax = 0.f;
 
+    if (tid == 0) stamp(fp, 0), stamp_all(fp, 700), stamp_all(fp, 701);
     for (int k = tid; k < K; k += kFsLanes) s_elr[k] = expf(__ldg(p.log_r + k));
-    if (tid < 16) s_cnt[tid] = (tid & 7) == 0 ? kFsLanes : 0;
-    named_bar_sync(1, kFsLanes);
+    if (gtid < 16) s_cnt[gtid] = (gtid & 7) == 0 ? kFsGroupLanes : 0;
+    named_bar_sync(15, kFsLanes);  // all sampler warps, once
 
     uint32_t bi = 0, ui = 0;
     for (int u = blockIdx.x; u < fp.n_units; u += gridDim.x, ++ui) {
-      const long long row0 = static_cast<long long>(u) * R;
-      const int nrows = static_cast<int>(min(static_cast<long long>(R), p.B - row0));
-      float* const kl_tab = s_kl + (ui & 1) * kFsMaxK;  // [k-block of the row][32 rows]
-      const uint32_t quad0 = static_cast<uint32_t>(((p.row_offset + row0) * p.K) >> 2);
-      float* const z0 = p.z + row0 * p.K;
-      float* const zlo0 = p.z_lo != nullptr ? p.z_lo + row0 * p.K : nullptr;
-      float* const dz0 = p.dz_out + row0 * p.K;
+      const long long row0 = static_cast<long long>(u) * R;           // first row of the unit
+      const int nrows = min(rows_g, static_cast<int>(min(static_cast<long long>(R), p.B - row0)) - grow0);  // valid rows of this group (may be <= 0)
+      const long long grow = row0 + grow0;                            // first row of the group
+      const uint32_t quad0 = static_cast<uint32_t>(((p.row_offset + grow) * p.K) >> 2);
+      float* const z0 = p.z + grow * p.K;
+      float* const zlo0 = p.z_lo != nullptr ? p.z_lo + grow * p.K : nullptr;
+      float* const dz0 = p.dz_out + grow * p.K;
 
 #pragma unroll 1
       for (int b = 0; b < nbatch; ++b, ++bi) {
         int* const cnt = s_cnt + (bi & 1) * 8;  // [0] pool cursor, [1] listed long chains, [2] its cursor, [3] late parks, [4] its cursor
+        const uint32_t gk0 = bi * kFsKb;  // the batch's first k-block in the operand-tile ring
         // ---- stage 1: prologue of the batch (uniform, coalesced: 8 lanes = the 32 latents of one row of one k-block)
 #pragma unroll 1
-        for (int e = tid; e < pool_n; e += kFsLanes) {
+        for (int e = gtid; e < pool_n; e += kFsGroupLanes) {
           const int kb = static_cast<int>(((static_cast<uint32_t>(e) >> 3) * rmagic) >> 16), rem = e - kb * ekb, r = rem >> 3, cq = rem & 7;
           float klsum = 0.f;
           bool pre = false;
@@ -243,7 +300,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
             const float4 lr4 = ldg4(p.log_r + k);
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.b_enc != nullptr) bias4 = ldg4(p.b_enc + k);
-            const float4 hv4 = ldg4(p.h + (row0 + r) * p.K + k);
+            const float4 hv4 = ldg4(p.h + (grow + r) * p.K + k);
             const float4 elr4 = *reinterpret_cast<const float4*>(s_elr + k);
             const float hv[4] = {hv4.x, hv4.y, hv4.z, hv4.w}, lr[4] = {lr4.x, lr4.y, lr4.z, lr4.w};
             const float bias[4] = {bias4.x, bias4.y, bias4.z, bias4.w}, elr[4] = {elr4.x, elr4.y, elr4.z, elr4.w};
@@ -251,7 +308,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const Latent q = prologue<false, false>(p, hv[j], lr[j], bias[j]);
-              s_rate[j * kFsPool + e] = q.rate;
+              s_rate[j * kFsGPool + e] = q.rate;
               qmax = fmaxf(qmax, q.rate);
               const float d = q.log_dr;
               klv[j] = elr[j] * (1.f + expf(d) * (d - 1.f));  // main/vae.py:448-449
@@ -264,25 +321,26 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
           klsum += __shfl_xor_sync(0xffffffffu, klsum, 1);
           klsum += __shfl_xor_sync(0xffffffffu, klsum, 2);
           klsum += __shfl_xor_sync(0xffffffffu, klsum, 4);
-          if (cq == 0 && r < nrows) kl_tab[(b * kFsKb + kb) * 32 + r] = klsum;
+          if (cq == 0 && r < nrows) kl_tab[(b * kFsKb + kb) * kFsGroupRows + r] = klsum;
           const unsigned pm = __ballot_sync(0xffffffffu, pre);
           if (pm != 0u) {
             int pbase = 0;
             if (lane == 0) pbase = atomicAdd(&cnt[1], __popc(pm));
             pbase = __shfl_sync(0xffffffffu, pbase, 0);
-            if (pre) s_parked[pbase + __popc(pm & lanes_below)] = static_cast<unsigned short>(e);
+            if (pre) s_list[pbase + __popc(pm & lanes_below)] = static_cast<unsigned short>(e);
           }
         }
-        if (bi > 0) mbar_wait(batch_done, (bi - 1) & 1);  // the tensor core has read the previous batch's operand tiles
-        named_bar_sync(1, kFsLanes);
-        if (tid < 8) s_cnt[((bi + 1) & 1) * 8 + tid] = tid == 0 ? kFsLanes : 0;  // the next batch's counters (idle since batch bi - 1)
+        named_bar_sync(bar_id, kFsGroupLanes);
+        if (gtid == 0) stamp(fp, 300 + (g * 8 + bi) * 4);
+        if (gtid < 8) s_cnt[((bi + 1) & 1) * 8 + gtid] = gtid == 0 ? kFsGroupLanes : 0;  // the next batch's counters (idle since batch bi - 1)
 
         // pass 0: the listed long chains (lane groups).  pass 1: the pool over everything else, then the chains that turned
         // out long on the way (lane groups again).
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
           if (pass == 1) {
-            int cur = tid;
+            if (gtid == 0) stamp(fp, 300 + (g * 8 + bi) * 4 + 1);
+            int cur = gtid;
             bool has = cur < pool_n, live = false, skip = false;
             int n = 0, ebase = 0;
             uint32_t quad = 0, zaddr = 0, zbar = 0;
@@ -291,10 +349,12 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
               live = false, skip = false;
               if (has) {
                 const int kb = static_cast<int>(((static_cast<uint32_t>(cur) >> 3) * rmagic) >> 16), rem = cur - kb * ekb, r = rem >> 3, cq = rem & 7;
-                zbar = zbar0 + kb * 8;
+                const uint32_t gk = gk0 + kb, slot = gk % kFsZSlots;
+                zbar = zbar0 + slot * 8;
+                if (gk >= kFsZSlots) mbar_wait_u32(zebar0 + slot * 8, ((gk / kFsZSlots) - 1) & 1);  // the slot's previous tenant has been consumed
                 if (r < nrows) {
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) rate[j] = s_rate[j * kFsPool + cur];
+                  for (int j = 0; j < 4; ++j) rate[j] = s_rate[j * kFsGPool + cur];
                   if (fmaxf(fmaxf(rate[0], rate[1]), fmaxf(rate[2], rate[3])) * fp.t_need > fp.park_events) {
                     skip = true;  // listed by the prologue, walked in pass 0
                   } else {
@@ -302,7 +362,8 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
                     const int qi = r * Kq + b * (kFsBatchK / 4) + kb * 8 + cq;
                     ebase = qi << 2;
                     quad = quad0 + static_cast<uint32_t>(qi);
-                    zaddr = zst + kb * (2 * kFsZTile) + r * 128 + ((cq ^ (r & 7)) << 4);
+                    const int ur = grow0 + r;  // row inside the unit = row of the operand tile
+                    zaddr = zst + slot * (2 * kFsZTile) + ur * 128 + ((cq ^ (ur & 7)) << 4);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                       inv_rate[j] = recip_for_div(rate[j]);
@@ -331,9 +392,9 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
                   soft_term<IND, true>(p, t[j], f, df);
                   acc[j] += f;
                   excess = fmaxf(excess, fmaf(-absorb, acc[j], f));
-                  const float g = df * t[j];
-                  acc2[j] += g;
-                  excess = fmaxf(excess, fmaf(-absorb, acc2[j], g));
+                  const float gg = df * t[j];
+                  acc2[j] += gg;
+                  excess = fmaxf(excess, fmaf(-absorb, acc2[j], gg));
                 }
                 ++n;
                 const float tmin = fminf(fminf(t[0], t[1]), fminf(t[2], t[3]));
@@ -359,7 +420,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
                 }
                 first = __shfl_sync(0xffffffffu, first, 0);
                 pbase = __shfl_sync(0xffffffffu, pbase, 0);
-                if (park) s_parked[kFsPool + pbase + __popc(pm & lanes_below)] = static_cast<unsigned short>(cur);
+                if (park) s_list[kFsGPool - 1 - (pbase + __popc(pm & lanes_below))] = static_cast<unsigned short>(cur);  // from the back
                 if (fin) {
                   cur = first + __popc(fm & lanes_below);
                   has = cur < pool_n;
@@ -367,11 +428,11 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
                 }
               }
             }
-            named_bar_sync(1, kFsLanes);  // every late long chain is on the list
+            named_bar_sync(bar_id, kFsGroupLanes);  // every late long chain of the group is on the list
+            if (gtid == 0) stamp(fp, 300 + (g * 8 + bi) * 4 + 2);
           }
 
-          // ---- groups of kGroup lanes walk the listed chains from their first event, kGroup events per step
-          const unsigned short* const list = s_parked + pass * kFsPool;
+          // ---- lane groups of kGroup walk the listed chains from their first event, kGroup events per step
           const int n_parked = cnt[1 + 2 * pass];
           int* const cursor = &cnt[2 + 2 * pass];
           if (n_parked > 0) {
@@ -416,16 +477,19 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
                 if (done) {
                   has = next < n_parked;
                   if (has) {
-                    const int cur = list[next];
+                    const int cur = s_list[pass == 0 ? next : kFsGPool - 1 - next];
                     const int kb = static_cast<int>(((static_cast<uint32_t>(cur) >> 3) * rmagic) >> 16), rem = cur - kb * ekb, r = rem >> 3, cq = rem & 7;
                     const int qi = r * Kq + b * (kFsBatchK / 4) + kb * 8 + cq;
                     ebase = qi << 2;
                     quad = quad0 + static_cast<uint32_t>(qi);
-                    zaddr = zst + kb * (2 * kFsZTile) + r * 128 + ((cq ^ (r & 7)) << 4);
-                    zbar = zbar0 + kb * 8;
+                    const int ur = grow0 + r;
+                    const uint32_t gk = gk0 + kb, slot = gk % kFsZSlots;
+                    if (gk >= kFsZSlots) mbar_wait_u32(zebar0 + slot * 8, ((gk / kFsZSlots) - 1) & 1);
+                    zaddr = zst + slot * (2 * kFsZTile) + ur * 128 + ((cq ^ (ur & 7)) << 4);
+                    zbar = zbar0 + slot * 8;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                      rate[j] = s_rate[j * kFsPool + cur];
+                      rate[j] = s_rate[j * kFsGPool + cur];
                       inv_rate[j] = recip_for_div(rate[j]);
                       t0[j] = 0.f, part[j] = 0.f, part2[j] = 0.f;
                     }
@@ -451,13 +515,13 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
                 const float t = t0[j] + x;
                 float f, df = 0.f;
                 soft_term<IND, true>(p, t, f, df);
-                const float g = df * t;
+                const float gg = df * t;
                 part[j] += valid ? f : 0.f;
                 // the group's last lane holds the smallest term of the step, its first lane the largest partial sum (a lower
                 // bound of the chain's running total)
                 excess = fmaxf(excess, fmaf(-absorb, __shfl_sync(0xffffffffu, part[j], 0, kGroup), f));
-                part2[j] += valid ? g : 0.f;
-                excess = fmaxf(excess, fmaf(-absorb, __shfl_sync(0xffffffffu, part2[j], 0, kGroup), g));
+                part2[j] += valid ? gg : 0.f;
+                excess = fmaxf(excess, fmaf(-absorb, __shfl_sync(0xffffffffu, part2[j], 0, kGroup), gg));
                 t0[j] = __shfl_sync(0xffffffffu, t, kGroup - 1, kGroup);
               }
               n0 += kGroup;
@@ -467,36 +531,43 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
             }
           }
         }  // passes
-        named_bar_sync(1, kFsLanes);  // the rate table and the lists are reused by the next batch
+        if (b == nbatch - 1 && p.kl_rowsum != nullptr && gtid < nrows) {  // KL row sums of the group's rows (k-blocks in order)
+          float s = 0.f;
+          for (int kbg = 0; kbg < nkb; ++kbg) s += kl_tab[kbg * kFsGroupRows + gtid];
+          p.kl_rowsum[grow + gtid] = s;
+        }
+        named_bar_sync(bar_id, kFsGroupLanes);  // the group's tables are reused by its next batch
+        if (gtid == 0) stamp(fp, 300 + (g * 8 + bi) * 4 + 3), stamp_all(fp, 703);
       }  // batches
 
-      // ---- unit epilogue: KL row sums (k-blocks in order: deterministic), then the reconstruction residual from TMEM
-      if (p.kl_rowsum != nullptr && warp == kFsWarps - 1 && lane < nrows) {  // the last sampler warp (not an epilogue warp)
-        float s = 0.f;
-        for (int kbg = 0; kbg < nkb; ++kbg) s += kl_tab[kbg * 32 + lane];
-        p.kl_rowsum[row0 + lane] = s;
-      }
+      // ---- unit epilogue (warps 0 .. n_ep - 1): the reconstruction residual from TMEM
       if (warp < n_ep) {
         // accumulator lane = output column, accumulator column = row of the unit: this lane owns column `col` of all rows
         const int q = warp & 3, hf = warp >> 2;
         const int col = hf * 128 + q * 32 + lane;
+        const int urows = static_cast<int>(min(static_cast<long long>(R), p.B - row0));
         mbar_wait(acc_full, ui & 1);
+        if (tid == 0) stamp(fp, 600), stamp_all(fp, 705);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + hf * 64;
         float* const rec = s_recon + (ui & 1) * 256 + warp * 32;
 #pragma unroll 1
         for (int r0 = 0; r0 < kFsRows; r0 += 16) {
           uint32_t v[16], w[16];
+          float xv[16];
           tmem_ld_32x16(tcol + r0, v);
           tmem_ld_32x16(tcol + 32 + r0, w);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)  // all loads of the chunk in flight before the first store (g_y may alias nothing, but the compiler cannot know)
+            xv[i] = r0 + i < urows ? __ldg(fp.x + (row0 + r0 + i) * D + col) : 0.f;
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int r = r0 + i;
             float sq = 0.f;
-            if (r < nrows) {  // warp-uniform
+            if (r < urows) {  // warp-uniform
               const long long gi = (row0 + r) * D + col;
-              const float res = (__uint_as_float(v[i]) + __uint_as_float(w[i])) - __ldg(fp.x + gi);
+              const float res = (__uint_as_float(v[i]) + __uint_as_float(w[i])) - xv[i];
               const float gv = fp.g_scale * res;
               fp.g_y[gi] = gv;
               if (fp.g_y_lo != nullptr) fp.g_y_lo[gi] = tf32_lo(gv);
@@ -509,31 +580,31 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive_u32(smem_u32(acc_empty));
-        named_bar_sync(2, n_ep * 32);
-        if (warp == 0 && lane < nrows) {
+        named_bar_sync(14, n_ep * 32);
+        if (warp == 0 && lane < urows) {
           const float* all = s_recon + (ui & 1) * 256;
           float s = all[lane];
           for (int j = 1; j < n_ep; ++j) s += all[j * 32 + lane];
           fp.recon[row0 + lane] = s;
         }
+        if (tid == 0) stamp(fp, 601), stamp_all(fp, 707);
       }
     }  // units
 
     if (p.rate_max != nullptr) {
       const float m = warp_max(rmax);
       if (lane == 0) s_max[warp] = m;
-      named_bar_sync(1, kFsLanes);
-      if (tid == 0) {
-        float mm = s_max[0];
-#pragma unroll
-        for (int w = 1; w < kFsWarps; ++w) mm = fmaxf(mm, s_max[w]);
-        atomicMax(reinterpret_cast<int*>(p.rate_max), __float_as_int(mm));  // rates are > 0
-      }
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (tid == 0 && p.rate_max != nullptr) {
+    float mm = s_max[0];
+#pragma unroll
+    for (int w = 1; w < kFsWarps; ++w) mm = fmaxf(mm, s_max[w]);
+    atomicMax(reinterpret_cast<int*>(p.rate_max), __float_as_int(mm));  // rates are > 0
+  }
   if (warp == kFsWarps) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kFsTmemCols));
@@ -542,6 +613,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
 
 // ---- host side ---------------------------------------------------------------------------------------------------
 static int g_fused_debug = 0;
+static unsigned long long* g_fused_ts = nullptr;
 
 static int fused_sms() {
   static int sms = 0;
@@ -553,10 +625,10 @@ static int fused_sms() {
   return sms;
 }
 
-// rows per unit: the batch dealt out evenly over m units per SM, m the smallest count that keeps a unit within 32 rows
+// rows per unit: the batch dealt out evenly over m units per SM, m the smallest count that keeps a unit within 28 rows
 static int fused_rows_per_unit(int64_t B) {
   const int64_t sms = fused_sms();
-  const int64_t m = (B + sms * kFsRows - 1) / (sms * kFsRows);
+  const int64_t m = (B + sms * kFsMaxUnitRows - 1) / (sms * kFsMaxUnitRows);
   return static_cast<int>((B + sms * m - 1) / (sms * m));
 }
 
@@ -603,6 +675,7 @@ int fused_fwd_impl(const float* h, const float* log_r, const float* b_enc, const
   // t - 1 > 23.6 temp (sigmoid); without it the chain runs to t_exit
   fp.t_need = p.absorb > 0.f ? std::min(1.f + 24.f * temp, p.t_exit) : p.t_exit;
   fp.debug = g_fused_debug;
+  fp.dbg_ts = g_fused_ts;
   fp.park_events = static_cast<float>((p.phase_a < n_exp ? p.phase_a : n_exp) - 1);
   CUtensorMap mw, mwl;
   {
@@ -628,6 +701,11 @@ int fused_fwd_impl(const float* h, const float* log_r, const float* b_enc, const
 
 extern "C" int pvae_set_fused_debug(int mode) {
   pvae::g_fused_debug = mode;
+  return PVAE_OK;
+}
+
+extern "C" int pvae_set_fused_timeline(uint64_t* ts_dev) {
+  pvae::g_fused_ts = reinterpret_cast<unsigned long long*>(ts_dev);
   return PVAE_OK;
 }
 

@@ -41,7 +41,7 @@ SideStream* side_stream() {
 void* const* g_trace = nullptr;  // pvae_set_step_trace: CUDA events recorded between the main-stream launches of a step
 int g_trace_n = 0;
 int g_overlap = 1;
-int g_fused = 1;  // pvae_set_step_fused: sampler + decoder GEMM + residual in one kernel where supported
+int g_fused = 0;  // pvae_set_step_fused: sampler + decoder GEMM + residual in one kernel where supported (measured slower: off)
 int g_coef = 0;  // pvae_set_step_coef: the forward sampler leaves the backward's coefficients (streaming backward); measured slower
 int g_dec_splits = 0;   // K-splits of the decoder GEMM (pvae_set_dec_splits); 0 = automatic
 int g_fuse_reduce = 1;  // pvae_lin_step_fwd_bwd: reduce all gradient partials with one kernel (bit-identical to the three)

@@ -1027,6 +1027,35 @@ __global__ void __launch_bounds__(256) kl_fwd_kernel(const float* __restrict__ l
   }
 }
 
+// kl_diag of main/train_vae.py:348 (torch.mean(kl, dim=0)) from the encoder output: per-block column sums of the KL over
+// kDiagRows rows; colsum_finalize adds the blocks in order and scales by 1 / B.  Runs at logging steps only.
+constexpr int kDiagRows = 32;
+__global__ void __launch_bounds__(256) kl_diag_kernel(const SamplerParams p, float* __restrict__ part) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long row0 = static_cast<long long>(blockIdx.x) * kDiagRows;
+  const int nrows = static_cast<int>(min(static_cast<long long>(kDiagRows), p.B - row0));
+  for (long long k = 4ll * threadIdx.x; k < p.K; k += 4 * 256) {
+    const float4 lr4 = ldg4(p.log_r + k);
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.b_enc != nullptr) b4 = ldg4(p.b_enc + k);
+    const float lr[4] = {lr4.x, lr4.y, lr4.z, lr4.w}, bias[4] = {b4.x, b4.y, b4.z, b4.w};
+    float elr[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) elr[j] = expf(lr[j]);
+    for (int r = 0; r < nrows; ++r) {
+      const float4 hv4 = ldg4(p.h + (row0 + r) * p.K + k);
+      const float hv[4] = {hv4.x, hv4.y, hv4.z, hv4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d = prologue<false, false>(p, hv[j], lr[j], bias[j]).log_dr;
+        acc[j] += elr[j] * (1.f + expf(d) * (d - 1.f));  // main/vae.py:448-449
+      }
+    }
+    stg4(part + static_cast<long long>(blockIdx.x) * p.K + k, make_float4(acc[0], acc[1], acc[2], acc[3]));
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) kl_bwd_kernel(const float* __restrict__ log_dr, const float* __restrict__ log_r,
                                                           const float* __restrict__ g_kl, float* __restrict__ g_log_dr,
                                                           float* __restrict__ part, long long B, long long K, int rows_per_block) {
@@ -1427,6 +1456,21 @@ extern "C" int pvae_kl_fwd(const float* log_dr, const float* log_r, float* kl, i
   const unsigned grid = static_cast<unsigned>(std::min<long long>((n4 + 255) / 256, 148ll * 16));
   return cuda_ok("pvae_kl_fwd", launch_pdl(kl_fwd_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), log_dr,
                                            log_r, kl, n4, static_cast<long long>(K)));
+}
+
+extern "C" int64_t pvae_kl_diag_ws_floats(int64_t B, int64_t K) { return B <= 0 || K <= 0 ? 0 : ((B + kDiagRows - 1) / kDiagRows) * K; }
+
+extern "C" int pvae_kl_diag(const float* h, const float* log_r, const float* b_enc, float* kl_diag, float* ws, int64_t B, int64_t K,
+                            int exc_only, void* stream) {
+  if (B <= 0 || K <= 0 || K % 4 != 0) return fail(PVAE_ERR_INVALID, "pvae_kl_diag: bad shape B=%lld K=%lld", (long long)B, (long long)K);
+  if (!h || !log_r || !kl_diag || !ws) return fail(PVAE_ERR_INVALID, "pvae_kl_diag: null pointer");
+  SamplerParams p{};
+  p.h = h, p.log_r = log_r, p.b_enc = b_enc, p.B = B, p.K = K;
+  p.clamp_dr = 10.f, p.clamp_rate = 5.f, p.exc_only = exc_only;  // main/vae.py:403-409
+  const long long P = (B + kDiagRows - 1) / kDiagRows;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = cuda_ok("pvae_kl_diag", launch_pdl(kl_diag_kernel, dim3(static_cast<unsigned>(P)), dim3(256), 0, s, p, ws))) return rc;
+  return finalize_cols(ws, kl_diag, P, K, 0, s, 1.f / static_cast<float>(B));
 }
 
 extern "C" int pvae_kl_bwd(const float* log_dr, const float* log_r, const float* g_kl, float* g_log_dr, float* g_log_r,

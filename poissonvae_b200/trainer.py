@@ -81,7 +81,7 @@ class ConfigTrainVAE:
                  kl_const_portion=1e-2, temp_anneal_portion=0.5, temp_anneal_type='lin', temp_start=1.0,
                  temp_stop=0.05, lr=0.002, epochs=1200, batch_size=200, warmup_portion=0.01,
                  optimizer='adamax_fast', scheduler_type='cosine', grad_clip=500, betas=(0.9, 0.999), eps=1e-8,
-                 weight_decay=0.0, eta_min=1e-5, **unused):
+                 weight_decay=0.0, eta_min=1e-5, log_freq=10, **unused):
         if method not in ('mc', 'exact'):
             raise ValueError(method)
         if kl_anneal_cycles != 0:
@@ -114,7 +114,14 @@ class TrainerVAE:
             self.temperatures = np.ones(self.n_iters) * cfg.temp_stop
         self._flatten_parameters()
         self.opt_step = 0
-        self.stats = {}
+        # per-gstep statistics with the reference's keys (main/train_vae.py:373-408) and, every cfg.log_freq steps, the
+        # dictionary the reference hands to wandb.log (:410-445).  The step itself never syncs: loss / mse / kl, the gradient
+        # norm and rate.max() of every step land in a small device ring that iteration() reads once per logging period.
+        self.stats = {k: {} for k in ('grad', 'loss', 'lr', 'temp', 'r_max', 'n_exp')}
+        self.log = []
+        self._ring = None
+        self._kl_diag = None       # (K) per-latent KL of the last logging step (device)
+        self._want_kl_diag = False
         self._bufs = {}
         self.lib = _lib.load()
         # data-parallel exchange: 'peer' = all-reduce over NVLink peer memory fused with Adamax (one kernel),
@@ -704,6 +711,8 @@ class TrainerVAE:
                 dist_, log_dr, z, y = m(xin)
                 recon = m.loss_recon(y, xin)
             kl = m.loss_kl(log_dr)
+            if self._want_kl_diag:
+                self._kl_diag = kl.detach().mean(0).reshape(-1)  # main/train_vae.py:348
         finally:
             m.row_offset, m.rate_max_out, m.philox_override = 0, None, None
         Bg = x.shape[0] * self.world
@@ -748,18 +757,107 @@ class TrainerVAE:
             params[k].grad = None
         return loss[:3]
 
+    def _kl_diag_of_last_step(self, B):
+        """kl_diag = mean_b kl (K) of the step that just ran (main/train_vae.py:348), on the device.  Fused path: recomputed
+        from the encoder output the step left in its workspace (pvae_kl_diag); autograd path: kept by the step."""
+        m, lib = self.model, self.lib
+        K, D = m.cfg.n_latents, m.cfg.input_sz ** 2
+        if not (self.fused and self.cfg.method == 'mc'):
+            return self._kl_diag
+        b = self._buffers(B)
+        if 'kld_ws' not in b:
+            b['kld_ws'] = torch.empty(lib.pvae_kl_diag_ws_floats(B, K), device=self.device)
+            b['kld'] = torch.empty(K, device=self.device)
+            offs = (ctypes.c_int64 * 7)()
+            _lib.check(lib.pvae_lin_step_ws_offsets(B, K, D, offs))
+            b['h_off'] = int(offs[0])
+        h = b['ws'][b['h_off']:]
+        bias = m.fc_enc.bias
+        _lib.check(lib.pvae_kl_diag(_ptr(h), _ptr(self.views['log_rate']), None if bias is None else _ptr(self.views['fc_enc.bias']),
+                                    _ptr(b['kld']), _ptr(b['kld_ws']), B, K, int(m.cfg.exc_only), _stream()))
+        return b['kld']
+
+    def _flush_stats(self, pend, ring, meters, write, kl_diag, beta):
+        """One device->host read for the steps in `pend` (ring rows [loss, mse, kl, -, grad_norm]); fills self.stats like
+        main/train_vae.py:373-408 and, when `write`, appends the reference's wandb dictionary (:410-445) to self.log."""
+        cfg, m = self.cfg, self.model
+        n, slots, K = len(pend), self.r_max.numel(), m.cfg.n_latents
+        parts = [ring[:n].reshape(-1), self.r_max]
+        if write and kl_diag is not None:
+            if self.world > 1:
+                kl_diag = kl_diag.clone()
+                torch.distributed.all_reduce(kl_diag, group=self.pg)
+                kl_diag /= self.world
+            parts.append(kl_diag)
+        host = torch.cat(parts).cpu()  # the only sync
+        rows, rmax = host[:n * 8].view(n, 8), host[n * 8:n * 8 + slots]
+        for j, g in enumerate(pend):
+            loss, mse, kl, gn = (float(rows[j, i]) for i in (0, 1, 2, 4))
+            if cfg.grad_clip is not None:  # :365-377
+                meters['grads'].update(gn)
+                self.stats['grad'][g] = gn
+                if gn > cfg.grad_clip:
+                    self.stats['loss'][g] = loss
+            meters['nelbo'].update(mse + kl)  # :379-388
+            meters['perdim_mse'].update(mse / m.cfg.input_sz ** 2)
+            meters['perdim_kl'].update(kl / K)
+            meters['r_max'].update(float(rmax[g % slots]))
+            warming = g / self.n_iters < cfg.warmup_portion
+            self.stats['lr'][g] = self.lr_at(g) if warming else self.lr_at(g + 1)  # read after the scheduler stepped, :394-402
+            self.stats['temp'][g] = float(self.temperatures[min(g, self.n_iters - 1)])
+            self.stats['r_max'][g] = meters['r_max'].avg
+            self.stats['n_exp'][g] = m._n_exp_host
+            if write and j == n - 1:
+                to_write = {'coeffs/beta': beta, 'coeffs/temp': self.stats['temp'][g], 'coeffs/lr': self.stats['lr'][g],
+                            'coeffs/r_max': meters['r_max'].avg, 'coeffs/n_exp': m._n_exp_host, 'train/loss_kl': kl,
+                            'train/loss_mse': mse, 'train/nelbo_avg': meters['nelbo'].avg, 'train/perdim_kl': meters['perdim_kl'].avg,
+                            'train/perdim_mse': meters['perdim_mse'].avg, 'train/weight_reg': 0}
+                if cfg.grad_clip is not None:
+                    to_write['train/grad_norm'] = meters['grads'].avg
+                if kl_diag is not None:
+                    n_active = int((host[n * 8 + slots:] > 0.01).sum())  # :442-445
+                    to_write['train/n_active'] = n_active
+                    to_write['train/n_active_ratio'] = n_active / K
+                to_write['gstep'] = g
+                self.log.append(to_write)
+            if g % 100 == 0:  # :447-449
+                meters['grads'].reset()
+                meters['nelbo'].reset()
+
     def iteration(self, data: torch.Tensor, epoch: int = 0):
         """One epoch over a device-resident dataset (N, 1, H, W), like main/train_vae.py:317-459 with a
-        batched index-select instead of the DataLoader; returns the epoch's mean nelbo (one host sync)."""
-        B = self.cfg.batch_size
+        batched index-select instead of the DataLoader; returns the epoch's mean nelbo.  Host syncs: one per
+        cfg.log_freq steps (the statistics ring) and one at the end of the epoch."""
+        cfg = self.cfg
+        B = cfg.batch_size
         self.model.train()  # main/train_vae.py:318
         n_batches = data.shape[0] // B  # drop_last
         perm = torch.randperm(data.shape[0], device=data.device)
         self.r_max.zero_()
         total = torch.zeros(3, device=self.device)
+        log_freq = max(int(cfg.log_freq), 1)
+        if self._ring is None or self._ring.shape[0] != log_freq + 1:
+            self._ring = torch.zeros(log_freq + 1, 8, device=self.device)
+        ring, pend = self._ring, []
+        meters = {k: _AverageMeter() for k in ('nelbo', 'grads', 'r_max', 'perdim_kl', 'perdim_mse')}
         for i in range(n_batches):
+            gstep = epoch * n_batches + i
             x = data[perm[i * B:(i + 1) * B]]
-            total += self.train_step(x, epoch * n_batches + i)
+            write = gstep > 0 and gstep % log_freq == 0
+            slot = ring[len(pend)]
+            self._want_kl_diag = write
+            self.train_step(x, gstep, loss_out=slot[:4])
+            self._want_kl_diag = False
+            total += slot[:3]
+            if cfg.grad_clip is not None:
+                slot[4:5].copy_(self._buffers(x.shape[0])['norm'][:1])
+            pend.append(gstep)
+            if write or len(pend) == ring.shape[0]:
+                kl_diag = self._kl_diag_of_last_step(x.shape[0]) if write else None
+                self._flush_stats(pend, ring, meters, write, kl_diag, float(self.betas[min(gstep, self.n_iters - 1)]))
+                pend = []
+        if pend:
+            self._flush_stats(pend, ring, meters, False, None, 0.0)
         nelbo_mse_kl = (total / max(n_batches, 1)).tolist()
         # end-of-epoch n_exp update from the mean of the per-step rate.max(), main/train_vae.py:388,456-457
         dp.allreduce_max(self.r_max, self.pg)
@@ -767,3 +865,18 @@ class TrainerVAE:
         if r_max > 0:
             self.model.update_n(r_max)
         return nelbo_mse_kl[1] + nelbo_mse_kl[2]
+
+
+class _AverageMeter:
+    """base/utils_model.py AverageMeter: running mean since the last reset."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.sum, self.cnt, self.avg = 0.0, 0, 0.0
+
+    def update(self, v, n=1):
+        self.sum += v * n
+        self.cnt += n
+        self.avg = self.sum / self.cnt

@@ -344,3 +344,83 @@ def test_coefficient_mode_matches_the_recompute_backward():
         assert torch.equal(a, b)
     for name, a, b in zip(("losses", "gradient", "parameters"), out["default"], out["coef"]):
         assert_rel(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-6, what=name)
+
+
+@pytest.mark.parametrize("clip", [None, 0.5])
+def test_iteration_statistics_match_a_synchronous_replay(clip):
+    """TrainerVAE.iteration fills the reference's per-gstep statistics (main/train_vae.py:373-408) and its logging dictionary
+    (:410-445: nelbo / per-dim averages, kl_diag -> n_active, grad norm) from a device ring read once per log_freq steps.
+    Replayed here step by step with a host read after every step and kl_diag from the torch formulas (main/vae.py:405,
+    446-450) on the parameters the step saw."""
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
+    B, n_batches, log_freq, K = 256, 7, 3, 128
+    data = torch.randn(B * n_batches, 1, 16, 16, generator=torch.Generator().manual_seed(3)).cuda()
+
+    def make():
+        model = PoissonVAE(ConfigPoisVAE(n_latents=K, prior_clamp=-4, seed=2)).cuda()
+        with torch.no_grad():
+            model.log_rate.add_(4.0)
+        model.update_n(15.0)
+        cfg = ConfigTrainVAE(lr=0.01, epochs=3, batch_size=B, temp_anneal_portion=0.5, kl_anneal_portion=0.3, kl_const_portion=0.0,
+                             warmup_portion=0.2, grad_clip=clip, log_freq=log_freq)
+        return model, TrainerVAE(model, cfg, n_batches_per_epoch=n_batches)
+
+    model, tr = make()
+    torch.manual_seed(21)
+    torch.cuda.manual_seed(21)
+    for epoch in range(2):
+        tr.iteration(data, epoch)
+    # replay
+    model2, tr2 = make()
+    torch.manual_seed(21)
+    torch.cuda.manual_seed(21)
+    sp = torch.nn.functional.softplus
+    want_log, want_rmax, want_grad = [], {}, {}
+    for epoch in range(2):
+        perm = torch.randperm(data.shape[0], device=data.device)
+        tr2.r_max.zero_()
+        nelbo_sum, nelbo_cnt, rsum, pk, pm, gsum, gcnt = 0.0, 0, 0.0, 0.0, 0.0, 0.0, 0
+        for i in range(n_batches):
+            g = epoch * n_batches + i
+            x = data[perm[i * B:(i + 1) * B]]
+            with torch.no_grad():
+                h = x.reshape(B, -1) @ model2.fc_enc.weight.T
+                log_dr = 10.0 - sp(10.0 - h)
+                kl_diag = (torch.exp(model2.log_rate) * (1 + torch.exp(log_dr) * (log_dr - 1))).mean(0)
+            loss, mse, kl = tr2.train_step(x, g).tolist()
+            nelbo_sum, nelbo_cnt = nelbo_sum + mse + kl, nelbo_cnt + 1
+            rsum += float(tr2.r_max[g % n_batches])
+            pk, pm = pk + kl / K, pm + mse / 256
+            want_rmax[g] = rsum / (i + 1)
+            if clip is not None:
+                gn = float(tr2._buffers(B)['norm'][0])
+                want_grad[g] = gn
+                gsum, gcnt = gsum + gn, gcnt + 1
+            if g > 0 and g % log_freq == 0:
+                want_log.append(dict(g=g, kl=kl, mse=mse, nelbo=nelbo_sum / nelbo_cnt, pk=pk / (i + 1), pm=pm / (i + 1),
+                                     n_active=int((kl_diag > 0.01).sum()), gn=gsum / max(gcnt, 1)))
+            if g % 100 == 0:
+                nelbo_sum, nelbo_cnt, gsum, gcnt = 0.0, 0, 0.0, 0
+        tr2.model.update_n(float(tr2.r_max[:n_batches].mean()))
+    assert sorted(tr.stats['lr']) == list(range(2 * n_batches))
+    for g in range(2 * n_batches):
+        warming = g / tr.n_iters < 0.2
+        assert tr.stats['lr'][g] == (tr.lr_at(g) if warming else tr.lr_at(g + 1))
+        assert tr.stats['temp'][g] == float(tr.temperatures[g])
+        assert abs(tr.stats['r_max'][g] - want_rmax[g]) <= 1e-6 * want_rmax[g]
+        if clip is not None:
+            assert abs(tr.stats['grad'][g] - want_grad[g]) <= 1e-5 * want_grad[g]
+            assert (g in tr.stats['loss']) == (want_grad[g] > clip)
+    assert tr.stats['n_exp'][0] == 15 or tr.stats['n_exp'][0] > 0
+    assert [e['gstep'] for e in tr.log] == [w['g'] for w in want_log] and len(tr.log) >= 3
+    for got, w in zip(tr.log, want_log):
+        for key, ref in (('train/loss_kl', w['kl']), ('train/loss_mse', w['mse']), ('train/nelbo_avg', w['nelbo']),
+                         ('train/perdim_kl', w['pk']), ('train/perdim_mse', w['pm'])):
+            assert abs(got[key] - ref) <= 2e-5 * abs(ref), (key, got[key], ref)
+        assert abs(got['train/n_active'] - w['n_active']) <= 1 and got['train/n_active_ratio'] == got['train/n_active'] / K
+        assert 0 < got['train/n_active'] <= K
+        if clip is not None:
+            assert abs(got['train/grad_norm'] - w['gn']) <= 1e-5 * w['gn']
+        assert got['coeffs/n_exp'] > 0 and got['coeffs/beta'] > 0
+    assert torch.equal(tr.flat_p, tr2.flat_p)  # the ring did not change the training itself

@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--no_overlap", action="store_true")
     ap.add_argument("--no_carveout", action="store_true")
     ap.add_argument("--coef", action="store_true")
-    ap.add_argument("--unfused", action="store_true", help="sampler, decoder GEMM and residual as three kernels")
+    ap.add_argument("--fused", action="store_true", help="fused forward kernel (sampler + decoder GEMM + residual in one launch)")
     ap.add_argument("--fused_debug", type=int, default=0)
     ap.add_argument("--pool", type=int, default=1, help="forward sampler schedule: 0 row by row, 1 per-row-tile pool, 2 one-wave pool")
     a = ap.parse_args()
@@ -44,7 +44,7 @@ def main():
         lib.pvae_set_carveout(0)
     lib.pvae_set_pool(a.pool)
     lib.pvae_set_step_coef(1 if a.coef else 0)
-    lib.pvae_set_step_fused(0 if a.unfused else 1)
+    lib.pvae_set_step_fused(1 if a.fused else 0)
     lib.pvae_set_fused_debug(a.fused_debug)
     B, K = a.batch, a.latents
     model = PoissonVAE(ConfigPoisVAE(n_latents=K, prior_clamp=-4, seed=0)).cuda()
