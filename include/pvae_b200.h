@@ -296,6 +296,8 @@ int pvae_set_fused_debug(int mode);
 /* Debugging aid: ts_dev = 1024 device words that CTA 0 of pvae_fused_fwd fills with %globaltimer stamps of its phases
  * (tools/fused_timeline.py decodes them); NULL switches it off. */
 int pvae_set_fused_timeline(uint64_t* ts_dev);
+/* The same for pvae_gemm_tf32 (tools/gemm_timeline.py): tile (0,0,0)'s pipeline stamps + extremes over all CTAs. */
+int pvae_set_gemm_timeline(uint64_t* ts_dev);
 /* Tuning knob (process-wide, default on): pvae_lin_step_fwd_bwd reduces the wgrad split partials and the sampler's column
  * partials with ONE kernel instead of two split-K reductions + one or two column-sum kernels (bit-identical results). */
 int pvae_set_fuse_reduce(int on);

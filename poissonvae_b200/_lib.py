@@ -127,6 +127,7 @@ _SIGNATURES = {
     "pvae_kl_diag": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _p]),
     "pvae_set_fused_debug": (_i, [_i]),
     "pvae_set_fused_timeline": (_i, [_p]),
+    "pvae_set_gemm_timeline": (_i, [_p]),
     "pvae_fused_fwd_supported": (_i, [_i64, _i64, _i64]),
     "pvae_fused_fwd": (_i, [_p] * 14 + [_i64, _i64, _i64, _i64, _i, _f, _i, _i, _f, _f, _u64, _u64, _p, _p]),
     "pvae_lin_step_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _i, _f, _f, _i, _i, _f, _i,

@@ -48,7 +48,19 @@ struct GemmParams {
   float* G_lo;  // optional: TF32 low plane of G for the GEMMs that consume it
   float* row_part;
   float g_scale;
+  unsigned long long* dbg_ts;  // optional: %globaltimer stamps of the tile (0,0,0) and extremes over all CTAs (pvae_set_gemm_timeline)
 };
+
+__device__ __forceinline__ void gstamp(const GemmParams& p, int idx, bool all = false) {
+  if (p.dbg_ts == nullptr) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  if (all) {
+    if (idx & 1) atomicMax(p.dbg_ts + idx, t); else atomicMin(p.dbg_ts + idx, t);
+  } else if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    p.dbg_ts[idx] = t;
+  }
+}
 
 // SPLIT: 0 = single-pass TF32; 1 = 3xTF32, the low parts computed in the kernel by the epilogue warps (operands as they
 // are in HBM); 2 = 3xTF32, the low parts arrive as their own planes by TMA (written once by whoever produced the operand:
@@ -114,7 +126,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
   pdl_launch_dependents();
+  if (threadIdx.x == 0) gstamp(p, 0), gstamp(p, 700, true);
   pdl_wait();
+  if (threadIdx.x == 0) gstamp(p, 1), gstamp(p, 701, true);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -126,6 +140,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         uint8_t* sa = smem + s * kStageBytes;
         uint8_t* sb = sa + kABytes;
         mbar_expect_tx(&full_bar[s], SPLIT == 2 ? 2 * kTileBytes : kTileBytes);
+        gstamp(p, 10 + kb);
         const int k0 = k_begin + kb * kBK;
 #pragma unroll
         for (int plane = 0; plane < (SPLIT == 2 ? 2 : 1); ++plane) {  // plane 1: the TF32 low parts, kTileBytes above
@@ -163,6 +178,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int s = kb % kStages;
         const uint32_t round = kb / kStages;
         mbar_wait(SPLIT == 1 ? &conv_bar[s] : &full_bar[s], round & 1);
+        gstamp(p, 30 + kb);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_u32(smem + s * kStageBytes), sb = sa + kABytes;
 #pragma unroll
@@ -178,6 +194,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        gstamp(p, 50 + kb);
       }
       umma_commit(accum_bar);  // accumulator complete
     }
@@ -207,6 +224,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     // ===== epilogue: TMEM -> registers -> global =====
     mbar_wait(accum_bar, 0);
+    if (threadIdx.x == 64) gstamp(p, 70), gstamp(p, 703, true);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quarter = warp & 3;  // a warp may only read TMEM lanes [32 * (warp % 4), +32)
     float* cbase = p.C + static_cast<long long>(blockIdx.z) * p.split_stride;
@@ -298,6 +316,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 64) gstamp(p, 71), gstamp(p, 705, true);
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
@@ -409,7 +428,8 @@ int launch_splitk_reduce(const float* ws, float* C, long long n, int splits, cud
   return cuda_ok("splitk_reduce_kernel", launch_pdl(splitk_reduce_kernel, dim3(grid), dim3(256), 0, s, ws, C, n4, splits));
 }
 
-static int g_gemm_variant = 0;  // tuning: 0 = automatic, 1 = wide tiles / 1 CTA per SM, 2 = narrow tiles / 2 CTAs per SM
+static int g_gemm_variant = 0;
+static unsigned long long* g_gemm_ts = nullptr;  // tuning: 0 = automatic, 1 = wide tiles / 1 CTA per SM, 2 = narrow tiles / 2 CTAs per SM
 
 }  // namespace pvae
 
@@ -423,6 +443,11 @@ extern "C" int pvae_gemm_effective_splits(int64_t Kd, int splits) {
   if (splits > kblocks) splits = static_cast<int>(kblocks);
   const long long per = (kblocks + splits - 1) / splits;  // every split owns at least one K block
   return static_cast<int>((kblocks + per - 1) / per);
+}
+
+extern "C" int pvae_set_gemm_timeline(uint64_t* ts_dev) {
+  g_gemm_ts = reinterpret_cast<unsigned long long*>(ts_dev);
+  return PVAE_OK;
 }
 
 extern "C" int pvae_set_gemm_variant(int v) {
@@ -476,6 +501,7 @@ int gemm_impl(const float* A, const float* A_lo, const float* B, const float* B_
   p.a_kmajor = a_kmajor, p.b_kmajor = b_kmajor;
   p.split_stride = splits > 1 ? M * N : 0;
   p.X = X, p.G = G, p.G_lo = G_lo, p.row_part = row_part, p.g_scale = g_scale;
+  p.dbg_ts = g_gemm_ts;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rc;
   if (planes) {
