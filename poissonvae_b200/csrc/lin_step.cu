@@ -22,7 +22,7 @@ namespace {
 // Side stream for the work that is off the critical path (decoder wgrad, loss assembly): created once per device.
 struct SideStream {
   cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, dgrad = nullptr;
 };
 
 SideStream* side_stream() {
@@ -34,6 +34,7 @@ SideStream* side_stream() {
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.dgrad, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   }
   return &s;
 }
@@ -238,10 +239,18 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
   if (has_bias) seg[3] = pvae_grad_segment{K + 2 * K * D, K, w.partials + bias_row * K, prow, 1, K, nullptr, 0, 0.f};
   pvae::AdamaxDev dev;
   dev.lr_sched = d.lr_sched, dev.n_sched = d.n_sched, dev.state = d.state;
+  // the data gradient first: it READS W_dec, which exchange bucket 0 below updates in place
+  if ((rc = gemm(w.g_y, g_y_lo, w_dec, w_dec_lo, w.g_z, B, K, D, 1, 0, 1, nullptr, s))) return rc;
   if (dp_peer) {
     // Exchange bucket 0 = W_dec's gradient (+ the loss statistics), complete as soon as the decoder wgrad is: its sum over
-    // the ranks and its Adamax update run on the side stream UNDER the dgrad GEMM, the sampler backward and the encoder
-    // wgrad of the main stream.  Only bucket 1 (log_r, W_enc, b_enc) stays on the critical path.
+    // the ranks and its Adamax update run on the side stream UNDER the sampler backward and the encoder wgrad of the main
+    // stream - but only after the dgrad GEMM, the last reader of W_dec, has finished (an event; without it the update raced
+    // with that GEMM: 2-rank parameters 5e-3 off the single-GPU ones).  Only bucket 1 (log_r, W_enc, b_enc) stays on the
+    // critical path.
+    if (side) {
+      if ((rc = pvae::cuda_ok("dgrad event", cudaEventRecord(side->dgrad, s)))) return rc;
+      if ((rc = pvae::cuda_ok("dgrad event", cudaStreamWaitEvent(s2, side->dgrad, 0)))) return rc;
+    }
     if (fuse && (rc = pvae::adamax_from_partials_impl(nullptr, nullptr, d.grads, nullptr, nullptr, seg + 2, 1, 0.f, 1, 0.f, 0.f, 0.f, 0.f,
                                                       pvae::AdamaxDev{}, s2)))
       return rc;
@@ -252,7 +261,6 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
       return rc;
   }
   if (side && (rc = pvae::cuda_ok("join", cudaEventRecord(side->join, s2)))) return rc;
-  if ((rc = gemm(w.g_y, g_y_lo, w_dec, w_dec_lo, w.g_z, B, K, D, 1, 0, 1, nullptr, s))) return rc;
   trace();  // 6: dgrad
   mark(2);
   if (coef) {
