@@ -153,7 +153,7 @@ int pvae_gemm_tf32(const float* A, const float* B, float* C, int64_t M, int64_t 
                    int precise, int splits, float* splitk_ws, void* stream);
 /* Decoder GEMM of the training step with BaseVAE.loss_recon (main/vae.py:68-72) and its gradient fused into the
  * epilogue: y = A B^T (A (M,Kd), B (N,Kd), both K-major) is never stored; instead G (M,N) = g_scale * (y - X) and
- * row_part (M, P) with P = pvae_gemm_residual_parts(N): row_part[m, p] = sum over the p-th 64-column tile of (y - X)^2. */
+ * row_part (M, P) with P = pvae_gemm_residual_parts(N): row_part[m, p] = sum over the p-th 32-column half tile of (y - X)^2. */
 int64_t pvae_gemm_residual_parts(int64_t N);
 int pvae_gemm_tf32_residual(const float* A, const float* B, const float* X, float* G, float* row_part, int64_t M, int64_t N,
                             int64_t Kd, float g_scale, int precise, void* stream);

@@ -66,6 +66,11 @@ __device__ __forceinline__ void gstamp(const GemmParams& p, int idx, bool all = 
 // are in HBM); 2 = 3xTF32, the low parts arrive as their own planes by TMA (written once by whoever produced the operand:
 // sampler / residual / Adamax epilogues), so the main loop is pure TMA -> tcgen05.mma.  Modes 1 and 2 issue the same MMAs
 // in the same order on the same bits: bit-identical results.
+// Warps 0 / 1: TMA producer / MMA issuer; warps 2..9: EIGHT epilogue warps - two per TMEM lane quarter, each half of the
+// tile's columns (the epilogue of a 128 x 128 tile took 2.2 of the kernel's 8.6 us with four, tools/gemm_timeline.py).
+constexpr int kEpiWarps = 8;
+constexpr int kDenseThreads = 64 + 32 * kEpiWarps;
+
 template <int BN, int SPLIT, int STAGES>
 struct GemmCfg {
   static constexpr uint32_t kABytes = kBM * kBK * 4;  // 16 KB
@@ -78,7 +83,7 @@ struct GemmCfg {
 };
 
 template <int BN, int SPLIT, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads, GemmCfg<BN, SPLIT, STAGES>::kCtasPerSm)
+__global__ void __launch_bounds__(kDenseThreads, GemmCfg<BN, SPLIT, STAGES>::kCtasPerSm)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_a_lo, const __grid_constant__ CUtensorMap tma_b_lo, const GemmParams p) {
   using Cfg = GemmCfg<BN, SPLIT, STAGES>;
@@ -108,7 +113,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
-      mbar_init(&conv_bar[s], kGemmThreads - 64);
+      mbar_init(&conv_bar[s], kDenseThreads - 64);
     }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -208,7 +213,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         uint4* tile = reinterpret_cast<uint4*>(smem + s * kStageBytes);
         uint4* tile_lo = reinterpret_cast<uint4*>(smem + s * kStageBytes + kTileBytes);
 #pragma unroll 4
-        for (int i = ct; i < static_cast<int>(kTileBytes / 16); i += kGemmThreads - 64) {
+        for (int i = ct; i < static_cast<int>(kTileBytes / 16); i += kDenseThreads - 64) {
           const uint4 v = tile[i];
           uint4 hi, lo;
           hi.x = v.x & 0xFFFFE000u, hi.y = v.y & 0xFFFFE000u, hi.z = v.z & 0xFFFFE000u, hi.w = v.w & 0xFFFFE000u;
@@ -227,11 +232,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (threadIdx.x == 64) gstamp(p, 70), gstamp(p, 703, true);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quarter = warp & 3;  // a warp may only read TMEM lanes [32 * (warp % 4), +32)
+    const int chalf = (warp - 2) >> 2;  // which half of the tile's columns
     float* cbase = p.C + static_cast<long long>(blockIdx.z) * p.split_stride;
     const bool residual = p.X != nullptr;
     float rowacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
       uint32_t v[32];
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0);
       asm volatile(
@@ -309,7 +315,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int mm = m0 + quarter * 32 + 4 * i + (lane >> 3);
-        if (mm < p.M) p.row_part[static_cast<long long>(mm) * gridDim.x + blockIdx.x] = rowacc[i];
+        if (mm < p.M) p.row_part[static_cast<long long>(mm) * (2 * gridDim.x) + 2 * blockIdx.x + chalf] = rowacc[i];
       }
     }
   }
@@ -419,7 +425,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
     configured = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, splits);
-  return cuda_ok("gemm_tf32_kernel", launch_pdl(gemm_tf32_kernel<BN, SPLIT, STAGES>, grid, dim3(kGemmThreads), smem, s, ma, mb, mal, mbl, p));
+  return cuda_ok("gemm_tf32_kernel", launch_pdl(gemm_tf32_kernel<BN, SPLIT, STAGES>, grid, dim3(kDenseThreads), smem, s, ma, mb, mal, mbl, p));
 }
 
 int launch_splitk_reduce(const float* ws, float* C, long long n, int splits, cudaStream_t s) {
@@ -534,8 +540,9 @@ extern "C" int pvae_gemm_tf32_planes(const float* A, const float* A_lo, const fl
   return gemm_impl(A, A_lo, B, B_lo, C, M, N, Kd, a_kmajor, b_kmajor, 1, splits, splitk_ws, nullptr, nullptr, nullptr, nullptr, 0.f, 0, stream);
 }
 
-// 64-wide tiles: the decoder output is only D = 256 wide, so this keeps 4 * M / 128 CTAs in flight
-extern "C" int64_t pvae_gemm_residual_parts(int64_t N) { return (N + 63) / 64; }
+// 64-wide tiles: the decoder output is only D = 256 wide, so this keeps 4 * M / 128 CTAs in flight; each tile's two
+// epilogue column halves write their own partial squared error
+extern "C" int64_t pvae_gemm_residual_parts(int64_t N) { return 2 * ((N + 63) / 64); }
 
 extern "C" int pvae_gemm_tf32_residual(const float* A, const float* B, const float* X, float* G, float* row_part, int64_t M,
                                        int64_t N, int64_t Kd, float g_scale, int precise, void* stream) {
