@@ -48,22 +48,20 @@ constexpr int kFsGroupLanes = kFsGroupWarps * 32;  // three warps each (704 thre
 constexpr int kFsWarps = kFsGroups * kFsGroupWarps; // sampler warps
 constexpr int kFsLanes = kFsWarps * 32;
 constexpr int kFsThreads = kFsLanes + 64;          // + the TMA warp and the MMA warp
-constexpr int kFsRows = 32;                        // N of the MMA (rows of the operand tile)
 constexpr int kFsMaxUnitRows = 28;                 // rows per unit: at most 4 per group
 constexpr int kFsGroupRows = 4;
 constexpr int kFsKb = 8;                           // k-blocks (32 latents) per batch
 constexpr int kFsBatchK = kFsKb * 32;              // 256 latents per batch
 constexpr int kFsGPool = kFsGroupRows * kFsKb * 8; // 256 pool entries (quads) per group and batch
 constexpr int kFsMaxK = 1024;
-constexpr int kFsWStages = 7;                        // 16 KB each.  A stage is free again a TMA latency + an MMA completion latency
-                                                     // (~1 us, measured) after its request: the ring must cover that at the issuer's pace
+constexpr int kFsWStages = 3;                        // 32 KB each (one plane of a k-block of W_dec, all D = 256 rows)
 constexpr int kFsZSlots = 8;                         // operand-tile ring: k-blocks a group may run ahead of the tensor core
 constexpr uint32_t kFsZTile = 32 * 128;            // one plane of a 32-row x 32-latent operand tile
-constexpr uint32_t kFsWTile = 128 * 128;           // one plane of a 128-row x 32-latent W_dec tile = one ring stage
+constexpr uint32_t kFsWTile = 256 * 128;           // one plane of a D-row x 32-latent W_dec tile = one ring stage (D <= 256)
 
 constexpr uint32_t kOffZ = 0;                                           // [slot][plane][32 rows x 128 B]
 constexpr uint32_t kOffW = kOffZ + kFsZSlots * 2 * kFsZTile;            // 64 KB
-constexpr uint32_t kOffRate = kOffW + kFsWStages * kFsWTile;            // + 112 KB
+constexpr uint32_t kOffRate = kOffW + kFsWStages * kFsWTile;            // + 96 KB
 constexpr uint32_t kOffList = kOffRate + kFsGroups * 4 * kFsGPool * 4;  // + 28 KB   [group][4][256]
 constexpr uint32_t kOffKl = kOffList + kFsGroups * kFsGPool * 2;        // + 3.75 KB [group][256]: listed from the front, late parks from the back
 constexpr uint32_t kOffElr = kOffKl + kFsGroups * 32 * kFsGroupRows * 4;  // + 3.75 KB [group][k-block][row]
@@ -72,7 +70,7 @@ constexpr uint32_t kOffMax = kOffRecon + 2 * 8 * 32 * 4;                // + 2 K
 constexpr uint32_t kOffCnt = kOffMax + 128;                             // [group][2 sets][8]
 constexpr uint32_t kOffBar = kOffCnt + kFsGroups * 16 * 4;
 constexpr uint32_t kFsSmem = kOffBar + 256 + 1024;                      // barriers, alignment slack
-constexpr uint32_t kFsTmemCols = 128;                                   // per column half: 32 (hi) + 32 (cross)
+constexpr uint32_t kFsTmemCols = 512;                                   // D columns hi*hi + D columns cross terms (lane = row)
 static_assert(kFsSmem <= 232448, "fused forward: shared memory");
 
 struct FusedParams {
@@ -153,9 +151,9 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = static_cast<int>(p.K), Kq = K >> 2, D = fp.D;
-  const int nkb = K / 32, nbatch = K / kFsBatchK, halves = D / 128;
+  const int nkb = K / 32, nbatch = K / kFsBatchK;
   const int R = fp.rows_unit;
-  const int n_ep = halves * 4;  // epilogue warps: (column half, TMEM lane quarter)
+  const int n_ep = 4;  // epilogue warps (the four with warp % 4 == 0 among the first 16)
 
   if (warp == kFsWarps) {
     if (lane == 0) {
@@ -186,19 +184,23 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
       int n_my = 0;
       for (int u = blockIdx.x; u < fp.n_units; u += gridDim.x) ++n_my;
       const uint32_t nplanes = fp.debug == 2 ? 1 : 2;
-      const uint32_t per_unit = static_cast<uint32_t>(nkb * halves) * nplanes, total = per_unit * n_my;
+      const uint32_t per_unit = static_cast<uint32_t>(nkb) * nplanes, total = per_unit * n_my;
+      const uint32_t stage_bytes = static_cast<uint32_t>(D) * 128;
       for (uint32_t j = 0; j < total; ++j) {
-        const uint32_t s = j % kFsWStages, w = j % per_unit, plane = w % nplanes, tile = w / nplanes;
+        const uint32_t s = j % kFsWStages, w = j % per_unit, plane = w % nplanes, kbg = w / nplanes;
         mbar_wait(&w_empty[s], ((j / kFsWStages) & 1) ^ 1);
-        mbar_expect_tx(&w_full[s], kFsWTile);
-        tma_load_2d(plane ? &tma_w_lo : &tma_w, &w_full[s], smem + kOffW + s * kFsWTile, static_cast<int>(tile / halves) * 32,
-                    static_cast<int>(tile % halves) * 128);
+        mbar_expect_tx(&w_full[s], stage_bytes);
+        tma_load_2d(plane ? &tma_w_lo : &tma_w, &w_full[s], smem + kOffW + s * kFsWTile, static_cast<int>(kbg) * 32, 0);
       }
     }
   } else if (warp == kFsWarps) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, kFsRows, false, false);  // M = 128 output columns, N = 32 rows
+      // y (rows, D) += z (rows, 32) W_dec(D, 32)^T: A = the z tile (M = 128 of which the unit's <= 28 rows are live - the rows
+      // above alias whatever follows the 4 KB tile in shared memory, their accumulator lanes are never read; an MMA costs
+      // the same ~0.09 us whatever its shape, so padding M is free while N = D = 256 halves the instruction count of the
+      // transposed product this kernel used first), B = the W_dec tile (N = D rows).  12 MMAs per k-block.
+      const uint32_t idesc = make_idesc(128, D, false, false);
       const bool no_mma = fp.debug == 1, hi_only = fp.debug == 2;
       const uint32_t nplanes = hi_only ? 1 : 2;
       stamp(fp, 1);
@@ -218,23 +220,22 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t za = smem_u32(smem + kOffZ + slot * 2 * kFsZTile), zl = za + kFsZTile;
-            for (uint32_t sub = 0; sub < static_cast<uint32_t>(halves) * nplanes && !no_mma; ++sub, ++it) {
-              const uint32_t hf = sub / nplanes, plane = sub % nplanes;
+            for (uint32_t plane = 0; plane < nplanes && !no_mma; ++plane, ++it) {
               const uint32_t s = it % kFsWStages;
               mbar_wait(&w_full[s], (it / kFsWStages) & 1);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               const uint32_t wb = smem_u32(smem + kOffW + s * kFsWTile);
-              const uint32_t d_hi = tmem_base + hf * 64, d_x = d_hi + 32;
+              const uint32_t d_hi = tmem_base, d_x = tmem_base + D;
 #pragma unroll
               for (int k = 0; k < kBK / kUmmaK; ++k) {
                 const uint64_t dz = make_smem_desc(za + k * 32, 16, 1024, 2), dzl = make_smem_desc(zl + k * 32, 16, 1024, 2);
                 const uint64_t dw = make_smem_desc(wb + k * 32, 16, 1024, 2);
                 const uint32_t acc = (b > 0 || kb > 0 || k > 0) ? 1u : 0u;
                 if (plane == 0) {
-                  umma_tf32(d_hi, dw, dz, idesc, acc);               // hi(W) hi(z)
-                  if (!hi_only) umma_tf32(d_x, dw, dzl, idesc, acc);  // hi(W) lo(z)
+                  umma_tf32(d_hi, dz, dw, idesc, acc);               // hi(z) hi(W)
+                  if (!hi_only) umma_tf32(d_x, dzl, dw, idesc, acc);  // lo(z) hi(W)
                 } else {
-                  umma_tf32(d_x, dw, dz, idesc, 1u);                 // lo(W) hi(z)
+                  umma_tf32(d_x, dz, dw, idesc, 1u);                 // hi(z) lo(W)
                 }
               }
               umma_commit(&w_empty[s]);  // frees the ring stage once these MMAs have read it
@@ -537,54 +538,60 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constan
           p.kl_rowsum[grow + gtid] = s;
         }
         named_bar_sync(bar_id, kFsGroupLanes);  // the group's tables are reused by its next batch
-        if (gtid == 0) stamp(fp, 300 + (g * 8 + bi) * 4 + 3), stamp_all(fp, 703);
+        if (gtid == 0) {
+          stamp(fp, 300 + (g * 8 + bi) * 4 + 3), stamp_all(fp, 703);
+          if (fp.dbg_ts != nullptr && blockIdx.x < 148) {  // per CTA: latest end of a batch (any group)
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            atomicMax(fp.dbg_ts + 800 + blockIdx.x, t);
+          }
+        }
       }  // batches
 
-      // ---- unit epilogue (warps 0 .. n_ep - 1): the reconstruction residual from TMEM
-      if (warp < n_ep) {
-        // accumulator lane = output column, accumulator column = row of the unit: this lane owns column `col` of all rows
-        const int q = warp & 3, hf = warp >> 2;
-        const int col = hf * 128 + q * 32 + lane;
+      // ---- unit epilogue: the reconstruction residual from TMEM.  Accumulator lane = row of the unit, so only the warps with
+      // warp % 4 == 0 (TMEM lanes 0..31) can read it: warps 0, 4, 8, 12 take D / 4 columns each
+      if ((warp & 3) == 0 && (warp >> 2) < n_ep) {
+        const int i = warp >> 2, ncol = D / n_ep;  // output columns [ncol i, ncol (i + 1))
         const int urows = static_cast<int>(min(static_cast<long long>(R), p.B - row0));
         mbar_wait(acc_full, ui & 1);
         if (tid == 0) stamp(fp, 600), stamp_all(fp, 705);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + hf * 64;
-        float* const rec = s_recon + (ui & 1) * 256 + warp * 32;
+        const uint32_t tcol = tmem_base + i * ncol;
+        const bool rv = lane < urows;
+        const long long gbase = (row0 + lane) * D + ncol * i;
+        float sq = 0.f;
 #pragma unroll 1
-        for (int r0 = 0; r0 < kFsRows; r0 += 16) {
+        for (int c0 = 0; c0 < ncol; c0 += 16) {
           uint32_t v[16], w[16];
-          float xv[16];
-          tmem_ld_32x16(tcol + r0, v);
-          tmem_ld_32x16(tcol + 32 + r0, w);
+          tmem_ld_32x16(tcol + c0, v);
+          tmem_ld_32x16(tcol + D + c0, w);
+          float4 xv[4];
 #pragma unroll
-          for (int i = 0; i < 16; ++i)  // all loads of the chunk in flight before the first store (g_y may alias nothing, but the compiler cannot know)
-            xv[i] = r0 + i < urows ? __ldg(fp.x + (row0 + r0 + i) * D + col) : 0.f;
+          for (int c = 0; c < 4; ++c) xv[c] = rv ? ldg4(fp.x + gbase + c0 + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
           tmem_ld_wait();
+          if (rv) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int r = r0 + i;
-            float sq = 0.f;
-            if (r < urows) {  // warp-uniform
-              const long long gi = (row0 + r) * D + col;
-              const float res = (__uint_as_float(v[i]) + __uint_as_float(w[i])) - xv[i];
-              const float gv = fp.g_scale * res;
-              fp.g_y[gi] = gv;
-              if (fp.g_y_lo != nullptr) fp.g_y_lo[gi] = tf32_lo(gv);
-              sq = res * res;
+            for (int c = 0; c < 4; ++c) {
+              const float4 r4 = make_float4((__uint_as_float(v[4 * c]) + __uint_as_float(w[4 * c])) - xv[c].x,
+                                            (__uint_as_float(v[4 * c + 1]) + __uint_as_float(w[4 * c + 1])) - xv[c].y,
+                                            (__uint_as_float(v[4 * c + 2]) + __uint_as_float(w[4 * c + 2])) - xv[c].z,
+                                            (__uint_as_float(v[4 * c + 3]) + __uint_as_float(w[4 * c + 3])) - xv[c].w);
+              const float4 gv = make_float4(fp.g_scale * r4.x, fp.g_scale * r4.y, fp.g_scale * r4.z, fp.g_scale * r4.w);
+              stg4(fp.g_y + gbase + c0 + 4 * c, gv);
+              if (fp.g_y_lo != nullptr) stg4(fp.g_y_lo + gbase + c0 + 4 * c, tf32_lo4f(gv));
+              sq += (r4.x * r4.x + r4.y * r4.y) + (r4.z * r4.z + r4.w * r4.w);
             }
-            sq = warp_sum(sq);
-            if (lane == 0) rec[r] = sq;
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive_u32(smem_u32(acc_empty));
+        float* const rec = s_recon + (ui & 1) * 256;
+        rec[i * 32 + lane] = sq;
         named_bar_sync(14, n_ep * 32);
-        if (warp == 0 && lane < urows) {
-          const float* all = s_recon + (ui & 1) * 256;
-          float s = all[lane];
-          for (int j = 1; j < n_ep; ++j) s += all[j * 32 + lane];
+        if (i == 0 && rv) {
+          float s = rec[lane];
+          for (int j = 1; j < n_ep; ++j) s += rec[j * 32 + lane];
           fp.recon[row0 + lane] = s;
         }
         if (tid == 0) stamp(fp, 601), stamp_all(fp, 707);
@@ -680,7 +687,7 @@ int fused_fwd_impl(const float* h, const float* log_r, const float* b_enc, const
   CUtensorMap mw, mwl;
   {
     const long long dims[2] = {K, D}, strides[1] = {K * 4};
-    const int box[2] = {32, 128}, estr[2] = {1, 1};
+    const int box[2] = {32, static_cast<int>(D)}, estr[2] = {1, 1};  // one plane of a k-block: {32 k, D rows}
     if (int rc = make_tensor_map(&mw, w_dec, 2, dims, strides, box, estr, 0)) return rc;
     if (int rc = make_tensor_map(&mwl, w_dec_lo, 2, dims, strides, box, estr, 0)) return rc;
   }

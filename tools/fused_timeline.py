@@ -42,7 +42,7 @@ def main():
     for _ in range(3):
         run()
     torch.cuda.synchronize()
-    ts[700::2] = 2 ** 62  # even words collect minima
+    ts[700:710:2] = 2 ** 62  # even words 700..708 collect minima
     lib.pvae_set_fused_timeline(ts.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -65,6 +65,10 @@ def main():
             print(f"  g{gi}: {us(t[b]):6.1f} {us(t[b + 1]):6.1f} {us(t[b + 2]):6.1f} {us(t[b + 3]):6.1f}")
     print(f"all CTAs: first start {us(t[700]):.1f}, last start {us(t[701]):.1f}, last batch end {us(t[703]):.1f}, "
           f"last accumulators complete {us(t[705]):.1f}, last epilogue done {us(t[707]):.1f}")
+    ends = sorted(us(v) for v in t[800:948] if v)
+    if ends:
+        print("per CTA, end of the sampler part (us): min %.1f  p25 %.1f  median %.1f  p75 %.1f  p90 %.1f  max %.1f" % (
+            ends[0], ends[len(ends) // 4], ends[len(ends) // 2], ends[3 * len(ends) // 4], ends[9 * len(ends) // 10], ends[-1]))
     print(f"accumulators complete {us(t[600]):.1f}, epilogue done {us(t[601]):.1f}")
 
 
