@@ -247,13 +247,13 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
     // stream - but only after the dgrad GEMM, the last reader of W_dec, has finished (an event; without it the update raced
     // with that GEMM: 2-rank parameters 5e-3 off the single-GPU ones).  Only bucket 1 (log_r, W_enc, b_enc) stays on the
     // critical path.
-    if (side) {
-      if ((rc = pvae::cuda_ok("dgrad event", cudaEventRecord(side->dgrad, s)))) return rc;
-      if ((rc = pvae::cuda_ok("dgrad event", cudaStreamWaitEvent(s2, side->dgrad, 0)))) return rc;
-    }
     if (fuse && (rc = pvae::adamax_from_partials_impl(nullptr, nullptr, d.grads, nullptr, nullptr, seg + 2, 1, 0.f, 1, 0.f, 0.f, 0.f, 0.f,
                                                       pvae::AdamaxDev{}, s2)))
       return rc;
+    if (side) {  // only the exchange (it writes W_dec) waits for the dgrad GEMM; the reduction of the wgrad partials does not
+      if ((rc = pvae::cuda_ok("dgrad event", cudaEventRecord(side->dgrad, s)))) return rc;
+      if ((rc = pvae::cuda_ok("dgrad event", cudaStreamWaitEvent(s2, side->dgrad, 0)))) return rc;
+    }
     const int64_t rs[1] = {K + K * D}, rl[1] = {D * K};
     if ((rc = pvae::peer_exchange_impl(d.params, planes ? d.params_lo : nullptr, d.exp_avg, d.exp_inf, rs, rl, 1, n, d.peer_grads, d.peer_flags,
                                        0, d.world, d.rank, d.token, d.loss3, nullptr, d.lr, d.step, d.beta1, d.beta2, d.eps, d.weight_decay,
