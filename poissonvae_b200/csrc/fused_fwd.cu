@@ -19,13 +19,15 @@
 //                            memory (z, its TF32 low plane, dz_acc - the backward needs them) AND into the 128-byte-swizzled
 //                            K-major operand tile of its k-block in shared memory (a ring of 8 k-block slots, released by the
 //                            tensor core as it consumes them); then the lane arrives on that k-block's mbarrier.
-//   warp 22      TMA         one thread streams W_dec tiles ({32 k, 128 rows} boxes, hi plane then lo plane) through a ring
-//   warp 21      MMA         one thread waits for a k-block of z and issues 3xTF32 tcgen05.mma for y^T = W_dec z^T: A = the W_dec tile
-//                            (M = 128 output columns), B = the z tile (N = 32 rows, no padding), accumulators hi / cross in
-//                            TMEM (lane = output column, column = row) - the tensor work hides under the sampler
-//   warps 0..7               epilogue of a unit: TMEM -> registers (a lane holds one output column of all rows, so every
-//                            global access is a coalesced 128-byte row segment), residual against x, g_y (+ low plane),
-//                            squared error per row
+//   warp 22      TMA         one thread streams W_dec through a 3-stage ring: one plane (hi, then lo) of one k-block with all
+//                            D rows ({32 k, D rows} box, 32 KB) per stage
+//   warp 21      MMA         one thread waits for a k-block of z and issues 3xTF32 tcgen05.mma for y = z W_dec^T: A = the z tile
+//                            (M = 128 of which the unit's <= 28 rows are live; the rows above alias whatever follows the 4 KB
+//                            tile in shared memory and their accumulator lanes are never read), B = the W_dec tile (N = D),
+//                            accumulators hi / cross in TMEM (lane = row) - twelve MMAs per k-block.  (A tcgen05.mma costs
+//                            ~0.09 us whatever its shape: the transposed product, N = 32 without padding, needed 24.)
+//   warps 0,4,8,12           epilogue of a unit (the warps that can read TMEM lanes 0..31): TMEM -> registers, residual
+//                            against x, g_y (+ low plane), squared error per row
 //
 // Full rows per CTA mean no split-K partials: y is complete in TMEM, so the reconstruction residual is fused too.
 // Per-chain arithmetic, Philox counters and exit rules are those of sampler.cu (sampler_device.cuh): a quad finished by
