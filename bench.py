@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--no_overlap", action="store_true", help="keep the whole step on one stream (A/B)")
     ap.add_argument("--tf32", action="store_true", help="single-pass TF32 GEMMs instead of 3xTF32 (A/B)")
     ap.add_argument("--dec_splits", type=int, default=-1, help="K-splits of the decoder GEMM (A/B; default: the library's choice)")
-    ap.add_argument("--pool", type=int, default=1, help="forward sampler schedule (A/B): 0 row by row, 1 per-row-tile pool, 2 one-wave pool")
+    ap.add_argument("--pool", type=int, default=3, help="forward sampler schedule (A/B): 0 row by row, 1 per-row-tile pool, 2 one-wave pool, 3 one wave where bit-identical to 1 (default)")
     ap.add_argument("--fused", action="store_true", help="the fused forward kernel (rsample + KL + decoder GEMM on z in shared memory "
                                                         "+ residual, one launch) instead of three kernels (A/B, measured slower; "
                                                         "see pvae_set_step_fused)")

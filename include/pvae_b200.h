@@ -496,12 +496,14 @@ int pvae_set_conv_variant(int v);
  * not depend on the launch geometry, but the float summation order of a chain depends on this value. */
 int pvae_set_phase_a_events(int n);
 int pvae_set_absorb_exit(int on);
-/* Tuning knob (process-wide, default on): forward sampler schedule.  1: every lane of a warp takes the next quad of the
- * warp's rows x 32 pool the moment its own chain ends (work-efficient under heavy-tailed chain lengths); 0: one row at a
- * time in lock step - bit-identical results; 2: one resident wave of blocks, every block pooling all quads of its rows
- * (sampler_pool_kernel; measured 39.2 vs 41.2 us at config 2).  Its long chains are walked again from their first event
- * by a lane group, so a chain that exceeds the phase-A cap may differ from schedules 0 / 1 in the last bits (~1e-6
- * relative) and its sum is no longer independent of where the chain exits: opt-in. */
+/* Tuning knob (process-wide): forward sampler schedule.  1: every lane of a warp takes the next quad of the block's rows x
+ * 128 pool the moment its own chain ends (work-efficient under heavy-tailed chain lengths); 0: one row at a time in lock
+ * step - bit-identical results; 2: one resident wave of blocks, every block pooling all quads of its rows
+ * (sampler_pool_kernel; 37.8 vs 41.7 us at config 2).  A chain that exceeds the phase-A cap is finished by a lane group:
+ * when the quad's three output slots exist (z, z_lo, dz_acc: the training forward with operand planes) its state is parked
+ * there and the chain continues exactly as in schedules 0 / 1 - bit-identical; otherwise the lane group walks it again from
+ * its first event, which may move the last bits (~1e-6 relative).  3 (default): schedule 2 where it is bit-identical to 1,
+ * schedule 1 elsewhere. */
 int pvae_set_pool(int on);
 /* Tuning knob (process-wide): rows (samples) per thread block of the sampler kernels, 1..4; 0 = automatic.
  * Changes pvae_num_partials(); results of the forward are unaffected. */

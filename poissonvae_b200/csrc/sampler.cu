@@ -675,6 +675,11 @@ __global__ void __launch_bounds__(kThreads) sampler_pool_kernel(const SamplerPar
     float* const z0 = p.z + row0 * p.K;
     float* const zlo0 = p.z_lo != nullptr ? p.z_lo + row0 * p.K : nullptr;
     float* const dz0 = MODE == kFwdBoth ? p.dz_out + row0 * p.K : nullptr;
+    // A long chain's state at the hand-over (arrival times, both running sums: 48 bytes per quad) is parked in the quad's own
+    // OUTPUT slots - z, z_lo, dz_acc, which nothing reads before the chain is complete - when all three exist (the training
+    // step with operand planes).  The lane group then continues the chain from event phase_a exactly as sampler_kernel's
+    // phase B does: bit-identical to schedules 0 / 1.  Without the three slots the chain is walked again from its first event.
+    const bool keep = MODE == kFwdBoth && zlo0 != nullptr;
     int n_parked = 0;  // warp-uniform
     // entry -> quad index relative to the tile's first quad (row r, column quad cq), or -1 for a column beyond K
     auto locate = [&](int e) -> int {
@@ -736,7 +741,12 @@ __global__ void __launch_bounds__(kThreads) sampler_pool_kernel(const SamplerPar
             stg4_planes(z0, zlo0, ebase, make_float4(acc[0], acc[1], acc[2], acc[3]));
             if (MODE == kFwdBoth) stg4(dz0 + ebase, make_float4(acc2[0], acc2[1], acc2[2], acc2[3]));
             fin = true;
-          } else if (n >= n_a) {  // a long chain: phase B walks it again, 8 events per step
+          } else if (n >= n_a) {  // a long chain: a lane group finishes it, 8 events per step
+            if (keep) {
+              stg4(z0 + ebase, make_float4(t[0], t[1], t[2], t[3]));
+              stg4(zlo0 + ebase, make_float4(acc[0], acc[1], acc[2], acc[3]));
+              stg4(dz0 + ebase, make_float4(acc2[0], acc2[1], acc2[2], acc2[3]));
+            }
             fin = park = true;
           }
         }
@@ -766,6 +776,7 @@ __global__ void __launch_bounds__(kThreads) sampler_pool_kernel(const SamplerPar
       uint32_t quad = 0;
       float rate[4] = {1.f, 1.f, 1.f, 1.f}, inv_rate[4] = {1.f, 1.f, 1.f, 1.f}, t0[4] = {0.f, 0.f, 0.f, 0.f};
       float part[4] = {0.f, 0.f, 0.f, 0.f}, part2[4] = {0.f, 0.f, 0.f, 0.f};
+      float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};  // the sums phase A handed over (zero when restarted)
       while (true) {
         if (__any_sync(0xffffffffu, done)) {
           float tot[4], tot2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -777,8 +788,8 @@ __global__ void __launch_bounds__(kThreads) sampler_pool_kernel(const SamplerPar
               v += __shfl_xor_sync(0xffffffffu, v, o, kGroup);
               if (MODE == kFwdBoth) v2 += __shfl_xor_sync(0xffffffffu, v2, o, kGroup);
             }
-            tot[j] = v;
-            if (MODE == kFwdBoth) tot2[j] = v2;
+            tot[j] = acc[j] + v;
+            if (MODE == kFwdBoth) tot2[j] = acc2[j] + v2;
           }
           if (done && gl == 0 && has) {
             stg4_planes(z0, zlo0, ebase, make_float4(tot[0], tot[1], tot[2], tot[3]));
@@ -802,9 +813,16 @@ __global__ void __launch_bounds__(kThreads) sampler_pool_kernel(const SamplerPar
               for (int j = 0; j < 4; ++j) {
                 rate[j] = s_rate[j][slot];
                 inv_rate[j] = recip_for_div(rate[j]);
-                t0[j] = 0.f, part[j] = 0.f, part2[j] = 0.f;
+                t0[j] = 0.f, part[j] = 0.f, part2[j] = 0.f, acc[j] = 0.f, acc2[j] = 0.f;
               }
               n0 = 0;
+              if (keep) {  // continue where the single lane stopped (coherent loads: this kernel wrote them)
+                const float4 tv = ld4(z0 + ebase), av = ld4(zlo0 + ebase), a2 = ld4(dz0 + ebase);
+                t0[0] = tv.x, t0[1] = tv.y, t0[2] = tv.z, t0[3] = tv.w;
+                acc[0] = av.x, acc[1] = av.y, acc[2] = av.z, acc[3] = av.w;
+                acc2[0] = a2.x, acc2[1] = a2.y, acc2[2] = a2.z, acc2[3] = a2.w;
+                n0 = n_a;
+              }
             }
             done = false;
           }
@@ -828,12 +846,11 @@ __global__ void __launch_bounds__(kThreads) sampler_pool_kernel(const SamplerPar
           soft_term<IND, MODE == kFwdBoth>(p, t, f, df);
           const float g = df * t;
           part[j] += valid ? f : 0.f;
-          // the group's last lane holds the smallest term of the step, its first lane the largest partial sum (a lower
-          // bound of the chain's running total)
-          excess = fmaxf(excess, fmaf(-absorb, __shfl_sync(0xffffffffu, part[j], 0, kGroup), f));
+          // the group's last lane holds the smallest term of the step; its own sums bound the totals from below
+          excess = fmaxf(excess, fmaf(-absorb, acc[j] + part[j], f));
           if (MODE == kFwdBoth) {
             part2[j] += valid ? g : 0.f;
-            excess = fmaxf(excess, fmaf(-absorb, __shfl_sync(0xffffffffu, part2[j], 0, kGroup), g));
+            excess = fmaxf(excess, fmaf(-absorb, acc2[j] + part2[j], g));
           }
           t0[j] = __shfl_sync(0xffffffffu, t, kGroup - 1, kGroup);
         }
@@ -1126,6 +1143,7 @@ static int rows_per_block_for(long long B) {
 }
 
 static int g_one_wave = 0;  // forward modes: 1 = the one-wave schedule (sampler_pool_kernel, pvae_set_pool(2)); 0 = the per-row-tile pool of sampler_kernel
+static int g_pool_auto = 1;  // default (pvae_set_pool(3)): one wave where it is bit-identical to the tile pool (training forward with operand planes)
 
 // One resident wave: occupancy x SM count blocks (queried once per kernel), rows dealt out evenly in the kernel, tiles
 // of as many rows as fit the pool.
@@ -1154,7 +1172,8 @@ static cudaError_t launch_pool(Kern kern, SamplerParams p, cudaStream_t s) {
 
 template <int MODE, bool RAW>
 static cudaError_t launch_ind(const SamplerParams& p, int indicator, dim3 grid, cudaStream_t s) {
-  if ((MODE == kFwdSoft || MODE == kFwdBoth) && p.pool && g_one_wave && p.K / 4 <= kPoolCap && p.K / 4 > 0 &&
+  const bool auto_wave = g_pool_auto && MODE == kFwdBoth && p.z_lo != nullptr && p.c_ddr == nullptr;
+  if ((MODE == kFwdSoft || MODE == kFwdBoth) && p.pool && (g_one_wave || auto_wave) && p.K / 4 <= kPoolCap && p.K / 4 > 0 &&
       kPoolRows / static_cast<int>((p.K / 4 + kThreads - 1) / kThreads) >= 1) {  // one-wave pool (forward modes)
     constexpr int M = (MODE == kFwdSoft || MODE == kFwdBoth) ? MODE : kFwdSoft;
     switch (indicator) {
@@ -1246,10 +1265,11 @@ extern "C" int64_t pvae_num_partials(int64_t B) {
   return (B + r - 1) / r;
 }
 
-extern "C" int pvae_set_pool(int on) {  // 0: row-by-row lock step; 1: work pool (default); 2: work pool + one-wave grid
-  if (on < 0 || on > 2) return fail(PVAE_ERR_INVALID, "pvae_set_pool: %d not in [0, 2]", on);
+extern "C" int pvae_set_pool(int on) {  // 0: row-by-row lock step; 1: tile pool; 2: one-wave pool; 3 (default): one wave where bit-identical to 1
+  if (on < 0 || on > 3) return fail(PVAE_ERR_INVALID, "pvae_set_pool: %d not in [0, 3]", on);
   g_pool = on != 0;
   g_one_wave = on == 2;
+  g_pool_auto = on == 3;
   return PVAE_OK;
 }
 

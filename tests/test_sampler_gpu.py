@@ -421,5 +421,5 @@ def test_work_pool_schedule_is_bit_identical(lib, K):
                         a, b = outs[2][k].cpu().numpy(), outs[1][k].cpu().numpy()
                         assert_rel(a, b, rtol=2e-6, what=f"{k} one-wave vs tile pool, cap {cap}")
     finally:
-        lib.pvae_set_pool(1)
+        lib.pvae_set_pool(3)  # the default
         lib.pvae_set_phase_a_events(8)

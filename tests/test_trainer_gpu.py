@@ -424,3 +424,37 @@ def test_iteration_statistics_match_a_synchronous_replay(clip):
             assert abs(got['train/grad_norm'] - w['gn']) <= 1e-5 * w['gn']
         assert got['coeffs/n_exp'] > 0 and got['coeffs/beta'] > 0
     assert torch.equal(tr.flat_p, tr2.flat_p)  # the ring did not change the training itself
+
+
+def test_one_wave_sampler_schedule_is_bit_identical_in_the_step():
+    """pvae_set_pool(3), the default: the training forward with operand planes runs the one-wave schedule, parking the state of
+    long chains in the quad's own output slots (z, z_lo, dz_acc) so that lane groups continue them exactly as the tile-pool
+    schedule does.  Rates high enough that many chains are handed over; several phase-A caps; losses, gradients and updated
+    parameters equal those of schedule 1 bit for bit."""
+    from poissonvae_b200 import _lib
+    from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
+    from poissonvae_b200.vae import ConfigPoisVAE, PoissonVAE
+    lib = _lib.load()
+    data = torch.randn(3, 2048, 256, generator=torch.Generator().manual_seed(31)).cuda()
+    try:
+        for cap, temp in ((8, 0.3), (3, 1.0)):
+            lib.pvae_set_phase_a_events(cap)
+            out = {}
+            for pool in (1, 3):
+                lib.pvae_set_pool(pool)
+                model = PoissonVAE(ConfigPoisVAE(n_latents=512, prior_clamp=-4, seed=6)).cuda()
+                with torch.no_grad():
+                    model.log_rate.add_(4.5)  # rates up to tens of events per chain
+                model.update_n(60.0)
+                tr = TrainerVAE(model, ConfigTrainVAE(lr=0.01, epochs=40, batch_size=2048, temp_anneal_portion=0.0, temp_stop=temp,
+                                                      kl_anneal_portion=0.0, kl_const_portion=0.0, grad_clip=None),
+                                n_batches_per_epoch=1)
+                assert tr.planes
+                torch.cuda.manual_seed(8)
+                losses = [tr.train_step(data[i], i).clone() for i in range(3)]
+                out[pool] = (torch.stack(losses), tr.flat_g.clone(), tr.flat_p.clone())
+            for name, a, b in zip(("losses", "gradient", "parameters"), out[1], out[3]):
+                assert torch.equal(a, b), (name, cap, temp)
+    finally:
+        lib.pvae_set_pool(3)
+        lib.pvae_set_phase_a_events(8)

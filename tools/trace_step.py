@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--coef", action="store_true")
     ap.add_argument("--fused", action="store_true", help="fused forward kernel (sampler + decoder GEMM + residual in one launch)")
     ap.add_argument("--fused_debug", type=int, default=0)
-    ap.add_argument("--pool", type=int, default=1, help="forward sampler schedule: 0 row by row, 1 per-row-tile pool, 2 one-wave pool")
+    ap.add_argument("--pool", type=int, default=3, help="forward sampler schedule: 0 row by row, 1 per-row-tile pool, 2 one-wave pool, 3 one wave where bit-identical to 1 (default)")
     a = ap.parse_args()
     from poissonvae_b200 import _lib, linear
     from poissonvae_b200.trainer import ConfigTrainVAE, TrainerVAE
