@@ -505,6 +505,8 @@ int pvae_set_absorb_exit(int on);
  * its first event, which may move the last bits (~1e-6 relative).  3 (default): schedule 2 where it is bit-identical to 1,
  * schedule 1 elsewhere. */
 int pvae_set_pool(int on);
+/* Tuning knob (A/B): grid of the one-wave schedule as a multiple of the resident wave (default 1). */
+int pvae_set_wave_factor(float f);
 /* Tuning knob (process-wide): rows (samples) per thread block of the sampler kernels, 1..4; 0 = automatic.
  * Changes pvae_num_partials(); results of the forward are unaffected. */
 int pvae_set_rows_per_block(int n);

@@ -170,6 +170,7 @@ _SIGNATURES = {
     "pvae_set_phase_a_events": (_i, [_i]),
     "pvae_set_absorb_exit": (_i, [_i]),
     "pvae_set_pool": (_i, [_i]),
+    "pvae_set_wave_factor": (_i, [_f]),
     "pvae_set_rows_per_block": (_i, [_i]),
     "pvae_debug_log_check": (_i, [_p, _p]),
     "pvae_debug_draws": (_i, [_p, _p, _i64, _i64, _i64, _i, _u64, _u64, _p, _p]),

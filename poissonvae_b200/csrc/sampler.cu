@@ -1177,12 +1177,14 @@ static int rows_per_block_for(long long B) {
 }
 
 static int g_one_wave = 0;  // forward modes: 1 = the one-wave schedule (sampler_pool_kernel, pvae_set_pool(2)); 0 = the per-row-tile pool of sampler_kernel
+float g_wave_factor = 1.f;  // blocks of the one-wave schedule as a multiple of the resident wave (pvae_set_wave_factor, A/B)
 static int g_pool_auto = 1;  // default (pvae_set_pool(3)): one wave where it is bit-identical to the tile pool (training forward with operand planes)
 
 // One resident wave: occupancy x SM count blocks (queried once per kernel), rows dealt out evenly in the kernel, tiles
 // of as many rows as fit the pool.
 template <typename Kern>
 static cudaError_t launch_one_wave(Kern kern, SamplerParams p, cudaStream_t s) {
+  extern float g_wave_factor;
   static int resident = 0;  // one copy per kernel instantiation
   if (resident == 0) {
     int per_sm = 0, dev = 0, sms = 0;
@@ -1191,7 +1193,7 @@ static cudaError_t launch_one_wave(Kern kern, SamplerParams p, cudaStream_t s) {
       per_sm = 6, sms = 148;
     resident = per_sm * sms;
   }
-  const long long grid = std::min<long long>(resident, p.B);
+  const long long grid = std::max<long long>(1, std::min<long long>(static_cast<long long>(resident * g_wave_factor + 0.5f), p.B));
   const int npass = static_cast<int>((p.K / 4 + kThreads - 1) / kThreads);
   const long long rows_block = (p.B + grid - 1) / grid;
   p.rows_per_block = static_cast<int>(std::min<long long>(kPoolRows / npass, rows_block));
@@ -1304,6 +1306,12 @@ extern "C" int pvae_set_pool(int on) {  // 0: row-by-row lock step; 1: tile pool
   g_pool = on != 0;
   g_one_wave = on == 2;
   g_pool_auto = on == 3;
+  return PVAE_OK;
+}
+
+extern "C" int pvae_set_wave_factor(float f) {
+  if (!(f > 0.f) || f > 16.f) return fail(PVAE_ERR_INVALID, "pvae_set_wave_factor: %g not in (0, 16]", f);
+  g_wave_factor = f;
   return PVAE_OK;
 }
 

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--coef", action="store_true")
     ap.add_argument("--fused", action="store_true", help="fused forward kernel (sampler + decoder GEMM + residual in one launch)")
     ap.add_argument("--fused_debug", type=int, default=0)
+    ap.add_argument("--wave", type=float, default=1.0, help="grid of the one-wave sampler schedule / resident wave")
     ap.add_argument("--pool", type=int, default=3, help="forward sampler schedule: 0 row by row, 1 per-row-tile pool, 2 one-wave pool, 3 one wave where bit-identical to 1 (default)")
     a = ap.parse_args()
     from poissonvae_b200 import _lib, linear
@@ -46,6 +47,7 @@ def main():
     lib.pvae_set_step_coef(1 if a.coef else 0)
     lib.pvae_set_step_fused(1 if a.fused else 0)
     lib.pvae_set_fused_debug(a.fused_debug)
+    lib.pvae_set_wave_factor(a.wave)
     B, K = a.batch, a.latents
     model = PoissonVAE(ConfigPoisVAE(n_latents=K, prior_clamp=-4, seed=0)).cuda()
     model.n_exp.fill_(263)
