@@ -148,7 +148,8 @@ def test_hard_counts_bit_exact(lib, golden_dir, exit_logit):
     # (c) the fixture the unmodified reference produced on CPU (double running sum there): the counts
     # may differ only where an arrival lands within an ulp of t = 1
     diff = counts.cpu().numpy() != g["counts"]
-    assert diff.mean() < 0.01
+    print(f"hard counts vs the unmodified reference's CPU fixture: {int(diff.sum())} of {diff.size} entries differ")
+    assert diff.sum() <= 1  # measured: 0 (an fp32 running sum and torch-CPU's double one disagree only within an ulp of t = 1)
 
 
 @pytest.mark.parametrize("kind", list(IND))
