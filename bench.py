@@ -465,7 +465,7 @@ def run_ours(args):
                      "implementation_extra_bytes_per_latent": impl_extra,
                      "sampler_fwd_is": ("fused_fwd_kernel: rsample + KL + decoder GEMM + residual (also moves x, g_y: "
                                         f"{8 * B * 256} B and W_dec: {4 * 256 * K} B per launch, not credited)") if fused_fwd
-                                       else "sampler_kernel (stand-alone)",
+                                       else "sampler_pool_kernel (one-wave schedule, pool 2 / 3) or sampler_kernel (pool 0 / 1): the stand-alone forward sampler",
                      "kernel_us": {k: round(v, 2) for k, v in ktimes.items()},
                      "kernels": {k: {"achieved": round(v, 1), "frac": round(v / peak, 4)} for k, v in gbs.items()},
                      "sampler_fwd_plus_bwd": {"achieved": round(B * K * 20 / ((ktimes["sampler_fwd"] + ktimes["sampler_bwd"]) * 1e-6) / 1e9, 1),
