@@ -437,12 +437,12 @@ def test_one_wave_sampler_schedule_is_bit_identical_in_the_step():
     lib = _lib.load()
     data = torch.randn(3, 2048, 256, generator=torch.Generator().manual_seed(31)).cuda()
     try:
-        for cap, temp in ((8, 0.3), (3, 1.0)):
+        for cap, temp, K in ((8, 0.3, 512), (3, 1.0, 512), (8, 0.5, 1024), (5, 1.0, 520)):  # K = 1024: two column passes; 520: ragged
             lib.pvae_set_phase_a_events(cap)
             out = {}
             for pool in (1, 3):
                 lib.pvae_set_pool(pool)
-                model = PoissonVAE(ConfigPoisVAE(n_latents=512, prior_clamp=-4, seed=6)).cuda()
+                model = PoissonVAE(ConfigPoisVAE(n_latents=K, prior_clamp=-4, seed=6)).cuda()
                 with torch.no_grad():
                     model.log_rate.add_(4.5)  # rates up to tens of events per chain
                 model.update_n(60.0)
@@ -454,7 +454,7 @@ def test_one_wave_sampler_schedule_is_bit_identical_in_the_step():
                 losses = [tr.train_step(data[i], i).clone() for i in range(3)]
                 out[pool] = (torch.stack(losses), tr.flat_g.clone(), tr.flat_p.clone())
             for name, a, b in zip(("losses", "gradient", "parameters"), out[1], out[3]):
-                assert torch.equal(a, b), (name, cap, temp)
+                assert torch.equal(a, b), (name, cap, temp, K)
     finally:
         lib.pvae_set_pool(3)
         lib.pvae_set_phase_a_events(8)
