@@ -476,6 +476,13 @@ def run_ours(args):
                      "timed": f"CUDA events on the launch stream around each sampler launch, mean over {K_steps} steps "
                               "run right after the timed regions"},
     }
+    if ktimes.get("exchange"):
+        # the exchange bucket that stays on the critical path (log_r, W_enc, b_enc): flag barrier + one-shot pull of every
+        # peer's slice + Adamax, timed with events on the launch stream; NVLink bytes = what this rank reads from its peers
+        nbytes = 4 * (K + K * 256) * (world - 1)
+        line["exchange_us"] = round(ktimes["exchange"], 2)
+        line["exchange"] = {"kernel": "allreduce_adamax_kernel (bucket 1 of 2; bucket 0 = W_dec runs on the side stream under the backward)",
+                            "peer_bytes_per_rank": nbytes, "nvlink_gbs_per_rank": round(nbytes / (ktimes["exchange"] * 1e-6) / 1e9, 1)}
     if dp_check is not None:
         line["dp_check"] = dp_check
     ref_bytes = 4.0 * args.n_exp * B * K  # one materialised (n_exp, B, K) fp32 tensor of the reference path

@@ -243,7 +243,8 @@ int pvae_allreduce_adamax(float* p, float* exp_avg, float* exp_inf, int64_t n, i
  *   grads is overwritten with d loss / d params where loss = mean over the GLOBAL batch (sum the buffers of all
  *   ranks to get the global gradient); loss3 = this rank's share of [loss, mse, kl] (sum over ranks);
  *   ws: pvae_lin_step_ws_floats(B, K, D) floats of scratch; rate_max: optional running max of the rates;
- *   precise: GEMM mode (see pvae_gemm_tf32); events: NULL or 4 cudaEvent_t recorded before/after the sampler
+ *   precise: GEMM mode (see pvae_gemm_tf32); events: NULL or 4 cudaEvent_t (6 with pvae_lin_step's update = 2: entries 4 / 5
+ *   bracket the exchange bucket that stays on the critical path) recorded before/after the sampler
  *   forward (0,1) and before/after the sampler backward (2,3) - used by bench.py for the roofline timing. */
 int64_t pvae_lin_step_ws_floats(int64_t B, int64_t K, int64_t D);
 /* Offsets (in floats from the start of ws) of the step's intermediates, for parity tests that read them back after a step:

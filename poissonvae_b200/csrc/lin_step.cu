@@ -284,10 +284,12 @@ static int lin_step_core(const pvae_lin_step_desc& d, void* stream) {
         return rc;
     }
     const int64_t rs[2] = {0, K + 2 * K * D}, rl[2] = {K + K * D, K};
+    mark(4);  // update == 2: the descriptor's `events` has six entries; 4 / 5 bracket the exchange bucket on the critical path
     if ((rc = pvae::peer_exchange_impl(d.params, planes ? d.params_lo : nullptr, d.exp_avg, d.exp_inf, rs, rl, has_bias ? 2 : 1, -1,
                                        d.peer_grads, d.peer_flags, 1, d.world, d.rank, d.token, nullptr, nullptr, d.lr, d.step, d.beta1,
                                        d.beta2, d.eps, d.weight_decay, s)))
       return rc;
+    mark(5);
     if (side && (rc = pvae::cuda_ok("join", cudaStreamWaitEvent(s, side->join, 0)))) return rc;
     return PVAE_OK;
   }

@@ -415,12 +415,15 @@ class TrainerVAE:
         chk = _lib.check
         events = None
         if self.kernel_events is not None:  # CUDA events around the two sampler launches (bench.py roofline)
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            n_ev = 6 if self.peer is not None else 4  # peer exchange: 4 / 5 bracket the bucket on the critical path
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
             for e in evs:
                 e.record()  # materialises the cudaEvent_t; the library re-records it at the right place
-            events = (ctypes.c_void_p * 4)(*[e.cuda_event for e in evs])
+            events = (ctypes.c_void_p * n_ev)(*[e.cuda_event for e in evs])
             self.kernel_events.setdefault('sampler_fwd', []).append((evs[0], evs[1]))
             self.kernel_events.setdefault('sampler_bwd', []).append((evs[2], evs[3]))
+            if n_ev == 6:
+                self.kernel_events.setdefault('exchange', []).append((evs[4], evs[5]))
         # one C call per step (csrc/lin_step.cu): forward + loss + backward and, single GPU without clipping or over
         # peer memory, the optimiser too.  The descriptor is kept from step to step; only what changes is rewritten.
         d = self._desc(B, Bg, row_offset, K, D)
