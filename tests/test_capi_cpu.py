@@ -79,3 +79,37 @@ def test_no_cpu_fallback():
     from poissonvae_b200 import Poisson
     with pytest.raises(RuntimeError):
         Poisson(torch.zeros(4, 8), temp=1.0).rsample()
+
+
+def test_host_only_shape_helpers(lib_path):
+    """Workspace sizes and shape predicates are host functions: callable without a GPU."""
+    from poissonvae_b200 import _lib
+    lib = _lib.load()
+    # fused forward kernel: K a multiple of 256 up to 1024, D in {128, 256}, at least 12 rows per SM (148 SMs assumed without a device)
+    assert lib.pvae_fused_fwd_supported(4096, 512, 256) == 1
+    assert lib.pvae_fused_fwd_supported(8192, 1024, 256) == 1
+    assert lib.pvae_fused_fwd_supported(2000, 256, 128) == 1
+    assert lib.pvae_fused_fwd_supported(1024, 512, 256) == 0  # 7 rows per SM: the pools would be too shallow
+    assert lib.pvae_fused_fwd_supported(4096, 520, 256) == 0
+    assert lib.pvae_fused_fwd_supported(4096, 2048, 256) == 0
+    assert lib.pvae_fused_fwd_supported(4096, 512, 64) == 0
+    assert lib.pvae_kl_diag_ws_floats(4096, 512) == 128 * 512 and lib.pvae_kl_diag_ws_floats(0, 512) == 0
+    assert lib.pvae_gemm_residual_parts(256) == 8  # two column halves per 64-wide tile
+    assert lib.pvae_lin_step_ws_floats(4096, 512, 256) > 3 * 4096 * 512
+    # knobs validate their argument
+    assert lib.pvae_set_pool(7) != 0 and b"pvae_set_pool" in lib.pvae_last_error()
+    assert lib.pvae_set_pool(3) == 0
+    assert lib.pvae_set_wave_factor(0.0) != 0 and lib.pvae_set_wave_factor(1.0) == 0
+
+
+def test_average_meter_and_log_freq_config():
+    """Host pieces of the statistics path (base/utils_model.py AverageMeter; cfg.log_freq, main/config_vae.py:311)."""
+    from poissonvae_b200.trainer import ConfigTrainVAE, _AverageMeter
+    m = _AverageMeter()
+    for v in (1.0, 2.0, 6.0):
+        m.update(v)
+    assert m.avg == 3.0 and m.cnt == 3
+    m.reset()
+    m.update(5.0, n=2)
+    assert m.avg == 5.0 and m.sum == 10.0
+    assert ConfigTrainVAE().log_freq == 10 and ConfigTrainVAE(log_freq=3).log_freq == 3
